@@ -1,0 +1,68 @@
+// extern "C" ABI of libb200clip.so — thin argument checking + dispatch to the kernel launchers.
+#include "../../include/b200clip.h"
+#include "common.cuh"
+#include "host_api.h"
+
+using namespace b2;
+using namespace b2host;
+
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int b200clip_abi_version(void) { return B200CLIP_ABI_VERSION; }
+
+const char* b200clip_strerror(int code) {
+  switch (code) {
+    case B2_OK: return "ok";
+    case B2_EINVAL: return "invalid argument (shape, alignment or null pointer)";
+    case B2_ENOSYS: return "driver entry point cuTensorMapEncodeTiled unavailable";
+    case B2_ECUDA: return "CUDA launch error (is this an sm_100a device?)";
+    case B2_ENOMEM: return "workspace too small";
+    default: return "unknown b200clip error";
+  }
+}
+
+int b200clip_sm_count(void) { return sm_count(); }
+
+int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim, void* operand, int ld_out, int Kp,
+                        int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, void* stream) {
+  if (!x || !operand) return B2_EINVAL;
+  if (ld_out < (split3_role >= 0 ? 3 * Kp : Kp)) return B2_EINVAL;
+  return l2norm_fwd(x, dtype, (long)ldx, rows, dim, operand, ld_out, Kp, split3_role, inv_norm, xhat_f32, ld_hat,
+                    S(stream));
+}
+
+int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* xhat_bf16, int ldx, const float* xhat_f32, int ldxf,
+                        const void* other_bf16, int ld_other, const float* usum, const float* inv_norm, float gscale,
+                        float ocoef, float ucoef, int rows, int other_rows, int dim, float* dx, int64_t lddx,
+                        void* stream) {
+  if (!dxhat || !(xhat_bf16 || xhat_f32) || !inv_norm || !dx) return B2_EINVAL;
+  return l2norm_bwd(dxhat, ldg, xhat_bf16, ldx, xhat_f32, ldxf, other_bf16, ld_other, usum, inv_norm, gscale, ocoef,
+                    ucoef, rows, other_rows, dim, dx, (long)lddx, S(stream));
+}
+
+int b200clip_colsum_bf16(const void* operand, int ld, int rows, int dim, float* out, void* stream) {
+  if (!operand || !out) return B2_EINVAL;
+  return colsum_bf16(operand, ld, rows, dim, out, S(stream));
+}
+
+int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const int64_t* idx, int rows, int b_rows,
+                         int K, float* out, void* stream) {
+  if (!a || !b || !out) return B2_EINVAL;
+  return rowdot_bf16(a, lda, b, ldb, reinterpret_cast<const long long*>(idx), rows, b_rows, K, out, S(stream));
+}
+
+int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
+                            float shift2, int gated, float* rowsum, float* colsum, void* stream) {
+  if (!A || !B || !rowsum || !colsum) return B2_EINVAL;
+  return logits_lse_fwd(A, B, Ma, Nb, Kp, lda, ldb, scale2, shift2, gated, rowsum, colsum, S(stream));
+}
+
+int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
+                         int max_ctas, void* stream) {
+  if (!A || !B || !out) return B2_EINVAL;
+  return logits_dump(A, B, Ma, Nb, Kp, lda, ldb, out, ldo, max_ctas, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+// Internal C++ host entry points (one per kernel family); abi.cu wraps them in the extern "C" ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2host {
+
+// l2norm.cu
+int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out, int ldo, int Kp, int split3_role,
+               float* inv_norm, float* xhat_f32, int ldh, cudaStream_t s);
+int l2norm_bwd(const float* dxh, int ldg, const void* xh, int ldx, const float* xh_f32, int ldxf, const void* oth,
+               int ldoth, const float* usum, const float* inv_norm, float gscale, float ocoef, float ucoef, int rows,
+               int oth_rows, int dim, float* dx, long lddx, cudaStream_t s);
+int colsum_bf16(const void* xh, int ld, int rows, int dim, float* out, cudaStream_t s);
+int rowdot_bf16(const void* a, int lda, const void* b, int ldb, const long long* idx, int rows, int b_rows, int K,
+                float* out, cudaStream_t s);
+
+// logits_fwd.cu
+int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
+                   float shift2, int gated, float* rowsum, float* colsum, cudaStream_t stream);
+int logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
+                int max_ctas, cudaStream_t stream);
+
+int sm_count();
+
+}  // namespace b2host

@@ -1,0 +1,164 @@
+// K2: fused logits forward for the softmax (CLIP / legacy gated) losses.
+//   S = A B^T on tcgen05 tiles; epilogue computes P = 2^(f(S)*scale2 - shift2) once per element and
+//   accumulates BOTH the row sums (over columns) and the column sums (over rows). The N x N matrix never
+//   leaves TMEM / registers. Reference math: utils/loss/contrastive.py:146-162 (CLIPLoss),
+//   utils/loss/losses.py:190-210 (gated SiglipLoss: f(s) = s*sigmoid(s)).
+//
+//   Column sums: each epilogue thread owns one A row (TMEM lane) and 128 columns; it keeps 128 fp32
+//   column accumulators in registers across the whole sweep over A tiles of one 256-column B block and
+//   reduces them across lanes only when the block changes (warp shuffles + one atomicAdd per column per
+//   warp). Row sums: one atomicAdd per thread per tile.
+#include "tile_engine.cuh"
+
+namespace b2 {
+
+struct LseParams {
+  float scale2;    // log2(e) / tau
+  float shift2;    // subtract after scaling (keeps 2^x inside fp32 range)
+  float* rowsum;   // [Ma] += sum_j P_ij
+  float* colsum;   // [Nb] += sum_i P_ij
+  int gated;       // 1: f(s) = s * sigmoid(s) (legacy "siglip" gating), 0: f(s) = s
+};
+
+template <bool kGated>
+struct LseEpi {
+  using Params = LseParams;
+  struct State {
+    float colacc[4][32];
+    float rowacc;
+  };
+  __device__ static __forceinline__ void init(State& st, const Params&) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int e = 0; e < 32; ++e) st.colacc[c][e] = 0.f;
+    st.rowacc = 0.f;
+  }
+  __device__ static __forceinline__ void begin_outer(State&, const Params&, int, const TeCtx&) {}
+  __device__ static __forceinline__ float prob(float s, const Params& p) {
+    if (kGated) {
+      // s * sigmoid(s) = s / (1 + 2^(-s*log2e))
+      const float e = ex2_approx(-1.4426950408889634f * s);
+      s = __fdividef(s, 1.f + e);
+    }
+    return ex2_approx(fmaf(s, p.scale2, -p.shift2));
+  }
+  __device__ static __forceinline__ void chunk(State& st, const Params& p, const TeCtx& ctx, int c,
+                                               const uint32_t (&acc)[32]) {
+    if (ctx.full) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float v = prob(__uint_as_float(acc[e]), p);
+        st.rowacc += v;
+        st.colacc[c][e] += v;
+      }
+    } else {
+      const int cbase = ctx.col0 + c * 32;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        float v = prob(__uint_as_float(acc[e]), p);
+        v = (ctx.row_ok && (cbase + e) < ctx.Nb) ? v : 0.f;
+        st.rowacc += v;
+        st.colacc[c][e] += v;
+      }
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State& st, const Params& p, const TeCtx& ctx) {
+    if (ctx.row_ok) atomicAdd(p.rowsum + ctx.row, st.rowacc);
+    st.rowacc = 0.f;
+  }
+  __device__ static __forceinline__ void end_outer(State& st, const Params& p, int outer, const TeCtx& ctx) {
+    // cross-lane reduce of the 128 per-thread column accumulators; lane e keeps column c*32+e
+    const int lane = threadIdx.x & 31;
+    const int cb = outer * TE_BN + ctx.wg * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float mine = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float s = warp_sum(st.colacc[c][e]);
+        if (lane == e) mine = s;
+        st.colacc[c][e] = 0.f;
+      }
+      const int col = cb + c * 32 + lane;
+      if (col < ctx.Nb) atomicAdd(p.colsum + col, mine);
+    }
+  }
+};
+
+// Debug / validation epilogue: dumps the raw fp32 S tile to global memory (only used by the self test).
+struct DumpParams {
+  float* out;
+  int ld;
+  int Ma;
+};
+struct DumpEpi {
+  using Params = DumpParams;
+  struct State {};
+  __device__ static __forceinline__ void init(State&, const Params&) {}
+  __device__ static __forceinline__ void begin_outer(State&, const Params&, int, const TeCtx&) {}
+  __device__ static __forceinline__ void chunk(State&, const Params& p, const TeCtx& ctx, int c,
+                                               const uint32_t (&acc)[32]) {
+    if (!ctx.row_ok) return;
+    const int cbase = ctx.col0 + c * 32;
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (cbase + e < ctx.Nb) p.out[(size_t)ctx.row * p.ld + cbase + e] = __uint_as_float(acc[e]);
+  }
+  __device__ static __forceinline__ void end_tile(State&, const Params&, const TeCtx&) {}
+  __device__ static __forceinline__ void end_outer(State&, const Params&, int, const TeCtx&) {}
+};
+
+}  // namespace b2
+
+namespace b2host {
+using namespace b2;
+
+static int make_shape(TeShape& g, int Ma, int Nb, int Kp) {
+  if (Ma <= 0 || Nb <= 0 || Kp <= 0 || (Kp % TE_BK) != 0) return B2_EINVAL;
+  g.Ma = Ma;
+  g.Nb = Nb;
+  g.Kp = Kp;
+  g.m_tiles = (Ma + TE_BM - 1) / TE_BM;
+  g.n_blocks = (Nb + TE_BN - 1) / TE_BN;
+  return B2_OK;
+}
+
+template <class Epi, bool kOuterIsB>
+static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb,
+                     const typename Epi::Params& ep, int max_ctas, cudaStream_t stream) {
+  TeShape g;
+  int rc = make_shape(g, Ma, Nb, Kp);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, TE_BN))) return rc;
+  auto kern = te_kernel<Epi, kOuterIsB>;
+  static bool attr_done = false;   // per template instantiation
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
+      return B2_ECUDA;
+    attr_done = true;
+  }
+  long long total = (long long)g.m_tiles * g.n_blocks;
+  int grid = sm_count();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (total < grid) grid = (int)total;
+  kern<<<grid, TE_THREADS, TE_SMEM_BYTES, stream>>>(tmA, tmB, g, ep);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
+                   float shift2, int gated, float* rowsum, float* colsum, cudaStream_t stream) {
+  LseParams p{scale2, shift2, rowsum, colsum, gated};
+  if (gated) return launch_te<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
+  return launch_te<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
+}
+
+int logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
+                int max_ctas, cudaStream_t stream) {
+  DumpParams p{out, ldo, Ma};
+  return launch_te<DumpEpi, true>(A, B, Ma, Nb, Kp, lda, ldb, p, max_ctas, stream);
+}
+
+}  // namespace b2host

@@ -1,0 +1,82 @@
+/*
+ * b200clip — C ABI of the B200-native contrastive head (libb200clip.so).
+ *
+ * Drop-in boundary for the ONE hot path of HeartWise-AI/DeepCORO_CLIP named in BASELINE.json:
+ * the CLIP / SigLIP losses (utils/loss), the streaming retrieval metrics
+ * (utils/retrieval_metrics_streaming.py), Rope3D (models/rope_3d.py), AttentionPool
+ * (models/attention_pool.py) and the multi-view query pool (models/video_aggregator.py:131-158).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *  - `stream` is a cudaStream_t passed as void*. No entry point synchronises, allocates or touches host
+ *    memory; the caller owns every buffer (workspace sizes are documented per call).
+ *  - Return value: 0 on success, negative errno-style code otherwise (b200clip_strerror()).
+ *  - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16.
+ *  - "operand" buffers are the bf16 L2-normalised MMA operands produced by b200clip_l2norm_fwd():
+ *    row-major [rows, ld] with the first Kp (= dim rounded up to 64) columns valid and zero padded; in
+ *    bf16x3 mode three such panels are K-concatenated (ld >= 3*Kp).
+ *
+ * There is no CPU fallback anywhere behind this header: on a machine without an sm_100a GPU the calls
+ * fail with a CUDA error code.
+ */
+#ifndef B200CLIP_H_
+#define B200CLIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CLIP_ABI_VERSION 1
+
+int b200clip_abi_version(void);
+const char* b200clip_strerror(int code);
+/* Number of SMs of the current device (grid sizing / tests). */
+int b200clip_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  L2 normalise + operand packing.   Replaces F.normalize(x.float(), dim=-1)
+ *     (reference utils/loss/contrastive.py:146-147, 259-260; utils/loss/losses.py:46-47, 138-139, 191-192;
+ *      utils/retrieval_metrics_streaming.py:130-131).
+ *   x [rows, dim] (row pitch ldx elements, dtype code) -> operand [rows, ld_out] bf16, inv_norm [rows] fp32
+ *   (= 1 / max(||x||, 1e-12)), optional xhat_f32 [rows, ld_hat] fp32 (may be NULL).
+ *   split3_role: -1 plain bf16 operand; 0 / 1 = A-side / B-side panels of the bf16x3 compensated product.
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim, void* operand, int ld_out,
+                        int Kp, int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, void* stream);
+
+/* K4  normalise backward (autograd of F.normalize) fused with the analytic diagonal terms:
+ *   g = gscale * dxhat + ocoef * other_hat[r] + ucoef * usum ;  dx = (g - (g . xhat) xhat) * inv_norm
+ *   dxhat [rows, ldg] fp32, xhat_bf16/other_bf16 operand buffers (hi panel), xhat_f32 optional, usum optional. */
+int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* xhat_bf16, int ldx, const float* xhat_f32,
+                        int ldxf, const void* other_bf16, int ld_other, const float* usum, const float* inv_norm,
+                        float gscale, float ocoef, float ucoef, int rows, int other_rows, int dim, float* dx,
+                        int64_t lddx, void* stream);
+
+/* out[c] += sum_r operand[r, c]  (label-smoothing helper; out must be zeroed by the caller) */
+int b200clip_colsum_bf16(const void* operand, int ld, int rows, int dim, float* out, void* stream);
+/* out[r] = a[r, :K] . b[idx ? idx[r] : r, :K]  (diagonal / ground-truth logits; idx int64 or NULL) */
+int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const int64_t* idx, int rows,
+                         int b_rows, int K, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  Fused logits forward for the softmax-CE losses. Replaces matmul -> /temp -> 2x cross_entropy
+ *     (utils/loss/contrastive.py:150-162; losses.py:50-62, 143-156; gated: losses.py:195-210, 258-274).
+ *   A [Ma, >=Kp], B [Nb, >=Kp] operands. P_ij = 2^(f(S_ij) * scale2 - shift2), S = A B^T,
+ *   f(s) = s (gated = 0) or s * sigmoid(s) (gated = 1).
+ *   rowsum[i] += sum_j P_ij, colsum[j] += sum_i P_ij (fp32, caller zeroes them). S is never stored.
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
+                            float shift2, int gated, float* rowsum, float* colsum, void* stream);
+
+/* Validation hook: out[i, j] = S_ij (fp32, row pitch ldo) computed by the same tcgen05 tile engine.
+ * max_ctas > 0 limits the grid (exercises the multi-tile-per-CTA schedule). Used by the tests only. */
+int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out,
+                         int ldo, int max_ctas, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CLIP_H_ */
