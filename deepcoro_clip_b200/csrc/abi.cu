@@ -65,4 +65,13 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
   return logits_dump(A, B, Ma, Nb, Kp, lda, ldb, out, ldo, max_ctas, S(stream));
 }
 
+int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
+                        float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
+                        const float* colscale, float out_scale, float* dX, int ldd, float* scal, int nseg_hint,
+                        void* stream) {
+  if (!X || !Y || !dX) return B2_EINVAL;
+  return logits_bwd(mode, X, Y, Nx, Ny, Kp, Dp, D, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c, rowscale,
+                    colscale, out_scale, dX, ldd, scal, nseg_hint, S(stream));
+}
+
 }  // extern "C"

@@ -1,5 +1,6 @@
 // Internal C++ host entry points (one per kernel family); abi.cu wraps them in the extern "C" ABI.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,6 +22,15 @@ int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda
 int logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
                 int max_ctas, cudaStream_t stream);
 
+// logits_bwd.cu
+int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
+               float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
+               const float* colscale, float out_scale, float* dX, int ldd, float* scal, int nseg_hint,
+               cudaStream_t stream);
+
+// tmap.cu
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                      uint32_t box_rows);
 int sm_count();
 
 }  // namespace b2host

@@ -76,6 +76,24 @@ int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp
 int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out,
                          int ldo, int max_ctas, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K3  Fused logits backward (tile recompute). Replaces autograd through matmul / cross_entropy /
+ *     binary_cross_entropy_with_logits (utils/loss/contrastive.py:150-162, 263-303; losses.py:195-210).
+ *       dX[i, :D] += out_scale * sum_j G_ij * Y[j, :D],   S = X Y^T recomputed per 128x128 tile.
+ *     mode 0 (CLIP)   : G = 2^(S*scale2 - shift2) * (rowscale[i] + colscale[j])
+ *     mode 1 (gated)  : same with f(S) = S*sigmoid(S) inside the exponent and G *= f'(S)
+ *     mode 2 (SigLIP) : R = S*inv_tau + bias, G = wneg_c * sigmoid(clamp(R,+-30)) * [|R| <= 30]
+ *     (diagonal targets / positives are rank-sparse corrections applied by other entry points.)
+ *   X [Nx, >=Kp], Y [Ny, >=Kp] operands; Dp = padded width of the hi panel (columns of Y used for the
+ *   output product), D = valid output columns; dX fp32 [Nx, ldd] accumulated atomically (caller zeroes).
+ *   scal (may be NULL): [0] += sum G*f(S)  [1] += sum softplus(L) (mode 2)  [2] += sum G (mode 2).
+ *   nseg_hint <= 0 lets the library pick the split of the Y sweep.
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx,
+                        int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
+                        const float* rowscale, const float* colscale, float out_scale, float* dX, int ldd,
+                        float* scal, int nseg_hint, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
