@@ -33,13 +33,13 @@ int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim
                     S(stream));
 }
 
-int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* xhat_bf16, int ldx, const float* xhat_f32, int ldxf,
-                        const void* other_bf16, int ld_other, const float* usum, const float* inv_norm, float gscale,
-                        float ocoef, float ucoef, int rows, int other_rows, int dim, float* dx, int64_t lddx,
-                        void* stream) {
-  if (!dxhat || !(xhat_bf16 || xhat_f32) || !inv_norm || !dx) return B2_EINVAL;
-  return l2norm_bwd(dxhat, ldg, xhat_bf16, ldx, xhat_f32, ldxf, other_bf16, ld_other, usum, inv_norm, gscale, ocoef,
-                    ucoef, rows, other_rows, dim, dx, (long)lddx, S(stream));
+int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* x, int dtype, int64_t ldx, const float* inv_norm,
+                        const void* other_bf16, int ld_other, int other_rows, const float* usum, const float* dots,
+                        int gated, float gscale, float ocoef, float ucoef, const float* dev_omul,
+                        const float* dev_gmul, int rows, int dim, float* dx, int64_t lddx, void* stream) {
+  if (!dxhat || !x || !inv_norm || !dx) return B2_EINVAL;
+  return l2norm_bwd(dxhat, ldg, x, dtype, (long)ldx, inv_norm, other_bf16, ld_other, other_rows, usum, dots, gated,
+                    gscale, ocoef, ucoef, dev_omul, dev_gmul, rows, dim, dx, (long)lddx, S(stream));
 }
 
 int b200clip_colsum_bf16(const void* operand, int ld, int rows, int dim, float* out, void* stream) {
@@ -54,9 +54,9 @@ int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const i
 }
 
 int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                            float shift2, int gated, float* rowsum, float* colsum, void* stream) {
+                            float shift2, int gated, const float* dyn, float* rowsum, float* colsum, void* stream) {
   if (!A || !B || !rowsum || !colsum) return B2_EINVAL;
-  return logits_lse_fwd(A, B, Ma, Nb, Kp, lda, ldb, scale2, shift2, gated, rowsum, colsum, S(stream));
+  return logits_lse_fwd(A, B, Ma, Nb, Kp, lda, ldb, scale2, shift2, gated, dyn, rowsum, colsum, S(stream));
 }
 
 int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
@@ -67,11 +67,29 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
 
 int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
                         float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
-                        const float* colscale, float out_scale, float* dX, int ldd, float* scal, int nseg_hint,
-                        void* stream) {
+                        const float* colscale, float out_scale, const float* dyn, float* dX, int ldd, float* scal,
+                        int nseg_hint, void* stream) {
   if (!X || !Y || !dX) return B2_EINVAL;
   return logits_bwd(mode, X, Y, Nx, Ny, Kp, Dp, D, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c, rowscale,
-                    colscale, out_scale, dX, ldd, scal, nseg_hint, S(stream));
+                    colscale, out_scale, dyn, dX, ldd, scal, nseg_hint, S(stream));
+}
+
+int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn,
+                      void* stream) {
+  if (!log_temp || !dyn) return B2_EINVAL;
+  return dyn_prep(log_temp, bias, clamp_min, bound, dyn, S(stream));
+}
+
+int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc,
+                          void* stream) {
+  if (!sums || !dyn) return B2_EINVAL;
+  return lse_finalize(sums, n, dyn, c, scale_out, acc, S(stream));
+}
+
+int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots,
+                      double* acc, void* stream) {
+  if (!a || !b || !acc) return B2_EINVAL;
+  return diag_sum(a, lda, b, ldb, rows, K, gated, dots, acc, S(stream));
 }
 
 }  // extern "C"

@@ -53,37 +53,47 @@ l2norm_fwd_kernel(const T* __restrict__ x, long ldx, int rows, int dim, __nv_bfl
   }
 }
 
-// dx[r, :] = ((g - (g . xh) xh) * inv_norm[r]),  g = gscale * dxh[r, :] + ocoef * oth[r, :] + ucoef * usum[:]
-// xh / oth are the bf16 "hi" operands (first Kp columns of the operand buffers).
-template <typename TOut>
+// dx[r, :] = (g - (g . xh) xh) * inv_norm[r],  xh = x[r, :] * inv_norm[r] (exact fp32 from the caller's input),
+//   g = gmul * ( gscale * dxh[r, :] + (ocoef * omul * fp_r) * oth[r, :] + (ucoef * omul) * usum[:] )
+// omul / gmul are optional DEVICE scalars (1/tau from dyn_prep, upstream grad_output); fp_r = f'(dots[r]) for the
+// gated variant (f(s) = s sigmoid(s)), 1 otherwise. oth is the bf16 hi panel of the partner operand.
+template <typename T>
 __global__ void __launch_bounds__(256)
-l2norm_bwd_kernel(const float* __restrict__ dxh, int ldg, const __nv_bfloat16* __restrict__ xh, int ldx,
-                  const float* __restrict__ xh_f32, int ldxf, const __nv_bfloat16* __restrict__ oth, int ldoth,
-                  const float* __restrict__ usum, const float* __restrict__ inv_norm, float gscale, float ocoef,
-                  float ucoef, int rows, int oth_rows, int dim, TOut* __restrict__ dx, long lddx) {
+l2norm_bwd_kernel(const float* __restrict__ dxh, int ldg, const T* __restrict__ x, long ldx,
+                  const float* __restrict__ inv_norm, const __nv_bfloat16* __restrict__ oth, int ldoth, int oth_rows,
+                  const float* __restrict__ usum, const float* __restrict__ dots, int gated, float gscale, float ocoef,
+                  float ucoef, const float* __restrict__ dev_omul, const float* __restrict__ dev_gmul, int rows, int dim,
+                  float* __restrict__ dx, long lddx) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const float* g = dxh + (size_t)warp * ldg;
+  const float omul = dev_omul ? dev_omul[0] : 1.f;
+  const float gmul = dev_gmul ? dev_gmul[0] : 1.f;
+  float fpr = 1.f;
+  if (gated && dots) {
+    const float sdot = dots[warp];
+    const float sig = 1.f / (1.f + __expf(-sdot));
+    fpr = sig * (1.f + sdot * (1.f - sig));
+  }
   const bool has_oth = oth != nullptr && warp < oth_rows && ocoef != 0.f;
+  const float oc = ocoef * omul * fpr, uc = ucoef * omul;
+  const float* g = dxh + (size_t)warp * ldg;
+  const T* xr = x + (size_t)warp * ldx;
+  const float inv = inv_norm[warp];
   float dot = 0.f;
   for (int c = lane; c < dim; c += 32) {
     float gv = gscale * g[c];
-    if (has_oth) gv = fmaf(ocoef, __bfloat162float(oth[(size_t)warp * ldoth + c]), gv);
-    if (usum) gv = fmaf(ucoef, usum[c], gv);
-    const float xv = xh_f32 ? xh_f32[(size_t)warp * ldxf + c] : __bfloat162float(xh[(size_t)warp * ldx + c]);
-    dot = fmaf(gv, xv, dot);
+    if (has_oth) gv = fmaf(oc, __bfloat162float(oth[(size_t)warp * ldoth + c]), gv);
+    if (usum) gv = fmaf(uc, usum[c], gv);
+    dot = fmaf(gv, to_f32<T>(xr[c]) * inv, dot);
   }
   dot = warp_sum(dot);
-  const float inv = inv_norm[warp];
   for (int c = lane; c < dim; c += 32) {
     float gv = gscale * g[c];
-    if (has_oth) gv = fmaf(ocoef, __bfloat162float(oth[(size_t)warp * ldoth + c]), gv);
-    if (usum) gv = fmaf(ucoef, usum[c], gv);
-    const float xv = xh_f32 ? xh_f32[(size_t)warp * ldxf + c] : __bfloat162float(xh[(size_t)warp * ldx + c]);
-    const float r = (gv - dot * xv) * inv;
-    if constexpr (sizeof(TOut) == 4) dx[(size_t)warp * lddx + c] = r;
-    else dx[(size_t)warp * lddx + c] = __float2bfloat16_rn(r);
+    if (has_oth) gv = fmaf(oc, __bfloat162float(oth[(size_t)warp * ldoth + c]), gv);
+    if (usum) gv = fmaf(uc, usum[c], gv);
+    const float xv = to_f32<T>(xr[c]) * inv;
+    dx[(size_t)warp * lddx + c] = gmul * (gv - dot * xv) * inv;
   }
 }
 
@@ -139,14 +149,19 @@ int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out,
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
-int l2norm_bwd(const float* dxh, int ldg, const void* xh, int ldx, const float* xh_f32, int ldxf, const void* oth,
-               int ldoth, const float* usum, const float* inv_norm, float gscale, float ocoef, float ucoef, int rows,
-               int oth_rows, int dim, float* dx, long lddx, cudaStream_t s) {
+int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, const float* inv_norm, const void* oth,
+               int ldoth, int oth_rows, const float* usum, const float* dots, int gated, float gscale, float ocoef,
+               float ucoef, const float* dev_omul, const float* dev_gmul, int rows, int dim, float* dx, long lddx,
+               cudaStream_t s) {
   if (rows <= 0 || dim <= 0) return B2_EINVAL;
   const int blocks = (rows + 7) / 8;
-  l2norm_bwd_kernel<float><<<blocks, 256, 0, s>>>(dxh, ldg, (const __nv_bfloat16*)xh, ldx, xh_f32, ldxf,
-                                                  (const __nv_bfloat16*)oth, ldoth, usum, inv_norm, gscale, ocoef,
-                                                  ucoef, rows, oth_rows, dim, dx, lddx);
+  auto o = (const __nv_bfloat16*)oth;
+  switch (dtype) {
+    case 0: l2norm_bwd_kernel<float><<<blocks, 256, 0, s>>>(dxh, ldg, (const float*)x, ldx, inv_norm, o, ldoth, oth_rows, usum, dots, gated, gscale, ocoef, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
+    case 1: l2norm_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(dxh, ldg, (const __nv_bfloat16*)x, ldx, inv_norm, o, ldoth, oth_rows, usum, dots, gated, gscale, ocoef, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
+    case 2: l2norm_bwd_kernel<__half><<<blocks, 256, 0, s>>>(dxh, ldg, (const __half*)x, ldx, inv_norm, o, ldoth, oth_rows, usum, dots, gated, gscale, ocoef, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
+    default: return B2_EINVAL;
+  }
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

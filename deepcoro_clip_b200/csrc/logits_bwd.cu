@@ -50,6 +50,7 @@ struct BwParams {
   float* dX;                   // [Nx, ldd] fp32, accumulated with atomics
   int ldd;
   float* scal;                 // [4] fp32 atomics: 0: sum G*f(S), 1: sum softplus(L), 2: sum G ; may be null
+  const float* dyn;            // optional device block from dyn_prep: overrides scale2/shift2/inv_tau/bias/out_scale
 };
 
 template <int kMode>
@@ -98,6 +99,13 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_col = 0, s_col0 = 256;
+  if (p.dyn) {   // temperature / bias live on the device: no host sync
+    p.scale2 = p.dyn[0];
+    p.shift2 = p.dyn[1];
+    p.inv_tau = p.dyn[2];
+    p.bias = p.dyn[5];
+    p.out_scale = p.dyn[2];
+  }
 
   // item decode (identical in every role)
   auto decode = [&](int item, int& xt, int& dp, int& j0, int& j1) {
@@ -354,8 +362,8 @@ using namespace b2;
 
 int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
                float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
-               const float* colscale, float out_scale, float* dX, int ldd, float* scal, int nseg_hint,
-               cudaStream_t stream) {
+               const float* colscale, float out_scale, const float* dyn, float* dX, int ldd, float* scal,
+               int nseg_hint, cudaStream_t stream) {
   if (Nx <= 0 || Ny <= 0 || Kp <= 0 || Kp % 64 || Dp <= 0 || Dp % 64 || Dp > Kp || D > Dp || D <= 0)
     return B2_EINVAL;
   if (mode != BW_SIGLIP && (!rowscale || !colscale)) return B2_EINVAL;
@@ -378,7 +386,7 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   p.nseg = nseg;
   p.scale2 = scale2; p.shift2 = shift2; p.inv_tau = inv_tau; p.bias = bias; p.wneg_c = wneg_c;
   p.rowscale = rowscale; p.colscale = colscale; p.out_scale = out_scale;
-  p.dX = dX; p.ldd = ldd; p.scal = scal;
+  p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
   CUtensorMap tmX, tmY;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, Kp, ldx, BW_BM))) return rc;

@@ -18,6 +18,7 @@ struct LseParams {
   float* rowsum;   // [Ma] += sum_j P_ij
   float* colsum;   // [Nb] += sum_i P_ij
   int gated;       // 1: f(s) = s * sigmoid(s) (legacy "siglip" gating), 0: f(s) = s
+  const float* dyn;   // optional device block from dyn_prep (overrides scale2 / shift2): no host sync on tau
 };
 
 template <bool kGated>
@@ -26,8 +27,11 @@ struct LseEpi {
   struct State {
     float colacc[4][32];
     float rowacc;
+    float scale2, shift2;
   };
-  __device__ static __forceinline__ void init(State& st, const Params&) {
+  __device__ static __forceinline__ void init(State& st, const Params& p) {
+    st.scale2 = p.dyn ? p.dyn[0] : p.scale2;
+    st.shift2 = p.dyn ? p.dyn[1] : p.shift2;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -35,7 +39,7 @@ struct LseEpi {
     st.rowacc = 0.f;
   }
   __device__ static __forceinline__ void begin_outer(State&, const Params&, int, const TeCtx&) {}
-  __device__ static __forceinline__ float prob(float s, const Params& p) {
+  __device__ static __forceinline__ float prob(float s, const State& p) {
     if (kGated) {
       // s * sigmoid(s) = s / (1 + 2^(-s*log2e))
       const float e = ex2_approx(-1.4426950408889634f * s);
@@ -48,7 +52,7 @@ struct LseEpi {
     if (ctx.full) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const float v = prob(__uint_as_float(acc[e]), p);
+        const float v = prob(__uint_as_float(acc[e]), st);
         st.rowacc += v;
         st.colacc[c][e] += v;
       }
@@ -56,7 +60,7 @@ struct LseEpi {
       const int cbase = ctx.col0 + c * 32;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        float v = prob(__uint_as_float(acc[e]), p);
+        float v = prob(__uint_as_float(acc[e]), st);
         v = (ctx.row_ok && (cbase + e) < ctx.Nb) ? v : 0.f;
         st.rowacc += v;
         st.colacc[c][e] += v;
@@ -149,8 +153,8 @@ static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int l
 }
 
 int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                   float shift2, int gated, float* rowsum, float* colsum, cudaStream_t stream) {
-  LseParams p{scale2, shift2, rowsum, colsum, gated};
+                   float shift2, int gated, const float* dyn, float* rowsum, float* colsum, cudaStream_t stream) {
+  LseParams p{scale2, shift2, rowsum, colsum, gated, dyn};
   if (gated) return launch_te<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
   return launch_te<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
 }

@@ -1,0 +1,118 @@
+// Small device-side scalar plumbing so the loss never forces a host sync:
+//   dyn_prep      : log_temp (device) -> tau, 1/tau, log2e/tau, exponent shift, clamp flag, bias
+//   lse_finalize  : sums -> log-sum-exp total (double) + per-row gradient scales c / sum
+//   diag_sum      : sum_i f(a_i . b_i) (double) for the target-logit term
+// Layout of the `dyn` float[16] block (read by logits_fwd / logits_bwd when their dyn pointer is non-null):
+//   [0] scale2 = log2(e)/tau   [1] shift2   [2] 1/tau   [3] tau   [4] 1 if tau was clamped (dlog_temp = 0)
+//   [5] bias                    [6] ln(2)*shift2        [7] 1 if (learnable) temperature gradient is live
+#include "common.cuh"
+#include "host_api.h"
+
+namespace b2 {
+
+__global__ void dyn_prep_kernel(const float* __restrict__ log_temp, const float* __restrict__ bias, float clamp_min,
+                                float bound, float* __restrict__ dyn) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float tau = expf(log_temp[0]);
+  float clamped = 0.f;
+  if (clamp_min > 0.f && tau < clamp_min) {   // torch.clamp(min=1e-4): gradient is zero when active
+    tau = clamp_min;
+    clamped = 1.f;
+  }
+  const float scale2 = 1.4426950408889634f / tau;
+  // P = 2^(f(S)*scale2 - shift2) with f(S) <= bound. shift2 = scale2*bound - OFF keeps the largest term at
+  // 2^OFF; OFF > 0 only when the dynamic range 2*bound/tau would otherwise underflow fp32 (tau < ~0.023).
+  float off = 2.f * bound * scale2 - 120.f;
+  off = fminf(fmaxf(off, 0.f), 100.f);
+  const float shift2 = scale2 * bound - off;
+  dyn[0] = scale2;
+  dyn[1] = shift2;
+  dyn[2] = 1.f / tau;
+  dyn[3] = tau;
+  dyn[4] = clamped;
+  dyn[5] = bias ? bias[0] : 0.f;
+  dyn[6] = 0.6931471805599453f * shift2;
+  dyn[7] = 1.f - clamped;
+}
+
+// acc[slot] += sum_r ln( sums[r] ) + ln2*shift2 ;  scale_out[r] = c / sums[r]
+__global__ void __launch_bounds__(256)
+lse_finalize_kernel(const float* __restrict__ sums, int n, const float* __restrict__ dyn, float c,
+                    float* __restrict__ scale_out, double* __restrict__ acc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < n) {
+    const float s = sums[i];
+    v = (double)logf(s) + (double)dyn[6];
+    if (scale_out) scale_out[i] = c / s;
+  }
+  // block reduce in double
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    v = sh[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0 && acc) atomicAdd(acc, v);
+  }
+}
+
+// acc += sum_r f(a[r,:K] . b[r,:K]),  f = identity or s*sigmoid(s);  optionally stores the raw dots
+__global__ void __launch_bounds__(256)
+diag_sum_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b, int ldb, int rows,
+                int K, int gated, float* __restrict__ dots, double* __restrict__ acc) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  if (warp < rows) {
+    const __nv_bfloat162* ar = reinterpret_cast<const __nv_bfloat162*>(a + (size_t)warp * lda);
+    const __nv_bfloat162* br = reinterpret_cast<const __nv_bfloat162*>(b + (size_t)warp * ldb);
+    for (int c = lane; c < K / 2; c += 32) {
+      const float2 av = __bfloat1622float2(ar[c]);
+      const float2 bv = __bfloat1622float2(br[c]);
+      s = fmaf(av.x, bv.x, s);
+      s = fmaf(av.y, bv.y, s);
+    }
+  }
+  s = warp_sum(s);
+  __shared__ double sh[8];
+  if (lane == 0) {
+    if (warp < rows && dots) dots[warp] = s;
+    double f = 0.0;
+    if (warp < rows) f = gated ? (double)s / (1.0 + exp(-(double)s)) : (double)s;
+    sh[threadIdx.x >> 5] = f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(acc, t);
+  }
+}
+
+}  // namespace b2
+
+namespace b2host {
+using namespace b2;
+
+int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s) {
+  dyn_prep_kernel<<<1, 32, 0, s>>>(log_temp, bias, clamp_min, bound, dyn);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s) {
+  if (n <= 0) return B2_EINVAL;
+  lse_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(sums, n, dyn, c, scale_out, acc);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots, double* acc,
+             cudaStream_t s) {
+  if (rows <= 0 || K <= 0 || (K & 1)) return B2_EINVAL;
+  diag_sum_kernel<<<(rows + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb, rows, K,
+                                                 gated, dots, acc);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+}  // namespace b2host

@@ -1,0 +1,96 @@
+"""Thin tensor-level wrappers over the C ABI (include/b200clip.h). No math happens in Python/PyTorch here:
+torch only provides device buffers, the current stream and (in dist.py) the NCCL process group."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import DTYPE_CODE, call, i64, stream_ptr
+
+LOG2E = math.log2(math.e)
+GATED_BOUND = 0.7310585786300049  # max of s*sigmoid(s) on [-1, 1] (at s = 1)
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.B200ClipError(
+                "deepcoro_clip_b200 runs on sm_100a GPUs only: got a CPU tensor and there is no CPU fallback")
+        dev = t.device
+    _lib.lib()  # fail loudly if the native library is absent
+    return dev
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _rowmajor(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() != 2:
+        raise ValueError(f"expected a 2-D [rows, dim] tensor, got shape {tuple(x.shape)}")
+    if x.dtype not in DTYPE_CODE:
+        x = x.float()
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    return x
+
+
+def l2norm_operand(x: torch.Tensor, split3_role: int = -1):
+    """x [rows, dim] -> (bf16 operand [rows, ld], inv_norm [rows] fp32, Kp). split3_role 0/1 = bf16x3 panels."""
+    x = _rowmajor(x)
+    rows, dim = x.shape
+    Kp = round_up(dim, 64)
+    ld = 3 * Kp if split3_role >= 0 else Kp
+    op = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    call("l2norm_fwd", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), rows, dim, op, ld, Kp, split3_role, inv, None, 0,
+         stream_ptr(x.device))
+    return op, inv, Kp
+
+
+def l2norm_backward(dxhat, x, inv_norm, *, other=None, other_rows=0, usum=None, dots=None, gated=False, gscale=1.0,
+                    ocoef=0.0, ucoef=0.0, dev_omul=None, dev_gmul=None):
+    x = _rowmajor(x)
+    rows, dim = x.shape
+    dx = torch.empty((rows, dim), dtype=torch.float32, device=x.device)
+    call("l2norm_bwd", dxhat, dxhat.stride(0), x, DTYPE_CODE[x.dtype], i64(x.stride(0)), inv_norm, other,
+         other.stride(0) if other is not None else 0, other_rows, usum, dots, int(gated), float(gscale), float(ocoef),
+         float(ucoef), dev_omul, dev_gmul, rows, dim, dx, i64(dim), stream_ptr(x.device))
+    return dx
+
+
+def dyn_prep(log_temp: torch.Tensor, bias, clamp_min: float, bound: float) -> torch.Tensor:
+    lt = log_temp.detach().reshape(-1)[:1].float().contiguous()
+    b = None if bias is None else bias.detach().reshape(-1)[:1].float().contiguous()
+    dyn = torch.empty(16, dtype=torch.float32, device=lt.device)
+    call("dyn_prep", lt, b, float(clamp_min), float(bound), dyn, stream_ptr(lt.device))
+    return dyn
+
+
+def lse_fwd(A, B, Ma, Nb, K, dyn, gated, rowsum, colsum):
+    call("logits_lse_fwd", A, B, Ma, Nb, K, A.stride(0), B.stride(0), 0.0, 0.0, int(gated), dyn, rowsum, colsum,
+         stream_ptr(A.device))
+
+
+def lse_finalize(sums, dyn, c, scale_out, acc_slot):
+    call("lse_finalize", sums, sums.numel(), dyn, float(c), scale_out, acc_slot, stream_ptr(sums.device))
+
+
+def diag_sum(a, b, rows, K, gated, dots, acc_slot):
+    call("diag_sum", a, a.stride(0), b, b.stride(0), rows, K, int(gated), dots, acc_slot, stream_ptr(a.device))
+
+
+def colsum_bf16(op, rows, dim):
+    out = torch.zeros(dim, dtype=torch.float32, device=op.device)
+    call("colsum_bf16", op, op.stride(0), rows, dim, out, stream_ptr(op.device))
+    return out
+
+
+def logits_bwd(mode, X, Y, Nx, Ny, K, Dp, D, dyn, rowscale, colscale, dX, scal, *, wneg_c=0.0, nseg=0):
+    call("logits_bwd", mode, X, Y, Nx, Ny, K, Dp, D, X.stride(0), Y.stride(0), 0.0, 0.0, 0.0, 0.0, float(wneg_c),
+         rowscale, colscale, 0.0, dyn, dX, dX.stride(0), scal, nseg, stream_ptr(X.device))

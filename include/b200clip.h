@@ -47,13 +47,16 @@ int b200clip_sm_count(void);
 int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim, void* operand, int ld_out,
                         int Kp, int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, void* stream);
 
-/* K4  normalise backward (autograd of F.normalize) fused with the analytic diagonal terms:
- *   g = gscale * dxhat + ocoef * other_hat[r] + ucoef * usum ;  dx = (g - (g . xhat) xhat) * inv_norm
- *   dxhat [rows, ldg] fp32, xhat_bf16/other_bf16 operand buffers (hi panel), xhat_f32 optional, usum optional. */
-int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* xhat_bf16, int ldx, const float* xhat_f32,
-                        int ldxf, const void* other_bf16, int ld_other, const float* usum, const float* inv_norm,
-                        float gscale, float ocoef, float ucoef, int rows, int other_rows, int dim, float* dx,
-                        int64_t lddx, void* stream);
+/* K4  normalise backward (autograd of F.normalize) fused with the analytic rank-sparse gradient terms:
+ *   g  = gmul * ( gscale * dxhat[r] + (ocoef * omul * fp_r) * other_hat[r] + (ucoef * omul) * usum )
+ *   dx = (g - (g . xhat) xhat) * inv_norm,   xhat = x * inv_norm (recomputed in fp32 from the caller's input)
+ *   other_bf16: hi panel of the partner operand (diagonal target term of the CLIP gradient), usum: column sum
+ *   of the partner operand (label smoothing), dots/gated: fp_r = f'(dots[r]) for the gated legacy variant.
+ *   dev_omul / dev_gmul: optional DEVICE scalars (1/tau inside dyn, upstream grad_output). dx fp32 [rows, lddx]. */
+int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* x, int dtype, int64_t ldx, const float* inv_norm,
+                        const void* other_bf16, int ld_other, int other_rows, const float* usum, const float* dots,
+                        int gated, float gscale, float ocoef, float ucoef, const float* dev_omul,
+                        const float* dev_gmul, int rows, int dim, float* dx, int64_t lddx, void* stream);
 
 /* out[c] += sum_r operand[r, c]  (label-smoothing helper; out must be zeroed by the caller) */
 int b200clip_colsum_bf16(const void* operand, int ld, int rows, int dim, float* out, void* stream);
@@ -67,9 +70,11 @@ int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const i
  *   A [Ma, >=Kp], B [Nb, >=Kp] operands. P_ij = 2^(f(S_ij) * scale2 - shift2), S = A B^T,
  *   f(s) = s (gated = 0) or s * sigmoid(s) (gated = 1).
  *   rowsum[i] += sum_j P_ij, colsum[j] += sum_i P_ij (fp32, caller zeroes them). S is never stored.
+ *   dyn (may be NULL): device float[16] written by b200clip_dyn_prep; when given, scale2/shift2 are read from
+ *   it on the device, so a learnable temperature never forces a host synchronisation.
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                            float shift2, int gated, float* rowsum, float* colsum, void* stream);
+                            float shift2, int gated, const float* dyn, float* rowsum, float* colsum, void* stream);
 
 /* Validation hook: out[i, j] = S_ij (fp32, row pitch ldo) computed by the same tcgen05 tile engine.
  * max_ctas > 0 limits the grid (exercises the multi-tile-per-CTA schedule). Used by the tests only. */
@@ -91,8 +96,23 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx,
                         int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
-                        const float* rowscale, const float* colscale, float out_scale, float* dX, int ldd,
-                        float* scal, int nseg_hint, void* stream);
+                        const float* rowscale, const float* colscale, float out_scale, const float* dyn, float* dX,
+                        int ldd, float* scal, int nseg_hint, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-side scalar plumbing (no host sync on log_temp / bias).
+ *   dyn_prep     : tau = exp(log_temp) [clamped at clamp_min if > 0: contrastive.py:153, 266]; bound = max of
+ *                  f(S) (1 for plain, 0.7311 for gated). dyn = {log2e/tau, shift2, 1/tau, tau, clamped, bias,
+ *                  ln2*shift2, 1-clamped, ...} (float[16]).
+ *   lse_finalize : acc[0] += sum_r (ln sums[r] + ln2*shift2)  (double) ; scale_out[r] = c / sums[r]
+ *   diag_sum     : acc[0] += sum_r f(a[r,:K] . b[r,:K]) (double), f = identity / s*sigmoid(s); optional dots[r].
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn,
+                      void* stream);
+int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc,
+                          void* stream);
+int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots,
+                      double* acc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,166 @@
+"""ORACLE (test infrastructure, never imported by the product package).
+
+CPU restatement in numpy of the reference's contrastive losses, with closed-form gradients.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+
+Pinned: tests/test_oracle_golden.py checks every function here against tests/golden/*.npz, which
+oracle/gen_golden.py produced by importing the UNMODIFIED reference modules from /root/reference
+(torch CPU, fp32 and fp64 autograd) in the build container.
+
+Follows, line by line:
+  CLIPLoss.forward            /root/reference/utils/loss/contrastive.py:140-164
+  SigLIPLoss.forward          /root/reference/utils/loss/contrastive.py:250-315
+  compute_entropy_regularization                          contrastive.py:19-68
+  ContrastiveLoss / DDP       /root/reference/utils/loss/losses.py:44-64, 132-158   (no tau clamp)
+  SiglipLoss / DDP (gated)    /root/reference/utils/loss/losses.py:190-211, 241-276
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def l2_normalize(x: np.ndarray, eps: float = 1e-12) -> tuple[np.ndarray, np.ndarray]:
+    """F.normalize(x, dim=-1): x / max(||x||, eps). Returns (xhat, norm_clamped)."""
+    n = np.sqrt((x * x).sum(axis=-1, keepdims=True))
+    n = np.maximum(n, eps)
+    return x / n, n
+
+
+def _normalize_backward(dxhat: np.ndarray, xhat: np.ndarray, n: np.ndarray) -> np.ndarray:
+    # d/dx of x/||x||  (rows with ||x|| < eps are clamped: derivative is dxhat/eps there; never hit in tests)
+    return (dxhat - (dxhat * xhat).sum(axis=-1, keepdims=True) * xhat) / n
+
+
+def _logsumexp(a: np.ndarray, axis: int) -> np.ndarray:
+    m = a.max(axis=axis, keepdims=True)
+    return (m + np.log(np.exp(a - m).sum(axis=axis, keepdims=True))).squeeze(axis)
+
+
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def clip_loss(video, text, log_temp, *, label_smoothing: float = 0.0, clamp_min: float | None = 1e-4,
+              gated: bool = False, dtype=np.float64, want_grads: bool = True) -> dict:
+    """0.5*(CE(L, arange) + CE(L^T, arange)), L = f(S)/tau, S = vhat that^T.
+
+    clamp_min=1e-4 -> CLIPLoss (contrastive.py:153); None -> legacy ContrastiveLoss (losses.py:53).
+    gated=True -> f(s) = s*sigmoid(s) (losses.py:198), else identity.
+    """
+    v = np.asarray(video, dtype=dtype)
+    t = np.asarray(text, dtype=dtype)
+    lt = dtype(np.asarray(log_temp, dtype=np.float64).reshape(-1)[0])
+    vh, vn = l2_normalize(v)
+    th, tn = l2_normalize(t)
+    S = vh @ th.T
+    tau = np.exp(lt)
+    clamped = False
+    if clamp_min is not None and tau < clamp_min:
+        tau, clamped = dtype(clamp_min), True
+    if gated:
+        sg = _sigmoid(S)
+        F = S * sg
+        Fp = sg * (1.0 + S * (1.0 - sg))
+    else:
+        F, Fp = S, None
+    L = F / tau
+    N = L.shape[0]
+    eps = label_smoothing
+    r = _logsumexp(L, 1)
+    c = _logsumexp(L, 0)
+    Y = (1.0 - eps) * np.eye(N, dtype=dtype) + eps / N
+    tgt = (Y * L).sum()
+    loss = 0.5 * ((r.sum() - tgt) / N + (c.sum() - tgt) / N)
+    out = {"loss": float(loss), "row_lse": r, "col_lse": c, "tau": float(tau)}
+    if not want_grads:
+        return out
+    G = ((np.exp(L - r[:, None]) - Y) + (np.exp(L - c[None, :]) - Y)) / (2.0 * N)      # dloss/dL
+    dS = G / tau if Fp is None else G * Fp / tau
+    dvh = dS @ th
+    dth = dS.T @ vh
+    out["dvideo"] = _normalize_backward(dvh, vh, vn)
+    out["dtext"] = _normalize_backward(dth, th, tn)
+    out["dlog_temp"] = 0.0 if clamped else float(-(G * L).sum())
+    return out
+
+
+def entropy_regularization(logits: np.ndarray, min_entropy_threshold: float = 2.0):
+    """contrastive.py:19-68 — relu(thr - mean_i H(softmax_j logits_i.)) with log(p + 1e-10)."""
+    z = logits - logits.max(axis=1, keepdims=True)
+    p = np.exp(z)
+    p = p / p.sum(axis=1, keepdims=True)
+    ent = -(p * np.log(p + 1e-10)).sum(axis=1)
+    mean_ent = ent.mean()
+    deficit = max(min_entropy_threshold - mean_ent, 0.0)
+    diag = {"entropy_mean": float(mean_ent), "entropy_min": float(ent.min()), "entropy_max": float(ent.max()),
+            "entropy_normalized": float(mean_ent / np.log(logits.shape[1])), "entropy_deficit": float(deficit)}
+    return deficit, diag, p, ent
+
+
+def siglip_loss(video, text, log_temp, *, bias: float = -10.0, pos_mask=None, pos_weights=None,
+                positive_weight: float = 1.0, negative_weight: float = 1.0, use_severity_weights: bool = True,
+                auto_balance: bool = False, entropy_regularization_on: bool = False, entropy_weight: float = 0.1,
+                min_entropy_threshold: float = 2.0, dtype=np.float64, want_grads: bool = True) -> dict:
+    """SigLIPLoss.forward, contrastive.py:250-315 (single process: the gather is the identity)."""
+    v = np.asarray(video, dtype=dtype)
+    t = np.asarray(text, dtype=dtype)
+    lt = dtype(np.asarray(log_temp, dtype=np.float64).reshape(-1)[0])
+    positive_weight = max(float(positive_weight), 1e-6)
+    negative_weight = max(float(negative_weight), 1e-6)
+    vh, vn = l2_normalize(v)
+    th, tn = l2_normalize(t)
+    S = vh @ th.T
+    tau = np.exp(lt)
+    clamped = tau < 1e-4
+    if clamped:
+        tau = dtype(1e-4)
+    R = S / tau + dtype(bias)
+    L = np.clip(R, -30.0, 30.0)
+    B, T = L.shape
+    if pos_mask is None:
+        y = np.zeros((B, T), dtype=dtype)
+        m = min(B, T)
+        y[:m, :m] = np.eye(m, dtype=dtype)
+    else:
+        y = np.clip(np.asarray(pos_mask, dtype=dtype), 0.0, 1.0)
+    w = np.full((B, T), negative_weight, dtype=dtype)
+    if use_severity_weights and pos_weights is not None:
+        pc = np.asarray(pos_weights, dtype=dtype) * positive_weight
+    else:
+        pc = np.full((B, T), positive_weight, dtype=dtype)
+    if auto_balance:
+        pos_counts = np.maximum(y.sum(axis=1, keepdims=True), 1.0)
+        ratio = np.maximum((T - pos_counts) / pos_counts, 1.0)
+        pc = np.broadcast_to(ratio, (B, T))
+    w = np.where(y > 0.5, pc, w)
+    bce = np.maximum(L, 0.0) - L * y + np.log1p(np.exp(-np.abs(L)))
+    loss = (w * bce).mean()
+    out = {"bce_loss": float(loss), "tau": float(tau)}
+    dL = w * (_sigmoid(L) - y) / (B * T)
+    if entropy_regularization_on:
+        deficit, diag, p, ent = entropy_regularization(L, min_entropy_threshold)
+        out["entropy_diagnostics"] = diag
+        loss = loss + entropy_weight * deficit
+        if deficit > 0.0:
+            # d(-mean H)/dL_ij = -(1/B) * dH_i/dL_ij ; dH_i/dz_j = -p_j*(log(p_j+e) + p_j/(p_j+e)) + p_j*sum_k p_k(...)
+            e = 1e-10
+            gterm = np.log(p + e) + p / (p + e)
+            dH = -p * gterm + p * (p * gterm).sum(axis=1, keepdims=True)
+            dL = dL + entropy_weight * (-dH / B)
+    out["loss"] = float(loss)
+    if not want_grads:
+        return out
+    dR = dL * ((R >= -30.0) & (R <= 30.0))
+    dS = dR / tau
+    out["dvideo"] = _normalize_backward(dS @ th, vh, vn)
+    out["dtext"] = _normalize_backward(dS.T @ vh, th, tn)
+    out["dbias"] = float(dR.sum())
+    out["dlog_temp"] = 0.0 if clamped else float(-(dR * (R - bias)).sum())
+    return out
+
+
+# ---- fp32 timing port used by bench.py (cpu_baseline / --impl reference); same algorithm, all host threads ----
+def clip_fwd_bwd_f32(video: np.ndarray, text: np.ndarray, log_temp: float):
+    """The reference step (normalize, matmul, 2x cross-entropy, backward) in fp32 numpy (BLAS threads)."""
+    r = clip_loss(video, text, log_temp, dtype=np.float32)
+    return r["loss"], r["dvideo"], r["dtext"], r["dlog_temp"]

@@ -1,0 +1,235 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference modules (imported from /root/reference,
+torch CPU) on seeded synthetic inputs. Run in the build container only:
+
+    python oracle/gen_golden.py
+
+The GPU box has no /root/reference; it checks against these committed vectors instead.
+"""
+from __future__ import annotations
+
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+OUT.mkdir(parents=True, exist_ok=True)
+
+from utils.loss.contrastive import CLIPLoss, SigLIPLoss  # noqa: E402
+from utils.loss.losses import ContrastiveLoss, SiglipLoss  # noqa: E402
+from utils.retrieval_metrics_streaming import compute_metrics_streaming, compute_recall_at_k_streaming  # noqa: E402
+from models.rope_3d import Rope3D  # noqa: E402
+from models.attention_pool import AttentionPool  # noqa: E402
+from models.video_aggregator import EnhancedVideoAggregator  # noqa: E402
+
+
+def _np(t):
+    return t.detach().cpu().double().numpy() if t.dtype != torch.bfloat16 else t.detach().float().numpy()
+
+
+def run_loss(mod, v, t, lt, dtype, **kw):
+    v = v.to(dtype).clone().requires_grad_(True)
+    t = t.to(dtype).clone().requires_grad_(True)
+    lt = lt.to(dtype).clone().requires_grad_(True)
+    kw = {k: (x.to(dtype) if isinstance(x, torch.Tensor) else x) for k, x in kw.items()}
+    if dtype == torch.float64:
+        mod = mod.double()
+    loss = mod(v, t, lt, **kw)
+    loss.backward()
+    out = dict(loss=_np(loss), dvideo=_np(v.grad), dtext=_np(t.grad), dlog_temp=_np(lt.grad))
+    if hasattr(mod, "bias") and isinstance(mod.bias, torch.nn.Parameter) and mod.bias.grad is not None:
+        out["dbias"] = _np(mod.bias.grad)
+    return out
+
+
+def save_loss_case(name, mod_fn, B, T, D, seed, log_temp, extra=None, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(B, D, generator=g) * scale
+    t = torch.randn(T, D, generator=g) * scale
+    lt = torch.tensor([log_temp])
+    kw = extra(g) if extra else {}
+    rec = dict(video=v.numpy(), text=t.numpy(), log_temp=np.array([log_temp]))
+    for k, x in kw.items():
+        rec["in_" + k] = x.numpy()
+    # torch's CPU float64 autocast guard: the reference casts to .float() internally, so the "fp64" run is
+    # only fp64 where the module does not force fp32; we therefore also record the fp32 run (the real reference).
+    r32 = run_loss(mod_fn(), v, t, lt, torch.float32, **kw)
+    for k, x in r32.items():
+        rec["f32_" + k] = x
+    np.savez_compressed(OUT / f"{name}.npz", **rec)
+    print(name, "loss", float(r32["loss"]))
+
+
+def losses():
+    save_loss_case("clip_c1_b64_d512", lambda: CLIPLoss(), 64, 64, 512, 0, math.log(0.07))
+    save_loss_case("clip_ls_b48_d96", lambda: CLIPLoss(label_smoothing=0.1), 48, 48, 96, 11, math.log(0.0588))
+    save_loss_case("clip_clamp_b8_d64", lambda: CLIPLoss(), 8, 8, 64, 12, math.log(5e-5))
+    save_loss_case("clip_b300_d200", lambda: CLIPLoss(), 300, 300, 200, 13, math.log(0.0588))
+    save_loss_case("contrastive_legacy_b32_d128", lambda: ContrastiveLoss(), 32, 32, 128, 14, math.log(0.1))
+    save_loss_case("gated_siglip_legacy_b40_d128", lambda: SiglipLoss(), 40, 40, 128, 15, math.log(0.1))
+
+    def mp(B, T, npos, weights=True):
+        def f(g):
+            m = torch.zeros(B, T)
+            idx = torch.arange(B) % T
+            m[torch.arange(B), idx] = 1.0
+            for _ in range(npos - 1):
+                m[torch.arange(B), torch.randint(0, T, (B,), generator=g)] = 1.0
+            out = {"pos_mask": m}
+            if weights:
+                choices = torch.tensor([1.0, 1.5, 2.5, 3.0])
+                out["pos_weights"] = m * choices[torch.randint(0, 4, (B, T), generator=g)]
+            return out
+        return f
+
+    save_loss_case("siglip_diag_b32_t32_d64", lambda: SigLIPLoss(), 32, 32, 64, 20, math.log(0.087))
+    save_loss_case("siglip_mp_b32_t40_d64", lambda: SigLIPLoss(), 32, 40, 64, 21, math.log(0.087), mp(32, 40, 4))
+    save_loss_case("siglip_mp_noweights_b24_t50_d96", lambda: SigLIPLoss(positive_weight=2.0, negative_weight=0.5,
+                                                                         use_severity_weights=False),
+                   24, 50, 96, 22, math.log(0.07), mp(24, 50, 3))
+    save_loss_case("siglip_autobalance_b16_t48_d64", lambda: SigLIPLoss(auto_balance=True), 16, 48, 64, 23,
+                   math.log(0.1), mp(16, 48, 3, weights=False))
+    save_loss_case("siglip_entropy_b16_t32_d64", lambda: SigLIPLoss(entropy_regularization=True, bias_init=-2.0,
+                                                                    min_entropy_threshold=5.0),
+                   16, 32, 64, 24, math.log(0.05), mp(16, 32, 2))
+    save_loss_case("siglip_bias0_b130_t260_d512", lambda: SigLIPLoss(bias_init=-1.0), 130, 260, 512, 25,
+                   math.log(0.087), mp(130, 260, 4))
+
+
+def retrieval():
+    g = torch.Generator().manual_seed(30)
+    v = torch.randn(300, 64, generator=g)
+    t = torch.randn(200, 64, generator=g)
+    gt = torch.randint(0, 200, (300,), generator=g)
+    m = compute_metrics_streaming(v, t, gt, k_values=[1, 5, 10, 50], video_chunk_size=128, text_chunk_size=64,
+                                  device="cpu")
+    np.savez_compressed(OUT / "retrieval_gauss_300x200.npz", video=v.numpy(), text=t.numpy(), gt=gt.numpy(),
+                        keys=np.array(list(m.keys())), values=np.array([float(x) for x in m.values()]))
+    # exact-grid inputs (tie free by construction check) through the recall-only API (no normalisation)
+    rng = np.random.default_rng(31)
+    ve = (rng.integers(-127, 128, size=(257, 64)) / 128.0).astype(np.float32)
+    te = (rng.integers(-127, 128, size=(300, 64)) / 128.0).astype(np.float32)
+    gte = rng.integers(0, 300, size=257)
+    r = compute_recall_at_k_streaming(torch.from_numpy(ve), torch.from_numpy(te), torch.from_numpy(gte),
+                                      k_values=[1, 5, 10], video_chunk_size=100, text_chunk_size=77, device="cpu")
+    sim = torch.from_numpy(ve) @ torch.from_numpy(te).t()
+    top = torch.topk(sim, 10, dim=1)
+    np.savez_compressed(OUT / "retrieval_grid_257x300.npz", video=ve, text=te, gt=gte,
+                        keys=np.array(list(r.keys())), values=np.array([float(x) for x in r.values()]),
+                        topk_idx=top.indices.numpy(), topk_val=top.values.numpy())
+    # known-answer cases of tests/test_retrieval_metrics.py re-expressed for the streaming API
+    eye = torch.eye(5)
+    m1 = compute_metrics_streaming(eye, eye, torch.arange(5), k_values=[1, 3, 5], device="cpu")
+    anti = torch.flip(torch.eye(5), dims=[1])
+    m2 = compute_metrics_streaming(eye, anti, torch.arange(5), k_values=[1], device="cpu")
+    np.savez_compressed(OUT / "retrieval_known.npz", eye_keys=np.array(list(m1.keys())),
+                        eye_values=np.array([float(x) for x in m1.values()]), anti_keys=np.array(list(m2.keys())),
+                        anti_values=np.array([float(x) for x in m2.values()]))
+    print("retrieval", m, r, m1, m2)
+
+
+def rope():
+    for name, (B, heads, T, H, W, cls, dtype) in {
+        "rope_f32_t2h3w4_cls": (2, 4, 2, 3, 4, 1, torch.float32),
+        "rope_f32_t3h2w2": (1, 8, 3, 2, 2, 0, torch.float32),
+        "rope_bf16_t4h7w7_cls": (2, 4, 4, 7, 7, 1, torch.bfloat16),
+    }.items():
+        g = torch.Generator().manual_seed(40)
+        N = T * H * W + cls
+        q = torch.randn(B, heads, N, 96, generator=g).to(dtype).requires_grad_(True)
+        k = torch.randn(B, heads, N, 96, generator=g).to(dtype).requires_grad_(True)
+        mod = Rope3D(embed_dim=96 * heads, num_heads=heads).eval()
+        qr, kr = mod(q, k, T, H, W)
+        gq = torch.randn(B, heads, N, 96, generator=g).to(dtype)
+        gk = torch.randn(B, heads, N, 96, generator=g).to(dtype)
+        (qr * gq).sum().backward(retain_graph=True)
+        (kr * gk).sum().backward()
+        sin, cos = mod._get_cached_freqs(T, H, W, q.device, dtype, cls)
+        np.savez_compressed(OUT / f"{name}.npz", q=_np(q), k=_np(k), gq=_np(gq), gk=_np(gk), q_rot=_np(qr),
+                            k_rot=_np(kr), dq=_np(q.grad), dk=_np(k.grad), sin=_np(sin), cos=_np(cos),
+                            meta=np.array([B, heads, T, H, W, cls]))
+        print(name, tuple(qr.shape))
+    # mismatch branch: N != THW (+1) -> unchanged
+    mod = Rope3D(embed_dim=96 * 2, num_heads=2).eval()
+    q = torch.randn(1, 2, 7, 96)
+    qr, kr = mod(q, q, 2, 2, 2)
+    assert qr is q and kr is q
+
+
+def attnpool():
+    for name, (B, N, D, heads, out_dim, use_mask) in {
+        "attnpool_b3_n50_d64_h8": (3, 50, 64, 8, None, False),
+        "attnpool_b4_n37_d128_h4_mask_proj": (4, 37, 128, 4, 32, True),
+    }.items():
+        torch.manual_seed(50)
+        mod = AttentionPool(D, num_heads=heads, output_dim=out_dim, dropout=0.0).double()
+        # default init leaves in_proj_bias / out_proj.bias at 0: randomise so every term is exercised
+        with torch.no_grad():
+            mod.attn.in_proj_bias.normal_(std=0.3)
+            mod.attn.out_proj.bias.normal_(std=0.3)
+            mod.norm.weight.normal_(mean=1.0, std=0.2)
+            mod.norm.bias.normal_(std=0.2)
+            mod.query.normal_(std=0.5)
+        g = torch.Generator().manual_seed(51)
+        x = torch.randn(B, N, D, generator=g).double().requires_grad_(True)
+        mask = None
+        if use_mask:
+            mask = torch.rand(B, N, generator=g) < 0.2
+            mask[:, 0] = False
+        out = mod(x, mask)
+        go = torch.randn(out.shape, generator=g).double()
+        (out * go).sum().backward()
+        rec = dict(x=_np(x), go=_np(go), out=_np(out), dx=_np(x.grad), heads=np.array(heads),
+                   mask=np.zeros((B, N), bool) if mask is None else mask.numpy(), has_mask=np.array(use_mask))
+        names = {"query": mod.query, "in_proj_weight": mod.attn.in_proj_weight, "in_proj_bias": mod.attn.in_proj_bias,
+                 "out_proj_weight": mod.attn.out_proj.weight, "out_proj_bias": mod.attn.out_proj.bias,
+                 "norm_weight": mod.norm.weight, "norm_bias": mod.norm.bias}
+        if out_dim is not None:
+            names["proj_weight"] = mod.proj.weight
+            names["proj_bias"] = mod.proj.bias
+        for k, p in names.items():
+            rec["p_" + k] = _np(p)
+            rec["g_" + k] = _np(p.grad)
+        np.savez_compressed(OUT / f"{name}.npz", **rec)
+        print(name, tuple(out.shape))
+
+
+def qpool():
+    for name, (B, N, D, use_mask) in {"qpool_b5_n4_d64": (5, 4, 64, False), "qpool_b6_n5_d128_mask": (6, 5, 128, True)}.items():
+        torch.manual_seed(60)
+        mod = EnhancedVideoAggregator(D, num_heads=4, dropout=0.0, aggregator_depth=0, max_segments=16).double()
+        with torch.no_grad():
+            mod.final_ln.weight.normal_(mean=1.0, std=0.2)
+            mod.final_ln.bias.normal_(std=0.2)
+            mod.attn_query.normal_(std=0.5)
+            mod.pos_encoding.normal_(std=0.3)
+        g = torch.Generator().manual_seed(61)
+        x = torch.randn(B, N, D, generator=g).double().requires_grad_(True)
+        mask = None
+        if use_mask:
+            mask = torch.rand(B, N, generator=g) < 0.3
+            mask[0] = False
+            mask[1] = True          # all-masked study: uniform-over-valid fallback => zeros
+        out = mod(x, mask)
+        go = torch.randn(out.shape, generator=g).double()
+        (out * go).sum().backward()
+        np.savez_compressed(OUT / f"{name}.npz", x=_np(x), go=_np(go), out=_np(out), dx=_np(x.grad),
+                            mask=np.zeros((B, N), bool) if mask is None else mask.numpy(), has_mask=np.array(use_mask),
+                            pos=_np(mod.pos_encoding), ln_w=_np(mod.final_ln.weight), ln_b=_np(mod.final_ln.bias),
+                            attn_query=_np(mod.attn_query), g_pos=_np(mod.pos_encoding.grad),
+                            g_ln_w=_np(mod.final_ln.weight.grad), g_ln_b=_np(mod.final_ln.bias.grad),
+                            g_attn_query=_np(mod.attn_query.grad))
+        print(name, tuple(out.shape))
+
+
+if __name__ == "__main__":
+    losses()
+    retrieval()
+    rope()
+    attnpool()
+    qpool()

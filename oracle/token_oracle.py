@@ -1,0 +1,220 @@
+"""ORACLE (test infrastructure, never imported by the product package).
+
+numpy restatements of the token-side modules, with closed-form backward passes:
+  rope3d_*            /root/reference/models/rope_3d.py:13-44 (tables), :130-184 (3D grid), :208-252 (apply)
+  attention_pool_*    /root/reference/models/attention_pool.py:73-101 (nn.MultiheadAttention with ONE query
+                      token + LayerNorm + optional Linear), written in the folded form of SURVEY Appendix A.4
+  query_pool_*        /root/reference/models/video_aggregator.py:119-123, 128-158 (pos-enc, final LN, masked
+                      softmax pooling with uniform fallback)
+Pinned against the imported reference by tests/golden/{rope,attnpool,qpool}_*.npz (oracle/gen_golden.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# RoPE 3D
+# ------------------------------------------------------------------------------------------------
+def rope3d_dims(head_dim: int) -> tuple[int, int, int]:
+    if head_dim % 6 != 0:
+        raise ValueError("head_dim must be divisible by 6")
+    t = head_dim // 3
+    return t, t, head_dim - 2 * t
+
+
+def rope3d_angles(head_dim, T, H, W, n_special=0, temporal_base=10000.0, spatial_base=10000.0, temporal_scale=1.0,
+                  dtype=np.float64) -> np.ndarray:
+    """theta[n, c] for token n (n_special leading rows are 0) and channel c; pair-duplicated (rope_3d.py:44)."""
+    td, hd, wd = rope3d_dims(head_dim)
+
+    def freqs(dim, length, base):
+        inv = 1.0 / (dtype(base) ** (np.arange(0, dim, 2, dtype=dtype) / dtype(dim)))
+        f = np.arange(length, dtype=dtype)[:, None] * inv[None, :]
+        return np.repeat(f, 2, axis=1)                         # (f0,f0,f1,f1,...)
+
+    tf = freqs(td, T, temporal_base * temporal_scale)
+    hf = freqs(hd, H, spatial_base)
+    wf = freqs(wd, W, spatial_base)
+    th = np.zeros((T, H, W, head_dim), dtype=dtype)
+    th[..., :td] = tf[:, None, None, :]
+    th[..., td:td + hd] = hf[None, :, None, :]
+    th[..., td + hd:] = wf[None, None, :, :]
+    th = th.reshape(T * H * W, head_dim)
+    if n_special:
+        th = np.concatenate([np.zeros((n_special, head_dim), dtype=dtype), th], axis=0)
+    return th
+
+
+def _rotate_half(x):
+    out = np.empty_like(x)
+    out[..., 0::2] = -x[..., 1::2]
+    out[..., 1::2] = x[..., 0::2]
+    return out
+
+
+def rope3d_apply(x: np.ndarray, cos: np.ndarray, sin: np.ndarray) -> np.ndarray:
+    """x [B, heads, N, Dh]; y = x*cos + rotate_half(x)*sin (rope_3d.py:240-246)."""
+    return x * cos[None, None] + _rotate_half(x) * sin[None, None]
+
+
+def rope3d_apply_backward(dy: np.ndarray, cos: np.ndarray, sin: np.ndarray) -> np.ndarray:
+    """Inverse rotation: dx = dy*cos - rotate_half(dy)*sin  (tables are pair-duplicated)."""
+    return dy * cos[None, None] - _rotate_half(dy) * sin[None, None]
+
+
+def rope3d_forward(q, k, T, H, W, n_special=0, **kw):
+    """Rope3D.forward incl. CLS auto-detect and the 'return unchanged on mismatch' branch (:208-221)."""
+    N, Dh = q.shape[2], q.shape[3]
+    if n_special == 0 and N == T * H * W + 1:
+        n_special = 1
+    if N != n_special + T * H * W:
+        return q, k
+    th = rope3d_angles(Dh, T, H, W, n_special, dtype=np.float64, **kw)
+    c, s = np.cos(th), np.sin(th)
+    return rope3d_apply(q, c, s), rope3d_apply(k, c, s)
+
+
+# ------------------------------------------------------------------------------------------------
+# AttentionPool (one learnable query, nn.MultiheadAttention algebra folded; eval / dropout = 0)
+# ------------------------------------------------------------------------------------------------
+def _layernorm(x, w, b, eps=1e-5):
+    mu = x.mean(-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(-1, keepdims=True)
+    xh = (x - mu) / np.sqrt(var + eps)
+    return xh * w + b, xh, 1.0 / np.sqrt(var + eps)
+
+
+def _layernorm_backward(dy, xh, rstd, w):
+    dxh = dy * w
+    D = xh.shape[-1]
+    dx = (dxh - dxh.mean(-1, keepdims=True) - xh * (dxh * xh).mean(-1, keepdims=True)) * rstd
+    return dx, (dy * xh).reshape(-1, D).sum(0), dy.reshape(-1, D).sum(0)
+
+
+def attention_pool_forward(x, params: dict, num_heads: int, mask=None, want_cache=False):
+    """x [B,N,D]; params: query(1,1,D), in_proj_weight(3D,D), in_proj_bias(3D), out_proj_weight(D,D),
+    out_proj_bias(D), norm_weight(D), norm_bias(D), optional proj_weight(O,D), proj_bias(O)."""
+    x = np.asarray(x, dtype=np.float64)
+    B, N, D = x.shape
+    Hn = num_heads
+    Dh = D // Hn
+    Wq, Wk, Wv = (np.asarray(params["in_proj_weight"], dtype=np.float64)[i * D:(i + 1) * D] for i in range(3))
+    bq, bk, bv = (np.asarray(params["in_proj_bias"], dtype=np.float64)[i * D:(i + 1) * D] for i in range(3))
+    query = np.asarray(params["query"], dtype=np.float64).reshape(D)
+    q0 = Wq @ query + bq                                              # [D]
+    scale = 1.0 / np.sqrt(Dh)
+    qt = np.stack([Wk[h * Dh:(h + 1) * Dh].T @ q0[h * Dh:(h + 1) * Dh] * scale for h in range(Hn)])   # [Hn, D]
+    beta = np.array([q0[h * Dh:(h + 1) * Dh] @ bk[h * Dh:(h + 1) * Dh] * scale for h in range(Hn)])
+    s = np.einsum("bnd,hd->bhn", x, qt) + beta[None, :, None]         # [B,Hn,N]
+    if mask is not None:
+        s = np.where(np.asarray(mask, dtype=bool)[:, None, :], -np.inf, s)
+    m = s.max(-1, keepdims=True)
+    e = np.exp(s - m)
+    a = e / e.sum(-1, keepdims=True)                                  # [B,Hn,N]
+    xbar = np.einsum("bhn,bnd->bhd", a, x)                            # [B,Hn,D]
+    o = np.stack([xbar[:, h] @ Wv[h * Dh:(h + 1) * Dh].T + bv[h * Dh:(h + 1) * Dh] for h in range(Hn)], 1)   # [B,Hn,Dh]
+    oc = o.reshape(B, D)
+    Wo = np.asarray(params["out_proj_weight"], dtype=np.float64)
+    bo = np.asarray(params["out_proj_bias"], dtype=np.float64)
+    y = oc @ Wo.T + bo
+    ln, xh, rstd = _layernorm(y, np.asarray(params["norm_weight"], np.float64), np.asarray(params["norm_bias"], np.float64))
+    out = ln
+    if "proj_weight" in params and params["proj_weight"] is not None:
+        out = ln @ np.asarray(params["proj_weight"], np.float64).T + np.asarray(params["proj_bias"], np.float64)
+    if want_cache:
+        return out, dict(x=x, a=a, xbar=xbar, qt=qt, q0=q0, oc=oc, xh=xh, rstd=rstd, ln=ln, query=query,
+                         Wq=Wq, Wk=Wk, Wv=Wv, Wo=Wo, scale=scale, Hn=Hn, Dh=Dh)
+    return out
+
+
+def attention_pool_backward(dout, cache: dict, params: dict) -> dict:
+    """Gradients w.r.t. x and every parameter."""
+    c = cache
+    x, a, xbar, qt, q0 = c["x"], c["a"], c["xbar"], c["qt"], c["q0"]
+    Hn, Dh, scale = c["Hn"], c["Dh"], c["scale"]
+    B, N, D = x.shape
+    g = {}
+    dln = np.asarray(dout, np.float64)
+    if "proj_weight" in params and params["proj_weight"] is not None:
+        Wp = np.asarray(params["proj_weight"], np.float64)
+        g["proj_weight"] = dln.T @ c["ln"]
+        g["proj_bias"] = dln.sum(0)
+        dln = dln @ Wp
+    dy, g["norm_weight"], g["norm_bias"] = _layernorm_backward(dln, c["xh"], c["rstd"], np.asarray(params["norm_weight"], np.float64))
+    g["out_proj_weight"] = dy.T @ c["oc"]
+    g["out_proj_bias"] = dy.sum(0)
+    do = (dy @ c["Wo"]).reshape(B, Hn, Dh)
+    dWv = np.zeros((D, D)); dbv = np.zeros(D); dWk = np.zeros((D, D)); dq0 = np.zeros(D)
+    dx = np.zeros_like(x)
+    for h in range(Hn):
+        sl = slice(h * Dh, (h + 1) * Dh)
+        dxbar = do[:, h] @ c["Wv"][sl]                                 # [B,D]
+        dWv[sl] = do[:, h].T @ xbar[:, h]
+        dbv[sl] = do[:, h].sum(0)
+        da = np.einsum("bd,bnd->bn", dxbar, x)
+        ds = a[:, h] * (da - (dxbar * xbar[:, h]).sum(-1, keepdims=True))
+        dx += a[:, h][:, :, None] * dxbar[:, None, :] + ds[:, :, None] * qt[h][None, None, :]
+        dqt = np.einsum("bn,bnd->d", ds, x)                            # [D]
+        dWk[sl] = np.outer(q0[sl], dqt) * scale
+        dq0[sl] = c["Wk"][sl] @ dqt * scale          # (+ bk term: ds sums to zero per row, so d beta contributes 0)
+    dWq = np.outer(dq0, c["query"])
+    g["in_proj_weight"] = np.concatenate([dWq, dWk, dWv], 0)
+    g["in_proj_bias"] = np.concatenate([dq0, np.zeros(D), dbv], 0)
+    g["query"] = (c["Wq"].T @ dq0).reshape(1, 1, D)
+    g["x"] = dx
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
+# Multi-view query pool (EnhancedVideoAggregator without its transformer blocks)
+# ------------------------------------------------------------------------------------------------
+def query_pool_forward(x, pos_encoding, ln_w, ln_b, attn_query, mask=None, want_cache=False):
+    """x [B,N,D] -> [B,D]: x + pos[:N]; LayerNorm; masked rows -> 0; softmax_n(q . x_n) (no 1/sqrt(D));
+    all-masked rows fall back to uniform over valid (=> zero output)."""
+    x = np.asarray(x, np.float64)
+    B, N, D = x.shape
+    if pos_encoding is not None:
+        x = x + np.asarray(pos_encoding, np.float64).reshape(-1, D)[None, :N]
+    ln, xh, rstd = _layernorm(x, np.asarray(ln_w, np.float64), np.asarray(ln_b, np.float64))
+    q = np.asarray(attn_query, np.float64).reshape(D)
+    if mask is not None:
+        mk = np.asarray(mask, bool)
+        ln = np.where(mk[..., None], 0.0, ln)
+    s = ln @ q                                                          # [B,N]
+    if mask is not None:
+        s = np.where(mk, -np.inf, s)
+        with np.errstate(invalid="ignore"):
+            m = s.max(-1, keepdims=True)
+            e = np.exp(s - m)
+            w = e / e.sum(-1, keepdims=True)
+        w = np.nan_to_num(w, nan=0.0, posinf=0.0, neginf=0.0)
+        bad = w.sum(-1, keepdims=True) <= 0
+        valid = (~mk).astype(np.float64)
+        fb = valid / np.maximum(valid.sum(-1, keepdims=True), 1e-6)
+        w = np.where(bad, fb, w)
+    else:
+        m = s.max(-1, keepdims=True)
+        e = np.exp(s - m)
+        w = e / e.sum(-1, keepdims=True)
+    out = np.einsum("bn,bnd->bd", w, ln)
+    if want_cache:
+        return out, dict(ln=ln, xh=xh, rstd=rstd, w=w, q=q, mask=None if mask is None else mk)
+    return out
+
+
+def query_pool_backward(dout, cache, ln_w):
+    c = cache
+    ln, w, q = c["ln"], c["w"], c["q"]
+    dout = np.asarray(dout, np.float64)
+    dw = np.einsum("bd,bnd->bn", dout, ln)
+    ds = w * (dw - (dw * w).sum(-1, keepdims=True))
+    if c["mask"] is not None:
+        allmasked = c["mask"].all(-1, keepdims=True)
+        ds = np.where(allmasked, 0.0, ds)
+    dln = w[..., None] * dout[:, None, :] + ds[..., None] * q[None, None, :]
+    dq = np.einsum("bn,bnd->d", ds, ln)
+    if c["mask"] is not None:
+        dln = np.where(c["mask"][..., None], 0.0, dln)
+    dx, dlw, dlb = _layernorm_backward(dln, c["xh"], c["rstd"], np.asarray(ln_w, np.float64))
+    return dict(x=dx, pos=dx.sum(0), ln_w=dlw, ln_b=dlb, attn_query=dq.reshape(1, 1, -1))

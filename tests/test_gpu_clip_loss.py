@@ -1,0 +1,119 @@
+"""GPU parity: fused CLIP / legacy / gated losses (through the module API -> C ABI -> sm_100a kernels) against
+the reference's golden vectors and the numpy oracle. Tolerances from BASELINE.json north_star:
+loss <= 1e-5 relative (fp32 accumulation), gradients <= 2e-3 (bf16 gradient operands)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import contrastive_oracle as co
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 2e-3
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def _run(mod, v, t, lt):
+    dev = torch.device("cuda:0")
+    v = torch.tensor(v, dtype=torch.float32, device=dev, requires_grad=True)
+    t = torch.tensor(t, dtype=torch.float32, device=dev, requires_grad=True)
+    lt = torch.tensor(np.asarray(lt, np.float32).reshape(1), device=dev, requires_grad=True)
+    loss = mod(video_features=v, text_features=t, log_temp=lt)
+    assert loss.ndim == 0 and loss.requires_grad and loss.device.type == "cuda"
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.item(), v.grad.cpu().numpy(), t.grad.cpu().numpy(), lt.grad.item()
+
+
+CASES = {
+    "clip_c1_b64_d512": ("CLIPLoss", {}),
+    "clip_ls_b48_d96": ("CLIPLoss", {"label_smoothing": 0.1}),
+    "clip_b300_d200": ("CLIPLoss", {}),
+    "contrastive_legacy_b32_d128": ("ContrastiveLoss", {}),
+    "gated_siglip_legacy_b40_d128": ("SiglipLoss", {}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_loss_matches_reference_golden(name):
+    from deepcoro_clip_b200 import loss as L
+    g = np.load(GOLDEN / f"{name}.npz")
+    cls, kw = CASES[name]
+    loss, dv, dt, dlt = _run(getattr(L, cls)(**kw), g["video"], g["text"], g["log_temp"])
+    ref = float(g["f32_loss"])
+    assert abs(loss - ref) <= LOSS_RTOL * abs(ref), (loss, ref)
+    assert _rel(dv, g["f32_dvideo"]) <= GRAD_RTOL
+    assert _rel(dt, g["f32_dtext"]) <= GRAD_RTOL
+    rlt = float(g["f32_dlog_temp"].reshape(-1)[0])
+    assert abs(dlt - rlt) <= GRAD_RTOL * max(abs(rlt), 1e-3)
+
+
+@pytest.mark.parametrize("N,D,tau,prec", [(64, 512, 0.07, "auto"), (1000, 512, 0.0588, "bf16x3"),
+                                           (1000, 512, 0.0588, "bf16"), (2048, 768, 0.0588, "bf16"),
+                                           (333, 100, 0.1, "auto")])
+def test_clip_vs_oracle(N, D, tau, prec):
+    from deepcoro_clip_b200.loss import CLIPLoss
+    rng = np.random.default_rng(N + D)
+    v = rng.standard_normal((N, D)).astype(np.float32)
+    t = (0.5 * v + rng.standard_normal((N, D))).astype(np.float32)      # correlated pairs: peaked diagonal
+    lt = math.log(tau)
+    loss, dv, dt, dlt = _run(CLIPLoss(precision=prec), v, t, lt)
+    o = co.clip_loss(v, t, lt)
+    # plain bf16 operands perturb each logit by ~1e-4/tau; the N-average keeps the loss within a few 1e-5
+    tol = LOSS_RTOL if prec != "bf16" else 1e-4
+    assert abs(loss - o["loss"]) <= tol * abs(o["loss"]), (loss, o["loss"])
+    gt = GRAD_RTOL if prec != "bf16" else 6e-3
+    assert _rel(dv, o["dvideo"]) <= gt
+    assert _rel(dt, o["dtext"]) <= gt
+    assert abs(dlt - o["dlog_temp"]) <= gt * max(abs(o["dlog_temp"]), 1e-3)
+
+
+def test_clip_no_grad_and_bf16_inputs():
+    from deepcoro_clip_b200.loss import CLIPLoss
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    v = torch.randn(256, 512, generator=g).to(dev)
+    t = torch.randn(256, 512, generator=g).to(dev)
+    lt = torch.tensor(math.log(0.07), device=dev)          # 0-d, no grad
+    with torch.no_grad():
+        l32 = CLIPLoss()(v, t, lt)
+        lbf = CLIPLoss()(v.bfloat16(), t.bfloat16(), lt)
+    o = co.clip_loss(v.cpu().numpy(), t.cpu().numpy(), math.log(0.07), want_grads=False)
+    assert abs(l32.item() - o["loss"]) <= LOSS_RTOL * o["loss"]
+    ob = co.clip_loss(v.bfloat16().float().cpu().numpy(), t.bfloat16().float().cpu().numpy(), math.log(0.07),
+                      want_grads=False)
+    assert abs(lbf.item() - ob["loss"]) <= LOSS_RTOL * ob["loss"]
+    with torch.autocast("cuda", dtype=torch.bfloat16):      # runner calls the loss under autocast (runner.py:1316)
+        la = CLIPLoss()(v, t, lt)
+    assert la.dtype == torch.float32 and abs(la.item() - l32.item()) < 1e-6
+
+
+def test_zero_rows_do_not_nan():
+    """F.normalize eps: an all-zero embedding row stays zero (reference 'sanitise to zeros' path)."""
+    from deepcoro_clip_b200.loss import CLIPLoss
+    dev = torch.device("cuda:0")
+    v = torch.randn(64, 128, device=dev)
+    t = torch.randn(64, 128, device=dev)
+    v[5] = 0
+    v.requires_grad_(True)
+    loss = CLIPLoss()(v, t, torch.tensor([math.log(0.07)], device=dev))
+    loss.backward()
+    o = co.clip_loss(v.detach().cpu().numpy(), t.cpu().numpy(), math.log(0.07), want_grads=False)
+    assert torch.isfinite(loss) and abs(loss.item() - o["loss"]) <= 1e-5 * o["loss"]
+    assert torch.isfinite(v.grad).all()
+
+
+def test_cpu_tensor_is_rejected():
+    from deepcoro_clip_b200.loss import CLIPLoss
+    from deepcoro_clip_b200._lib import B200ClipError
+    with pytest.raises(B200ClipError):
+        CLIPLoss()(torch.randn(4, 8), torch.randn(4, 8), torch.tensor(0.0))
