@@ -34,12 +34,14 @@ int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim
 }
 
 int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* x, int dtype, int64_t ldx, const float* inv_norm,
-                        const void* other_bf16, int ld_other, int other_rows, const float* usum, const float* dots,
-                        int gated, float gscale, float ocoef, float ucoef, const float* dev_omul,
-                        const float* dev_gmul, int rows, int dim, float* dx, int64_t lddx, void* stream) {
+                        const void* other_x, int other_dtype, int64_t ld_other_x, const float* other_inv_norm,
+                        const void* other_hi, int ld_other_hi, const float* diag_corr, const float* usum, float gscale,
+                        float ucoef, const float* dev_omul, const float* dev_gmul, int rows, int dim, float* dx,
+                        int64_t lddx, void* stream) {
   if (!dxhat || !x || !inv_norm || !dx) return B2_EINVAL;
-  return l2norm_bwd(dxhat, ldg, x, dtype, (long)ldx, inv_norm, other_bf16, ld_other, other_rows, usum, dots, gated,
-                    gscale, ocoef, ucoef, dev_omul, dev_gmul, rows, dim, dx, (long)lddx, S(stream));
+  return l2norm_bwd(dxhat, ldg, x, dtype, (long)ldx, inv_norm, other_x, other_dtype, (long)ld_other_x, other_inv_norm,
+                    other_hi, ld_other_hi, diag_corr, usum, gscale, ucoef, dev_omul, dev_gmul, rows, dim, dx,
+                    (long)lddx, S(stream));
 }
 
 int b200clip_colsum_bf16(const void* operand, int ld, int rows, int dim, float* out, void* stream) {
@@ -54,9 +56,11 @@ int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const i
 }
 
 int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                            float shift2, int gated, const float* dyn, float* rowsum, float* colsum, void* stream) {
+                            float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag,
+                            int diag_off, void* stream) {
   if (!A || !B || !rowsum || !colsum) return B2_EINVAL;
-  return logits_lse_fwd(A, B, Ma, Nb, Kp, lda, ldb, scale2, shift2, gated, dyn, rowsum, colsum, S(stream));
+  return logits_lse_fwd(A, B, Ma, Nb, Kp, lda, ldb, scale2, shift2, gated, dyn, rowsum, colsum, diag, diag_off,
+                        S(stream));
 }
 
 int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
@@ -65,13 +69,14 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
   return logits_dump(A, B, Ma, Nb, Kp, lda, ldb, out, ldo, max_ctas, S(stream));
 }
 
-int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
+int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off,
+                        int ldx, int ldy,
                         float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
-                        const float* colscale, float out_scale, const float* dyn, float* dX, int ldd, float* scal,
-                        int nseg_hint, void* stream) {
+                        const float* colscale, float out_scale, const float* dyn, float ydiag, int diag_off,
+                        float* diag_corr, float* dX, int ldd, float* scal, int nseg_hint, void* stream) {
   if (!X || !Y || !dX) return B2_EINVAL;
-  return logits_bwd(mode, X, Y, Nx, Ny, Kp, Dp, D, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c, rowscale,
-                    colscale, out_scale, dyn, dX, ldd, scal, nseg_hint, S(stream));
+  return logits_bwd(mode, X, Y, Nx, Ny, Kp, Dp, D, hi_off, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c, rowscale,
+                    colscale, out_scale, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal, nseg_hint, S(stream));
 }
 
 int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn,
@@ -84,6 +89,11 @@ int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, f
                           void* stream) {
   if (!sums || !dyn) return B2_EINVAL;
   return lse_finalize(sums, n, dyn, c, scale_out, acc, S(stream));
+}
+
+int b200clip_vec_fsum(const float* v, int n, int gated, double* acc, void* stream) {
+  if (!v || !acc) return B2_EINVAL;
+  return vec_fsum(v, n, gated, acc, S(stream));
 }
 
 int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots,

@@ -9,29 +9,32 @@ namespace b2host {
 // l2norm.cu
 int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out, int ldo, int Kp, int split3_role,
                float* inv_norm, float* xhat_f32, int ldh, cudaStream_t s);
-int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, const float* inv_norm, const void* oth,
-               int ldoth, int oth_rows, const float* usum, const float* dots, int gated, float gscale, float ocoef,
-               float ucoef, const float* dev_omul, const float* dev_gmul, int rows, int dim, float* dx, long lddx,
-               cudaStream_t s);
+int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, const float* inv_norm, const void* ox,
+               int odtype, long ldox, const float* oinv, const void* ohi, int ldohi, const float* dc,
+               const float* usum, float gscale, float ucoef, const float* dev_omul, const float* dev_gmul, int rows,
+               int dim, float* dx, long lddx, cudaStream_t s);
 int colsum_bf16(const void* xh, int ld, int rows, int dim, float* out, cudaStream_t s);
 int rowdot_bf16(const void* a, int lda, const void* b, int ldb, const long long* idx, int rows, int b_rows, int K,
                 float* out, cudaStream_t s);
 
 // logits_fwd.cu
 int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                   float shift2, int gated, const float* dyn, float* rowsum, float* colsum, cudaStream_t stream);
+                   float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag, int diag_off,
+                   cudaStream_t stream);
 int logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
                 int max_ctas, cudaStream_t stream);
 
 // logits_bwd.cu
-int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
+int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off, int ldx,
+               int ldy,
                float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
-               const float* colscale, float out_scale, const float* dyn, float* dX, int ldd, float* scal,
-               int nseg_hint, cudaStream_t stream);
+               const float* colscale, float out_scale, const float* dyn, float ydiag, int diag_off, float* diag_corr,
+               float* dX, int ldd, float* scal, int nseg_hint, cudaStream_t stream);
 
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
 int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s);
+int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s);
 int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots, double* acc,
              cudaStream_t s);
 

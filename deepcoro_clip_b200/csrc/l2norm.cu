@@ -2,8 +2,11 @@
 //   forward : xhat = x / max(||x||, 1e-12)   (F.normalize, utils/loss/contrastive.py:146-147)
 //             writes the bf16 MMA operand row [Kp] (zero padded to a multiple of 64) and 1/max(||x||,eps);
 //             split3 != 0 additionally writes the error-compensated K-concatenated operand
-//             [hi | second | third] so that  A3 . B3 = hi.hi + hi.lo + lo.hi  (bf16x3, ~fp32 accuracy):
-//             role 0 (A side): [hi | hi | lo], role 1 (B side): [hi | lo | hi].
+//             so that  A3 . B3 = lo.hi + hi.lo + hi.hi  (bf16x3, ~fp32 accuracy):
+//             role 0 (A side): [lo | hi | hi], role 1 (B side): [hi | lo | hi].  The hi panel is LAST in both
+//             (offset 2*Kp): the tensor core truncates its fp32 accumulator every K=16 step (measured bias
+//             ~ -0.25 ulp per step), so the small correction terms are accumulated first, while the
+//             accumulator is still small, and the dominant hi.hi term last.
 //   backward: dx = (g - (g . xhat) xhat) * inv_norm, with g = scale * dxhat + diag_coef * other_hat
 //             (the analytic diagonal / label-smoothing terms of the CLIP gradient are folded in here so the
 //             tile kernels never special-case the diagonal). SURVEY Appendix A.1.
@@ -46,54 +49,61 @@ l2norm_fwd_kernel(const T* __restrict__ x, long ldx, int rows, int dim, __nv_bfl
       o[c] = hi;
     } else {
       const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-      o[c] = hi;
+      o[c] = split3_role == 0 ? lo : hi;
       o[Kp + c] = split3_role == 0 ? hi : lo;
-      o[2 * Kp + c] = split3_role == 0 ? lo : hi;
+      o[2 * Kp + c] = hi;
     }
   }
 }
 
 // dx[r, :] = (g - (g . xh) xh) * inv_norm[r],  xh = x[r, :] * inv_norm[r] (exact fp32 from the caller's input),
-//   g = gmul * ( gscale * dxh[r, :] + (ocoef * omul * fp_r) * oth[r, :] + (ucoef * omul) * usum[:] )
-// omul / gmul are optional DEVICE scalars (1/tau from dyn_prep, upstream grad_output); fp_r = f'(dots[r]) for the
-// gated variant (f(s) = s sigmoid(s)), 1 otherwise. oth is the bf16 hi panel of the partner operand.
-template <typename T>
+//   g = gmul * ( gscale * dxh[r, :] + omul * (dc[r].res * yh + dc[r].gb * (yh - yhi)) + (ucoef * omul) * usum[:] )
+// where yh = ox[r, :] * oinv[r] is the exact fp32 partner row, yhi its bf16 hi panel and dc = {res, gb} the
+// diagonal correction written by logits_bwd: the tensor-core product used bf16(g_ii) * yhi for the target pair;
+// res = g_ii - bf16(g_ii) and gb = bf16(g_ii) restore g_ii * yh exactly (the dominant, cancellation-prone term).
+// omul / gmul are optional DEVICE scalars (1/tau from dyn_prep, upstream grad_output).
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float* __restrict__ dxh, int ldg, const T* __restrict__ x, long ldx,
-                  const float* __restrict__ inv_norm, const __nv_bfloat16* __restrict__ oth, int ldoth, int oth_rows,
-                  const float* __restrict__ usum, const float* __restrict__ dots, int gated, float gscale, float ocoef,
-                  float ucoef, const float* __restrict__ dev_omul, const float* __restrict__ dev_gmul, int rows, int dim,
+                  const float* __restrict__ inv_norm, const TO* __restrict__ ox, long ldox,
+                  const float* __restrict__ oinv, const __nv_bfloat16* __restrict__ ohi, int ldohi,
+                  const float2* __restrict__ dc, const float* __restrict__ usum, float gscale, float ucoef,
+                  const float* __restrict__ dev_omul, const float* __restrict__ dev_gmul, int rows, int dim,
                   float* __restrict__ dx, long lddx) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float omul = dev_omul ? dev_omul[0] : 1.f;
   const float gmul = dev_gmul ? dev_gmul[0] : 1.f;
-  float fpr = 1.f;
-  if (gated && dots) {
-    const float sdot = dots[warp];
-    const float sig = 1.f / (1.f + __expf(-sdot));
-    fpr = sig * (1.f + sdot * (1.f - sig));
+  const bool has_dc = dc != nullptr && ox != nullptr;
+  float res = 0.f, gb = 0.f, oi = 0.f;
+  if (has_dc) {
+    const float2 d = dc[warp];
+    res = d.x * omul;
+    gb = d.y * omul;
+    oi = oinv[warp];
   }
-  const bool has_oth = oth != nullptr && warp < oth_rows && ocoef != 0.f;
-  const float oc = ocoef * omul * fpr, uc = ucoef * omul;
+  const float uc = ucoef * omul;
   const float* g = dxh + (size_t)warp * ldg;
   const T* xr = x + (size_t)warp * ldx;
   const float inv = inv_norm[warp];
-  float dot = 0.f;
-  for (int c = lane; c < dim; c += 32) {
+  auto gval = [&](int c) {
     float gv = gscale * g[c];
-    if (has_oth) gv = fmaf(oc, __bfloat162float(oth[(size_t)warp * ldoth + c]), gv);
+    if (has_dc) {
+      const float yh = to_f32<TO>(ox[(size_t)warp * ldox + c]) * oi;
+      const float yhi = __bfloat162float(ohi[(size_t)warp * ldohi + c]);
+      gv = fmaf(res, yh, gv);
+      gv = fmaf(gb, yh - yhi, gv);
+    }
     if (usum) gv = fmaf(uc, usum[c], gv);
-    dot = fmaf(gv, to_f32<T>(xr[c]) * inv, dot);
-  }
+    return gv;
+  };
+  float dot = 0.f;
+  for (int c = lane; c < dim; c += 32) dot = fmaf(gval(c), to_f32<T>(xr[c]) * inv, dot);
   dot = warp_sum(dot);
   for (int c = lane; c < dim; c += 32) {
-    float gv = gscale * g[c];
-    if (has_oth) gv = fmaf(oc, __bfloat162float(oth[(size_t)warp * ldoth + c]), gv);
-    if (usum) gv = fmaf(uc, usum[c], gv);
     const float xv = to_f32<T>(xr[c]) * inv;
-    dx[(size_t)warp * lddx + c] = gmul * (gv - dot * xv) * inv;
+    dx[(size_t)warp * lddx + c] = gmul * (gval(c) - dot * xv) * inv;
   }
 }
 
@@ -149,20 +159,35 @@ int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out,
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
-int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, const float* inv_norm, const void* oth,
-               int ldoth, int oth_rows, const float* usum, const float* dots, int gated, float gscale, float ocoef,
-               float ucoef, const float* dev_omul, const float* dev_gmul, int rows, int dim, float* dx, long lddx,
-               cudaStream_t s) {
-  if (rows <= 0 || dim <= 0) return B2_EINVAL;
+template <typename T>
+static int l2norm_bwd_t(const float* dxh, int ldg, const T* x, long ldx, const float* inv_norm, const void* ox,
+                        int odtype, long ldox, const float* oinv, const __nv_bfloat16* ohi, int ldohi, const float2* dc,
+                        const float* usum, float gscale, float ucoef, const float* dev_omul, const float* dev_gmul,
+                        int rows, int dim, float* dx, long lddx, cudaStream_t s) {
   const int blocks = (rows + 7) / 8;
-  auto o = (const __nv_bfloat16*)oth;
-  switch (dtype) {
-    case 0: l2norm_bwd_kernel<float><<<blocks, 256, 0, s>>>(dxh, ldg, (const float*)x, ldx, inv_norm, o, ldoth, oth_rows, usum, dots, gated, gscale, ocoef, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
-    case 1: l2norm_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(dxh, ldg, (const __nv_bfloat16*)x, ldx, inv_norm, o, ldoth, oth_rows, usum, dots, gated, gscale, ocoef, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
-    case 2: l2norm_bwd_kernel<__half><<<blocks, 256, 0, s>>>(dxh, ldg, (const __half*)x, ldx, inv_norm, o, ldoth, oth_rows, usum, dots, gated, gscale, ocoef, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
+  switch (ox ? odtype : 0) {
+    case 0: l2norm_bwd_kernel<T, float><<<blocks, 256, 0, s>>>(dxh, ldg, x, ldx, inv_norm, (const float*)ox, ldox, oinv, ohi, ldohi, dc, usum, gscale, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
+    case 1: l2norm_bwd_kernel<T, __nv_bfloat16><<<blocks, 256, 0, s>>>(dxh, ldg, x, ldx, inv_norm, (const __nv_bfloat16*)ox, ldox, oinv, ohi, ldohi, dc, usum, gscale, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
+    case 2: l2norm_bwd_kernel<T, __half><<<blocks, 256, 0, s>>>(dxh, ldg, x, ldx, inv_norm, (const __half*)ox, ldox, oinv, ohi, ldohi, dc, usum, gscale, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx); break;
     default: return B2_EINVAL;
   }
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, const float* inv_norm, const void* ox,
+               int odtype, long ldox, const float* oinv, const void* ohi, int ldohi, const float* dc,
+               const float* usum, float gscale, float ucoef, const float* dev_omul, const float* dev_gmul, int rows,
+               int dim, float* dx, long lddx, cudaStream_t s) {
+  if (rows <= 0 || dim <= 0) return B2_EINVAL;
+  if (dc && (!ox || !oinv || !ohi)) return B2_EINVAL;
+  auto h = (const __nv_bfloat16*)ohi;
+  auto d2 = (const float2*)dc;
+  switch (dtype) {
+    case 0: return l2norm_bwd_t<float>(dxh, ldg, (const float*)x, ldx, inv_norm, ox, odtype, ldox, oinv, h, ldohi, d2, usum, gscale, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx, s);
+    case 1: return l2norm_bwd_t<__nv_bfloat16>(dxh, ldg, (const __nv_bfloat16*)x, ldx, inv_norm, ox, odtype, ldox, oinv, h, ldohi, d2, usum, gscale, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx, s);
+    case 2: return l2norm_bwd_t<__half>(dxh, ldg, (const __half*)x, ldx, inv_norm, ox, odtype, ldox, oinv, h, ldohi, d2, usum, gscale, ucoef, dev_omul, dev_gmul, rows, dim, dx, lddx, s);
+    default: return B2_EINVAL;
+  }
 }
 
 int colsum_bf16(const void* xh, int ld, int rows, int dim, float* out, cudaStream_t s) {

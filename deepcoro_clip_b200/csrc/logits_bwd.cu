@@ -41,6 +41,10 @@ struct BwParams {
   int Kp;              // K of the S product (multiple of 64; 3*Dp in bf16x3 mode)
   int Dp;              // padded width of the hi panel (multiple of 64): out-product columns come from Y[:, :Dp]
   int D;               // valid output columns
+  int hi_off;          // column offset of the hi panel inside Y (0 plain bf16, 2*Dp in bf16x3 mode)
+  float ydiag;         // CLIP: subtracted from G where (row + diag_off == column) BEFORE the bf16 rounding, so the
+  int diag_off;        //   diagonal target (1-eps)/N cancels against P_ii(...) at full precision; 0 disables
+  float* diag_corr;    // optional [Nx][2]: {g_ii - bf16(g_ii), bf16(g_ii)} for the fp32 fix-up in l2norm_bwd
   int x_tiles, y_tiles, dparts, nseg;
   float scale2, shift2;        // CLIP: P = 2^(f(S)*scale2 - shift2)
   float inv_tau, bias, wneg_c; // SigLIP: R = S*inv_tau + bias ; G = wneg_c * sigmoid(clamp R) * [|R|<=30]
@@ -142,7 +146,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
           mbar_wait(&empty_bar[slot], phase ^ 1);
           uint8_t* sy = smem + slot * BW_SLOT_BYTES;
           mbar_expect_tx(&full_bar[slot], BW_CHUNK);
-          tma_load_2d(sy, &tmY, &full_bar[slot], dp * BW_DP + dc * BW_BK, j * BW_BN);
+          tma_load_2d(sy, &tmY, &full_bar[slot], p.hi_off + dp * BW_DP + dc * BW_BK, j * BW_BN);
           if (++slot == BW_SLOTS) { slot = 0; phase ^= 1; }
         }
       };
@@ -249,6 +253,10 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
           named_bar_sync(1, 256);
         }
         const bool full = (xt * BW_BM + BW_BM <= p.Nx) && (j * BW_BN + BW_BN <= p.Ny);
+        // does the target diagonal cross this tile? (block-uniform)
+        const int dlo = xt * BW_BM + p.diag_off - j * BW_BN;
+        const bool has_diag = kMode != BW_SIGLIP && p.ydiag != 0.f && dlo > -BW_BM && dlo < BW_BN;
+        const int dcol = row + p.diag_off - j * BW_BN - wg * 64;   // diagonal column relative to this thread's half
         mbar_wait(&sfull_bar[buf], (tile_ctr >> 1) & 1);
         tc_fence_after();
         const uint32_t sbase = tmem_base + lane_off + s_col0 + buf * BW_BN + wg * 64;
@@ -290,9 +298,15 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 }
                 const float pr = ex2_approx(fmaf(f, p.scale2, -p.shift2));
                 g = pr * (rs + cs[cl]);
+                if (has_diag && (c * 32 + e + h) == dcol) g -= p.ydiag;
                 if (!full && !(row_ok && (j * BW_BN + cl) < p.Ny)) g = 0.f;
                 tacc = fmaf(g, f, tacc);
                 if (kMode == BW_GATED) g *= fp;
+                if (has_diag && (c * 32 + e + h) == dcol && dp == 0 && row_ok && p.diag_corr) {
+                  const float gb = __bfloat162float(__float2bfloat16_rn(g));
+                  p.diag_corr[2 * row] = g - gb;
+                  p.diag_corr[2 * row + 1] = gb;
+                }
               }
               g2[h] = g;
             }
@@ -360,15 +374,17 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
 namespace b2host {
 using namespace b2;
 
-int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
+int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off, int ldx,
+               int ldy,
                float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
-               const float* colscale, float out_scale, const float* dyn, float* dX, int ldd, float* scal,
-               int nseg_hint, cudaStream_t stream) {
-  if (Nx <= 0 || Ny <= 0 || Kp <= 0 || Kp % 64 || Dp <= 0 || Dp % 64 || Dp > Kp || D > Dp || D <= 0)
+               const float* colscale, float out_scale, const float* dyn, float ydiag, int diag_off, float* diag_corr,
+               float* dX, int ldd, float* scal, int nseg_hint, cudaStream_t stream) {
+  if (Nx <= 0 || Ny <= 0 || Kp <= 0 || Kp % 64 || Dp <= 0 || Dp % 64 || hi_off < 0 || hi_off % 64 ||
+      hi_off + Dp > Kp || D > Dp || D <= 0)
     return B2_EINVAL;
   if (mode != BW_SIGLIP && (!rowscale || !colscale)) return B2_EINVAL;
   BwParams p;
-  p.Nx = Nx; p.Ny = Ny; p.Kp = Kp; p.Dp = Dp; p.D = D;
+  p.Nx = Nx; p.Ny = Ny; p.Kp = Kp; p.Dp = Dp; p.D = D; p.hi_off = hi_off; p.ydiag = ydiag; p.diag_off = diag_off; p.diag_corr = diag_corr;
   p.x_tiles = (Nx + BW_BM - 1) / BW_BM;
   p.y_tiles = (Ny + BW_BN - 1) / BW_BN;
   p.dparts = (Dp + BW_DP - 1) / BW_DP;

@@ -19,6 +19,8 @@ struct LseParams {
   float* colsum;   // [Nb] += sum_i P_ij
   int gated;       // 1: f(s) = s * sigmoid(s) (legacy "siglip" gating), 0: f(s) = s
   const float* dyn;   // optional device block from dyn_prep (overrides scale2 / shift2): no host sync on tau
+  float* diag;        // optional [Ma]: diag[i] = S[i, i + diag_off] exactly as the tensor core produced it, so the
+  int diag_off;       //   target logit and the row/column LSE share the same rounding (they cancel in the loss)
 };
 
 template <bool kGated>
@@ -49,6 +51,15 @@ struct LseEpi {
   }
   __device__ static __forceinline__ void chunk(State& st, const Params& p, const TeCtx& ctx, int c,
                                                const uint32_t (&acc)[32]) {
+    if (p.diag) {
+      const int d = ctx.row + p.diag_off - (ctx.col0 + c * 32);
+      if (d >= 0 && d < 32 && ctx.row_ok) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v = (e == d) ? acc[e] : v;
+        p.diag[ctx.row] = __uint_as_float(v);
+      }
+    }
     if (ctx.full) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
@@ -153,8 +164,9 @@ static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int l
 }
 
 int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                   float shift2, int gated, const float* dyn, float* rowsum, float* colsum, cudaStream_t stream) {
-  LseParams p{scale2, shift2, rowsum, colsum, gated, dyn};
+                   float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag, int diag_off,
+                   cudaStream_t stream) {
+  LseParams p{scale2, shift2, rowsum, colsum, gated, dyn, diag, diag_off};
   if (gated) return launch_te<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
   return launch_te<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
 }

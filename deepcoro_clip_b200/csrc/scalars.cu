@@ -58,6 +58,25 @@ lse_finalize_kernel(const float* __restrict__ sums, int n, const float* __restri
   }
 }
 
+// acc += sum_i f(v[i])
+__global__ void __launch_bounds__(256)
+vec_fsum_kernel(const float* __restrict__ v, int n, int gated, double* __restrict__ acc) {
+  double t = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double s = (double)v[i];
+    t += gated ? s / (1.0 + exp(-s)) : s;
+  }
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double u = 0.0;
+    for (int w = 0; w < 8; ++w) u += sh[w];
+    atomicAdd(acc, u);
+  }
+}
+
 // acc += sum_r f(a[r,:K] . b[r,:K]),  f = identity or s*sigmoid(s);  optionally stores the raw dots
 __global__ void __launch_bounds__(256)
 diag_sum_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b, int ldb, int rows,
@@ -104,6 +123,14 @@ int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bo
 int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s) {
   if (n <= 0) return B2_EINVAL;
   lse_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(sums, n, dyn, c, scale_out, acc);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s) {
+  if (n <= 0) return B2_EINVAL;
+  int blocks = (n + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  vec_fsum_kernel<<<blocks, 256, 0, s>>>(v, n, gated, acc);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

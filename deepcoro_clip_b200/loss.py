@@ -83,7 +83,8 @@ class _ClipLossFn(torch.autograd.Function):
 
         rowsum = torch.zeros(B, dtype=torch.float32, device=dev)
         colsum = torch.zeros(N, dtype=torch.float32, device=dev)
-        ops.lse_fwd(vop, tall, B, N, K, dyn, gated, rowsum, colsum)
+        dots = torch.empty(B, dtype=torch.float32, device=dev)      # S_ii as the tensor core rounded it
+        ops.lse_fwd(vop, tall, B, N, K, dyn, gated, rowsum, colsum, dots, rank * B)
         if W > 1:
             dist.all_reduce(colsum, group=group)
             rowsum_all = _all_gather_rows(rowsum, W, group)
@@ -96,30 +97,31 @@ class _ClipLossFn(torch.autograd.Function):
         colscale_all = torch.empty(N, dtype=torch.float32, device=dev)
         ops.lse_finalize(rowsum_all, dyn, c, rowscale_all, acc[0:1])
         ops.lse_finalize(colsum, dyn, c, colscale_all, acc[1:2])
-        dots = torch.empty(B, dtype=torch.float32, device=dev) if gated else None
-        ops.diag_sum(vop, top, B, K, gated, dots, acc[2:3])
+        ops.vec_fsum(dots, gated, acc[2:3])
         if W > 1:
             dist.all_reduce(acc[2:3], group=group)
         inv_tau = dyn[2].double()
         sum_tgt = (1.0 - eps) * acc[2] * inv_tau
+        unif_tgt = torch.zeros((), dtype=torch.float64, device=dev)
         vsum = tsum = None
         if eps != 0.0:
             if gated:
                 raise B200ClipError("label_smoothing is not defined for the gated legacy loss")
-            vsum = ops.colsum_bf16(vall, N, D)
-            tsum = ops.colsum_bf16(tall, N, D)
-            sum_tgt = sum_tgt + (eps / N) * torch.dot(vsum.double(), tsum.double()) * inv_tau
+            vsum = ops.colsum_bf16(vall[:, K - Kp:], N, D)      # hi panel (last in bf16x3 mode)
+            tsum = ops.colsum_bf16(tall[:, K - Kp:], N, D)
+            unif_tgt = (eps / N) * torch.dot(vsum.double(), tsum.double()) * inv_tau
+            sum_tgt = sum_tgt + unif_tgt
         loss = (0.5 / N) * (acc[0] + acc[1]) - sum_tgt / N
 
         ctx.save_for_backward(video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, dots,
-                              vsum, tsum, sum_tgt)
+                              vsum, tsum, unif_tgt)
         ctx.cfg = (B, D, Kp, K, W, rank, N, eps, mode, group, log_temp.shape, log_temp.dtype)
         return loss.float()
 
     @staticmethod
     def backward(ctx, grad_out):
         (video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, dots, vsum, tsum,
-         sum_tgt) = ctx.saved_tensors
+         unif_tgt) = ctx.saved_tensors
         B, D, Kp, K, W, rank, N, eps, mode, group, lt_shape, lt_dtype = ctx.cfg
         dev = video.device
         gmul = grad_out.detach().reshape(1).float().contiguous()
@@ -129,23 +131,28 @@ class _ClipLossFn(torch.autograd.Function):
         need_lt = ctx.needs_input_grad[2]
         if ctx.needs_input_grad[0] or need_lt:
             dVh = torch.zeros((B, D), dtype=torch.float32, device=dev)
-            ops.logits_bwd(mode, vop, tall, B, N, K, Kp, D, dyn, rowscale_all[lo:hi], colscale_all, dVh, scal)
+            dcv = torch.zeros((B, 2), dtype=torch.float32, device=dev)
+            ops.logits_bwd(mode, vop, tall, B, N, K, Kp, D, dyn, rowscale_all[lo:hi], colscale_all, dVh, scal,
+                           ydiag=(1.0 - eps) / N, diag_off=lo, diag_corr=dcv)
             if ctx.needs_input_grad[0]:
-                dV = ops.l2norm_backward(dVh, video, vinv, other=top, other_rows=B, usum=tsum, dots=dots,
-                                         gated=(mode == BW_GATED), ocoef=-(1.0 - eps) / N, ucoef=-eps / (N * N),
-                                         dev_omul=dyn[2:3], dev_gmul=gmul).to(video.dtype)
+                dV = ops.l2norm_backward(dVh, video, vinv, other_x=text, other_inv=tinv, other_hi=top[:, K - Kp:],
+                                         diag_corr=dcv, usum=tsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3],
+                                         dev_gmul=gmul).to(video.dtype)
         if ctx.needs_input_grad[1]:
             dTh = torch.zeros((B, D), dtype=torch.float32, device=dev)
-            ops.logits_bwd(mode, top, vall, B, N, K, Kp, D, dyn, colscale_all[lo:hi], rowscale_all, dTh, None)
-            dT = ops.l2norm_backward(dTh, text, tinv, other=vop, other_rows=B, usum=vsum, dots=dots,
-                                     gated=(mode == BW_GATED), ocoef=-(1.0 - eps) / N, ucoef=-eps / (N * N),
-                                     dev_omul=dyn[2:3], dev_gmul=gmul).to(text.dtype)
+            dct = torch.zeros((B, 2), dtype=torch.float32, device=dev)
+            ops.logits_bwd(mode, top, vall, B, N, K, Kp, D, dyn, colscale_all[lo:hi], rowscale_all, dTh, None,
+                           ydiag=(1.0 - eps) / N, diag_off=lo, diag_corr=dct)
+            dT = ops.l2norm_backward(dTh, text, tinv, other_x=video, other_inv=vinv, other_hi=vop[:, K - Kp:],
+                                     diag_corr=dct, usum=vsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3],
+                                     dev_gmul=gmul).to(text.dtype)
         if need_lt:
             s0 = scal[0:1].double()
             if W > 1:
                 dist.all_reduce(s0, group=group)
             # d loss / d log_temp = -sum_ij G_ij L_ij  (zero while the tau clamp is active)
-            dlt = (sum_tgt / N - s0 * dyn[2].double()) * dyn[7].double() * gmul.double()
+            # (the kernel's sum already contains the diagonal target; only the uniform label-smoothing part is added)
+            dlt = (unif_tgt / N - s0 * dyn[2].double()) * dyn[7].double() * gmul.double()
             dLT = dlt.to(lt_dtype).reshape(lt_shape)
         return dV, dT, dLT, None, None, None, None, None, None
 

@@ -53,13 +53,16 @@ def l2norm_operand(x: torch.Tensor, split3_role: int = -1):
     return op, inv, Kp
 
 
-def l2norm_backward(dxhat, x, inv_norm, *, other=None, other_rows=0, usum=None, dots=None, gated=False, gscale=1.0,
-                    ocoef=0.0, ucoef=0.0, dev_omul=None, dev_gmul=None):
+def l2norm_backward(dxhat, x, inv_norm, *, other_x=None, other_inv=None, other_hi=None, diag_corr=None, usum=None,
+                    gscale=1.0, ucoef=0.0, dev_omul=None, dev_gmul=None):
     x = _rowmajor(x)
     rows, dim = x.shape
     dx = torch.empty((rows, dim), dtype=torch.float32, device=x.device)
-    call("l2norm_bwd", dxhat, dxhat.stride(0), x, DTYPE_CODE[x.dtype], i64(x.stride(0)), inv_norm, other,
-         other.stride(0) if other is not None else 0, other_rows, usum, dots, int(gated), float(gscale), float(ocoef),
+    if other_x is not None:
+        other_x = _rowmajor(other_x)
+    call("l2norm_bwd", dxhat, dxhat.stride(0), x, DTYPE_CODE[x.dtype], i64(x.stride(0)), inv_norm, other_x,
+         DTYPE_CODE[other_x.dtype] if other_x is not None else 0, i64(other_x.stride(0) if other_x is not None else 0),
+         other_inv, other_hi, other_hi.stride(0) if other_hi is not None else 0, diag_corr, usum, float(gscale),
          float(ucoef), dev_omul, dev_gmul, rows, dim, dx, i64(dim), stream_ptr(x.device))
     return dx
 
@@ -72,9 +75,13 @@ def dyn_prep(log_temp: torch.Tensor, bias, clamp_min: float, bound: float) -> to
     return dyn
 
 
-def lse_fwd(A, B, Ma, Nb, K, dyn, gated, rowsum, colsum):
+def lse_fwd(A, B, Ma, Nb, K, dyn, gated, rowsum, colsum, diag=None, diag_off=0, diag_corr=None):
     call("logits_lse_fwd", A, B, Ma, Nb, K, A.stride(0), B.stride(0), 0.0, 0.0, int(gated), dyn, rowsum, colsum,
-         stream_ptr(A.device))
+         diag, int(diag_off), stream_ptr(A.device))
+
+
+def vec_fsum(v, gated, acc_slot):
+    call("vec_fsum", v, v.numel(), int(gated), acc_slot, stream_ptr(v.device))
 
 
 def lse_finalize(sums, dyn, c, scale_out, acc_slot):
@@ -91,6 +98,7 @@ def colsum_bf16(op, rows, dim):
     return out
 
 
-def logits_bwd(mode, X, Y, Nx, Ny, K, Dp, D, dyn, rowscale, colscale, dX, scal, *, wneg_c=0.0, nseg=0):
-    call("logits_bwd", mode, X, Y, Nx, Ny, K, Dp, D, X.stride(0), Y.stride(0), 0.0, 0.0, 0.0, 0.0, float(wneg_c),
-         rowscale, colscale, 0.0, dyn, dX, dX.stride(0), scal, nseg, stream_ptr(X.device))
+def logits_bwd(mode, X, Y, Nx, Ny, K, Dp, D, dyn, rowscale, colscale, dX, scal, *, wneg_c=0.0, nseg=0, ydiag=0.0,
+               diag_off=0, diag_corr=None):
+    call("logits_bwd", mode, X, Y, Nx, Ny, K, Dp, D, K - Dp, X.stride(0), Y.stride(0), 0.0, 0.0, 0.0, 0.0, float(wneg_c),
+         rowscale, colscale, 0.0, dyn, float(ydiag), int(diag_off), diag_corr, dX, dX.stride(0), scal, nseg, stream_ptr(X.device))

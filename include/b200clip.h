@@ -42,21 +42,25 @@ int b200clip_sm_count(void);
  *      utils/retrieval_metrics_streaming.py:130-131).
  *   x [rows, dim] (row pitch ldx elements, dtype code) -> operand [rows, ld_out] bf16, inv_norm [rows] fp32
  *   (= 1 / max(||x||, 1e-12)), optional xhat_f32 [rows, ld_hat] fp32 (may be NULL).
- *   split3_role: -1 plain bf16 operand; 0 / 1 = A-side / B-side panels of the bf16x3 compensated product.
+ *   split3_role: -1 plain bf16 operand; 0 / 1 = A-side [lo|hi|hi] / B-side [hi|lo|hi] panels of the bf16x3
+ *   compensated product (small terms first: the tensor core truncates its fp32 accumulator each K step).
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim, void* operand, int ld_out,
                         int Kp, int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, void* stream);
 
-/* K4  normalise backward (autograd of F.normalize) fused with the analytic rank-sparse gradient terms:
- *   g  = gmul * ( gscale * dxhat[r] + (ocoef * omul * fp_r) * other_hat[r] + (ucoef * omul) * usum )
+/* K4  normalise backward (autograd of F.normalize) fused with the rank-sparse gradient corrections:
+ *   g  = gmul * ( gscale * dxhat[r] + omul * (res_r * yh_r + gb_r * (yh_r - yhi_r)) + (ucoef * omul) * usum )
  *   dx = (g - (g . xhat) xhat) * inv_norm,   xhat = x * inv_norm (recomputed in fp32 from the caller's input)
- *   other_bf16: hi panel of the partner operand (diagonal target term of the CLIP gradient), usum: column sum
- *   of the partner operand (label smoothing), dots/gated: fp_r = f'(dots[r]) for the gated legacy variant.
- *   dev_omul / dev_gmul: optional DEVICE scalars (1/tau inside dyn, upstream grad_output). dx fp32 [rows, lddx]. */
+ *   yh_r = other_x[r] * other_inv_norm[r] is the exact fp32 partner (target) row, yhi_r = other_hi[r] its bf16 hi
+ *   panel, diag_corr[r] = {res_r, gb_r} as written by b200clip_logits_bwd: the tensor-core product contributed
+ *   bf16(g_rr) * yhi_r for the target pair, this restores g_rr * yh_r in fp32. usum: column sum of the partner
+ *   operand (label smoothing). other_x / diag_corr / usum may be NULL. dev_omul / dev_gmul: optional DEVICE scalars
+ *   (1/tau inside dyn, upstream grad_output). dx fp32 [rows, lddx]. */
 int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* x, int dtype, int64_t ldx, const float* inv_norm,
-                        const void* other_bf16, int ld_other, int other_rows, const float* usum, const float* dots,
-                        int gated, float gscale, float ocoef, float ucoef, const float* dev_omul,
-                        const float* dev_gmul, int rows, int dim, float* dx, int64_t lddx, void* stream);
+                        const void* other_x, int other_dtype, int64_t ld_other_x, const float* other_inv_norm,
+                        const void* other_hi, int ld_other_hi, const float* diag_corr, const float* usum, float gscale,
+                        float ucoef, const float* dev_omul, const float* dev_gmul, int rows, int dim, float* dx,
+                        int64_t lddx, void* stream);
 
 /* out[c] += sum_r operand[r, c]  (label-smoothing helper; out must be zeroed by the caller) */
 int b200clip_colsum_bf16(const void* operand, int ld, int rows, int dim, float* out, void* stream);
@@ -72,9 +76,12 @@ int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const i
  *   rowsum[i] += sum_j P_ij, colsum[j] += sum_i P_ij (fp32, caller zeroes them). S is never stored.
  *   dyn (may be NULL): device float[16] written by b200clip_dyn_prep; when given, scale2/shift2 are read from
  *   it on the device, so a learnable temperature never forces a host synchronisation.
+ *   diag (may be NULL): diag[i] = S[i, i + diag_off] as produced by the tensor core (the target logit of row i;
+ *   diag_off = rank * B_local under DDP), so target and LSE share one rounding and cancel in the loss.
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                            float shift2, int gated, const float* dyn, float* rowsum, float* colsum, void* stream);
+                            float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag,
+                            int diag_off, void* stream);
 
 /* Validation hook: out[i, j] = S_ij (fp32, row pitch ldo) computed by the same tcgen05 tile engine.
  * max_ctas > 0 limits the grid (exercises the multi-tile-per-CTA schedule). Used by the tests only. */
@@ -88,16 +95,20 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
  *     mode 0 (CLIP)   : G = 2^(S*scale2 - shift2) * (rowscale[i] + colscale[j])
  *     mode 1 (gated)  : same with f(S) = S*sigmoid(S) inside the exponent and G *= f'(S)
  *     mode 2 (SigLIP) : R = S*inv_tau + bias, G = wneg_c * sigmoid(clamp(R,+-30)) * [|R| <= 30]
- *     (diagonal targets / positives are rank-sparse corrections applied by other entry points.)
- *   X [Nx, >=Kp], Y [Ny, >=Kp] operands; Dp = padded width of the hi panel (columns of Y used for the
- *   output product), D = valid output columns; dX fp32 [Nx, ldd] accumulated atomically (caller zeroes).
+ *     modes 0/1: G_ij -= ydiag where i + diag_off == j (the (1-eps)/N diagonal target, subtracted in fp32 before G
+ *     is rounded to bf16; diag_off = rank * B_local under DDP); diag_corr (may be NULL) receives per row
+ *     {g_ii - bf16(g_ii), bf16(g_ii)} for b200clip_l2norm_bwd. SigLIP positives are rank-sparse corrections applied
+ *     by b200clip_siglip_pos.
+ *   X [Nx, >=Kp], Y [Ny, >=Kp] operands; Dp = padded width of the hi panel (columns Y[:, hi_off:hi_off+Dp] feed
+ *   the output product; hi_off = 0 for plain bf16 operands, 2*Dp in bf16x3 mode), D = valid output columns; dX fp32 [Nx, ldd] accumulated atomically (caller zeroes).
  *   scal (may be NULL): [0] += sum G*f(S)  [1] += sum softplus(L) (mode 2)  [2] += sum G (mode 2).
  *   nseg_hint <= 0 lets the library pick the split of the Y sweep.
  * ------------------------------------------------------------------------------------------------ */
-int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx,
-                        int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
-                        const float* rowscale, const float* colscale, float out_scale, const float* dyn, float* dX,
-                        int ldd, float* scal, int nseg_hint, void* stream);
+int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off,
+                        int ldx, int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
+                        const float* rowscale, const float* colscale, float out_scale, const float* dyn, float ydiag,
+                        int diag_off, float* diag_corr, float* dX, int ldd, float* scal, int nseg_hint,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Device-side scalar plumbing (no host sync on log_temp / bias).
@@ -111,6 +122,8 @@ int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min,
                       void* stream);
 int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc,
                           void* stream);
+/* acc[0] += sum_i f(v[i]) in double, f = identity (gated = 0) or s*sigmoid(s) (gated = 1) */
+int b200clip_vec_fsum(const float* v, int n, int gated, double* acc, void* stream);
 int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots,
                       double* acc, void* stream);
 
