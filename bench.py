@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native contrastive head.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workloads (BASELINE.json):
+  clip32k  (default)  CLIP InfoNCE loss fwd+bwd, global batch N=32,768, D=512 (the configuration the metric
+                      "contrastive loss fwd+bwd samples/s @B=32k,D=512" is quoted on), bf16 operands / fp32 accumulate.
+                      N GPUs: STRONG scaling — the global batch is fixed and row-sharded, each rank owns a slab of
+                      the logits; embeddings all-gathered, column sums all-reduced, row sums all-gathered (NCCL).
+  clip32k_d768        same at D=768 (BASELINE config 5)
+A "step" = one loss forward + backward over the whole global batch (normalise, logits tiles, LSE, gradients).
+One JSON line on rank 0. `value` = device-resident inputs; `e2e` = same step through the public module API with
+pinned-host inputs copied in and the loss copied out every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "contrastive loss fwd+bwd samples/s @B=32k,D=512"
+UNIT = "samples/s"
+WORKLOADS = {"clip32k": (32768, 512), "clip32k_d768": (32768, 768), "clip8k": (8192, 512)}
+TAU = 0.0588   # config/clip/base_config.yaml:46
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step(N: int, D: int, steps: int, warmup: int):
+    """The reference's CPU path (oracle port: normalise, matmul, 2x CE, closed-form backward; fp32 numpy with all
+    BLAS threads) on a bounded sample of the workload."""
+    import numpy as np
+    from oracle import contrastive_oracle as co
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((N, D)).astype(np.float32)
+    t = rng.standard_normal((N, D)).astype(np.float32)
+    for _ in range(warmup):
+        co.clip_fwd_bwd_f32(v, t, math.log(TAU))
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        co.clip_fwd_bwd_f32(v, t, math.log(TAU))
+        ts.append(time.perf_counter() - t0)
+    return min(ts), sum(ts) / len(ts)
+
+
+def run_reference(args, N, D):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Ns = 4096                                  # bounded sample; the loss is O(N^2 D): extrapolate by (Ns/N)
+    best, mean = cpu_reference_step(Ns, D, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    sps_sample = Ns / best
+    value = sps_sample * (Ns / N)               # samples/s the CPU path would reach at the full N (N^2 scaling)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3 * (N / Ns) ** 2,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "global_batch": N, "dim": D, "tau": TAU},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"oracle port (numpy fp32, BLAS threads) fwd+bwd at N={Ns}: {sps_sample:.0f} samples/s, "
+                                   f"N^2-extrapolated to N={N}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="clip32k", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    N, D = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, N, D)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from deepcoro_clip_b200 import _lib, ops
+    from deepcoro_clip_b200.loss import CLIPLoss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert N % world == 0
+    B = N // world
+    W = max(3, args.warmup)
+
+    g = torch.Generator().manual_seed(5 + rank)
+    v_host = torch.randn(B, D, generator=g).pin_memory()
+    t_host = torch.randn(B, D, generator=g).pin_memory()
+    v = v_host.to(dev).requires_grad_(True)
+    t = t_host.to(dev).requires_grad_(True)
+    log_temp = torch.tensor([math.log(TAU)], device=dev, requires_grad=True)
+    loss_mod = CLIPLoss(precision=args.precision)
+
+    def step(vv, tt):
+        vv.grad = None; tt.grad = None; log_temp.grad = None
+        loss = loss_mod(video_features=vv, text_features=tt, log_temp=log_temp)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM ----------------
+    for _ in range(W):
+        step(v, t)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.LAUNCHES
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(v, t)
+    e1.record()
+    barrier()
+    launches = _lib.LAUNCHES - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = loss.item()
+
+    # ---------------- e2e: pinned host inputs in, loss out, every step ----------------
+    def e2e_step():
+        vv = v_host.to(dev, non_blocking=True).requires_grad_(True)
+        tt = t_host.to(dev, non_blocking=True).requires_grad_(True)
+        return step(vv, tt).to("cpu", non_blocking=False)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = ms2.item() / args.steps
+
+    # ---------------- roofline of the dominant kernel (logits_bwd), timed alone on its stream ----------------
+    roof = None
+    if rank == 0:
+        bf16_burst, bf16_sust, hbm, src = peaks()
+        Kp = ops.round_up(D, 64)
+        x = torch.nn.functional.normalize(torch.randn(B, Kp, device=dev), dim=-1).bfloat16()
+        y = torch.nn.functional.normalize(torch.randn(N, Kp, device=dev), dim=-1).bfloat16()
+        rs = torch.full((B,), 0.5 / N, device=dev); cs = torch.full((N,), 0.5 / N, device=dev)
+        dX = torch.zeros(B, D, device=dev); scal = torch.zeros(4, device=dev)
+        dyn = ops.dyn_prep(log_temp, None, 1e-4, 1.0)
+        for _ in range(3):
+            ops.logits_bwd(0, x, y, B, N, Kp, Kp, D, dyn, rs, cs, dX, scal)
+        torch.cuda.synchronize()
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            ops.logits_bwd(0, x, y, B, N, Kp, Kp, D, dyn, rs, cs, dX, scal)
+        e1.record(); torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / reps
+        alg = 2.0 * B * N * D                      # algorithmic FLOPs of one launch (one gradient GEMM; recompute not counted)
+        achieved = alg / (kms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "bw_kernel<CLIP> (logits_bwd)", "achieved": achieved, "peak": bf16_burst,
+                "unit": "TFLOP/s", "frac": achieved / bf16_burst, "traffic": None, "peak_source": src,
+                "ms_per_launch": kms, "executed_tflops": 3 * achieved,
+                "note": "algorithmic = 2*B*N*D per launch (SURVEY 8d: recompute and the second d-half pass not counted)"}
+        step_alg = 6.0 * B * N * D
+        roof["step_algorithmic_tflops"] = step_alg / (ms_per_step * 1e-3) / 1e12
+        roof["step_frac_of_peak"] = roof["step_algorithmic_tflops"] / bf16_sust
+        roof["step_peak"] = bf16_sust
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Ns = 4096
+        best, _ = cpu_reference_step(Ns, D, 3, 1)
+        cpu = {"value": (Ns / best) * (Ns / N), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle port (numpy fp32, BLAS threads) fwd+bwd at N={Ns}: {Ns / best:.0f} samples/s ({best * 1e3:.0f} ms), "
+                         f"N^2-extrapolated to N={N}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": N / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "global_batch": N, "per_gpu_rows": B, "dim": D, "tau": TAU,
+                       "precision": args.precision, "parallelism": f"row-slab x{world}",
+                       "l2": "no explicit flush: per-step working set (fp32 inputs+grads, bf16 operands, fp32 dXhat) "
+                             f"= {(4 * B * D * 4 + 2 * N * D * 2 + 2 * B * D * 4) / 1e6:.0f} MB > 126 MB L2"},
+            "e2e": {"value": N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 2 * B * D * 4 * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches, "loss": loss_val, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

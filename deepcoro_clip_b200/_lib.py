@@ -16,6 +16,8 @@ _PKG = Path(__file__).resolve().parent
 _LIB_PATH = _PKG / "libb200clip.so"
 _HEADER = _PKG.parent / "include" / "b200clip.h"
 _lib = None
+LAUNCHES = 0      # number of b200clip_* kernel-launching calls made by this process (bench.py reports it)
+_NO_LAUNCH = {"abi_version", "strerror", "sm_count"}
 
 DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
@@ -64,8 +66,11 @@ def i64(v: int) -> ctypes.c_int64:
 
 def call(name: str, *args) -> None:
     """Calls ``b200clip_<name>`` with tensors converted to device pointers; raises on error."""
+    global LAUNCHES
     fn = getattr(lib(), "b200clip_" + name)
     rc = fn(*[_conv(a) for a in args])
+    if name not in _NO_LAUNCH:
+        LAUNCHES += 1
     if rc != 0:
         msg = lib().b200clip_strerror(rc).decode()
         raise B200ClipError(f"b200clip_{name} failed: {msg} (code {rc})")
