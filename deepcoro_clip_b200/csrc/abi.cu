@@ -26,11 +26,11 @@ const char* b200clip_strerror(int code) {
 int b200clip_sm_count(void) { return sm_count(); }
 
 int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim, void* operand, int ld_out, int Kp,
-                        int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, void* stream) {
+                        int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, int normalize, void* stream) {
   if (!x || !operand) return B2_EINVAL;
   if (ld_out < (split3_role >= 0 ? 3 * Kp : Kp)) return B2_EINVAL;
   return l2norm_fwd(x, dtype, (long)ldx, rows, dim, operand, ld_out, Kp, split3_role, inv_norm, xhat_f32, ld_hat,
-                    S(stream));
+                    normalize, S(stream));
 }
 
 int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* x, int dtype, int64_t ldx, const float* inv_norm,
@@ -100,6 +100,29 @@ int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, 
                       double* acc, void* stream) {
   if (!a || !b || !acc) return B2_EINVAL;
   return diag_sum(a, lda, b, ldb, rows, K, gated, dots, acc, S(stream));
+}
+
+int b200clip_retrieval_segments(int n_video, int n_text) { return retrieval_segments(n_video, n_text); }
+
+int b200clip_retrieval_sweep(const void* video, const void* text, int n_video, int n_text, int Kp, int ldv, int ldt,
+                             const float* s_gt, const int64_t* gt, int col_offset, int32_t* counts, int k, int segs,
+                             float* part_score, int32_t* part_idx, void* stream) {
+  if (!video || !text) return B2_EINVAL;
+  return retrieval_sweep(video, text, n_video, n_text, Kp, ldv, ldt, s_gt, reinterpret_cast<const long long*>(gt),
+                         col_offset, counts, k, segs, part_score, part_idx, S(stream));
+}
+
+int b200clip_topk_merge(const float* part_score, const int32_t* part_idx, int rows, int candidates, int k,
+                        float* out_score, int64_t* out_idx, void* stream) {
+  if (!part_score || !part_idx || !out_score || !out_idx) return B2_EINVAL;
+  return topk_merge(part_score, part_idx, rows, candidates, k, out_score, reinterpret_cast<long long*>(out_idx),
+                    S(stream));
+}
+
+int b200clip_recall_hits(const int32_t* counts, int rows, const int32_t* k_values, int nk, uint64_t* hits,
+                         void* stream) {
+  if (!counts || !k_values || !hits) return B2_EINVAL;
+  return recall_hits(counts, rows, k_values, nk, reinterpret_cast<unsigned long long*>(hits), S(stream));
 }
 
 }  // extern "C"

@@ -8,7 +8,7 @@ namespace b2host {
 
 // l2norm.cu
 int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out, int ldo, int Kp, int split3_role,
-               float* inv_norm, float* xhat_f32, int ldh, cudaStream_t s);
+               float* inv_norm, float* xhat_f32, int ldh, int normalize, cudaStream_t s);
 int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, const float* inv_norm, const void* ox,
                int odtype, long ldox, const float* oinv, const void* ohi, int ldohi, const float* dc,
                const float* usum, float gscale, float ucoef, const float* dev_omul, const float* dev_gmul, int rows,
@@ -37,6 +37,15 @@ int lse_finalize(const float* sums, int n, const float* dyn, float c, float* sca
 int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s);
 int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots, double* acc,
              cudaStream_t s);
+
+// retrieval.cu
+int retrieval_segments(int Ma, int Nb);
+int retrieval_sweep(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, const float* sgt,
+                    const long long* gt, int col_offset, int* counts, int k, int segs, float* part_score,
+                    int* part_idx, cudaStream_t stream);
+int topk_merge(const float* ps, const int* pi, int rows, int cand, int k, float* out_s, long long* out_i,
+               cudaStream_t s);
+int recall_hits(const int* counts, int rows, const int* kvals, int nk, unsigned long long* hits, cudaStream_t s);
 
 // tmap.cu
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,

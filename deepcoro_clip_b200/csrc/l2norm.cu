@@ -27,7 +27,8 @@ __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(
 template <typename T>
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const T* __restrict__ x, long ldx, int rows, int dim, __nv_bfloat16* __restrict__ out, int ldo,
-                  int Kp, int split3_role, float* __restrict__ inv_norm, float* __restrict__ xhat_f32, int ldh) {
+                  int Kp, int split3_role, float* __restrict__ inv_norm, float* __restrict__ xhat_f32, int ldh,
+                  int normalize) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -38,8 +39,11 @@ l2norm_fwd_kernel(const T* __restrict__ x, long ldx, int rows, int dim, __nv_bfl
     ss = fmaf(v, v, ss);
   }
   ss = warp_sum(ss);
-  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  if (lane == 0 && inv_norm) inv_norm[warp] = inv;
+  // normalize == 0: pack the raw features (retrieval_metrics_streaming.py:35-41 does not normalise); inv_norm then
+  // receives ||x|| itself (used for the *_norm metrics)
+  const float nrm = sqrtf(ss);
+  const float inv = normalize ? 1.f / fmaxf(nrm, 1e-12f) : 1.f;
+  if (lane == 0 && inv_norm) inv_norm[warp] = normalize ? inv : nrm;
   __nv_bfloat16* o = out + (size_t)warp * ldo;
   for (int c = lane; c < Kp; c += 32) {
     const float v = c < dim ? to_f32<T>(xr[c]) * inv : 0.f;
@@ -146,14 +150,14 @@ namespace b2host {
 using namespace b2;
 
 int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out, int ldo, int Kp, int split3_role,
-               float* inv_norm, float* xhat_f32, int ldh, cudaStream_t s) {
+               float* inv_norm, float* xhat_f32, int ldh, int normalize, cudaStream_t s) {
   if (rows <= 0 || dim <= 0 || Kp < dim || Kp % 64) return B2_EINVAL;
   const int blocks = (rows + 7) / 8;
   auto o = reinterpret_cast<__nv_bfloat16*>(out);
   switch (dtype) {
-    case 0: l2norm_fwd_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh); break;
-    case 1: l2norm_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh); break;
-    case 2: l2norm_fwd_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh); break;
+    case 0: l2norm_fwd_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); break;
+    case 1: l2norm_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); break;
+    case 2: l2norm_fwd_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); break;
     default: return B2_EINVAL;
   }
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;

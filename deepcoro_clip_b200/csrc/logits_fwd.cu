@@ -129,13 +129,14 @@ struct DumpEpi {
 namespace b2host {
 using namespace b2;
 
-static int make_shape(TeShape& g, int Ma, int Nb, int Kp) {
+int make_shape(TeShape& g, int Ma, int Nb, int Kp) {
   if (Ma <= 0 || Nb <= 0 || Kp <= 0 || (Kp % TE_BK) != 0) return B2_EINVAL;
   g.Ma = Ma;
   g.Nb = Nb;
   g.Kp = Kp;
   g.m_tiles = (Ma + TE_BM - 1) / TE_BM;
   g.n_blocks = (Nb + TE_BN - 1) / TE_BN;
+  g.segs = 0;
   return B2_OK;
 }
 

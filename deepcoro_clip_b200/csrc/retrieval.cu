@@ -1,0 +1,271 @@
+// K5 / K6: streaming retrieval — similarity tiles on tcgen05 with a rank-count + top-k epilogue.
+// Replaces the chunked matmul / topk / cat / topk / gather / argsort loops of
+// utils/retrieval_metrics_streaming.py:47-101, 143-169. The [N, M] similarity matrix never exists.
+//
+//   tile order: outer = 128-row video tile (one TMEM lane = one video), inner = 256-wide text blocks.
+//   per element (thread = row, 128 columns per tile per epilogue warpgroup):
+//     * rank count: cnt += [s > s_gt] (+ [s == s_gt] for columns before the ground truth): lowest-index tie rule,
+//       rank_i = 1 + cnt_i    -> recall@k and MRR need only these integer counts;
+//     * top-k (optional, K <= 16 or <= 64): sorted list in REGISTERS per (row, warpgroup, sweep segment); a chunk is
+//       scanned only if its maximum beats the current k-th score; columns arrive in increasing index, so a strict
+//       ">" keeps the lowest index among equal scores.
+//   Partial lists go to global memory; topk_merge (one warp per row) merges the slots (and, across GPUs, the
+//   text shards) by (score desc, index asc).
+#include "tile_engine.cuh"
+#include "host_api.h"
+
+namespace b2 {
+
+struct RetrParams {
+  const float* sgt;        // [Ma] ground-truth similarity per row (null: no rank counting)
+  const long long* gt;     // [Ma] ground-truth GLOBAL column per row
+  int col_offset;          // global index of B row 0 (text shard offset)
+  int* counts;             // [Ma] += number of columns ranked before the ground truth
+  float* part_score;       // [Ma][slots][k] partial top-k lists (null when kMaxK == 0)
+  int* part_idx;
+  int slots;
+  int k;
+};
+
+template <int kMaxK>
+struct RetrEpi {
+  using Params = RetrParams;
+  static constexpr int KL = kMaxK > 0 ? kMaxK : 1;
+  struct State {
+    float ls[KL];
+    int li[KL];
+    float thr;
+    int cnt;
+    float sg;
+    int g;        // ground-truth column relative to this shard (may be out of range)
+  };
+  __device__ static __forceinline__ void init(State&, const Params&) {}
+  __device__ static __forceinline__ void begin_outer(State& st, const Params& p, int, const TeCtx& ctx) {
+#pragma unroll
+    for (int i = 0; i < KL; ++i) {
+      st.ls[i] = -INFINITY;
+      st.li[i] = 0x7fffffff;
+    }
+    st.thr = -INFINITY;
+    st.cnt = 0;
+    st.sg = 0.f;
+    st.g = -1;
+    if (p.sgt && ctx.row_ok) {
+      st.sg = p.sgt[ctx.row];
+      const long long gg = p.gt[ctx.row] - p.col_offset;
+      st.g = gg < -1 ? -1 : (gg > 0x3fffffff ? 0x3fffffff : (int)gg);
+    } else if (p.sgt) {
+      st.g = 0x3fffffff;
+    }
+  }
+  __device__ static __forceinline__ void insert(State& st, float s, int idx, int k) {
+    float cs = s;
+    int ci = idx;
+    bool ins = false;
+#pragma unroll
+    for (int q = 0; q < KL; ++q) {
+      const bool b = ins || (cs > st.ls[q]);
+      const float ts = b ? st.ls[q] : cs;
+      const int ti = b ? st.li[q] : ci;
+      st.ls[q] = b ? cs : st.ls[q];
+      st.li[q] = b ? ci : st.li[q];
+      cs = ts;
+      ci = ti;
+      ins = b;
+    }
+    float t = st.ls[0];
+#pragma unroll
+    for (int q = 1; q < KL; ++q) t = (q == k - 1) ? st.ls[q] : t;
+    st.thr = (k == 1) ? st.ls[0] : t;
+  }
+  __device__ static __forceinline__ void chunk(State& st, const Params& p, const TeCtx& ctx, int c,
+                                               const uint32_t (&acc)[32]) {
+    const int cbase = ctx.col0 + c * 32;               // shard-local column of element 0
+    const int nvalid = ctx.Nb - cbase;                 // elements e < nvalid are real columns
+    if (p.sgt) {
+      // ---- rank counting ----
+      const int gl = st.g - cbase;                     // position of the ground truth inside this chunk
+      int cnt = 0;
+      if (nvalid >= 32 && (gl >= 32 || gl < 0)) {
+        if (gl >= 32) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) cnt += (__uint_as_float(acc[e]) >= st.sg) ? 1 : 0;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) cnt += (__uint_as_float(acc[e]) > st.sg) ? 1 : 0;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float s = __uint_as_float(acc[e]);
+          const bool before = e < gl;
+          const bool better = before ? (s >= st.sg) : (s > st.sg);
+          cnt += (e < nvalid && e != gl && better) ? 1 : 0;
+        }
+      }
+      st.cnt += cnt;
+    }
+    if (kMaxK > 0) {
+      // ---- top-k ----
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, (e < nvalid) ? __uint_as_float(acc[e]) : -INFINITY);
+      if (cmax > st.thr && ctx.row_ok) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) m |= ((e < nvalid) && (__uint_as_float(acc[e]) > st.thr)) ? (1u << e) : 0u;
+        while (m) {
+          const int e = __ffs(m) - 1;
+          m &= m - 1;
+          uint32_t v = acc[0];
+#pragma unroll
+          for (int q = 1; q < 32; ++q) v = (q == e) ? acc[q] : v;
+          const float s = __uint_as_float(v);
+          if (s > st.thr) insert(st, s, p.col_offset + cbase + e, p.k);
+        }
+      }
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State&, const Params&, const TeCtx&) {}
+  __device__ static __forceinline__ void end_outer(State& st, const Params& p, int, const TeCtx& ctx) {
+    if (!ctx.row_ok) return;
+    if (p.sgt && st.cnt) atomicAdd(p.counts + ctx.row, st.cnt);
+    if (kMaxK > 0) {
+      const int slot = ctx.seg * 2 + ctx.wg;
+      const size_t base = ((size_t)ctx.row * p.slots + slot) * p.k;
+#pragma unroll
+      for (int q = 0; q < KL; ++q)
+        if (q < p.k) {
+          p.part_score[base + q] = st.ls[q];
+          p.part_idx[base + q] = st.li[q];
+        }
+    }
+  }
+};
+
+// K6: out[row][0..k) = best k of the row's `slots * kin` candidates by (score desc, index asc). One warp per row.
+__device__ __forceinline__ unsigned long long retr_key(float s, int idx) {
+  uint32_t u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (uint32_t)(0x7fffffff - idx);
+}
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ ps, const int* __restrict__ pi, int rows, int cand, int k,
+                  float* __restrict__ out_s, long long* __restrict__ out_i) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* s = ps + (size_t)warp * cand;
+  const int* id = pi + (size_t)warp * cand;
+  // keys are unique per (score, idx): round r takes the largest key below the previous winner
+  unsigned long long last = ~0ull;
+  for (int r = 0; r < k; ++r) {
+    unsigned long long best = 0ull;
+    for (int c = lane; c < cand; c += 32) {
+      const int ix = id[c];
+      const unsigned long long key = ix != 0x7fffffff ? retr_key(s[c], ix) : 0ull;
+      if (key < last && key > best) best = key;
+    }
+    unsigned long long wbest = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, wbest, o);
+      wbest = other > wbest ? other : wbest;
+    }
+    last = wbest != 0ull ? wbest : 0ull;
+    if (lane == 0) {
+      if (wbest == 0ull) {
+        out_s[(size_t)warp * k + r] = -INFINITY;
+        out_i[(size_t)warp * k + r] = -1;
+      } else {
+        uint32_t u = (uint32_t)(wbest >> 32);
+        u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        out_s[(size_t)warp * k + r] = __uint_as_float(u);
+        out_i[(size_t)warp * k + r] = (long long)(0x7fffffff - (uint32_t)(wbest & 0xffffffffu));
+      }
+    }
+  }
+}
+
+// hits[j] += #{rows: counts[row] < k_values[j]} (recall numerators, integer exact); mrr in double is done on the host
+__global__ void __launch_bounds__(256)
+recall_hits_kernel(const int* __restrict__ counts, int rows, const int* __restrict__ kvals, int nk,
+                   unsigned long long* __restrict__ hits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = 0; j < nk; ++j) {
+    const bool hit = i < rows && counts[i] < kvals[j];
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(hits + j, (unsigned long long)__popc(b));
+  }
+}
+
+}  // namespace b2
+
+namespace b2host {
+using namespace b2;
+
+int make_shape(TeShape& g, int Ma, int Nb, int Kp);   // logits_fwd.cu
+
+template <int kMaxK>
+static int launch_retr(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, const RetrParams& p,
+                       int segs, cudaStream_t stream) {
+  TeShape g;
+  int rc = make_shape(g, Ma, Nb, Kp);
+  if (rc) return rc;
+  g.segs = segs;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, TE_BN))) return rc;
+  auto kern = te_kernel<RetrEpi<kMaxK>, false>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
+      return B2_ECUDA;
+    attr_done = true;
+  }
+  const long long items = (long long)g.m_tiles * segs;
+  int grid = sm_count();
+  if (items < grid) grid = (int)items;
+  kern<<<grid, TE_THREADS, TE_SMEM_BYTES, stream>>>(tmA, tmB, g, p);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int retrieval_segments(int Ma, int Nb) {
+  const int m_tiles = (Ma + TE_BM - 1) / TE_BM, n_blocks = (Nb + TE_BN - 1) / TE_BN;
+  const int sms = sm_count();
+  int segs = 1;
+  if (m_tiles < 4 * sms) {          // too few row tiles to fill the machine: split the text sweep
+    segs = (4 * sms + m_tiles - 1) / m_tiles;
+    if (segs > n_blocks) segs = n_blocks;
+    if (segs > 64) segs = 64;
+    if (segs < 1) segs = 1;
+  }
+  return segs;
+}
+
+int retrieval_sweep(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, const float* sgt,
+                    const long long* gt, int col_offset, int* counts, int k, int segs, float* part_score,
+                    int* part_idx, cudaStream_t stream) {
+  if (Nv <= 0 || Mt <= 0 || k < 0 || k > 64 || segs < 1) return B2_EINVAL;
+  if (k > 0 && (!part_score || !part_idx)) return B2_EINVAL;
+  if (sgt && (!gt || !counts)) return B2_EINVAL;
+  RetrParams p{sgt, gt, col_offset, counts, part_score, part_idx, 2 * segs, k};
+  if (k == 0) return launch_retr<0>(V, T, Nv, Mt, Kp, ldv, ldt, p, segs, stream);
+  if (k <= 16) return launch_retr<16>(V, T, Nv, Mt, Kp, ldv, ldt, p, segs, stream);
+  return launch_retr<64>(V, T, Nv, Mt, Kp, ldv, ldt, p, segs, stream);
+}
+
+int topk_merge(const float* ps, const int* pi, int rows, int cand, int k, float* out_s, long long* out_i,
+               cudaStream_t s) {
+  if (rows <= 0 || cand <= 0 || cand > (1 << 20) || k <= 0) return B2_EINVAL;
+  topk_merge_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ps, pi, rows, cand, k, out_s, out_i);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int recall_hits(const int* counts, int rows, const int* kvals, int nk, unsigned long long* hits, cudaStream_t s) {
+  if (rows <= 0 || nk <= 0) return B2_EINVAL;
+  recall_hits_kernel<<<(rows + 255) / 256, 256, 0, s>>>(counts, rows, kvals, nk, hits);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+}  // namespace b2host

@@ -42,6 +42,51 @@ struct TeShape {
   int Kp;        // padded K (multiple of 64)
   int m_tiles;   // ceil(Ma / 128)
   int n_blocks;  // ceil(Nb / 256)
+  int segs;      // 0: each CTA takes one contiguous range of the (outer, inner) tile order (long sweeps);
+                 // s > 0: work items = (outer, segment of the inner sweep), items dealt round-robin to CTAs
+};
+
+// Identical tile sequence for the producer, MMA and epilogue roles of one CTA.
+struct TileSeq {
+  int inner_n, segs, items, item, stride;   // item mode
+  int t, t1;                                // contiguous mode
+  int i, i1, outer, seg;
+  __device__ __forceinline__ void init(const TeShape& g, bool outer_is_b) {
+    inner_n = outer_is_b ? g.m_tiles : g.n_blocks;
+    const int outer_n = outer_is_b ? g.n_blocks : g.m_tiles;
+    segs = g.segs;
+    if (segs > 0) {
+      items = outer_n * segs;
+      item = blockIdx.x;
+      stride = gridDim.x;
+      i = i1 = 0;
+    } else {
+      const long long total = (long long)g.m_tiles * g.n_blocks;
+      t = (int)(total * blockIdx.x / gridDim.x);
+      t1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    }
+  }
+  // returns false when the CTA is done; (outer, inner, seg) describe the next tile
+  __device__ __forceinline__ bool next(int& o, int& in, int& sg) {
+    if (segs > 0) {
+      while (i >= i1) {
+        if (item >= items) return false;
+        outer = item / segs;
+        seg = item - outer * segs;
+        i = (int)((long long)inner_n * seg / segs);
+        i1 = (int)((long long)inner_n * (seg + 1) / segs);
+        item += stride;
+      }
+      o = outer; in = i++; sg = seg;
+      return true;
+    }
+    if (t >= t1) return false;
+    o = t / inner_n;
+    in = t - o * inner_n;
+    sg = 0;
+    ++t;
+    return true;
+  }
 };
 
 struct TeCtx {
@@ -50,6 +95,7 @@ struct TeCtx {
   int row;        // global A row owned by this thread (m_tile*128 + lane quarter*32 + lane)
   int col0;       // first global B row (output column) of this thread's 128-column half
   int wg;         // epilogue warpgroup 0/1
+  int seg;        // segment of the inner sweep (item schedule), 0 otherwise
   bool row_ok;    // row < Ma
   bool full;      // whole 128x256 tile inside [Ma, Nb]
   int Nb;
@@ -73,11 +119,6 @@ te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // contiguous tile range of this CTA
-  const long long total = (long long)g.m_tiles * g.n_blocks;
-  const int t0 = (int)(total * blockIdx.x / gridDim.x);
-  const int t1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
-  const int inner_n = kOuterIsB ? g.m_tiles : g.n_blocks;
   const int kchunks = g.Kp / TE_BK;
 
   if (warp == 0 && lane == 0) {
@@ -111,8 +152,10 @@ te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = t0; t < t1; ++t) {
-          const int outer = t / inner_n, inner = t - outer * inner_n;
+        TileSeq seq;
+        seq.init(g, kOuterIsB);
+        int outer, inner, sg;
+        while (seq.next(outer, inner, sg)) {
           const int m_tile = kOuterIsB ? inner : outer;
           const int n_block = kOuterIsB ? outer : inner;
           for (int kc = 0; kc < kchunks; ++kc) {
@@ -133,7 +176,10 @@ te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         int stage = 0;
         uint32_t phase = 0;
         int lt = 0;
-        for (int t = t0; t < t1; ++t, ++lt) {
+        TileSeq seq;
+        seq.init(g, kOuterIsB);
+        int outer, inner, sg;
+        for (; seq.next(outer, inner, sg); ++lt) {
           const int as = lt & 1;
           const uint32_t aphase = (lt >> 1) & 1;
           mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -164,22 +210,28 @@ te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int wg = (warp - 4) >> 2;    // column half
     typename Epi::State st;
     Epi::init(st, ep);
-    TeCtx ctx;
+    TeCtx ctx, last;
     ctx.wg = wg;
     ctx.Nb = g.Nb;
-    int cur_outer = -1;
+    ctx.seg = 0;
+    last = ctx;
+    int cur_outer = -1, cur_seg = -1;
     int lt = 0;
-    for (int t = t0; t < t1; ++t, ++lt) {
-      const int outer = t / inner_n, inner = t - outer * inner_n;
+    TileSeq seq;
+    seq.init(g, kOuterIsB);
+    int outer, inner, sg;
+    for (; seq.next(outer, inner, sg); ++lt) {
       ctx.m_tile = kOuterIsB ? inner : outer;
       ctx.n_block = kOuterIsB ? outer : inner;
       ctx.row = ctx.m_tile * TE_BM + q * 32 + lane;
       ctx.col0 = ctx.n_block * TE_BN + wg * 128;
       ctx.row_ok = ctx.row < g.Ma;
       ctx.full = (ctx.m_tile * TE_BM + TE_BM <= g.Ma) && (ctx.n_block * TE_BN + TE_BN <= g.Nb);
-      if (outer != cur_outer) {
-        if (cur_outer >= 0) Epi::end_outer(st, ep, cur_outer, ctx);
+      if (outer != cur_outer || sg != cur_seg) {
+        if (cur_outer >= 0) Epi::end_outer(st, ep, cur_outer, last);   // coordinates of the finished sweep
         cur_outer = outer;
+        cur_seg = sg;
+        ctx.seg = sg;
         Epi::begin_outer(st, ep, outer, ctx);
       }
       const int as = lt & 1;
@@ -200,8 +252,9 @@ te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       Epi::end_tile(st, ep, ctx);
+      last = ctx;
     }
-    if (cur_outer >= 0) Epi::end_outer(st, ep, cur_outer, ctx);
+    if (cur_outer >= 0) Epi::end_outer(st, ep, cur_outer, last);
   }
 
   tc_fence_before();

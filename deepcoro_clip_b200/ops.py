@@ -40,8 +40,9 @@ def _rowmajor(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def l2norm_operand(x: torch.Tensor, split3_role: int = -1):
-    """x [rows, dim] -> (bf16 operand [rows, ld], inv_norm [rows] fp32, Kp). split3_role 0/1 = bf16x3 panels."""
+def l2norm_operand(x: torch.Tensor, split3_role: int = -1, normalize: bool = True):
+    """x [rows, dim] -> (bf16 operand [rows, ld], inv_norm [rows] fp32, Kp). split3_role 0/1 = bf16x3 panels.
+    normalize=False packs the raw features (inv_norm then holds ||x||)."""
     x = _rowmajor(x)
     rows, dim = x.shape
     Kp = round_up(dim, 64)
@@ -49,7 +50,7 @@ def l2norm_operand(x: torch.Tensor, split3_role: int = -1):
     op = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
     inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
     call("l2norm_fwd", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), rows, dim, op, ld, Kp, split3_role, inv, None, 0,
-         stream_ptr(x.device))
+         int(normalize), stream_ptr(x.device))
     return op, inv, Kp
 
 

@@ -42,11 +42,14 @@ int b200clip_sm_count(void);
  *      utils/retrieval_metrics_streaming.py:130-131).
  *   x [rows, dim] (row pitch ldx elements, dtype code) -> operand [rows, ld_out] bf16, inv_norm [rows] fp32
  *   (= 1 / max(||x||, 1e-12)), optional xhat_f32 [rows, ld_hat] fp32 (may be NULL).
+ *   normalize = 0 packs the raw features instead (compute_recall_at_k_streaming does not normalise:
+ *   retrieval_metrics_streaming.py:35-41) and writes ||x|| to inv_norm.
  *   split3_role: -1 plain bf16 operand; 0 / 1 = A-side [lo|hi|hi] / B-side [hi|lo|hi] panels of the bf16x3
  *   compensated product (small terms first: the tensor core truncates its fp32 accumulator each K step).
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim, void* operand, int ld_out,
-                        int Kp, int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, void* stream);
+                        int Kp, int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, int normalize,
+                        void* stream);
 
 /* K4  normalise backward (autograd of F.normalize) fused with the rank-sparse gradient corrections:
  *   g  = gmul * ( gscale * dxhat[r] + omul * (res_r * yh_r + gb_r * (yh_r - yhi_r)) + (ucoef * omul) * usum )
@@ -126,6 +129,27 @@ int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, f
 int b200clip_vec_fsum(const float* v, int n, int gated, double* acc, void* stream);
 int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots,
                       double* acc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5 / K6  Streaming retrieval. Replaces compute_recall_at_k_streaming / compute_metrics_streaming
+ *          (utils/retrieval_metrics_streaming.py:10-101, 104-197): chunked matmul + topk + merge + argsort rank.
+ *   retrieval_sweep : one pass of similarity tiles video [n_video, >=Kp] x text [n_text, >=Kp] (operands).
+ *       s_gt/gt/counts (all or none): counts[i] += #{j : s_ij > s_gt[i]  or  (s_ij == s_gt[i] and col(j) < gt[i])},
+ *       col(j) = col_offset + j, the ground-truth column itself excluded  => rank_i = 1 + counts[i]
+ *       (lowest-index tie rule, BASELINE.json north_star).
+ *       k > 0 (<= 64): partial top-k lists part_score/part_idx [n_video][2*segs][k] (global column indices,
+ *       unused entries idx = INT32_MAX), to be merged by topk_merge.  segs = retrieval_segments(...) or any >= 1.
+ *   topk_merge      : out[row] = best k of `candidates` (<= 512) entries by (score desc, index asc); idx -1 = none.
+ *   recall_hits     : hits[j] += #{i : counts[i] < k_values[j]}  (recall@k numerators, exact integers).
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_retrieval_segments(int n_video, int n_text);
+int b200clip_retrieval_sweep(const void* video, const void* text, int n_video, int n_text, int Kp, int ldv, int ldt,
+                             const float* s_gt, const int64_t* gt, int col_offset, int32_t* counts, int k, int segs,
+                             float* part_score, int32_t* part_idx, void* stream);
+int b200clip_topk_merge(const float* part_score, const int32_t* part_idx, int rows, int candidates, int k,
+                        float* out_score, int64_t* out_idx, void* stream);
+int b200clip_recall_hits(const int32_t* counts, int rows, const int32_t* k_values, int nk, uint64_t* hits,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,112 @@
+"""GPU parity: streaming retrieval (rank counts, recall@k, MRR, top-k lists) vs the reference golden vectors and
+the numpy oracle. Bar (BASELINE.json north_star): top-k indices and recall counts BIT-EXACT."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval_oracle as ro
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.tensor(np.asarray(a), device=DEV)
+
+
+def test_known_answers_identity_and_antidiagonal():
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_metrics_streaming
+    g = np.load(GOLDEN / "retrieval_known.npz")
+    eye = torch.eye(5, device=DEV)
+    m = compute_metrics_streaming(eye, eye, torch.arange(5, device=DEV), k_values=[1, 3, 5])
+    ref = dict(zip([str(k) for k in g["eye_keys"]], g["eye_values"]))
+    for k in ("Recall@1", "Recall@3", "Recall@5", "MRR_V2T", "alignment_score", "video_norm", "text_norm"):
+        assert abs(m[k] - ref[k]) < 1e-6, k
+    assert m["median_rank"] == 1
+    anti = torch.flip(torch.eye(5, device=DEV), dims=[1])
+    m2 = compute_metrics_streaming(eye, anti, torch.arange(5, device=DEV), k_values=[1])
+    assert m2["Recall@1"] == 20.0
+    o = ro.metrics_streaming(np.eye(5, dtype=np.float32), np.flip(np.eye(5, dtype=np.float32), 1), np.arange(5), [1])
+    assert abs(m2["MRR_V2T"] - o["MRR_V2T"]) < 1e-12     # all-ties rows: lowest-index rule == oracle
+
+
+def test_gauss_golden_metrics():
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_metrics_streaming
+    g = np.load(GOLDEN / "retrieval_gauss_300x200.npz")
+    m = compute_metrics_streaming(_t(g["video"]), _t(g["text"]), _t(g["gt"]), k_values=[1, 5, 10, 50],
+                                  video_chunk_size=128, text_chunk_size=64, device="cuda")
+    ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
+    for k in ("Recall@1", "Recall@5", "Recall@10", "Recall@50"):
+        assert m[k] == ref[k], (k, m[k], ref[k])
+    assert abs(m["MRR_V2T"] - ref["MRR_V2T"]) < 1e-9
+    assert abs(m["alignment_score"] - ref["alignment_score"]) < 1e-6
+    assert set(m) == set(ref)
+
+
+def test_exact_grid_golden_topk_and_recall_bit_exact():
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_recall_at_k_streaming, streaming_topk
+    g = np.load(GOLDEN / "retrieval_grid_257x300.npz")
+    v, t = _t(g["video"]), _t(g["text"])
+    r = compute_recall_at_k_streaming(v, t, _t(g["gt"]), k_values=[1, 5, 10], device="cuda")
+    ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
+    assert r == {k: ref[k] for k in r}
+    s, i = streaming_topk(v, t, 10)
+    sim = ro.similarity(g["video"], g["text"])
+    ov, oi = ro.topk_lowest_index(sim, 10)
+    assert (i.cpu().numpy() == oi).all()
+    assert (s.cpu().numpy() == ov).all()                       # scores bit-exact too (exact arithmetic inputs)
+    s11 = -np.sort(-sim, axis=1)[:, :11]
+    tie_free = (np.diff(s11, axis=1) != 0).all(axis=1)
+    assert (i.cpu().numpy()[tie_free] == g["topk_idx"][tie_free]).all()   # == torch.topk of the reference
+
+
+@pytest.mark.parametrize("N,M,D,k", [(1000, 777, 512, 10), (130, 5000, 512, 50), (4096, 2048, 768, 5), (300, 40, 64, 50)])
+def test_exact_grid_vs_oracle(N, M, D, k):
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_recall_at_k_streaming, streaming_topk
+    v = ro.exact_grid_embeddings(N, D, 3)
+    t = ro.exact_grid_embeddings(M, D, 4)
+    gt = np.random.default_rng(5).integers(0, M, size=N)
+    keep = []
+    kv = [1, 5, 10, 50]
+    r = compute_recall_at_k_streaming(_t(v), _t(t), _t(gt), k_values=kv, _counts_out=keep)
+    sim = ro.similarity(v, t)
+    ranks = ro.gt_ranks(sim, gt)
+    assert (keep[0].cpu().numpy() + 1 == ranks).all()           # every rank count exact
+    assert r == ro.recall_at_k_streaming(v, t, gt, kv)
+    s, i = streaming_topk(_t(v), _t(t), k)
+    ov, oi = ro.topk_lowest_index(sim, k)
+    kk = min(k, M)
+    assert (i.cpu().numpy()[:, :kk] == oi).all() and (s.cpu().numpy()[:, :kk] == ov).all()
+
+
+def test_planted_ties_lowest_index():
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_recall_at_k_streaming, streaming_topk
+    rng = np.random.default_rng(7)
+    v = ro.exact_grid_embeddings(600, 128, 8)
+    t = ro.exact_grid_embeddings(900, 128, 9)
+    dup = rng.integers(0, 900, size=90)
+    t[rng.integers(0, 900, size=90)] = t[dup]                  # exact duplicate text rows => exact score ties
+    gt = rng.integers(0, 900, size=600)
+    gt[:90] = dup                                               # many ground truths sit inside a tie group
+    keep = []
+    compute_recall_at_k_streaming(_t(v), _t(t), _t(gt), k_values=[1, 5], _counts_out=keep)
+    sim = ro.similarity(v, t)
+    assert (keep[0].cpu().numpy() + 1 == ro.gt_ranks(sim, gt)).all()
+    s, i = streaming_topk(_t(v), _t(t), 16)
+    _, oi = ro.topk_lowest_index(sim, 16)
+    assert (i.cpu().numpy() == oi).all()
+
+
+def test_gaussian_normalised_counts_match_oracle():
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_metrics_streaming
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal((3000, 512)).astype(np.float32)
+    t = rng.standard_normal((2000, 512)).astype(np.float32)
+    gt = rng.integers(0, 2000, size=3000)
+    m = compute_metrics_streaming(_t(v), _t(t), _t(gt), k_values=[1, 5, 10])
+    o = ro.metrics_streaming(v, t, gt, [1, 5, 10])
+    for k in ("Recall@1", "Recall@5", "Recall@10"):
+        assert m[k] == o[k]
+    assert abs(m["MRR_V2T"] - o["MRR_V2T"]) < 1e-7
+    assert abs(m["alignment_score"] - o["alignment_score"]) < 1e-6
