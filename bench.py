@@ -226,15 +226,15 @@ def main():
         x = torch.nn.functional.normalize(torch.randn(B, Kp, device=dev), dim=-1).bfloat16()
         y = torch.nn.functional.normalize(torch.randn(N, Kp, device=dev), dim=-1).bfloat16()
         rs = torch.full((B,), 0.5 / N, device=dev); cs = torch.full((N,), 0.5 / N, device=dev)
-        dX = torch.zeros(B, D, device=dev); scal = torch.zeros(4, device=dev)
+        dX = torch.zeros(B, D, device=dev); scal = torch.zeros(4, dtype=torch.float64, device=dev)
         dyn = ops.dyn_prep(log_temp, None, 1e-4, 1.0)
         for _ in range(3):
-            ops.logits_bwd(0, x, y, B, N, Kp, Kp, D, dyn, rs, cs, dX, scal)
+            ops.logits_bwd(0, x, y, B, N, Kp, Kp, D, dyn, rs, cs, dX, scal, gnorm=2.0 * N)
         torch.cuda.synchronize()
         reps = 10
         e0.record()
         for _ in range(reps):
-            ops.logits_bwd(0, x, y, B, N, Kp, Kp, D, dyn, rs, cs, dX, scal)
+            ops.logits_bwd(0, x, y, B, N, Kp, Kp, D, dyn, rs, cs, dX, scal, gnorm=2.0 * N)
         e1.record(); torch.cuda.synchronize()
         kms = e0.elapsed_time(e1) / reps
         alg = 2.0 * B * N * D                      # algorithmic FLOPs of one launch (one gradient GEMM; recompute not counted)

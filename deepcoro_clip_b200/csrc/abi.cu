@@ -72,11 +72,11 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
 int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off,
                         int ldx, int ldy,
                         float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
-                        const float* colscale, float out_scale, const float* dyn, float ydiag, int diag_off,
-                        float* diag_corr, float* dX, int ldd, float* scal, int nseg_hint, void* stream) {
+                        const float* colscale, float out_scale, float gnorm, int hp, const float* dyn,
+                        float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal, int nseg_hint, void* stream) {
   if (!X || !Y || !dX) return B2_EINVAL;
   return logits_bwd(mode, X, Y, Nx, Ny, Kp, Dp, D, hi_off, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c, rowscale,
-                    colscale, out_scale, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal, nseg_hint, S(stream));
+                    colscale, out_scale, gnorm, hp, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal, nseg_hint, S(stream));
 }
 
 int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn,
@@ -100,6 +100,30 @@ int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, 
                       double* acc, void* stream) {
   if (!a || !b || !acc) return B2_EINVAL;
   return diag_sum(a, lda, b, ldb, rows, K, gated, dots, acc, S(stream));
+}
+
+int b200clip_siglip_dense_fwd(const void* video, const void* text, int B, int T, int Kp, int ldv, int ldt,
+                              const float* dyn, double* acc, void* stream) {
+  if (!video || !text || !dyn || !acc) return B2_EINVAL;
+  return siglip_dense_fwd(video, text, B, T, Kp, ldv, ldt, dyn, acc, S(stream));
+}
+
+int b200clip_siglip_compact(const float* pos_mask, int64_t ld_mask, const float* pos_weights, int64_t ld_weights, int B,
+                            int T, int cap, int32_t* col, float* y, float* w, int32_t* cnt, float* ysum,
+                            int32_t* overflow, void* stream) {
+  if (!col || !y || !w || !cnt || !ysum || !overflow) return B2_EINVAL;
+  return siglip_compact(pos_mask, (long)ld_mask, pos_weights, (long)ld_weights, B, T, cap, col, y, w, cnt, ysum,
+                        overflow, S(stream));
+}
+
+int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, int K, int Dp, int D, int hi_off, int B,
+                        int T, int cap, const int32_t* col, const float* y, const float* w, const int32_t* cnt,
+                        const float* ysum, const float* dyn, float positive_weight, float negative_weight, float c,
+                        float gnorm, int hp, int use_pos_weights, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc,
+                        void* stream) {
+  if (!video || !text || !col || !y || !w || !cnt || !ysum || !dyn || !acc) return B2_EINVAL;
+  return siglip_pos(video, ldv, text, ldt, K, Dp, D, hi_off, B, T, cap, col, y, w, cnt, ysum, dyn, positive_weight,
+                    negative_weight, c, gnorm, hp, use_pos_weights, auto_balance, dV, lddv, dT, lddt, acc, S(stream));
 }
 
 int b200clip_retrieval_segments(int n_video, int n_text) { return retrieval_segments(n_video, n_text); }

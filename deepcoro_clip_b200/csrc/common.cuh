@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -154,8 +155,9 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 // Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulate (bit layout: PTX ISA
 // "Instruction descriptor" table; c_format[4,6) a_format[7,10) b_format[10,13) a_major[15] b_major[16]
 // n>>3 [17,23) m>>4 [24,29)).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
+// a_fp16 = 1 selects an FP16 A operand (B stays BF16): kind::f16 allows the two 16-bit formats to be mixed.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major, int a_fp16 = 0) {
+  return (1u << 4) | (uint32_t(a_fp16 ? 0u : 1u) << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
@@ -224,6 +226,10 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

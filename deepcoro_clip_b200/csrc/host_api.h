@@ -28,8 +28,9 @@ int logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, i
 int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off, int ldx,
                int ldy,
                float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
-               const float* colscale, float out_scale, const float* dyn, float ydiag, int diag_off, float* diag_corr,
-               float* dX, int ldd, float* scal, int nseg_hint, cudaStream_t stream);
+               const float* colscale, float out_scale, float gnorm, int hp, const float* dyn, float ydiag,
+               int diag_off, float* diag_corr,
+               float* dX, int ldd, double* scal, int nseg_hint, cudaStream_t stream);
 
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
@@ -37,6 +38,16 @@ int lse_finalize(const float* sums, int n, const float* dyn, float c, float* sca
 int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s);
 int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots, double* acc,
              cudaStream_t s);
+
+// siglip.cu
+int siglip_dense_fwd(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const float* dyn,
+                     double* acc, cudaStream_t stream);
+int siglip_compact(const float* mask, long ldm, const float* pw, long ldw, int B, int T, int cap, int* col, float* y,
+                   float* w, int* cnt, float* ysum, int* overflow, cudaStream_t s);
+int siglip_pos(const void* V, int ldv, const void* T, int ldt, int K, int Dp, int D, int hi_off, int B, int Tn, int cap,
+               const int* col, const float* y, const float* w, const int* cnt, const float* ysum, const float* dyn,
+               float positive_weight, float negative_weight, float c, float gnorm, int hp, int use_pw, int auto_balance,
+               float* dV, int lddv, float* dT, int lddt, double* acc, cudaStream_t s);
 
 // retrieval.cu
 int retrieval_segments(int Ma, int Nb);

@@ -51,9 +51,13 @@ struct BwParams {
   const float* rowscale;       // [Nx]  c / rowsum_x  (CLIP)
   const float* colscale;       // [Ny]  c / colsum_y  (CLIP)
   float out_scale;             // 1 / tau
+  float gnorm;                 // G is formed, rounded (bf16) and fed to the tensor core as G*gnorm = O(1); the
+                               // accumulator and the scalar sums are multiplied back by 1/gnorm
+  int hp;                      // 1: G is split into bf16 hi + lo (two TS-MMAs per K step): gradient rounding error
+                               // 2^-17 instead of 2^-9; used together with the bf16x3 operands on small problems
   float* dX;                   // [Nx, ldd] fp32, accumulated with atomics
   int ldd;
-  float* scal;                 // [4] fp32 atomics: 0: sum G*f(S), 1: sum softplus(L), 2: sum G ; may be null
+  double* scal;                // [4] fp64 atomics: 0: sum G*f(S), 1: sum softplus(L), 2: sum G ; may be null
   const float* dyn;            // optional device block from dyn_prep: overrides scale2/shift2/inv_tau/bias/out_scale
 };
 
@@ -165,7 +169,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BW_BM, BW_BN, 0, 0);    // A, B K-major
-      constexpr uint32_t idesc_o = make_idesc_bf16(BW_BM, BW_BK, 0, 1);    // A from TMEM, B MN-major, N = 64
+      constexpr uint32_t idesc_o = make_idesc_bf16(BW_BM, BW_BK, 0, 1);    // A = bf16 G from TMEM, B MN-major, N = 64
       int slot = 0;
       uint32_t phase = 0;
       uint32_t tile_ctr = 0;      // S/G buffer = tile_ctr & 1, phase = (tile_ctr >> 1) & 1
@@ -197,9 +201,10 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
           for (int ks = 0; ks < BW_BN / 16; ++ks) {
             // B: rows = K (Y rows 16ks..16ks+15), 64 output columns contiguous per 128-byte row
             const uint64_t bdesc = make_smem_desc_sw128(sy + ks * 2048, 1024);
-            // A: G bf16x2-packed; each epilogue half keeps its 64 K-values in its own 32 columns
+            // A: G bf16x2-packed; each epilogue half keeps its 64 K-values in its own 32 columns (hi), lo next 32
             const uint32_t a_tmem = g_tmem + (ks >> 2) * 64 + (ks & 3) * 8;
             mma_ts(d_tmem, a_tmem, bdesc, idesc_o, !(first && ks == 0));
+            if (p.hp) mma_ts(d_tmem, a_tmem + 32, bdesc, idesc_o, 1u);
           }
           tc_commit(&empty_bar[slot]);
           if (++slot == BW_SLOTS) { slot = 0; phase ^= 1; }
@@ -240,15 +245,17 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
       const int row = xt * BW_BM + q * 32 + lane;
       const bool row_ok = row < p.Nx;
       float rs = 0.f;
-      if (kMode != BW_SIGLIP) rs = row_ok ? p.rowscale[row] : 0.f;
-      float tacc = 0.f, lacc = 0.f, bacc = 0.f;
+      if (kMode != BW_SIGLIP) rs = row_ok ? p.rowscale[row] * p.gnorm : 0.f;
+      const float ydn = p.ydiag * p.gnorm, wn = p.wneg_c * p.gnorm, ign = 1.f / p.gnorm;
+      double dtacc = 0.0, dlacc = 0.0, dbacc = 0.0;
       for (int j = j0; j < j1; ++j, ++tile_ctr) {
+        float tacc = 0.f, lacc = 0.f, bacc = 0.f;      // per-tile fp32 partials, accumulated in fp64 across tiles
         const int buf = tile_ctr & 1;
         float* cs = col_s + buf * 128;
         if (kMode != BW_SIGLIP) {
           if (etid < 128) {
             const int col = j * BW_BN + etid;
-            cs[etid] = col < p.Ny ? p.colscale[col] : 0.f;
+            cs[etid] = col < p.Ny ? p.colscale[col] * p.gnorm : 0.f;
           }
           named_bar_sync(1, 256);
         }
@@ -266,7 +273,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
         tc_wait_ld();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t packed[16];
+          uint32_t packed[16], packed_lo[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             float g2[2];
@@ -282,7 +289,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 const float den = 1.f + ex;
                 const float r = __fdividef(1.f, den);
                 const float sig = Lc >= 0.f ? r : ex * r;
-                g = (fabsf(R) <= 30.f) ? p.wneg_c * sig : 0.f;
+                g = (fabsf(R) <= 30.f) ? wn * sig : 0.f;
                 float sp = fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den);
                 if (!full && !(row_ok && (j * BW_BN + cl) < p.Ny)) { g = 0.f; sp = 0.f; }
                 lacc += sp;
@@ -298,26 +305,38 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 }
                 const float pr = ex2_approx(fmaf(f, p.scale2, -p.shift2));
                 g = pr * (rs + cs[cl]);
-                if (has_diag && (c * 32 + e + h) == dcol) g -= p.ydiag;
+                if (has_diag && (c * 32 + e + h) == dcol) g -= ydn;
                 if (!full && !(row_ok && (j * BW_BN + cl) < p.Ny)) g = 0.f;
                 tacc = fmaf(g, f, tacc);
                 if (kMode == BW_GATED) g *= fp;
                 if (has_diag && (c * 32 + e + h) == dcol && dp == 0 && row_ok && p.diag_corr) {
-                  const float gb = __bfloat162float(__float2bfloat16_rn(g));
-                  p.diag_corr[2 * row] = g - gb;
-                  p.diag_corr[2 * row + 1] = gb;
+                  float gb = __bfloat162float(__float2bfloat16_rn(g));
+                  if (p.hp) gb += __bfloat162float(__float2bfloat16_rn(g - gb));
+                  p.diag_corr[2 * row] = (g - gb) * ign;
+                  p.diag_corr[2 * row + 1] = gb * ign;
                 }
               }
               g2[h] = g;
             }
             packed[e >> 1] = pack_bf16x2(g2[0], g2[1]);
+            if (p.hp) {
+              const float r0 = g2[0] - __bfloat162float(__float2bfloat16_rn(g2[0]));
+              const float r1 = g2[1] - __bfloat162float(__float2bfloat16_rn(g2[1]));
+              packed_lo[e >> 1] = pack_bf16x2(r0, r1);
+            }
           }
           tmem_st16(sbase + c * 16, packed);
+          if (p.hp) tmem_st16(sbase + 32 + c * 16, packed_lo);
         }
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gready_bar[buf]);
+        dtacc += (double)tacc;
+        if (kMode == BW_SIGLIP) {
+          dlacc += (double)lacc;
+          dbacc += (double)bacc;
+        }
       }
       // ---- drain the accumulator of this item ----
       mbar_wait(accfull_bar, item_ctr & 1);
@@ -335,7 +354,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
             if (row_ok) {
 #pragma unroll
               for (int e = 0; e < 32; ++e)
-                if (c * 32 + e < cvalid) atomicAdd(drow + c * 32 + e, __uint_as_float(a[e]) * p.out_scale);
+                if (c * 32 + e < cvalid) atomicAdd(drow + c * 32 + e, __uint_as_float(a[e]) * (p.out_scale * ign));
             }
           }
         }
@@ -345,16 +364,18 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
       if (lane == 0) mbar_arrive(accempty_bar);
       ++item_ctr;
       if (p.scal && dp == 0) {
-        tacc = warp_sum(tacc);
-        if (kMode == BW_SIGLIP) {
-          lacc = warp_sum(lacc);
-          bacc = warp_sum(bacc);
+        for (int o = 16; o > 0; o >>= 1) {
+          dtacc += __shfl_xor_sync(0xffffffffu, dtacc, o);
+          if (kMode == BW_SIGLIP) {
+            dlacc += __shfl_xor_sync(0xffffffffu, dlacc, o);
+            dbacc += __shfl_xor_sync(0xffffffffu, dbacc, o);
+          }
         }
         if (lane == 0) {
-          atomicAdd(p.scal + 0, tacc);
+          atomicAdd(p.scal + 0, dtacc * (double)ign);
           if (kMode == BW_SIGLIP) {
-            atomicAdd(p.scal + 1, lacc);
-            atomicAdd(p.scal + 2, bacc);
+            atomicAdd(p.scal + 1, dlacc);
+            atomicAdd(p.scal + 2, dbacc * (double)ign);
           }
         }
       }
@@ -377,8 +398,9 @@ using namespace b2;
 int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off, int ldx,
                int ldy,
                float scale2, float shift2, float inv_tau, float bias, float wneg_c, const float* rowscale,
-               const float* colscale, float out_scale, const float* dyn, float ydiag, int diag_off, float* diag_corr,
-               float* dX, int ldd, float* scal, int nseg_hint, cudaStream_t stream) {
+               const float* colscale, float out_scale, float gnorm, int hp, const float* dyn, float ydiag,
+               int diag_off, float* diag_corr,
+               float* dX, int ldd, double* scal, int nseg_hint, cudaStream_t stream) {
   if (Nx <= 0 || Ny <= 0 || Kp <= 0 || Kp % 64 || Dp <= 0 || Dp % 64 || hi_off < 0 || hi_off % 64 ||
       hi_off + Dp > Kp || D > Dp || D <= 0)
     return B2_EINVAL;
@@ -402,6 +424,8 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   p.nseg = nseg;
   p.scale2 = scale2; p.shift2 = shift2; p.inv_tau = inv_tau; p.bias = bias; p.wneg_c = wneg_c;
   p.rowscale = rowscale; p.colscale = colscale; p.out_scale = out_scale;
+  p.gnorm = gnorm > 0.f ? gnorm : 1.f;
+  p.hp = hp ? 1 : 0;
   p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
   CUtensorMap tmX, tmY;
   int rc;

@@ -127,13 +127,13 @@ class _ClipLossFn(torch.autograd.Function):
         gmul = grad_out.detach().reshape(1).float().contiguous()
         lo, hi = rank * B, (rank + 1) * B
         dV = dT = dLT = None
-        scal = torch.zeros(4, dtype=torch.float32, device=dev)
+        scal = torch.zeros(4, dtype=torch.float64, device=dev)
         need_lt = ctx.needs_input_grad[2]
         if ctx.needs_input_grad[0] or need_lt:
             dVh = torch.zeros((B, D), dtype=torch.float32, device=dev)
             dcv = torch.zeros((B, 2), dtype=torch.float32, device=dev)
             ops.logits_bwd(mode, vop, tall, B, N, K, Kp, D, dyn, rowscale_all[lo:hi], colscale_all, dVh, scal,
-                           ydiag=(1.0 - eps) / N, diag_off=lo, diag_corr=dcv)
+                           ydiag=(1.0 - eps) / N, diag_off=lo, diag_corr=dcv, gnorm=2.0 * N, hp=(K != Kp))
             if ctx.needs_input_grad[0]:
                 dV = ops.l2norm_backward(dVh, video, vinv, other_x=text, other_inv=tinv, other_hi=top[:, K - Kp:],
                                          diag_corr=dcv, usum=tsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3],
@@ -142,12 +142,12 @@ class _ClipLossFn(torch.autograd.Function):
             dTh = torch.zeros((B, D), dtype=torch.float32, device=dev)
             dct = torch.zeros((B, 2), dtype=torch.float32, device=dev)
             ops.logits_bwd(mode, top, vall, B, N, K, Kp, D, dyn, colscale_all[lo:hi], rowscale_all, dTh, None,
-                           ydiag=(1.0 - eps) / N, diag_off=lo, diag_corr=dct)
+                           ydiag=(1.0 - eps) / N, diag_off=lo, diag_corr=dct, gnorm=2.0 * N, hp=(K != Kp))
             dT = ops.l2norm_backward(dTh, text, tinv, other_x=video, other_inv=vinv, other_hi=vop[:, K - Kp:],
                                      diag_corr=dct, usum=vsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3],
                                      dev_gmul=gmul).to(text.dtype)
         if need_lt:
-            s0 = scal[0:1].double()
+            s0 = scal[0:1].clone()
             if W > 1:
                 dist.all_reduce(s0, group=group)
             # d loss / d log_temp = -sum_ij G_ij L_ij  (zero while the tau clamp is active)
@@ -258,3 +258,151 @@ class InfoNCELoss(nn.Module):
         if self.loss_type == "contrastive":
             return (ContrastiveLossDDP() if ddp else ContrastiveLoss())(video_features, text_features, temp)
         raise ValueError(f"Invalid loss type: {self.loss_type}")
+
+
+# --------------------------------------------------------------------------------------------------
+# SigLIP multi-positive sigmoid loss
+# --------------------------------------------------------------------------------------------------
+class _SigLIPFn(torch.autograd.Function):
+    """utils/loss/contrastive.py:250-315; SURVEY Appendix A.2. Backward is a pure recompute, so when any input
+    needs a gradient the two gradient passes run eagerly in forward (no separate forward GEMM) and ``backward``
+    only applies the normalise-backward with the upstream scale."""
+
+    @staticmethod
+    def forward(ctx, video, text, log_temp, bias, pos_mask, pos_weights, cfg):
+        dev = ops.require_cuda(video, text, log_temp, bias)
+        if video.dim() != 2 or text.dim() != 2 or video.shape[1] != text.shape[1]:
+            raise ValueError(f"video_features {tuple(video.shape)} / text_features {tuple(text.shape)} must be "
+                             "[B, D] and [T, D]")
+        B, D = video.shape
+        T = text.shape[0]
+        W, rank = _world(True, cfg["group"])
+        Bg = B * W
+        if pos_mask is not None and tuple(pos_mask.shape) != (B, T):
+            raise ValueError(f"pos_mask must be [B, T] = {(B, T)}, got {tuple(pos_mask.shape)}")
+        if pos_weights is not None and tuple(pos_weights.shape) != (B, T):
+            raise ValueError(f"pos_weights must be [B, T] = {(B, T)}, got {tuple(pos_weights.shape)}")
+        x3 = _pick_precision(cfg["precision"], Bg, T)
+        vop, vinv, Kp = ops.l2norm_operand(video, 0 if x3 else -1)
+        top, tinv, _ = ops.l2norm_operand(text, 1 if x3 else -1)
+        K = vop.shape[1]
+        dyn = ops.dyn_prep(log_temp, bias, 1e-4, 1.0)
+        c = 1.0 / (Bg * T)
+        wp, wn = cfg["positive_weight"], cfg["negative_weight"]
+
+        # ---- positives: one streaming pass over the dense mask / weights ----
+        cap = cfg["max_positives"]
+        col = torch.empty((B, cap), dtype=torch.int32, device=dev)
+        yv = torch.empty((B, cap), dtype=torch.float32, device=dev)
+        wv = torch.empty((B, cap), dtype=torch.float32, device=dev)
+        cnt = torch.empty(B, dtype=torch.int32, device=dev)
+        ysum = torch.empty(B, dtype=torch.float32, device=dev)
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        pm = pw = None
+        if pos_mask is not None:
+            pm = pos_mask.detach().float()
+            pm = pm if pm.stride(1) == 1 else pm.contiguous()
+            if pos_weights is not None and cfg["use_severity_weights"]:
+                pw = pos_weights.detach().float()
+                pw = pw if pw.stride(1) == 1 else pw.contiguous()
+        st = ops.stream_ptr(dev)
+        if pos_mask is None and W > 1:
+            # diagonal targets on the GLOBAL [B_global, T] matrix (:274-278): local row r is global row rank*B + r
+            rows = torch.arange(B, device=dev, dtype=torch.int64) + rank * B
+            valid = rows < min(Bg, T)
+            col[:, 0] = rows.clamp(max=T - 1).to(torch.int32)
+            yv[:, 0] = 1.0
+            wv[:, 0] = 1.0
+            cnt.copy_(valid.to(torch.int32))
+            ysum.copy_(valid.float())
+        else:
+            ops.call("siglip_compact", pm, ops.i64(pm.stride(0) if pm is not None else 0), pw,
+                     ops.i64(pw.stride(0) if pw is not None else 0), B, T, cap, col, yv, wv, cnt, ysum, overflow, st)
+
+        need_grad = any(ctx.needs_input_grad[:4])
+        acc = torch.zeros(8, dtype=torch.float64, device=dev)   # [0] sum g*s [1] sum softplus [2] sum g | [4..6] positives
+        dVh = dTh = None
+        if need_grad:
+            dVh = torch.zeros((B, D), dtype=torch.float32, device=dev)
+            dTh = torch.zeros((T, D), dtype=torch.float32, device=dev)
+            ops.logits_bwd(BW_SIGLIP, vop, top, B, T, K, Kp, D, dyn, None, None, dVh, acc[0:4], wneg_c=wn * c,
+                           gnorm=1.0 / (wn * c), hp=x3)
+            ops.logits_bwd(BW_SIGLIP, top, vop, T, B, K, Kp, D, dyn, None, None, dTh, None, wneg_c=wn * c,
+                           gnorm=1.0 / (wn * c), hp=x3)
+        else:
+            ops.call("siglip_dense_fwd", vop, top, B, T, K, vop.stride(0), top.stride(0), dyn, acc[1:2], st)
+        ops.call("siglip_pos", vop, vop.stride(0), top, top.stride(0), K, Kp, D, K - Kp, B, T, cap, col, yv, wv, cnt,
+                 ysum, dyn, float(wp), float(wn), float(c), 1.0 / (wn * c), int(x3), int(pw is not None), int(cfg["auto_balance"]), dVh,
+                 D if dVh is not None else 0, dTh, D if dTh is not None else 0, acc[4:7], st)
+        # local sums -> global (every rank returns the full loss, reference DDP semantics)
+        red = torch.stack([wn * c * acc[1] + acc[4], acc[2] + acc[5], acc[0] + acc[6]])   # loss, dbias, sum G*s
+        if W > 1:
+            dist.all_reduce(red, group=cfg["group"])
+            if dTh is not None:
+                dist.all_reduce(dTh, group=cfg["group"])      # text is replicated: every rank gets the full text grad
+            dist.all_reduce(overflow, group=cfg["group"])
+        loss = red[0] + torch.where(overflow[0] > 0, float("nan"), 0.0)    # never silently drop positives
+        ctx.save_for_backward(video, text, vinv, tinv, dyn, dVh, dTh, red)
+        ctx.meta = (log_temp.shape, log_temp.dtype, bias.shape, bias.dtype)
+        return loss.float()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        video, text, vinv, tinv, dyn, dVh, dTh, red = ctx.saved_tensors
+        lt_shape, lt_dtype, b_shape, b_dtype = ctx.meta
+        gmul = grad_out.detach().reshape(1).float().contiguous()
+        dV = dT = dLT = dB = None
+        if ctx.needs_input_grad[0]:
+            dV = ops.l2norm_backward(dVh, video, vinv, dev_gmul=gmul).to(video.dtype)
+        if ctx.needs_input_grad[1]:
+            dT = ops.l2norm_backward(dTh, text, tinv, dev_gmul=gmul).to(text.dtype)
+        if ctx.needs_input_grad[2]:
+            # d loss / d log_temp = -sum G (R - b) = -(sum G*s)/tau ; zero while the tau clamp is active
+            dLT = (-(red[2] * dyn[2].double()) * dyn[7].double() * gmul.double()).to(lt_dtype).reshape(lt_shape)
+        if ctx.needs_input_grad[3]:
+            dB = (red[1] * gmul.double()).to(b_dtype).reshape(b_shape)
+        return dV, dT, dLT, dB, None, None, None
+
+
+class SigLIPLoss(nn.Module):
+    """utils/loss/contrastive.py:171-319 — sigmoid BCE over every (video, text) pair with multi-positive masks,
+    severity weights and auto-balance. Same constructor / forward signature / ``bias`` attribute."""
+
+    def __init__(self, bias_init: float = -10.0, learnable_bias: bool = True, positive_weight: float = 1.0,
+                 negative_weight: float = 1.0, use_severity_weights: bool = True, auto_balance: bool = False,
+                 entropy_regularization: bool = False, entropy_weight: float = 0.1,
+                 min_entropy_threshold: float = 2.0, precision: str = "auto", max_positives_per_row: int = 64):
+        super().__init__()
+        self.positive_weight = max(float(positive_weight), 1e-6)
+        self.negative_weight = max(float(negative_weight), 1e-6)
+        self.use_severity_weights = use_severity_weights
+        self.auto_balance = auto_balance
+        self.entropy_regularization = entropy_regularization
+        self.entropy_weight = entropy_weight
+        self.min_entropy_threshold = min_entropy_threshold
+        self.precision = precision
+        self.max_positives_per_row = int(max_positives_per_row)
+        self._last_entropy_diagnostics: dict = {}
+        if learnable_bias:
+            self.bias = nn.Parameter(torch.tensor(bias_init))
+        else:
+            self.register_buffer("bias", torch.tensor(bias_init))
+
+    def forward(self, video_features: torch.Tensor, text_features: torch.Tensor, log_temp: torch.Tensor,
+                pos_mask: Optional[torch.Tensor] = None, pos_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.entropy_regularization:
+            raise NotImplementedError(
+                "entropy_regularization=True is not provided by the B200 kernels yet (the registry path constructs "
+                "SigLIPLoss() with the default False); see DESIGN.md 'out of scope'")
+        dev = video_features.device
+        if not isinstance(log_temp, torch.Tensor):
+            log_temp = torch.tensor(float(log_temp), device=dev)
+        log_temp = log_temp.to(dev)
+        bias = self.bias if self.bias.device == dev else self.bias.to(dev)
+        cfg = dict(positive_weight=self.positive_weight, negative_weight=self.negative_weight,
+                   use_severity_weights=self.use_severity_weights, auto_balance=self.auto_balance,
+                   precision=self.precision, max_positives=self.max_positives_per_row, group=None)
+        return _SigLIPFn.apply(video_features, text_features, log_temp, bias, pos_mask, pos_weights, cfg)
+
+    def get_entropy_diagnostics(self) -> dict:
+        return self._last_entropy_diagnostics

@@ -76,7 +76,7 @@ def dyn_prep(log_temp: torch.Tensor, bias, clamp_min: float, bound: float) -> to
     return dyn
 
 
-def lse_fwd(A, B, Ma, Nb, K, dyn, gated, rowsum, colsum, diag=None, diag_off=0, diag_corr=None):
+def lse_fwd(A, B, Ma, Nb, K, dyn, gated, rowsum, colsum, diag=None, diag_off=0, diag_corr=None, gnorm=1.0, hp=False):
     call("logits_lse_fwd", A, B, Ma, Nb, K, A.stride(0), B.stride(0), 0.0, 0.0, int(gated), dyn, rowsum, colsum,
          diag, int(diag_off), stream_ptr(A.device))
 
@@ -100,6 +100,11 @@ def colsum_bf16(op, rows, dim):
 
 
 def logits_bwd(mode, X, Y, Nx, Ny, K, Dp, D, dyn, rowscale, colscale, dX, scal, *, wneg_c=0.0, nseg=0, ydiag=0.0,
-               diag_off=0, diag_corr=None):
+               diag_off=0, diag_corr=None, gnorm=1.0, hp=False):
     call("logits_bwd", mode, X, Y, Nx, Ny, K, Dp, D, K - Dp, X.stride(0), Y.stride(0), 0.0, 0.0, 0.0, 0.0, float(wneg_c),
-         rowscale, colscale, 0.0, dyn, float(ydiag), int(diag_off), diag_corr, dX, dX.stride(0), scal, nseg, stream_ptr(X.device))
+         rowscale, colscale, 0.0, float(gnorm), int(hp), dyn, float(ydiag), int(diag_off), diag_corr, dX, dX.stride(0), scal, nseg, stream_ptr(X.device))
+
+
+call = call  # re-export for the loss module
+i64 = i64
+stream_ptr = stream_ptr

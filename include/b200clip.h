@@ -100,17 +100,21 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
  *     mode 2 (SigLIP) : R = S*inv_tau + bias, G = wneg_c * sigmoid(clamp(R,+-30)) * [|R| <= 30]
  *     modes 0/1: G_ij -= ydiag where i + diag_off == j (the (1-eps)/N diagonal target, subtracted in fp32 before G
  *     is rounded to bf16; diag_off = rank * B_local under DDP); diag_corr (may be NULL) receives per row
- *     {g_ii - bf16(g_ii), bf16(g_ii)} for b200clip_l2norm_bwd. SigLIP positives are rank-sparse corrections applied
+ *     {g_ii - rounded(g_ii), rounded(g_ii)} for b200clip_l2norm_bwd. SigLIP positives are rank-sparse corrections applied
  *     by b200clip_siglip_pos.
  *   X [Nx, >=Kp], Y [Ny, >=Kp] operands; Dp = padded width of the hi panel (columns Y[:, hi_off:hi_off+Dp] feed
  *   the output product; hi_off = 0 for plain bf16 operands, 2*Dp in bf16x3 mode), D = valid output columns; dX fp32 [Nx, ldd] accumulated atomically (caller zeroes).
  *   scal (may be NULL): [0] += sum G*f(S)  [1] += sum softplus(L) (mode 2)  [2] += sum G (mode 2).
+ *   gnorm: G is formed, rounded to bf16 and fed to the tensor core as G*gnorm (choose gnorm so that G*gnorm = O(1):
+ *   2N for CLIP, 1/wneg_c for SigLIP); sums and dX are scaled back.
+ *   hp = 1: G is split into bf16 hi + lo and the output product issues two TS-MMAs per K step (rounding error of
+ *   the gradient operand 2^-17 instead of 2^-9); meant for the small, latency-bound problems that also use bf16x3.
  *   nseg_hint <= 0 lets the library pick the split of the Y sweep.
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off,
                         int ldx, int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
-                        const float* rowscale, const float* colscale, float out_scale, const float* dyn, float ydiag,
-                        int diag_off, float* diag_corr, float* dX, int ldd, float* scal, int nseg_hint,
+                        const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
+                        const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal, int nseg_hint,
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -129,6 +133,29 @@ int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, f
 int b200clip_vec_fsum(const float* v, int n, int gated, double* acc, void* stream);
 int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots,
                       double* acc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SigLIP multi-positive loss pieces (utils/loss/contrastive.py:230-315). The dense term treats every pair as a
+ * negative (b200clip_logits_bwd mode 2 when gradients are needed, siglip_dense_fwd otherwise); the positives are
+ * compacted from the dense fp32 pos_mask / pos_weights in ONE streaming pass and applied as exact corrections.
+ *   siglip_dense_fwd : acc[0] += sum_ij softplus(clamp(S_ij/tau + bias, +-30))   (dyn from b200clip_dyn_prep)
+ *   siglip_compact   : per video row, entries with clamp(pos_mask,0,1) > 0 -> col/y/w [B][cap], cnt[B], ysum[B]
+ *                      (= sum_j y_ij, for auto_balance); *overflow = 1 if a row holds more than cap positives.
+ *                      pos_mask == NULL: diagonal targets (:274-278). pos_weights may be NULL.
+ *   siglip_pos       : for every entry adds  w(sp - L y) - wn sp  to acc[0] (scaled by c = 1/(B_global*T)), the
+ *                      dbias / dlog_temp corrections to acc[1] / acc[2], and (dV, dT non-NULL) the gradient
+ *                      corrections to dVhat[row] and (atomically) dThat[col]. Weight rule :283-298.
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_siglip_dense_fwd(const void* video, const void* text, int B, int T, int Kp, int ldv, int ldt,
+                              const float* dyn, double* acc, void* stream);
+int b200clip_siglip_compact(const float* pos_mask, int64_t ld_mask, const float* pos_weights, int64_t ld_weights, int B,
+                            int T, int cap, int32_t* col, float* y, float* w, int32_t* cnt, float* ysum,
+                            int32_t* overflow, void* stream);
+int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, int K, int Dp, int D, int hi_off, int B,
+                        int T, int cap, const int32_t* col, const float* y, const float* w, const int32_t* cnt,
+                        const float* ysum, const float* dyn, float positive_weight, float negative_weight, float c,
+                        float gnorm, int hp, int use_pos_weights, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5 / K6  Streaming retrieval. Replaces compute_recall_at_k_streaming / compute_metrics_streaming

@@ -23,7 +23,7 @@ def run(mode, Nx, Ny, D, tau=0.0588, nseg=0, bias=-3.0):
     scal = torch.zeros(4, device=dev)
     wneg_c = 0.37
     L.call("logits_bwd", mode, x, y, Nx, Ny, Dp, Dp, D, 0, Dp, Dp, scale2, shift2, 1.0 / tau, bias, wneg_c, rs, cs,
-           1.0 / tau, None, 0.0, 0, None, dX, D, scal, nseg, st)
+           1.0 / tau, 1.0, 0, None, 0.0, 0, None, dX, D, scal, nseg, st)
     torch.cuda.synchronize()
     if mode == 0:
         f = S; G = torch.exp((f - 1.0) / tau) * (rs.double()[:, None] + cs.double()[None, :]); GS = G
@@ -62,12 +62,12 @@ dX = torch.zeros(N, D, device=dev); scal = torch.zeros(4, device=dev)
 tau = 0.0588
 for nseg in (0, 1, 2, 4, 8):
     for it in range(2):
-        L.call("logits_bwd", 0, x, y, N, N, D, D, D, 0, D, D, LOG2E / tau, LOG2E / tau, 1 / tau, 0.0, 0.0, rs, cs, 1 / tau, None, 0.0, 0, None, dX, D, scal, nseg, st)
+        L.call("logits_bwd", 0, x, y, N, N, D, D, D, 0, D, D, LOG2E / tau, LOG2E / tau, 1 / tau, 0.0, 0.0, rs, cs, 1 / tau, 1.0, 0, None, 0.0, 0, None, dX, D, scal, nseg, st)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for it in range(3):
-        L.call("logits_bwd", 0, x, y, N, N, D, D, D, 0, D, D, LOG2E / tau, LOG2E / tau, 1 / tau, 0.0, 0.0, rs, cs, 1 / tau, None, 0.0, 0, None, dX, D, scal, nseg, st)
+        L.call("logits_bwd", 0, x, y, N, N, D, D, D, 0, D, D, LOG2E / tau, LOG2E / tau, 1 / tau, 0.0, 0.0, rs, cs, 1 / tau, 1.0, 0, None, 0.0, 0, None, dX, D, scal, nseg, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     print("bwd pass 32k nseg=%d: %.3f ms  algorithmic %.1f TFLOP/s executed %.1f TFLOP/s" % (nseg, ms, 2 * N * N * D / ms / 1e9, 6 * N * N * D / ms / 1e9), flush=True)
