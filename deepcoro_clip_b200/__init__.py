@@ -1,0 +1,15 @@
+"""deepcoro_clip_b200 — B200-native (sm_100a) contrastive head for DeepCORO_CLIP: CLIP / SigLIP losses, streaming
+retrieval metrics, Rope3D, AttentionPool and the multi-view query pool behind the reference's own interfaces.
+Hand-written CUDA (tcgen05 / TMEM / TMA) behind a C ABI (include/b200clip.h); no CPU or PyTorch fallback."""
+from .attention_pool import AttentionPool
+from .install import install, loss_table
+from .loss import (CLIPLoss, ContrastiveLoss, ContrastiveLossDDP, InfoNCELoss, SigLIPLoss, SiglipLoss,
+                   SiglipLossDDP, clip_loss)
+from .retrieval_metrics_streaming import (compute_metrics_streaming, compute_recall_at_k_streaming, streaming_topk)
+from .rope_3d import Rope3D, apply_rope_qk
+from .video_aggregator import EnhancedVideoAggregator, query_pool
+
+__all__ = ["AttentionPool", "CLIPLoss", "ContrastiveLoss", "ContrastiveLossDDP", "EnhancedVideoAggregator",
+           "InfoNCELoss", "Rope3D", "SigLIPLoss", "SiglipLoss", "SiglipLossDDP", "apply_rope_qk", "clip_loss",
+           "compute_metrics_streaming", "compute_recall_at_k_streaming", "install", "loss_table", "query_pool",
+           "streaming_topk"]

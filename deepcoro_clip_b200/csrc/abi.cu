@@ -149,4 +149,40 @@ int b200clip_recall_hits(const int32_t* counts, int rows, const int32_t* k_value
   return recall_hits(counts, rows, k_values, nk, reinterpret_cast<unsigned long long*>(hits), S(stream));
 }
 
+int b200clip_rope3d_apply(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, void* q_out, const void* k,
+                          int64_t k_sb, int64_t k_sh, int64_t k_sn, void* k_out, const void* sin_table,
+                          const void* cos_table, int dtype, int B, int heads, int N, int head_dim, int backward,
+                          void* stream) {
+  return rope3d_apply(q, q_sb, q_sh, q_sn, q_out, k, k_sb, k_sh, k_sn, k_out, sin_table, cos_table, dtype, B, heads, N,
+                      head_dim, backward, S(stream));
+}
+
+int b200clip_attnpool_splits(int B, int N) { return attnpool_splits(B, N); }
+
+int b200clip_attnpool_fwd(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
+                          const float* qt, const float* weights, int64_t w_sb, int64_t w_sh, int B, int N, int D,
+                          int heads, int splits, float* part_m, float* part_l, float* part_acc, void* stream) {
+  return attnpool_fwd(x, dtype, x_sb, x_sn, mask, mask_sb, qt, weights, w_sb, w_sh, B, N, D, heads, splits, part_m,
+                      part_l, part_acc, S(stream));
+}
+
+int b200clip_attnpool_merge(const float* part_m, const float* part_l, const float* part_acc, int B, int splits,
+                            int heads, int D, float* out, float* out_m, float* out_l, int sum_over_b, void* stream) {
+  return attnpool_merge(part_m, part_l, part_acc, B, splits, heads, D, out, out_m, out_l, sum_over_b, S(stream));
+}
+
+int b200clip_attnpool_bwd_dx(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
+                             const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l,
+                             int B, int N, int D, int heads, void* dx, float* ds, void* stream) {
+  return attnpool_bwd_dx(x, dtype, x_sb, x_sn, mask, mask_sb, qt, dxbar, xbar, m, l, B, N, D, heads, dx, ds, S(stream));
+}
+
+int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,
+                       const float* ln_b, const float* query, const uint8_t* mask, int64_t mask_sb, int B, int N, int D,
+                       float eps, float* out, const float* dout, float* dx, float* dpos, float* dln_w, float* dln_b,
+                       float* dquery, void* stream) {
+  return querypool(backward, x, x_sb, x_sn, pos, ln_w, ln_b, query, mask, mask_sb, B, N, D, eps, out, dout, dx, dpos,
+                   dln_w, dln_b, dquery, S(stream));
+}
+
 }  // extern "C"

@@ -58,6 +58,28 @@ int topk_merge(const float* ps, const int* pi, int rows, int cand, int k, float*
                cudaStream_t s);
 int recall_hits(const int* counts, int rows, const int* kvals, int nk, unsigned long long* hits, cudaStream_t s);
 
+// rope3d.cu
+int rope3d_apply(const void* q, long long qsb, long long qsh, long long qsn, void* q_out, const void* k, long long ksb,
+                 long long ksh, long long ksn, void* k_out, const void* sin_t, const void* cos_t, int dtype, int B,
+                 int Hh, int N, int Dh, int backward, cudaStream_t s);
+
+// attnpool.cu
+int attnpool_splits(int B, int N);
+int attnpool_fwd(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                 const float* qt, const float* w, long long wb, long long wh, int B, int N, int D, int H, int S,
+                 float* part_m, float* part_l, float* part_acc, cudaStream_t s);
+int attnpool_merge(const float* part_m, const float* part_l, const float* part_acc, int B, int S, int H, int D,
+                   float* out, float* out_m, float* out_l, int sum_over_b, cudaStream_t s);
+int attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                    const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
+                    int D, int H, void* dx, float* ds, cudaStream_t s);
+
+// querypool.cu
+int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,
+              const float* lnb, const float* q, const unsigned char* mask, long long mb, int B, int N, int D, float eps,
+              float* out, const float* dout, float* dx, float* dpos, float* dlnw, float* dlnb, float* dq,
+              cudaStream_t s);
+
 // tmap.cu
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                       uint32_t box_rows);

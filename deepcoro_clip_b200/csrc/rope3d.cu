@@ -1,0 +1,145 @@
+// K7: 3D axial RoPE apply (forward and backward) for q and k in ONE launch.
+//   y = x*cos + rotate_half(x)*sin   (models/rope_3d.py:13-17, 240-246); backward is the inverse rotation
+//   dx = dy*cos - rotate_half(dy)*sin. The tables are the reference's own [N, Dh] sin/cos in
+//   the tensor dtype (built once per (T,H,W) on the host side with the reference's formula and cached; 600 KB at
+//   N=3137, L2 resident), so the ~30 elementwise kernels + autograd saves of the reference become one streaming
+//   read + write of q and k: 4 * B*heads*N*Dh*sizeof(dtype) bytes.
+//   Rounding follows the reference op by op (mul, mul, add each rounded to the tensor dtype), so bf16/fp16/fp32
+//   results are bit-identical to the PyTorch module.
+// Layout: x[b, h, n, :] at b*sb + h*sh + n*sn (+ contiguous Dh), any strides (MViT hands permuted views).
+#include "common.cuh"
+#include "host_api.h"
+
+namespace b2 {
+
+template <typename T> struct RopeT;
+template <> struct RopeT<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ float rnd(float v) { return v; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct RopeT<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct RopeT<__half> {
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
+struct RopeTensor {
+  const void* in;
+  void* out;
+  long long sb, sh, sn;      // input strides (elements)
+};
+
+// one thread = VEC consecutive channels (VEC even) of one (b, h, n) row; blockIdx.y selects q / k
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+rope3d_kernel(RopeTensor tq, RopeTensor tk, const T* __restrict__ sin_t, const T* __restrict__ cos_t, int B, int Hh,
+              int N, int Dh, float sgn) {
+  const RopeTensor t = blockIdx.y == 0 ? tq : tk;
+  const int vpr = Dh / VEC;
+  const long long total = (long long)B * Hh * N * vpr;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % vpr);
+    long long row = idx / vpr;
+    const int n = (int)(row % N);
+    row /= N;
+    const int h = (int)(row % Hh);
+    const int b = (int)(row / Hh);
+    const T* src = reinterpret_cast<const T*>(t.in) + b * t.sb + h * t.sh + n * t.sn + v * VEC;
+    T* dst = reinterpret_cast<T*>(t.out) + ((((long long)b * Hh + h) * N + n) * Dh) + v * VEC;
+    const T* sp = sin_t + (long long)n * Dh + v * VEC;
+    const T* cp = cos_t + (long long)n * Dh + v * VEC;
+    float x[VEC], s[VEC], c[VEC];
+    if (VEC * sizeof(T) == 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      // 16-byte vector path
+      const uint4 xv = *reinterpret_cast<const uint4*>(src);
+      const uint4 sv = *reinterpret_cast<const uint4*>(sp);
+      const uint4 cv = *reinterpret_cast<const uint4*>(cp);
+      const T* xe = reinterpret_cast<const T*>(&xv);
+      const T* se = reinterpret_cast<const T*>(&sv);
+      const T* ce = reinterpret_cast<const T*>(&cv);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        x[i] = RopeT<T>::ld(xe + i);
+        s[i] = RopeT<T>::ld(se + i);
+        c[i] = RopeT<T>::ld(ce + i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        x[i] = RopeT<T>::ld(src + i);
+        s[i] = RopeT<T>::ld(sp + i);
+        c[i] = RopeT<T>::ld(cp + i);
+      }
+    }
+    T outv[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; i += 2) {
+      // rotate_half: r[2i] = -x[2i+1], r[2i+1] = x[2i]; every product and the sum rounded like the reference ops
+      const float a0 = RopeT<T>::rnd(__fmul_rn(x[i], c[i]));
+      const float a1 = RopeT<T>::rnd(__fmul_rn(x[i + 1], c[i + 1]));
+      float b0, b1;
+      if (sgn > 0.f) {   // forward: y = x*cos + r*sin
+        b0 = RopeT<T>::rnd(__fmul_rn(-x[i + 1], s[i]));
+        b1 = RopeT<T>::rnd(__fmul_rn(x[i], s[i + 1]));
+      } else {           // backward: dx[2i] = dy[2i]c[2i] + dy[2i+1]s[2i+1] ; dx[2i+1] = dy[2i+1]c[2i+1] - dy[2i]s[2i]
+        b0 = RopeT<T>::rnd(__fmul_rn(x[i + 1], s[i + 1]));
+        b1 = RopeT<T>::rnd(__fmul_rn(-x[i], s[i]));
+      }
+      RopeT<T>::st(&outv[i], __fadd_rn(a0, b0));
+      RopeT<T>::st(&outv[i + 1], __fadd_rn(a1, b1));
+    }
+    if (VEC * sizeof(T) == 16) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(outv);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) dst[i] = outv[i];
+    }
+  }
+}
+
+}  // namespace b2
+
+namespace b2host {
+using namespace b2;
+
+template <typename T>
+static int rope_launch(const RopeTensor& q, const RopeTensor& k, int ntens, const void* sin_t, const void* cos_t, int B,
+                       int Hh, int N, int Dh, float sgn, cudaStream_t s) {
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = Dh % VEC == 0;
+  const long long total = (long long)B * Hh * N * (vec_ok ? Dh / VEC : Dh / 2);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, ntens);
+  if (vec_ok)
+    rope3d_kernel<T, VEC><<<grid, 256, 0, s>>>(q, k, (const T*)sin_t, (const T*)cos_t, B, Hh, N, Dh, sgn);
+  else
+    rope3d_kernel<T, 2><<<grid, 256, 0, s>>>(q, k, (const T*)sin_t, (const T*)cos_t, B, Hh, N, Dh, sgn);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int rope3d_apply(const void* q, long long qsb, long long qsh, long long qsn, void* q_out, const void* k, long long ksb,
+                 long long ksh, long long ksn, void* k_out, const void* sin_t, const void* cos_t, int dtype, int B,
+                 int Hh, int N, int Dh, int backward, cudaStream_t s) {
+  if (!q || !q_out || !sin_t || !cos_t || B <= 0 || Hh <= 0 || N <= 0 || Dh <= 0 || (Dh & 1)) return B2_EINVAL;
+  RopeTensor tq{q, q_out, qsb, qsh, qsn};
+  RopeTensor tk{k, k_out, ksb, ksh, ksn};
+  const int ntens = (k && k_out) ? 2 : 1;
+  const float sgn = backward ? -1.f : 1.f;
+  switch (dtype) {
+    case 0: return rope_launch<float>(tq, tk, ntens, sin_t, cos_t, B, Hh, N, Dh, sgn, s);
+    case 1: return rope_launch<__nv_bfloat16>(tq, tk, ntens, sin_t, cos_t, B, Hh, N, Dh, sgn, s);
+    case 2: return rope_launch<__half>(tq, tk, ntens, sin_t, cos_t, B, Hh, N, Dh, sgn, s);
+    default: return B2_EINVAL;
+  }
+}
+
+}  // namespace b2host

@@ -1,0 +1,84 @@
+"""Plugs the B200 implementations into the reference's own extension points:
+
+  * ``LossRegistry`` (utils/registry.py:18-24, plain dict overwrite — last registration wins) under the same
+    ``LossType`` keys the reference registers;
+  * the module-level names ``models.video_encoder.Rope3D`` / ``AttentionPool`` / ``EnhancedVideoAggregator`` that
+    ``VideoEncoder.__init__`` instantiates (models/video_encoder.py:13, 115-140, 207-212);
+  * the function names ``compute_metrics_streaming`` / ``compute_recall_at_k_streaming`` imported by
+    runners/multitask_runner.py:35.
+
+Call ``install()`` AFTER ``register_submodules("utils.loss")`` (scripts/main.py:26-30) so that these entries are
+the last ones written."""
+from __future__ import annotations
+
+import importlib
+import sys
+from typing import Dict
+
+from . import attention_pool, loss, retrieval_metrics_streaming, rope_3d, video_aggregator
+
+# key -> class, for the two import orders the reference can end up with (SURVEY §8b "registration order hazard")
+_MAIN = {          # scripts/main.py order: utils/loss/contrastive.py registers last
+    "clip": loss.CLIPLoss, "contrastive": loss.CLIPLoss, "contrastive_ddp": loss.CLIPLoss,
+    "siglip": loss.SigLIPLoss, "siglip_pairwise": loss.SigLIPLoss, "siglip2_bce": loss.SigLIPLoss,
+    "siglip2_bce_ddp": loss.SigLIPLoss, "siglip2_multi_positive": loss.SigLIPLoss,
+    "siglip_ddp": loss.SiglipLossDDP, "InfoNCE": loss.InfoNCELoss,
+}
+_COLD = dict(_MAIN)   # cold import (alphabetical walk): utils/loss/losses.py overwrites three keys with legacy classes
+_COLD.update({"contrastive": loss.ContrastiveLoss, "contrastive_ddp": loss.ContrastiveLossDDP, "siglip": loss.SiglipLoss})
+
+
+def loss_table(semantics: str = "main") -> Dict[str, type]:
+    if semantics not in ("main", "cold"):
+        raise ValueError("semantics must be 'main' (scripts/main.py import order) or 'cold'")
+    return dict(_MAIN if semantics == "main" else _COLD)
+
+
+def install(reference_root: str | None = None, semantics: str = "main", losses: bool = True, modules: bool = True,
+            metrics: bool = True) -> dict:
+    """Registers / rebinds everything; returns a report {what: [names]} of what was replaced."""
+    if reference_root and reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    report = {"losses": [], "modules": [], "metrics": []}
+    if losses:
+        registry = importlib.import_module("utils.registry").LossRegistry
+        for key, cls in loss_table(semantics).items():
+            registry.register(key)(cls)
+            report["losses"].append(key)
+    if modules:
+        for modname in ("models.video_encoder",):
+            mod = sys.modules.get(modname)
+            if mod is None:
+                try:
+                    mod = importlib.import_module(modname)
+                except Exception:      # backbone deps (torchvision / timm) may be absent: nothing to rebind then
+                    mod = None
+            if mod is not None:
+                mod.Rope3D = rope_3d.Rope3D
+                mod.AttentionPool = attention_pool.AttentionPool
+                if hasattr(mod, "EnhancedVideoAggregator"):
+                    mod.EnhancedVideoAggregator = video_aggregator.EnhancedVideoAggregator
+                report["modules"].append(modname)
+        for modname, names in (("models.rope_3d", ("Rope3D", "apply_rope_qk")), ("models.attention_pool", ("AttentionPool",)),
+                               ("models.video_aggregator", ("EnhancedVideoAggregator",))):
+            mod = sys.modules.get(modname)
+            if mod is not None:
+                src = {"models.rope_3d": rope_3d, "models.attention_pool": attention_pool,
+                       "models.video_aggregator": video_aggregator}[modname]
+                for n in names:
+                    setattr(mod, n, getattr(src, n))
+                report["modules"].append(modname)
+    if metrics:
+        for modname in ("utils.retrieval_metrics_streaming", "runners.multitask_runner"):
+            mod = sys.modules.get(modname)
+            if mod is None and modname == "utils.retrieval_metrics_streaming":
+                try:
+                    mod = importlib.import_module(modname)
+                except Exception:
+                    mod = None
+            if mod is not None:
+                mod.compute_metrics_streaming = retrieval_metrics_streaming.compute_metrics_streaming
+                if hasattr(mod, "compute_recall_at_k_streaming"):
+                    mod.compute_recall_at_k_streaming = retrieval_metrics_streaming.compute_recall_at_k_streaming
+                report["metrics"].append(modname)
+    return report

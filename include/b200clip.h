@@ -178,6 +178,52 @@ int b200clip_topk_merge(const float* part_score, const int32_t* part_idx, int ro
 int b200clip_recall_hits(const int32_t* counts, int rows, const int32_t* k_values, int nk, uint64_t* hits,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K7  3D RoPE apply. Replaces Rope3D.forward's split / rotate_half / mul / add / cat graph and its autograd
+ *     (models/rope_3d.py:13-17, 232-250; free function apply_rope_qk :255-282).
+ *   q, k [B, heads, N, head_dim]: element strides (sb, sh, sn), head_dim contiguous; outputs contiguous, same dtype.
+ *   sin_table / cos_table [N, head_dim] in the tensor dtype (the reference's cached tables, special-token rows
+ *   cos = 1 / sin = 0). backward = 1 applies the adjoint (inverse rotation) to upstream gradients.
+ *   Every product and the sum are rounded to the tensor dtype like the reference ops => bit-identical results.
+ *   k / k_out may be NULL (single tensor).
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_rope3d_apply(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, void* q_out, const void* k,
+                          int64_t k_sb, int64_t k_sh, int64_t k_sn, void* k_out, const void* sin_table,
+                          const void* cos_table, int dtype, int B, int heads, int N, int head_dim, int backward,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K8  Attention pooling with one learnable query (models/attention_pool.py:77-93), folded form:
+ *     scores s_hn = x_n . qt_h, a_h = softmax_n(s_h), xbar_h = sum_n a_hn x_n. x [B, N, D] (D contiguous,
+ *     D*sizeof(dtype) a multiple of 512 bytes), mask [B, N] bytes (non-zero = ignore) or NULL, heads <= 16.
+ *   attnpool_fwd    : per (batch row, token split) partial (m, l, acc[heads][D]); with `weights` [B, heads, N]
+ *                     given instead of qt it computes plain weighted sums (used for dqt in the backward).
+ *   attnpool_merge  : merges the splits -> out [B, heads, D] (+ m, l [B, heads]); weighted-sum mode: part_m NULL,
+ *                     sum_over_b = 1 accumulates over the batch into out [heads, D] (caller zeroes).
+ *   attnpool_bwd_dx : dx_n = sum_h a_hn dxbar_h + ds_hn qt_h, ds_hn = a_hn (dxbar_h . x_n - dxbar_h . xbar_h);
+ *                     writes dx [B, N, D] (input dtype, contiguous) and ds [B, heads, N] fp32.
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_attnpool_splits(int B, int N);
+int b200clip_attnpool_fwd(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
+                          const float* qt, const float* weights, int64_t w_sb, int64_t w_sh, int B, int N, int D,
+                          int heads, int splits, float* part_m, float* part_l, float* part_acc, void* stream);
+int b200clip_attnpool_merge(const float* part_m, const float* part_l, const float* part_acc, int B, int splits,
+                            int heads, int D, float* out, float* out_m, float* out_l, int sum_over_b, void* stream);
+int b200clip_attnpool_bwd_dx(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
+                             const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l,
+                             int B, int N, int D, int heads, void* dx, float* ds, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).
+ *   x [B, N, D] fp32 (strides sb, sn), pos [>=N, D] or NULL, final LayerNorm (ln_w, ln_b, eps), attn_query [D],
+ *   mask [B, N] bytes (non-zero = masked view) or NULL. backward = 0: out [B, D]. backward = 1: dx [B, N, D] written,
+ *   dpos [N, D] / dln_w / dln_b / dquery [D] ACCUMULATED atomically (caller zeroes). N*D*4 + 20 N <= 200 KB.
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,
+                       const float* ln_b, const float* query, const uint8_t* mask, int64_t mask_sb, int B, int N, int D,
+                       float eps, float* out, const float* dout, float* dx, float* dpos, float* dln_w, float* dln_b,
+                       float* dquery, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

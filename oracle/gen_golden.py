@@ -163,8 +163,8 @@ def rope():
 
 def attnpool():
     for name, (B, N, D, heads, out_dim, use_mask) in {
-        "attnpool_b3_n50_d64_h8": (3, 50, 64, 8, None, False),
-        "attnpool_b4_n37_d128_h4_mask_proj": (4, 37, 128, 4, 32, True),
+        "attnpool_b3_n50_d128_h8": (3, 50, 128, 8, None, False),
+        "attnpool_b4_n37_d256_h4_mask_proj": (4, 37, 256, 4, 32, True),
     }.items():
         torch.manual_seed(50)
         mod = AttentionPool(D, num_heads=heads, output_dim=out_dim, dropout=0.0).double()
@@ -228,8 +228,6 @@ def qpool():
 
 
 if __name__ == "__main__":
-    losses()
-    retrieval()
-    rope()
-    attnpool()
-    qpool()
+    which = sys.argv[1:] or ["losses", "retrieval", "rope", "attnpool", "qpool"]
+    for name in which:
+        globals()[name]()

@@ -1,0 +1,153 @@
+"""GPU parity: Rope3D, AttentionPool and the multi-view query pool vs the reference golden vectors / the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import token_oracle as to
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.mark.parametrize("name,dtype", [("rope_f32_t2h3w4_cls", torch.float32), ("rope_f32_t3h2w2", torch.float32),
+                                        ("rope_bf16_t4h7w7_cls", torch.bfloat16)])
+def test_rope_bit_exact_with_reference_tables(name, dtype):
+    from deepcoro_clip_b200.rope_3d import apply_rope_qk
+    g = np.load(GOLDEN / f"{name}.npz")
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device=DEV).to(dtype)
+    q, k = t(g["q"]).requires_grad_(True), t(g["k"]).requires_grad_(True)
+    qr, kr = apply_rope_qk(q, k, t(g["sin"]), t(g["cos"]))
+    assert (qr.detach().float().cpu().numpy() == g["q_rot"].astype(np.float32)).all()
+    assert (kr.detach().float().cpu().numpy() == g["k_rot"].astype(np.float32)).all()
+    ((qr * t(g["gq"])).sum() + (kr * t(g["gk"])).sum()).backward()
+    assert (q.grad.float().cpu().numpy() == g["dq"].astype(np.float32)).all()
+    assert (k.grad.float().cpu().numpy() == g["dk"].astype(np.float32)).all()
+
+
+@pytest.mark.parametrize("name,dtype", [("rope_f32_t2h3w4_cls", torch.float32), ("rope_bf16_t4h7w7_cls", torch.bfloat16)])
+def test_rope_module_forward(name, dtype):
+    from deepcoro_clip_b200.rope_3d import Rope3D
+    g = np.load(GOLDEN / f"{name}.npz")
+    B, heads, T, H, W, cls = [int(x) for x in g["meta"]]
+    mod = Rope3D(96 * heads, heads).eval()
+    q = torch.tensor(g["q"], dtype=torch.float32, device=DEV).to(dtype)
+    k = torch.tensor(g["k"], dtype=torch.float32, device=DEV).to(dtype)
+    qr, kr = mod(q, k, T, H, W)                       # CLS auto-detected; tables built on the GPU
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -7    # GPU sin/cos may differ from the CPU tables by one ulp
+    assert np.abs(qr.float().cpu().numpy() - g["q_rot"]).max() <= tol * max(1.0, np.abs(g["q_rot"]).max())
+    assert np.abs(kr.float().cpu().numpy() - g["k_rot"]).max() <= tol * max(1.0, np.abs(g["k_rot"]).max())
+    # non-contiguous (permuted) views, as MViT hands them over
+    qp = q.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+    assert not qp.is_contiguous()
+    qr2, _ = mod(qp, k, T, H, W)
+    assert torch.equal(qr2, qr)
+    # mismatch -> unchanged
+    bad = torch.randn(1, heads, 7, 96, device=DEV)
+    o1, o2 = mod(bad, bad, 2, 2, 2)
+    assert o1 is bad and o2 is bad
+
+
+def test_rope_large_bf16_vs_oracle():
+    from deepcoro_clip_b200.rope_3d import Rope3D
+    T, H, W = 16, 14, 14
+    mod = Rope3D(768, 8).eval()
+    q = torch.randn(2, 8, T * H * W + 1, 96, device=DEV).bfloat16()
+    k = torch.randn(2, 8, T * H * W + 1, 96, device=DEV).bfloat16()
+    qr, kr = mod(q, k, T, H, W)
+    oq, ok = to.rope3d_forward(q.float().cpu().numpy().astype(np.float64), k.float().cpu().numpy().astype(np.float64), T, H, W)
+    # bf16 tables + bf16 roundings: ~1e-2 absolute at |x| ~ 4 (same as the reference module in bf16)
+    assert np.abs(qr.float().cpu().numpy() - oq).max() < 0.2
+    assert _rel(qr.float().cpu().numpy(), oq) < 2e-2
+
+
+@pytest.mark.parametrize("name", ["attnpool_b3_n50_d128_h8", "attnpool_b4_n37_d256_h4_mask_proj"])
+def test_attention_pool_golden(name):
+    from deepcoro_clip_b200.attention_pool import AttentionPool
+    g = np.load(GOLDEN / f"{name}.npz")
+    B, N, D = g["x"].shape
+    out_dim = g["out"].shape[1]
+    mod = AttentionPool(D, int(g["heads"]), output_dim=None if out_dim == D else out_dim).to(DEV)
+    sd = {"query": g["p_query"], "attn.in_proj_weight": g["p_in_proj_weight"], "attn.in_proj_bias": g["p_in_proj_bias"],
+          "attn.out_proj.weight": g["p_out_proj_weight"], "attn.out_proj.bias": g["p_out_proj_bias"],
+          "norm.weight": g["p_norm_weight"], "norm.bias": g["p_norm_bias"]}
+    if out_dim != D:
+        sd["proj.weight"] = g["p_proj_weight"]; sd["proj.bias"] = g["p_proj_bias"]
+    mod.load_state_dict({k: torch.tensor(v, dtype=torch.float32) for k, v in sd.items()})
+    x = torch.tensor(g["x"], dtype=torch.float32, device=DEV, requires_grad=True)
+    mask = torch.tensor(g["mask"], device=DEV) if bool(g["has_mask"]) else None
+    out = mod(x, mask)
+    assert out.shape == (B, out_dim)
+    assert _rel(out.detach().cpu().numpy(), g["out"]) < 2e-5
+    (out * torch.tensor(g["go"], dtype=torch.float32, device=DEV)).sum().backward()
+    assert _rel(x.grad.cpu().numpy(), g["dx"]) < 5e-5
+    grads = {"query": mod.query.grad, "in_proj_weight": mod.attn.in_proj_weight.grad, "in_proj_bias": mod.attn.in_proj_bias.grad,
+             "out_proj_weight": mod.attn.out_proj.weight.grad, "out_proj_bias": mod.attn.out_proj.bias.grad,
+             "norm_weight": mod.norm.weight.grad, "norm_bias": mod.norm.bias.grad}
+    for k, v in grads.items():
+        ref = g["g_" + k]
+        assert np.abs(v.cpu().numpy() - ref).max() <= 5e-5 * max(np.abs(ref).max(), 1e-3), k
+
+
+def test_attention_pool_c3_shape_bf16_vs_oracle():
+    from deepcoro_clip_b200.attention_pool import AttentionPool
+    torch.manual_seed(2)
+    mod = AttentionPool(512, 8, dropout=0.0).to(DEV)
+    x = torch.randn(4, 3136, 512, device=DEV).bfloat16().requires_grad_(True)
+    mask = torch.rand(4, 3136, device=DEV) < 0.1
+    out = mod(x, mask)
+    params = {"query": mod.query, "in_proj_weight": mod.attn.in_proj_weight, "in_proj_bias": mod.attn.in_proj_bias,
+              "out_proj_weight": mod.attn.out_proj.weight, "out_proj_bias": mod.attn.out_proj.bias,
+              "norm_weight": mod.norm.weight, "norm_bias": mod.norm.bias}
+    pn = {k: v.detach().double().cpu().numpy() for k, v in params.items()}
+    o, cache = to.attention_pool_forward(x.detach().float().cpu().numpy(), pn, 8, mask.cpu().numpy(), want_cache=True)
+    assert out.dtype == torch.bfloat16
+    assert _rel(out.float().detach().cpu().numpy(), o) < 1e-2          # bf16 output rounding
+    go = torch.randn(4, 512, device=DEV)
+    (out.float() * go).sum().backward()
+    gr = to.attention_pool_backward(go.cpu().numpy(), cache, pn)
+    assert _rel(x.grad.float().cpu().numpy(), gr["x"]) < 1e-2
+
+
+@pytest.mark.parametrize("name", ["qpool_b5_n4_d64", "qpool_b6_n5_d128_mask"])
+def test_query_pool_golden(name):
+    from deepcoro_clip_b200.video_aggregator import EnhancedVideoAggregator
+    g = np.load(GOLDEN / f"{name}.npz")
+    B, N, D = g["x"].shape
+    mod = EnhancedVideoAggregator(D, num_heads=4, dropout=0.0, aggregator_depth=0, max_segments=16).to(DEV)
+    mod.load_state_dict({"pos_encoding": torch.tensor(g["pos"], dtype=torch.float32),
+                         "final_ln.weight": torch.tensor(g["ln_w"], dtype=torch.float32),
+                         "final_ln.bias": torch.tensor(g["ln_b"], dtype=torch.float32),
+                         "attn_query": torch.tensor(g["attn_query"], dtype=torch.float32)})
+    x = torch.tensor(g["x"], dtype=torch.float32, device=DEV, requires_grad=True)
+    mask = torch.tensor(g["mask"], device=DEV) if bool(g["has_mask"]) else None
+    out = mod(x, mask)
+    assert _rel(out.detach().cpu().numpy(), g["out"]) < 1e-5
+    (out * torch.tensor(g["go"], dtype=torch.float32, device=DEV)).sum().backward()
+    assert _rel(x.grad.cpu().numpy(), g["dx"]) < 2e-5
+    assert _rel(mod.pos_encoding.grad.cpu().numpy(), g["g_pos"]) < 2e-5
+    assert _rel(mod.final_ln.weight.grad.cpu().numpy(), g["g_ln_w"]) < 2e-5
+    assert _rel(mod.final_ln.bias.grad.cpu().numpy(), g["g_ln_b"]) < 2e-5
+    assert _rel(mod.attn_query.grad.cpu().numpy(), g["g_attn_query"]) < 2e-5
+
+
+def test_aggregator_with_blocks_matches_torch_composition():
+    """depth > 0: blocks stay PyTorch; the fused tail must equal the unfused torch tail on the same block output."""
+    from deepcoro_clip_b200.video_aggregator import EnhancedVideoAggregator
+    torch.manual_seed(0)
+    mod = EnhancedVideoAggregator(512, num_heads=4, dropout=0.0, aggregator_depth=2, max_segments=16).to(DEV).eval()
+    x = torch.randn(8, 4, 512, device=DEV)
+    mask = torch.zeros(8, 4, dtype=torch.bool, device=DEV); mask[3, 2:] = True
+    out = mod(x, mask)
+    h = x + mod.pos_encoding[:, :4]
+    for b in mod.blocks:
+        h = b(h, key_padding_mask=mask)
+    h = mod.final_ln(h).masked_fill(mask.unsqueeze(-1), 0.0)
+    s = (mod.attn_query.expand(8, -1, -1) @ h.transpose(1, 2)).masked_fill(mask.unsqueeze(1), float("-inf"))
+    ref = (torch.softmax(s, -1) @ h).squeeze(1)
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-5)

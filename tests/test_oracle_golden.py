@@ -138,7 +138,7 @@ def test_rope_oracle_mismatch_returns_inputs():
     assert qr is q and kr is q
 
 
-@pytest.mark.parametrize("name", ["attnpool_b3_n50_d64_h8", "attnpool_b4_n37_d128_h4_mask_proj"])
+@pytest.mark.parametrize("name", ["attnpool_b3_n50_d128_h8", "attnpool_b4_n37_d256_h4_mask_proj"])
 def test_attention_pool_oracle(name):
     g = _load(name)
     params = {k[2:]: g[k] for k in g.files if k.startswith("p_")}
