@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops
+from . import dist_plan, ops
 from ._lib import B200ClipError
 
 BW_CLIP, BW_GATED, BW_SIGLIP = 0, 1, 2
@@ -32,18 +32,8 @@ BW_CLIP, BW_GATED, BW_SIGLIP = 0, 1, 2
 # --------------------------------------------------------------------------------------------------
 # helpers
 # --------------------------------------------------------------------------------------------------
-def _world(use_ddp: bool = True, group=None):
-    if use_ddp and dist.is_available() and dist.is_initialized():
-        return dist.get_world_size(group), dist.get_rank(group)
-    return 1, 0
-
-
-def _all_gather_rows(x: torch.Tensor, world: int, group=None) -> torch.Tensor:
-    if world == 1:
-        return x
-    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
-    return out
+_world = dist_plan.world
+_all_gather_rows = dist_plan.gather_rows
 
 
 def _pick_precision(precision: str, n_rows: int, n_cols: int) -> bool:
@@ -111,7 +101,7 @@ class _ClipLossFn(torch.autograd.Function):
             tsum = ops.colsum_bf16(tall[:, K - Kp:], N, D)
             unif_tgt = (eps / N) * torch.dot(vsum.double(), tsum.double()) * inv_tau
             sum_tgt = sum_tgt + unif_tgt
-        loss = (0.5 / N) * (acc[0] + acc[1]) - sum_tgt / N
+        loss = dist_plan.clip_loss_from_sums(acc[0], acc[1], sum_tgt, N)
 
         ctx.save_for_backward(video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, dots,
                               vsum, tsum, unif_tgt)

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import dist_plan, ops
 from ._lib import call, stream_ptr
 
 
@@ -43,13 +43,8 @@ def _operands(video, text, normalize: bool, precision: str):
 
 
 def _shard(M: int, use_ddp: bool, group=None) -> Tuple[int, int, int, int]:
-    if use_ddp and dist.is_available() and dist.is_initialized():
-        W, r = dist.get_world_size(group), dist.get_rank(group)
-    else:
-        W, r = 1, 0
-    per = (M + W - 1) // W
-    lo = min(r * per, M)
-    hi = min(lo + per, M)
+    W, r = dist_plan.world(use_ddp, group)
+    lo, hi = dist_plan.text_shard(M, W, r)
     return W, r, lo, hi
 
 

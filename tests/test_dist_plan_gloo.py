@@ -1,0 +1,83 @@
+"""CPU, world_size 2, gloo: the host-side sharding plan (deepcoro_clip_b200/dist_plan.py) reproduces the reference's
+DDP semantics when each rank's kernel outputs are emulated with the numpy oracle:
+every rank obtains the FULL global loss; retrieval rank counts over text shards add up to the global ranks."""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import contrastive_oracle as co
+from oracle import retrieval_oracle as ro
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deepcoro_clip_b200 import dist_plan as dp
+        assert dp.world() == (world, rank)
+        B, D, tau = 24, 32, 0.07
+        N = B * world
+        rng = np.random.default_rng(0)                        # identical global data on every rank
+        v = rng.standard_normal((N, D)); t = rng.standard_normal((N, D))
+        lo, hi = dp.row_slab(rank, B)
+        vh, _ = co.l2_normalize(v); th, _ = co.l2_normalize(t)
+        # --- what the rank's kernels would produce for its row slab (oracle stand-in) ---
+        vall = dp.gather_rows(torch.tensor(vh[lo:hi]), world)
+        tall = dp.gather_rows(torch.tensor(th[lo:hi]), world)
+        assert np.allclose(vall.numpy(), vh) and np.allclose(tall.numpy(), th)      # rank-major concatenation
+        L = vh[lo:hi] @ tall.numpy().T / tau                                         # slab logits [B, N]
+        shift = 1.0 / tau
+        rowsum = torch.tensor(np.exp(L - shift).sum(1))
+        colsum = torch.tensor(np.exp(L - shift).sum(0))
+        diag = torch.tensor([L[np.arange(B), lo + np.arange(B)].sum()])
+        # --- the plan's collectives + assembly ---
+        dp.reduce_sum_(colsum, world)
+        rowsum_all = dp.gather_rows(rowsum, world)
+        dp.reduce_sum_(diag, world)
+        sum_r = (torch.log(rowsum_all) + shift).sum()
+        sum_c = (torch.log(colsum) + shift).sum()
+        loss = dp.clip_loss_from_sums(sum_r, sum_c, diag[0], N)
+        ref = co.clip_loss(v, t, math.log(tau), want_grads=False)["loss"]
+        assert abs(float(loss) - ref) < 1e-10, (float(loss), ref)
+        # --- retrieval: text shards, rank counts all-reduced ---
+        M = 37
+        tv = ro.exact_grid_embeddings(50, 16, 1); tt = ro.exact_grid_embeddings(M, 16, 2)
+        tt[5] = tt[30]                                        # exact tie across the two shards
+        gt = np.random.default_rng(3).integers(0, M, size=50); gt[0] = 30; gt[1] = 5
+        s_lo, s_hi = dp.text_shard(M, world, rank)
+        sim = ro.similarity(tv, tt)
+        sg = sim[np.arange(50), gt][:, None]
+        cols = np.arange(M)[None, :]
+        better = (sim > sg) | ((sim == sg) & (cols < gt[:, None]))
+        counts = torch.tensor(better[:, s_lo:s_hi].sum(1))
+        dp.reduce_sum_(counts, world)
+        assert (counts.numpy() + 1 == ro.gt_ranks(sim, gt)).all()
+        covered = dp.gather_rows(torch.tensor([[s_lo, s_hi]]), world).numpy()
+        assert covered[0, 0] == 0 and covered[-1, 1] == M and (covered[1:, 0] == covered[:-1, 1]).all()
+        out[rank] = float(loss)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_plan():
+    world = 2
+    port = 29000 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == world and abs(out[0] - out[1]) < 1e-12       # every rank returns the same full loss
+
+
+def test_shard_helpers_single_process():
+    from deepcoro_clip_b200 import dist_plan as dp
+    assert dp.world() == (1, 0)
+    assert dp.row_slab(3, 128) == (384, 512)
+    spans = [dp.text_shard(32473, 8, r) for r in range(8)]
+    assert spans[0][0] == 0 and spans[-1][1] == 32473 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert dp.text_shard(3, 8, 7) == (3, 3)                # more ranks than rows: empty shard
+    x = torch.arange(6).view(3, 2)
+    assert dp.gather_rows(x, 1) is x
