@@ -32,6 +32,13 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
                int diag_off, float* diag_corr,
                float* dX, int ldd, double* scal, int nseg_hint, cudaStream_t stream);
 
+// logits_bwd2.cu: the same contract on CTA pairs (tcgen05 cta_group::2); Kp <= 512, Dp % 128 == 0, hp == 0 only
+int logits_bwd_pair(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off, int ldx,
+                    int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
+                    const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
+                    const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
+                    int nseg_hint, cudaStream_t stream);
+
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
 int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s);

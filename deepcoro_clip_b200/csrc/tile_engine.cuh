@@ -116,7 +116,9 @@ te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]          epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps the MMA /
+  // TMA operands in uniform registers (a `lane == 0` branch makes it wrap every UTCHMMA in a ~100-cycle waterfall loop)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   const int kchunks = g.Kp / TE_BK;
@@ -149,7 +151,7 @@ te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     setmaxnreg_dec<40>();
     if (warp == 0) {
       // ===================== TMA producer =====================
-      if (lane == 0) {
+      if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
         TileSeq seq;
@@ -171,7 +173,7 @@ te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      if (lane == 0) {
+      if (elect_one()) {
         constexpr uint32_t idesc = make_idesc_bf16(TE_BM, TE_BN, 0, 0);
         int stage = 0;
         uint32_t phase = 0;

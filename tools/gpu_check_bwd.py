@@ -20,7 +20,7 @@ def run(mode, Nx, Ny, D, tau=0.0588, nseg=0, bias=-3.0):
     rs = torch.rand(Nx, device=dev) * 0.5 + 0.5
     cs = torch.rand(Ny, device=dev) * 0.5 + 0.5
     dX = torch.zeros(Nx, D, device=dev)
-    scal = torch.zeros(4, device=dev)
+    scal = torch.zeros(4, device=dev, dtype=torch.float64)
     wneg_c = 0.37
     L.call("logits_bwd", mode, x, y, Nx, Ny, Dp, Dp, D, 0, Dp, Dp, scale2, shift2, 1.0 / tau, bias, wneg_c, rs, cs,
            1.0 / tau, 1.0, 0, None, 0.0, 0, None, dX, D, scal, nseg, st)
@@ -58,7 +58,7 @@ N, D = 32768, 512
 x = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=-1).bfloat16()
 y = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=-1).bfloat16()
 rs = torch.rand(N, device=dev); cs = torch.rand(N, device=dev)
-dX = torch.zeros(N, D, device=dev); scal = torch.zeros(4, device=dev)
+dX = torch.zeros(N, D, device=dev); scal = torch.zeros(4, device=dev, dtype=torch.float64)
 tau = 0.0588
 for nseg in (0, 1, 2, 4, 8):
     for it in range(2):
