@@ -55,6 +55,17 @@ int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const i
   return rowdot_bf16(a, lda, b, ldb, reinterpret_cast<const long long*>(idx), rows, b_rows, K, out, S(stream));
 }
 
+int b200clip_gather_rows_bf16(const void* src, int lds, const int64_t* idx, int rows, int src_rows, int K, void* dst,
+                              int ldd, void* stream) {
+  if (!src || !idx || !dst) return B2_EINVAL;
+  return gather_rows_bf16(src, lds, reinterpret_cast<const long long*>(idx), rows, src_rows, K, dst, ldd, S(stream));
+}
+
+int b200clip_rowdot_tc(const void* a, int lda, const void* b, int ldb, int rows, int Kp, float* out, void* stream) {
+  if (!a || !b || !out || rows <= 0) return B2_EINVAL;
+  return rowdot_tc(a, b, rows, Kp, lda, ldb, out, S(stream));
+}
+
 int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
                             float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag,
                             int diag_off, void* stream) {

@@ -14,6 +14,8 @@ int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, co
                const float* usum, float gscale, float ucoef, const float* dev_omul, const float* dev_gmul, int rows,
                int dim, float* dx, long lddx, cudaStream_t s);
 int colsum_bf16(const void* xh, int ld, int rows, int dim, float* out, cudaStream_t s);
+int gather_rows_bf16(const void* src, int lds, const long long* idx, int rows, int src_rows, int K, void* dst, int ldd,
+                     cudaStream_t s);
 int rowdot_bf16(const void* a, int lda, const void* b, int ldb, const long long* idx, int rows, int b_rows, int K,
                 float* out, cudaStream_t s);
 
@@ -21,6 +23,7 @@ int rowdot_bf16(const void* a, int lda, const void* b, int ldb, const long long*
 int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
                    float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag, int diag_off,
                    cudaStream_t stream);
+int rowdot_tc(const void* A, const void* B, int rows, int Kp, int lda, int ldb, float* out, cudaStream_t stream);
 int logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
                 int max_ctas, cudaStream_t stream);
 

@@ -144,6 +144,19 @@ rowdot_bf16_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bflo
   if (lane == 0) out[warp] = s;
 }
 
+// dst[r, :K] = src[idx[r], :K] (bf16 operand rows, 16-byte vectors; rows with an out-of-range index are zeroed)
+__global__ void __launch_bounds__(256)
+gather_rows_bf16_kernel(const uint4* __restrict__ src, int lds16, const long long* __restrict__ idx, int rows,
+                        int src_rows, int k16, uint4* __restrict__ dst, int ldd16) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const long long r = idx[warp];
+  const bool ok = r >= 0 && r < src_rows;
+  for (int c = lane; c < k16; c += 32)
+    dst[(size_t)warp * ldd16 + c] = ok ? src[(size_t)r * lds16 + c] : make_uint4(0u, 0u, 0u, 0u);
+}
+
 }  // namespace b2
 
 namespace b2host {
@@ -198,6 +211,14 @@ int colsum_bf16(const void* xh, int ld, int rows, int dim, float* out, cudaStrea
   if (rows <= 0 || dim <= 0) return B2_EINVAL;
   dim3 grid((dim + 255) / 256, rows < 256 ? 1 : 64);
   colsum_bf16_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)xh, ld, rows, dim, out);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int gather_rows_bf16(const void* src, int lds, const long long* idx, int rows, int src_rows, int K, void* dst, int ldd,
+                     cudaStream_t s) {
+  if (rows <= 0 || K <= 0 || (K & 7) || (lds & 7) || (ldd & 7)) return B2_EINVAL;
+  gather_rows_bf16_kernel<<<(rows + 7) / 8, 256, 0, s>>>((const uint4*)src, lds / 8, idx, rows, src_rows, K / 8,
+                                                         (uint4*)dst, ldd / 8);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

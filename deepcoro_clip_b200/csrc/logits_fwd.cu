@@ -101,6 +101,29 @@ struct LseEpi {
   }
 };
 
+// out[i] = S[i, i] exactly as the tensor core produces it (used with TeShape::diag: only the diagonal tiles run).
+struct DiagParams {
+  float* out;
+};
+struct DiagEpi {
+  using Params = DiagParams;
+  struct State {};
+  __device__ static __forceinline__ void init(State&, const Params&) {}
+  __device__ static __forceinline__ void begin_outer(State&, const Params&, int, const TeCtx&) {}
+  __device__ static __forceinline__ void chunk(State&, const Params& p, const TeCtx& ctx, int c,
+                                               const uint32_t (&acc)[32]) {
+    const int d = ctx.row - (ctx.col0 + c * 32);
+    if (d >= 0 && d < 32 && ctx.row_ok) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v = (e == d) ? acc[e] : v;
+      p.out[ctx.row] = __uint_as_float(v);
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State&, const Params&, const TeCtx&) {}
+  __device__ static __forceinline__ void end_outer(State&, const Params&, int, const TeCtx&) {}
+};
+
 // Debug / validation epilogue: dumps the raw fp32 S tile to global memory (only used by the self test).
 struct DumpParams {
   float* out;
@@ -137,15 +160,17 @@ int make_shape(TeShape& g, int Ma, int Nb, int Kp) {
   g.m_tiles = (Ma + TE_BM - 1) / TE_BM;
   g.n_blocks = (Nb + TE_BN - 1) / TE_BN;
   g.segs = 0;
+  g.diag = 0;
   return B2_OK;
 }
 
 template <class Epi, bool kOuterIsB>
 static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb,
-                     const typename Epi::Params& ep, int max_ctas, cudaStream_t stream) {
+                     const typename Epi::Params& ep, int max_ctas, cudaStream_t stream, int diag = 0) {
   TeShape g;
   int rc = make_shape(g, Ma, Nb, Kp);
   if (rc) return rc;
+  g.diag = diag;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, TE_BN))) return rc;
@@ -156,7 +181,7 @@ static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int l
       return B2_ECUDA;
     attr_done = true;
   }
-  long long total = (long long)g.m_tiles * g.n_blocks;
+  long long total = diag ? (long long)g.m_tiles : (long long)g.m_tiles * g.n_blocks;
   int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (total < grid) grid = (int)total;
@@ -170,6 +195,13 @@ int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda
   LseParams p{scale2, shift2, rowsum, colsum, gated, dyn, diag, diag_off};
   if (gated) return launch_te<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
   return launch_te<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
+}
+
+// out[i] = (A[i,:] . B[i,:]) with the tensor core's own rounding: bit-identical to the value any S = A B^T tile of the
+// engine produces for that pair (same k-chunk order), which a CUDA-core dot product is not.
+int rowdot_tc(const void* A, const void* B, int rows, int Kp, int lda, int ldb, float* out, cudaStream_t stream) {
+  DiagParams p{out};
+  return launch_te<DiagEpi, false>(A, B, rows, rows, Kp, lda, ldb, p, 0, stream, 1);
 }
 
 int logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,

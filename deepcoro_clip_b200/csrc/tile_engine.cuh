@@ -44,6 +44,7 @@ struct TeShape {
   int n_blocks;  // ceil(Nb / 256)
   int segs;      // 0: each CTA takes one contiguous range of the (outer, inner) tile order (long sweeps);
                  // s > 0: work items = (outer, segment of the inner sweep), items dealt round-robin to CTAs
+  int diag;      // 1: only the tiles crossed by the main diagonal (tile t = A tile t x B block t/2); segs must be 0
 };
 
 // Identical tile sequence for the producer, MMA and epilogue roles of one CTA.
@@ -51,7 +52,10 @@ struct TileSeq {
   int inner_n, segs, items, item, stride;   // item mode
   int t, t1;                                // contiguous mode
   int i, i1, outer, seg;
+  bool diag, diag_outer_is_b;
   __device__ __forceinline__ void init(const TeShape& g, bool outer_is_b) {
+    diag = g.diag != 0;
+    diag_outer_is_b = outer_is_b;
     inner_n = outer_is_b ? g.m_tiles : g.n_blocks;
     const int outer_n = outer_is_b ? g.n_blocks : g.m_tiles;
     segs = g.segs;
@@ -61,7 +65,7 @@ struct TileSeq {
       stride = gridDim.x;
       i = i1 = 0;
     } else {
-      const long long total = (long long)g.m_tiles * g.n_blocks;
+      const long long total = diag ? (long long)g.m_tiles : (long long)g.m_tiles * g.n_blocks;
       t = (int)(total * blockIdx.x / gridDim.x);
       t1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
     }
@@ -81,6 +85,14 @@ struct TileSeq {
       return true;
     }
     if (t >= t1) return false;
+    if (diag) {
+      const int mt = t, nb = (t * TE_BM) / TE_BN;
+      o = diag_outer_is_b ? nb : mt;
+      in = diag_outer_is_b ? mt : nb;
+      sg = 0;
+      ++t;
+      return true;
+    }
     o = t / inner_n;
     in = t - o * inner_n;
     sg = 0;

@@ -57,8 +57,11 @@ def _sweep(vop, top, gt, k: int, use_ddp: bool, group=None):
     counts = sgt = gt64 = None
     if gt is not None:
         gt64 = gt.to(device=dev, dtype=torch.int64).contiguous()
+        # ground-truth similarity with the tensor core's own rounding (ties with duplicate texts stay exact ties)
         sgt = torch.empty(N, dtype=torch.float32, device=dev)
-        call("rowdot_bf16", vop, vop.stride(0), top, top.stride(0), gt64, N, M, K, sgt, st)
+        tg = torch.empty((N, K), dtype=torch.bfloat16, device=dev)
+        call("gather_rows_bf16", top, top.stride(0), gt64, N, M, K, tg, K, st)
+        call("rowdot_tc", vop, vop.stride(0), tg, K, N, K, sgt, st)
         counts = torch.zeros(N, dtype=torch.int32, device=dev)
     k = min(k, M)
     Ms = hi - lo

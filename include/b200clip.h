@@ -71,6 +71,15 @@ int b200clip_colsum_bf16(const void* operand, int ld, int rows, int dim, float* 
 int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const int64_t* idx, int rows,
                          int b_rows, int K, float* out, void* stream);
 
+/* dst[r, :K] = src[idx[r], :K]  (bf16 operand rows; K, lds, ldd multiples of 8; out-of-range idx -> zero row) */
+int b200clip_gather_rows_bf16(const void* src, int lds, const int64_t* idx, int rows, int src_rows, int K, void* dst,
+                              int ldd, void* stream);
+/* out[r] = a[r, :Kp] . b[r, :Kp] computed by the tcgen05 tile engine (diagonal tiles only): BIT-IDENTICAL to the value
+ * every similarity tile of retrieval_sweep / logits_* produces for that pair, which a CUDA-core dot product is not.
+ * The ground-truth similarity of the rank counts (retrieval_metrics_streaming.py:151-166 compares s_ij with s_i,gt)
+ * must come from here so that exact duplicates of the ground-truth text tie exactly. */
+int b200clip_rowdot_tc(const void* a, int lda, const void* b, int ldb, int rows, int Kp, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2  Fused logits forward for the softmax-CE losses. Replaces matmul -> /temp -> 2x cross_entropy
  *     (utils/loss/contrastive.py:150-162; losses.py:50-62, 143-156; gated: losses.py:195-210, 258-274).

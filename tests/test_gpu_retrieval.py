@@ -110,3 +110,33 @@ def test_gaussian_normalised_counts_match_oracle():
         assert m[k] == o[k]
     assert abs(m["MRR_V2T"] - o["MRR_V2T"]) < 1e-7
     assert abs(m["alignment_score"] - o["alignment_score"]) < 1e-6
+
+
+def test_duplicate_texts_tie_exactly_after_normalisation():
+    """Inexact (Gaussian, L2-normalised) embeddings with duplicated text rows: the duplicates of the ground truth must
+    tie EXACTLY with it (ground-truth similarity taken from the tensor core, not from a CUDA-core dot product), so the
+    rank is 1 + the number of duplicates with a lower index, whatever the rounding."""
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_metrics_streaming, streaming_topk
+    rng = np.random.default_rng(21)
+    M, D = 500, 512
+    t = rng.standard_normal((M, D)).astype(np.float32)
+    t[100:150] = t[0:50]
+    t[300:325] = t[0:25]
+    gt = np.concatenate([np.arange(0, 50), np.arange(100, 150), np.arange(300, 325)])
+    gt = np.tile(gt, 8)
+    v = (t[gt] + 0.1 * rng.standard_normal((len(gt), D))).astype(np.float32)
+    expect = np.where(gt >= 300, 3, np.where(gt >= 100, 2, 1))
+    from deepcoro_clip_b200 import retrieval_metrics_streaming as rms
+    keep = []
+    vop, top, _, _, _ = rms._operands(_t(v), _t(t), True, "auto")
+    rms._recall_from_operands(vop, top, _t(gt), [1, 2, 3], False, None, keep)
+    assert (keep[0].cpu().numpy() + 1 == expect).all()
+    m = compute_metrics_streaming(_t(v), _t(t), _t(gt), k_values=[1, 2, 3])
+    assert m["Recall@1"] == 100.0 * (expect <= 1).mean() and m["Recall@3"] == 100.0
+    assert abs(m["MRR_V2T"] - (1.0 / expect).mean()) < 1e-12
+    s, i = streaming_topk(_t(v), _t(t), 3, normalize=True)
+    i = i.cpu().numpy()
+    base = gt % 100
+    trip = base < 25
+    assert (i[trip] == np.stack([base[trip], base[trip] + 100, base[trip] + 300], 1)).all()
+    assert (i[~trip][:, :2] == np.stack([base[~trip], base[~trip] + 100], 1)).all()
