@@ -57,7 +57,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -106,6 +106,48 @@ def cpu_reference_step(N: int, D: int, steps: int, warmup: int):
     return min(ts), sum(ts) / len(ts)
 
 
+def retrieval_leg(dev, world, rank):
+    """recall@1/5/10 + MRR over the 203,808 x 32,473 x 512 sweep (BASELINE config 4): exact-grid embeddings (entries
+    k/128, exact in bf16, every dot product exact in fp32 in any order), text database sharded by rows across ranks.
+    Timed through the public API (operand packing, tensor-core ground-truth similarity, sweep, rank counts all-reduced,
+    recall hits, MRR on the host in float64)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_recall_at_k_streaming
+    Nv, M, D = 203808, 32473, 512
+    g = torch.Generator(device=dev).manual_seed(3)
+    v = torch.randint(-127, 128, (Nv, D), device=dev, generator=g).float() / 128
+    t = torch.randint(-127, 128, (M, D), device=dev, generator=g).float() / 128
+    gt = torch.randint(0, M, (Nv,), device=dev, generator=g)
+
+    def once():
+        keep = []
+        r = compute_recall_at_k_streaming(v, t, gt, k_values=[1, 5, 10], precision="bf16", _counts_out=keep)
+        ranks = keep[0].cpu().numpy().astype(np.float64) + 1.0
+        r["MRR_V2T"] = float(np.cumsum(1.0 / ranks)[-1] / Nv)
+        return r
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        r = once()
+    e1.record(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    bf16_burst, _, _, src = peaks()
+    tf = 2.0 * Nv * M * D / (ms * 1e-3) / 1e12
+    return {"metric": "streaming retrieval recall@1/5/10 + MRR", "value": Nv * M / (ms * 1e-3) / 1e9, "unit": "Gsim/s",
+            "ms_per_sweep": ms, "n_video": Nv, "n_text": M, "dim": D, "text_shards": world, "achieved_tflops": tf,
+            "frac_of_bf16_peak": tf / bf16_burst / world, "peak_source": src, "recall@1": r["Recall@1"], "mrr": r["MRR_V2T"]}
+
+
 def run_reference(args, N, D):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -137,6 +179,7 @@ def main():
     ap.add_argument("--workload", default="clip32k", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-retrieval", action="store_true")
     args = ap.parse_args()
     N, D = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -201,16 +244,23 @@ def main():
     loss_val = loss.item()
 
     # ---------------- e2e: pinned host inputs in, loss out, every step ----------------
-    def e2e_step():
-        vv = v_host.to(dev, non_blocking=True).requires_grad_(True)
-        tt = t_host.to(dev, non_blocking=True).requires_grad_(True)
-        return step(vv, tt).to("cpu", non_blocking=False)
-    for _ in range(3):
-        e2e_step()
+    # Public API: HostBatchPrefetcher double-buffers the H2D copies of step k+1 behind step k's kernels; every step's
+    # copies (2 x B x D fp32 from pinned memory) and its 4-byte loss read-back are inside the timed region.
+    from deepcoro_clip_b200 import HostBatchPrefetcher
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_loop(n):
+        pf = HostBatchPrefetcher(((v_host, t_host) for _ in range(n)), dev)
+        for batch in pf:
+            vv = batch[0].requires_grad_(True); tt = batch[1].requires_grad_(True)
+            loss_host.copy_(step(vv, tt).detach().reshape(1), non_blocking=True)
+            pf.release(batch)
+            vv.requires_grad_(False); tt.requires_grad_(False)
+            torch.cuda.current_stream().synchronize()          # the step's result is on the host before the next step
+    e2e_loop(3)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
     e1.record()
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -239,14 +289,29 @@ def main():
         kms = e0.elapsed_time(e1) / reps
         alg = 2.0 * B * N * D                      # algorithmic FLOPs of one launch (one gradient GEMM; recompute not counted)
         achieved = alg / (kms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "bw_kernel<CLIP> (logits_bwd)", "achieved": achieved, "peak": bf16_burst,
-                "unit": "TFLOP/s", "frac": achieved / bf16_burst, "traffic": None, "peak_source": src,
-                "ms_per_launch": kms, "executed_tflops": 3 * achieved,
-                "note": "algorithmic = 2*B*N*D per launch (SURVEY 8d: recompute and the second d-half pass not counted)"}
+        pair = Kp <= 512 and Kp % 128 == 0 and os.environ.get("B200CLIP_BWD_PAIR", "1") != "0"
+        traffic = None
+        prof = ROOT / "profiles" / "r01c_bw2_kernel_ncu_full_summary.json"
+        if pair and world == 1 and args.workload == "clip32k" and prof.exists():
+            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+        dparts = (Kp + 255) // 256
+        roof = {"bound": "tensor", "kernel": ("bw2_kernel<CLIP> (logits_bwd, CTA pairs, cta_group::2)" if pair else
+                                              "bw_kernel<CLIP> (logits_bwd, single CTA)"),
+                "achieved": achieved, "peak": bf16_burst,
+                "unit": "TFLOP/s", "frac": achieved / bf16_burst, "traffic": traffic, "peak_source": src,
+                "ms_per_launch": kms, "executed_tflops": (1 + dparts) * achieved,
+                "note": "algorithmic = 2*B*N*D per launch (SURVEY 8d: the S recompute of each 256-column half of D is "
+                        "executed but not counted); traffic = dram read+write bytes per launch from the committed "
+                        "ncu --set full capture (profiles/r01c_*)"}
         step_alg = 6.0 * B * N * D
         roof["step_algorithmic_tflops"] = step_alg / (ms_per_step * 1e-3) / 1e12
         roof["step_frac_of_peak"] = roof["step_algorithmic_tflops"] / bf16_sust
         roof["step_peak"] = bf16_sust
+
+    # ---------------- second half of BASELINE's metric: streaming retrieval Gsim/s (C4 sweep) ----------------
+    retr = None
+    if not args.no_retrieval:
+        retr = retrieval_leg(dev, world, rank)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -268,6 +333,7 @@ def main():
             "e2e": {"value": N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 2 * B * D * 4 * world, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches, "loss": loss_val, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "retrieval": retr,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -104,6 +104,73 @@ rope3d_kernel(RopeTensor tq, RopeTensor tk, const T* __restrict__ sin_t, const T
   }
 }
 
+// Fast path (16-byte vectors): one thread = one 16-byte vector position (n, v) of the [N, Dh] plane, kept for RPB
+// consecutive (b, h) rows, so the sin / cos vectors are loaded once per thread and ROPE_UNROLL independent 16-byte row
+// loads are in flight per thread; a warp reads 512 contiguous bytes of one row per load. grid = (plane chunks,
+// row groups, q|k). All index math is 32-bit.
+constexpr int ROPE_UNROLL = 4;
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope3d_plane_kernel(RopeTensor tq, RopeTensor tk, const T* __restrict__ sin_t, const T* __restrict__ cos_t, int rows,
+                    int Hh, int N, int Dh, int rpb, float sgn) {
+  constexpr int VEC = 16 / sizeof(T);
+  const RopeTensor t = blockIdx.z == 0 ? tq : tk;
+  const int vpr = Dh / VEC;
+  const int pv = blockIdx.x * blockDim.x + threadIdx.x;        // vector index inside the [N, Dh] plane
+  if (pv >= N * vpr) return;
+  const int n = pv / vpr, v = pv - n * vpr;
+  float s[VEC], c[VEC];
+  {
+    const uint4 sv = *reinterpret_cast<const uint4*>(sin_t + (size_t)pv * VEC);
+    const uint4 cv = *reinterpret_cast<const uint4*>(cos_t + (size_t)pv * VEC);
+    const T* se = reinterpret_cast<const T*>(&sv);
+    const T* ce = reinterpret_cast<const T*>(&cv);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      s[i] = RopeT<T>::ld(se + i);
+      c[i] = RopeT<T>::ld(ce + i);
+    }
+  }
+  const int r0 = blockIdx.y * rpb;
+  const int r1 = min(rows, r0 + rpb);
+  const long long in_off = (long long)n * t.sn + v * VEC;
+  const size_t out_off = (size_t)n * Dh + v * VEC;
+  for (int r = r0; r < r1; r += ROPE_UNROLL) {
+    uint4 xv[ROPE_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ROPE_UNROLL; ++u) {
+      const int rr = min(r + u, r1 - 1);
+      const int b = rr / Hh, h = rr - b * Hh;
+      xv[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(t.in) + b * t.sb + h * t.sh + in_off);
+    }
+#pragma unroll
+    for (int u = 0; u < ROPE_UNROLL; ++u) {
+      if (r + u < r1) {
+        const T* xe = reinterpret_cast<const T*>(&xv[u]);
+        T outv[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; i += 2) {
+          const float x0 = RopeT<T>::ld(xe + i), x1 = RopeT<T>::ld(xe + i + 1);
+          const float a0 = RopeT<T>::rnd(__fmul_rn(x0, c[i]));
+          const float a1 = RopeT<T>::rnd(__fmul_rn(x1, c[i + 1]));
+          float b0, b1;
+          if (sgn > 0.f) {
+            b0 = RopeT<T>::rnd(__fmul_rn(-x1, s[i]));
+            b1 = RopeT<T>::rnd(__fmul_rn(x0, s[i + 1]));
+          } else {
+            b0 = RopeT<T>::rnd(__fmul_rn(x1, s[i + 1]));
+            b1 = RopeT<T>::rnd(__fmul_rn(-x0, s[i]));
+          }
+          RopeT<T>::st(&outv[i], __fadd_rn(a0, b0));
+          RopeT<T>::st(&outv[i + 1], __fadd_rn(a1, b1));
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<T*>(t.out) + (size_t)(r + u) * N * Dh + out_off) =
+            *reinterpret_cast<const uint4*>(outv);
+      }
+    }
+  }
+}
+
 }  // namespace b2
 
 namespace b2host {
@@ -114,6 +181,26 @@ static int rope_launch(const RopeTensor& q, const RopeTensor& k, int ntens, cons
                        int Hh, int N, int Dh, float sgn, cudaStream_t s) {
   constexpr int VEC = 16 / sizeof(T);
   const bool vec_ok = Dh % VEC == 0;
+  auto aligned = [&](const RopeTensor& t) {
+    return (reinterpret_cast<uintptr_t>(t.in) % 16 == 0) && (t.sb * sizeof(T)) % 16 == 0 && (t.sh * sizeof(T)) % 16 == 0 &&
+           (t.sn * sizeof(T)) % 16 == 0;
+  };
+  const long long plane = (long long)N * (Dh / VEC);
+  if (vec_ok && aligned(q) && (ntens == 1 || aligned(k)) && (long long)N * Dh < (1ll << 31) && plane < (1ll << 31)) {
+    const int rows = B * Hh;
+    const int pblocks = (int)((plane + 255) / 256);
+    // enough row groups for >= 8 CTAs per SM in total, at least ROPE_UNROLL rows per CTA
+    int groups = (8 * sm_count() + pblocks * ntens - 1) / (pblocks * ntens);
+    if (groups < 1) groups = 1;
+    int rpb = (rows + groups - 1) / groups;
+    rpb = (rpb + ROPE_UNROLL - 1) / ROPE_UNROLL * ROPE_UNROLL;
+    groups = (rows + rpb - 1) / rpb;
+    if (groups <= 65535) {
+      dim3 grid((unsigned)pblocks, (unsigned)groups, ntens);
+      rope3d_plane_kernel<T><<<grid, 256, 0, s>>>(q, k, (const T*)sin_t, (const T*)cos_t, rows, Hh, N, Dh, rpb, sgn);
+      return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+    }
+  }
   const long long total = (long long)B * Hh * N * (vec_ok ? Dh / VEC : Dh / 2);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
