@@ -8,7 +8,8 @@
 //   column accumulators in registers across the whole sweep over A tiles of one 256-column B block and
 //   reduces them across lanes only when the block changes (warp shuffles + one atomicAdd per column per
 //   warp). Row sums: one atomicAdd per thread per tile.
-#include "tile_engine.cuh"
+#include "tile_engine2.cuh"
+#include <stdlib.h>
 
 namespace b2 {
 
@@ -189,10 +190,43 @@ static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int l
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
+// CTA-pair engine (tile_engine2.cuh): Kp <= 512 only. B200CLIP_TE_PAIR=0 keeps the single-CTA engine (A/B runs).
+bool te_pair_enabled(int Kp) {
+  static const bool on = [] { const char* e = getenv("B200CLIP_TE_PAIR"); return !(e && e[0] == '0'); }();
+  return on && Kp <= 512 && sm_count() >= 2;
+}
+
+template <class Epi, bool kOuterIsB>
+static int launch_te2(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb,
+                      const typename Epi::Params& ep, cudaStream_t stream) {
+  TeShape g;
+  int rc = make_shape(g, Ma, Nb, Kp);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, 128))) return rc;      // each CTA loads 128 of the 256 block rows
+  auto kern = te2_kernel<Epi, kOuterIsB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE2_SMEM_BYTES) != cudaSuccess)
+      return B2_ECUDA;
+    attr_done = true;
+  }
+  const long long total = (long long)((g.m_tiles + 1) / 2) * g.n_blocks;
+  long long clusters = sm_count() / 2;
+  if (total < clusters) clusters = total;
+  kern<<<(int)(2 * clusters), TE_THREADS, TE2_SMEM_BYTES, stream>>>(tmA, tmB, g, ep);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
 int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
                    float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag, int diag_off,
                    cudaStream_t stream) {
   LseParams p{scale2, shift2, rowsum, colsum, gated, dyn, diag, diag_off};
+  if (te_pair_enabled(Kp)) {
+    if (gated) return launch_te2<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, stream);
+    return launch_te2<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, stream);
+  }
   if (gated) return launch_te<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
   return launch_te<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
 }

@@ -11,7 +11,7 @@
 //       ">" keeps the lowest index among equal scores.
 //   Partial lists go to global memory; topk_merge (one warp per row) merges the slots (and, across GPUs, the
 //   text shards) by (score desc, index asc).
-#include "tile_engine.cuh"
+#include "tile_engine2.cuh"
 #include "host_api.h"
 
 namespace b2 {
@@ -205,6 +205,7 @@ namespace b2host {
 using namespace b2;
 
 int make_shape(TeShape& g, int Ma, int Nb, int Kp);   // logits_fwd.cu
+bool te_pair_enabled(int Kp);                          // logits_fwd.cu
 
 template <int kMaxK>
 static int launch_retr(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, const RetrParams& p,
@@ -216,6 +217,23 @@ static int launch_retr(const void* A, const void* B, int Ma, int Nb, int Kp, int
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, TE_BN))) return rc;
+  if (te_pair_enabled(Kp)) {
+    // CTA pairs: A tile (video rows) resident per CTA, text blocks streamed as halves (tile_engine2.cuh)
+    CUtensorMap tmB2;
+    if ((rc = make_tmap_bf16_2d(&tmB2, B, Nb, Kp, ldb, 128))) return rc;
+    auto kern2 = te2_kernel<RetrEpi<kMaxK>, false>;
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, TE2_SMEM_BYTES) != cudaSuccess)
+        return B2_ECUDA;
+      attr2_done = true;
+    }
+    const long long items2 = (long long)((g.m_tiles + 1) / 2) * segs;
+    long long clusters = sm_count() / 2;
+    if (items2 < clusters) clusters = items2;
+    kern2<<<(int)(2 * clusters), TE_THREADS, TE2_SMEM_BYTES, stream>>>(tmA, tmB2, g, p);
+    return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+  }
   auto kern = te_kernel<RetrEpi<kMaxK>, false>;
   static bool attr_done = false;
   if (!attr_done) {
