@@ -287,7 +287,7 @@ using namespace b2;
 
 static int pick_splits(int B, int N) {
   const int sms = sm_count();
-  int S = (2 * sms + B - 1) / B;
+  int S = (2 * sms) / B;                 // B * S <= 2 CTAs per SM: one full wave of the 16-bit MMA kernel
   const int maxS = (N + 4 * AP_TOK - 1) / (4 * AP_TOK);
   if (S > maxS) S = maxS;
   if (S < 1) S = 1;
@@ -323,6 +323,8 @@ int attnpool_fwd(const void* x, int dtype, long long sb, long long sn, const uns
                  const float* qt, const float* w, long long wb, long long wh, int B, int N, int D, int H, int S,
                  float* part_m, float* part_l, float* part_acc, cudaStream_t s) {
   if (!x || !part_acc || B <= 0 || N <= 0 || H <= 0 || H > 16 || S < 1 || (!qt && !w)) return B2_EINVAL;
+  if (attnpool_mma_ok(x, dtype, sb, sn, D, H) && sb == (long long)N * sn)      // 16-bit inputs: tensor-core kernel (attnpool_mma.cu)
+    return attnpool_fwd_mma(x, dtype, sb, sn, mask, mb, qt, w, wb, wh, B, N, D, H, S, part_m, part_l, part_acc, s);
   PoolFwdParams p{x, sb, sn, mask, mb, qt, w, wb, wh, part_m, part_l, part_acc, B, N, D, H, S};
   switch (dtype) {
     case 0: return pool_fwd_t<float>(p, s);
@@ -370,6 +372,8 @@ int attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const 
                     const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
                     int D, int H, void* dx, float* ds, cudaStream_t s) {
   if (!x || !qt || !dxbar || !xbar || !m || !l || !dx || !ds || H > 16) return B2_EINVAL;
+  if (attnpool_mma_ok(x, dtype, sb, sn, D, H) && sb == (long long)N * sn && (reinterpret_cast<uintptr_t>(dx) % 16) == 0)
+    return attnpool_bwd_dx_mma(x, dtype, sb, sn, mask, mb, qt, dxbar, xbar, m, l, B, N, D, H, dx, ds, s);
   PoolBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H};
   switch (dtype) {
     case 0: return pool_bwd_t<float>(p, s);

@@ -42,6 +42,16 @@ int logits_bwd_pair(int mode, const void* X, const void* Y, int Nx, int Ny, int 
                     const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
                     int nseg_hint, cudaStream_t stream);
 
+// attnpool_mma.cu: 16-bit inputs on mma.sync (heads <= 8, D % 128 == 0, D <= 1024, 16-byte aligned rows)
+bool attnpool_mma_ok(const void* x, int dtype, long long sb, long long sn, int D, int H);
+int attnpool_fwd_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                     const float* qt, const float* w, long long wb, long long wh, int B, int N, int D, int H, int S,
+                     float* part_m, float* part_l, float* part_acc, cudaStream_t s);
+
+int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                        const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
+                        int N, int D, int H, void* dx, float* ds, cudaStream_t s);
+
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
 int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s);

@@ -42,17 +42,20 @@ def _operands(video, text, normalize: bool, precision: str):
     return vop, top, vn, tn, Kp
 
 
-def _shard(M: int, use_ddp: bool, group=None) -> Tuple[int, int, int, int]:
+def _shard_rows(M: int, use_ddp: bool, group=None) -> Tuple[int, int, int, int]:
     W, r = dist_plan.world(use_ddp, group)
     lo, hi = dist_plan.text_shard(M, W, r)
     return W, r, lo, hi
 
 
-def _sweep(vop, top, gt, k: int, use_ddp: bool, group=None):
-    """Returns (counts [N] int32 or None, top-k scores [N,k] / indices [N,k] int64 or None)."""
+def _sweep(vop, top, gt, k: int, use_ddp: bool, group=None, _shard=None):
+    """Returns (counts [N] int32 or None, top-k scores [N,k] / indices [N,k] int64 or None).
+    ``_shard=(lo, hi)`` restricts the sweep to text rows [lo, hi) of a single process (tests: shard additivity)."""
     dev = vop.device
     N, M, K = vop.shape[0], top.shape[0], vop.shape[1]
-    W, rank, lo, hi = _shard(M, use_ddp, group)
+    W, rank, lo, hi = _shard_rows(M, use_ddp, group)
+    if _shard is not None:
+        W, rank, (lo, hi) = 1, 0, _shard
     st = stream_ptr(dev)
     counts = sgt = gt64 = None
     if gt is not None:
