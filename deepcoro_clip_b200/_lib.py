@@ -33,6 +33,25 @@ def header_symbols() -> list[str]:
     return sorted(set(re.findall(r"\b(b200clip_[a-z0-9_]+)\s*\(", text)))
 
 
+_CTYPE = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double}
+
+
+def _prototypes() -> dict:
+    """{name: (restype, [argtypes])} parsed from include/b200clip.h, so ctypes converts every argument in C (and a
+    Python int can never be silently truncated into the wrong width)."""
+    text = re.sub(r"/\*.*?\*/", "", _HEADER.read_text(), flags=re.S)
+    out = {}
+    for ret, name, args in re.findall(r"\b(int|const char\*)\s+(b200clip_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        types = []
+        for a in [x.strip() for x in args.replace("\n", " ").split(",")]:
+            if a == "void":
+                continue
+            t = re.sub(r"\s+[A-Za-z_0-9]+$", "", a).replace("const ", "").strip()
+            types.append(ctypes.c_void_p if t.endswith("*") else _CTYPE[t])
+        out[name] = (ctypes.c_char_p if ret != "int" else ctypes.c_int, types)
+    return out
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
@@ -41,34 +60,30 @@ def lib() -> ctypes.CDLL:
                 f"{_LIB_PATH} is missing: build it with `python -m deepcoro_clip_b200.build` "
                 "(there is deliberately no CPU / PyTorch fallback)")
         _lib = ctypes.CDLL(str(_LIB_PATH))
-        _lib.b200clip_strerror.restype = ctypes.c_char_p
-        _lib.b200clip_strerror.argtypes = [ctypes.c_int]
+        for name, (ret, types) in _prototypes().items():
+            fn = getattr(_lib, name, None)
+            if fn is not None:
+                fn.restype = ret
+                fn.argtypes = types
     return _lib
 
 
-def _conv(a):
-    if isinstance(a, torch.Tensor):
-        return ctypes.c_void_p(a.data_ptr())
-    if a is None:
-        return ctypes.c_void_p(0)
-    if isinstance(a, float):
-        return ctypes.c_float(a)
-    if isinstance(a, bool):
-        return ctypes.c_int(int(a))
-    if isinstance(a, int):
-        return ctypes.c_int64(a) if abs(a) > 0x7FFFFFFF else ctypes.c_int(a)
-    return a
+_FN: dict = {}
+_Tensor = torch.Tensor
 
 
-def i64(v: int) -> ctypes.c_int64:
-    return ctypes.c_int64(int(v))
+def i64(v: int) -> int:
+    return int(v)
 
 
 def call(name: str, *args) -> None:
-    """Calls ``b200clip_<name>`` with tensors converted to device pointers; raises on error."""
+    """Calls ``b200clip_<name>``: tensors become device pointers, everything else is converted by ctypes against the
+    header prototype; raises on a non-zero status."""
     global LAUNCHES
-    fn = getattr(lib(), "b200clip_" + name)
-    rc = fn(*[_conv(a) for a in args])
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(lib(), "b200clip_" + name)
+    rc = fn(*[a.data_ptr() if type(a) is _Tensor or isinstance(a, _Tensor) else a for a in args])
     if name not in _NO_LAUNCH:
         LAUNCHES += 1
     if rc != 0:
@@ -76,5 +91,8 @@ def call(name: str, *args) -> None:
         raise B200ClipError(f"b200clip_{name} failed: {msg} (code {rc})")
 
 
-def stream_ptr(device=None) -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+def stream_ptr(device=None) -> int:
+    """Raw cudaStream_t of torch's current stream on ``device``."""
+    idx = device.index if isinstance(device, torch.device) and device.index is not None else (
+        device if isinstance(device, int) else torch.cuda.current_device())
+    return torch._C._cuda_getCurrentRawStream(idx)

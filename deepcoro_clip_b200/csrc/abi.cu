@@ -55,6 +55,16 @@ int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const i
   return rowdot_bf16(a, lda, b, ldb, reinterpret_cast<const long long*>(idx), rows, b_rows, K, out, S(stream));
 }
 
+int b200clip_clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif,
+                           float* rowscale, float* colscale, float* loss_out, double* acc_out, void* stream) {
+  return clip_finalize(sums, n, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out, S(stream));
+}
+
+int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
+                           float* out, void* stream) {
+  return clip_dlogtemp(scal0, dyn, gmul, unif, n, out, S(stream));
+}
+
 int b200clip_gather_rows_bf16(const void* src, int lds, const int64_t* idx, int rows, int src_rows, int K, void* dst,
                               int ldd, void* stream) {
   if (!src || !idx || !dst) return B2_EINVAL;

@@ -56,6 +56,10 @@ int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, co
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
 int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s);
 int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s);
+int clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif, float* rowscale,
+                  float* colscale, float* loss_out, double* acc_out, cudaStream_t s);
+int clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n, float* out,
+                  cudaStream_t s);
 int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots, double* acc,
              cudaStream_t s);
 

@@ -110,6 +110,59 @@ diag_sum_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat1
   }
 }
 
+
+// One launch for the whole scalar tail of the softmax (CLIP / gated) loss forward (utils/loss/contrastive.py:155-164):
+//   sums = [colsum (N) | rowsum (N) | target dots (N)]  (already all-reduced across ranks)
+//   rowscale[i] = c / rowsum[i], colscale[j] = c / colsum[j]  (c = 0.5 / N, the backward's softmax denominators)
+//   loss = c * (sum_i ln rowsum_i + sum_j ln colsum_j + 2 N ln2 shift2) - ((1 - eps) / tau * sum_i f(dot_i) + unif) / N
+// A single CTA: N <= a few 100k elements, fp64 accumulation, deterministic order.
+__global__ void __launch_bounds__(1024)
+clip_finalize_kernel(const float* __restrict__ sums, int n, const float* __restrict__ dyn, float eps, int gated,
+                     const double* __restrict__ unif, float* __restrict__ rowscale, float* __restrict__ colscale,
+                     float* __restrict__ loss_out, double* __restrict__ acc_out) {
+  const float c = 0.5f / (float)n;
+  const double shift = (double)dyn[6];
+  double a_row = 0.0, a_col = 0.0, a_dot = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float cs = sums[i], rs = sums[n + i];
+    const double d = (double)sums[2 * n + i];
+    colscale[i] = c / cs;
+    rowscale[i] = c / rs;
+    a_col += (double)logf(cs) + shift;
+    a_row += (double)logf(rs) + shift;
+    a_dot += gated ? d / (1.0 + exp(-d)) : d;
+  }
+  __shared__ double sh[3][32];
+  for (int o = 16; o > 0; o >>= 1) {
+    a_row += __shfl_xor_sync(0xffffffffu, a_row, o);
+    a_col += __shfl_xor_sync(0xffffffffu, a_col, o);
+    a_dot += __shfl_xor_sync(0xffffffffu, a_dot, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = a_row;
+    sh[1][threadIdx.x >> 5] = a_col;
+    sh[2][threadIdx.x >> 5] = a_dot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0, cc = 0.0, d = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { r += sh[0][w]; cc += sh[1][w]; d += sh[2][w]; }
+    const double u = unif ? unif[0] : 0.0;
+    const double loss = (0.5 / n) * (r + cc) - ((1.0 - (double)eps) * d * (double)dyn[2] + u) / n;
+    loss_out[0] = (float)loss;
+    if (acc_out) { acc_out[0] = r; acc_out[1] = cc; acc_out[2] = d; }
+  }
+}
+
+// d loss / d log_temp = (unif / N - scal0 / tau) * [tau not clamped] * grad_out   (Appendix A.1: -sum G L)
+__global__ void clip_dlogtemp_kernel(const double* __restrict__ scal0, const float* __restrict__ dyn,
+                                     const float* __restrict__ gmul, const double* __restrict__ unif, int n,
+                                     float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double u = unif ? unif[0] : 0.0;
+  out[0] = (float)((u / n - scal0[0] * (double)dyn[2]) * (double)dyn[7] * (double)gmul[0]);
+}
+
 }  // namespace b2
 
 namespace b2host {
@@ -131,6 +184,20 @@ int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s) {
   int blocks = (n + 255) / 256;
   if (blocks > 64) blocks = 64;
   vec_fsum_kernel<<<blocks, 256, 0, s>>>(v, n, gated, acc);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif, float* rowscale,
+                  float* colscale, float* loss_out, double* acc_out, cudaStream_t s) {
+  if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out) return B2_EINVAL;
+  clip_finalize_kernel<<<1, 1024, 0, s>>>(sums, n, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n, float* out,
+                  cudaStream_t s) {
+  if (!scal0 || !dyn || !gmul || !out || n <= 0) return B2_EINVAL;
+  clip_dlogtemp_kernel<<<1, 32, 0, s>>>(scal0, dyn, gmul, unif, n, out);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

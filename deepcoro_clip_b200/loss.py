@@ -49,7 +49,10 @@ def _pick_precision(precision: str, n_rows: int, n_cols: int) -> bool:
 
 
 class _ClipLossFn(torch.autograd.Function):
-    """Softmax-CE both directions, diagonal targets."""
+    """Softmax-CE both directions, diagonal targets.
+
+    Host side kept lean on purpose (at 8 GPUs a step is ~1 ms and Python dispatch is the limiter): one zeroed fp32 arena
+    per pass, ONE all-reduce of [colsum | rowsum | target dots] (3N floats), one finalize kernel for the scalar tail."""
 
     @staticmethod
     def forward(ctx, video, text, log_temp, label_smoothing, gated, clamp_min, precision, use_ddp, group):
@@ -63,6 +66,7 @@ class _ClipLossFn(torch.autograd.Function):
         x3 = _pick_precision(precision, N, N)
         eps = float(label_smoothing)
         mode = BW_GATED if gated else BW_CLIP
+        st = ops.stream_ptr(dev)
 
         vop, vinv, Kp = ops.l2norm_operand(video, 0 if x3 else -1)
         top, tinv, _ = ops.l2norm_operand(text, 1 if x3 else -1)
@@ -71,79 +75,77 @@ class _ClipLossFn(torch.autograd.Function):
         tall = _all_gather_rows(top, W, group)
         dyn = ops.dyn_prep(log_temp, None, clamp_min, ops.GATED_BOUND if gated else 1.0)
 
-        rowsum = torch.zeros(B, dtype=torch.float32, device=dev)
-        colsum = torch.zeros(N, dtype=torch.float32, device=dev)
-        dots = torch.empty(B, dtype=torch.float32, device=dev)      # S_ii as the tensor core rounded it
-        ops.lse_fwd(vop, tall, B, N, K, dyn, gated, rowsum, colsum, dots, rank * B)
+        # arena: [colsum (N) | rowsum (N) | dots (N)] zeroed (other ranks' slices stay 0 for the all-reduce) | scales (2N)
+        ws = torch.zeros(5 * N + 2, dtype=torch.float32, device=dev)
+        sums = ws[:3 * N]
+        lo = rank * B
+        ops.call("logits_lse_fwd", vop, tall, B, N, K, vop.stride(0), tall.stride(0), 0.0, 0.0, int(gated), dyn,
+                 ws[N + lo:N + lo + B], ws[:N], ws[2 * N + lo:2 * N + lo + B], lo, st)
         if W > 1:
-            dist.all_reduce(colsum, group=group)
-            rowsum_all = _all_gather_rows(rowsum, W, group)
-        else:
-            rowsum_all = rowsum
-
-        c = 0.5 / N
-        acc = torch.zeros(4, dtype=torch.float64, device=dev)      # [sum r_i, sum c_j, sum f(S_ii), -]
-        rowscale_all = torch.empty(N, dtype=torch.float32, device=dev)
-        colscale_all = torch.empty(N, dtype=torch.float32, device=dev)
-        ops.lse_finalize(rowsum_all, dyn, c, rowscale_all, acc[0:1])
-        ops.lse_finalize(colsum, dyn, c, colscale_all, acc[1:2])
-        ops.vec_fsum(dots, gated, acc[2:3])
-        if W > 1:
-            dist.all_reduce(acc[2:3], group=group)
-        inv_tau = dyn[2].double()
-        sum_tgt = (1.0 - eps) * acc[2] * inv_tau
-        unif_tgt = torch.zeros((), dtype=torch.float64, device=dev)
-        vsum = tsum = None
+            dist.all_reduce(sums, group=group)
+        rowscale_all = ws[3 * N:4 * N]
+        colscale_all = ws[4 * N:5 * N]
+        unif_tgt = vsum = tsum = None
         if eps != 0.0:
             if gated:
                 raise B200ClipError("label_smoothing is not defined for the gated legacy loss")
             vsum = ops.colsum_bf16(vall[:, K - Kp:], N, D)      # hi panel (last in bf16x3 mode)
             tsum = ops.colsum_bf16(tall[:, K - Kp:], N, D)
-            unif_tgt = (eps / N) * torch.dot(vsum.double(), tsum.double()) * inv_tau
-            sum_tgt = sum_tgt + unif_tgt
-        loss = dist_plan.clip_loss_from_sums(acc[0], acc[1], sum_tgt, N)
+            unif_tgt = ((eps / N) * torch.dot(vsum.double(), tsum.double()) * dyn[2].double()).reshape(1)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        ops.call("clip_finalize", sums, N, dyn, eps, int(gated), unif_tgt, rowscale_all, colscale_all, loss, None, st)
 
-        ctx.save_for_backward(video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, dots,
-                              vsum, tsum, unif_tgt)
+        ctx.save_for_backward(video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, vsum, tsum,
+                              unif_tgt)
         ctx.cfg = (B, D, Kp, K, W, rank, N, eps, mode, group, log_temp.shape, log_temp.dtype)
-        return loss.float()
+        return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        (video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, dots, vsum, tsum,
+        (video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, vsum, tsum,
          unif_tgt) = ctx.saved_tensors
         B, D, Kp, K, W, rank, N, eps, mode, group, lt_shape, lt_dtype = ctx.cfg
         dev = video.device
-        gmul = grad_out.detach().reshape(1).float().contiguous()
+        gmul = grad_out.detach().reshape(1)
+        if gmul.dtype != torch.float32:
+            gmul = gmul.float()
         lo, hi = rank * B, (rank + 1) * B
+        need_v, need_t, need_lt = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dV = dT = dLT = None
-        scal = torch.zeros(4, dtype=torch.float64, device=dev)
-        need_lt = ctx.needs_input_grad[2]
-        if ctx.needs_input_grad[0] or need_lt:
-            dVh = torch.zeros((B, D), dtype=torch.float32, device=dev)
-            dcv = torch.zeros((B, 2), dtype=torch.float32, device=dev)
+        # arena: dVhat [B, D] | dThat [B, D] | diag corrections 2 x [B, 2] | fp64 scalars (8 floats)
+        nbd = B * D
+        ws = torch.zeros(2 * nbd + 4 * B + 8, dtype=torch.float32, device=dev)
+        scal = ws[2 * nbd + 4 * B:].view(torch.float64)
+        ydiag = (1.0 - eps) / N
+        if need_v or need_lt:
+            dVh = ws[:nbd].view(B, D)
+            dcv = ws[2 * nbd:2 * nbd + 2 * B]
             ops.logits_bwd(mode, vop, tall, B, N, K, Kp, D, dyn, rowscale_all[lo:hi], colscale_all, dVh, scal,
-                           ydiag=(1.0 - eps) / N, diag_off=lo, diag_corr=dcv, gnorm=2.0 * N, hp=(K != Kp))
-            if ctx.needs_input_grad[0]:
+                           ydiag=ydiag, diag_off=lo, diag_corr=dcv, gnorm=2.0 * N, hp=(K != Kp))
+            if need_v:
                 dV = ops.l2norm_backward(dVh, video, vinv, other_x=text, other_inv=tinv, other_hi=top[:, K - Kp:],
                                          diag_corr=dcv, usum=tsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3],
-                                         dev_gmul=gmul).to(video.dtype)
-        if ctx.needs_input_grad[1]:
-            dTh = torch.zeros((B, D), dtype=torch.float32, device=dev)
-            dct = torch.zeros((B, 2), dtype=torch.float32, device=dev)
+                                         dev_gmul=gmul)
+                if dV.dtype != video.dtype:
+                    dV = dV.to(video.dtype)
+        if need_t:
+            dTh = ws[nbd:2 * nbd].view(B, D)
+            dct = ws[2 * nbd + 2 * B:2 * nbd + 4 * B]
             ops.logits_bwd(mode, top, vall, B, N, K, Kp, D, dyn, colscale_all[lo:hi], rowscale_all, dTh, None,
-                           ydiag=(1.0 - eps) / N, diag_off=lo, diag_corr=dct, gnorm=2.0 * N, hp=(K != Kp))
+                           ydiag=ydiag, diag_off=lo, diag_corr=dct, gnorm=2.0 * N, hp=(K != Kp))
             dT = ops.l2norm_backward(dTh, text, tinv, other_x=video, other_inv=vinv, other_hi=vop[:, K - Kp:],
                                      diag_corr=dct, usum=vsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3],
-                                     dev_gmul=gmul).to(text.dtype)
+                                     dev_gmul=gmul)
+            if dT.dtype != text.dtype:
+                dT = dT.to(text.dtype)
         if need_lt:
-            s0 = scal[0:1].clone()
             if W > 1:
-                dist.all_reduce(s0, group=group)
-            # d loss / d log_temp = -sum_ij G_ij L_ij  (zero while the tau clamp is active)
-            # (the kernel's sum already contains the diagonal target; only the uniform label-smoothing part is added)
-            dlt = (unif_tgt / N - s0 * dyn[2].double()) * dyn[7].double() * gmul.double()
-            dLT = dlt.to(lt_dtype).reshape(lt_shape)
+                dist.all_reduce(scal[0:1], group=group)
+            # d loss / d log_temp = -sum_ij G_ij L_ij  (zero while the tau clamp is active); the kernel's sum already
+            # contains the diagonal target, only the uniform label-smoothing part is added
+            dlt = torch.empty(1, dtype=torch.float32, device=dev)
+            ops.call("clip_dlogtemp", scal, dyn, gmul, unif_tgt, N, dlt, ops.stream_ptr(dev))
+            dLT = (dlt if lt_dtype == torch.float32 else dlt.to(lt_dtype)).reshape(lt_shape)
         return dV, dT, dLT, None, None, None, None, None, None
 
 

@@ -68,9 +68,17 @@ def l2norm_backward(dxhat, x, inv_norm, *, other_x=None, other_inv=None, other_h
     return dx
 
 
+def _scalar_f32(t: torch.Tensor) -> torch.Tensor:
+    """First element of ``t`` as an fp32 device tensor without copies in the common case (fp32 0-d / [1] parameter)."""
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.numel() == 1 else t.reshape(-1)[:1].contiguous()
+
+
 def dyn_prep(log_temp: torch.Tensor, bias, clamp_min: float, bound: float) -> torch.Tensor:
-    lt = log_temp.detach().reshape(-1)[:1].float().contiguous()
-    b = None if bias is None else bias.detach().reshape(-1)[:1].float().contiguous()
+    lt = _scalar_f32(log_temp)
+    b = None if bias is None else _scalar_f32(bias)
     dyn = torch.empty(16, dtype=torch.float32, device=lt.device)
     call("dyn_prep", lt, b, float(clamp_min), float(bound), dyn, stream_ptr(lt.device))
     return dyn

@@ -142,6 +142,17 @@ int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, f
 int b200clip_vec_fsum(const float* v, int n, int gated, double* acc, void* stream);
 int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots,
                       double* acc, void* stream);
+/* The whole scalar tail of the softmax-CE forward in ONE launch (replaces 2x cross_entropy's reductions and the
+ * scalar arithmetic of utils/loss/contrastive.py:155-164; losses.py:56-62):
+ *   sums = [colsum (n) | rowsum (n) | target dots S_ii (n)] as produced by logits_lse_fwd (all-reduced across ranks);
+ *   rowscale[i] = c / rowsum[i], colscale[j] = c / colsum[j], c = 0.5 / n;
+ *   loss_out[0] = c * (sum ln rowsum + sum ln colsum) - ((1 - eps) / tau * sum f(S_ii) + unif[0]) / n  (fp64 inside);
+ *   unif (may be NULL): label-smoothing uniform-target term; acc_out (may be NULL): the three fp64 sums.
+ * clip_dlogtemp: out[0] = (unif / n - scal0[0] / tau) * [tau not clamped] * gmul[0]  (d loss / d log_temp). */
+int b200clip_clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif,
+                           float* rowscale, float* colscale, float* loss_out, double* acc_out, void* stream);
+int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
+                           float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SigLIP multi-positive loss pieces (utils/loss/contrastive.py:230-315). The dense term treats every pair as a
