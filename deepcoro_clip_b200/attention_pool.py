@@ -16,10 +16,11 @@ from ._lib import DTYPE_CODE, call, i64, lib, stream_ptr
 
 
 class _StreamPool(torch.autograd.Function):
-    """xbar[b, h, :] = sum_n softmax_n(x[b, n] . qt[h]) x[b, n]   (fp32 [B, H, D])"""
+    """xbar[b, h, :] = sum_n a'[b, h, n] x[b, n],  a = softmax_n(x[b, n] . qt[h]),  a' = dropout(a)  (fp32 [B, H, D]);
+    second output sa[b, h] = sum_n a'[b, h, n] (== 1 without dropout; it multiplies the value bias)."""
 
     @staticmethod
-    def forward(ctx, x, qt, mask):
+    def forward(ctx, x, qt, mask, drop_p, drop_seed):
         ops.require_cuda(x, qt)
         if x.dtype not in DTYPE_CODE:
             x = x.float()
@@ -37,42 +38,48 @@ class _StreamPool(torch.autograd.Function):
         S = lib().b200clip_attnpool_splits(B, N)
         pm = torch.empty((B, S, H), dtype=torch.float32, device=dev)
         pl = torch.empty((B, S, H), dtype=torch.float32, device=dev)
+        pl2 = torch.empty((B, S, H), dtype=torch.float32, device=dev) if drop_p > 0.0 else None
         pa = torch.empty((B, S, H, D), dtype=torch.float32, device=dev)
         st = stream_ptr(dev)
         call("attnpool_fwd", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), mk,
-             i64(mk.stride(0) if mk is not None else 0), qt32, None, i64(0), i64(0), B, N, D, H, S, pm, pl, pa, st)
+             i64(mk.stride(0) if mk is not None else 0), qt32, None, i64(0), i64(0), B, N, D, H, S, pm, pl, pa,
+             float(drop_p), int(drop_seed), pl2, st)
         xbar = torch.empty((B, H, D), dtype=torch.float32, device=dev)
         m = torch.empty((B, H), dtype=torch.float32, device=dev)
         l = torch.empty((B, H), dtype=torch.float32, device=dev)
-        call("attnpool_merge", pm, pl, pa, B, S, H, D, xbar, m, l, 0, st)
-        ctx.save_for_backward(x, qt32, mk if mk is not None else torch.empty(0, device=dev), xbar, m, l)
+        sa = torch.empty((B, H), dtype=torch.float32, device=dev)
+        call("attnpool_merge", pm, pl, pa, B, S, H, D, xbar, m, l, 0, pl2, sa, st)
+        ctx.save_for_backward(x, qt32, mk if mk is not None else torch.empty(0, device=dev), xbar, m, l, sa)
         ctx.has_mask = mk is not None
         ctx.S = S
-        return xbar
+        ctx.drop = (float(drop_p), int(drop_seed))
+        return xbar, sa
 
     @staticmethod
-    def backward(ctx, dxbar):
-        x, qt32, mk, xbar, m, l = ctx.saved_tensors
+    def backward(ctx, dxbar, dsa):
+        x, qt32, mk, xbar, m, l, sa = ctx.saved_tensors
         mk = mk if ctx.has_mask else None
+        drop_p, drop_seed = ctx.drop
         B, N, D = x.shape
         H = qt32.shape[0]
         dev = x.device
         st = stream_ptr(dev)
         dxbar = dxbar.float().contiguous()
+        dsa = dsa.float().contiguous() if (dsa is not None and drop_p > 0.0) else None
         dx = torch.empty((B, N, D), dtype=x.dtype, device=dev)
         ds = torch.empty((B, H, N), dtype=torch.float32, device=dev)
         mb = i64(mk.stride(0) if mk is not None else 0)
         call("attnpool_bwd_dx", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), mk, mb, qt32, dxbar, xbar, m,
-             l, B, N, D, H, dx, ds, st)
+             l, B, N, D, H, dx, ds, sa if dsa is not None else None, dsa, drop_p if dsa is not None else 0.0, drop_seed, st)
         dqt = None
         if ctx.needs_input_grad[1]:
             S = ctx.S
             pa = torch.empty((B, S, H, D), dtype=torch.float32, device=dev)
             call("attnpool_fwd", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), None, i64(0), None, ds,
-                 i64(ds.stride(0)), i64(ds.stride(1)), B, N, D, H, S, None, None, pa, st)
+                 i64(ds.stride(0)), i64(ds.stride(1)), B, N, D, H, S, None, None, pa, 0.0, 0, None, st)
             dqt = torch.zeros((H, D), dtype=torch.float32, device=dev)
-            call("attnpool_merge", None, None, pa, B, S, H, D, dqt, None, None, 1, st)
-        return (dx if ctx.needs_input_grad[0] else None), dqt, None
+            call("attnpool_merge", None, None, pa, B, S, H, D, dqt, None, None, 1, None, None, st)
+        return (dx if ctx.needs_input_grad[0] else None), dqt, None, None, None
 
 
 class AttentionPool(nn.Module):
@@ -92,9 +99,12 @@ class AttentionPool(nn.Module):
     def forward(self, x: torch.Tensor, mask: torch.Tensor = None) -> torch.Tensor:
         B, N, D = x.shape
         assert D == self.embed_dim, f"Input dim {D} != expected {self.embed_dim}"
+        drop_p, drop_seed = 0.0, 0
         if self.training and self.dropout > 0.0:
-            raise NotImplementedError("AttentionPool kernel: attention dropout > 0 in training mode is not supported "
-                                      "(the folded single-query algebra needs sum(a) = 1); use dropout=0.0")
+            # nn.MultiheadAttention drops attention WEIGHTS (after the softmax). Same here, with a counter-based mask
+            # seeded from torch's CPU generator (reproducible under torch.manual_seed; not PyTorch's Philox stream).
+            drop_p = float(self.dropout)
+            drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         H, Dh = self.num_heads, D // self.num_heads
         with torch.autocast("cuda", enabled=False):
             W = self.attn.in_proj_weight.float()
@@ -103,8 +113,9 @@ class AttentionPool(nn.Module):
             bq, bv = bias[:D], bias[2 * D:]
             q0 = F.linear(self.query.float().view(1, D), Wq, bq).view(H, Dh)
             qt = torch.einsum("hkd,hk->hd", Wk.view(H, Dh, D), q0) * (1.0 / math.sqrt(Dh))     # [H, D]
-            xbar = _StreamPool.apply(x, qt, mask)                                              # [B, H, D] fp32
-            o = torch.einsum("bhd,hkd->bhk", xbar, Wv.view(H, Dh, D)).reshape(B, D) + bv
+            xbar, sa = _StreamPool.apply(x, qt, mask, drop_p, drop_seed)                       # [B, H, D], [B, H] fp32
+            o = torch.einsum("bhd,hkd->bhk", xbar, Wv.view(H, Dh, D))
+            o = (o + bv.view(1, H, Dh) * sa.unsqueeze(-1) if drop_p > 0.0 else o + bv.view(1, H, Dh)).reshape(B, D)
             y = F.linear(o, self.attn.out_proj.weight.float(), self.attn.out_proj.bias.float())
             y = F.layer_norm(y, (D,), self.norm.weight.float(), self.norm.bias.float(), self.norm.eps)
             if isinstance(self.proj, nn.Linear):

@@ -182,20 +182,26 @@ int b200clip_attnpool_splits(int B, int N) { return attnpool_splits(B, N); }
 
 int b200clip_attnpool_fwd(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
                           const float* qt, const float* weights, int64_t w_sb, int64_t w_sh, int B, int N, int D,
-                          int heads, int splits, float* part_m, float* part_l, float* part_acc, void* stream) {
+                          int heads, int splits, float* part_m, float* part_l, float* part_acc, float drop_p,
+                          int64_t drop_seed, float* part_l2, void* stream) {
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !part_l2)) return B2_EINVAL;
   return attnpool_fwd(x, dtype, x_sb, x_sn, mask, mask_sb, qt, weights, w_sb, w_sh, B, N, D, heads, splits, part_m,
-                      part_l, part_acc, S(stream));
+                      part_l, part_acc, drop_p, (unsigned long long)drop_seed, part_l2, S(stream));
 }
 
 int b200clip_attnpool_merge(const float* part_m, const float* part_l, const float* part_acc, int B, int splits,
-                            int heads, int D, float* out, float* out_m, float* out_l, int sum_over_b, void* stream) {
-  return attnpool_merge(part_m, part_l, part_acc, B, splits, heads, D, out, out_m, out_l, sum_over_b, S(stream));
+                            int heads, int D, float* out, float* out_m, float* out_l, int sum_over_b,
+                            const float* part_l2, float* out_sa, void* stream) {
+  return attnpool_merge(part_m, part_l, part_acc, B, splits, heads, D, out, out_m, out_l, sum_over_b, part_l2, out_sa,
+                        S(stream));
 }
 
 int b200clip_attnpool_bwd_dx(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
                              const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l,
-                             int B, int N, int D, int heads, void* dx, float* ds, void* stream) {
-  return attnpool_bwd_dx(x, dtype, x_sb, x_sn, mask, mask_sb, qt, dxbar, xbar, m, l, B, N, D, heads, dx, ds, S(stream));
+                             int B, int N, int D, int heads, void* dx, float* ds, const float* sa, const float* dsa,
+                             float drop_p, int64_t drop_seed, void* stream) {
+  return attnpool_bwd_dx(x, dtype, x_sb, x_sn, mask, mask_sb, qt, dxbar, xbar, m, l, B, N, D, heads, dx, ds, sa, dsa,
+                         drop_p, (unsigned long long)drop_seed, S(stream));
 }
 
 int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,

@@ -22,6 +22,7 @@ namespace b2 {
 
 constexpr int AP_TOK = 32;   // tokens per smem tile
 
+
 template <typename T> __device__ __forceinline__ float ap_ld(const T* p);
 template <> __device__ __forceinline__ float ap_ld<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ap_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
@@ -46,6 +47,7 @@ struct PoolFwdParams {
   const float* w; long long wb, wh;    // [B, H, N] given weights (weighted-sum mode), else null
   float* part_m; float* part_l; float* part_acc;   // [B, S, H], [B, S, H], [B, S, H, D]
   int B, N, D, H, S;
+  float drop_p; unsigned long long drop_seed; float* part_l2;   // attention dropout (training): sum of kept weights
 };
 
 template <typename T, int NCH>
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(512) pool_fwd_kernel(PoolFwdParams p) {
       q[c * L::VE + i] = p.w ? 0.f : p.qt[(size_t)h * p.D + L::d(lane, c, i)];
       acc[c * L::VE + i] = 0.f;
     }
-  float m = -INFINITY, l = 0.f;
+  float m = -INFINITY, l = 0.f, l2 = 0.f;
+  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const unsigned char* mk = p.mask ? p.mask + b * p.mb : nullptr;
   const float* wrow = p.w ? p.w + b * p.wb + h * p.wh : nullptr;
 
@@ -115,7 +118,9 @@ __global__ void __launch_bounds__(512) pool_fwd_kernel(PoolFwdParams p) {
         if (mn == -INFINITY) continue;                   // every token so far masked
         const float sc = __expf(m - mn);                 // exp(-inf) = 0 on the first real token
         wgt = __expf(s - mn);
-        l = l * sc + wgt;
+        l = l * sc + wgt;                                // softmax denominator: BEFORE dropout (nn.MultiheadAttention)
+        if (p.drop_p > 0.f) wgt = attn_keep(p.drop_seed, b * p.H + h, t0 + r, p.drop_p) ? wgt * keep_scale : 0.f;
+        l2 = l2 * sc + wgt;
         m = mn;
 #pragma unroll
         for (int i = 0; i < L::EPL; ++i) acc[i] *= sc;
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__(512) pool_fwd_kernel(PoolFwdParams p) {
   if (lane == 0 && p.part_m) {
     p.part_m[slot] = m;
     p.part_l[slot] = l;
+    if (p.part_l2) p.part_l2[slot] = l2;
   }
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
@@ -142,17 +148,19 @@ __global__ void __launch_bounds__(512) pool_fwd_kernel(PoolFwdParams p) {
 __global__ void __launch_bounds__(256)
 pool_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, const float* __restrict__ part_acc,
                   int B, int S, int H, int D, float* __restrict__ out, float* __restrict__ out_m,
-                  float* __restrict__ out_l, int sum_over_b) {
+                  float* __restrict__ out_l, int sum_over_b, const float* __restrict__ part_l2,
+                  float* __restrict__ out_sa) {
   const int bh = blockIdx.x;               // b * H + h
   const int b = bh / H, h = bh - b * H;
   float m = -INFINITY;
   if (part_m)
     for (int s = 0; s < S; ++s) m = fmaxf(m, part_m[((size_t)b * S + s) * H + h]);
-  float l = 0.f;
+  float l = 0.f, l2 = 0.f;
   if (part_m)
     for (int s = 0; s < S; ++s) {
       const float ms = part_m[((size_t)b * S + s) * H + h];
       l += ms == -INFINITY ? 0.f : part_l[((size_t)b * S + s) * H + h] * __expf(ms - m);
+      if (part_l2) l2 += ms == -INFINITY ? 0.f : part_l2[((size_t)b * S + s) * H + h] * __expf(ms - m);
     }
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float a = 0.f;
@@ -172,6 +180,7 @@ pool_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
   if (threadIdx.x == 0 && part_m) {
     out_m[bh] = m;
     out_l[bh] = l;
+    if (out_sa) out_sa[bh] = part_l2 ? l2 / l : 1.f;       // sum of the (dropped, rescaled) attention weights
   }
 }
 
@@ -185,6 +194,8 @@ struct PoolBwdParams {
   void* dx;               // [B, N, D] contiguous, dtype T
   float* ds;              // [B, H, N]
   int B, N, D, H;
+  const float* sa; const float* dsa;   // [B, H] sum of dropped weights and its upstream gradient (dropout only)
+  float drop_p; unsigned long long drop_seed;
 };
 
 // warp = token. smem: qt [H][D], dxbar_b [H][D] (fp32), c_h = dxbar_h . xbar_h
@@ -208,6 +219,7 @@ __global__ void __launch_bounds__(256) pool_bwd_dx_kernel(PoolBwdParams p) {
     float c = 0.f;
     for (int d = lane; d < p.D; d += 32) c = fmaf(sd[h * p.D + d], p.xbar[((size_t)b * p.H + h) * p.D + d], c);
     c = warp_sum(c);
+    if (p.dsa) c = fmaf(p.dsa[b * p.H + h], p.sa[b * p.H + h], c);      // c = sum_n a_n kappa_n (T_n + dsa)
     if (lane == 0) {
       sc[h] = c;
       sm[h] = p.m[b * p.H + h];
@@ -251,8 +263,11 @@ __global__ void __launch_bounds__(256) pool_bwd_dx_kernel(PoolBwdParams p) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         da += __shfl_xor_sync(0xffffffffu, da, o);
       }
-      const float a = masked ? 0.f : __expf(s - sm[h]) * sl[h];
-      const float dsv = a * (da - sc[h]);
+      const float a0 = masked ? 0.f : __expf(s - sm[h]) * sl[h];
+      float kap = 1.f;
+      if (p.drop_p > 0.f) kap = attn_keep(p.drop_seed, b * p.H + h, n, p.drop_p) ? 1.f / (1.f - p.drop_p) : 0.f;
+      const float dsv = a0 * (kap * (da + (p.dsa ? p.dsa[b * p.H + h] : 0.f)) - sc[h]);
+      const float a = a0 * kap;                            // weight that multiplied x_n in the forward
       if (lane == 0) p.ds[((size_t)b * p.H + h) * p.N + n] = dsv;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -321,11 +336,13 @@ static int pool_fwd_t(const PoolFwdParams& p, cudaStream_t s) {
 
 int attnpool_fwd(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                  const float* qt, const float* w, long long wb, long long wh, int B, int N, int D, int H, int S,
-                 float* part_m, float* part_l, float* part_acc, cudaStream_t s) {
+                 float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
+                 float* part_l2, cudaStream_t s) {
   if (!x || !part_acc || B <= 0 || N <= 0 || H <= 0 || H > 16 || S < 1 || (!qt && !w)) return B2_EINVAL;
   if (attnpool_mma_ok(x, dtype, sb, sn, D, H) && sb == (long long)N * sn)      // 16-bit inputs: tensor-core kernel (attnpool_mma.cu)
-    return attnpool_fwd_mma(x, dtype, sb, sn, mask, mb, qt, w, wb, wh, B, N, D, H, S, part_m, part_l, part_acc, s);
-  PoolFwdParams p{x, sb, sn, mask, mb, qt, w, wb, wh, part_m, part_l, part_acc, B, N, D, H, S};
+    return attnpool_fwd_mma(x, dtype, sb, sn, mask, mb, qt, w, wb, wh, B, N, D, H, S, part_m, part_l, part_acc, drop_p,
+                            drop_seed, part_l2, s);
+  PoolFwdParams p{x, sb, sn, mask, mb, qt, w, wb, wh, part_m, part_l, part_acc, B, N, D, H, S, drop_p, drop_seed, part_l2};
   switch (dtype) {
     case 0: return pool_fwd_t<float>(p, s);
     case 1: return pool_fwd_t<__nv_bfloat16>(p, s);
@@ -335,9 +352,11 @@ int attnpool_fwd(const void* x, int dtype, long long sb, long long sn, const uns
 }
 
 int attnpool_merge(const float* part_m, const float* part_l, const float* part_acc, int B, int S, int H, int D,
-                   float* out, float* out_m, float* out_l, int sum_over_b, cudaStream_t s) {
+                   float* out, float* out_m, float* out_l, int sum_over_b, const float* part_l2, float* out_sa,
+                   cudaStream_t s) {
   if (!part_acc || !out) return B2_EINVAL;
-  pool_merge_kernel<<<B * H, 256, 0, s>>>(part_m, part_l, part_acc, B, S, H, D, out, out_m, out_l, sum_over_b);
+  pool_merge_kernel<<<B * H, 256, 0, s>>>(part_m, part_l, part_acc, B, S, H, D, out, out_m, out_l, sum_over_b, part_l2,
+                                          out_sa);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
@@ -370,11 +389,14 @@ static int pool_bwd_t(const PoolBwdParams& p, cudaStream_t s) {
 
 int attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                     const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
-                    int D, int H, void* dx, float* ds, cudaStream_t s) {
+                    int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
+                    unsigned long long drop_seed, cudaStream_t s) {
   if (!x || !qt || !dxbar || !xbar || !m || !l || !dx || !ds || H > 16) return B2_EINVAL;
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && (!sa || !dsa))) return B2_EINVAL;
   if (attnpool_mma_ok(x, dtype, sb, sn, D, H) && sb == (long long)N * sn && (reinterpret_cast<uintptr_t>(dx) % 16) == 0)
-    return attnpool_bwd_dx_mma(x, dtype, sb, sn, mask, mb, qt, dxbar, xbar, m, l, B, N, D, H, dx, ds, s);
-  PoolBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H};
+    return attnpool_bwd_dx_mma(x, dtype, sb, sn, mask, mb, qt, dxbar, xbar, m, l, B, N, D, H, dx, ds, sa, dsa, drop_p,
+                               drop_seed, s);
+  PoolBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, sa, dsa, drop_p, drop_seed};
   switch (dtype) {
     case 0: return pool_bwd_t<float>(p, s);
     case 1: return pool_bwd_t<__nv_bfloat16>(p, s);

@@ -83,6 +83,7 @@ struct PmFwdParams {
   const float* w; long long wb, wh;    // [B, H, N] given weights, or null
   float* part_m; float* part_l; float* part_acc;
   int B, N, D, H, S;
+  float drop_p; unsigned long long drop_seed; float* part_l2;   // attention dropout: see attnpool.cu
   int stages;                          // cp.async pipeline depth (2..4 tiles of 32 tokens in flight)
 };
 
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) pool_fwd_mma_kernel(
   float acc[MAXC][4];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;                // warp h < H owns head h's running max / sum (lane-uniform)
+  float m_run = -INFINITY, l_run = 0.f, l2_run = 0.f;  // warp h < H owns head h's running max / sums (lane-uniform)
+  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const unsigned char* mk = p.mask ? p.mask + b * p.mb : nullptr;
   const uint32_t qh_addr = smem_u32(q_hi), ql_addr = smem_u32(q_lo), ph_addr = smem_u32(p_hi), pl_addr = smem_u32(p_lo);
 
@@ -193,7 +195,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) pool_fwd_mma_kernel(
           sc = __expf(m_run - m_new);                  // exp(-inf) = 0 on the first unmasked tile
           pv = __expf(s - m_new);
         }
-        l_run = l_run * sc + warp_sum(pv);
+        l_run = l_run * sc + warp_sum(pv);             // softmax denominator: before dropout
+        if (p.drop_p > 0.f) {
+          pv = (h < p.H && attn_keep(p.drop_seed, b * p.H + h, t0 + lane, p.drop_p)) ? pv * keep_scale : 0.f;
+          l2_run = l2_run * sc + warp_sum(pv);
+        }
         m_run = m_new;
         const uint16_t hi = PmT<T>::bits(pv);
         p_hi[h * PP + lane] = hi;
@@ -247,6 +253,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) pool_fwd_mma_kernel(
     const size_t slot = ((size_t)b * p.S + sp) * p.H + warp;
     p.part_m[slot] = m_run;
     p.part_l[slot] = l_run;
+    if (p.part_l2) p.part_l2[slot] = p.drop_p > 0.f ? l2_run : l_run;
   }
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
@@ -272,6 +279,7 @@ struct PmBwdParams {
   void* dx;               // [B, N, D] contiguous
   float* ds;              // [B, H, N]
   int B, N, D, H, S;      // S = token splits (gridDim.y)
+  const float* sa; const float* dsa; float drop_p; unsigned long long drop_seed;
   int stages;
 };
 
@@ -336,6 +344,7 @@ __global__ void __launch_bounds__(NW * 32) pool_bwd_mma_kernel(const __grid_cons
       for (int d = lane; d < D; d += 32)
         c = fmaf(p.dxbar[((size_t)b * p.H + h) * D + d], p.xbar[((size_t)b * p.H + h) * D + d], c);
     c = warp_sum(c);
+    if (p.dsa && h < p.H) c = fmaf(p.dsa[b * p.H + h], p.sa[b * p.H + h], c);
     if (lane == 0) {
       s_c[h] = c;
       s_m[h] = h < p.H ? p.m[b * p.H + h] : 0.f;
@@ -399,8 +408,11 @@ __global__ void __launch_bounds__(NW * 32) pool_bwd_mma_kernel(const __grid_cons
         tv += st_part[((size_t)kq * PM_TT + lane) * 16 + 8 + h];
       }
       const bool live = h < p.H && lane < rows && !(mk && mk[t0 + lane]);
-      const float a = live ? __expf(sv - s_m[h]) * s_il[h] : 0.f;
-      const float dsv = a * (tv - s_c[h]);
+      const float a0 = live ? __expf(sv - s_m[h]) * s_il[h] : 0.f;
+      float kap = 1.f;
+      if (p.drop_p > 0.f && h < p.H) kap = attn_keep(p.drop_seed, b * p.H + h, t0 + lane, p.drop_p) ? 1.f / (1.f - p.drop_p) : 0.f;
+      const float dsv = a0 * (kap * (tv + ((p.dsa && h < p.H) ? p.dsa[b * p.H + h] : 0.f)) - s_c[h]);
+      const float a = a0 * kap;
       if (h < p.H && lane < rows) p.ds[((size_t)b * p.H + h) * p.N + t0 + lane] = dsv;
       const uint16_t ah = PmT<T>::bits(a), dh2 = PmT<T>::bits(dsv);
       c_hi[lane * 16 + h] = ah;
@@ -469,11 +481,12 @@ bool attnpool_mma_ok(const void* x, int dtype, long long sb, long long sn, int D
 
 int attnpool_fwd_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                      const float* qt, const float* w, long long wb, long long wh, int B, int N, int D, int H, int S,
-                     float* part_m, float* part_l, float* part_acc, cudaStream_t s) {
+                     float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
+                     float* part_l2, cudaStream_t s) {
   // forward: 8-warp CTAs, two per SM when the 2-tile pipeline fits (measured best at D = 512); 16 warps for wide rows
   const bool wide = D % 256 == 0 && (size_t)2 * PM_TT * D * 2 + pm_fwd_smem(D, 0) > 112 * 1024;
   const int stages = pm_stages(D, pm_fwd_smem(D, 0), wide);
-  PmFwdParams p{x, sb, sn, mask, mb, qt, w, wb, wh, part_m, part_l, part_acc, B, N, D, H, S, stages};
+  PmFwdParams p{x, sb, sn, mask, mb, qt, w, wb, wh, part_m, part_l, part_acc, B, N, D, H, S, drop_p, drop_seed, part_l2, stages};
   const size_t smem = pm_fwd_smem(D, stages);
   CUtensorMap tmx;
   {
@@ -500,13 +513,14 @@ static size_t pm_bwd_smem(int D, int stages) {
 
 int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                         const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
-                        int N, int D, int H, void* dx, float* ds, cudaStream_t s) {
+                        int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
+                        unsigned long long drop_seed, cudaStream_t s) {
   int S = sm_count() / B;
   const int maxS = (N + 2 * PM_TT - 1) / (2 * PM_TT);
   if (S > maxS) S = maxS;
   if (S < 1) S = 1;
   const int stages = pm_stages(D, pm_bwd_smem(D, 0), D % 256 == 0);
-  PmBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, S, stages};
+  PmBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, S, sa, dsa, drop_p, drop_seed, stages};
   const size_t smem = pm_bwd_smem(D, stages);
   CUtensorMap tmx;
   {

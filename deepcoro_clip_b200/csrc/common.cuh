@@ -302,6 +302,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Attention-dropout keep decision for (row = b * H + h, token n): splitmix64 of (seed, row, n), top 24 bits as a uniform
+// in [0, 1). Counter-based, so forward and backward regenerate the same mask without storing it (the reference's
+// nn.MultiheadAttention dropout uses PyTorch's Philox stream, which cannot be reproduced bit for bit: parity is
+// statistical, the gradient is exact for the mask actually drawn).
+__host__ __device__ __forceinline__ bool attn_keep(unsigned long long seed, int row, int n, float p) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)(unsigned)row * 0x100000001B3ull + (unsigned)n + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;
+}
+
 // named barrier among a subset of warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

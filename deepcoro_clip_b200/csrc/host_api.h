@@ -46,11 +46,13 @@ int logits_bwd_pair(int mode, const void* X, const void* Y, int Nx, int Ny, int 
 bool attnpool_mma_ok(const void* x, int dtype, long long sb, long long sn, int D, int H);
 int attnpool_fwd_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                      const float* qt, const float* w, long long wb, long long wh, int B, int N, int D, int H, int S,
-                     float* part_m, float* part_l, float* part_acc, cudaStream_t s);
+                     float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
+                     float* part_l2, cudaStream_t s);
 
 int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                         const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
-                        int N, int D, int H, void* dx, float* ds, cudaStream_t s);
+                        int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
+                        unsigned long long drop_seed, cudaStream_t s);
 
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
@@ -91,12 +93,15 @@ int rope3d_apply(const void* q, long long qsb, long long qsh, long long qsn, voi
 int attnpool_splits(int B, int N);
 int attnpool_fwd(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                  const float* qt, const float* w, long long wb, long long wh, int B, int N, int D, int H, int S,
-                 float* part_m, float* part_l, float* part_acc, cudaStream_t s);
+                 float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
+                 float* part_l2, cudaStream_t s);
 int attnpool_merge(const float* part_m, const float* part_l, const float* part_acc, int B, int S, int H, int D,
-                   float* out, float* out_m, float* out_l, int sum_over_b, cudaStream_t s);
+                   float* out, float* out_m, float* out_l, int sum_over_b, const float* part_l2, float* out_sa,
+                   cudaStream_t s);
 int attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                     const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
-                    int D, int H, void* dx, float* ds, cudaStream_t s);
+                    int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
+                    unsigned long long drop_seed, cudaStream_t s);
 
 // querypool.cu
 int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,

@@ -214,24 +214,34 @@ int b200clip_rope3d_apply(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_s
 
 /* ------------------------------------------------------------------------------------------------
  * K8  Attention pooling with one learnable query (models/attention_pool.py:77-93), folded form:
- *     scores s_hn = x_n . qt_h, a_h = softmax_n(s_h), xbar_h = sum_n a_hn x_n. x [B, N, D] (D contiguous,
+ *     scores s_hn = x_n . qt_h, a_h = softmax_n(s_h), xbar_h = sum_n a'_hn x_n. x [B, N, D] (D contiguous,
  *     D*sizeof(dtype) a multiple of 512 bytes), mask [B, N] bytes (non-zero = ignore) or NULL, heads <= 16.
- *   attnpool_fwd    : per (batch row, token split) partial (m, l, acc[heads][D]); with `weights` [B, heads, N]
- *                     given instead of qt it computes plain weighted sums (used for dqt in the backward).
- *   attnpool_merge  : merges the splits -> out [B, heads, D] (+ m, l [B, heads]); weighted-sum mode: part_m NULL,
- *                     sum_over_b = 1 accumulates over the batch into out [heads, D] (caller zeroes).
- *   attnpool_bwd_dx : dx_n = sum_h a_hn dxbar_h + ds_hn qt_h, ds_hn = a_hn (dxbar_h . x_n - dxbar_h . xbar_h);
- *                     writes dx [B, N, D] (input dtype, contiguous) and ds [B, heads, N] fp32.
+ *     16-bit x with heads <= 8 and D % 128 == 0 runs on mma.sync tiles fed by TMA, fp32 x on CUDA cores.
+ *     Attention dropout (nn.MultiheadAttention(dropout=p) in training mode, attention_pool.py:45-50): a' = a * keep /
+ *     (1 - p) with a counter-based keep mask (splitmix64 of drop_seed, b*heads + h, n) that the backward regenerates;
+ *     drop_p = 0 disables it. sa_h = sum_n a'_hn (1 without dropout) multiplies the value bias b_v.
+ *   attnpool_fwd    : per (batch row, token split) partial (m, l, acc[heads][D]) (+ l2 = sum of kept weights when
+ *                     drop_p > 0); with `weights` [B, heads, N] given instead of qt it computes plain weighted sums
+ *                     (used for dqt in the backward).
+ *   attnpool_merge  : merges the splits -> out [B, heads, D] (+ m, l [B, heads], sa [B, heads] if part_l2 / out_sa are
+ *                     given); weighted-sum mode: part_m NULL, sum_over_b = 1 accumulates over the batch into
+ *                     out [heads, D] (caller zeroes).
+ *   attnpool_bwd_dx : dx_n = sum_h a'_hn dxbar_h + ds_hn qt_h, ds_hn = a_hn (kappa_hn (dxbar_h . x_n + dsa_h) - c_h),
+ *                     c_h = dxbar_h . xbar_h + dsa_h sa_h; writes dx [B, N, D] (input dtype, contiguous) and
+ *                     ds [B, heads, N] fp32. sa / dsa [B, heads] may be NULL when drop_p = 0.
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_attnpool_splits(int B, int N);
 int b200clip_attnpool_fwd(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
                           const float* qt, const float* weights, int64_t w_sb, int64_t w_sh, int B, int N, int D,
-                          int heads, int splits, float* part_m, float* part_l, float* part_acc, void* stream);
+                          int heads, int splits, float* part_m, float* part_l, float* part_acc, float drop_p,
+                          int64_t drop_seed, float* part_l2, void* stream);
 int b200clip_attnpool_merge(const float* part_m, const float* part_l, const float* part_acc, int B, int splits,
-                            int heads, int D, float* out, float* out_m, float* out_l, int sum_over_b, void* stream);
+                            int heads, int D, float* out, float* out_m, float* out_l, int sum_over_b,
+                            const float* part_l2, float* out_sa, void* stream);
 int b200clip_attnpool_bwd_dx(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
                              const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l,
-                             int B, int N, int D, int heads, void* dx, float* ds, void* stream);
+                             int B, int N, int D, int heads, void* dx, float* ds, const float* sa, const float* dsa,
+                             float drop_p, int64_t drop_seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).

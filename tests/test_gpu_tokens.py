@@ -1,4 +1,6 @@
 """GPU parity: Rope3D, AttentionPool and the multi-view query pool vs the reference golden vectors / the oracle."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -151,3 +153,58 @@ def test_aggregator_with_blocks_matches_torch_composition():
     s = (mod.attn_query.expand(8, -1, -1) @ h.transpose(1, 2)).masked_fill(mask.unsqueeze(1), float("-inf"))
     ref = (torch.softmax(s, -1) @ h).squeeze(1)
     assert torch.allclose(out, ref, atol=2e-5, rtol=1e-5)
+
+
+def _keep_mask(seed, B, H, N, p, device):
+    """torch replica of attn_keep() (csrc/common.cuh): splitmix64 of (seed, b*H + h, n), top 24 bits >= p."""
+    M = (1 << 64) - 1
+    import numpy as np
+    rows = np.arange(B * H, dtype=np.uint64)[:, None]
+    n = np.arange(N, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (rows * np.uint64(0x100000001B3) + n + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return torch.tensor(u >= np.float32(p), device=device).view(B, H, N)
+
+
+@pytest.mark.parametrize("dtype,D,N", [(torch.float32, 128, 70), (torch.bfloat16, 256, 333), (torch.bfloat16, 512, 100)])
+def test_attention_pool_training_dropout(dtype, D, N):
+    """Training-mode attention dropout (reference default attention_pool_dropout = 0.1): our counter-based mask is not
+    PyTorch's Philox stream, so the check is (1) exact: forward / backward equal a float64 autograd replica of
+    nn.MultiheadAttention's math driven by the SAME mask, (2) statistical: the keep rate is 1 - p."""
+    from deepcoro_clip_b200 import attention_pool as ap
+    B, H, p = 3, 8, 0.25
+    torch.manual_seed(7)
+    mod = ap.AttentionPool(D, H, dropout=p).to("cuda:0").train()
+    x = torch.randn(B, N, D, device="cuda:0").to(dtype).requires_grad_(True)
+    torch.manual_seed(123)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # what forward() will draw
+    torch.manual_seed(123)
+    out = mod(x)
+    gout = torch.randn_like(out.float())
+    out.float().backward(gout)
+    keep = _keep_mask(seed, B, H, N, p, "cuda:0")
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.03
+    # float64 replica with the same mask
+    xd = x.detach().double().requires_grad_(True)
+    Wd = mod.attn.in_proj_weight.detach().double(); bd = mod.attn.in_proj_bias.detach().double()
+    Dh = D // H
+    q0 = (mod.query.detach().double().view(1, D) @ Wd[:D].T + bd[:D]).view(H, Dh)
+    K = (xd @ Wd[D:2 * D].T + bd[D:2 * D]).view(B, N, H, Dh)
+    V = (xd @ Wd[2 * D:].T + bd[2 * D:]).view(B, N, H, Dh)
+    s_ = torch.einsum("hk,bnhk->bhn", q0, K) / math.sqrt(Dh)
+    a = torch.softmax(s_, dim=-1) * keep.double() / (1 - p)
+    o = torch.einsum("bhn,bnhk->bhk", a, V).reshape(B, D)
+    y = o @ mod.attn.out_proj.weight.detach().double().T + mod.attn.out_proj.bias.detach().double()
+    y = torch.nn.functional.layer_norm(y, (D,), mod.norm.weight.detach().double(), mod.norm.bias.detach().double(), mod.norm.eps)
+    y.backward(gout.double())
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert _rel(out.float().detach().cpu().numpy(), y.detach().cpu().numpy()) < tol
+    assert _rel(x.grad.float().cpu().numpy(), xd.grad.cpu().numpy()) < (5e-5 if dtype == torch.float32 else 1.5e-2)
+    # eval mode ignores dropout
+    mod.eval()
+    o1 = mod(x.detach()); o2 = mod(x.detach())
+    assert torch.equal(o1, o2)

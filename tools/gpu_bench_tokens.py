@@ -68,13 +68,13 @@ pm = torch.empty((Bp, S, 8), device=dev); pl = torch.empty((Bp, S, 8), device=de
 xbar = torch.empty((Bp, 8, D), device=dev); m = torch.empty((Bp, 8), device=dev); l = torch.empty((Bp, 8), device=dev)
 st = stream_ptr(dev)
 def k_fwd():
-    call("attnpool_fwd", xd, DTYPE_CODE[xd.dtype], i64(xd.stride(0)), i64(xd.stride(1)), None, i64(0), qt, None, i64(0), i64(0), Bp, Np, D, 8, S, pm, pl, pa, st)
-    call("attnpool_merge", pm, pl, pa, Bp, S, 8, D, xbar, m, l, 0, st)
+    call("attnpool_fwd", xd, DTYPE_CODE[xd.dtype], i64(xd.stride(0)), i64(xd.stride(1)), None, i64(0), qt, None, i64(0), i64(0), Bp, Np, D, 8, S, pm, pl, pa, 0.0, 0, None, st)
+    call("attnpool_merge", pm, pl, pa, Bp, S, 8, D, xbar, m, l, 0, None, None, st)
 ms_k = timeit(k_fwd, reps=20)
 res["attnpool_fwd_kernels_only"] = {"ms": ms_k, "splits": S, "GBps": bx / ms_k / 1e6, "frac_hbm": bx / ms_k / 1e6 / HBM}
 dxbar = torch.randn(Bp, 8, D, device=dev); dx = torch.empty_like(xd); ds = torch.empty((Bp, 8, Np), device=dev)
 def k_bwd():
-    call("attnpool_bwd_dx", xd, DTYPE_CODE[xd.dtype], i64(xd.stride(0)), i64(xd.stride(1)), None, i64(0), qt, dxbar, xbar, m, l, Bp, Np, D, 8, dx, ds, st)
+    call("attnpool_bwd_dx", xd, DTYPE_CODE[xd.dtype], i64(xd.stride(0)), i64(xd.stride(1)), None, i64(0), qt, dxbar, xbar, m, l, Bp, Np, D, 8, dx, ds, None, None, 0.0, 0, st)
 ms_k = timeit(k_bwd, reps=20)
 res["attnpool_bwd_dx_kernel_only"] = {"ms": ms_k, "GBps": 2 * bx / ms_k / 1e6, "frac_hbm": 2 * bx / ms_k / 1e6 / HBM, "algorithmic_bytes": 2 * bx}
 # ---- multi-view query pool: [8, 4, 512] fp32 ----
