@@ -43,6 +43,16 @@ def gather_rows(x: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
     return out
 
 
+def gather_rows_async(x: torch.Tensor, world_size: int, group=None):
+    """Like gather_rows but returns (out, work) with the all-gather running on the communicator's stream; call
+    ``work.wait()`` (a stream dependency, not a host sync) before the first kernel that reads ``out``."""
+    if world_size == 1:
+        return x, None
+    out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    work = dist.all_gather_into_tensor(out, x.contiguous(), group=group, async_op=True)
+    return out, work
+
+
 def reduce_sum_(x: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
     if world_size > 1:
         dist.all_reduce(x, group=group)

@@ -68,17 +68,21 @@ class _ClipLossFn(torch.autograd.Function):
         mode = BW_GATED if gated else BW_CLIP
         st = ops.stream_ptr(dev)
 
-        vop, vinv, Kp = ops.l2norm_operand(video, 0 if x3 else -1)
-        top, tinv, _ = ops.l2norm_operand(text, 1 if x3 else -1)
+        # text operands first: their all-gather overlaps the video normalise; the video all-gather (needed only by the
+        # backward's text-side pass) overlaps the forward tile kernel
+        top, tinv, Kp = ops.l2norm_operand(text, 1 if x3 else -1)
+        tall, t_work = dist_plan.gather_rows_async(top, W, group)
+        vop, vinv, _ = ops.l2norm_operand(video, 0 if x3 else -1)
+        vall, v_work = dist_plan.gather_rows_async(vop, W, group)
         K = vop.shape[1]
-        vall = _all_gather_rows(vop, W, group)
-        tall = _all_gather_rows(top, W, group)
         dyn = ops.dyn_prep(log_temp, None, clamp_min, ops.GATED_BOUND if gated else 1.0)
 
         # arena: [colsum (N) | rowsum (N) | dots (N)] zeroed (other ranks' slices stay 0 for the all-reduce) | scales (2N)
         ws = torch.zeros(5 * N + 2, dtype=torch.float32, device=dev)
         sums = ws[:3 * N]
         lo = rank * B
+        if t_work is not None:
+            t_work.wait()
         ops.call("logits_lse_fwd", vop, tall, B, N, K, vop.stride(0), tall.stride(0), 0.0, 0.0, int(gated), dyn,
                  ws[N + lo:N + lo + B], ws[:N], ws[2 * N + lo:2 * N + lo + B], lo, st)
         if W > 1:
@@ -89,11 +93,16 @@ class _ClipLossFn(torch.autograd.Function):
         if eps != 0.0:
             if gated:
                 raise B200ClipError("label_smoothing is not defined for the gated legacy loss")
+            if v_work is not None:
+                v_work.wait()
+                v_work = None
             vsum = ops.colsum_bf16(vall[:, K - Kp:], N, D)      # hi panel (last in bf16x3 mode)
             tsum = ops.colsum_bf16(tall[:, K - Kp:], N, D)
             unif_tgt = ((eps / N) * torch.dot(vsum.double(), tsum.double()) * dyn[2].double()).reshape(1)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         ops.call("clip_finalize", sums, N, dyn, eps, int(gated), unif_tgt, rowscale_all, colscale_all, loss, None, st)
+        if v_work is not None:
+            v_work.wait()                  # vall is read by the backward only
 
         ctx.save_for_backward(video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, vsum, tsum,
                               unif_tgt)
