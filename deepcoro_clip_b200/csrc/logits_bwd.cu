@@ -360,8 +360,8 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   // B200CLIP_BWD_PAIR=0 keeps the single-CTA kernel (A/B measurements).
   // Experimental (opt-in, B200CLIP_BWD_QUAD=1): 4-CTA clusters sharing one S/G tile between the two D halves
   // (logits_bwd4.cu). Correct, executes 4*B*N*D instead of 6*B*N*D, but MEASURED SLOWER than the pair kernel (2.74 vs
-  // 2.03 ms at 32k x 32k x 512): next to the resident X panel and the G staging buffer only a 64 KB TMA ring fits,
-  // below the bandwidth-delay product of the 32 B/cycle operand stream. Kept for the next round's shared-memory plan.
+  // 2.03 ms at 32k x 32k x 512): only ONE 32 KB staging buffer fits next to the X panel and the ring, so every push
+  // waits for the partner pair's previous output product. Kept for the next round's shared-memory plan.
   static const bool quad_on = [] { const char* e = getenv("B200CLIP_BWD_QUAD"); return e && e[0] == '1'; }();
   if (quad_on && Kp <= BW_XRES_CHUNKS * BW_BK && !hp && Dp == 2 * BW_DP && Nx >= 1024 && Ny >= 2048) {
     const int rc = logits_bwd_quad(mode, X, Y, Nx, Ny, Kp, Dp, D, hi_off, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c,

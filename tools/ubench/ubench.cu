@@ -23,6 +23,7 @@ struct UB {
   int stagger;     // CTA-dependent start offset
   int nacc;        // accumulators rotated between consecutive MMA instructions (1 = dependent chain)
   int kmajor_b;    // 0: B K-major, 1: B MN-major
+  int nslots;      // ring slots actually used by the tma test (<= SLOTS); 0 = SLOTS
   unsigned long long* cyc;   // [grid][2]
 };
 
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(128, 1) ub_kernel(const __grid_constant__ CUte
   tc_fence_after();
   const uint32_t tbase = *tslot;
   const int row_tiles = p.rows / 128;
+  const int NSL = p.nslots > 0 ? p.nslots : SLOTS;
   if (warp == 0 && lane == 0 && (p.mode & 1)) {
     int slot = 0; uint32_t ph = 0;
     int t = p.stagger ? (blockIdx.x * 7) % row_tiles : 0, kc = 0;
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(128, 1) ub_kernel(const __grid_constant__ CUte
       mbar_expect_tx(&full[slot], CH);
       tma_load_2d(ring + slot * CH, &tm, &full[slot], kc * 64, t * 128);
       if (++kc == 8) { kc = 0; if (++t == row_tiles) t = 0; }
-      if (++slot == SLOTS) { slot = 0; ph ^= 1; }
+      if (++slot == NSL) { slot = 0; ph ^= 1; }
     }
   } else if (warp == 1 && lane == 0 && (p.mode & 1)) {
     unsigned long long t0 = clock64();
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(128, 1) ub_kernel(const __grid_constant__ CUte
     for (int c = 0; c < p.tma_chunks; ++c) {
       mbar_wait(&full[slot], ph);
       mbar_arrive(&empty[slot]);
-      if (++slot == SLOTS) { slot = 0; ph ^= 1; }
+      if (++slot == NSL) { slot = 0; ph ^= 1; }
     }
     p.cyc[blockIdx.x * 2 + 0] = clock64() - t0;
   } else if (warp == 3 && (p.mode & 2)) {
@@ -198,6 +200,12 @@ int main(int argc, char** argv) {
   run_tight<64,1>(cyc,sms); run_tight<128,1>(cyc,sms); run_tight<256,1>(cyc,sms);
   if (argc > 1 && argv[1][0]=='t') return 0;
   UB p{}; 
+  if (argc > 1 && argv[1][0]=='l') {     // latency: bytes in flight vs achieved rate (Little's law), all 148 CTAs streaming
+    for (int ns : {1, 2, 3, 4, 6, 8}) { char nm[64]; snprintf(nm, 64, "tma slots in flight=%d", ns); UB q{}; q.mode = 1; q.tma_chunks = 6000; q.stagger = 1; q.nslots = ns; run(nm, q); }
+    grid = 8;
+    for (int ns : {1, 2, 4}) { char nm[64]; snprintf(nm, 64, "tma slots=%d, 8 CTAs only", ns); UB q{}; q.mode = 1; q.tma_chunks = 6000; q.stagger = 1; q.nslots = ns; run(nm, q); }
+    return 0;
+  }
   if (argc > 1 && argv[1][0]=='g') {
     for (int g : {1, 8, 37, 74, 111, 148}) { grid = g; char nm[64]; snprintf(nm, 64, "tma grid=%d", g); UB q{}; q.mode = 1; q.tma_chunks = 20000; q.stagger = 1; run(nm, q); }
     return 0;
