@@ -4,13 +4,15 @@ Hand-written CUDA (tcgen05 / TMEM / TMA) behind a C ABI (include/b200clip.h); no
 from .attention_pool import AttentionPool
 from .host_pipeline import HostBatchPrefetcher
 from .install import install, loss_table
-from .loss import (CLIPLoss, ContrastiveLoss, ContrastiveLossDDP, InfoNCELoss, SigLIPLoss, SiglipLoss,
-                   SiglipLossDDP, clip_loss)
+from .loss import (CLIPLoss, ContrastiveLoss, ContrastiveLossDDP, InfoNCELoss, SigLIP2BCELoss, SigLIP2BCELossDDP,
+                   SigLIP2MultiPositiveBCELoss, SigLIPLoss, SiglipLoss, SiglipLossDDP, SiglipPairwiseFeatureLoss,
+                   clip_loss)
 from .retrieval_metrics_streaming import (compute_metrics_streaming, compute_recall_at_k_streaming, streaming_topk)
 from .rope_3d import Rope3D, apply_rope_qk
 from .video_aggregator import EnhancedVideoAggregator, query_pool
 
 __all__ = ["AttentionPool", "CLIPLoss", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EnhancedVideoAggregator",
-           "InfoNCELoss", "Rope3D", "SigLIPLoss", "SiglipLoss", "SiglipLossDDP", "apply_rope_qk", "clip_loss",
+           "InfoNCELoss", "Rope3D", "SigLIP2BCELoss", "SigLIP2BCELossDDP", "SigLIP2MultiPositiveBCELoss", "SigLIPLoss",
+           "SiglipLoss", "SiglipLossDDP", "SiglipPairwiseFeatureLoss", "apply_rope_qk", "clip_loss",
            "compute_metrics_streaming", "compute_recall_at_k_streaming", "install", "loss_table", "query_pool",
            "streaming_topk"]

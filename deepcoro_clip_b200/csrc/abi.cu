@@ -106,6 +106,11 @@ int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min,
   return dyn_prep(log_temp, bias, clamp_min, bound, dyn, S(stream));
 }
 
+int b200clip_dyn_set_siglip(float* dyn, float logit_clamp, float neg_target, void* stream) {
+  if (!dyn || !(logit_clamp > 0.f)) return B2_EINVAL;
+  return dyn_set_siglip(dyn, logit_clamp, neg_target, S(stream));
+}
+
 int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc,
                           void* stream) {
   if (!sums || !dyn) return B2_EINVAL;
@@ -127,6 +132,30 @@ int b200clip_siglip_dense_fwd(const void* video, const void* text, int B, int T,
                               const float* dyn, double* acc, void* stream) {
   if (!video || !text || !dyn || !acc) return B2_EINVAL;
   return siglip_dense_fwd(video, text, B, T, Kp, ldv, ldt, dyn, acc, S(stream));
+}
+
+int b200clip_siglip_entropy_rowsum(const void* video, const void* text, int B, int T, int Kp, int ldv, int ldt,
+                                   const float* dyn, float* Z, void* stream) {
+  if (!video || !text || !dyn || !Z) return B2_EINVAL;
+  return siglip_entropy_rowsum(video, text, B, T, Kp, ldv, ldt, dyn, Z, S(stream));
+}
+
+int b200clip_siglip_entropy_stats(const void* video, const void* text, int B, int T, int Kp, int ldv, int ldt,
+                                  const float* dyn, const float* Z, float* H, float* Q, void* stream) {
+  if (!video || !text || !dyn || !Z || !H || !Q) return B2_EINVAL;
+  return siglip_entropy_stats(video, text, B, T, Kp, ldv, ldt, dyn, Z, H, Q, S(stream));
+}
+
+int b200clip_siglip_entropy_rows(const float* Z, const float* H, const float* Q, int B, float* rowvec, double* stats,
+                                 void* stream) {
+  if (!Z || !H || !Q || !rowvec || !stats) return B2_EINVAL;
+  return siglip_entropy_rows(Z, H, Q, B, rowvec, stats, S(stream));
+}
+
+int b200clip_siglip_entropy_coef(const double* stats_all, int W, int B_global, int T, float weight, float threshold,
+                                 float* dyn, float* out, void* stream) {
+  if (!stats_all || !dyn || !out) return B2_EINVAL;
+  return siglip_entropy_coef(stats_all, W, B_global, T, weight, threshold, dyn, out, S(stream));
 }
 
 int b200clip_siglip_compact(const float* pos_mask, int64_t ld_mask, const float* pos_weights, int64_t ld_weights, int B,

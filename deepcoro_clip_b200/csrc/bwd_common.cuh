@@ -24,7 +24,13 @@ struct BwSmem {
   static constexpr int kBytes = kColOff + 2 * 128 * 4 + 1024 /*alignment slack*/;
 };
 
-enum { BW_CLIP = 0, BW_GATED = 1, BW_SIGLIP = 2 };
+enum { BW_CLIP = 0, BW_GATED = 1, BW_SIGLIP = 2, BW_SIGLIP_ENT = 3 };
+// BW_SIGLIP_ENT = BW_SIGLIP plus the gradient of the entropy regulariser (utils/loss/contrastive.py:19-68):
+//   G_ij += ent_coef * p_ij * (h_ij - m_i) * [|R| <= clamp],  p_ij = exp(L_ij - 30) / Z_i,
+//   h_ij = -ln(p_ij + 1e-10) - p_ij / (p_ij + 1e-10),  m_i = sum_j p_ij h_ij.
+// The per-video pairs {1/Z_i, m_i} arrive through `rowscale` ([Nx][2], X = video) or `colscale` ([Ny][2], Y = video).
+template <int kMode>
+struct BwIsSiglip { static constexpr bool value = kMode == BW_SIGLIP || kMode == BW_SIGLIP_ENT; };
 
 struct BwParams {
   int Nx, Ny;          // valid rows of X and Y
@@ -37,7 +43,10 @@ struct BwParams {
   float* diag_corr;    // optional [Nx][2]: {g_ii - bf16(g_ii), bf16(g_ii)} for the fp32 fix-up in l2norm_bwd
   int x_tiles, y_tiles, dparts, nseg;
   float scale2, shift2;        // CLIP: P = 2^(f(S)*scale2 - shift2)
-  float inv_tau, bias, wneg_c; // SigLIP: R = S*inv_tau + bias ; G = wneg_c * sigmoid(clamp R) * [|R|<=30]
+  float inv_tau, bias, wneg_c; // SigLIP: R = S*inv_tau + bias ; G = wneg_c * (sigmoid(clamp R) - yneg) * [|R|<=lclamp]
+  float lclamp;                // logit clamp (30; 3e38 for the SigLIP2 BCE variants that do not clamp)   dyn[8]
+  float yneg;                  // target of the non-positive pairs (label smoothing eps/2, default 0)      dyn[9]
+  float ent_coef;              // BW_SIGLIP_ENT: -entropy_weight / B_global while the deficit is positive  dyn[10]
   const float* rowscale;       // [Nx]  c / rowsum_x  (CLIP)
   const float* colscale;       // [Ny]  c / colsum_y  (CLIP)
   float out_scale;             // 1 / tau
@@ -66,6 +75,7 @@ struct BwThread {
   int wg;           // column half of the S tile / accumulator
   float rs;         // rowscale[row] * gnorm (CLIP / gated)
   float ydn, wn, ign, nshift2;
+  float ent_iz = 0.f, ent_m = 0.f;   // BW_SIGLIP_ENT with X = video: 1/Z_row, m_row
 };
 
 // G tile of one step: S (fp32, TMEM) -> elementwise gradient -> bf16x2 packed IN PLACE (tcgen05.st).
@@ -86,19 +96,22 @@ template <int kMode>
 __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th, uint32_t sbase, uint32_t cs_addr,
                                           const float* cs, int xt, int j, int dp, bool want_scal, float& tacc,
                                           float& lacc, float& bacc, uint32_t remote_row = 0) {
+  constexpr bool kSig = BwIsSiglip<kMode>::value;
+  constexpr bool kEnt = kMode == BW_SIGLIP_ENT;
   const int row = th.row, wg = th.wg;
   const bool row_ok = th.row_ok;
   const float rs = th.rs, ydn = th.ydn, wn = th.wn, ign = th.ign, nshift2 = th.nshift2;
+  const float lc = p.lclamp, yneg = p.yneg;
   const bool full = (xt * BW_BM + BW_BM <= p.Nx) && (j * BW_BN + BW_BN <= p.Ny);
   // does the target diagonal cross this tile? (block-uniform)
   const int dlo = xt * BW_BM + p.diag_off - j * BW_BN;
-  const bool has_diag = kMode != BW_SIGLIP && p.ydiag != 0.f && dlo > -BW_BM && dlo < BW_BN;
+  const bool has_diag = !kSig && p.ydiag != 0.f && dlo > -BW_BM && dlo < BW_BN;
   const int dcol = row + p.diag_off - j * BW_BN - wg * 64;   // diagonal column relative to this thread's half
   uint32_t acc[2][32];
   tmem_ld32(sbase, acc[0]);
   tmem_ld32(sbase + 32, acc[1]);
   tc_wait_ld();
-  if (full && !has_diag && !p.hp) {
+  if (full && !has_diag && !p.hp && !kEnt) {
     // -------- fast path: interior tile, no bounds / diagonal tests --------
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -106,22 +119,22 @@ __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th,
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
         float cs4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (kMode != BW_SIGLIP) lds128(cs_addr + (c * 32 + e) * 4, cs4);
+        if (!kSig) lds128(cs_addr + (c * 32 + e) * 4, cs4);
         float g4[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const float s = __uint_as_float(acc[c][e + h]);
           float g;
-          if (kMode == BW_SIGLIP) {
+          if (kSig) {
             const float R = fmaf(s, p.inv_tau, p.bias);
-            const float Lc = fminf(fmaxf(R, -30.f), 30.f);
+            const float Lc = fminf(fmaxf(R, -lc), lc);
             const float ex = ex2_approx(-1.4426950408889634f * fabsf(Lc));
             const float den = 1.f + ex;
             const float r = __fdividef(1.f, den);
             const float sig = Lc >= 0.f ? r : ex * r;
-            g = (fabsf(R) <= 30.f) ? wn * sig : 0.f;
+            g = (fabsf(R) <= lc) ? wn * (sig - yneg) : 0.f;
             if (want_scal) {
-              lacc += fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den);
+              lacc += fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den));
               bacc += g;
               tacc = fmaf(g, s, tacc);
             }
@@ -158,15 +171,30 @@ __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th,
           const float s = __uint_as_float(acc[c][e + h]);
           const int cl = wg * 64 + c * 32 + e + h;     // column inside the tile
           float g, f = s;
-          if (kMode == BW_SIGLIP) {
+          if (kSig) {
             const float R = fmaf(s, p.inv_tau, p.bias);
-            const float Lc = fminf(fmaxf(R, -30.f), 30.f);
+            const float Lc = fminf(fmaxf(R, -lc), lc);
             const float ex = ex2_approx(-1.4426950408889634f * fabsf(Lc));
             const float den = 1.f + ex;
             const float r = __fdividef(1.f, den);
             const float sig = Lc >= 0.f ? r : ex * r;
-            g = (fabsf(R) <= 30.f) ? wn * sig : 0.f;
-            float sp = fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den);
+            const bool inr = fabsf(R) <= lc;
+            g = inr ? wn * (sig - yneg) : 0.f;
+            float sp = fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den));
+            if (kEnt) {
+              // entropy regulariser: p = exp(L - 30) / Z_video, video = this row (rowscale) or this column (colscale)
+              const int colg = j * BW_BN + cl;
+              float iz = th.ent_iz, mv = th.ent_m;
+              if (p.colscale) {
+                const bool cok = colg < p.Ny;
+                iz = cok ? __ldg(p.colscale + 2 * colg) : 0.f;
+                mv = cok ? __ldg(p.colscale + 2 * colg + 1) : 0.f;
+              }
+              const float pij = ex2_approx((Lc - 30.f) * 1.4426950408889634f) * iz;
+              const float pe = pij + 1e-10f;
+              const float h = -0.6931471805599453f * lg2_approx(pe) - __fdividef(pij, pe);
+              if (inr) g = fmaf(p.ent_coef * p.gnorm, pij * (h - mv), g);
+            }
             if (!full && !(row_ok && (j * BW_BN + cl) < p.Ny)) { g = 0.f; sp = 0.f; }
             lacc += sp;
             bacc += g;

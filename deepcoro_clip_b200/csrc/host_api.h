@@ -63,6 +63,7 @@ int logits_bwd_quad(int mode, const void* X, const void* Y, int Nx, int Ny, int 
 
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
+int dyn_set_siglip(float* dyn, float lclamp, float yneg, cudaStream_t s);
 int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s);
 int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s);
 int clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif, float* rowscale,
@@ -75,6 +76,14 @@ int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, in
 // siglip.cu
 int siglip_dense_fwd(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const float* dyn,
                      double* acc, cudaStream_t stream);
+int siglip_entropy_rowsum(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const float* dyn,
+                          float* Z, cudaStream_t stream);
+int siglip_entropy_stats(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const float* dyn,
+                         const float* Z, float* H, float* Q, cudaStream_t stream);
+int siglip_entropy_rows(const float* Z, const float* H, const float* Q, int B, float* rowvec, double* stats,
+                        cudaStream_t s);
+int siglip_entropy_coef(const double* stats_all, int W, int Bg, int T, float weight, float thr, float* dyn, float* out,
+                        cudaStream_t s);
 int siglip_compact(const float* mask, long ldm, const float* pw, long ldw, int B, int T, int cap, int* col, float* y,
                    float* w, int* cnt, float* ysum, int* overflow, cudaStream_t s);
 int siglip_pos(const void* V, int ldv, const void* T, int ldt, int K, int Dp, int D, int hi_off, int B, int Tn, int cap,

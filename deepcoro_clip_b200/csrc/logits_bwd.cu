@@ -95,6 +95,9 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
     p.inv_tau = p.dyn[2];
     p.bias = p.dyn[5];
     p.out_scale = p.dyn[2];
+    p.lclamp = p.dyn[8];
+    p.yneg = p.dyn[9];
+    p.ent_coef = p.dyn[10];
   }
 
   // item decode (identical in every role): item -> X tile, Y tile range [j0, j1)
@@ -255,15 +258,19 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
       const int T = nj * p.dparts;
       const int row = xt * BW_BM + q * 32 + lane;
       const bool row_ok = row < p.Nx;
-      float rs = 0.f;
-      if (kMode != BW_SIGLIP) rs = row_ok ? p.rowscale[row] * p.gnorm : 0.f;
+      float rs = 0.f, ent_iz = 0.f, ent_m = 0.f;
+      if (!BwIsSiglip<kMode>::value) rs = row_ok ? p.rowscale[row] * p.gnorm : 0.f;
+      if (kMode == BW_SIGLIP_ENT && p.rowscale && row_ok) {
+        ent_iz = p.rowscale[2 * row];
+        ent_m = p.rowscale[2 * row + 1];
+      }
       double dtacc = 0.0, dlacc = 0.0, dbacc = 0.0;
       for (int t = 0; t < T; ++t, ++tile_ctr) {
         const int dp = t / nj, jr = t - dp * nj, j = j0 + jr;
         const bool want_scal = p.scal != nullptr && dp == 0;
         float tacc = 0.f, lacc = 0.f, bacc = 0.f;      // per-tile fp32 partials, accumulated in fp64 across tiles
         const int buf = tile_ctr & 1;
-        if (kMode != BW_SIGLIP) {
+        if (!BwIsSiglip<kMode>::value) {
           if (etid < 128) {
             const int col = j * BW_BN + etid;
             col_s[buf * 128 + etid] = col < p.Ny ? p.colscale[col] * p.gnorm : 0.f;
@@ -275,7 +282,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
         const uint32_t sbase = tmem_base + lane_off + s_col0 + buf * BW_BN + wg * 64;
         const uint32_t cs_addr = cs_base + buf * 128 * 4;
         {
-          BwThread th{row, row_ok, wg, rs, ydn, wn, ign, nshift2};
+          BwThread th{row, row_ok, wg, rs, ydn, wn, ign, nshift2, ent_iz, ent_m};
           bw_g_tile<kMode>(p, th, sbase, cs_addr, col_s + buf * 128, xt, j, dp, want_scal, tacc, lacc, bacc);
         }
         tc_wait_st();
@@ -283,7 +290,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
         __syncwarp();
         if (lane == 0) mbar_arrive(&gready_bar[buf]);
         dtacc += (double)tacc;
-        if (kMode == BW_SIGLIP) {
+        if (BwIsSiglip<kMode>::value) {
           dlacc += (double)lacc;
           dbacc += (double)bacc;
         }
@@ -293,7 +300,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
           ++acc_ctr;
           tc_fence_after();
           {
-            BwThread th{row, row_ok, wg, rs, ydn, wn, ign, nshift2};
+            BwThread th{row, row_ok, wg, rs, ydn, wn, ign, nshift2, ent_iz, ent_m};
             bw_drain(p, th, tmem_base + lane_off + acc_col + wg * 128, dp);
           }
           tc_fence_before();
@@ -304,14 +311,14 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
       if (p.scal) {
         for (int o = 16; o > 0; o >>= 1) {
           dtacc += __shfl_xor_sync(0xffffffffu, dtacc, o);
-          if (kMode == BW_SIGLIP) {
+          if (BwIsSiglip<kMode>::value) {
             dlacc += __shfl_xor_sync(0xffffffffu, dlacc, o);
             dbacc += __shfl_xor_sync(0xffffffffu, dbacc, o);
           }
         }
         if (lane == 0) {
           atomicAdd(p.scal + 0, dtacc * (double)ign);
-          if (kMode == BW_SIGLIP) {
+          if (BwIsSiglip<kMode>::value) {
             atomicAdd(p.scal + 1, dlacc);
             atomicAdd(p.scal + 2, dbacc * (double)ign);
           }
@@ -355,7 +362,9 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   if (Nx <= 0 || Ny <= 0 || Kp <= 0 || Kp % 64 || Dp <= 0 || Dp % 64 || hi_off < 0 || hi_off % 64 ||
       hi_off + Dp > Kp || D > Dp || D <= 0)
     return B2_EINVAL;
-  if (mode != BW_SIGLIP && (!rowscale || !colscale)) return B2_EINVAL;
+  if (mode != BW_SIGLIP && mode != BW_SIGLIP_ENT && (!rowscale || !colscale)) return B2_EINVAL;
+  if (mode == BW_SIGLIP_ENT && ((rowscale != nullptr) == (colscale != nullptr) || !dyn)) return B2_EINVAL;
+  const bool ent = mode == BW_SIGLIP_ENT;   // entropy term: single-CTA kernel only (general epilogue path)
   // headline shapes (plain bf16 operands, D <= 512): CTA-pair kernel, half the shared-memory ingest per SM.
   // B200CLIP_BWD_PAIR=0 keeps the single-CTA kernel (A/B measurements).
   // Experimental (opt-in, B200CLIP_BWD_QUAD=1): 4-CTA clusters sharing one S/G tile between the two D halves
@@ -363,14 +372,14 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   // 2.03 ms at 32k x 32k x 512): only ONE 32 KB staging buffer fits next to the X panel and the ring, so every push
   // waits for the partner pair's previous output product. Kept for the next round's shared-memory plan.
   static const bool quad_on = [] { const char* e = getenv("B200CLIP_BWD_QUAD"); return e && e[0] == '1'; }();
-  if (quad_on && Kp <= BW_XRES_CHUNKS * BW_BK && !hp && Dp == 2 * BW_DP && Nx >= 1024 && Ny >= 2048) {
+  if (!ent && quad_on && Kp <= BW_XRES_CHUNKS * BW_BK && !hp && Dp == 2 * BW_DP && Nx >= 1024 && Ny >= 2048) {
     const int rc = logits_bwd_quad(mode, X, Y, Nx, Ny, Kp, Dp, D, hi_off, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c,
                                    rowscale, colscale, out_scale, gnorm, hp, dyn, ydiag, diag_off, diag_corr, dX, ldd,
                                    scal, nseg_hint, stream);
     if (rc != B2_ENOSYS) return rc;
   }
   static const bool pair_ok = [] { const char* e = getenv("B200CLIP_BWD_PAIR"); return !(e && e[0] == '0'); }();
-  if (pair_ok && Kp <= BW_XRES_CHUNKS * BW_BK && !hp && Dp % 128 == 0 && sm_count() >= 2)
+  if (!ent && pair_ok && Kp <= BW_XRES_CHUNKS * BW_BK && !hp && Dp % 128 == 0 && sm_count() >= 2)
     return logits_bwd_pair(mode, X, Y, Nx, Ny, Kp, Dp, D, hi_off, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c,
                            rowscale, colscale, out_scale, gnorm, hp, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal,
                            nseg_hint, stream);
@@ -400,6 +409,7 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   p.rowscale = rowscale; p.colscale = colscale; p.out_scale = out_scale;
   p.gnorm = gnorm > 0.f ? gnorm : 1.f;
   p.hp = hp ? 1 : 0;
+  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f;
   p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
   CUtensorMap tmX, tmY;
   int rc;
@@ -412,6 +422,7 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   if (mode == BW_CLIP) return LAUNCH(BW_CLIP);
   if (mode == BW_GATED) return LAUNCH(BW_GATED);
   if (mode == BW_SIGLIP) return LAUNCH(BW_SIGLIP);
+  if (mode == BW_SIGLIP_ENT) return LAUNCH(BW_SIGLIP_ENT);
 #undef LAUNCH
   return B2_EINVAL;
 }

@@ -96,6 +96,8 @@ bw2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     p.inv_tau = p.dyn[2];
     p.bias = p.dyn[5];
     p.out_scale = p.dyn[2];
+    p.lclamp = p.dyn[8];
+    p.yneg = p.dyn[9];
   }
 
   auto decode = [&](int item, int& xp, int& j0, int& j1) {
@@ -380,6 +382,7 @@ int logits_bwd_pair(int mode, const void* X, const void* Y, int Nx, int Ny, int 
   p.rowscale = rowscale; p.colscale = colscale; p.out_scale = out_scale;
   p.gnorm = gnorm > 0.f ? gnorm : 1.f;
   p.hp = 0;
+  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f;
   p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
   CUtensorMap tmX, tmYs, tmYo;
   int rc;

@@ -5,6 +5,8 @@
 // Layout of the `dyn` float[16] block (read by logits_fwd / logits_bwd when their dyn pointer is non-null):
 //   [0] scale2 = log2(e)/tau   [1] shift2   [2] 1/tau   [3] tau   [4] 1 if tau was clamped (dlog_temp = 0)
 //   [5] bias                    [6] ln(2)*shift2        [7] 1 if (learnable) temperature gradient is live
+//   [8] SigLIP logit clamp (30) [9] SigLIP target of non-positive pairs (label smoothing eps/2, default 0)
+//   [10] entropy-regulariser gradient coefficient (written by siglip_entropy_coef, default 0)
 #include "common.cuh"
 #include "host_api.h"
 
@@ -33,6 +35,15 @@ __global__ void dyn_prep_kernel(const float* __restrict__ log_temp, const float*
   dyn[5] = bias ? bias[0] : 0.f;
   dyn[6] = 0.6931471805599453f * shift2;
   dyn[7] = 1.f - clamped;
+  dyn[8] = 30.f;
+  dyn[9] = 0.f;
+  dyn[10] = 0.f;
+}
+
+__global__ void dyn_set_siglip_kernel(float* __restrict__ dyn, float lclamp, float yneg) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  dyn[8] = lclamp;
+  dyn[9] = yneg;
 }
 
 // acc[slot] += sum_r ln( sums[r] ) + ln2*shift2 ;  scale_out[r] = c / sums[r]
@@ -170,6 +181,11 @@ using namespace b2;
 
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s) {
   dyn_prep_kernel<<<1, 32, 0, s>>>(log_temp, bias, clamp_min, bound, dyn);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int dyn_set_siglip(float* dyn, float lclamp, float yneg, cudaStream_t s) {
+  dyn_set_siglip_kernel<<<1, 32, 0, s>>>(dyn, lclamp, yneg);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

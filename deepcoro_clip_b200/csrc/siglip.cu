@@ -10,7 +10,7 @@
 namespace b2 {
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward-only dense term: acc += sum_ij softplus(clamp(S_ij/tau + bias, -30, 30))
+// forward-only dense term: acc += sum_ij [softplus(L_ij) - yneg L_ij], L = clamp(S_ij/tau + bias, -lclamp, lclamp)
 // ---------------------------------------------------------------------------------------------------------------
 struct SpParams {
   const float* dyn;     // [2] = 1/tau, [5] = bias
@@ -20,12 +20,14 @@ struct SoftplusEpi {
   using Params = SpParams;
   struct State {
     double total;
-    float inv_tau, bias;
+    float inv_tau, bias, lc, yneg;
   };
   __device__ static __forceinline__ void init(State& st, const Params& p) {
     st.total = 0.0;
     st.inv_tau = p.dyn[2];
     st.bias = p.dyn[5];
+    st.lc = p.dyn[8];
+    st.yneg = p.dyn[9];
   }
   __device__ static __forceinline__ void begin_outer(State&, const Params&, int, const TeCtx&) {}
   __device__ static __forceinline__ void chunk(State& st, const Params&, const TeCtx& ctx, int c,
@@ -35,9 +37,9 @@ struct SoftplusEpi {
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
       const float R = fmaf(__uint_as_float(acc[e]), st.inv_tau, st.bias);
-      const float L = fminf(fmaxf(R, -30.f), 30.f);
+      const float L = fminf(fmaxf(R, -st.lc), st.lc);
       const float ex = ex2_approx(-1.4426950408889634f * fabsf(L));
-      const float sp = fmaxf(L, 0.f) + 0.6931471805599453f * lg2_approx(1.f + ex);
+      const float sp = fmaf(-st.yneg, L, fmaxf(L, 0.f) + 0.6931471805599453f * lg2_approx(1.f + ex));
       part += (ctx.full || e < nvalid) ? sp : 0.f;
     }
     st.total += (double)part;
@@ -50,6 +52,125 @@ struct SoftplusEpi {
     st.total = 0.0;
   }
 };
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// entropy regulariser (utils/loss/contrastive.py:19-68), forward row statistics over the clamped logits L:
+//   pass 1 (EntSumEpi) : Z_i = sum_j exp(L_ij - 30)                     (L <= 30, so every term is in [e^-60, 1])
+//   pass 2 (EntStatEpi): p_ij = exp(L_ij - 30) / Z_i ; H_i = -sum_j p ln(p + 1e-10) ; Q_i = sum_j p^2 / (p + 1e-10)
+// (m_i = sum_j p_ij h_ij = H_i - Q_i is what the backward needs.) One fp32 atomic per thread per tile and row.
+// ---------------------------------------------------------------------------------------------------------------
+struct EntParams {
+  const float* dyn;
+  const float* Z;    // pass 2: [Ma] row sums of pass 1
+  float* out0;       // pass 1: Z ; pass 2: H
+  float* out1;       // pass 2: Q
+};
+template <bool kStats>
+struct EntEpi {
+  using Params = EntParams;
+  struct State {
+    float inv_tau, bias, a0, a1, iz;
+  };
+  __device__ static __forceinline__ void init(State& st, const Params& p) {
+    st.inv_tau = p.dyn[2];
+    st.bias = p.dyn[5];
+    st.a0 = st.a1 = 0.f;
+    st.iz = 0.f;
+  }
+  __device__ static __forceinline__ void begin_outer(State&, const Params&, int, const TeCtx&) {}
+  __device__ static __forceinline__ void chunk(State& st, const Params& p, const TeCtx& ctx, int c,
+                                               const uint32_t (&acc)[32]) {
+    if (kStats && c == 0) st.iz = ctx.row_ok ? 1.f / p.Z[ctx.row] : 0.f;
+    const int nvalid = ctx.row_ok ? ctx.Nb - (ctx.col0 + c * 32) : 0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float R = fmaf(__uint_as_float(acc[e]), st.inv_tau, st.bias);
+      const float L = fminf(fmaxf(R, -30.f), 30.f);
+      const float ex = ex2_approx((L - 30.f) * 1.4426950408889634f);
+      const bool ok = ctx.full || e < nvalid;
+      if (!kStats) {
+        st.a0 += ok ? ex : 0.f;
+      } else {
+        const float pij = ex * st.iz;
+        const float pe = pij + 1e-10f;
+        st.a0 -= ok ? pij * 0.6931471805599453f * lg2_approx(pe) : 0.f;
+        st.a1 += ok ? pij * __fdividef(pij, pe) : 0.f;
+      }
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State& st, const Params& p, const TeCtx& ctx) {
+    if (ctx.row_ok) {
+      atomicAdd(p.out0 + ctx.row, st.a0);
+      if (kStats) atomicAdd(p.out1 + ctx.row, st.a1);
+    }
+    st.a0 = st.a1 = 0.f;
+  }
+  __device__ static __forceinline__ void end_outer(State&, const Params&, int, const TeCtx&) {}
+};
+
+// rowvec[i] = {1/Z_i, m_i = H_i - Q_i}; stats = {sum_i H_i, min_i H_i, max_i H_i} over the local rows. One CTA,
+// fixed reduction order (deterministic).
+__global__ void __launch_bounds__(1024)
+siglip_entropy_rows_kernel(const float* __restrict__ Z, const float* __restrict__ H, const float* __restrict__ Q, int B,
+                           float* __restrict__ rowvec, double* __restrict__ stats) {
+  double sum = 0.0;
+  float mn = 3.4e38f, mx = -3.4e38f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float h = H[i];
+    rowvec[2 * i] = 1.f / Z[i];
+    rowvec[2 * i + 1] = h - Q[i];
+    sum += (double)h;
+    mn = fminf(mn, h);
+    mx = fmaxf(mx, h);
+  }
+  __shared__ double ssum[32];
+  __shared__ float smn[32], smx[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ssum[threadIdx.x >> 5] = sum;
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      sum += ssum[w];
+      mn = fminf(mn, smn[w]);
+      mx = fmaxf(mx, smx[w]);
+    }
+    stats[0] = sum;
+    stats[1] = (double)mn;
+    stats[2] = (double)mx;
+  }
+}
+
+// stats_all [W][3] (one triple per rank) -> mean / min / max entropy over the B_global rows, the penalty and the gradient
+// coefficient: out = {mean, min, max, mean / ln T, deficit = relu(thr - mean), weight * deficit};
+// dyn[10] = deficit > 0 ? -weight / B_global : 0.
+__global__ void siglip_entropy_coef_kernel(const double* __restrict__ stats_all, int W, int Bg, int T, float weight,
+                                           float thr, float* __restrict__ dyn, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sum = 0.0, mn = 3.4e38, mx = -3.4e38;
+  for (int r = 0; r < W; ++r) {
+    sum += stats_all[3 * r];
+    mn = fmin(mn, stats_all[3 * r + 1]);
+    mx = fmax(mx, stats_all[3 * r + 2]);
+  }
+  const float mean = (float)(sum / (double)Bg);
+  const float deficit = fmaxf(thr - mean, 0.f);
+  out[0] = mean;
+  out[1] = (float)mn;
+  out[2] = (float)mx;
+  out[3] = mean / logf((float)T);
+  out[4] = deficit;
+  out[5] = weight * deficit;
+  dyn[10] = deficit > 0.f ? -weight / (float)Bg : 0.f;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // positive-list compaction: one warp per video row scans pos_mask[row, :T] (and pos_weights) once.
@@ -126,7 +247,7 @@ struct PosParams {
   const float* dyn;
   float positive_weight, negative_weight, c, gnorm;
   int hp;
-  int use_pw, auto_balance;
+  int use_pw, auto_balance;  // use_pw: bit 0 = per-pair pos_weights, bit 1 = weight rule "mask > 0" instead of "target > 0.5"
   float* dV; int lddv;     // may be null (loss only)
   float* dT; int lddt;
   double* acc;
@@ -137,7 +258,8 @@ __global__ void __launch_bounds__(256) siglip_pos_kernel(PosParams p) {
   const int lane = threadIdx.x & 31;
   double a_loss = 0.0, a_bias = 0.0, a_t = 0.0;
   if (row < p.B) {
-    const float inv_tau = p.dyn[2], bias = p.dyn[5];
+    const float inv_tau = p.dyn[2], bias = p.dyn[5], lc = p.dyn[8], yneg = p.dyn[9];
+    const bool use_pw = (p.use_pw & 1) != 0, rule_mask = (p.use_pw & 2) != 0;
     const int n = p.cnt[row];
     float ratio = 1.f;
     if (p.auto_balance) {
@@ -147,7 +269,8 @@ __global__ void __launch_bounds__(256) siglip_pos_kernel(PosParams p) {
     const __nv_bfloat16* vr = p.V + (size_t)row * p.ldv;
     for (int e = 0; e < n; ++e) {
       const int j = p.col[(size_t)row * p.cap + e];
-      const float yv = p.y[(size_t)row * p.cap + e];
+      const float yraw = p.y[(size_t)row * p.cap + e];
+      const float yv = fmaf(yraw, 1.f - 2.f * yneg, yneg);          // label smoothing: y (1 - eps) + eps / 2
       const float pwv = p.w[(size_t)row * p.cap + e];
       const __nv_bfloat16* tr = p.T + (size_t)j * p.ldt;
       float s = 0.f;
@@ -159,17 +282,18 @@ __global__ void __launch_bounds__(256) siglip_pos_kernel(PosParams p) {
       }
       s = warp_sum(s);
       const float R = fmaf(s, inv_tau, bias);
-      const float L = fminf(fmaxf(R, -30.f), 30.f);
+      const float L = fminf(fmaxf(R, -lc), lc);
       const float ex = __expf(-fabsf(L));
       const float sp = fmaxf(L, 0.f) + log1pf(ex);
       const float sig = L >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
-      const float inr = fabsf(R) <= 30.f ? 1.f : 0.f;
+      const float inr = fabsf(R) <= lc ? 1.f : 0.f;
       float w = p.negative_weight;
-      if (yv > 0.5f) w = p.auto_balance ? ratio : (p.use_pw ? pwv * p.positive_weight : p.positive_weight);
+      if (rule_mask ? yraw > 0.f : yv > 0.5f)
+        w = p.auto_balance ? ratio : (use_pw ? pwv * p.positive_weight : p.positive_weight);
       const float g_full = w * (sig - yv) * inr * p.c;
-      const float g_dense = p.negative_weight * p.c * sig * inr;
+      const float g_dense = p.negative_weight * p.c * (sig - yneg) * inr;
       if (lane == 0) {
-        a_loss += (double)((w * (sp - L * yv) - p.negative_weight * sp) * p.c);
+        a_loss += (double)((w * (sp - L * yv) - p.negative_weight * (sp - L * yneg)) * p.c);
         a_bias += (double)(g_full - g_dense);
         a_t += (double)((g_full - g_dense) * s);
       }
@@ -228,6 +352,55 @@ int siglip_dense_fwd(const void* V, const void* T, int B, int Tn, int Kp, int ld
   if (total < grid) grid = (int)total;
   SpParams p{dyn, acc};
   kern<<<grid, TE_THREADS, TE_SMEM_BYTES, stream>>>(tmA, tmB, g, p);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+template <bool kStats>
+static int launch_ent(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const EntParams& p,
+                      cudaStream_t stream) {
+  TeShape g;
+  int rc = make_shape(g, B, Tn, Kp);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16_2d(&tmA, V, B, Kp, ldv, TE_BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmB, T, Tn, Kp, ldt, TE_BN))) return rc;
+  auto kern = te_kernel<EntEpi<kStats>, false>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
+      return B2_ECUDA;
+    attr_done = true;
+  }
+  const long long total = (long long)g.m_tiles * g.n_blocks;
+  int grid = sm_count();
+  if (total < grid) grid = (int)total;
+  kern<<<grid, TE_THREADS, TE_SMEM_BYTES, stream>>>(tmA, tmB, g, p);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int siglip_entropy_rowsum(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const float* dyn,
+                          float* Z, cudaStream_t stream) {
+  EntParams p{dyn, nullptr, Z, nullptr};
+  return launch_ent<false>(V, T, B, Tn, Kp, ldv, ldt, p, stream);
+}
+
+int siglip_entropy_stats(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const float* dyn,
+                         const float* Z, float* H, float* Q, cudaStream_t stream) {
+  EntParams p{dyn, Z, H, Q};
+  return launch_ent<true>(V, T, B, Tn, Kp, ldv, ldt, p, stream);
+}
+
+int siglip_entropy_rows(const float* Z, const float* H, const float* Q, int B, float* rowvec, double* stats,
+                        cudaStream_t s) {
+  if (B <= 0) return B2_EINVAL;
+  siglip_entropy_rows_kernel<<<1, 1024, 0, s>>>(Z, H, Q, B, rowvec, stats);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int siglip_entropy_coef(const double* stats_all, int W, int Bg, int T, float weight, float thr, float* dyn, float* out,
+                        cudaStream_t s) {
+  if (W <= 0 || Bg <= 0 || T <= 0) return B2_EINVAL;
+  siglip_entropy_coef_kernel<<<1, 32, 0, s>>>(stats_all, W, Bg, T, weight, thr, dyn, out);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -34,6 +34,16 @@ def loss_table(semantics: str = "main") -> Dict[str, type]:
     return dict(_MAIN if semantics == "main" else _COLD)
 
 
+# classes the reference keeps importable by name without registering them (utils/loss/siglip_pairwise.py:36-40,
+# utils/loss/siglip2_bce.py): rebound on their modules so `from utils.loss.siglip2_bce import SigLIP2BCELoss`
+# (utils/loss/locca_loss.py:429) picks up the B200 implementation
+_BY_NAME = {
+    "utils.loss.siglip_pairwise": {"SiglipPairwiseFeatureLoss": loss.SiglipPairwiseFeatureLoss},
+    "utils.loss.siglip2_bce": {"SigLIP2BCELoss": loss.SigLIP2BCELoss, "SigLIP2BCELossDDP": loss.SigLIP2BCELossDDP,
+                               "SigLIP2MultiPositiveBCELoss": loss.SigLIP2MultiPositiveBCELoss},
+}
+
+
 def install(reference_root: str | None = None, semantics: str = "main", losses: bool = True, modules: bool = True,
             metrics: bool = True) -> dict:
     """Registers / rebinds everything; returns a report {what: [names]} of what was replaced."""
@@ -45,6 +55,14 @@ def install(reference_root: str | None = None, semantics: str = "main", losses: 
         for key, cls in loss_table(semantics).items():
             registry.register(key)(cls)
             report["losses"].append(key)
+        for modname, names in _BY_NAME.items():
+            try:
+                mod = importlib.import_module(modname)
+            except Exception:
+                continue
+            for n, cls in names.items():
+                setattr(mod, n, cls)
+                report["losses"].append(f"{modname}.{n}")
     if modules:
         for modname in ("models.video_encoder",):
             mod = sys.modules.get(modname)

@@ -26,7 +26,8 @@ import torch.nn as nn
 from . import dist_plan, ops
 from ._lib import B200ClipError
 
-BW_CLIP, BW_GATED, BW_SIGLIP = 0, 1, 2
+BW_CLIP, BW_GATED, BW_SIGLIP, BW_SIGLIP_ENT = 0, 1, 2, 3
+_LOCAL = "local"   # cfg['group'] marker: never gather, even inside an initialised process group
 
 
 # --------------------------------------------------------------------------------------------------
@@ -264,10 +265,25 @@ class InfoNCELoss(nn.Module):
 # --------------------------------------------------------------------------------------------------
 # SigLIP multi-positive sigmoid loss
 # --------------------------------------------------------------------------------------------------
+_NO_CLAMP = 3.0e38   # logit clamp of the variants that do not clamp (utils/loss/siglip2_bce.py:88-90)
+
+
+def _siglip_cfg(**kw) -> dict:
+    cfg = dict(positive_weight=1.0, negative_weight=1.0, use_severity_weights=True, auto_balance=False,
+               precision="auto", max_positives=64, group=None, tau_clamp=1e-4, logit_clamp=30.0, label_smoothing=0.0,
+               pos_rule_mask=False, entropy=False, entropy_weight=0.1, entropy_threshold=2.0, ent_holder=None)
+    cfg.update(kw)
+    return cfg
+
+
 class _SigLIPFn(torch.autograd.Function):
     """utils/loss/contrastive.py:250-315; SURVEY Appendix A.2. Backward is a pure recompute, so when any input
     needs a gradient the two gradient passes run eagerly in forward (no separate forward GEMM) and ``backward``
-    only applies the normalise-backward with the upstream scale."""
+    only applies the normalise-backward with the upstream scale.
+
+    ``cfg`` selects the reference variant: ``tau_clamp`` (1e-4 | 0), ``logit_clamp`` (30 | none), ``label_smoothing``
+    (y (1 - eps) + eps / 2 on every pair, siglip2_bce.py:98-99), ``pos_rule_mask`` (positive weight where
+    pos_mask > 0, siglip_pairwise.py:352), ``entropy`` (contrastive.py:19-68, 306-313)."""
 
     @staticmethod
     def forward(ctx, video, text, log_temp, bias, pos_mask, pos_weights, cfg):
@@ -277,7 +293,7 @@ class _SigLIPFn(torch.autograd.Function):
                              "[B, D] and [T, D]")
         B, D = video.shape
         T = text.shape[0]
-        W, rank = _world(True, cfg["group"])
+        W, rank = (1, 0) if cfg["group"] is _LOCAL else _world(True, cfg["group"])
         Bg = B * W
         if pos_mask is not None and tuple(pos_mask.shape) != (B, T):
             raise ValueError(f"pos_mask must be [B, T] = {(B, T)}, got {tuple(pos_mask.shape)}")
@@ -287,9 +303,14 @@ class _SigLIPFn(torch.autograd.Function):
         vop, vinv, Kp = ops.l2norm_operand(video, 0 if x3 else -1)
         top, tinv, _ = ops.l2norm_operand(text, 1 if x3 else -1)
         K = vop.shape[1]
-        dyn = ops.dyn_prep(log_temp, bias, 1e-4, 1.0)
+        st = ops.stream_ptr(dev)
+        dyn = ops.dyn_prep(log_temp, bias, cfg["tau_clamp"], 1.0)
+        eps = float(cfg["label_smoothing"])
+        if cfg["logit_clamp"] != 30.0 or eps != 0.0:
+            ops.call("dyn_set_siglip", dyn, float(cfg["logit_clamp"]), 0.5 * eps, st)
         c = 1.0 / (Bg * T)
         wp, wn = cfg["positive_weight"], cfg["negative_weight"]
+        gn = 1.0 / ((wn if wn > 0.0 else 1.0) * c)     # the dense G is fed to the tensor core as G * gn = O(1)
 
         # ---- positives: one streaming pass over the dense mask / weights ----
         cap = cfg["max_positives"]
@@ -306,7 +327,6 @@ class _SigLIPFn(torch.autograd.Function):
             if pos_weights is not None and cfg["use_severity_weights"]:
                 pw = pos_weights.detach().float()
                 pw = pw if pw.stride(1) == 1 else pw.contiguous()
-        st = ops.stream_ptr(dev)
         if pos_mask is None and W > 1:
             # diagonal targets on the GLOBAL [B_global, T] matrix (:274-278): local row r is global row rank*B + r
             rows = torch.arange(B, device=dev, dtype=torch.int64) + rank * B
@@ -320,20 +340,39 @@ class _SigLIPFn(torch.autograd.Function):
             ops.call("siglip_compact", pm, ops.i64(pm.stride(0) if pm is not None else 0), pw,
                      ops.i64(pw.stride(0) if pw is not None else 0), B, T, cap, col, yv, wv, cnt, ysum, overflow, st)
 
+        # ---- entropy regulariser: row statistics of softmax_j(L_ij) before the gradient passes ----
+        mode, rowvec, ent = BW_SIGLIP, None, None
+        if cfg["entropy"]:
+            zhq = torch.zeros((3, B), dtype=torch.float32, device=dev)
+            ops.call("siglip_entropy_rowsum", vop, top, B, T, K, vop.stride(0), top.stride(0), dyn, zhq[0], st)
+            ops.call("siglip_entropy_stats", vop, top, B, T, K, vop.stride(0), top.stride(0), dyn, zhq[0], zhq[1], zhq[2],
+                     st)
+            rowvec = torch.empty((B, 2), dtype=torch.float32, device=dev)
+            stats = torch.empty(3, dtype=torch.float64, device=dev)
+            ops.call("siglip_entropy_rows", zhq[0], zhq[1], zhq[2], B, rowvec, stats, st)
+            stats_all = stats
+            if W > 1:
+                stats_all = torch.empty((W, 3), dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(stats_all, stats, group=cfg["group"])
+            ent = torch.empty(8, dtype=torch.float32, device=dev)
+            ops.call("siglip_entropy_coef", stats_all, W, Bg, T, float(cfg["entropy_weight"]),
+                     float(cfg["entropy_threshold"]), dyn, ent, st)
+            mode = BW_SIGLIP_ENT
+
         need_grad = any(ctx.needs_input_grad[:4])
         acc = torch.zeros(8, dtype=torch.float64, device=dev)   # [0] sum g*s [1] sum softplus [2] sum g | [4..6] positives
         dVh = dTh = None
         if need_grad:
             dVh = torch.zeros((B, D), dtype=torch.float32, device=dev)
             dTh = torch.zeros((T, D), dtype=torch.float32, device=dev)
-            ops.logits_bwd(BW_SIGLIP, vop, top, B, T, K, Kp, D, dyn, None, None, dVh, acc[0:4], wneg_c=wn * c,
-                           gnorm=1.0 / (wn * c), hp=x3)
-            ops.logits_bwd(BW_SIGLIP, top, vop, T, B, K, Kp, D, dyn, None, None, dTh, None, wneg_c=wn * c,
-                           gnorm=1.0 / (wn * c), hp=x3)
+            ops.logits_bwd(mode, vop, top, B, T, K, Kp, D, dyn, rowvec, None, dVh, acc[0:4], wneg_c=wn * c, gnorm=gn,
+                           hp=x3)
+            ops.logits_bwd(mode, top, vop, T, B, K, Kp, D, dyn, None, rowvec, dTh, None, wneg_c=wn * c, gnorm=gn, hp=x3)
         else:
             ops.call("siglip_dense_fwd", vop, top, B, T, K, vop.stride(0), top.stride(0), dyn, acc[1:2], st)
+        flags = int(pw is not None) | (2 if cfg["pos_rule_mask"] else 0)
         ops.call("siglip_pos", vop, vop.stride(0), top, top.stride(0), K, Kp, D, K - Kp, B, T, cap, col, yv, wv, cnt,
-                 ysum, dyn, float(wp), float(wn), float(c), 1.0 / (wn * c), int(x3), int(pw is not None), int(cfg["auto_balance"]), dVh,
+                 ysum, dyn, float(wp), float(wn), float(c), float(gn), int(x3), flags, int(cfg["auto_balance"]), dVh,
                  D if dVh is not None else 0, dTh, D if dTh is not None else 0, acc[4:7], st)
         # local sums -> global (every rank returns the full loss, reference DDP semantics)
         red = torch.stack([wn * c * acc[1] + acc[4], acc[2] + acc[5], acc[0] + acc[6]])   # loss, dbias, sum G*s
@@ -343,14 +382,18 @@ class _SigLIPFn(torch.autograd.Function):
                 dist.all_reduce(dTh, group=cfg["group"])      # text is replicated: every rank gets the full text grad
             dist.all_reduce(overflow, group=cfg["group"])
         loss = red[0] + torch.where(overflow[0] > 0, float("nan"), 0.0)    # never silently drop positives
+        if ent is not None:
+            if cfg["ent_holder"] is not None:
+                cfg["ent_holder"]["raw"] = torch.cat([ent[:6], loss.float().reshape(1)])
+            loss = loss + ent[5].double()
         ctx.save_for_backward(video, text, vinv, tinv, dyn, dVh, dTh, red)
-        ctx.meta = (log_temp.shape, log_temp.dtype, bias.shape, bias.dtype)
+        ctx.meta = (log_temp.shape, log_temp.dtype, None if bias is None else (bias.shape, bias.dtype))
         return loss.float()
 
     @staticmethod
     def backward(ctx, grad_out):
         video, text, vinv, tinv, dyn, dVh, dTh, red = ctx.saved_tensors
-        lt_shape, lt_dtype, b_shape, b_dtype = ctx.meta
+        lt_shape, lt_dtype, bmeta = ctx.meta
         gmul = grad_out.detach().reshape(1).float().contiguous()
         dV = dT = dLT = dB = None
         if ctx.needs_input_grad[0]:
@@ -360,14 +403,32 @@ class _SigLIPFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             # d loss / d log_temp = -sum G (R - b) = -(sum G*s)/tau ; zero while the tau clamp is active
             dLT = (-(red[2] * dyn[2].double()) * dyn[7].double() * gmul.double()).to(lt_dtype).reshape(lt_shape)
-        if ctx.needs_input_grad[3]:
-            dB = (red[1] * gmul.double()).to(b_dtype).reshape(b_shape)
+        if bmeta is not None and ctx.needs_input_grad[3]:
+            dB = (red[1] * gmul.double()).to(bmeta[1]).reshape(bmeta[0])
         return dV, dT, dLT, dB, None, None, None
+
+
+def _as_log_temp(log_temp, dev) -> torch.Tensor:
+    if not isinstance(log_temp, torch.Tensor):
+        log_temp = torch.tensor(float(log_temp), device=dev)
+    return log_temp.to(dev)
+
+
+_ENT_KEYS = ("entropy_mean", "entropy_min", "entropy_max", "entropy_normalized", "entropy_deficit", "entropy_loss",
+             "bce_loss")
+
+
+def _entropy_diagnostics(holder: dict) -> dict:
+    """The reference fills this dict with seven .item() calls per step (contrastive.py:58-64, 311-312); here it is ONE
+    device->host copy of seven floats."""
+    raw = holder.pop("raw", None)
+    return dict(zip(_ENT_KEYS, raw.tolist())) if raw is not None else {}
 
 
 class SigLIPLoss(nn.Module):
     """utils/loss/contrastive.py:171-319 — sigmoid BCE over every (video, text) pair with multi-positive masks,
-    severity weights and auto-balance. Same constructor / forward signature / ``bias`` attribute."""
+    severity weights, auto-balance and the optional entropy regulariser. Same constructor / forward signature /
+    ``bias`` attribute / ``get_entropy_diagnostics()``."""
 
     def __init__(self, bias_init: float = -10.0, learnable_bias: bool = True, positive_weight: float = 1.0,
                  negative_weight: float = 1.0, use_severity_weights: bool = True, auto_balance: bool = False,
@@ -391,19 +452,144 @@ class SigLIPLoss(nn.Module):
 
     def forward(self, video_features: torch.Tensor, text_features: torch.Tensor, log_temp: torch.Tensor,
                 pos_mask: Optional[torch.Tensor] = None, pos_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
-        if self.entropy_regularization:
-            raise NotImplementedError(
-                "entropy_regularization=True is not provided by the B200 kernels yet (the registry path constructs "
-                "SigLIPLoss() with the default False); see DESIGN.md 'out of scope'")
         dev = video_features.device
-        if not isinstance(log_temp, torch.Tensor):
-            log_temp = torch.tensor(float(log_temp), device=dev)
-        log_temp = log_temp.to(dev)
+        log_temp = _as_log_temp(log_temp, dev)
         bias = self.bias if self.bias.device == dev else self.bias.to(dev)
-        cfg = dict(positive_weight=self.positive_weight, negative_weight=self.negative_weight,
-                   use_severity_weights=self.use_severity_weights, auto_balance=self.auto_balance,
-                   precision=self.precision, max_positives=self.max_positives_per_row, group=None)
-        return _SigLIPFn.apply(video_features, text_features, log_temp, bias, pos_mask, pos_weights, cfg)
+        holder: dict = {}
+        cfg = _siglip_cfg(positive_weight=self.positive_weight, negative_weight=self.negative_weight,
+                          use_severity_weights=self.use_severity_weights, auto_balance=self.auto_balance,
+                          precision=self.precision, max_positives=self.max_positives_per_row,
+                          entropy=bool(self.entropy_regularization), entropy_weight=self.entropy_weight,
+                          entropy_threshold=self.min_entropy_threshold, ent_holder=holder)
+        loss = _SigLIPFn.apply(video_features, text_features, log_temp, bias, pos_mask, pos_weights, cfg)
+        if self.entropy_regularization:
+            self._last_entropy_diagnostics = _entropy_diagnostics(holder)
+        return loss
 
     def get_entropy_diagnostics(self) -> dict:
         return self._last_entropy_diagnostics
+
+
+class SiglipPairwiseFeatureLoss(nn.Module):
+    """utils/loss/siglip_pairwise.py:261-376 — the feature-level pairwise loss kept by the reference for backwards
+    compatibility: no bias, tau NOT clamped (:333), logits clamped to +-30 (:337), positive weight wherever
+    ``pos_mask > 0`` (:352), optional entropy regulariser; gathers video / mask / weights under DDP (:322-326)."""
+
+    def __init__(self, *, positive_weight: float = 1.0, negative_weight: float = 1.0, use_positive_weights: bool = True,
+                 auto_positive_weight: bool = False, entropy_regularization: bool = False, entropy_weight: float = 0.1,
+                 min_entropy_threshold: float = 2.0, precision: str = "auto", max_positives_per_row: int = 64) -> None:
+        super().__init__()
+        self.positive_weight = max(float(positive_weight), 1e-6)
+        self.negative_weight = max(float(negative_weight), 0.0)
+        self.use_positive_weights = use_positive_weights
+        self.auto_positive_weight = auto_positive_weight
+        self.entropy_regularization = entropy_regularization
+        self.entropy_weight = entropy_weight
+        self.min_entropy_threshold = min_entropy_threshold
+        self.precision = precision
+        self.max_positives_per_row = int(max_positives_per_row)
+        self._last_entropy_diagnostics: dict = {}
+
+    def forward(self, video_features: torch.Tensor, text_features: torch.Tensor, log_temp: torch.Tensor,
+                pos_mask: torch.Tensor, pos_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        dev = video_features.device
+        holder: dict = {}
+        cfg = _siglip_cfg(positive_weight=self.positive_weight, negative_weight=self.negative_weight,
+                          use_severity_weights=self.use_positive_weights, auto_balance=self.auto_positive_weight,
+                          precision=self.precision, max_positives=self.max_positives_per_row, tau_clamp=0.0,
+                          pos_rule_mask=True, entropy=bool(self.entropy_regularization),
+                          entropy_weight=self.entropy_weight, entropy_threshold=self.min_entropy_threshold,
+                          ent_holder=holder)
+        loss = _SigLIPFn.apply(video_features, text_features, _as_log_temp(log_temp, dev), None, pos_mask, pos_weights,
+                               cfg)
+        if self.entropy_regularization:
+            self._last_entropy_diagnostics = _entropy_diagnostics(holder)
+        return loss
+
+    def get_entropy_diagnostics(self) -> dict:
+        return self._last_entropy_diagnostics
+
+
+class _GatherTextRows(torch.autograd.Function):
+    """all_gather of the local text rows for the SigLIP2 DDP loss (siglip2_bce.py:194-224). ``_SigLIPFn`` already
+    all-reduces the text gradient, so the backward is the reference's: keep this rank's chunk, no reduce."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        W, rank = _world(True, group)
+        ctx.meta = (rank, x.shape[0])
+        out = torch.empty((W * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rank, n = ctx.meta
+        return g[rank * n:(rank + 1) * n], None
+
+
+class SigLIP2BCELoss(nn.Module):
+    """utils/loss/siglip2_bce.py:22-108 — one-to-one sigmoid BCE: identity labels, learnable bias, tau and logits NOT
+    clamped, label smoothing ``y (1 - eps) + eps / 2`` (:98-99); never gathers."""
+
+    _gather = False
+
+    def __init__(self, bias_init: float = -10.0, learnable_bias: bool = True, label_smoothing: float = 0.0,
+                 precision: str = "auto"):
+        super().__init__()
+        self.label_smoothing = label_smoothing
+        self.precision = precision
+        if learnable_bias:
+            self.bias = nn.Parameter(torch.tensor(bias_init))
+        else:
+            self.register_buffer("bias", torch.tensor(bias_init))
+
+    def forward(self, video_features: torch.Tensor, text_features: torch.Tensor,
+                log_temp: torch.Tensor) -> torch.Tensor:
+        dev = video_features.device
+        if video_features.shape != text_features.shape:
+            raise ValueError(f"video_features {tuple(video_features.shape)} and text_features "
+                             f"{tuple(text_features.shape)} must both be [B, D]")
+        bias = self.bias if self.bias.device == dev else self.bias.to(dev)
+        ddp = self._gather and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if ddp:
+            text_features = _GatherTextRows.apply(text_features, None)
+        cfg = _siglip_cfg(precision=self.precision, tau_clamp=0.0, logit_clamp=_NO_CLAMP,
+                          label_smoothing=float(self.label_smoothing), group=None if ddp else _LOCAL)
+        return _SigLIPFn.apply(video_features, text_features, _as_log_temp(log_temp, dev), bias, None, None, cfg)
+
+
+class SigLIP2BCELossDDP(SigLIP2BCELoss):
+    """utils/loss/siglip2_bce.py:115-186 — the same loss over the global batch: video AND text are gathered."""
+
+    _gather = True
+
+
+class SigLIP2MultiPositiveBCELoss(nn.Module):
+    """utils/loss/siglip2_bce.py:227-335 — multi-positive sigmoid BCE with label smoothing: logits clamped to +-30
+    (:296), tau not clamped, weights ``labels > 0.5 ? positive_weight [* pos_weights] : negative_weight`` (:313-322);
+    single process only (the reference never gathers here)."""
+
+    def __init__(self, bias_init: float = -10.0, learnable_bias: bool = True, positive_weight: float = 1.0,
+                 negative_weight: float = 1.0, label_smoothing: float = 0.0, precision: str = "auto",
+                 max_positives_per_row: int = 64):
+        super().__init__()
+        self.positive_weight = positive_weight
+        self.negative_weight = negative_weight
+        self.label_smoothing = label_smoothing
+        self.precision = precision
+        self.max_positives_per_row = int(max_positives_per_row)
+        if learnable_bias:
+            self.bias = nn.Parameter(torch.tensor(bias_init))
+        else:
+            self.register_buffer("bias", torch.tensor(bias_init))
+
+    def forward(self, video_features: torch.Tensor, text_features: torch.Tensor, log_temp: torch.Tensor,
+                pos_mask: Optional[torch.Tensor] = None, pos_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        dev = video_features.device
+        bias = self.bias if self.bias.device == dev else self.bias.to(dev)
+        cfg = _siglip_cfg(positive_weight=float(self.positive_weight), negative_weight=float(self.negative_weight),
+                          precision=self.precision, max_positives=self.max_positives_per_row, tau_clamp=0.0,
+                          label_smoothing=float(self.label_smoothing), group=_LOCAL)
+        return _SigLIPFn.apply(video_features, text_features, _as_log_temp(log_temp, dev), bias, pos_mask, pos_weights,
+                               cfg)

@@ -106,7 +106,13 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
  *       dX[i, :D] += out_scale * sum_j G_ij * Y[j, :D],   S = X Y^T recomputed per 128x128 tile.
  *     mode 0 (CLIP)   : G = 2^(S*scale2 - shift2) * (rowscale[i] + colscale[j])
  *     mode 1 (gated)  : same with f(S) = S*sigmoid(S) inside the exponent and G *= f'(S)
- *     mode 2 (SigLIP) : R = S*inv_tau + bias, G = wneg_c * sigmoid(clamp(R,+-30)) * [|R| <= 30]
+ *     mode 2 (SigLIP) : R = S*inv_tau + bias, G = wneg_c * (sigmoid(clamp(R,+-lc)) - yneg) * [|R| <= lc]; lc = dyn[8]
+ *                       (30), yneg = dyn[9] (label-smoothing target of the non-positive pairs, default 0)
+ *     mode 3 (SigLIP + entropy regulariser, utils/loss/contrastive.py:19-68, 306-313): mode 2 plus
+ *                       G_ij += dyn[10] * p_ij (h_ij - m_v) [|R| <= lc], p_ij = exp(L_ij - 30) / Z_v,
+ *                       h = -ln(p + 1e-10) - p / (p + 1e-10); v = the video of the pair. The pairs {1/Z_v, m_v}
+ *                       (b200clip_siglip_entropy_rows) are passed as rowscale [Nx][2] when X holds the videos or
+ *                       as colscale [Ny][2] when Y does (exactly one of the two non-NULL); dyn is required.
  *     modes 0/1: G_ij -= ydiag where i + diag_off == j (the (1-eps)/N diagonal target, subtracted in fp32 before G
  *     is rounded to bf16; diag_off = rank * B_local under DDP); diag_corr (may be NULL) receives per row
  *     {g_ii - rounded(g_ii), rounded(g_ii)} for b200clip_l2norm_bwd. SigLIP positives are rank-sparse corrections applied
@@ -130,12 +136,16 @@ int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, 
  * Device-side scalar plumbing (no host sync on log_temp / bias).
  *   dyn_prep     : tau = exp(log_temp) [clamped at clamp_min if > 0: contrastive.py:153, 266]; bound = max of
  *                  f(S) (1 for plain, 0.7311 for gated). dyn = {log2e/tau, shift2, 1/tau, tau, clamped, bias,
- *                  ln2*shift2, 1-clamped, ...} (float[16]).
+ *                  ln2*shift2, 1-clamped, logit clamp = 30, negative target = 0, entropy coefficient = 0, ...}
+ *                  (float[16]).
+ *   dyn_set_siglip : overrides dyn[8] (logit clamp; 3e38 = the SigLIP2 BCE variants that do not clamp,
+ *                  utils/loss/siglip2_bce.py:88-90) and dyn[9] (label smoothing eps/2, siglip2_bce.py:98-99).
  *   lse_finalize : acc[0] += sum_r (ln sums[r] + ln2*shift2)  (double) ; scale_out[r] = c / sums[r]
  *   diag_sum     : acc[0] += sum_r f(a[r,:K] . b[r,:K]) (double), f = identity / s*sigmoid(s); optional dots[r].
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn,
                       void* stream);
+int b200clip_dyn_set_siglip(float* dyn, float logit_clamp, float neg_target, void* stream);
 int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc,
                           void* stream);
 /* acc[0] += sum_i f(v[i]) in double, f = identity (gated = 0) or s*sigmoid(s) (gated = 1) */
@@ -158,16 +168,34 @@ int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* g
  * SigLIP multi-positive loss pieces (utils/loss/contrastive.py:230-315). The dense term treats every pair as a
  * negative (b200clip_logits_bwd mode 2 when gradients are needed, siglip_dense_fwd otherwise); the positives are
  * compacted from the dense fp32 pos_mask / pos_weights in ONE streaming pass and applied as exact corrections.
- *   siglip_dense_fwd : acc[0] += sum_ij softplus(clamp(S_ij/tau + bias, +-30))   (dyn from b200clip_dyn_prep)
+ *   siglip_dense_fwd : acc[0] += sum_ij [softplus(L_ij) - dyn[9] L_ij], L = clamp(S_ij/tau + bias, +-dyn[8])
  *   siglip_compact   : per video row, entries with clamp(pos_mask,0,1) > 0 -> col/y/w [B][cap], cnt[B], ysum[B]
  *                      (= sum_j y_ij, for auto_balance); *overflow = 1 if a row holds more than cap positives.
  *                      pos_mask == NULL: diagonal targets (:274-278). pos_weights may be NULL.
  *   siglip_pos       : for every entry adds  w(sp - L y) - wn sp  to acc[0] (scaled by c = 1/(B_global*T)), the
  *                      dbias / dlog_temp corrections to acc[1] / acc[2], and (dV, dT non-NULL) the gradient
  *                      corrections to dVhat[row] and (atomically) dThat[col]. Weight rule :283-298.
+ *                      use_pos_weights: bit 0 = multiply by the per-pair pos_weights; bit 1 = weight rule
+ *                      "pos_mask > 0" (utils/loss/siglip_pairwise.py:352) instead of "target > 0.5". Targets are
+ *                      smoothed with dyn[9]: y (1 - 2 yneg) + yneg.
+ *   Entropy regulariser (contrastive.py:19-68; compute_entropy_regularization), three passes over L = clamp(R):
+ *   siglip_entropy_rowsum : Z[i] += sum_j exp(L_ij - 30)                                  (caller zeroes Z)
+ *   siglip_entropy_stats  : p = exp(L - 30) / Z_i ; H[i] += -sum_j p ln(p + 1e-10) ; Q[i] += sum_j p^2 / (p + 1e-10)
+ *   siglip_entropy_rows   : rowvec[i] = {1 / Z_i, m_i = H_i - Q_i}; stats = {sum_i H_i, min_i H_i, max_i H_i} (double[3])
+ *   siglip_entropy_coef   : stats_all [W][3] (one triple per rank) -> out = {mean, min, max, mean / ln T,
+ *                           deficit = relu(threshold - mean), weight * deficit} and dyn[10] = deficit > 0 ?
+ *                           -weight / B_global : 0 (read by b200clip_logits_bwd mode 3).
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_siglip_dense_fwd(const void* video, const void* text, int B, int T, int Kp, int ldv, int ldt,
                               const float* dyn, double* acc, void* stream);
+int b200clip_siglip_entropy_rowsum(const void* video, const void* text, int B, int T, int Kp, int ldv, int ldt,
+                                   const float* dyn, float* Z, void* stream);
+int b200clip_siglip_entropy_stats(const void* video, const void* text, int B, int T, int Kp, int ldv, int ldt,
+                                  const float* dyn, const float* Z, float* H, float* Q, void* stream);
+int b200clip_siglip_entropy_rows(const float* Z, const float* H, const float* Q, int B, float* rowvec, double* stats,
+                                 void* stream);
+int b200clip_siglip_entropy_coef(const double* stats_all, int W, int B_global, int T, float weight, float threshold,
+                                 float* dyn, float* out, void* stream);
 int b200clip_siglip_compact(const float* pos_mask, int64_t ld_mask, const float* pos_weights, int64_t ld_weights, int B,
                             int T, int cap, int32_t* col, float* y, float* w, int32_t* cnt, float* ysum,
                             int32_t* overflow, void* stream);

@@ -11,6 +11,9 @@ Follows, line by line:
   CLIPLoss.forward            /root/reference/utils/loss/contrastive.py:140-164
   SigLIPLoss.forward          /root/reference/utils/loss/contrastive.py:250-315
   compute_entropy_regularization                          contrastive.py:19-68
+  SiglipPairwiseFeatureLoss   /root/reference/utils/loss/siglip_pairwise.py:300-371
+  SigLIP2BCELoss / DDP        /root/reference/utils/loss/siglip2_bce.py:79-106, 160-184
+  SigLIP2MultiPositiveBCELoss /root/reference/utils/loss/siglip2_bce.py:284-331
   ContrastiveLoss / DDP       /root/reference/utils/loss/losses.py:44-64, 132-158   (no tau clamp)
   SiglipLoss / DDP (gated)    /root/reference/utils/loss/losses.py:190-211, 241-276
 """
@@ -97,42 +100,68 @@ def entropy_regularization(logits: np.ndarray, min_entropy_threshold: float = 2.
     return deficit, diag, p, ent
 
 
-def siglip_loss(video, text, log_temp, *, bias: float = -10.0, pos_mask=None, pos_weights=None,
+def siglip_loss(video, text, log_temp, *, bias: float | None = -10.0, pos_mask=None, pos_weights=None,
                 positive_weight: float = 1.0, negative_weight: float = 1.0, use_severity_weights: bool = True,
                 auto_balance: bool = False, entropy_regularization_on: bool = False, entropy_weight: float = 0.1,
-                min_entropy_threshold: float = 2.0, dtype=np.float64, want_grads: bool = True) -> dict:
-    """SigLIPLoss.forward, contrastive.py:250-315 (single process: the gather is the identity)."""
+                min_entropy_threshold: float = 2.0, dtype=np.float64, want_grads: bool = True,
+                variant: str = "unified", label_smoothing: float = 0.0) -> dict:
+    """Sigmoid-BCE family (single process: the gather is the identity). ``variant``:
+      "unified"        SigLIPLoss.forward, contrastive.py:250-315
+      "pairwise"       SiglipPairwiseFeatureLoss.forward, siglip_pairwise.py:320-371 (no bias, tau unclamped,
+                       weights where pos_mask > 0, negative_weight >= 0)
+      "bce2"           SigLIP2BCELoss.forward, siglip2_bce.py:79-106 (identity labels, no clamps, label smoothing)
+      "multipositive2" SigLIP2MultiPositiveBCELoss.forward, siglip2_bce.py:284-331 (logit clamp, raw mask labels,
+                       label smoothing, weights by smoothed label > 0.5, pos_weights multiply)"""
     v = np.asarray(video, dtype=dtype)
     t = np.asarray(text, dtype=dtype)
     lt = dtype(np.asarray(log_temp, dtype=np.float64).reshape(-1)[0])
-    positive_weight = max(float(positive_weight), 1e-6)
-    negative_weight = max(float(negative_weight), 1e-6)
+    if variant == "unified":
+        positive_weight = max(float(positive_weight), 1e-6)
+        negative_weight = max(float(negative_weight), 1e-6)
+    elif variant == "pairwise":
+        positive_weight = max(float(positive_weight), 1e-6)
+        negative_weight = max(float(negative_weight), 0.0)
+        bias = None
     vh, vn = l2_normalize(v)
     th, tn = l2_normalize(t)
     S = vh @ th.T
     tau = np.exp(lt)
-    clamped = tau < 1e-4
+    clamped = variant == "unified" and tau < 1e-4
     if clamped:
         tau = dtype(1e-4)
-    R = S / tau + dtype(bias)
-    L = np.clip(R, -30.0, 30.0)
+    b = dtype(0.0 if bias is None else bias)
+    R = S / tau + b
+    lc = np.inf if variant == "bce2" else 30.0
+    L = np.clip(R, -lc, lc)
     B, T = L.shape
-    if pos_mask is None:
+    if pos_mask is None or variant == "bce2":
         y = np.zeros((B, T), dtype=dtype)
         m = min(B, T)
         y[:m, :m] = np.eye(m, dtype=dtype)
+        raw_mask = y
     else:
-        y = np.clip(np.asarray(pos_mask, dtype=dtype), 0.0, 1.0)
-    w = np.full((B, T), negative_weight, dtype=dtype)
-    if use_severity_weights and pos_weights is not None:
-        pc = np.asarray(pos_weights, dtype=dtype) * positive_weight
+        raw_mask = np.asarray(pos_mask, dtype=dtype)
+        y = raw_mask if variant == "multipositive2" else np.clip(raw_mask, 0.0, 1.0)
+    if label_smoothing > 0:
+        y = y * (1.0 - label_smoothing) + label_smoothing / 2.0
+    if variant in ("unified", "pairwise"):
+        w = np.full((B, T), negative_weight, dtype=dtype)
+        if use_severity_weights and pos_weights is not None:
+            pc = np.asarray(pos_weights, dtype=dtype) * positive_weight
+        else:
+            pc = np.full((B, T), positive_weight, dtype=dtype)
+        if auto_balance:
+            cnt_src = raw_mask if variant == "pairwise" else y
+            pos_counts = np.maximum(cnt_src.sum(axis=1, keepdims=True), 1.0)
+            ratio = np.maximum((T - pos_counts) / pos_counts, 1.0)
+            pc = np.broadcast_to(ratio, (B, T))
+        w = np.where((raw_mask > 0) if variant == "pairwise" else (y > 0.5), pc, w)
+    elif variant == "bce2":
+        w = np.ones((B, T), dtype=dtype)
     else:
-        pc = np.full((B, T), positive_weight, dtype=dtype)
-    if auto_balance:
-        pos_counts = np.maximum(y.sum(axis=1, keepdims=True), 1.0)
-        ratio = np.maximum((T - pos_counts) / pos_counts, 1.0)
-        pc = np.broadcast_to(ratio, (B, T))
-    w = np.where(y > 0.5, pc, w)
+        w = np.where(y > 0.5, dtype(positive_weight), dtype(negative_weight))
+        if pos_weights is not None:
+            w = np.where(y > 0.5, w * np.asarray(pos_weights, dtype=dtype), w)
     bce = np.maximum(L, 0.0) - L * y + np.log1p(np.exp(-np.abs(L)))
     loss = (w * bce).mean()
     out = {"bce_loss": float(loss), "tau": float(tau)}
@@ -150,12 +179,12 @@ def siglip_loss(video, text, log_temp, *, bias: float = -10.0, pos_mask=None, po
     out["loss"] = float(loss)
     if not want_grads:
         return out
-    dR = dL * ((R >= -30.0) & (R <= 30.0))
+    dR = dL * ((R >= -lc) & (R <= lc))
     dS = dR / tau
     out["dvideo"] = _normalize_backward(dS @ th, vh, vn)
     out["dtext"] = _normalize_backward(dS.T @ vh, th, tn)
     out["dbias"] = float(dR.sum())
-    out["dlog_temp"] = 0.0 if clamped else float(-(dR * (R - bias)).sum())
+    out["dlog_temp"] = 0.0 if clamped else float(-(dR * (R - b)).sum())
     return out
 
 

@@ -22,6 +22,8 @@ OUT.mkdir(parents=True, exist_ok=True)
 
 from utils.loss.contrastive import CLIPLoss, SigLIPLoss  # noqa: E402
 from utils.loss.losses import ContrastiveLoss, SiglipLoss  # noqa: E402
+from utils.loss.siglip_pairwise import SiglipPairwiseFeatureLoss  # noqa: E402
+from utils.loss.siglip2_bce import SigLIP2BCELoss, SigLIP2MultiPositiveBCELoss  # noqa: E402
 from utils.retrieval_metrics_streaming import compute_metrics_streaming, compute_recall_at_k_streaming  # noqa: E402
 from models.rope_3d import Rope3D  # noqa: E402
 from models.attention_pool import AttentionPool  # noqa: E402
@@ -99,6 +101,37 @@ def losses():
                    16, 32, 64, 24, math.log(0.05), mp(16, 32, 2))
     save_loss_case("siglip_bias0_b130_t260_d512", lambda: SigLIPLoss(bias_init=-1.0), 130, 260, 512, 25,
                    math.log(0.087), mp(130, 260, 4))
+
+
+def siglip_variants():
+    """Rows a6 of SURVEY §8: the SigLIP classes the reference keeps importable next to the unified SigLIPLoss."""
+    def mp(B, T, npos, weights=True):
+        def f(g):
+            m = torch.zeros(B, T)
+            m[torch.arange(B), torch.arange(B) % T] = 1.0
+            for _ in range(npos - 1):
+                m[torch.arange(B), torch.randint(0, T, (B,), generator=g)] = 1.0
+            out = {"pos_mask": m}
+            if weights:
+                choices = torch.tensor([1.0, 1.5, 2.5, 3.0])
+                out["pos_weights"] = m * choices[torch.randint(0, 4, (B, T), generator=g)]
+            return out
+        return f
+
+    save_loss_case("pairwise_mp_b24_t40_d64", lambda: SiglipPairwiseFeatureLoss(positive_weight=1.5, negative_weight=0.7),
+                   24, 40, 64, 30, math.log(0.087), mp(24, 40, 3))
+    save_loss_case("pairwise_entropy_auto_b16_t48_d64",
+                   lambda: SiglipPairwiseFeatureLoss(auto_positive_weight=True, entropy_regularization=True,
+                                                     entropy_weight=0.2, min_entropy_threshold=6.0),
+                   16, 48, 64, 31, math.log(0.06), mp(16, 48, 2, weights=False))
+    save_loss_case("bce2_b40_d96", lambda: SigLIP2BCELoss(), 40, 40, 96, 32, math.log(0.1))
+    save_loss_case("bce2_ls_noclamp_b32_d64", lambda: SigLIP2BCELoss(bias_init=-4.0, label_smoothing=0.1), 32, 32, 64, 33,
+                   math.log(0.02))          # |S / tau + b| reaches ~50: the variant must NOT clamp at 30
+    save_loss_case("mp2_ls_b20_t36_d64", lambda: SigLIP2MultiPositiveBCELoss(bias_init=-3.0, positive_weight=2.0,
+                                                                            negative_weight=0.5, label_smoothing=0.2),
+                   20, 36, 64, 34, math.log(0.08), mp(20, 36, 3))
+    save_loss_case("mp2_diag_b18_t30_d64", lambda: SigLIP2MultiPositiveBCELoss(bias_init=-5.0), 18, 30, 64, 35,
+                   math.log(0.04))          # clamp at +-30 active on part of the matrix
 
 
 def retrieval():
@@ -228,6 +261,6 @@ def qpool():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["losses", "retrieval", "rope", "attnpool", "qpool"]
+    which = sys.argv[1:] or ["losses", "siglip_variants", "retrieval", "rope", "attnpool", "qpool"]
     for name in which:
         globals()[name]()
