@@ -79,6 +79,45 @@ def main():
     check("  dlog_temp", abs(lt.grad.item() - o["dlog_temp"]) <= 2e-3 * max(abs(o["dlog_temp"]), 1e-4), (lt.grad.item(), o["dlog_temp"]))
     check("  dbias", abs(mod.bias.grad.item() - o["dbias"]) <= 2e-3 * max(abs(o["dbias"]), 1e-4), (mod.bias.grad.item(), o["dbias"]))
 
+    # ---------------- SigLIP + entropy regulariser: row statistics local, mean entropy over the GLOBAL rows ----------------
+    ent = SigLIPLoss(bias_init=-2.0, precision="bf16x3", entropy_regularization=True, entropy_weight=0.3,
+                     min_entropy_threshold=7.0).to(dev)
+    vt = torch.tensor(v[lo:hi], device=dev, requires_grad=True)
+    tt = torch.tensor(t, device=dev, requires_grad=True)
+    lt = torch.tensor([math.log(0.05)], device=dev, requires_grad=True)
+    loss = ent(vt, tt, lt, pos_mask=torch.tensor(pm[lo:hi], device=dev))
+    loss.backward()
+    o = co.siglip_loss(v, t, math.log(0.05), bias=-2.0, pos_mask=pm, entropy_regularization_on=True, entropy_weight=0.3,
+                       min_entropy_threshold=7.0)
+    check("siglip+entropy loss", abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"]) and
+          o["entropy_diagnostics"]["entropy_deficit"] > 0.05, (loss.item(), o["loss"]))
+    check("  dvideo rows", rel(vt.grad.cpu().numpy(), o["dvideo"][lo:hi]) <= 2e-3, rel(vt.grad.cpu().numpy(), o["dvideo"][lo:hi]))
+    check("  dtext (full)", rel(tt.grad.cpu().numpy(), o["dtext"]) <= 2e-3, rel(tt.grad.cpu().numpy(), o["dtext"]))
+    check("  dlog_temp", abs(lt.grad.item() - o["dlog_temp"]) <= 2e-3 * max(abs(o["dlog_temp"]), 1e-4), (lt.grad.item(), o["dlog_temp"]))
+    dg = ent.get_entropy_diagnostics()
+    check("  entropy_mean (global rows)", abs(dg["entropy_mean"] - o["entropy_diagnostics"]["entropy_mean"]) <= 2e-4,
+          (dg["entropy_mean"], o["entropy_diagnostics"]["entropy_mean"]))
+
+    # ---------------- SigLIP2BCELossDDP: video AND text gathered, identity labels on the global batch ----------------
+    from deepcoro_clip_b200.loss import SigLIP2BCELossDDP
+    B2, D2 = 96, 128
+    N2 = B2 * world
+    rng = np.random.default_rng(13)
+    v2 = rng.standard_normal((N2, D2)).astype(np.float32)
+    t2 = (0.6 * v2 + rng.standard_normal((N2, D2))).astype(np.float32)
+    lo2, hi2 = rank * B2, (rank + 1) * B2
+    vt = torch.tensor(v2[lo2:hi2], device=dev, requires_grad=True)
+    tt = torch.tensor(t2[lo2:hi2], device=dev, requires_grad=True)
+    lt = torch.tensor([math.log(0.1)], device=dev, requires_grad=True)
+    m2 = SigLIP2BCELossDDP(bias_init=-4.0, label_smoothing=0.1, precision="bf16x3").to(dev)
+    loss = m2(vt, tt, lt)
+    loss.backward()
+    o = co.siglip_loss(v2, t2, math.log(0.1), bias=-4.0, variant="bce2", label_smoothing=0.1)
+    check("siglip2 bce ddp loss", abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"]), (loss.item(), o["loss"]))
+    check("  dvideo rows", rel(vt.grad.cpu().numpy(), o["dvideo"][lo2:hi2]) <= 2e-3, rel(vt.grad.cpu().numpy(), o["dvideo"][lo2:hi2]))
+    check("  dtext rows", rel(tt.grad.cpu().numpy(), o["dtext"][lo2:hi2]) <= 2e-3, rel(tt.grad.cpu().numpy(), o["dtext"][lo2:hi2]))
+    check("  dbias", abs(m2.bias.grad.item() - o["dbias"]) <= 2e-3 * max(abs(o["dbias"]), 1e-4), (m2.bias.grad.item(), o["dbias"]))
+
     # ---------------- retrieval: text database sharded by rows, exact-grid embeddings with planted ties ----------------
     Nv, M, D = 3000, 1237, 256
     vv = ro.exact_grid_embeddings(Nv, D, 3); tx = ro.exact_grid_embeddings(M, D, 4)
