@@ -42,6 +42,13 @@ int logits_bwd_pair(int mode, const void* X, const void* Y, int Nx, int Ny, int 
                     const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
                     int nseg_hint, cudaStream_t stream);
 
+// logits_bwd3.cu: 64-row CTA pairs, whole output width in TMEM (Kp == Dp in {256, 512, 768}, hp == 0); B2_ENOSYS otherwise
+int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off, int ldx,
+                      int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
+                      const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
+                      const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
+                      int nseg_hint, cudaStream_t stream);
+
 // attnpool_mma.cu: 16-bit inputs on mma.sync (heads <= 8, D % 128 == 0, D <= 1024, 16-byte aligned rows)
 bool attnpool_mma_ok(const void* x, int dtype, long long sb, long long sn, int D, int H);
 int attnpool_fwd_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,

@@ -378,6 +378,16 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
                                    scal, nseg_hint, stream);
     if (rc != B2_ENOSYS) return rc;
   }
+  // 64-row CTA pairs with the whole output width in TMEM (logits_bwd3.cu): no S recompute. Default whenever the shape
+  // qualifies (plain bf16 operands, Dp in {256, 512, 768}): measured 1.54 vs 1.98 ms (D = 512) and 2.28 vs 5.50 ms
+  // (D = 768) per launch at 32k x 32k. B200CLIP_BWD3=0 keeps the 128-row kernels (A/B measurements).
+  static const bool bw3_on = [] { const char* e = getenv("B200CLIP_BWD3"); return !(e && e[0] == '0'); }();
+  if (!ent && bw3_on) {
+    const int rc = logits_bwd_pair64(mode, X, Y, Nx, Ny, Kp, Dp, D, hi_off, ldx, ldy, scale2, shift2, inv_tau, bias,
+                                     wneg_c, rowscale, colscale, out_scale, gnorm, hp, dyn, ydiag, diag_off, diag_corr,
+                                     dX, ldd, scal, nseg_hint, stream);
+    if (rc != B2_ENOSYS) return rc;
+  }
   static const bool pair_ok = [] { const char* e = getenv("B200CLIP_BWD_PAIR"); return !(e && e[0] == '0'); }();
   if (!ent && pair_ok && Kp <= BW_XRES_CHUNKS * BW_BK && !hp && Dp % 128 == 0 && sm_count() >= 2)
     return logits_bwd_pair(mode, X, Y, Nx, Ny, Kp, Dp, D, hi_off, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c,

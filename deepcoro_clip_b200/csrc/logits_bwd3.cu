@@ -1,0 +1,528 @@
+// K3 on CTA pairs with the WHOLE output width in TMEM: no S recompute per 256-column slice of D (Dp = 256/512/768).
+//
+// Why: the 128-row kernels (logits_bwd.cu, logits_bwd2.cu) keep a [128 x 256] fp32 accumulator next to the S/G buffers,
+// so D = 512 recomputes every S tile twice and D = 768 three times, and at Kp = 768 the 128-row X panel (192 KB) no
+// longer fits in shared memory, so X is re-streamed for every Y tile (measured 5.5 ms per launch at 32k x 32k x 768,
+// 0.18 of the bf16 peak). Here a CTA owns only 64 X rows:
+//
+//   cluster (2 CTAs) = one 128-row X tile; CTA rank r keeps rows [64 r, 64 r + 64) resident (Kp/64 boxes of 8 KB)
+//   tcgen05.mma.cta_group::2 with M = 128: every CTA holds a [64 x N] slice of the accumulator in the "2x2" TMEM
+//     layout — row m in lane m for columns [0, N/2) and in lane 64 + m for columns [N/2, N) — i.e. N/2 TMEM columns
+//     per N accumulator columns, so [64 x 768] fp32 takes 384 of the 512 columns and two [64 x 128] S buffers 128.
+//   S step   : SS, M = 128, N = 128: A = the X panels, B = Y_j rows [64 r, 64 r + 64) per CTA, K = Kp
+//   G        : epilogue warps read S (lanes 32q.., 32 columns per thread), form the gradient, round to bf16 and store it
+//              into SHARED memory as the K-major SWIZZLE_128B A operand [64 rows x 128 j] (the 2x2 accumulator layout
+//              splits the columns over the two lane halves, so G cannot be consumed from TMEM as in logits_bwd2.cu)
+//   out step : SS, M = 128, N = 256, K = 128 (the j of the tile), once per 256 output columns: A = G (own shared
+//              memory), B = Y_j[:, 256 n + 128 r + [0, 128)] as two MN-major [128 j x 64] boxes (LBO = 16 KB apart)
+//   The accumulator is drained once per (X tile, Y segment): executed work 4 * B * N * D per launch instead of
+//   (2 + 2 * Dp/256) * B * N * D.
+//
+// Barriers as in logits_bwd2.cu (TMA of both CTAs credits the leader's full barriers, multicast commits, remote arrives
+// of the peer's epilogue warps); the G hand-off crosses proxies (generic st.shared -> tensor-core read of the SAME
+// CTA's shared memory), so every writer executes fence.proxy.async.shared::cta before its warp arrives.
+#include "bwd_common.cuh"
+#include "host_api.h"
+#include <stdlib.h>
+
+namespace b2 {
+
+constexpr int BW3_NJ = 128;                 // Y rows per step
+constexpr int BW3_XROWS = 64;               // X rows per CTA
+constexpr int BW3_XCHUNK = BW3_XROWS * BW_BK * 2;     // 8 KB: [64 rows x 64 bf16]
+constexpr int BW3_MAXK = 12;                // Kp <= 768
+constexpr int BW3_SLOTS = 6;
+constexpr int BW3_SLOT = 16384;
+constexpr int BW3_GBUF = (BW3_NJ / 64) * BW3_XCHUNK;  // 16 KB: [64 rows x 128 j] bf16
+constexpr int BW3_G_OFF = BW3_MAXK * BW3_XCHUNK;      // 96 KB
+constexpr int BW3_RING_OFF = BW3_G_OFF + 2 * BW3_GBUF;
+constexpr int BW3_BAR_OFF = BW3_RING_OFF + BW3_SLOTS * BW3_SLOT;
+constexpr int BW3_COL_OFF = BW3_BAR_OFF + 256;
+constexpr int BW3_SMEM = BW3_COL_OFF + 8 * 32 * 4 + 1024;
+static_assert(BW3_SMEM <= 232448, "shared memory budget");
+constexpr int BW3_SCOL = 384;               // TMEM: [0, Dp/2) accumulator | [384, 448) S 0 | [448, 512) S 1
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// 32 S values of one thread (row th.row, tile columns c0 .. c0+31) -> 32 gradient values, packed bf16x2.
+// cs_addr: shared address of the 32 staged colscale*gnorm values; colg0: global column of element 0.
+template <int kMode, bool kFast>
+__device__ __forceinline__ void bw3_g32(const BwParams& p, const BwThread& th, const uint32_t (&acc)[32], uint32_t cs_addr,
+                                        int colg0, int dcol, float& tacc, float& lacc, float& bacc,
+                                        uint32_t (&packed)[16]) {
+  constexpr bool kSig = BwIsSiglip<kMode>::value;
+  const float lc = p.lclamp, yneg = p.yneg;
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    float cs4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!kSig) lds128(cs_addr + e * 4, cs4);
+    float g4[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float s = __uint_as_float(acc[e + h]);
+      const bool ok = kFast || (th.row_ok && (colg0 + e + h) < p.Ny);
+      float g;
+      if (kSig) {
+        const float R = fmaf(s, p.inv_tau, p.bias);
+        const float Lc = fminf(fmaxf(R, -lc), lc);
+        const float ex = ex2_approx(-1.4426950408889634f * fabsf(Lc));
+        const float den = 1.f + ex;
+        const float r = __fdividef(1.f, den);
+        const float sig = Lc >= 0.f ? r : ex * r;
+        g = (fabsf(R) <= lc) ? th.wn * (sig - yneg) : 0.f;
+        float sp = fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den));
+        if (!ok) { g = 0.f; sp = 0.f; }
+        lacc += sp;
+        bacc += g;
+        tacc = fmaf(g, s, tacc);
+      } else {
+        float f = s, fp = 1.f;
+        if (kMode == BW_GATED) {
+          const float ex = ex2_approx(-1.4426950408889634f * s);
+          const float sig = __fdividef(1.f, 1.f + ex);
+          f = s * sig;
+          fp = sig * (1.f + s * (1.f - sig));
+        }
+        g = ex2_approx(fmaf(f, p.scale2, th.nshift2)) * (th.rs + cs4[h]);
+        if (!kFast) {
+          if (e + h == dcol) g -= th.ydn;
+          if (!ok) g = 0.f;
+        }
+        tacc = fmaf(g, f, tacc);
+        if (kMode == BW_GATED) g *= fp;
+        if (!kFast && e + h == dcol && th.row_ok && p.diag_corr) {
+          const float gb = __bfloat162float(__float2bfloat16_rn(g));
+          p.diag_corr[2 * th.row] = (g - gb) * th.ign;
+          p.diag_corr[2 * th.row + 1] = gb * th.ign;
+        }
+      }
+      g4[h] = g;
+    }
+    packed[e >> 1] = pack_bf16x2(g4[0], g4[1]);
+    packed[(e >> 1) + 1] = pack_bf16x2(g4[2], g4[3]);
+  }
+}
+
+template <int kMode>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BW_THREADS, 1)
+bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmYs,
+           const __grid_constant__ CUtensorMap tmYo, BwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xs = smem;
+  uint8_t* gbuf = smem + BW3_G_OFF;
+  uint8_t* ring = smem + BW3_RING_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BW3_BAR_OFF);
+  uint64_t* full_bar = bars;                       // [6]  leader only: TMA (both CTAs) -> MMA
+  uint64_t* empty_bar = bars + BW3_SLOTS;          // [6]  both: MMA (multicast commit) -> TMA
+  uint64_t* sfull_bar = bars + 2 * BW3_SLOTS;      // [2]  both: S tile ready (multicast commit)
+  uint64_t* gready_bar = sfull_bar + 2;            // [2]  leader only: G in shared memory, 16 arrivals (8 warps x 2 CTAs)
+  uint64_t* accfull_bar = gready_bar + 2;          // [1]  both: accumulator ready (multicast commit)
+  uint64_t* accempty_bar = accfull_bar + 1;        // [1]  leader only: accumulator drained, 16 arrivals
+  uint64_t* xfull_bar = accempty_bar + 1;          // [1]  leader only: both X panels landed
+  uint64_t* xempty_bar = xfull_bar + 1;            // [1]  both: X panels free (multicast commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty_bar + 1);
+  float* col_s = reinterpret_cast<float*>(smem + BW3_COL_OFF);   // [8 epilogue warps][32]: warp-private colscale stage
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int kchunks = p.Kp / BW_BK;                // even (host checks Kp % 256 == 0)
+  const int nparts = p.Dp / 256;                   // N = 256 accumulator parts
+  const int items = p.x_tiles * p.nseg;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmYs);
+    tma_prefetch_desc(&tmYo);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < BW3_SLOTS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sfull_bar[s], 1);
+      mbar_init(&gready_bar[s], 16);
+    }
+    mbar_init(accfull_bar, 1);
+    mbar_init(accempty_bar, 16);
+    mbar_init(xfull_bar, 1);
+    mbar_init(xempty_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (p.dyn) {
+    p.scale2 = p.dyn[0];
+    p.shift2 = p.dyn[1];
+    p.inv_tau = p.dyn[2];
+    p.bias = p.dyn[5];
+    p.out_scale = p.dyn[2];
+    p.lclamp = p.dyn[8];
+    p.yneg = p.dyn[9];
+  }
+
+  auto decode = [&](int item, int& xt, int& j0, int& j1) {
+    const int seg = item % p.nseg;
+    xt = item / p.nseg;
+    j0 = (int)((long long)p.y_tiles * seg / p.nseg);
+    j1 = (int)((long long)p.y_tiles * (seg + 1) / p.nseg);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, each for its own halves) =====================
+    if (elect_one()) {
+      int slot = 0;
+      uint32_t phase = 0, xphase = 0;
+      for (int item = cluster_id; item < items; item += n_clusters) {
+        int xt, j0, j1;
+        decode(item, xt, j0, j1);
+        const int nj = j1 - j0;
+        if (nj <= 0) continue;
+        mbar_wait(xempty_bar, xphase ^ 1);
+        xphase ^= 1;
+        if (leader) mbar_expect_tx(xfull_bar, 2 * kchunks * BW3_XCHUNK);
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_2d_pair(xs + kc * BW3_XCHUNK, &tmX, xfull_bar, kc * BW_BK, xt * BW_BM + BW3_XROWS * (int)rank);
+        auto load_s = [&](int t) {
+          const int j = j0 + t;
+          for (int kp = 0; kp < kchunks / 2; ++kp) {
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            uint8_t* sl = ring + slot * BW3_SLOT;
+            if (leader) mbar_expect_tx(&full_bar[slot], 2 * BW3_SLOT);
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d_pair(sl + h * 8192, &tmYs, &full_bar[slot], (2 * kp + h) * BW_BK, j * BW3_NJ + 64 * (int)rank);
+            if (++slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
+          }
+        };
+        auto load_out = [&](int t) {
+          const int j = j0 + t;
+          for (int n = 0; n < nparts; ++n)
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait(&empty_bar[slot], phase ^ 1);
+              if (leader) mbar_expect_tx(&full_bar[slot], 2 * BW3_SLOT);
+              tma_load_2d_pair(ring + slot * BW3_SLOT, &tmYo, &full_bar[slot],
+                               p.hi_off + (4 * n + 2 * (int)rank + h) * BW_BK, j * BW3_NJ);
+              if (++slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
+            }
+        };
+        load_s(0);
+        for (int t = 0; t < nj; ++t) {
+          if (t + 1 < nj) load_s(t + 1);
+          load_out(t);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, BW3_NJ, 0, 0);     // A, B K-major; 64 rows of A and B per CTA
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 256, 0, 1);        // A = G (K-major), B MN-major, 128 columns / CTA
+      int slot = 0;
+      uint32_t phase = 0, xphase = 0;
+      uint32_t tile_ctr = 0, acc_ctr = 0;
+      const uint32_t xs_addr = smem_u32(xs), g_addr = smem_u32(gbuf);
+      for (int item = cluster_id; item < items; item += n_clusters) {
+        int xt, j0, j1;
+        decode(item, xt, j0, j1);
+        const int nj = j1 - j0;
+        if (nj <= 0) continue;
+        mbar_wait(xfull_bar, xphase);
+        xphase ^= 1;
+        tc_fence_after();
+        auto mma_s = [&](uint32_t tc) {
+          const uint32_t d_tmem = tmem_base + BW3_SCOL + (tc & 1) * (BW3_NJ / 2);
+          for (int kp = 0; kp < kchunks / 2; ++kp) {
+            mbar_wait(&full_bar[slot], phase);
+            tc_fence_after();
+            const uint32_t sl = smem_u32(ring + slot * BW3_SLOT);
+            for (int h = 0; h < 2; ++h) {
+              const uint64_t bdesc = make_smem_desc_sw128(sl + h * 8192, 1024);
+              const uint64_t adesc = make_smem_desc_sw128(xs_addr + (2 * kp + h) * BW3_XCHUNK, 1024);
+#pragma unroll
+              for (int k = 0; k < BW_BK / 16; ++k)
+                mma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_s, (kp | h | k) != 0);
+            }
+            tc_commit_pair(&empty_bar[slot], 3);
+            if (++slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
+          }
+          tc_commit_pair(&sfull_bar[tc & 1], 3);
+        };
+        auto mma_out = [&](uint32_t tc, bool first) {
+          const uint32_t ga = g_addr + (tc & 1) * BW3_GBUF;
+          for (int n = 0; n < nparts; ++n) {
+            // two consecutive ring slots = the two [128 j x 64] boxes of this CTA's 128 output columns (never wraps:
+            // every step uses an even number of slots and BW3_SLOTS is even)
+            mbar_wait(&full_bar[slot], phase);
+            mbar_wait(&full_bar[slot + 1], phase);
+            tc_fence_after();
+            const uint32_t sy = smem_u32(ring + slot * BW3_SLOT);
+            const uint32_t d_tmem = tmem_base + n * 128;
+            const uint64_t bdesc0 = make_smem_desc_sw128(sy, BW3_SLOT);
+#pragma unroll
+            for (int ks = 0; ks < BW3_NJ / 16; ++ks) {
+              const uint64_t bdesc = bdesc0 + uint64_t(ks * (2048 >> 4));
+              const uint64_t adesc = make_smem_desc_sw128(ga + (ks >> 2) * BW3_XCHUNK, 1024) + 2 * (ks & 3);
+              mma_ss_pair(d_tmem, adesc, bdesc, idesc_o, !(first && ks == 0));
+            }
+            tc_commit_pair(&empty_bar[slot], 3);
+            tc_commit_pair(&empty_bar[slot + 1], 3);
+            slot += 2;
+            if (slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
+          }
+        };
+        mma_s(tile_ctr);
+        if (nj == 1) tc_commit_pair(xempty_bar, 3);
+        for (int t = 0; t < nj; ++t) {
+          if (t + 1 < nj) {
+            mma_s(tile_ctr + 1);
+            if (t + 2 == nj) tc_commit_pair(xempty_bar, 3);
+          }
+          if (t == 0) {
+            mbar_wait(accempty_bar, (acc_ctr & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(&gready_bar[tile_ctr & 1], (tile_ctr >> 1) & 1);
+          tc_fence_after();
+          mma_out(tile_ctr, t == 0);
+          ++tile_ctr;
+          if (t == nj - 1) {
+            tc_commit_pair(accfull_bar, 3);
+            ++acc_ctr;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps 4..11 (both CTAs, own TMEM / own shared memory) =====================
+    const int q = warp & 3;               // TMEM lane quarter: rows 32 (q & 1) .., tile columns 64 (q >> 1) ..
+    const int wg = (warp - 4) >> 2;       // 32-column half of the quarter's 64 TMEM columns
+    uint32_t tile_ctr = 0, acc_ctr = 0;
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+    const int rloc = (q & 1) * 32 + lane;                 // row inside this CTA's 64
+    const int ctile = (q >> 1) * 64 + wg * 32;            // first tile column of this thread
+    const uint32_t gready_remote0 = mapa_cluster(smem_u32(&gready_bar[0]), 0);
+    const uint32_t gready_remote1 = mapa_cluster(smem_u32(&gready_bar[1]), 0);
+    const uint32_t accempty_remote = mapa_cluster(smem_u32(accempty_bar), 0);
+    // this thread's 64 bytes of the K-major SWIZZLE_128B G row: chunk (q >> 1), 16-byte units wg*4 .. wg*4+3
+    const uint32_t grow_addr = smem_u32(gbuf) + (q >> 1) * BW3_XCHUNK + rloc * 128;
+    BwThread th;
+    th.wg = wg;
+    th.ydn = p.ydiag * p.gnorm;
+    th.wn = p.wneg_c * p.gnorm;
+    th.ign = 1.f / p.gnorm;
+    th.nshift2 = -p.shift2;
+    for (int item = cluster_id; item < items; item += n_clusters) {
+      int xt, j0, j1;
+      decode(item, xt, j0, j1);
+      const int nj = j1 - j0;
+      if (nj <= 0) continue;
+      th.row = xt * BW_BM + BW3_XROWS * (int)rank + rloc;
+      th.row_ok = th.row < p.Nx;
+      th.rs = 0.f;
+      if (!BwIsSiglip<kMode>::value) th.rs = th.row_ok ? p.rowscale[th.row] * p.gnorm : 0.f;
+      const bool rows_full = xt * BW_BM + BW_BM <= p.Nx;
+      double dtacc = 0.0, dlacc = 0.0, dbacc = 0.0;
+      // column scales: lane e of every warp fetches the scale of the warp's e-th column one tile ahead (registers),
+      // stages it in a warp-private 32-float slot (__syncwarp only, no CTA barrier) and reads it back broadcast
+      auto load_cs = [&](int jt) -> float {
+        const int col = jt * BW3_NJ + ctile + lane;
+        return col < p.Ny ? __ldg(p.colscale + col) * p.gnorm : 0.f;
+      };
+      float cs_next = 0.f;
+      if (!BwIsSiglip<kMode>::value) cs_next = load_cs(j0);
+      for (int t = 0; t < nj; ++t, ++tile_ctr) {
+        const int j = j0 + t;
+        float tacc = 0.f, lacc = 0.f, bacc = 0.f;
+        const int buf = tile_ctr & 1;
+        if (!BwIsSiglip<kMode>::value) {
+          __syncwarp();                                   // previous tile's reads of the slot are done
+          col_s[(warp - 4) * 32 + lane] = cs_next;
+          if (t + 1 < nj) cs_next = load_cs(j + 1);
+          __syncwarp();
+        }
+        mbar_wait(&sfull_bar[buf], (tile_ctr >> 1) & 1);
+        tc_fence_after();
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + lane_off + BW3_SCOL + buf * (BW3_NJ / 2) + wg * 32, acc);
+        tc_wait_ld();
+        const int colg0 = j * BW3_NJ + ctile;
+        const bool full = rows_full && (j * BW3_NJ + BW3_NJ <= p.Ny);
+        // diagonal target column relative to this thread's 32 columns (CLIP / gated only)
+        int dcol = -1;
+        if (!BwIsSiglip<kMode>::value && p.ydiag != 0.f) {
+          const int d = th.row + p.diag_off - colg0;
+          dcol = (d >= 0 && d < 32) ? d : -1;
+        }
+        const int dlo = xt * BW_BM + p.diag_off - j * BW3_NJ;     // does the diagonal cross this pair tile? (uniform)
+        const bool has_diag = !BwIsSiglip<kMode>::value && p.ydiag != 0.f && dlo > -BW_BM && dlo < BW3_NJ;
+        uint32_t packed[16];
+        const uint32_t cs_addr = smem_u32(col_s) + (warp - 4) * 32 * 4;
+        if (full && !has_diag)
+          bw3_g32<kMode, true>(p, th, acc, cs_addr, colg0, -1, tacc, lacc, bacc, packed);
+        else
+          bw3_g32<kMode, false>(p, th, acc, cs_addr, colg0, dcol, tacc, lacc, bacc, packed);
+        const uint32_t ga = grow_addr + buf * BW3_GBUF;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          sts128(ga + (uint32_t((wg * 4 + u) ^ (rloc & 7)) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                 packed[4 * u + 3]);
+        // generic-proxy stores -> visible to the tensor core's (async proxy) reads of THIS CTA's shared memory. The
+        // .shared::cta form is enough (each SM's tensor core reads its own CTA's G half) and, unlike the unqualified
+        // fence.proxy.async / mbarrier.arrive.release.cluster pair, does not compile to MEMBAR.ALL.GPU + ERRBAR
+        // (measured: those two took 40 % of the epilogue's issue slots, profiles/r01d_*).
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(buf ? gready_remote1 : gready_remote0);
+        if (p.scal) {
+          dtacc += (double)tacc;
+          if (BwIsSiglip<kMode>::value) {
+            dlacc += (double)lacc;
+            dbacc += (double)bacc;
+          }
+        }
+        if (t == nj - 1) {
+          // ---- drain: accumulator part n, TMEM columns n*128 + wg*64 + [0, 64) of this lane quarter hold output
+          //      columns 256 n + 128 (q >> 1) + 64 wg + [0, 64) of row rloc ----
+          mbar_wait(accfull_bar, acc_ctr & 1);
+          ++acc_ctr;
+          tc_fence_after();
+          const float osc = p.out_scale * th.ign;
+          const bool vec_ok = (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dX) & 15) == 0;
+          for (int n = 0; n < nparts; ++n) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int d0 = 256 * n + 128 * (q >> 1) + 64 * wg + 32 * c;
+              if (d0 < p.D) {                     // warp-uniform
+                uint32_t a[32];
+                tmem_ld32(tmem_base + lane_off + n * 128 + wg * 64 + c * 32, a);
+                tc_wait_ld();
+                if (th.row_ok) {
+                  float* drow = p.dX + (size_t)th.row * p.ldd + d0;
+                  if (vec_ok && d0 + 32 <= p.D) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                      red_add_v4(drow + e, __uint_as_float(a[e]) * osc, __uint_as_float(a[e + 1]) * osc,
+                                 __uint_as_float(a[e + 2]) * osc, __uint_as_float(a[e + 3]) * osc);
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                      if (d0 + e < p.D) atomicAdd(drow + e, __uint_as_float(a[e]) * osc);
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(accempty_remote);
+        }
+      }
+      if (p.scal) {
+        for (int o = 16; o > 0; o >>= 1) {
+          dtacc += __shfl_xor_sync(0xffffffffu, dtacc, o);
+          if (BwIsSiglip<kMode>::value) {
+            dlacc += __shfl_xor_sync(0xffffffffu, dlacc, o);
+            dbacc += __shfl_xor_sync(0xffffffffu, dbacc, o);
+          }
+        }
+        if (lane == 0) {
+          atomicAdd(p.scal + 0, dtacc * (double)th.ign);
+          if (BwIsSiglip<kMode>::value) {
+            atomicAdd(p.scal + 1, dlacc);
+            atomicAdd(p.scal + 2, dbacc * (double)th.ign);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+}  // namespace b2
+
+namespace b2host {
+using namespace b2;
+
+template <int kMode>
+static int launch_bw3(const CUtensorMap& tmX, const CUtensorMap& tmYs, const CUtensorMap& tmYo, const BwParams& p,
+                      int grid, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(bw3_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW3_SMEM) != cudaSuccess)
+      return B2_ECUDA;
+    attr_done = true;
+  }
+  bw3_kernel<kMode><<<grid, BW_THREADS, BW3_SMEM, stream>>>(tmX, tmYs, tmYo, p);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+// Same contract as logits_bwd() (host_api.h) for plain bf16 operands with Kp == Dp in {256, 512, 768}; B2_ENOSYS for
+// anything else (the caller falls back to the other kernels).
+int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off, int ldx,
+                      int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
+                      const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
+                      const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
+                      int nseg_hint, cudaStream_t stream) {
+  if (hp || hi_off != 0 || Kp != Dp || Dp % 256 || Dp > BW3_MAXK * BW_BK || sm_count() < 2) return B2_ENOSYS;
+  if (mode != BW_CLIP && mode != BW_GATED && mode != BW_SIGLIP) return B2_ENOSYS;
+  BwParams p;
+  p.Nx = Nx; p.Ny = Ny; p.Kp = Kp; p.Dp = Dp; p.D = D; p.hi_off = 0; p.ydiag = ydiag; p.diag_off = diag_off;
+  p.diag_corr = diag_corr;
+  p.x_tiles = (Nx + BW_BM - 1) / BW_BM;              // 128-row X tiles, one per cluster item
+  p.y_tiles = (Ny + BW3_NJ - 1) / BW3_NJ;
+  p.dparts = 1;
+  const int clusters = sm_count() / 2;
+  int nseg = nseg_hint;
+  if (nseg <= 0) {
+    const int max_seg = p.y_tiles / 4 > 1 ? p.y_tiles / 4 : 1;
+    double best = 1e30;
+    nseg = 1;
+    for (int s = 1; s <= max_seg && s <= 64; ++s) {
+      const long long it = (long long)p.x_tiles * s;
+      const long long waves = (it + clusters - 1) / clusters;
+      const double cost = (double)waves * ((p.y_tiles + s - 1) / s + 3.0);
+      if (cost < best * 0.995) { best = cost; nseg = s; }
+    }
+  }
+  if (nseg > p.y_tiles) nseg = p.y_tiles;
+  p.nseg = nseg;
+  p.scale2 = scale2; p.shift2 = shift2; p.inv_tau = inv_tau; p.bias = bias; p.wneg_c = wneg_c;
+  p.rowscale = rowscale; p.colscale = colscale; p.out_scale = out_scale;
+  p.gnorm = gnorm > 0.f ? gnorm : 1.f;
+  p.hp = 0;
+  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f;
+  p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
+  CUtensorMap tmX, tmYs, tmYo;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, Kp, ldx, BW3_XROWS))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmYs, Y, Ny, Kp, ldy, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmYo, Y, Ny, Kp, ldy, BW3_NJ))) return rc;
+  const int items = p.x_tiles * p.nseg;
+  const int grid = 2 * (items < clusters ? items : clusters);
+  if (mode == BW_CLIP) return launch_bw3<BW_CLIP>(tmX, tmYs, tmYo, p, grid, stream);
+  if (mode == BW_GATED) return launch_bw3<BW_GATED>(tmX, tmYs, tmYo, p, grid, stream);
+  return launch_bw3<BW_SIGLIP>(tmX, tmYs, tmYo, p, grid, stream);
+}
+
+}  // namespace b2host
