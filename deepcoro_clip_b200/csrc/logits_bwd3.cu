@@ -27,20 +27,30 @@
 
 namespace b2 {
 
-constexpr int BW3_NJ = 128;                 // Y rows per step
 constexpr int BW3_XROWS = 64;               // X rows per CTA
 constexpr int BW3_XCHUNK = BW3_XROWS * BW_BK * 2;     // 8 KB: [64 rows x 64 bf16]
-constexpr int BW3_MAXK = 12;                // Kp <= 768
 constexpr int BW3_SLOTS = 6;
 constexpr int BW3_SLOT = 16384;
-constexpr int BW3_GBUF = (BW3_NJ / 64) * BW3_XCHUNK;  // 16 KB: [64 rows x 128 j] bf16
-constexpr int BW3_G_OFF = BW3_MAXK * BW3_XCHUNK;      // 96 KB
-constexpr int BW3_RING_OFF = BW3_G_OFF + 2 * BW3_GBUF;
-constexpr int BW3_BAR_OFF = BW3_RING_OFF + BW3_SLOTS * BW3_SLOT;
-constexpr int BW3_COL_OFF = BW3_BAR_OFF + 256;
-constexpr int BW3_SMEM = BW3_COL_OFF + 8 * 32 * 4 + 1024;
-static_assert(BW3_SMEM <= 232448, "shared memory budget");
-constexpr int BW3_SCOL = 384;               // TMEM: [0, Dp/2) accumulator | [384, 448) S 0 | [448, 512) S 1
+
+// kNJ = Y rows per step. 128: Kp <= 768 (X panel 96 KB, two [64 x 128] S buffers in 128 TMEM columns next to a 384-column
+// accumulator). 256: Kp <= 512 only (X panel 64 KB, two [64 x 256] S buffers in 256 columns next to a 256-column
+// accumulator): the S product re-reads its A operand (the X panel) half as often per logit, which matters because this
+// kernel is bound by the 128 B/cycle/SM shared-memory port (tensor-core operand reads + TMA writes + G stores).
+template <int kNJ>
+struct Bw3Cfg {
+  static constexpr int kMaxK = kNJ == 128 ? 12 : 8;                   // resident X chunks
+  static constexpr int kSRows = kNJ / 2;                              // Y rows per CTA in the S product
+  static constexpr int kSBox = kSRows * 128;                          // bytes of one [kSRows x 64] S box
+  static constexpr int kCps = BW3_SLOT / kSBox;                       // k-chunks per ring slot (2 | 1)
+  static constexpr int kGBuf = (kNJ / 64) * BW3_XCHUNK;               // [64 rows x kNJ] bf16
+  static constexpr int kGOff = kMaxK * BW3_XCHUNK;
+  static constexpr int kRingOff = kGOff + 2 * kGBuf;
+  static constexpr int kBarOff = kRingOff + BW3_SLOTS * BW3_SLOT;
+  static constexpr int kColOff = kBarOff + 256;
+  static constexpr int kSmem = kColOff + 8 * 32 * 4 + 1024;
+  static constexpr int kSCol = kNJ == 128 ? 384 : 256;                // TMEM: accumulator | S 0 | S 1
+  static_assert(kSmem <= 232448, "shared memory budget");
+};
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -105,16 +115,17 @@ __device__ __forceinline__ void bw3_g32(const BwParams& p, const BwThread& th, c
   }
 }
 
-template <int kMode>
+template <int kMode, int kNJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BW_THREADS, 1)
 bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmYs,
            const __grid_constant__ CUtensorMap tmYo, BwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using C = Bw3Cfg<kNJ>;
   uint8_t* xs = smem;
-  uint8_t* gbuf = smem + BW3_G_OFF;
-  uint8_t* ring = smem + BW3_RING_OFF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BW3_BAR_OFF);
+  uint8_t* gbuf = smem + C::kGOff;
+  uint8_t* ring = smem + C::kRingOff;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
   uint64_t* full_bar = bars;                       // [6]  leader only: TMA (both CTAs) -> MMA
   uint64_t* empty_bar = bars + BW3_SLOTS;          // [6]  both: MMA (multicast commit) -> TMA
   uint64_t* sfull_bar = bars + 2 * BW3_SLOTS;      // [2]  both: S tile ready (multicast commit)
@@ -124,7 +135,7 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   uint64_t* xfull_bar = accempty_bar + 1;          // [1]  leader only: both X panels landed
   uint64_t* xempty_bar = xfull_bar + 1;            // [1]  both: X panels free (multicast commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty_bar + 1);
-  float* col_s = reinterpret_cast<float*>(smem + BW3_COL_OFF);   // [8 epilogue warps][32]: warp-private colscale stage
+  float* col_s = reinterpret_cast<float*>(smem + C::kColOff);   // [8 epilogue warps][32]: warp-private colscale stage
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -198,25 +209,27 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           tma_load_2d_pair(xs + kc * BW3_XCHUNK, &tmX, xfull_bar, kc * BW_BK, xt * BW_BM + BW3_XROWS * (int)rank);
         auto load_s = [&](int t) {
           const int j = j0 + t;
-          for (int kp = 0; kp < kchunks / 2; ++kp) {
+          for (int kp = 0; kp < kchunks / C::kCps; ++kp) {
             mbar_wait(&empty_bar[slot], phase ^ 1);
             uint8_t* sl = ring + slot * BW3_SLOT;
             if (leader) mbar_expect_tx(&full_bar[slot], 2 * BW3_SLOT);
-            for (int h = 0; h < 2; ++h)
-              tma_load_2d_pair(sl + h * 8192, &tmYs, &full_bar[slot], (2 * kp + h) * BW_BK, j * BW3_NJ + 64 * (int)rank);
+            for (int h = 0; h < C::kCps; ++h)
+              tma_load_2d_pair(sl + h * C::kSBox, &tmYs, &full_bar[slot], (C::kCps * kp + h) * BW_BK,
+                               j * kNJ + C::kSRows * (int)rank);
             if (++slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
           }
         };
         auto load_out = [&](int t) {
           const int j = j0 + t;
           for (int n = 0; n < nparts; ++n)
-            for (int h = 0; h < 2; ++h) {
-              mbar_wait(&empty_bar[slot], phase ^ 1);
-              if (leader) mbar_expect_tx(&full_bar[slot], 2 * BW3_SLOT);
-              tma_load_2d_pair(ring + slot * BW3_SLOT, &tmYo, &full_bar[slot],
-                               p.hi_off + (4 * n + 2 * (int)rank + h) * BW_BK, j * BW3_NJ);
-              if (++slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
-            }
+            for (int jh = 0; jh < kNJ / 128; ++jh)
+              for (int h = 0; h < 2; ++h) {
+                mbar_wait(&empty_bar[slot], phase ^ 1);
+                if (leader) mbar_expect_tx(&full_bar[slot], 2 * BW3_SLOT);
+                tma_load_2d_pair(ring + slot * BW3_SLOT, &tmYo, &full_bar[slot],
+                                 p.hi_off + (4 * n + 2 * (int)rank + h) * BW_BK, j * kNJ + jh * 128);
+                if (++slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
+              }
         };
         load_s(0);
         for (int t = 0; t < nj; ++t) {
@@ -228,7 +241,7 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, BW3_NJ, 0, 0);     // A, B K-major; 64 rows of A and B per CTA
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, kNJ, 0, 0);        // A, B K-major; 64 rows of A, kNJ/2 of B per CTA
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 256, 0, 1);        // A = G (K-major), B MN-major, 128 columns / CTA
       int slot = 0;
       uint32_t phase = 0, xphase = 0;
@@ -243,14 +256,15 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         xphase ^= 1;
         tc_fence_after();
         auto mma_s = [&](uint32_t tc) {
-          const uint32_t d_tmem = tmem_base + BW3_SCOL + (tc & 1) * (BW3_NJ / 2);
-          for (int kp = 0; kp < kchunks / 2; ++kp) {
+          const uint32_t d_tmem = tmem_base + C::kSCol + (tc & 1) * (kNJ / 2);
+          for (int kp = 0; kp < kchunks / C::kCps; ++kp) {
             mbar_wait(&full_bar[slot], phase);
             tc_fence_after();
             const uint32_t sl = smem_u32(ring + slot * BW3_SLOT);
-            for (int h = 0; h < 2; ++h) {
-              const uint64_t bdesc = make_smem_desc_sw128(sl + h * 8192, 1024);
-              const uint64_t adesc = make_smem_desc_sw128(xs_addr + (2 * kp + h) * BW3_XCHUNK, 1024);
+#pragma unroll
+            for (int h = 0; h < C::kCps; ++h) {
+              const uint64_t bdesc = make_smem_desc_sw128(sl + h * C::kSBox, 1024);
+              const uint64_t adesc = make_smem_desc_sw128(xs_addr + (C::kCps * kp + h) * BW3_XCHUNK, 1024);
 #pragma unroll
               for (int k = 0; k < BW_BK / 16; ++k)
                 mma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_s, (kp | h | k) != 0);
@@ -261,27 +275,28 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           tc_commit_pair(&sfull_bar[tc & 1], 3);
         };
         auto mma_out = [&](uint32_t tc, bool first) {
-          const uint32_t ga = g_addr + (tc & 1) * BW3_GBUF;
-          for (int n = 0; n < nparts; ++n) {
-            // two consecutive ring slots = the two [128 j x 64] boxes of this CTA's 128 output columns (never wraps:
-            // every step uses an even number of slots and BW3_SLOTS is even)
-            mbar_wait(&full_bar[slot], phase);
-            mbar_wait(&full_bar[slot + 1], phase);
-            tc_fence_after();
-            const uint32_t sy = smem_u32(ring + slot * BW3_SLOT);
-            const uint32_t d_tmem = tmem_base + n * 128;
-            const uint64_t bdesc0 = make_smem_desc_sw128(sy, BW3_SLOT);
+          const uint32_t ga = g_addr + (tc & 1) * C::kGBuf;
+          for (int n = 0; n < nparts; ++n)
+            for (int jh = 0; jh < kNJ / 128; ++jh) {
+              // two consecutive ring slots = the two [128 j x 64] boxes of this CTA's 128 output columns (never wraps:
+              // every step uses an even number of slots and BW3_SLOTS is even)
+              mbar_wait(&full_bar[slot], phase);
+              mbar_wait(&full_bar[slot + 1], phase);
+              tc_fence_after();
+              const uint32_t sy = smem_u32(ring + slot * BW3_SLOT);
+              const uint32_t d_tmem = tmem_base + n * 128;
+              const uint64_t bdesc0 = make_smem_desc_sw128(sy, BW3_SLOT);
 #pragma unroll
-            for (int ks = 0; ks < BW3_NJ / 16; ++ks) {
-              const uint64_t bdesc = bdesc0 + uint64_t(ks * (2048 >> 4));
-              const uint64_t adesc = make_smem_desc_sw128(ga + (ks >> 2) * BW3_XCHUNK, 1024) + 2 * (ks & 3);
-              mma_ss_pair(d_tmem, adesc, bdesc, idesc_o, !(first && ks == 0));
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t bdesc = bdesc0 + uint64_t(ks * (2048 >> 4));
+                const uint64_t adesc = make_smem_desc_sw128(ga + (2 * jh + (ks >> 2)) * BW3_XCHUNK, 1024) + 2 * (ks & 3);
+                mma_ss_pair(d_tmem, adesc, bdesc, idesc_o, !(first && jh == 0 && ks == 0));
+              }
+              tc_commit_pair(&empty_bar[slot], 3);
+              tc_commit_pair(&empty_bar[slot + 1], 3);
+              slot += 2;
+              if (slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
             }
-            tc_commit_pair(&empty_bar[slot], 3);
-            tc_commit_pair(&empty_bar[slot + 1], 3);
-            slot += 2;
-            if (slot == BW3_SLOTS) { slot = 0; phase ^= 1; }
-          }
         };
         mma_s(tile_ctr);
         if (nj == 1) tc_commit_pair(xempty_bar, 3);
@@ -308,16 +323,18 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   } else if (warp >= 4) {
     // ===================== epilogue warps 4..11 (both CTAs, own TMEM / own shared memory) =====================
     const int q = warp & 3;               // TMEM lane quarter: rows 32 (q & 1) .., tile columns 64 (q >> 1) ..
-    const int wg = (warp - 4) >> 2;       // 32-column half of the quarter's 64 TMEM columns
+    const int wg = (warp - 4) >> 2;       // half of the quarter's kNJ/2 TMEM columns
     uint32_t tile_ctr = 0, acc_ctr = 0;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const int rloc = (q & 1) * 32 + lane;                 // row inside this CTA's 64
-    const int ctile = (q >> 1) * 64 + wg * 32;            // first tile column of this thread
+    constexpr int NC = kNJ / 128;                         // 32-column chunks per thread and tile
+    const int ctile = (q >> 1) * (kNJ / 2) + wg * (kNJ / 4);   // first tile column of this thread
     const uint32_t gready_remote0 = mapa_cluster(smem_u32(&gready_bar[0]), 0);
     const uint32_t gready_remote1 = mapa_cluster(smem_u32(&gready_bar[1]), 0);
     const uint32_t accempty_remote = mapa_cluster(smem_u32(accempty_bar), 0);
-    // this thread's 64 bytes of the K-major SWIZZLE_128B G row: chunk (q >> 1), 16-byte units wg*4 .. wg*4+3
-    const uint32_t grow_addr = smem_u32(gbuf) + (q >> 1) * BW3_XCHUNK + rloc * 128;
+    // this thread's bytes of the K-major SWIZZLE_128B G row rloc: tile column cc lives in chunk cc >> 6, 16-byte unit
+    // (cc & 63) >> 3 (XOR-swizzled with the row)
+    const uint32_t grow_addr = smem_u32(gbuf) + rloc * 128;
     BwThread th;
     th.wg = wg;
     th.ydn = p.ydiag * p.gnorm;
@@ -337,48 +354,59 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       double dtacc = 0.0, dlacc = 0.0, dbacc = 0.0;
       // column scales: lane e of every warp fetches the scale of the warp's e-th column one tile ahead (registers),
       // stages it in a warp-private 32-float slot (__syncwarp only, no CTA barrier) and reads it back broadcast
-      auto load_cs = [&](int jt) -> float {
-        const int col = jt * BW3_NJ + ctile + lane;
+      auto load_cs = [&](int jt, int c) -> float {
+        const int col = jt * kNJ + ctile + 32 * c + lane;
         return col < p.Ny ? __ldg(p.colscale + col) * p.gnorm : 0.f;
       };
-      float cs_next = 0.f;
-      if (!BwIsSiglip<kMode>::value) cs_next = load_cs(j0);
+      float cs_next[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) cs_next[c] = BwIsSiglip<kMode>::value ? 0.f : load_cs(j0, c);
       for (int t = 0; t < nj; ++t, ++tile_ctr) {
         const int j = j0 + t;
         float tacc = 0.f, lacc = 0.f, bacc = 0.f;
         const int buf = tile_ctr & 1;
-        if (!BwIsSiglip<kMode>::value) {
-          __syncwarp();                                   // previous tile's reads of the slot are done
-          col_s[(warp - 4) * 32 + lane] = cs_next;
-          if (t + 1 < nj) cs_next = load_cs(j + 1);
-          __syncwarp();
+        float cs_cur[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          cs_cur[c] = cs_next[c];
+          if (!BwIsSiglip<kMode>::value && t + 1 < nj) cs_next[c] = load_cs(j + 1, c);
         }
         mbar_wait(&sfull_bar[buf], (tile_ctr >> 1) & 1);
         tc_fence_after();
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + lane_off + BW3_SCOL + buf * (BW3_NJ / 2) + wg * 32, acc);
-        tc_wait_ld();
-        const int colg0 = j * BW3_NJ + ctile;
-        const bool full = rows_full && (j * BW3_NJ + BW3_NJ <= p.Ny);
-        // diagonal target column relative to this thread's 32 columns (CLIP / gated only)
-        int dcol = -1;
-        if (!BwIsSiglip<kMode>::value && p.ydiag != 0.f) {
-          const int d = th.row + p.diag_off - colg0;
-          dcol = (d >= 0 && d < 32) ? d : -1;
-        }
-        const int dlo = xt * BW_BM + p.diag_off - j * BW3_NJ;     // does the diagonal cross this pair tile? (uniform)
-        const bool has_diag = !BwIsSiglip<kMode>::value && p.ydiag != 0.f && dlo > -BW_BM && dlo < BW3_NJ;
-        uint32_t packed[16];
+        const bool full = rows_full && (j * kNJ + kNJ <= p.Ny);
+        const int dlo = xt * BW_BM + p.diag_off - j * kNJ;        // does the diagonal cross this pair tile? (uniform)
+        const bool has_diag = !BwIsSiglip<kMode>::value && p.ydiag != 0.f && dlo > -BW_BM && dlo < kNJ;
         const uint32_t cs_addr = smem_u32(col_s) + (warp - 4) * 32 * 4;
-        if (full && !has_diag)
-          bw3_g32<kMode, true>(p, th, acc, cs_addr, colg0, -1, tacc, lacc, bacc, packed);
-        else
-          bw3_g32<kMode, false>(p, th, acc, cs_addr, colg0, dcol, tacc, lacc, bacc, packed);
-        const uint32_t ga = grow_addr + buf * BW3_GBUF;
+        const uint32_t ga = grow_addr + buf * C::kGBuf;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          sts128(ga + (uint32_t((wg * 4 + u) ^ (rloc & 7)) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
-                 packed[4 * u + 3]);
+        for (int c = 0; c < NC; ++c) {
+          const int cc = ctile + 32 * c;
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + lane_off + C::kSCol + buf * (kNJ / 2) + wg * (kNJ / 4) + 32 * c, acc);
+          if (!BwIsSiglip<kMode>::value) {
+            __syncwarp();                                 // previous reads of the warp's slot are done
+            col_s[(warp - 4) * 32 + lane] = cs_cur[c];
+            __syncwarp();
+          }
+          tc_wait_ld();
+          const int colg0 = j * kNJ + cc;
+          int dcol = -1;                                  // diagonal target column relative to these 32 columns
+          if (has_diag) {
+            const int d = th.row + p.diag_off - colg0;
+            dcol = (d >= 0 && d < 32) ? d : -1;
+          }
+          uint32_t packed[16];
+          if (full && !has_diag)
+            bw3_g32<kMode, true>(p, th, acc, cs_addr, colg0, -1, tacc, lacc, bacc, packed);
+          else
+            bw3_g32<kMode, false>(p, th, acc, cs_addr, colg0, dcol, tacc, lacc, bacc, packed);
+          const uint32_t gc = ga + (cc >> 6) * BW3_XCHUNK;
+          const int u0 = (cc & 63) >> 3;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            sts128(gc + (uint32_t((u0 + u) ^ (rloc & 7)) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                   packed[4 * u + 3]);
+        }
         // generic-proxy stores -> visible to the tensor core's (async proxy) reads of THIS CTA's shared memory. The
         // .shared::cta form is enough (each SM's tensor core reads its own CTA's G half) and, unlike the unqualified
         // fence.proxy.async / mbarrier.arrive.release.cluster pair, does not compile to MEMBAR.ALL.GPU + ERRBAR
@@ -464,16 +492,17 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 namespace b2host {
 using namespace b2;
 
-template <int kMode>
+template <int kMode, int kNJ>
 static int launch_bw3(const CUtensorMap& tmX, const CUtensorMap& tmYs, const CUtensorMap& tmYo, const BwParams& p,
                       int grid, cudaStream_t stream) {
   static bool attr_done = false;
+  constexpr int smem = Bw3Cfg<kNJ>::kSmem;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(bw3_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW3_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(bw3_kernel<kMode, kNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B2_ECUDA;
     attr_done = true;
   }
-  bw3_kernel<kMode><<<grid, BW_THREADS, BW3_SMEM, stream>>>(tmX, tmYs, tmYo, p);
+  bw3_kernel<kMode, kNJ><<<grid, BW_THREADS, smem, stream>>>(tmX, tmYs, tmYo, p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
@@ -484,24 +513,28 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
                       const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
                       const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
                       int nseg_hint, cudaStream_t stream) {
-  if (hp || hi_off != 0 || Kp != Dp || Dp % 256 || Dp > BW3_MAXK * BW_BK || sm_count() < 2) return B2_ENOSYS;
+  if (hp || hi_off != 0 || Kp != Dp || Dp % 256 || Dp > 768 || sm_count() < 2) return B2_ENOSYS;
+  // 256 Y rows per step whenever the X panel and the S buffers allow it (Kp <= 512); B200CLIP_BWD3_NJ=128 forces 128
+  static const bool nj256_ok = [] { const char* e = getenv("B200CLIP_BWD3_NJ"); return !(e && e[0] == '1' && e[1] == '2'); }();
+  const int NJ = (Kp <= 512 && nj256_ok) ? 256 : 128;
   if (mode != BW_CLIP && mode != BW_GATED && mode != BW_SIGLIP) return B2_ENOSYS;
   BwParams p;
   p.Nx = Nx; p.Ny = Ny; p.Kp = Kp; p.Dp = Dp; p.D = D; p.hi_off = 0; p.ydiag = ydiag; p.diag_off = diag_off;
   p.diag_corr = diag_corr;
   p.x_tiles = (Nx + BW_BM - 1) / BW_BM;              // 128-row X tiles, one per cluster item
-  p.y_tiles = (Ny + BW3_NJ - 1) / BW3_NJ;
+  p.y_tiles = (Ny + NJ - 1) / NJ;
   p.dparts = 1;
   const int clusters = sm_count() / 2;
   int nseg = nseg_hint;
   if (nseg <= 0) {
-    const int max_seg = p.y_tiles / 4 > 1 ? p.y_tiles / 4 : 1;
+    const int min_tiles = NJ == 128 ? 4 : 2;
+    const int max_seg = p.y_tiles / min_tiles > 1 ? p.y_tiles / min_tiles : 1;
     double best = 1e30;
     nseg = 1;
     for (int s = 1; s <= max_seg && s <= 64; ++s) {
       const long long it = (long long)p.x_tiles * s;
       const long long waves = (it + clusters - 1) / clusters;
-      const double cost = (double)waves * ((p.y_tiles + s - 1) / s + 3.0);
+      const double cost = (double)waves * ((p.y_tiles + s - 1) / s + (NJ == 128 ? 3.0 : 1.5));
       if (cost < best * 0.995) { best = cost; nseg = s; }
     }
   }
@@ -516,13 +549,16 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
   CUtensorMap tmX, tmYs, tmYo;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, Kp, ldx, BW3_XROWS))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmYs, Y, Ny, Kp, ldy, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmYo, Y, Ny, Kp, ldy, BW3_NJ))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmYs, Y, Ny, Kp, ldy, NJ / 2))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmYo, Y, Ny, Kp, ldy, 128))) return rc;
   const int items = p.x_tiles * p.nseg;
   const int grid = 2 * (items < clusters ? items : clusters);
-  if (mode == BW_CLIP) return launch_bw3<BW_CLIP>(tmX, tmYs, tmYo, p, grid, stream);
-  if (mode == BW_GATED) return launch_bw3<BW_GATED>(tmX, tmYs, tmYo, p, grid, stream);
-  return launch_bw3<BW_SIGLIP>(tmX, tmYs, tmYo, p, grid, stream);
+#define LAUNCH3(M) (NJ == 256 ? launch_bw3<M, 256>(tmX, tmYs, tmYo, p, grid, stream) \
+                              : launch_bw3<M, 128>(tmX, tmYs, tmYo, p, grid, stream))
+  if (mode == BW_CLIP) return LAUNCH3(BW_CLIP);
+  if (mode == BW_GATED) return LAUNCH3(BW_GATED);
+  return LAUNCH3(BW_SIGLIP);
+#undef LAUNCH3
 }
 
 }  // namespace b2host
