@@ -289,20 +289,30 @@ def main():
         kms = e0.elapsed_time(e1) / reps
         alg = 2.0 * B * N * D                      # algorithmic FLOPs of one launch (one gradient GEMM; recompute not counted)
         achieved = alg / (kms * 1e-3) / 1e12
+        bw3 = Kp == D and Kp % 256 == 0 and Kp <= 768 and os.environ.get("B200CLIP_BWD3", "1") != "0"
         pair = Kp <= 512 and Kp % 128 == 0 and os.environ.get("B200CLIP_BWD_PAIR", "1") != "0"
+        if bw3:
+            kname = f"bw3_kernel<CLIP, {256 if Kp <= 512 else 128}> (logits_bwd3.cu: 64-row CTA pairs, cta_group::2 M=128, whole output width in TMEM)"
+            executed = 2.0 * achieved                    # S once + the output product
+            prof = ROOT / "profiles" / "r01e_bw3_kernel_ncu_full_summary.json"
+        elif pair:
+            kname = "bw2_kernel<CLIP> (logits_bwd2.cu: 128-row CTA pairs, cta_group::2)"
+            executed = (1 + (Kp + 255) // 256) * achieved
+            prof = ROOT / "profiles" / "r01c_bw2_kernel_ncu_full_summary.json"
+        else:
+            kname = "bw_kernel<CLIP> (logits_bwd.cu: single CTA)"
+            executed = (1 + (Kp + 255) // 256) * achieved
+            prof = None
         traffic = None
-        prof = ROOT / "profiles" / "r01c_bw2_kernel_ncu_full_summary.json"
-        if pair and world == 1 and args.workload == "clip32k" and prof.exists():
+        if prof is not None and world == 1 and args.workload == "clip32k" and prof.exists():
             traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
-        dparts = (Kp + 255) // 256
-        roof = {"bound": "tensor", "kernel": ("bw2_kernel<CLIP> (logits_bwd, CTA pairs, cta_group::2)" if pair else
-                                              "bw_kernel<CLIP> (logits_bwd, single CTA)"),
-                "achieved": achieved, "peak": bf16_burst,
+        roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": bf16_burst,
                 "unit": "TFLOP/s", "frac": achieved / bf16_burst, "traffic": traffic, "peak_source": src,
-                "ms_per_launch": kms, "executed_tflops": (1 + dparts) * achieved,
-                "note": "algorithmic = 2*B*N*D per launch (SURVEY 8d: the S recompute of each 256-column half of D is "
-                        "executed but not counted); traffic = dram read+write bytes per launch from the committed "
-                        "ncu --set full capture (profiles/r01c_*)"}
+                "ms_per_launch": kms, "executed_tflops": executed,
+                "note": "algorithmic = 2*B*N*D FLOP per launch (SURVEY 8d: one gradient GEMM; the S recompute is executed "
+                        "but not counted); achieved = algorithmic / CUDA-event time of the kernel alone on its stream; "
+                        "traffic = dram read+write bytes per launch from the committed ncu --set full capture "
+                        f"({prof.name if prof is not None else 'none'})"}
         step_alg = 6.0 * B * N * D
         roof["step_algorithmic_tflops"] = step_alg / (ms_per_step * 1e-3) / 1e12
         roof["step_frac_of_peak"] = roof["step_algorithmic_tflops"] / bf16_sust
