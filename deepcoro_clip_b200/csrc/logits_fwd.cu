@@ -190,10 +190,11 @@ static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int l
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
-// CTA-pair engine (tile_engine2.cuh): Kp <= 512 only. B200CLIP_TE_PAIR=0 keeps the single-CTA engine (A/B runs).
+// CTA-pair engine (tile_engine2.cuh): Kp <= 1024 (first 512 columns of the outer operand resident).
+// B200CLIP_TE_PAIR=0 keeps the single-CTA engine (A/B runs).
 bool te_pair_enabled(int Kp) {
   static const bool on = [] { const char* e = getenv("B200CLIP_TE_PAIR"); return !(e && e[0] == '0'); }();
-  return on && Kp <= 512 && sm_count() >= 2;
+  return on && Kp <= 1024 && sm_count() >= 2;
 }
 
 template <class Epi, bool kOuterIsB>

@@ -1,5 +1,6 @@
-// CTA-pair version of the S = A * B^T tile engine (tile_engine.cuh) for Kp <= 512: tcgen05 cta_group::2 with ONE
-// OPERAND RESIDENT in shared memory.
+// CTA-pair version of the S = A * B^T tile engine (tile_engine.cuh): tcgen05 cta_group::2 with ONE OPERAND RESIDENT in
+// shared memory (all of it for Kp <= 512; for 512 < Kp <= 1024 its first 512 columns, the tail k-chunks of the resident
+// operand are re-streamed per tile next to the other operand: 42 B/cycle per SM at Kp = 768, still under the ingest port).
 //
 // Why: a single SM ingests at most 61.5 B/cycle through TMA (tools/ubench). The single-CTA engine streams a 16 KB A
 // chunk and a 32 KB B chunk per 64-wide k-chunk for 512 tensor cycles = 94 B/cycle: ingest-bound (~65 % tensor pipe).
@@ -75,6 +76,7 @@ te2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int kchunks = g.Kp / TE_BK;
+  const int rch = kchunks < 8 ? kchunks : 8;       // resident k-chunks of the outer operand (the rest is streamed)
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (warp == 0 && elect_one()) {
@@ -129,8 +131,8 @@ te2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             cur_seg = sg;
             mbar_wait(rempty_bar, rphase ^ 1);
             rphase ^= 1;
-            if (leader) mbar_expect_tx(rfull_bar, 2 * kchunks * 16384);
-            for (int kc = 0; kc < kchunks; ++kc)
+            if (leader) mbar_expect_tx(rfull_bar, 2 * rch * 16384);
+            for (int kc = 0; kc < rch; ++kc)
               tma_load_2d_pair(res + kc * 16384, tmRes, rfull_bar, kc * TE_BK, res_row(outer));
           }
           for (int kc = 0; kc < kchunks; ++kc) {
@@ -138,6 +140,12 @@ te2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (leader) mbar_expect_tx(&full_bar[slot], 2 * TE2_SLOT);
             tma_load_2d_pair(ring + slot * TE2_SLOT, tmStr, &full_bar[slot], kc * TE_BK, str_row(inner));
             if (++slot == TE2_SLOTS) { slot = 0; phase ^= 1; }
+            if (kc >= rch) {             // tail chunk of the outer operand: not resident, streamed for every tile
+              mbar_wait(&empty_bar[slot], phase ^ 1);
+              if (leader) mbar_expect_tx(&full_bar[slot], 2 * TE2_SLOT);
+              tma_load_2d_pair(ring + slot * TE2_SLOT, tmRes, &full_bar[slot], kc * TE_BK, res_row(outer));
+              if (++slot == TE2_SLOTS) { slot = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -171,13 +179,23 @@ te2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             mbar_wait(&full_bar[slot], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(ring + slot * TE2_SLOT);
-            const uint32_t rs = res_addr + kc * 16384;
+            uint32_t rs = res_addr + kc * 16384;
+            const int slot0 = slot;
+            if (++slot == TE2_SLOTS) { slot = 0; phase ^= 1; }
+            int slot1 = -1;
+            if (kc >= rch) {
+              mbar_wait(&full_bar[slot], phase);
+              tc_fence_after();
+              rs = smem_u32(ring + slot * TE2_SLOT);
+              slot1 = slot;
+              if (++slot == TE2_SLOTS) { slot = 0; phase ^= 1; }
+            }
             const uint64_t adesc = make_smem_desc_sw128(kOuterIsB ? st : rs, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(kOuterIsB ? rs : st, 1024);
 #pragma unroll
             for (int k = 0; k < TE_BK / 16; ++k) mma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
-            tc_commit_pair(&empty_bar[slot], 3);
-            if (++slot == TE2_SLOTS) { slot = 0; phase ^= 1; }
+            tc_commit_pair(&empty_bar[slot0], 3);
+            if (slot1 >= 0) tc_commit_pair(&empty_bar[slot1], 3);
           }
           tc_commit_pair(&tfull_bar[as], 3);
           ++lt;
