@@ -7,6 +7,7 @@ from .install import install, loss_table
 from .loss import (CLIPLoss, ContrastiveLoss, ContrastiveLossDDP, InfoNCELoss, SigLIP2BCELoss, SigLIP2BCELossDDP,
                    SigLIP2MultiPositiveBCELoss, SigLIPLoss, SiglipLoss, SiglipLossDDP, SiglipPairwiseFeatureLoss,
                    clip_loss)
+from . import retrieval_metrics
 from .retrieval_metrics_streaming import (compute_metrics_streaming, compute_recall_at_k_streaming, streaming_topk)
 from .rope_3d import Rope3D, apply_rope_qk
 from .video_aggregator import EnhancedVideoAggregator, query_pool

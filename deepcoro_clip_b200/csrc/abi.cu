@@ -176,6 +176,21 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                     negative_weight, c, gnorm, hp, use_pos_weights, auto_balance, dV, lddv, dT, lddt, acc, S(stream));
 }
 
+int b200clip_dense_gt_ranks(const void* sim, int dtype, int64_t ld, int n_rows, int n_cols, const int32_t* gt, int G,
+                            int sanitize, int32_t* ranks, void* stream) {
+  if (!sim || !gt || !ranks) return B2_EINVAL;
+  return dense_gt_ranks(sim, dtype, (long long)ld, n_rows, n_cols, gt, G, sanitize, ranks, S(stream));
+}
+
+int b200clip_dense_rank_metrics(const int32_t* ranks, const int32_t* gsize, int n_rows, int G, int n_cols,
+                                const int32_t* recall_k, int n_recall_k, const int32_t* ndcg_k, int n_ndcg_k,
+                                int32_t* best, double* rr, double* ap, uint8_t* hit, double* ndcg, void* stream) {
+  if (!ranks || !gsize || !best || !rr || !ap) return B2_EINVAL;
+  if ((n_recall_k > 0 && (!recall_k || !hit)) || (n_ndcg_k > 0 && (!ndcg_k || !ndcg))) return B2_EINVAL;
+  return dense_rank_metrics(ranks, gsize, n_rows, G, n_cols, recall_k, n_recall_k, ndcg_k, n_ndcg_k, best, rr, ap, hit,
+                            ndcg, S(stream));
+}
+
 int b200clip_retrieval_segments(int n_video, int n_text) { return retrieval_segments(n_video, n_text); }
 
 int b200clip_retrieval_sweep(const void* video, const void* text, int n_video, int n_text, int Kp, int ldv, int ldt,

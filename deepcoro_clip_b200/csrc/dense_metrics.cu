@@ -1,0 +1,151 @@
+// Dense multi-label retrieval metrics (utils/retrieval_metrics.py:65-324): recall@k with ground-truth
+// SETS, MRR, MAP, NDCG@k and median rank over a materialised similarity matrix [N, M].
+//
+// The reference argsorts every row (O(M log M)) and then walks Python loops over rows and ground-truth items. Every one
+// of its metrics is a function of the RANKS of the row's ground-truth items only, and a rank needs no sort:
+//     rank(i, g) = 1 + #{j : s_ij > s_ig} + #{j < g : s_ij == s_ig}        (score descending, lowest index first)
+// so one streaming pass over the matrix (HBM-bound, each element read exactly once, up to 16 thresholds per row kept in
+// registers) replaces the argsort, and a per-row kernel turns the <= 16 ranks into the per-row metric terms.
+#include "common.cuh"
+#include "host_api.h"
+
+namespace b2 {
+
+template <typename T> __device__ __forceinline__ float dm_val(T v);
+template <> __device__ __forceinline__ float dm_val<float>(float v) { return v; }
+template <> __device__ __forceinline__ float dm_val<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float dm_val<__half>(__half v) { return __half2float(v); }
+
+// torch.nan_to_num(x, nan=0, posinf=1e4, neginf=-1e4) (compute_mrr, retrieval_metrics.py:118-120)
+__device__ __forceinline__ float dm_sanitize(float v, int on) {
+  if (!on) return v;
+  if (v != v) return 0.f;
+  if (v == INFINITY) return 1e4f;
+  if (v == -INFINITY) return -1e4f;
+  return v;
+}
+
+// One CTA per row. gt [N, G] int32 (entries < 0 or >= M: absent). ranks [N, G] int32: 1-based rank, 0 = absent.
+template <typename T, int GMAX>
+__global__ void __launch_bounds__(256)
+dense_gt_ranks_kernel(const T* __restrict__ sim, long long ld, int N, int M, const int* __restrict__ gt, int G,
+                      int sanitize, int* __restrict__ ranks) {
+  const int row = blockIdx.x;
+  if (row >= N) return;
+  const T* sr = sim + (size_t)row * ld;
+  float thr[GMAX];
+  int gidx[GMAX];
+#pragma unroll
+  for (int g = 0; g < GMAX; ++g) {
+    int c = g < G ? gt[(size_t)row * G + g] : -1;
+    if (c >= M) c = -1;
+    gidx[g] = c;
+    thr[g] = c >= 0 ? dm_sanitize(dm_val<T>(sr[c]), sanitize) : INFINITY;     // nothing beats +inf: count stays 0
+  }
+  int cnt[GMAX];
+#pragma unroll
+  for (int g = 0; g < GMAX; ++g) cnt[g] = 0;
+#pragma unroll 4
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const float s = dm_sanitize(dm_val<T>(sr[j]), sanitize);
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g) cnt[g] += (s > thr[g] || (s == thr[g] && j < gidx[g])) ? 1 : 0;
+  }
+  __shared__ int sh[8][GMAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int g = 0; g < GMAX; ++g) {
+    int v = cnt[g];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][g] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    int v = 0;
+    for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
+    int c = gt[(size_t)row * G + threadIdx.x];
+    ranks[(size_t)row * G + threadIdx.x] = (c >= 0 && c < M) ? v + 1 : 0;
+  }
+}
+
+// Per-row metric terms from the ranks (one thread per row), arithmetic in double in the reference's operation order:
+//   best[row]  = smallest rank, or M when the row has no ground truth in range (compute_median_rank :266-281)
+//   rr[row]    = 1 / best or 0                                                  (compute_mrr :127-146)
+//   ap[row]    = (1/H) sum_h h / r_(h), ranks ascending, H found items          (compute_map :305-322)
+//   hit[row,k] = best <= min(k, M)                                              (compute_recall_at_k :77-99)
+//   ndcg[row,k]= sum_{r <= k_eff} 1/log2(r + 1) / sum_{r < min(|set|, k_eff)} 1/log2(r + 2)   (compute_ndcg_at_k :214-242)
+// gsize [N]: size of the row's ground-truth set (items >= M still count towards the ideal DCG, as in the reference).
+__global__ void __launch_bounds__(256)
+dense_rank_metrics_kernel(const int* __restrict__ ranks, const int* __restrict__ gsize, int N, int G, int M,
+                          const int* __restrict__ recall_k, int nrk, const int* __restrict__ ndcg_k, int nnk,
+                          int* __restrict__ best, double* __restrict__ rr, double* __restrict__ ap,
+                          unsigned char* __restrict__ hit, double* __restrict__ ndcg) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  int r[16];
+  int H = 0;
+  for (int g = 0; g < G && g < 16; ++g) {
+    const int v = ranks[(size_t)row * G + g];
+    if (v > 0) {
+      int p = H++;
+      while (p > 0 && r[p - 1] > v) { r[p] = r[p - 1]; --p; }     // insertion sort, ascending
+      r[p] = v;
+    }
+  }
+  const int b = H > 0 ? r[0] : 0;
+  best[row] = b > 0 ? b : M;
+  rr[row] = b > 0 ? 1.0 / (double)b : 0.0;
+  double psum = 0.0;
+  for (int h = 0; h < H; ++h) psum += (double)(h + 1) / (double)r[h];
+  ap[row] = H > 0 ? psum / (double)H : 0.0;
+  for (int k = 0; k < nrk; ++k) {
+    const int ku = recall_k[k] < M ? recall_k[k] : M;
+    hit[(size_t)row * nrk + k] = (b > 0 && b <= ku) ? 1 : 0;
+  }
+  const int gs = gsize[row];
+  for (int k = 0; k < nnk; ++k) {
+    const int ke = ndcg_k[k] < M ? ndcg_k[k] : M;
+    double dcg = 0.0;
+    for (int h = 0; h < H; ++h)
+      if (r[h] <= ke) dcg += 1.0 / log2((double)(r[h] + 1));
+    const int ideal = gs < ke ? gs : ke;
+    double idcg = 0.0;
+    for (int q = 0; q < ideal; ++q) idcg += 1.0 / log2((double)(q + 2));
+    ndcg[(size_t)row * nnk + k] = (gs > 0 && ideal > 0 && idcg > 0.0) ? dcg / idcg : 0.0;
+  }
+}
+
+}  // namespace b2
+
+namespace b2host {
+using namespace b2;
+
+template <typename T>
+static int launch_ranks(const void* sim, long long ld, int N, int M, const int* gt, int G, int sanitize, int* ranks,
+                        cudaStream_t s) {
+  const T* p = reinterpret_cast<const T*>(sim);
+  if (G <= 1) dense_gt_ranks_kernel<T, 1><<<N, 256, 0, s>>>(p, ld, N, M, gt, G, sanitize, ranks);
+  else if (G <= 4) dense_gt_ranks_kernel<T, 4><<<N, 256, 0, s>>>(p, ld, N, M, gt, G, sanitize, ranks);
+  else dense_gt_ranks_kernel<T, 16><<<N, 256, 0, s>>>(p, ld, N, M, gt, G, sanitize, ranks);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int dense_gt_ranks(const void* sim, int dtype, long long ld, int N, int M, const int* gt, int G, int sanitize,
+                   int* ranks, cudaStream_t s) {
+  if (N <= 0 || M <= 0 || G <= 0 || G > 16) return B2_EINVAL;
+  if (dtype == 0) return launch_ranks<float>(sim, ld, N, M, gt, G, sanitize, ranks, s);
+  if (dtype == 1) return launch_ranks<__nv_bfloat16>(sim, ld, N, M, gt, G, sanitize, ranks, s);
+  if (dtype == 2) return launch_ranks<__half>(sim, ld, N, M, gt, G, sanitize, ranks, s);
+  return B2_EINVAL;
+}
+
+int dense_rank_metrics(const int* ranks, const int* gsize, int N, int G, int M, const int* recall_k, int nrk,
+                       const int* ndcg_k, int nnk, int* best, double* rr, double* ap, unsigned char* hit, double* ndcg,
+                       cudaStream_t s) {
+  if (N <= 0 || G <= 0 || G > 16 || M <= 0) return B2_EINVAL;
+  dense_rank_metrics_kernel<<<(N + 255) / 256, 256, 0, s>>>(ranks, gsize, N, G, M, recall_k, nrk, ndcg_k, nnk, best, rr,
+                                                           ap, hit, ndcg);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+}  // namespace b2host

@@ -107,6 +107,13 @@ int topk_merge(const float* ps, const int* pi, int rows, int cand, int k, float*
                cudaStream_t s);
 int recall_hits(const int* counts, int rows, const int* kvals, int nk, unsigned long long* hits, cudaStream_t s);
 
+// dense_metrics.cu
+int dense_gt_ranks(const void* sim, int dtype, long long ld, int N, int M, const int* gt, int G, int sanitize,
+                   int* ranks, cudaStream_t s);
+int dense_rank_metrics(const int* ranks, const int* gsize, int N, int G, int M, const int* recall_k, int nrk,
+                       const int* ndcg_k, int nnk, int* best, double* rr, double* ap, unsigned char* hit, double* ndcg,
+                       cudaStream_t s);
+
 // rope3d.cu
 int rope3d_apply(const void* q, long long qsb, long long qsh, long long qsn, void* q_out, const void* k, long long ksb,
                  long long ksh, long long ksn, void* k_out, const void* sin_t, const void* cos_t, int dtype, int B,

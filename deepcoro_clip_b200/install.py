@@ -5,7 +5,7 @@
   * the module-level names ``models.video_encoder.Rope3D`` / ``AttentionPool`` / ``EnhancedVideoAggregator`` that
     ``VideoEncoder.__init__`` instantiates (models/video_encoder.py:13, 115-140, 207-212);
   * the function names ``compute_metrics_streaming`` / ``compute_recall_at_k_streaming`` imported by
-    runners/multitask_runner.py:35.
+    runners/multitask_runner.py:35, and the dense multi-label metrics of utils/retrieval_metrics.py.
 
 Call ``install()`` AFTER ``register_submodules("utils.loss")`` (scripts/main.py:26-30) so that these entries are
 the last ones written."""
@@ -15,7 +15,7 @@ import importlib
 import sys
 from typing import Dict
 
-from . import attention_pool, loss, retrieval_metrics_streaming, rope_3d, video_aggregator
+from . import attention_pool, loss, retrieval_metrics, retrieval_metrics_streaming, rope_3d, video_aggregator
 
 # key -> class, for the two import orders the reference can end up with (SURVEY §8b "registration order hazard")
 _MAIN = {          # scripts/main.py order: utils/loss/contrastive.py registers last
@@ -98,5 +98,22 @@ def install(reference_root: str | None = None, semantics: str = "main", losses: 
                 mod.compute_metrics_streaming = retrieval_metrics_streaming.compute_metrics_streaming
                 if hasattr(mod, "compute_recall_at_k_streaming"):
                     mod.compute_recall_at_k_streaming = retrieval_metrics_streaming.compute_recall_at_k_streaming
+                report["metrics"].append(modname)
+        # dense multi-label metrics (utils/retrieval_metrics.py): rebind the functions on their home module and on
+        # every runner module that imported them by name (runners/multitask_runner.py:26-34, ..._runner_simple.py:19-27)
+        dense = ("compute_recall_at_k", "compute_mrr", "compute_ndcg_at_k", "compute_median_rank", "compute_map",
+                 "compute_similarity_matrix", "compute_embedding_norms", "compute_alignment_score")
+        for modname in ("utils.retrieval_metrics", "runners.multitask_runner", "runners.video_constrative_learning_runner",
+                        "runners.video_constrative_learning_runner_simple"):
+            mod = sys.modules.get(modname)
+            if mod is None and modname == "utils.retrieval_metrics":
+                try:
+                    mod = importlib.import_module(modname)
+                except Exception:
+                    mod = None
+            if mod is not None:
+                for n in dense:
+                    if hasattr(mod, n):
+                        setattr(mod, n, getattr(retrieval_metrics, n))
                 report["metrics"].append(modname)
     return report

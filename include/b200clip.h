@@ -206,6 +206,24 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dense multi-label retrieval metrics over a materialised similarity matrix. Replaces the argsort + Python loops of
+ * compute_recall_at_k / compute_mrr / compute_ndcg_at_k / compute_median_rank / compute_map
+ * (utils/retrieval_metrics.py:65-324): every metric is a function of the ranks of the ground-truth items,
+ *     rank(i, g) = 1 + #{j : s_ij > s_ig} + #{j < g : s_ij == s_ig}     (score descending, lowest index first).
+ *   dense_gt_ranks    : sim [n_rows, n_cols] (dtype code, row stride ld elements) read ONCE; gt [n_rows, G] int32,
+ *                       G <= 16, entries < 0 or >= n_cols absent; ranks [n_rows, G] (0 = absent). sanitize = 1
+ *                       applies nan_to_num(nan=0, posinf=1e4, neginf=-1e4) first (compute_mrr :118-120).
+ *   dense_rank_metrics: per-row terms in double, in the reference's operation order: best (smallest rank, n_cols
+ *                       when none), rr = 1/best | 0, ap, hit [n_rows, n_recall_k] (best <= min(k, n_cols)), ndcg
+ *                       [n_rows, n_ndcg_k]; gsize [n_rows] = size of the row's ground-truth set (ideal DCG).
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_dense_gt_ranks(const void* sim, int dtype, int64_t ld, int n_rows, int n_cols, const int32_t* gt, int G,
+                            int sanitize, int32_t* ranks, void* stream);
+int b200clip_dense_rank_metrics(const int32_t* ranks, const int32_t* gsize, int n_rows, int G, int n_cols,
+                                const int32_t* recall_k, int n_recall_k, const int32_t* ndcg_k, int n_ndcg_k,
+                                int32_t* best, double* rr, double* ap, uint8_t* hit, double* ndcg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K5 / K6  Streaming retrieval. Replaces compute_recall_at_k_streaming / compute_metrics_streaming
  *          (utils/retrieval_metrics_streaming.py:10-101, 104-197): chunked matmul + topk + merge + argsort rank.
  *   retrieval_sweep : one pass of similarity tiles video [n_video, >=Kp] x text [n_text, >=Kp] (operands).

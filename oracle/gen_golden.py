@@ -134,6 +134,33 @@ def siglip_variants():
                    math.log(0.04))          # clamp at +-30 active on part of the matrix
 
 
+def dense_metrics():
+    """SURVEY §8f #1: utils/retrieval_metrics.py on tie-free Gaussian similarities with multi-label ground truth."""
+    from utils.retrieval_metrics import (compute_map, compute_median_rank, compute_mrr, compute_ndcg_at_k,
+                                         compute_recall_at_k, compute_similarity_matrix)
+    for name, N, M, gmax, seed in (("dense_metrics_120x90_g1", 120, 90, 1, 40), ("dense_metrics_200x300_g4", 200, 300, 4, 41),
+                                   ("dense_metrics_64x7_g3", 64, 7, 3, 42)):
+        g = torch.Generator().manual_seed(seed)
+        v = torch.randn(N, 48, generator=g)
+        t = torch.randn(M, 48, generator=g)
+        sim = compute_similarity_matrix(v, t)
+        assert all(len(set(r.tolist())) == M for r in sim)                      # tie-free rows
+        gt = torch.full((N, gmax), -1, dtype=torch.int64)
+        for i in range(N):
+            n_i = int(torch.randint(0 if gmax > 1 else 1, gmax + 1, (1,), generator=g))
+            gt[i, :n_i] = torch.randperm(M, generator=g)[:n_i]
+        gt_arg = gt[:, 0] if gmax == 1 else gt
+        ks = [1, 5, 10]
+        rec = compute_recall_at_k(sim, gt_arg, ks)
+        nd = compute_ndcg_at_k(sim, gt_arg, ks)
+        rec_v = np.array([rec[f"Recall@{k}"] for k in ks])
+        nd_v = np.array([nd[f"NDCG@{k}_V2T"] for k in ks])
+        np.savez_compressed(OUT / f"{name}.npz", video=v.numpy(), text=t.numpy(), sim=sim.numpy(), gt=gt.numpy(),
+                            k_values=np.array(ks), recall=rec_v, ndcg=nd_v, mrr=np.array(compute_mrr(sim, gt_arg)["MRR_V2T"]),
+                            map=np.array(compute_map(sim, gt_arg)), median_rank=np.array(compute_median_rank(sim, gt_arg)))
+        print(name, rec, nd)
+
+
 def retrieval():
     g = torch.Generator().manual_seed(30)
     v = torch.randn(300, 64, generator=g)
@@ -261,6 +288,6 @@ def qpool():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["losses", "siglip_variants", "retrieval", "rope", "attnpool", "qpool"]
+    which = sys.argv[1:] or ["losses", "siglip_variants", "dense_metrics", "retrieval", "rope", "attnpool", "qpool"]
     for name in which:
         globals()[name]()

@@ -174,3 +174,20 @@ def test_query_pool_oracle(name):
     _close(grads["ln_w"], g["g_ln_w"], 1e-9, 1e-12)
     _close(grads["ln_b"], g["g_ln_b"], 1e-9, 1e-12)
     _close(grads["attn_query"], g["g_attn_query"], 1e-9, 1e-12)
+
+
+# ---- dense multi-label retrieval metrics: oracle pinned to utils/retrieval_metrics.py ----
+@pytest.mark.parametrize("name", ["dense_metrics_120x90_g1", "dense_metrics_200x300_g4", "dense_metrics_64x7_g3"])
+def test_dense_metrics_oracle_matches_reference(name):
+    from oracle import dense_metrics_oracle as dmo
+    g = _load(name)
+    sim, ks = g["sim"], [int(k) for k in g["k_values"]]
+    gt = g["gt"][:, 0] if g["gt"].shape[1] == 1 else [[int(c) for c in row if c >= 0] for row in g["gt"]]
+    rec = dmo.recall_at_k(sim, gt, ks)
+    nd = dmo.ndcg_at_k(sim, gt, ks)
+    for i, k in enumerate(ks):
+        assert rec[f"Recall@{k}"] == float(g["recall"][i])
+        assert abs(nd[f"NDCG@{k}_V2T"] - float(g["ndcg"][i])) <= 1e-6
+    assert abs(dmo.mrr(sim, gt)["MRR_V2T"] - float(g["mrr"])) <= 1e-12
+    assert abs(dmo.mean_ap(sim, gt) - float(g["map"])) <= 1e-6
+    assert dmo.median_rank(sim, gt) == int(g["median_rank"])
