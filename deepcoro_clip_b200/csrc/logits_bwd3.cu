@@ -115,6 +115,48 @@ __device__ __forceinline__ void bw3_g32(const BwParams& p, const BwThread& th, c
   }
 }
 
+// Work of one cluster, identical in every warp role. nseg > 0: items = (X tile, segment of the Y tiles) dealt round-robin
+// (explicit nseg_hint). nseg == 0 (default): the flattened (X tile, Y tile) sequence is cut into one CONTIGUOUS, equally
+// long range per cluster — perfect balance for any shape (at 8 ranks a rank has only 32 X tiles for 74 clusters); a range
+// that crosses X tiles is walked as up to a few (X tile, [j0, j1)) pieces, each with its own X panel load and drain.
+struct Bw3Sched {
+  long long r, r1;
+  int item, items, stride, nseg, y_tiles;
+  __device__ __forceinline__ void init(const BwParams& p, int cluster_id, int n_clusters) {
+    nseg = p.nseg;
+    y_tiles = p.y_tiles;
+    if (nseg > 0) {
+      items = p.x_tiles * nseg;
+      item = cluster_id;
+      stride = n_clusters;
+    } else {
+      const long long total = (long long)p.x_tiles * p.y_tiles;
+      r = total * cluster_id / n_clusters;
+      r1 = total * (cluster_id + 1) / n_clusters;
+    }
+  }
+  __device__ __forceinline__ bool next(int& xt, int& j0, int& j1) {
+    if (nseg > 0) {
+      while (item < items) {
+        const int seg = item % nseg;
+        xt = item / nseg;
+        j0 = (int)((long long)y_tiles * seg / nseg);
+        j1 = (int)((long long)y_tiles * (seg + 1) / nseg);
+        item += stride;
+        if (j1 > j0) return true;
+      }
+      return false;
+    }
+    if (r >= r1) return false;
+    xt = (int)(r / y_tiles);
+    j0 = (int)(r - (long long)xt * y_tiles);
+    const long long left = r1 - r;
+    j1 = (left < (long long)(y_tiles - j0)) ? j0 + (int)left : y_tiles;
+    r += j1 - j0;
+    return true;
+  }
+};
+
 template <int kMode, int kNJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BW_THREADS, 1)
 bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmYs,
@@ -143,7 +185,6 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   const bool leader = rank == 0;
   const int kchunks = p.Kp / BW_BK;                // even (host checks Kp % 256 == 0)
   const int nparts = p.Dp / 256;                   // N = 256 accumulator parts
-  const int items = p.x_tiles * p.nseg;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (warp == 0 && elect_one()) {
@@ -185,23 +226,16 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     p.yneg = p.dyn[9];
   }
 
-  auto decode = [&](int item, int& xt, int& j0, int& j1) {
-    const int seg = item % p.nseg;
-    xt = item / p.nseg;
-    j0 = (int)((long long)p.y_tiles * seg / p.nseg);
-    j1 = (int)((long long)p.y_tiles * (seg + 1) / p.nseg);
-  };
-
   if (warp == 0) {
     // ===================== TMA producer (both CTAs, each for its own halves) =====================
     if (elect_one()) {
       int slot = 0;
       uint32_t phase = 0, xphase = 0;
-      for (int item = cluster_id; item < items; item += n_clusters) {
-        int xt, j0, j1;
-        decode(item, xt, j0, j1);
+      Bw3Sched sched;
+      sched.init(p, cluster_id, n_clusters);
+      int xt, j0, j1;
+      while (sched.next(xt, j0, j1)) {
         const int nj = j1 - j0;
-        if (nj <= 0) continue;
         mbar_wait(xempty_bar, xphase ^ 1);
         xphase ^= 1;
         if (leader) mbar_expect_tx(xfull_bar, 2 * kchunks * BW3_XCHUNK);
@@ -247,11 +281,11 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       uint32_t phase = 0, xphase = 0;
       uint32_t tile_ctr = 0, acc_ctr = 0;
       const uint32_t xs_addr = smem_u32(xs), g_addr = smem_u32(gbuf);
-      for (int item = cluster_id; item < items; item += n_clusters) {
-        int xt, j0, j1;
-        decode(item, xt, j0, j1);
+      Bw3Sched sched;
+      sched.init(p, cluster_id, n_clusters);
+      int xt, j0, j1;
+      while (sched.next(xt, j0, j1)) {
         const int nj = j1 - j0;
-        if (nj <= 0) continue;
         mbar_wait(xfull_bar, xphase);
         xphase ^= 1;
         tc_fence_after();
@@ -341,11 +375,11 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     th.wn = p.wneg_c * p.gnorm;
     th.ign = 1.f / p.gnorm;
     th.nshift2 = -p.shift2;
-    for (int item = cluster_id; item < items; item += n_clusters) {
-      int xt, j0, j1;
-      decode(item, xt, j0, j1);
+    Bw3Sched sched;
+    sched.init(p, cluster_id, n_clusters);
+    int xt, j0, j1;
+    while (sched.next(xt, j0, j1)) {
       const int nj = j1 - j0;
-      if (nj <= 0) continue;
       th.row = xt * BW_BM + BW3_XROWS * (int)rank + rloc;
       th.row_ok = th.row < p.Nx;
       th.rs = 0.f;
@@ -525,19 +559,8 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
   p.y_tiles = (Ny + NJ - 1) / NJ;
   p.dparts = 1;
   const int clusters = sm_count() / 2;
-  int nseg = nseg_hint;
-  if (nseg <= 0) {
-    const int min_tiles = NJ == 128 ? 4 : 2;
-    const int max_seg = p.y_tiles / min_tiles > 1 ? p.y_tiles / min_tiles : 1;
-    double best = 1e30;
-    nseg = 1;
-    for (int s = 1; s <= max_seg && s <= 64; ++s) {
-      const long long it = (long long)p.x_tiles * s;
-      const long long waves = (it + clusters - 1) / clusters;
-      const double cost = (double)waves * ((p.y_tiles + s - 1) / s + (NJ == 128 ? 3.0 : 1.5));
-      if (cost < best * 0.995) { best = cost; nseg = s; }
-    }
-  }
+  // nseg_hint > 0: explicit (X tile, Y segment) items; otherwise balanced contiguous ranges (Bw3Sched)
+  int nseg = nseg_hint > 0 ? nseg_hint : 0;
   if (nseg > p.y_tiles) nseg = p.y_tiles;
   p.nseg = nseg;
   p.scale2 = scale2; p.shift2 = shift2; p.inv_tau = inv_tau; p.bias = bias; p.wneg_c = wneg_c;
@@ -551,8 +574,8 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
   if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, Kp, ldx, BW3_XROWS))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmYs, Y, Ny, Kp, ldy, NJ / 2))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmYo, Y, Ny, Kp, ldy, 128))) return rc;
-  const int items = p.x_tiles * p.nseg;
-  const int grid = 2 * (items < clusters ? items : clusters);
+  const long long items = p.nseg > 0 ? (long long)p.x_tiles * p.nseg : (long long)p.x_tiles * p.y_tiles;
+  const int grid = 2 * (int)(items < clusters ? items : clusters);
 #define LAUNCH3(M) (NJ == 256 ? launch_bw3<M, 256>(tmX, tmYs, tmYo, p, grid, stream) \
                               : launch_bw3<M, 128>(tmX, tmYs, tmYo, p, grid, stream))
   if (mode == BW_CLIP) return LAUNCH3(BW_CLIP);

@@ -126,7 +126,13 @@ diag_sum_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat1
 //   sums = [colsum (N) | rowsum (N) | target dots (N)]  (already all-reduced across ranks)
 //   rowscale[i] = c / rowsum[i], colscale[j] = c / colsum[j]  (c = 0.5 / N, the backward's softmax denominators)
 //   loss = c * (sum_i ln rowsum_i + sum_j ln colsum_j + 2 N ln2 shift2) - ((1 - eps) / tau * sum_i f(dot_i) + unif) / N
-// A single CTA: N <= a few 100k elements, fp64 accumulation, deterministic order.
+// Up to 64 CTAs; every CTA reduces its slice in fp64 and parks three partial sums in a device scratch block, the CTA that
+// draws the last ticket adds the partials in CTA order (deterministic) and writes the loss. (Was one CTA: 28 us at
+// N = 32k — 3 % of an 8-GPU step.) The scratch block is shared by all launches of the process: one stream at a time.
+constexpr int FIN_MAX_BLOCKS = 64;
+__device__ double g_fin_partial[3 * FIN_MAX_BLOCKS];
+__device__ unsigned int g_fin_ticket = 0;
+
 __global__ void __launch_bounds__(1024)
 clip_finalize_kernel(const float* __restrict__ sums, int n, const float* __restrict__ dyn, float eps, int gated,
                      const double* __restrict__ unif, float* __restrict__ rowscale, float* __restrict__ colscale,
@@ -134,7 +140,7 @@ clip_finalize_kernel(const float* __restrict__ sums, int n, const float* __restr
   const float c = 0.5f / (float)n;
   const double shift = (double)dyn[6];
   double a_row = 0.0, a_col = 0.0, a_dot = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float cs = sums[i], rs = sums[n + i];
     const double d = (double)sums[2 * n + i];
     colscale[i] = c / cs;
@@ -144,6 +150,7 @@ clip_finalize_kernel(const float* __restrict__ sums, int n, const float* __restr
     a_dot += gated ? d / (1.0 + exp(-d)) : d;
   }
   __shared__ double sh[3][32];
+  __shared__ bool last;
   for (int o = 16; o > 0; o >>= 1) {
     a_row += __shfl_xor_sync(0xffffffffu, a_row, o);
     a_col += __shfl_xor_sync(0xffffffffu, a_col, o);
@@ -158,6 +165,22 @@ clip_finalize_kernel(const float* __restrict__ sums, int n, const float* __restr
   if (threadIdx.x == 0) {
     double r = 0.0, cc = 0.0, d = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { r += sh[0][w]; cc += sh[1][w]; d += sh[2][w]; }
+    g_fin_partial[3 * blockIdx.x] = r;
+    g_fin_partial[3 * blockIdx.x + 1] = cc;
+    g_fin_partial[3 * blockIdx.x + 2] = d;
+    __threadfence();
+    last = atomicAdd(&g_fin_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double r = 0.0, cc = 0.0, d = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) {
+      r += g_fin_partial[3 * b];
+      cc += g_fin_partial[3 * b + 1];
+      d += g_fin_partial[3 * b + 2];
+    }
+    g_fin_ticket = 0;                                   // ready for the next launch (stream order)
     const double u = unif ? unif[0] : 0.0;
     const double loss = (0.5 / n) * (r + cc) - ((1.0 - (double)eps) * d * (double)dyn[2] + u) / n;
     loss_out[0] = (float)loss;
@@ -206,7 +229,9 @@ int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s) {
 int clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif, float* rowscale,
                   float* colscale, float* loss_out, double* acc_out, cudaStream_t s) {
   if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out) return B2_EINVAL;
-  clip_finalize_kernel<<<1, 1024, 0, s>>>(sums, n, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out);
+  int blocks = (n + 1023) / 1024;
+  if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
+  clip_finalize_kernel<<<blocks, 1024, 0, s>>>(sums, n, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -127,11 +127,15 @@ class _ClipLossFn(torch.autograd.Function):
         ws = torch.zeros(2 * nbd + 4 * B + 8, dtype=torch.float32, device=dev)
         scal = ws[2 * nbd + 4 * B:].view(torch.float64)
         ydiag = (1.0 - eps) / N
+        lt_work = None
         if need_v or need_lt:
             dVh = ws[:nbd].view(B, D)
             dcv = ws[2 * nbd:2 * nbd + 2 * B]
             ops.logits_bwd(mode, vop, tall, B, N, K, Kp, D, dyn, rowscale_all[lo:hi], colscale_all, dVh, scal,
                            ydiag=ydiag, diag_off=lo, diag_corr=dcv, gnorm=2.0 * N, hp=(K != Kp))
+            if need_lt and W > 1:
+                # sum_ij G_ij L_ij is complete after the video-side pass: its all-reduce overlaps the text-side pass
+                lt_work = dist.all_reduce(scal[0:1], group=group, async_op=True)
             if need_v:
                 dV = ops.l2norm_backward(dVh, video, vinv, other_x=text, other_inv=tinv, other_hi=top[:, K - Kp:],
                                          diag_corr=dcv, usum=tsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3],
@@ -149,8 +153,8 @@ class _ClipLossFn(torch.autograd.Function):
             if dT.dtype != text.dtype:
                 dT = dT.to(text.dtype)
         if need_lt:
-            if W > 1:
-                dist.all_reduce(scal[0:1], group=group)
+            if lt_work is not None:
+                lt_work.wait()
             # d loss / d log_temp = -sum_ij G_ij L_ij  (zero while the tau clamp is active); the kernel's sum already
             # contains the diagonal target, only the uniform label-smoothing part is added
             dlt = torch.empty(1, dtype=torch.float32, device=dev)
