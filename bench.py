@@ -224,10 +224,8 @@ def main():
     from deepcoro_clip_b200 import GraphedLossStep
     gstep = None
     launches_per_step = None
-    # Multi-rank capture (NCCL collectives inside the graph) hung on a 2-GPU box in this round and is not used here:
-    # world > 1 runs the eager module (GraphedLossStep itself is rank-agnostic).
-    if not args.no_graph and world == 1:
-        step(v, t)                                   # library attribute calls before the capture
+    if not args.no_graph:
+        step(v, t)                                   # library attribute calls / communicators before the capture
         l0 = _lib.LAUNCHES
         gstep = GraphedLossStep(loss_mod, v, t, log_temp, warmup=2)
         launches_per_step = (_lib.LAUNCHES - l0) // 3      # 2 warm-up passes + the captured one
@@ -375,6 +373,11 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # a live CUDA graph that holds NCCL kernels keeps destroy_process_group() waiting forever: drop it first
+        gstep = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

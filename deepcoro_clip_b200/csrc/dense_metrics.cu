@@ -45,12 +45,28 @@ dense_gt_ranks_kernel(const T* __restrict__ sim, long long ld, int N, int M, con
   int cnt[GMAX];
 #pragma unroll
   for (int g = 0; g < GMAX; ++g) cnt[g] = 0;
-#pragma unroll 4
-  for (int j = threadIdx.x; j < M; j += blockDim.x) {
-    const float s = dm_sanitize(dm_val<T>(sr[j]), sanitize);
+  auto consider = [&](float v, int j) {
+    const float s = dm_sanitize(v, sanitize);
 #pragma unroll
     for (int g = 0; g < GMAX; ++g) cnt[g] += (s > thr[g] || (s == thr[g] && j < gidx[g])) ? 1 : 0;
+  };
+  // 16-byte vector loads over the aligned middle of the row, scalar head / tail
+  constexpr int VE = 16 / (int)sizeof(T);
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(sr);
+  int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+  if (head > M) head = M;
+  const int nvec = (M - head) / VE;
+  for (int j = threadIdx.x; j < head; j += blockDim.x) consider(dm_val<T>(sr[j]), j);
+  const uint4* vp = reinterpret_cast<const uint4*>(sr + head);
+#pragma unroll 2
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 raw = __ldg(vp + v);
+    const T* e = reinterpret_cast<const T*>(&raw);
+    const int j0 = head + v * VE;
+#pragma unroll
+    for (int k = 0; k < VE; ++k) consider(dm_val<T>(e[k]), j0 + k);
   }
+  for (int j = head + nvec * VE + threadIdx.x; j < M; j += blockDim.x) consider(dm_val<T>(sr[j]), j);
   __shared__ int sh[8][GMAX];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll

@@ -65,9 +65,10 @@ class HostBatchPrefetcher:
 
 
 class GraphedLossStep:
-    """One loss forward + backward captured in a CUDA graph and replayed: removes the per-step host work (≈25 kernel
-    launches and a dozen allocations). Verified single-process; capturing the NCCL collectives of the sharded path hung
-    on a 2-GPU box in round 1 and is NOT supported yet (use the eager module under torch.distributed). Inputs live in static
+    """One loss forward + backward captured in a CUDA graph (kernels AND the NCCL collectives of the sharded path) and
+    replayed: removes the per-step host work (≈25 kernel launches, four collective enqueues, a dozen allocations) that
+    makes the eager step host-bound at 8 ranks. Under torch.distributed drop the object (``del step; gc.collect()``)
+    BEFORE ``destroy_process_group()`` — a live graph holding NCCL kernels keeps the teardown waiting. Inputs live in static
     buffers: ``step(video, text)`` copies the new batch in (device or pinned-host tensors), replays, and returns
     ``(loss, dvideo, dtext, dlog_temp)`` — views of static tensors, valid until the next call. Shapes, dtypes and the loss
     configuration are fixed at construction; the parity of a replayed step with the eager module is covered by

@@ -59,6 +59,17 @@ def _gt_matrix(gt: GtSpec, n: int, dev: torch.device):
     if isinstance(gt, torch.Tensor) and gt.ndim == 1 and gt.numel() >= n and not gt.is_floating_point():
         g = gt[:n].to(device=dev, dtype=torch.int32).reshape(n, 1).contiguous()
         return g, torch.ones(n, dtype=torch.int32, device=dev), 1       # a negative index stays "absent" in the kernel
+    if isinstance(gt, torch.Tensor) and gt.ndim == 2 and gt.shape[0] >= n and not gt.is_floating_point():
+        # 2-D index tensor (-1 padded): per-row sort + duplicate removal on the device instead of n Python sets
+        G = int(gt.shape[1])
+        if G > MAX_GT:
+            raise ValueError(f"at most {MAX_GT} ground-truth items per query are supported, got {G}")
+        g = gt[:n].to(device=dev, dtype=torch.int32).clamp(min=-1)
+        g, _ = torch.sort(g, dim=1)
+        dup = torch.zeros_like(g, dtype=torch.bool)
+        dup[:, 1:] = g[:, 1:] == g[:, :-1]
+        g = torch.where(dup, torch.full_like(g, -1), g).contiguous()
+        return g, (g >= 0).sum(dim=1, dtype=torch.int32), max(G, 1)
     sets = _normalize_ground_truth_sets(gt, n)
     G = max(1, max((len(s) for s in sets), default=1))
     if G > MAX_GT:

@@ -32,6 +32,12 @@ def test_dense_metrics_match_reference_golden(name):
     assert abs(rm.compute_mrr(sim, gt)["MRR_V2T"] - float(g["mrr"])) <= 1e-15
     assert abs(rm.compute_map(sim, gt) - float(g["map"])) <= 1e-6
     assert rm.compute_median_rank(sim, gt) == int(g["median_rank"])
+    if g["gt"].shape[1] > 1:
+        # the same ground truth as a -1 padded 2-D index tensor (device-side sort + duplicate removal) with a duplicate
+        gt2 = torch.tensor(np.concatenate([g["gt"], g["gt"][:, :1]], axis=1))
+        assert rm.compute_recall_at_k(sim, gt2, ks) == rec
+        assert rm.compute_ndcg_at_k(sim, gt2, ks) == nd
+        assert rm.compute_map(sim, gt2) == rm.compute_map(sim, gt)
     allm = rm.compute_all_dense_metrics(sim, gt, recall_k=ks, ndcg_k=ks)
     assert allm["Recall@5"] == rec["Recall@5"] and allm["MedianRank_V2T"] == int(g["median_rank"])
     # the materialised similarity matrix itself (normalize + matmul, bf16x3 operands ~ fp32)
