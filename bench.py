@@ -187,6 +187,11 @@ def main():
         run_reference(args, N, D)
         return
 
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    # chatter) is sent to stderr for the duration of the run
+    real_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from deepcoro_clip_b200 import _lib, ops
@@ -371,7 +376,8 @@ def main():
             "gpu_launches": launches, "loss": loss_val, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "retrieval": retr,
         }
-        print(json.dumps(line), flush=True)
+        real_out.write(json.dumps(line) + "\n")
+        real_out.flush()
     if world > 1:
         # a live CUDA graph that holds NCCL kernels keeps destroy_process_group() waiting forever: drop it first
         gstep = None

@@ -25,6 +25,15 @@ __device__ __forceinline__ float dm_sanitize(float v, int on) {
   return v;
 }
 
+// (score descending, index ascending) as ONE unsigned 64-bit order: monotone map of the float bits in the high word
+// (-0 canonicalised to +0 first), complemented column index in the low word. "column j ranks before ground truth g"
+// <=> key(s_j, j) > key(s_g, g): two instructions per (element, threshold) instead of a float compare chain.
+__device__ __forceinline__ unsigned long long dm_key(float v, int j) {
+  const uint32_t u = __float_as_uint(v + 0.f);
+  const uint32_t o = u ^ (uint32_t(int32_t(u) >> 31) | 0x80000000u);
+  return (static_cast<unsigned long long>(o) << 32) | (0xFFFFFFFFu - (uint32_t)j);
+}
+
 // One CTA per row. gt [N, G] int32 (entries < 0 or >= M: absent). ranks [N, G] int32: 1-based rank, 0 = absent.
 template <typename T, int GMAX>
 __global__ void __launch_bounds__(256)
@@ -33,22 +42,21 @@ dense_gt_ranks_kernel(const T* __restrict__ sim, long long ld, int N, int M, con
   const int row = blockIdx.x;
   if (row >= N) return;
   const T* sr = sim + (size_t)row * ld;
-  float thr[GMAX];
-  int gidx[GMAX];
+  unsigned long long thr[GMAX];
 #pragma unroll
   for (int g = 0; g < GMAX; ++g) {
     int c = g < G ? gt[(size_t)row * G + g] : -1;
     if (c >= M) c = -1;
-    gidx[g] = c;
-    thr[g] = c >= 0 ? dm_sanitize(dm_val<T>(sr[c]), sanitize) : INFINITY;     // nothing beats +inf: count stays 0
+    // absent entries: the maximal key, nothing ranks before it, the count stays 0
+    thr[g] = c >= 0 ? dm_key(dm_sanitize(dm_val<T>(sr[c]), sanitize), c) : ~0ull;
   }
   int cnt[GMAX];
 #pragma unroll
   for (int g = 0; g < GMAX; ++g) cnt[g] = 0;
   auto consider = [&](float v, int j) {
-    const float s = dm_sanitize(v, sanitize);
+    const unsigned long long k = dm_key(dm_sanitize(v, sanitize), j);
 #pragma unroll
-    for (int g = 0; g < GMAX; ++g) cnt[g] += (s > thr[g] || (s == thr[g] && j < gidx[g])) ? 1 : 0;
+    for (int g = 0; g < GMAX; ++g) cnt[g] += k > thr[g] ? 1 : 0;
   };
   // 16-byte vector loads over the aligned middle of the row, scalar head / tail
   constexpr int VE = 16 / (int)sizeof(T);
@@ -142,6 +150,7 @@ static int launch_ranks(const void* sim, long long ld, int N, int M, const int* 
   const T* p = reinterpret_cast<const T*>(sim);
   if (G <= 1) dense_gt_ranks_kernel<T, 1><<<N, 256, 0, s>>>(p, ld, N, M, gt, G, sanitize, ranks);
   else if (G <= 4) dense_gt_ranks_kernel<T, 4><<<N, 256, 0, s>>>(p, ld, N, M, gt, G, sanitize, ranks);
+  else if (G <= 8) dense_gt_ranks_kernel<T, 8><<<N, 256, 0, s>>>(p, ld, N, M, gt, G, sanitize, ranks);
   else dense_gt_ranks_kernel<T, 16><<<N, 256, 0, s>>>(p, ld, N, M, gt, G, sanitize, ranks);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
