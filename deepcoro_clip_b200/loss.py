@@ -356,7 +356,7 @@ class _SigLIPFn(torch.autograd.Function):
             ops.call("siglip_entropy_rows", zhq[0], zhq[1], zhq[2], B, rowvec, stats, st)
             stats_all = stats
             if W > 1:
-                stats_all = torch.empty((W, 3), dtype=torch.float64, device=dev)
+                stats_all = torch.empty(W * 3, dtype=torch.float64, device=dev)      # [W, 3], flat for every backend
                 dist.all_gather_into_tensor(stats_all, stats, group=cfg["group"])
             ent = torch.empty(8, dtype=torch.float32, device=dev)
             ops.call("siglip_entropy_coef", stats_all, W, Bg, T, float(cfg["entropy_weight"]),

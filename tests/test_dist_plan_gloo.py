@@ -81,3 +81,46 @@ def test_shard_helpers_single_process():
     assert dp.text_shard(3, 8, 7) == (3, 3)                # more ranks than rows: empty shard
     x = torch.arange(6).view(3, 2)
     assert dp.gather_rows(x, 1) is x
+
+
+def _worker_siglip_pieces(rank, world, port, out):
+    """Host pieces of the SigLIP variants under DDP: the text-row gather of SigLIP2BCELossDDP (forward = rank-major
+    concatenation, backward = this rank's chunk without a reduce, utils/loss/siglip2_bce.py:194-224) and the assembly of
+    the entropy regulariser's global statistics from per-rank {sum, min, max} triples."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deepcoro_clip_b200.loss import _GatherTextRows
+        B, D = 5, 4
+        x = (torch.arange(B * D, dtype=torch.float32).view(B, D) + 100 * rank).requires_grad_(True)
+        full = _GatherTextRows.apply(x, None)
+        assert full.shape == (world * B, D)
+        for r in range(world):
+            assert torch.equal(full[r * B:(r + 1) * B], torch.arange(B * D, dtype=torch.float32).view(B, D) + 100 * r)
+        w = torch.arange(world * B * D, dtype=torch.float32).view(world * B, D)
+        (full * w).sum().backward()
+        assert torch.equal(x.grad, w[rank * B:(rank + 1) * B])            # own chunk, no reduction, no 1/W
+        # entropy statistics: every rank contributes (sum_i H_i, min_i H_i, max_i H_i) of its rows; the coefficient
+        # kernel consumes the [W, 3] gather (loss.py: stats_all)
+        rng = np.random.default_rng(7)
+        H = rng.random(world * B) * 3.0                                    # global per-row entropies
+        mine = H[rank * B:(rank + 1) * B]
+        stats = torch.tensor([mine.sum(), mine.min(), mine.max()], dtype=torch.float64)
+        stats_all = torch.empty(world * 3, dtype=torch.float64)
+        dist.all_gather_into_tensor(stats_all, stats)
+        stats_all = stats_all.view(world, 3)
+        mean = float(stats_all[:, 0].sum() / (world * B))
+        assert abs(mean - H.mean()) < 1e-12
+        assert float(stats_all[:, 1].min()) == H.min() and float(stats_all[:, 2].max()) == H.max()
+        out[rank] = mean
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_siglip_variant_pieces():
+    world = 2
+    port = 31000 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_siglip_pieces, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == world and out[0] == out[1]

@@ -112,5 +112,49 @@ def test_install_into_reference_registry():
             LossRegistry.get("INFONCE_LOSS_DDP")                           # dead config key stays an error
         import utils.retrieval_metrics_streaming as rms
         assert rms.compute_metrics_streaming is pkg.compute_metrics_streaming
+        # SURVEY §8 row a6 classes are rebound by name on their home modules, §8f #1 functions on utils.retrieval_metrics
+        import utils.loss.siglip2_bce as s2
+        import utils.loss.siglip_pairwise as sp
+        import utils.retrieval_metrics as urm
+        assert s2.SigLIP2BCELoss is pkg.SigLIP2BCELoss and s2.SigLIP2MultiPositiveBCELoss is pkg.SigLIP2MultiPositiveBCELoss
+        assert s2.SigLIP2BCELossDDP is pkg.SigLIP2BCELossDDP and sp.SiglipPairwiseFeatureLoss is pkg.SiglipPairwiseFeatureLoss
+        assert urm.compute_mrr is pkg.retrieval_metrics.compute_mrr and urm.compute_map is pkg.retrieval_metrics.compute_map
+        assert "utils.retrieval_metrics" in rep["metrics"] or "utils.retrieval_metrics" in pkg.install("/root/reference")["metrics"]
     finally:
         sys.path.remove("/root/reference")
+
+
+def test_ground_truth_set_normalisation_matches_reference():
+    """Host logic of the dense metrics: ground-truth specifications -> one index set per query, as the reference's
+    _normalize_ground_truth_sets (utils/retrieval_metrics.py:7-62) builds them (compared with the imported reference where
+    it is available, with the documented rules otherwise)."""
+    import importlib.util
+    import os
+    from deepcoro_clip_b200.retrieval_metrics import _normalize_ground_truth_sets as ours
+    cases = [
+        (torch.tensor([3, 0, 7]), 3),
+        (torch.tensor([[1, 2, -1], [4, -1, -1], [-1, -1, -1]]), 3),
+        ([[1, 2], [3], [], None, 5], 5),
+        ([1, 2, 3], 5),                      # shorter than the number of queries: padded with empty sets
+        ([[1], [2], [3], [4]], 2),           # longer: truncated
+        ((0, (1, 1, 2), {4, 5}), 3),
+    ]
+    expect = [
+        [{3}, {0}, {7}], [{1, 2}, {4}, set()], [{1, 2}, {3}, set(), set(), {5}], [{1}, {2}, {3}, set(), set()],
+        [{1}, {2}], [{0}, {1, 2}, {4, 5}],
+    ]
+    ref = None
+    path = "/root/reference/utils/retrieval_metrics.py"
+    if os.path.exists(path):
+        spec = importlib.util.spec_from_file_location("_ref_retrieval_metrics", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref = mod._normalize_ground_truth_sets
+    for (gt, n), want in zip(cases, expect):
+        assert ours(gt, n) == want
+        if ref is not None:
+            assert ref(gt, n) == want
+    with pytest.raises(ValueError):
+        ours(torch.zeros(2, 2, 2, dtype=torch.long), 2)
+    with pytest.raises(TypeError):
+        ours(3.5, 1)
