@@ -24,7 +24,6 @@ const char* b200clip_strerror(int code) {
 }
 
 int b200clip_sm_count(void) { return sm_count(); }
-int b200clip_set_sm_reserve(int n) { set_sm_reserve(n); return B2_OK; }
 
 int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim, void* operand, int ld_out, int Kp,
                         int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, int normalize, void* stream) {

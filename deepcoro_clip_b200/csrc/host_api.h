@@ -143,7 +143,5 @@ int querypool(int backward, const float* x, long long sb, long long sn, const fl
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                       uint32_t box_rows);
 int sm_count();
-void set_sm_reserve(int n);
-int sm_budget();   // sm_count() minus the reserve (even, >= 2): grid size of the forward / retrieval tile kernels
 
 }  // namespace b2host

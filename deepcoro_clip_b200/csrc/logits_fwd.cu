@@ -183,7 +183,7 @@ static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int l
     attr_done = true;
   }
   long long total = diag ? (long long)g.m_tiles : (long long)g.m_tiles * g.n_blocks;
-  int grid = sm_budget();
+  int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (total < grid) grid = (int)total;
   kern<<<grid, TE_THREADS, TE_SMEM_BYTES, stream>>>(tmA, tmB, g, ep);
@@ -214,7 +214,7 @@ static int launch_te2(const void* A, const void* B, int Ma, int Nb, int Kp, int 
     attr_done = true;
   }
   const long long total = (long long)((g.m_tiles + 1) / 2) * g.n_blocks;
-  long long clusters = sm_budget() / 2;
+  long long clusters = sm_count() / 2;
   if (total < clusters) clusters = total;
   kern<<<(int)(2 * clusters), TE_THREADS, TE2_SMEM_BYTES, stream>>>(tmA, tmB, g, ep);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;

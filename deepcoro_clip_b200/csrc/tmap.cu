@@ -52,16 +52,4 @@ int sm_count() {
   return n;
 }
 
-// SMs left free by the persistent forward / retrieval tile kernels (set_sm_reserve): under torch.distributed the video
-// all-gather runs concurrently with the logits forward; NCCL's CTAs cannot share an SM with a 227 KB-shared-memory CTA,
-// so a grid that asks for every SM has part of its CTAs start only after the collective ends (measured: forward 127 us
-// instead of 75 us at 8 ranks). Leaving NCCL its SMs costs ~10 % of the forward instead.
-static int g_sm_reserve = 0;
-void set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
-int sm_budget() {
-  int n = sm_count() - g_sm_reserve;
-  n &= ~1;
-  return n < 2 ? 2 : n;
-}
-
 }  // namespace b2host

@@ -27,7 +27,6 @@ from . import dist_plan, ops
 from ._lib import B200ClipError
 
 BW_CLIP, BW_GATED, BW_SIGLIP, BW_SIGLIP_ENT = 0, 1, 2, 3
-_NCCL_SMS = int(__import__("os").environ.get("B200CLIP_NCCL_SMS", "20"))   # SMs left to an overlapping collective
 _LOCAL = "local"   # cfg['group'] marker: never gather, even inside an initialised process group
 
 
@@ -85,12 +84,8 @@ class _ClipLossFn(torch.autograd.Function):
         lo = rank * B
         if t_work is not None:
             t_work.wait()
-        if v_work is not None:
-            ops.call("set_sm_reserve", _NCCL_SMS)      # the video all-gather is still running: leave NCCL its SMs
         ops.call("logits_lse_fwd", vop, tall, B, N, K, vop.stride(0), tall.stride(0), 0.0, 0.0, int(gated), dyn,
                  ws[N + lo:N + lo + B], ws[:N], ws[2 * N + lo:2 * N + lo + B], lo, st)
-        if v_work is not None:
-            ops.call("set_sm_reserve", 0)
         if W > 1:
             dist.all_reduce(sums, group=group)
         rowscale_all = ws[3 * N:4 * N]

@@ -35,10 +35,6 @@ int b200clip_abi_version(void);
 const char* b200clip_strerror(int code);
 /* Number of SMs of the current device (grid sizing / tests). */
 int b200clip_sm_count(void);
-/* Host-side setting (no stream): the persistent logits-forward / retrieval tile kernels size their grids to
- * sm_count - n SMs until it is reset to 0. Used while an NCCL collective overlaps the forward (its CTAs cannot share an SM
- * with a 227 KB-shared-memory CTA, so a full grid would have CTAs start only after the collective). */
-int b200clip_set_sm_reserve(int n);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  L2 normalise + operand packing.   Replaces F.normalize(x.float(), dim=-1)
