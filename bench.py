@@ -65,15 +65,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self) -> dict:
+    def wait_first_sample(self, timeout: float = 3.0) -> None:
+        """nvidia-smi needs a few hundred ms before its first line: the sampler is started ahead of the warm-up steps and
+        the timed region begins only once it is producing."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")) -> dict:
+        """Statistics over the samples taken inside [t_begin, t_end] (host clock around the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [(ts, ln) for ts, ln in self.lines if t_begin <= ts <= t_end + 0.025]
+        note = None
+        if not inside and self.lines:      # region shorter than the 20 ms sampling period: the nearest samples
+            mid = 0.5 * (t_begin + min(t_end, time.time()))
+            inside = sorted(self.lines, key=lambda x: abs(x[0] - mid))[:3]
+            note = "timed region shorter than the 20 ms sampling period: nearest samples"
+        for ts, ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -84,8 +98,11 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def cpu_reference_step(N: int, D: int, steps: int, warmup: int):
@@ -246,12 +263,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- value: inputs resident in HBM ----------------
-    for _ in range(W):
-        run_step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        run_step()
+    if rank == 0:
+        sampler.wait_first_sample()
+    barrier()
+    t_begin = time.time()
     l0 = _lib.LAUNCHES
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -264,7 +284,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     loss_val = loss.item()
 
     # ---------------- e2e: pinned host inputs in, loss out, every step ----------------
