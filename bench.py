@@ -343,7 +343,7 @@ def main():
         if bw3:
             kname = f"bw3_kernel<CLIP, {256 if Kp <= 512 else 128}> (logits_bwd3.cu: 64-row CTA pairs, cta_group::2 M=128, whole output width in TMEM)"
             executed = 2.0 * achieved                    # S once + the output product
-            prof = ROOT / "profiles" / "r01e_bw3_kernel_ncu_full_summary.json"
+            prof = ROOT / "profiles" / "r01f_bw3_kernel_ncu_full_summary.json"
         elif pair:
             kname = "bw2_kernel<CLIP> (logits_bwd2.cu: 128-row CTA pairs, cta_group::2)"
             executed = (1 + (Kp + 255) // 256) * achieved
