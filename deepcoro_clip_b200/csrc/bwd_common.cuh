@@ -80,22 +80,10 @@ struct BwThread {
 
 // G tile of one step: S (fp32, TMEM) -> elementwise gradient -> bf16x2 packed IN PLACE (tcgen05.st).
 // sbase: TMEM address of this thread's 64 S columns; cs_addr / cs: staged colscale*gnorm of the tile (shared).
-// remote_row (0 = none): shared::cluster address of this thread's 128-byte row inside the D-partner CTA's G staging
-// atom (SWIZZLE_128B K-major A operand of that CTA's output MMA); the packed row is ALSO pushed there (logits_bwd4.cu).
-__device__ __forceinline__ void bw_push_row(uint32_t remote_row, int row, int c, const uint32_t (&packed)[16]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t addr = remote_row + ((uint32_t)((c * 4 + j) ^ (row & 7)) << 4);
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j]), "r"(packed[4 * j + 1]),
-                 "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
-                 : "memory");
-  }
-}
-
 template <int kMode>
 __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th, uint32_t sbase, uint32_t cs_addr,
                                           const float* cs, int xt, int j, int dp, bool want_scal, float& tacc,
-                                          float& lacc, float& bacc, uint32_t remote_row = 0) {
+                                          float& lacc, float& bacc) {
   constexpr bool kSig = BwIsSiglip<kMode>::value;
   constexpr bool kEnt = kMode == BW_SIGLIP_ENT;
   const int row = th.row, wg = th.wg;
@@ -156,7 +144,6 @@ __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th,
         packed[(e >> 1) + 1] = pack_bf16x2(g4[2], g4[3]);
       }
       tmem_st16(sbase + c * 16, packed);
-      if (remote_row) bw_push_row(remote_row, th.row, c, packed);
     }
   } else {
     // -------- general path: edge tiles, diagonal tiles, hi+lo gradient operand --------
@@ -230,7 +217,6 @@ __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th,
         }
       }
       tmem_st16(sbase + c * 16, packed);
-      if (remote_row) bw_push_row(remote_row, th.row, c, packed);
       if (p.hp) tmem_st16(sbase + 32 + c * 16, packed_lo);
     }
     if (!want_scal) { tacc = 0.f; lacc = 0.f; bacc = 0.f; }

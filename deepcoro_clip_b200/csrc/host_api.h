@@ -61,13 +61,6 @@ int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, co
                         int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
                         unsigned long long drop_seed, cudaStream_t s);
 
-// logits_bwd4.cu: 4-CTA clusters, S/G tile shared by the two D halves (Dp == 512 only); B2_ENOSYS -> use the pair kernel
-int logits_bwd_quad(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off, int ldx,
-                    int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
-                    const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
-                    const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
-                    int nseg_hint, cudaStream_t stream);
-
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
 int dyn_set_siglip(float* dyn, float lclamp, float yneg, cudaStream_t s);

@@ -367,17 +367,6 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   const bool ent = mode == BW_SIGLIP_ENT;   // entropy term: single-CTA kernel only (general epilogue path)
   // headline shapes (plain bf16 operands, D <= 512): CTA-pair kernel, half the shared-memory ingest per SM.
   // B200CLIP_BWD_PAIR=0 keeps the single-CTA kernel (A/B measurements).
-  // Experimental (opt-in, B200CLIP_BWD_QUAD=1): 4-CTA clusters sharing one S/G tile between the two D halves
-  // (logits_bwd4.cu). Correct, executes 4*B*N*D instead of 6*B*N*D, but MEASURED SLOWER than the pair kernel (2.74 vs
-  // 2.03 ms at 32k x 32k x 512): only ONE 32 KB staging buffer fits next to the X panel and the ring, so every push
-  // waits for the partner pair's previous output product. Kept for the next round's shared-memory plan.
-  static const bool quad_on = [] { const char* e = getenv("B200CLIP_BWD_QUAD"); return e && e[0] == '1'; }();
-  if (!ent && quad_on && Kp <= BW_XRES_CHUNKS * BW_BK && !hp && Dp == 2 * BW_DP && Nx >= 1024 && Ny >= 2048) {
-    const int rc = logits_bwd_quad(mode, X, Y, Nx, Ny, Kp, Dp, D, hi_off, ldx, ldy, scale2, shift2, inv_tau, bias, wneg_c,
-                                   rowscale, colscale, out_scale, gnorm, hp, dyn, ydiag, diag_off, diag_corr, dX, ldd,
-                                   scal, nseg_hint, stream);
-    if (rc != B2_ENOSYS) return rc;
-  }
   // 64-row CTA pairs with the whole output width in TMEM (logits_bwd3.cu): no S recompute. Default whenever the shape
   // qualifies (plain bf16 operands, Dp in {256, 512, 768}): measured 1.54 vs 1.98 ms (D = 512) and 2.28 vs 5.50 ms
   // (D = 768) per launch at 32k x 32k. B200CLIP_BWD3=0 keeps the 128-row kernels (A/B measurements).
