@@ -2,6 +2,7 @@
 retrieval metrics, Rope3D, AttentionPool and the multi-view query pool behind the reference's own interfaces.
 Hand-written CUDA (tcgen05 / TMEM / TMA) behind a C ABI (include/b200clip.h); no CPU or PyTorch fallback."""
 from .attention_pool import AttentionPool
+from .embedding_store import EmbeddingStore, epoch_end_retrieval_metrics, gather_tensor_along_batch
 from .host_pipeline import GraphedLossStep, HostBatchPrefetcher
 from .install import install, loss_table
 from .loss import (CLIPLoss, ContrastiveLoss, ContrastiveLossDDP, InfoNCELoss, SigLIP2BCELoss, SigLIP2BCELossDDP,
@@ -12,8 +13,8 @@ from .retrieval_metrics_streaming import (compute_metrics_streaming, compute_rec
 from .rope_3d import Rope3D, apply_rope_qk
 from .video_aggregator import EnhancedVideoAggregator, query_pool
 
-__all__ = ["AttentionPool", "CLIPLoss", "GraphedLossStep", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EnhancedVideoAggregator",
+__all__ = ["AttentionPool", "CLIPLoss", "GraphedLossStep", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EmbeddingStore", "EnhancedVideoAggregator",
            "InfoNCELoss", "Rope3D", "SigLIP2BCELoss", "SigLIP2BCELossDDP", "SigLIP2MultiPositiveBCELoss", "SigLIPLoss",
            "SiglipLoss", "SiglipLossDDP", "SiglipPairwiseFeatureLoss", "apply_rope_qk", "clip_loss",
-           "compute_metrics_streaming", "compute_recall_at_k_streaming", "install", "loss_table", "query_pool",
+           "compute_metrics_streaming", "compute_recall_at_k_streaming", "epoch_end_retrieval_metrics", "gather_tensor_along_batch", "install", "loss_table", "query_pool",
            "streaming_topk"]

@@ -1,0 +1,85 @@
+"""Device-resident validation embeddings and their cross-rank gather.
+
+The reference moves every validation batch's embeddings to the host (runners/video_constrative_learning_runner.py:759-760,
+832-833), concatenates them at epoch end, and gathers them across ranks with ``_gather_tensor_along_batch`` (:494-534):
+W zero-filled allocations for the sizes, W for the padded data, a stack and a Python loop of slices. Here the embeddings
+stay on the device in ONE preallocated buffer, the ragged gather is one size exchange plus ONE
+``all_gather_into_tensor`` into a preallocated [W, max_rows, ...] buffer followed by a single index_select, and the result
+feeds the streaming retrieval kernels directly. Pure torch.distributed plumbing — no kernels, works on any backend (the
+gloo test runs it on CPU)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def gather_tensor_along_batch(local_tensor: torch.Tensor, world_size: Optional[int] = None, group=None) -> torch.Tensor:
+    """Rank-major concatenation along dim 0 of per-rank tensors whose first dimension may differ — the result of the
+    reference's ``_gather_tensor_along_batch`` (:494-534) with 2 collectives and no per-rank Python loop."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local_tensor
+    W = dist.get_world_size(group) if world_size is None else world_size
+    if W < 2:
+        return local_tensor
+    dev = local_tensor.device
+    n_local = local_tensor.shape[0]
+    sizes = torch.empty(W, dtype=torch.long, device=dev)
+    dist.all_gather_into_tensor(sizes, torch.tensor([n_local], dtype=torch.long, device=dev), group=group)
+    sizes_h: List[int] = sizes.tolist()
+    max_rows = max(sizes_h)
+    tail = tuple(local_tensor.shape[1:])
+    if max_rows == 0:
+        return local_tensor.new_empty((0,) + tail)
+    padded = local_tensor.new_zeros((max_rows,) + tail)
+    padded[:n_local] = local_tensor
+    gathered = local_tensor.new_empty((W * max_rows,) + tail)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    if all(s == max_rows for s in sizes_h):
+        return gathered
+    # rows r*max_rows + [0, sizes[r]) of every rank, in rank order: one gather of the valid row indices
+    idx = torch.cat([torch.arange(s, device=dev) + r * max_rows for r, s in enumerate(sizes_h)])
+    return gathered.index_select(0, idx)
+
+
+class EmbeddingStore:
+    """Append-only device buffer for one side (video or text) of the validation embeddings.
+
+    ``append(batch)`` copies a [b, D] batch into the preallocated [capacity, D] buffer (grown geometrically if needed);
+    ``local()`` is the filled view; ``gather()`` is the global [N, D] tensor on every rank (rank-major, ragged sizes
+    allowed)."""
+
+    def __init__(self, dim: int, capacity: int = 4096, dtype: torch.dtype = torch.float32, device="cuda"):
+        self.buf = torch.empty((max(1, capacity), dim), dtype=dtype, device=device)
+        self.n = 0
+
+    def append(self, batch: torch.Tensor) -> None:
+        b = batch.shape[0]
+        if self.n + b > self.buf.shape[0]:
+            grown = torch.empty((max(2 * self.buf.shape[0], self.n + b), self.buf.shape[1]), dtype=self.buf.dtype,
+                                device=self.buf.device)
+            grown[:self.n] = self.buf[:self.n]
+            self.buf = grown
+        self.buf[self.n:self.n + b] = batch.detach().to(device=self.buf.device, dtype=self.buf.dtype)
+        self.n += b
+
+    def reset(self) -> None:
+        self.n = 0
+
+    def local(self) -> torch.Tensor:
+        return self.buf[:self.n]
+
+    def gather(self, group=None) -> torch.Tensor:
+        return gather_tensor_along_batch(self.local(), group=group)
+
+
+def epoch_end_retrieval_metrics(video: EmbeddingStore, text: EmbeddingStore, ground_truth_indices: torch.Tensor,
+                                k_values=(1, 5, 10, 50), group=None) -> Dict[str, float]:
+    """Gathers both stores across ranks and runs the streaming retrieval metrics on the device-resident result (every
+    rank obtains the same dict; the text database is sharded across ranks inside ``compute_metrics_streaming``)."""
+    from .retrieval_metrics_streaming import compute_metrics_streaming
+    v = video.gather(group)
+    t = text.gather(group)
+    gt = gather_tensor_along_batch(ground_truth_indices, group=group)
+    return compute_metrics_streaming(v, t, gt, k_values=list(k_values), group=group)

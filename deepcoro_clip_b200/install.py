@@ -116,4 +116,14 @@ def install(reference_root: str | None = None, semantics: str = "main", losses: 
                     if hasattr(mod, n):
                         setattr(mod, n, getattr(retrieval_metrics, n))
                 report["metrics"].append(modname)
+        # epoch-end ragged gather: the runner method keeps its signature (self, local_tensor, world_size)
+        runner_mod = sys.modules.get("runners.video_constrative_learning_runner")
+        cls = getattr(runner_mod, "VideoContrastiveLearningRunner", None) if runner_mod is not None else None
+        if cls is not None and hasattr(cls, "_gather_tensor_along_batch"):
+            from .embedding_store import gather_tensor_along_batch
+
+            def _gather(self, local_tensor, world_size):
+                return gather_tensor_along_batch(local_tensor, world_size)
+            cls._gather_tensor_along_batch = _gather
+            report["metrics"].append("VideoContrastiveLearningRunner._gather_tensor_along_batch")
     return report

@@ -124,3 +124,41 @@ def test_two_rank_gloo_siglip_variant_pieces():
     out = mgr.dict()
     mp.spawn(_worker_siglip_pieces, args=(world, port, out), nprocs=world, join=True)
     assert len(out) == world and out[0] == out[1]
+
+
+def _worker_ragged_gather(rank, world, port, out):
+    """the ragged cross-rank gather of validation embeddings equals the reference's
+    _gather_tensor_along_batch semantics (rank-major concatenation of the valid rows), 1-D and 2-D, empty ranks too."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deepcoro_clip_b200.embedding_store import EmbeddingStore, gather_tensor_along_batch
+        sizes = [5, 3]
+        full = torch.arange(sum(sizes) * 4, dtype=torch.float32).view(sum(sizes), 4)
+        lo = sum(sizes[:rank])
+        mine = full[lo:lo + sizes[rank]]
+        assert torch.equal(gather_tensor_along_batch(mine), full)
+        assert torch.equal(gather_tensor_along_batch(mine[:, 0].contiguous()), full[:, 0])
+        # equal sizes: no compaction step; an empty rank
+        assert torch.equal(gather_tensor_along_batch(full[3 * rank:3 * rank + 3]), full[:6])
+        e = gather_tensor_along_batch(full[:4] if rank == 0 else full[:0])
+        assert torch.equal(e, full[:4])
+        store = EmbeddingStore(dim=4, capacity=2, device="cpu")
+        for i in range(0, sizes[rank], 2):                      # appended batch by batch, buffer grows
+            store.append(mine[i:i + 2])
+        assert store.n == sizes[rank] and torch.equal(store.local(), mine)
+        assert torch.equal(store.gather(), full)
+        store.reset()
+        assert store.local().shape == (0, 4)
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_ragged_embedding_gather():
+    world = 2
+    port = 33000 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_ragged_gather, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == world
