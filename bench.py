@@ -127,11 +127,11 @@ def retrieval_leg(dev, world, rank):
     """recall@1/5/10 + MRR over the 203,808 x 32,473 x 512 sweep (BASELINE config 4): exact-grid embeddings (entries
     k/128, exact in bf16, every dot product exact in fp32 in any order), text database sharded by rows across ranks.
     Timed through the public API (operand packing, tensor-core ground-truth similarity, sweep, rank counts all-reduced,
-    recall hits, MRR on the host in float64)."""
+    recall hits and the fp64 MRR sum on the device, results read back every sweep)."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_recall_at_k_streaming
+    from deepcoro_clip_b200.retrieval_metrics_streaming import compute_recall_at_k_streaming, mrr_sum_from_counts
     Nv, M, D = 203808, 32473, 512
     g = torch.Generator(device=dev).manual_seed(3)
     v = torch.randint(-127, 128, (Nv, D), device=dev, generator=g).float() / 128
@@ -141,8 +141,7 @@ def retrieval_leg(dev, world, rank):
     def once():
         keep = []
         r = compute_recall_at_k_streaming(v, t, gt, k_values=[1, 5, 10], precision="bf16", _counts_out=keep)
-        ranks = keep[0].cpu().numpy().astype(np.float64) + 1.0
-        r["MRR_V2T"] = float(np.cumsum(1.0 / ranks)[-1] / Nv)
+        r["MRR_V2T"] = float(mrr_sum_from_counts(keep[0], M).item() / Nv)
         return r
     once()
     torch.cuda.synchronize()

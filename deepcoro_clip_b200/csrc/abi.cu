@@ -176,6 +176,11 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                     negative_weight, c, gnorm, hp, use_pos_weights, auto_balance, dV, lddv, dT, lddt, acc, S(stream));
 }
 
+int b200clip_mrr_from_counts(const int32_t* counts, int rows, int n_bins, int32_t* hist, double* out, void* stream) {
+  if (!counts || !hist || !out) return B2_EINVAL;
+  return mrr_from_counts(counts, rows, n_bins, hist, out, S(stream));
+}
+
 int b200clip_dense_gt_ranks(const void* sim, int dtype, int64_t ld, int n_rows, int n_cols, const int32_t* gt, int G,
                             int sanitize, int32_t* ranks, void* stream) {
   if (!sim || !gt || !ranks) return B2_EINVAL;

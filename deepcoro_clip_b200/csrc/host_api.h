@@ -99,6 +99,7 @@ int retrieval_sweep(const void* V, const void* T, int Nv, int Mt, int Kp, int ld
 int topk_merge(const float* ps, const int* pi, int rows, int cand, int k, float* out_s, long long* out_i,
                cudaStream_t s);
 int recall_hits(const int* counts, int rows, const int* kvals, int nk, unsigned long long* hits, cudaStream_t s);
+int mrr_from_counts(const int* counts, int rows, int n_bins, int* hist, double* out, cudaStream_t s);
 
 // dense_metrics.cu
 int dense_gt_ranks(const void* sim, int dtype, long long ld, int N, int M, const int* gt, int G, int sanitize,

@@ -123,6 +123,16 @@ def compute_recall_at_k_streaming(video_features: torch.Tensor, text_features: t
     return _recall_from_operands(vop, top, ground_truth_indices, k_values, use_ddp, group, _counts_out)
 
 
+def mrr_sum_from_counts(counts: torch.Tensor, n_texts: int) -> torch.Tensor:
+    """sum_i 1 / (counts[i] + 1) as a 0-d float64 device tensor (deterministic histogram-order fp64 sum; no host pass over
+    the rows — the host loop of the reference costs 2.6 ms for 203,808 rows even vectorised with numpy)."""
+    dev = counts.device
+    hist = torch.zeros(max(1, int(n_texts)), dtype=torch.int32, device=dev)
+    out = torch.empty(1, dtype=torch.float64, device=dev)
+    call("mrr_from_counts", counts, counts.numel(), hist.numel(), hist, out, stream_ptr(dev))
+    return out[0]
+
+
 def _recall_from_operands(vop, top, gt, k_values, use_ddp, group, counts_out=None) -> Dict[str, float]:
     dev = vop.device
     N, M = vop.shape[0], top.shape[0]
@@ -150,9 +160,8 @@ def compute_metrics_streaming(video_features: torch.Tensor, text_features: torch
     keep: list = []
     metrics = _recall_from_operands(vop, top, ground_truth_indices, k_values, use_ddp, group, keep)
     counts = keep[0]
-    # MRR: host double accumulation in row order (reference :162-166, :172)
-    ranks = counts.cpu().numpy().astype(np.float64) + 1.0
-    metrics["MRR_V2T"] = float(np.cumsum(1.0 / ranks)[-1] / N) if N else 0.0
+    # MRR = mean_i 1 / rank_i (reference :162-172), summed on the device over the rank histogram in fp64
+    metrics["MRR_V2T"] = float(mrr_sum_from_counts(counts, M).item() / N) if N else 0.0
     # alignment = mean_i vhat_i . that_gt(i)  (:175-190)
     gt64 = ground_truth_indices.to(device=dev, dtype=torch.int64).contiguous()
     sg = torch.empty(N, dtype=torch.float32, device=dev)

@@ -205,6 +205,12 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                         float gnorm, int hp, int use_pos_weights, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc,
                         void* stream);
 
+/* MRR numerator: out[0] = sum_i 1 / (counts[i] + 1) in fp64 through the rank histogram (hist [n_bins] int32, zeroed by
+ * the caller; n_bins > max count, i.e. the number of texts): sum_r hist[r] / (r + 1) in increasing-rank order with a fixed
+ * reduction tree — deterministic, independent of row order and sharding. Replaces the per-row Python loop of
+ * compute_metrics_streaming (utils/retrieval_metrics_streaming.py:162-172). */
+int b200clip_mrr_from_counts(const int32_t* counts, int rows, int n_bins, int32_t* hist, double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense multi-label retrieval metrics over a materialised similarity matrix. Replaces the argsort + Python loops of
  * compute_recall_at_k / compute_mrr / compute_ndcg_at_k / compute_median_rank / compute_map
