@@ -158,6 +158,23 @@ int b200clip_siglip_entropy_coef(const double* stats_all, int W, int B_global, i
   return siglip_entropy_coef(stats_all, W, B_global, T, weight, threshold, dyn, out, S(stream));
 }
 
+int b200clip_siglip_combine(const double* acc, double wn_c, double* red, void* stream) {
+  if (!acc || !red) return B2_EINVAL;
+  return siglip_combine(acc, wn_c, red, S(stream));
+}
+
+int b200clip_siglip_loss_out(const double* red, const int32_t* overflow, const float* ent, float* loss_out, float* diag,
+                             void* stream) {
+  if (!red || !loss_out) return B2_EINVAL;
+  return siglip_loss_out(red, overflow, ent, loss_out, diag, S(stream));
+}
+
+int b200clip_siglip_scalar_grads(const double* red, const float* dyn, const float* grad_out, float* dlog_temp,
+                                 float* dbias, void* stream) {
+  if (!red || !dyn || !grad_out) return B2_EINVAL;
+  return siglip_scalar_grads(red, dyn, grad_out, dlog_temp, dbias, S(stream));
+}
+
 int b200clip_siglip_compact(const float* pos_mask, int64_t ld_mask, const float* pos_weights, int64_t ld_weights, int B,
                             int T, int cap, int32_t* col, float* y, float* w, int32_t* cnt, float* ysum,
                             int32_t* overflow, void* stream) {

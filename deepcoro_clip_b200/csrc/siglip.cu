@@ -173,6 +173,41 @@ __global__ void siglip_entropy_coef_kernel(const double* __restrict__ stats_all,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// scalar tails (one thread each; they replace ~20 single-element PyTorch launches per step):
+//   siglip_combine : red = {loss, dbias, sum G*s} from the dense sums acc[0..2] and the positive corrections acc[4..6]
+//   siglip_loss_out: loss_out = red[0] (+ NaN when a row overflowed its positive list) (+ entropy penalty ent[5]);
+//                    diag (optional, 7 floats) = {ent[0..5], bce loss} for get_entropy_diagnostics()
+//   siglip_scalar_grads: dlog_temp = -red[2] / tau * [tau not clamped] * grad_out ; dbias = red[1] * grad_out
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void siglip_combine_kernel(const double* __restrict__ acc, double wn_c, double* __restrict__ red) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  red[0] = wn_c * acc[1] + acc[4];
+  red[1] = acc[2] + acc[5];
+  red[2] = acc[0] + acc[6];
+}
+__global__ void siglip_loss_out_kernel(const double* __restrict__ red, const int* __restrict__ overflow,
+                                       const float* __restrict__ ent, float* __restrict__ loss_out,
+                                       float* __restrict__ diag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double loss = red[0];
+  if (overflow && overflow[0] > 0) loss = nan("");
+  if (diag) {
+    for (int i = 0; i < 6; ++i) diag[i] = ent ? ent[i] : 0.f;
+    diag[6] = (float)loss;
+  }
+  if (ent) loss += (double)ent[5];
+  loss_out[0] = (float)loss;
+}
+__global__ void siglip_scalar_grads_kernel(const double* __restrict__ red, const float* __restrict__ dyn,
+                                           const float* __restrict__ gmul, float* __restrict__ dlt,
+                                           float* __restrict__ dbias) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double g = (double)gmul[0];
+  if (dlt) dlt[0] = (float)(-(red[2] * (double)dyn[2]) * (double)dyn[7] * g);
+  if (dbias) dbias[0] = (float)(red[1] * g);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // positive-list compaction: one warp per video row scans pos_mask[row, :T] (and pos_weights) once.
 //   lists: col[row][cap] int32, y[row][cap] (= clamp(mask,0,1)), pw[row][cap] (raw pos_weights or 1)
 //   cnt[row] = number of entries, ysum[row] = sum_j y_ij (auto_balance), overflow flag if a row has > cap positives
@@ -401,6 +436,21 @@ int siglip_entropy_coef(const double* stats_all, int W, int Bg, int T, float wei
                         cudaStream_t s) {
   if (W <= 0 || Bg <= 0 || T <= 0) return B2_EINVAL;
   siglip_entropy_coef_kernel<<<1, 32, 0, s>>>(stats_all, W, Bg, T, weight, thr, dyn, out);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int siglip_combine(const double* acc, double wn_c, double* red, cudaStream_t s) {
+  siglip_combine_kernel<<<1, 32, 0, s>>>(acc, wn_c, red);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+int siglip_loss_out(const double* red, const int* overflow, const float* ent, float* loss_out, float* diag,
+                    cudaStream_t s) {
+  siglip_loss_out_kernel<<<1, 32, 0, s>>>(red, overflow, ent, loss_out, diag);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+int siglip_scalar_grads(const double* red, const float* dyn, const float* gmul, float* dlt, float* dbias,
+                        cudaStream_t s) {
+  siglip_scalar_grads_kernel<<<1, 32, 0, s>>>(red, dyn, gmul, dlt, dbias);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -378,21 +378,24 @@ class _SigLIPFn(torch.autograd.Function):
         ops.call("siglip_pos", vop, vop.stride(0), top, top.stride(0), K, Kp, D, K - Kp, B, T, cap, col, yv, wv, cnt,
                  ysum, dyn, float(wp), float(wn), float(c), float(gn), int(x3), flags, int(cfg["auto_balance"]), dVh,
                  D if dVh is not None else 0, dTh, D if dTh is not None else 0, acc[4:7], st)
-        # local sums -> global (every rank returns the full loss, reference DDP semantics)
-        red = torch.stack([wn * c * acc[1] + acc[4], acc[2] + acc[5], acc[0] + acc[6]])   # loss, dbias, sum G*s
+        # local sums -> global (every rank returns the full loss, reference DDP semantics); scalar tails on the device
+        red = torch.empty(3, dtype=torch.float64, device=dev)           # loss, dbias, sum G*s
+        ops.call("siglip_combine", acc, float(wn * c), red, st)
         if W > 1:
             dist.all_reduce(red, group=cfg["group"])
             if dTh is not None:
                 dist.all_reduce(dTh, group=cfg["group"])      # text is replicated: every rank gets the full text grad
             dist.all_reduce(overflow, group=cfg["group"])
-        loss = red[0] + torch.where(overflow[0] > 0, float("nan"), 0.0)    # never silently drop positives
-        if ent is not None:
-            if cfg["ent_holder"] is not None:
-                cfg["ent_holder"]["raw"] = torch.cat([ent[:6], loss.float().reshape(1)])
-            loss = loss + ent[5].double()
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        diag = None
+        if ent is not None and cfg["ent_holder"] is not None:
+            diag = torch.empty(7, dtype=torch.float32, device=dev)
+        ops.call("siglip_loss_out", red, overflow, ent, loss, diag, st)   # NaN on overflow: never silently drop positives
+        if diag is not None:
+            cfg["ent_holder"]["raw"] = diag
         ctx.save_for_backward(video, text, vinv, tinv, dyn, dVh, dTh, red)
         ctx.meta = (log_temp.shape, log_temp.dtype, None if bias is None else (bias.shape, bias.dtype))
-        return loss.float()
+        return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -404,11 +407,17 @@ class _SigLIPFn(torch.autograd.Function):
             dV = ops.l2norm_backward(dVh, video, vinv, dev_gmul=gmul).to(video.dtype)
         if ctx.needs_input_grad[1]:
             dT = ops.l2norm_backward(dTh, text, tinv, dev_gmul=gmul).to(text.dtype)
-        if ctx.needs_input_grad[2]:
-            # d loss / d log_temp = -sum G (R - b) = -(sum G*s)/tau ; zero while the tau clamp is active
-            dLT = (-(red[2] * dyn[2].double()) * dyn[7].double() * gmul.double()).to(lt_dtype).reshape(lt_shape)
-        if bmeta is not None and ctx.needs_input_grad[3]:
-            dB = (red[1] * gmul.double()).to(bmeta[1]).reshape(bmeta[0])
+        need_lt = ctx.needs_input_grad[2]
+        need_b = bmeta is not None and ctx.needs_input_grad[3]
+        if need_lt or need_b:
+            # d loss / d log_temp = -sum G (R - b) = -(sum G*s)/tau (zero while the tau clamp is active); dbias = sum G
+            sg = torch.empty(2, dtype=torch.float32, device=video.device)
+            ops.call("siglip_scalar_grads", red, dyn, gmul, sg[0:1] if need_lt else None, sg[1:2] if need_b else None,
+                     ops.stream_ptr(video.device))
+            if need_lt:
+                dLT = (sg[0:1] if lt_dtype == torch.float32 else sg[0:1].to(lt_dtype)).reshape(lt_shape)
+            if need_b:
+                dB = (sg[1:2] if bmeta[1] == torch.float32 else sg[1:2].to(bmeta[1])).reshape(bmeta[0])
         return dV, dT, dLT, dB, None, None, None
 
 
