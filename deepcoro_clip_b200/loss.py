@@ -316,14 +316,24 @@ class _SigLIPFn(torch.autograd.Function):
         wp, wn = cfg["positive_weight"], cfg["negative_weight"]
         gn = 1.0 / ((wn if wn > 0.0 else 1.0) * c)     # the dense G is fed to the tensor core as G * gn = O(1)
 
+        need_grad = any(ctx.needs_input_grad[:4])
+        # one zeroed arena (128-byte header keeps the gradient buffers 16-byte aligned for the vectorised reductions):
+        # fp64 sums [8] | overflow flag | pad | dVhat [B, D] | dThat [T, D]
+        nz = (B * D + T * D) if need_grad else 0
+        arena = torch.zeros(32 + nz, dtype=torch.float32, device=dev)
+        acc = arena[:16].view(torch.float64)     # [0] sum g*s [1] sum softplus [2] sum g | [4..6] positives
+        overflow = arena[16:17].view(torch.int32)
+        dVh = dTh = None
+
         # ---- positives: one streaming pass over the dense mask / weights ----
         cap = cfg["max_positives"]
-        col = torch.empty((B, cap), dtype=torch.int32, device=dev)
-        yv = torch.empty((B, cap), dtype=torch.float32, device=dev)
-        wv = torch.empty((B, cap), dtype=torch.float32, device=dev)
-        cnt = torch.empty(B, dtype=torch.int32, device=dev)
-        ysum = torch.empty(B, dtype=torch.float32, device=dev)
-        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        # one allocation for the compacted positive lists: col | y | w  [B, cap] each, then cnt [B], ysum [B]
+        lists = torch.empty(3 * B * cap + 2 * B, dtype=torch.int32, device=dev)
+        col = lists[:B * cap].view(B, cap)
+        yv = lists[B * cap:2 * B * cap].view(torch.float32).view(B, cap)
+        wv = lists[2 * B * cap:3 * B * cap].view(torch.float32).view(B, cap)
+        cnt = lists[3 * B * cap:3 * B * cap + B]
+        ysum = lists[3 * B * cap + B:].view(torch.float32)
         pm = pw = None
         if pos_mask is not None:
             pm = pos_mask.detach().float()
@@ -363,12 +373,9 @@ class _SigLIPFn(torch.autograd.Function):
                      float(cfg["entropy_threshold"]), dyn, ent, st)
             mode = BW_SIGLIP_ENT
 
-        need_grad = any(ctx.needs_input_grad[:4])
-        acc = torch.zeros(8, dtype=torch.float64, device=dev)   # [0] sum g*s [1] sum softplus [2] sum g | [4..6] positives
-        dVh = dTh = None
         if need_grad:
-            dVh = torch.zeros((B, D), dtype=torch.float32, device=dev)
-            dTh = torch.zeros((T, D), dtype=torch.float32, device=dev)
+            dVh = arena[32:32 + B * D].view(B, D)
+            dTh = arena[32 + B * D:].view(T, D)
             ops.logits_bwd(mode, vop, top, B, T, K, Kp, D, dyn, rowvec, None, dVh, acc[0:4], wneg_c=wn * c, gnorm=gn,
                            hp=x3)
             ops.logits_bwd(mode, top, vop, T, B, K, Kp, D, dyn, None, rowvec, dTh, None, wneg_c=wn * c, gnorm=gn, hp=x3)
