@@ -208,3 +208,32 @@ def test_attention_pool_training_dropout(dtype, D, N):
     mod.eval()
     o1 = mod(x.detach()); o2 = mod(x.detach())
     assert torch.equal(o1, o2)
+
+
+def test_attention_pool_cuda_graph_callable():
+    """The module's forward + backward are capturable (no host sync, no stream-unsafe call inside the custom ops):
+    torch.cuda.make_graphed_callables(AttentionPool) reproduces the eager module. This is the recommended way to
+    remove the per-call host work of the [B, D] projection tails around the streaming kernel."""
+    import copy
+    from deepcoro_clip_b200.attention_pool import AttentionPool
+    torch.manual_seed(5)
+    pool = AttentionPool(512, 8).to(DEV)
+    ref = copy.deepcopy(pool)
+    xs = torch.randn(4, 393, 512, device=DEV).bfloat16().requires_grad_(True)
+    graphed = torch.cuda.make_graphed_callables(pool, (xs,))
+    for trial in range(2):
+        x = torch.randn(4, 393, 512, device=DEV).bfloat16()
+        xg = x.clone().requires_grad_(True)
+        xe = x.clone().requires_grad_(True)
+        up = torch.randn(4, 512, device=DEV).bfloat16()
+        for p in list(pool.parameters()) + list(ref.parameters()):
+            p.grad = None
+        yg = graphed(xg)
+        yg.backward(up)
+        ye = ref(xe)
+        ye.backward(up)
+        torch.cuda.synchronize()
+        assert torch.equal(yg, ye)
+        assert float((xg.grad.float() - xe.grad.float()).abs().max()) <= 1e-2 * float(xe.grad.float().abs().max())
+        for (n, a), (_, b) in zip(pool.named_parameters(), ref.named_parameters()):
+            assert float((a.grad - b.grad).abs().max()) <= 1e-4 * float(b.grad.abs().max()) + 1e-8, n

@@ -54,6 +54,20 @@ params = [p for p in pool.parameters() if p.requires_grad]
 ms_b = timeit(lambda: torch.autograd.grad(y, [x] + params, gy, retain_graph=True, allow_unused=True))
 res["attnpool_bwd"] = {"ms": ms_b, "algorithmic_bytes": 3 * bx, "GBps": 3 * bx / ms_b / 1e6, "frac_hbm": 3 * bx / ms_b / 1e6 / HBM,
                        "note": "includes the second pass over x for d(query) (4*bx executed) and the dense [B,D] tails"}
+# ---- the same module forward + backward replayed from a CUDA graph (torch.cuda.make_graphed_callables) ----
+import copy
+gpool = torch.cuda.make_graphed_callables(copy.deepcopy(pool), (x.detach().clone().requires_grad_(True),))
+xg = x.detach().clone().requires_grad_(True)
+def fb_graphed():
+    yy = gpool(xg)
+    yy.backward(gy)
+def fb_eager():
+    yy = pool(x)
+    yy.backward(gy)
+ms_fb_g = timeit(fb_graphed)
+ms_fb_e = timeit(fb_eager)
+res["attnpool_fwd_bwd_module"] = {"eager_ms": ms_fb_e, "cuda_graph_ms": ms_fb_g, "algorithmic_bytes": 4 * bx,
+                                  "cuda_graph_GBps": 4 * bx / ms_fb_g / 1e6, "cuda_graph_frac_hbm": 4 * bx / ms_fb_g / 1e6 / HBM}
 mask = torch.rand(Bp, Np, device=dev) < 0.1
 with torch.no_grad():
     ms_m = timeit(lambda: pool(x, mask))
