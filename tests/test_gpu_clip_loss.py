@@ -121,7 +121,7 @@ def test_cpu_tensor_is_rejected():
 
 
 def test_graphed_step_matches_eager():
-    """GraphedLossStep (forward + backward captured in a CUDA graph) reproduces the eager module bit for bit on new
+    """GraphedLossStep (forward + backward captured in a CUDA graph) reproduces the eager module (up to the order of fp32 atomic sums) on new
     inputs copied into its static buffers, for several replays."""
     import math
     from deepcoro_clip_b200 import GraphedLossStep
@@ -138,7 +138,8 @@ def test_graphed_step_matches_eager():
         le_loss = mod(video_features=ve, text_features=te, log_temp=le)
         le_loss.backward()
         torch.cuda.synchronize()
-        assert loss.item() == le_loss.item()
+        # row / column sums are accumulated with fp32 atomics: equal up to summation order, run to run
+        assert abs(loss.item() - le_loss.item()) <= 1e-6 * abs(le_loss.item())
         # dX accumulates with red.global.add in a data-dependent order: equal up to fp32 summation order
         assert float((dv - ve.grad).abs().max()) <= 2e-5 * float(ve.grad.abs().max())
         assert float((dt - te.grad).abs().max()) <= 2e-5 * float(te.grad.abs().max())
