@@ -193,6 +193,11 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                     negative_weight, c, gnorm, hp, use_pos_weights, auto_balance, dV, lddv, dT, lddt, acc, S(stream));
 }
 
+int b200clip_inexact_bf16(const void* x, int dtype, int64_t ld, int rows, int dim, int32_t* flag, void* stream) {
+  if (!x || !flag) return B2_EINVAL;
+  return inexact_bf16(x, dtype, (long long)ld, rows, dim, flag, S(stream));
+}
+
 int b200clip_mrr_from_counts(const int32_t* counts, int rows, int n_bins, int32_t* hist, double* out, void* stream) {
   if (!counts || !hist || !out) return B2_EINVAL;
   return mrr_from_counts(counts, rows, n_bins, hist, out, S(stream));

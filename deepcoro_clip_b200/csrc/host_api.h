@@ -13,6 +13,7 @@ int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, co
                int odtype, long ldox, const float* oinv, const void* ohi, int ldohi, const float* dc,
                const float* usum, float gscale, float ucoef, const float* dev_omul, const float* dev_gmul, int rows,
                int dim, float* dx, long lddx, cudaStream_t s);
+int inexact_bf16(const void* x, int dtype, long long ld, int rows, int dim, int* flag, cudaStream_t s);
 int colsum_bf16(const void* xh, int ld, int rows, int dim, float* out, cudaStream_t s);
 int gather_rows_bf16(const void* src, int lds, const long long* idx, int rows, int src_rows, int K, void* dst, int ldd,
                      cudaStream_t s);

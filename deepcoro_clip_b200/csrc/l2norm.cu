@@ -157,10 +157,40 @@ gather_rows_bf16_kernel(const uint4* __restrict__ src, int lds16, const long lon
     dst[(size_t)warp * ldd16 + c] = ok ? src[(size_t)r * lds16 + c] : make_uint4(0u, 0u, 0u, 0u);
 }
 
+// flag[0] = 1 if any element of the row-major [rows, dim] matrix is not exactly representable in bf16 (one streaming
+// read, grid-stride, no temporaries): the test behind precision="auto" of the streaming metrics. fp16 / fp32 inputs;
+// a bf16 input is exact by construction (the host does not launch this for it).
+template <typename T>
+__global__ void __launch_bounds__(256)
+inexact_bf16_kernel(const T* __restrict__ x, long long ld, int rows, int dim, int* __restrict__ flag) {
+  bool bad = false;
+  const long long total = (long long)rows * dim;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total && !bad; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / dim;
+    const float v = to_f32<T>(x[r * ld + (i - r * dim)]);
+    bad = __bfloat162float(__float2bfloat16_rn(v)) != v;                 // NaN compares unequal: counted as inexact
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
+}
+
 }  // namespace b2
 
 namespace b2host {
 using namespace b2;
+
+int inexact_bf16(const void* x, int dtype, long long ld, int rows, int dim, int* flag, cudaStream_t s) {
+  if (rows <= 0 || dim <= 0) return B2_EINVAL;
+  const long long total = (long long)rows * dim;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  switch (dtype) {
+    case 0: inexact_bf16_kernel<float><<<(int)blocks, 256, 0, s>>>((const float*)x, ld, rows, dim, flag); break;
+    case 2: inexact_bf16_kernel<__half><<<(int)blocks, 256, 0, s>>>((const __half*)x, ld, rows, dim, flag); break;
+    default: return B2_EINVAL;
+  }
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
 
 int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out, int ldo, int Kp, int split3_role,
                float* inv_norm, float* xhat_f32, int ldh, int normalize, cudaStream_t s) {

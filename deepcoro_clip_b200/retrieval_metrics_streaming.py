@@ -26,13 +26,25 @@ from . import dist_plan, ops
 from ._lib import call, stream_ptr
 
 
-def _exact_in_bf16(x: torch.Tensor) -> bool:
-    return bool((x.float() == x.bfloat16().float()).all().item())
+def _exact_in_bf16(*xs: torch.Tensor) -> bool:
+    """True when every element of every tensor is exactly representable in bf16 (one streaming kernel pass per tensor and
+    ONE host read for all of them; bf16 inputs are exact by construction)."""
+    from ._lib import DTYPE_CODE, i64
+    flag = None
+    for x in xs:
+        if x.dtype == torch.bfloat16:
+            continue
+        if x.dim() != 2 or x.dtype not in DTYPE_CODE or x.stride(1) != 1:
+            x = x.float().reshape(x.shape[0], -1).contiguous() if x.dim() >= 1 else x.float().reshape(1, 1)
+        if flag is None:
+            flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+        call("inexact_bf16", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), x.shape[0], x.shape[1], flag, stream_ptr(x.device))
+    return True if flag is None else flag.item() == 0
 
 
 def _operands(video, text, normalize: bool, precision: str):
     if precision == "auto":
-        x3 = normalize or not (_exact_in_bf16(video) and _exact_in_bf16(text))
+        x3 = normalize or not _exact_in_bf16(video, text)
     elif precision in ("bf16", "bf16x3"):
         x3 = precision == "bf16x3"
     else:

@@ -218,6 +218,11 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                         float gnorm, int hp, int use_pos_weights, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc,
                         void* stream);
 
+/* flag[0] = 1 (never cleared: caller zeroes) if any element of the row-major [rows, dim] fp32 (dtype 0) / fp16 (dtype 2)
+ * matrix is not exactly representable in bf16 — one streaming read, no temporaries. Decides precision="auto" of the
+ * streaming metrics (exact-grid evaluation embeddings run on plain bf16 operands and stay bit-exact). */
+int b200clip_inexact_bf16(const void* x, int dtype, int64_t ld, int rows, int dim, int32_t* flag, void* stream);
+
 /* MRR numerator: out[0] = sum_i 1 / (counts[i] + 1) in fp64 through the rank histogram (hist [n_bins] int32, zeroed by
  * the caller; n_bins > max count, i.e. the number of texts): sum_r hist[r] / (r + 1) in increasing-rank order with a fixed
  * reduction tree — deterministic, independent of row order and sharding. Replaces the per-row Python loop of

@@ -140,3 +140,21 @@ def test_duplicate_texts_tie_exactly_after_normalisation():
     trip = base < 25
     assert (i[trip] == np.stack([base[trip], base[trip] + 100, base[trip] + 300], 1)).all()
     assert (i[~trip][:, :2] == np.stack([base[~trip], base[~trip] + 100], 1)).all()
+
+
+def test_exact_in_bf16_probe():
+    """precision="auto": the one-pass device probe agrees with the definition (x == bf16(x) everywhere) for fp32 / fp16 /
+    bf16 inputs, strided rows, a single inexact element anywhere, and NaN (inexact)."""
+    from deepcoro_clip_b200.retrieval_metrics_streaming import _exact_in_bf16
+    from oracle import retrieval_oracle as ro
+    g = torch.tensor(ro.exact_grid_embeddings(3000, 520, 9), device="cuda:0")           # entries k/128: exact in bf16
+    assert _exact_in_bf16(g) and _exact_in_bf16(g, g[:7]) and _exact_in_bf16(g.bfloat16())
+    assert _exact_in_bf16(g.half()) and _exact_in_bf16(g[:, :300]) and _exact_in_bf16(g.double())
+    for pos in ((0, 0), (2999, 519), (1234, 77)):
+        h = g.clone()
+        h[pos] += 1e-4
+        assert not _exact_in_bf16(h) and not _exact_in_bf16(g, h) and not _exact_in_bf16(h[:, :520:1])
+    h = g.clone()
+    h[5, 5] = float("nan")
+    assert not _exact_in_bf16(h)
+    assert not _exact_in_bf16(torch.randn(64, 64, device="cuda:0"))
