@@ -4,7 +4,8 @@
  * Drop-in boundary for the ONE hot path of HeartWise-AI/DeepCORO_CLIP named in BASELINE.json:
  * the CLIP / SigLIP losses (utils/loss), the streaming retrieval metrics
  * (utils/retrieval_metrics_streaming.py), Rope3D (models/rope_3d.py), AttentionPool
- * (models/attention_pool.py) and the multi-view query pool (models/video_aggregator.py:131-158).
+ * (models/attention_pool.py) and the multi-view query pool (models/video_aggregator.py:131-158); widened to the
+ * dense multi-label retrieval metrics (utils/retrieval_metrics.py).
  *
  * Conventions
  *  - Every pointer is a DEVICE pointer unless its name ends in `_host`.
