@@ -9,12 +9,13 @@ from .loss import (CLIPLoss, ContrastiveLoss, ContrastiveLossDDP, InfoNCELoss, S
                    SigLIP2MultiPositiveBCELoss, SigLIPLoss, SiglipLoss, SiglipLossDDP, SiglipPairwiseFeatureLoss,
                    clip_loss)
 from . import retrieval_metrics
+from .multipos_loss import MultiPositiveInfoNCELoss, WeightedSigLIPLoss
 from .retrieval_metrics_streaming import (compute_metrics_streaming, compute_recall_at_k_streaming, streaming_topk)
 from .rope_3d import Rope3D, apply_rope_qk
 from .video_aggregator import EnhancedVideoAggregator, query_pool
 
 __all__ = ["AttentionPool", "CLIPLoss", "GraphedLossStep", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EmbeddingStore", "EnhancedVideoAggregator",
-           "InfoNCELoss", "Rope3D", "SigLIP2BCELoss", "SigLIP2BCELossDDP", "SigLIP2MultiPositiveBCELoss", "SigLIPLoss",
-           "SiglipLoss", "SiglipLossDDP", "SiglipPairwiseFeatureLoss", "apply_rope_qk", "clip_loss",
+           "InfoNCELoss", "MultiPositiveInfoNCELoss", "Rope3D", "SigLIP2BCELoss", "SigLIP2BCELossDDP", "SigLIP2MultiPositiveBCELoss", "SigLIPLoss",
+           "SiglipLoss", "SiglipLossDDP", "SiglipPairwiseFeatureLoss", "WeightedSigLIPLoss", "apply_rope_qk", "clip_loss",
            "compute_metrics_streaming", "compute_recall_at_k_streaming", "epoch_end_retrieval_metrics", "gather_tensor_along_batch", "install", "loss_table", "query_pool",
            "streaming_topk"]

@@ -193,6 +193,24 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                     negative_weight, c, gnorm, hp, use_pos_weights, auto_balance, dV, lddv, dT, lddt, acc, S(stream));
 }
 
+int b200clip_multipos_workspace_bytes(int n_rows, int n_cols) { return multipos_workspace_bytes(n_rows, n_cols); }
+
+int b200clip_multipos_fwd(const float* logits, int64_t ld_logits, const float* pos_weights, const float* pos_mask,
+                          int64_t ld_w, int n_rows, int n_cols, int mode, float eps, int reduce_sum, float* rstat,
+                          float* cstat, float* coef, float* loss_out, void* workspace, void* stream) {
+  if (!logits || !rstat || !cstat || !coef || !loss_out || !workspace) return B2_EINVAL;
+  return multipos_fwd(logits, (long long)ld_logits, pos_weights, pos_mask, (long long)ld_w, n_rows, n_cols, mode, eps,
+                      reduce_sum, rstat, cstat, coef, loss_out, workspace, S(stream));
+}
+
+int b200clip_multipos_bwd(const float* logits, int64_t ld_logits, const float* pos_weights, const float* pos_mask,
+                          int64_t ld_w, int n_rows, int n_cols, const float* rstat, const float* cstat, const float* coef,
+                          const float* grad_out, float* dlogits, int64_t ld_d, void* stream) {
+  if (!logits || !rstat || !cstat || !coef || !grad_out || !dlogits) return B2_EINVAL;
+  return multipos_bwd(logits, (long long)ld_logits, pos_weights, pos_mask, (long long)ld_w, n_rows, n_cols, rstat, cstat,
+                      coef, grad_out, dlogits, (long long)ld_d, S(stream));
+}
+
 int b200clip_inexact_bf16(const void* x, int dtype, int64_t ld, int rows, int dim, int32_t* flag, void* stream) {
   if (!x || !flag) return B2_EINVAL;
   return inexact_bf16(x, dtype, (long long)ld, rows, dim, flag, S(stream));

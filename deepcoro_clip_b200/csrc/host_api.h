@@ -114,6 +114,15 @@ int dense_rank_metrics(const int* ranks, const int* gsize, int N, int G, int M, 
                        const int* ndcg_k, int nnk, int* best, double* rr, double* ap, unsigned char* hit, double* ndcg,
                        cudaStream_t s);
 
+// multipos.cu
+int multipos_workspace_bytes(int N, int M);
+int multipos_fwd(const float* L, long long ldl, const float* pw, const float* mk, long long ldw, int N, int M, int mode,
+                 float eps, int reduce_sum, float* rstat, float* cstat, float* coef, float* loss_out, void* workspace,
+                 cudaStream_t s);
+int multipos_bwd(const float* L, long long ldl, const float* pw, const float* mk, long long ldw, int N, int M,
+                 const float* rstat, const float* cstat, const float* coef, const float* gmul, float* dL, long long ldd,
+                 cudaStream_t s);
+
 // rope3d.cu
 int rope3d_apply(const void* q, long long qsb, long long qsh, long long qsn, void* q_out, const void* k, long long ksb,
                  long long ksh, long long ksn, void* k_out, const void* sin_t, const void* cos_t, int dtype, int B,

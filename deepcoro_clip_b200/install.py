@@ -15,7 +15,7 @@ import importlib
 import sys
 from typing import Dict
 
-from . import attention_pool, loss, retrieval_metrics, retrieval_metrics_streaming, rope_3d, video_aggregator
+from . import attention_pool, loss, multipos_loss, retrieval_metrics, retrieval_metrics_streaming, rope_3d, video_aggregator
 
 # key -> class, for the two import orders the reference can end up with (SURVEY §8b "registration order hazard")
 _MAIN = {          # scripts/main.py order: utils/loss/contrastive.py registers last
@@ -23,6 +23,7 @@ _MAIN = {          # scripts/main.py order: utils/loss/contrastive.py registers 
     "siglip": loss.SigLIPLoss, "siglip_pairwise": loss.SigLIPLoss, "siglip2_bce": loss.SigLIPLoss,
     "siglip2_bce_ddp": loss.SigLIPLoss, "siglip2_multi_positive": loss.SigLIPLoss,
     "siglip_ddp": loss.SiglipLossDDP, "InfoNCE": loss.InfoNCELoss,
+    "multi_positive_infonce": multipos_loss.MultiPositiveInfoNCELoss,     # logits-level loss
 }
 _COLD = dict(_MAIN)   # cold import (alphabetical walk): utils/loss/losses.py overwrites three keys with legacy classes
 _COLD.update({"contrastive": loss.ContrastiveLoss, "contrastive_ddp": loss.ContrastiveLossDDP, "siglip": loss.SiglipLoss})
@@ -39,6 +40,8 @@ def loss_table(semantics: str = "main") -> Dict[str, type]:
 # (utils/loss/locca_loss.py:429) picks up the B200 implementation
 _BY_NAME = {
     "utils.loss.siglip_pairwise": {"SiglipPairwiseFeatureLoss": loss.SiglipPairwiseFeatureLoss},
+    "utils.loss.weighted_siglip": {"WeightedSigLIPLoss": multipos_loss.WeightedSigLIPLoss},
+    "utils.loss.multi_positive_infonce": {"MultiPositiveInfoNCELoss": multipos_loss.MultiPositiveInfoNCELoss},
     "utils.loss.siglip2_bce": {"SigLIP2BCELoss": loss.SigLIP2BCELoss, "SigLIP2BCELossDDP": loss.SigLIP2BCELossDDP,
                                "SigLIP2MultiPositiveBCELoss": loss.SigLIP2MultiPositiveBCELoss},
 }
@@ -63,6 +66,11 @@ def install(reference_root: str | None = None, semantics: str = "main", losses: 
             for n, cls in names.items():
                 setattr(mod, n, cls)
                 report["losses"].append(f"{modname}.{n}")
+        # the runner binds WeightedSigLIPLoss by name at import (runners/video_constrative_learning_runner.py:35)
+        runner_mod = sys.modules.get("runners.video_constrative_learning_runner")
+        if runner_mod is not None and hasattr(runner_mod, "WeightedSigLIPLoss"):
+            runner_mod.WeightedSigLIPLoss = multipos_loss.WeightedSigLIPLoss
+            report["losses"].append("runners.video_constrative_learning_runner.WeightedSigLIPLoss")
     if modules:
         for modname in ("models.video_encoder",):
             mod = sys.modules.get(modname)

@@ -219,6 +219,24 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                         float gnorm, int hp, int use_pos_weights, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-positive softmax cross-entropy over MATERIALISED fp32 logits [n_rows, n_cols]. Replaces
+ * WeightedSigLIPLoss.forward (utils/loss/weighted_siglip.py:18-51; mode 0, eps) and MultiPositiveInfoNCELoss.forward
+ * (utils/loss/multi_positive_infonce.py:30-100; mode 1, reduce_sum = 0 mean / 1 sum, no importance weighting).
+ *   w_ij = max(0, pos_weights_ij [* pos_mask_ij]) (either may be NULL, not both; same row stride ld_w).
+ *   multipos_fwd : rstat [n_rows][4] / cstat [n_cols][4] = {logsumexp, sum w L, sum w, #mask > 0} per row / column (one
+ *                  read of logits and weights per direction), coef [n_rows + n_cols] gradient coefficients, loss_out[0];
+ *                  workspace of b200clip_multipos_workspace_bytes(n_rows, n_cols) bytes.
+ *   multipos_bwd : dlogits_ij = grad_out[0] * (coef_i (exp(L_ij - lse_i) P_i - w_ij) + coef_j (exp(L_ij - lse_j) Q_j - w_ij)).
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_multipos_workspace_bytes(int n_rows, int n_cols);
+int b200clip_multipos_fwd(const float* logits, int64_t ld_logits, const float* pos_weights, const float* pos_mask,
+                          int64_t ld_w, int n_rows, int n_cols, int mode, float eps, int reduce_sum, float* rstat,
+                          float* cstat, float* coef, float* loss_out, void* workspace, void* stream);
+int b200clip_multipos_bwd(const float* logits, int64_t ld_logits, const float* pos_weights, const float* pos_mask,
+                          int64_t ld_w, int n_rows, int n_cols, const float* rstat, const float* cstat, const float* coef,
+                          const float* grad_out, float* dlogits, int64_t ld_d, void* stream);
+
 /* flag[0] = 1 (never cleared: caller zeroes) if any element of the row-major [rows, dim] fp32 (dtype 0) / fp16 (dtype 2)
  * matrix is not exactly representable in bf16 — one streaming read, no temporaries. Decides precision="auto" of the
  * streaming metrics (exact-grid evaluation embeddings run on plain bf16 operands and stay bit-exact). */

@@ -14,6 +14,8 @@ Follows, line by line:
   SiglipPairwiseFeatureLoss   /root/reference/utils/loss/siglip_pairwise.py:300-371
   SigLIP2BCELoss / DDP        /root/reference/utils/loss/siglip2_bce.py:79-106, 160-184
   SigLIP2MultiPositiveBCELoss /root/reference/utils/loss/siglip2_bce.py:284-331
+  WeightedSigLIPLoss          /root/reference/utils/loss/weighted_siglip.py:33-51
+  MultiPositiveInfoNCELoss    /root/reference/utils/loss/multi_positive_infonce.py:30-100
   ContrastiveLoss / DDP       /root/reference/utils/loss/losses.py:44-64, 132-158   (no tau clamp)
   SiglipLoss / DDP (gated)    /root/reference/utils/loss/losses.py:190-211, 241-276
 """
@@ -185,6 +187,40 @@ def siglip_loss(video, text, log_temp, *, bias: float | None = -10.0, pos_mask=N
     out["dtext"] = _normalize_backward(dS.T @ vh, th, tn)
     out["dbias"] = float(dR.sum())
     out["dlog_temp"] = 0.0 if clamped else float(-(dR * (R - b)).sum())
+    return out
+
+
+def multipos_softmax_loss(logits, weights, *, mask=None, mode="weighted_siglip", eps=1e-6, reduction="mean",
+                          dtype=np.float64, want_grads=True) -> dict:
+    """WeightedSigLIPLoss.forward (utils/loss/weighted_siglip.py:33-51; mode "weighted_siglip": weights = positive_weights)
+    and MultiPositiveInfoNCELoss.forward without importance weighting (utils/loss/multi_positive_infonce.py:30-100; mode
+    "infonce": weights = pos_mask [* pos_weights], ``mask`` = pos_mask decides which rows / columns count), with the
+    closed-form gradient with respect to the logits."""
+    L = np.asarray(logits, dtype=dtype)
+    w = np.maximum(np.asarray(weights, dtype=dtype), 0.0)
+    N, M = L.shape
+    lr = L - _logsumexp(L, 1)[:, None]
+    lc = L - _logsumexp(L, 0)[None, :]
+    P, Q = w.sum(1), w.sum(0)
+    if mode == "weighted_siglip":
+        dr, dc = np.maximum(P, eps), np.maximum(Q, eps)
+        loss = 0.5 * ((-(w * lr).sum(1) / dr).mean() + (-(w * lc).sum(0) / dc).mean())
+        gr, gc = 0.5 / (N * dr), 0.5 / (M * dc)
+    else:
+        mk = np.asarray(mask, dtype=dtype)
+        rsel, csel = mk.sum(1) > 0, mk.sum(0) > 0
+        dr, dc = np.maximum(P, 1.0), np.maximum(Q, 1.0)
+        lrow = -(w * lr).sum(1) / dr
+        lcol = -(w * lc).sum(0) / dc
+        stacked = np.concatenate([lrow[rsel], lcol[csel]])
+        if stacked.size == 0:
+            return {"loss": 0.0, "dlogits": np.zeros_like(L)}
+        scale = 1.0 / stacked.size if reduction == "mean" else 1.0
+        loss = stacked.sum() * scale
+        gr, gc = np.where(rsel, scale / dr, 0.0), np.where(csel, scale / dc, 0.0)
+    out = {"loss": float(loss)}
+    if want_grads:
+        out["dlogits"] = gr[:, None] * (np.exp(lr) * P[:, None] - w) + gc[None, :] * (np.exp(lc) * Q[None, :] - w)
     return out
 
 

@@ -134,6 +134,31 @@ def siglip_variants():
                    math.log(0.04))          # clamp at +-30 active on part of the matrix
 
 
+def multipos():
+    """SURVEY §8f #2: the logits-level multi-positive softmax losses (fp32 autograd through the reference classes)."""
+    from utils.loss.multi_positive_infonce import MultiPositiveInfoNCELoss
+    from utils.loss.weighted_siglip import WeightedSigLIPLoss
+    for name, N, M, seed in (("multipos_48x64", 48, 64, 50), ("multipos_130x37", 130, 37, 51)):
+        g = torch.Generator().manual_seed(seed)
+        logits = torch.randn(N, M, generator=g) * 4.0
+        mask = (torch.rand(N, M, generator=g) < 0.06).float()
+        mask[torch.arange(min(N, M)), torch.arange(min(N, M))] = 1.0
+        mask[N // 2] = 0.0                                    # a row without positives
+        mask[:, M // 3] = 0.0                                 # a column without positives
+        pw = torch.tensor([1.0, 1.5, 2.5, 3.0])[torch.randint(0, 4, (N, M), generator=g)]
+        rec = dict(logits=logits.numpy(), mask=mask.numpy(), pos_weights=pw.numpy())
+        for key, fn in (("wsl", lambda L: WeightedSigLIPLoss()(L, mask * pw - 0.2 * (1 - mask))),      # negatives clamp to 0
+                        ("mpi_mean", lambda L: MultiPositiveInfoNCELoss()(L, mask, pw)),
+                        ("mpi_sum_noweights", lambda L: MultiPositiveInfoNCELoss(reduction="sum")(L, mask))):
+            L = logits.clone().requires_grad_(True)
+            loss = fn(L)
+            loss.backward()
+            rec[key + "_loss"] = _np(loss)
+            rec[key + "_dlogits"] = _np(L.grad)
+        np.savez_compressed(OUT / f"{name}.npz", **rec)
+        print(name, {k: float(v) for k, v in rec.items() if k.endswith("_loss")})
+
+
 def dense_metrics():
     """SURVEY §8f #1: utils/retrieval_metrics.py on tie-free Gaussian similarities with multi-label ground truth."""
     from utils.retrieval_metrics import (compute_map, compute_median_rank, compute_mrr, compute_ndcg_at_k,
@@ -288,6 +313,6 @@ def qpool():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["losses", "siglip_variants", "dense_metrics", "retrieval", "rope", "attnpool", "qpool"]
+    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "dense_metrics", "retrieval", "rope", "attnpool", "qpool"]
     for name in which:
         globals()[name]()

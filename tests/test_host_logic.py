@@ -118,6 +118,9 @@ def test_install_into_reference_registry():
         import utils.retrieval_metrics as urm
         assert s2.SigLIP2BCELoss is pkg.SigLIP2BCELoss and s2.SigLIP2MultiPositiveBCELoss is pkg.SigLIP2MultiPositiveBCELoss
         assert s2.SigLIP2BCELossDDP is pkg.SigLIP2BCELossDDP and sp.SiglipPairwiseFeatureLoss is pkg.SiglipPairwiseFeatureLoss
+        import utils.loss.weighted_siglip as uws
+        assert uws.WeightedSigLIPLoss is pkg.WeightedSigLIPLoss
+        assert LossRegistry.get("multi_positive_infonce") is pkg.MultiPositiveInfoNCELoss
         assert urm.compute_mrr is pkg.retrieval_metrics.compute_mrr and urm.compute_map is pkg.retrieval_metrics.compute_map
         assert "utils.retrieval_metrics" in rep["metrics"] or "utils.retrieval_metrics" in pkg.install("/root/reference")["metrics"]
     finally:

@@ -191,3 +191,19 @@ def test_dense_metrics_oracle_matches_reference(name):
     assert abs(dmo.mrr(sim, gt)["MRR_V2T"] - float(g["mrr"])) <= 1e-12
     assert abs(dmo.mean_ap(sim, gt) - float(g["map"])) <= 1e-6
     assert dmo.median_rank(sim, gt) == int(g["median_rank"])
+
+
+# ---- logits-level multi-positive softmax losses: oracle pinned to the reference classes ----
+@pytest.mark.parametrize("name", ["multipos_48x64", "multipos_130x37"])
+def test_multipos_oracle_matches_reference(name):
+    g = _load(name)
+    L, mk, pw = g["logits"], g["mask"], g["pos_weights"]
+    cases = {
+        "wsl": co.multipos_softmax_loss(L, mk * pw - 0.2 * (1 - mk), mode="weighted_siglip"),
+        "mpi_mean": co.multipos_softmax_loss(L, mk * pw, mask=mk, mode="infonce"),
+        "mpi_sum_noweights": co.multipos_softmax_loss(L, mk, mask=mk, mode="infonce", reduction="sum"),
+    }
+    for key, r in cases.items():
+        ref = float(g[key + "_loss"])
+        assert abs(r["loss"] - ref) <= 3e-6 * abs(ref), key
+        _close(r["dlogits"], g[key + "_dlogits"], 3e-5, 1e-9)
