@@ -7,6 +7,7 @@ exceptions, e.g. utils/registry.py:27-34).
 from __future__ import annotations
 
 import ctypes
+import os
 import re
 from pathlib import Path
 
@@ -76,6 +77,11 @@ def i64(v: int) -> int:
     return int(v)
 
 
+# B200CLIP_NVTX=1: every ABI call is wrapped in an NVTX range named after the entry point, so nsys / ncu timelines show
+# the library's kernels grouped by the call that launched them (the reference has no tracing hooks at all).
+_NVTX = os.environ.get("B200CLIP_NVTX", "0") == "1"
+
+
 def call(name: str, *args) -> None:
     """Calls ``b200clip_<name>``: tensors become device pointers, everything else is converted by ctypes against the
     header prototype; raises on a non-zero status."""
@@ -83,7 +89,14 @@ def call(name: str, *args) -> None:
     fn = _FN.get(name)
     if fn is None:
         fn = _FN[name] = getattr(lib(), "b200clip_" + name)
-    rc = fn(*[a.data_ptr() if type(a) is _Tensor or isinstance(a, _Tensor) else a for a in args])
+    if _NVTX:
+        torch.cuda.nvtx.range_push("b200clip_" + name)
+        try:
+            rc = fn(*[a.data_ptr() if type(a) is _Tensor or isinstance(a, _Tensor) else a for a in args])
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        rc = fn(*[a.data_ptr() if type(a) is _Tensor or isinstance(a, _Tensor) else a for a in args])
     if name not in _NO_LAUNCH:
         LAUNCHES += 1
     if rc != 0:
