@@ -1,7 +1,7 @@
 """deepcoro_clip_b200 — B200-native (sm_100a) contrastive head for DeepCORO_CLIP: CLIP / SigLIP losses, streaming
 retrieval metrics, Rope3D, AttentionPool and the multi-view query pool behind the reference's own interfaces.
 Hand-written CUDA (tcgen05 / TMEM / TMA) behind a C ABI (include/b200clip.h); no CPU or PyTorch fallback."""
-from .attention_pool import AttentionPool
+from .attention_pool import AttentionPool, AttentionPoolWithCLS
 from .embedding_store import EmbeddingStore, epoch_end_retrieval_metrics, gather_tensor_along_batch
 from .host_pipeline import GraphedLossStep, HostBatchPrefetcher
 from .install import install, loss_table
@@ -14,7 +14,7 @@ from .retrieval_metrics_streaming import (compute_metrics_streaming, compute_rec
 from .rope_3d import Rope3D, apply_rope_qk
 from .video_aggregator import EnhancedVideoAggregator, query_pool
 
-__all__ = ["AttentionPool", "CLIPLoss", "GraphedLossStep", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EmbeddingStore", "EnhancedVideoAggregator",
+__all__ = ["AttentionPool", "AttentionPoolWithCLS", "CLIPLoss", "GraphedLossStep", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EmbeddingStore", "EnhancedVideoAggregator",
            "InfoNCELoss", "MultiPositiveInfoNCELoss", "Rope3D", "SigLIP2BCELoss", "SigLIP2BCELossDDP", "SigLIP2MultiPositiveBCELoss", "SigLIPLoss",
            "SiglipLoss", "SiglipLossDDP", "SiglipPairwiseFeatureLoss", "WeightedSigLIPLoss", "apply_rope_qk", "clip_loss",
            "compute_metrics_streaming", "compute_recall_at_k_streaming", "epoch_end_retrieval_metrics", "gather_tensor_along_batch", "install", "loss_table", "query_pool",

@@ -1,8 +1,9 @@
-"""Drop-in for models/attention_pool.py::AttentionPool (reference :10-101): same constructor, parameter names
-(``query``, ``attn.in_proj_weight``, ``attn.in_proj_bias``, ``attn.out_proj.weight``, ``attn.out_proj.bias``,
-``norm.*``, ``proj.*``) and forward signature, so checkpoints and the ``video_attention_pool`` optimizer group keep
-working. The pass over the tokens is the streaming sm_100a kernel (csrc/attnpool.cu); the O(B*D^2) projections and
-the LayerNorm around it act on [B, D] vectors and stay ordinary dense ops under autograd."""
+"""Drop-ins for models/attention_pool.py::AttentionPool (reference :10-101) and ::AttentionPoolWithCLS (:104-197):
+same constructors, parameter names (``query``, ``attn.in_proj_weight``, ``attn.in_proj_bias``,
+``attn.out_proj.weight``, ``attn.out_proj.bias``, ``norm.*``, ``proj.*``; ``cls_token``, ``transformer.layers.0.*``)
+and forward signatures, so checkpoints and the ``video_attention_pool`` optimizer group keep working. The pass over
+the tokens is the streaming sm_100a kernel (csrc/attnpool.cu, csrc/attnpool_mma.cu); the O(B*D^2) projections, the
+feed-forward block and the LayerNorms around it act on [B, D] vectors and stay ordinary dense ops under autograd."""
 from __future__ import annotations
 
 import math
@@ -17,10 +18,12 @@ from ._lib import DTYPE_CODE, call, i64, lib, stream_ptr
 
 class _StreamPool(torch.autograd.Function):
     """xbar[b, h, :] = sum_n a'[b, h, n] x[b, n],  a = softmax_n(x[b, n] . qt[h]),  a' = dropout(a)  (fp32 [B, H, D]);
-    second output sa[b, h] = sum_n a'[b, h, n] (== 1 without dropout; it multiplies the value bias)."""
+    second output sa[b, h] = sum_n a'[b, h, n] (== 1 without dropout; it multiplies the value bias); third output (only
+    with want_lse) lse[b, h] = log sum_n exp(x[b, n] . qt[h]) over the unmasked tokens, -inf when all are masked -- the
+    statistic that lets a caller merge further keys into the same softmax (AttentionPoolWithCLS)."""
 
     @staticmethod
-    def forward(ctx, x, qt, mask, drop_p, drop_seed):
+    def forward(ctx, x, qt, mask, drop_p, drop_seed, want_lse=False):
         ops.require_cuda(x, qt)
         if x.dtype not in DTYPE_CODE:
             x = x.float()
@@ -49,14 +52,20 @@ class _StreamPool(torch.autograd.Function):
         l = torch.empty((B, H), dtype=torch.float32, device=dev)
         sa = torch.empty((B, H), dtype=torch.float32, device=dev)
         call("attnpool_merge", pm, pl, pa, B, S, H, D, xbar, m, l, 0, pl2, sa, st)
+        lse = None
+        if want_lse:
+            lse = m + torch.log(l)
+            # fully masked rows: xbar is 0/0 there and the caller weighs it with exp(lse - LSE) = 0; keep 0 * NaN out of
+            # both passes (AttentionPool itself keeps nn.MultiheadAttention's NaN for such rows)
+            torch.nan_to_num_(xbar, nan=0.0)
         ctx.save_for_backward(x, qt32, mk if mk is not None else torch.empty(0, device=dev), xbar, m, l, sa)
         ctx.has_mask = mk is not None
         ctx.S = S
         ctx.drop = (float(drop_p), int(drop_seed))
-        return xbar, sa
+        return xbar, sa, lse
 
     @staticmethod
-    def backward(ctx, dxbar, dsa):
+    def backward(ctx, dxbar, dsa, dlse=None):
         x, qt32, mk, xbar, m, l, sa = ctx.saved_tensors
         mk = mk if ctx.has_mask else None
         drop_p, drop_seed = ctx.drop
@@ -66,11 +75,13 @@ class _StreamPool(torch.autograd.Function):
         st = stream_ptr(dev)
         dxbar = dxbar.float().contiguous()
         dsa = dsa.float().contiguous() if (dsa is not None and drop_p > 0.0) else None
+        dlse = dlse.float().contiguous() if dlse is not None else None
         dx = torch.empty((B, N, D), dtype=x.dtype, device=dev)
         ds = torch.empty((B, H, N), dtype=torch.float32, device=dev)
         mb = i64(mk.stride(0) if mk is not None else 0)
         call("attnpool_bwd_dx", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), mk, mb, qt32, dxbar, xbar, m,
-             l, B, N, D, H, dx, ds, sa if dsa is not None else None, dsa, drop_p if dsa is not None else 0.0, drop_seed, st)
+             l, B, N, D, H, dx, ds, sa if dsa is not None else None, dsa, drop_p if dsa is not None else 0.0, drop_seed,
+             dlse, st)
         dqt = None
         if ctx.needs_input_grad[1]:
             S = ctx.S
@@ -79,7 +90,7 @@ class _StreamPool(torch.autograd.Function):
                  i64(ds.stride(0)), i64(ds.stride(1)), B, N, D, H, S, None, None, pa, 0.0, 0, None, st)
             dqt = torch.zeros((H, D), dtype=torch.float32, device=dev)
             call("attnpool_merge", None, None, pa, B, S, H, D, dqt, None, None, 1, None, None, st)
-        return (dx if ctx.needs_input_grad[0] else None), dqt, None, None, None
+        return (dx if ctx.needs_input_grad[0] else None), dqt, None, None, None, None
 
 
 class AttentionPool(nn.Module):
@@ -113,10 +124,88 @@ class AttentionPool(nn.Module):
             bq, bv = bias[:D], bias[2 * D:]
             q0 = F.linear(self.query.float().view(1, D), Wq, bq).view(H, Dh)
             qt = torch.einsum("hkd,hk->hd", Wk.view(H, Dh, D), q0) * (1.0 / math.sqrt(Dh))     # [H, D]
-            xbar, sa = _StreamPool.apply(x, qt, mask, drop_p, drop_seed)                       # [B, H, D], [B, H] fp32
+            xbar, sa, _ = _StreamPool.apply(x, qt, mask, drop_p, drop_seed, False)             # [B, H, D], [B, H] fp32
             o = torch.einsum("bhd,hkd->bhk", xbar, Wv.view(H, Dh, D))
             o = (o + bv.view(1, H, Dh) * sa.unsqueeze(-1) if drop_p > 0.0 else o + bv.view(1, H, Dh)).reshape(B, D)
             y = F.linear(o, self.attn.out_proj.weight.float(), self.attn.out_proj.bias.float())
+            y = F.layer_norm(y, (D,), self.norm.weight.float(), self.norm.bias.float(), self.norm.eps)
+            if isinstance(self.proj, nn.Linear):
+                y = F.linear(y, self.proj.weight.float(), self.proj.bias.float())
+        return y.to(x.dtype)
+
+
+class AttentionPoolWithCLS(nn.Module):
+    """models/attention_pool.py:104-197 (built by VideoEncoder for ``token_pooling_mode == "cls_token"``,
+    models/video_encoder.py:214-219): a learnable CLS token is prepended, one post-LN ``nn.TransformerEncoderLayer``
+    runs over [CLS; x] and only the CLS row is kept (:187-195). Only that row is computed here: its attention is the
+    one-query pool over the N tokens (streaming kernel, x read once, never concatenated or projected to K / V) plus
+    the CLS key itself, merged through the log-sum-exp of the streamed scores:
+
+        w_c = exp(s_c - logaddexp(lse_x, s_c)),   attn = W_v ((1 - w_c) xbar + w_c cls) + b_v
+
+    followed by out_proj, residual + norm1, the feed-forward block, norm2, the final norm and proj on [B, D] vectors.
+    The reference computes all N + 1 rows of the layer (QKV projections 6 (N + 1) D^2 FLOP per sample and a dense
+    [N + 1, N + 1] attention) and throws N of them away. ``num_layers`` must be 1, the only value the reference ever
+    constructs (a deeper stack needs every row of the earlier layers)."""
+
+    def __init__(self, embed_dim: int, num_heads: int = 8, num_layers: int = 1, output_dim: int = None,
+                 dropout: float = 0.0):
+        super().__init__()
+        if num_layers != 1:
+            raise ValueError("AttentionPoolWithCLS: only num_layers=1 is implemented (the reference never builds "
+                             "another value: models/video_encoder.py:215-219)")
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.num_layers = num_layers
+        self.output_dim = output_dim or embed_dim
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        nn.init.trunc_normal_(self.cls_token, std=0.02)
+        # parameter container only (keeps the reference state-dict keys transformer.layers.0.*); never called
+        self.transformer = nn.TransformerEncoder(
+            nn.TransformerEncoderLayer(d_model=embed_dim, nhead=num_heads, dropout=dropout, batch_first=True),
+            num_layers=num_layers)
+        self.norm = nn.LayerNorm(embed_dim)
+        self.proj = nn.Linear(embed_dim, self.output_dim) if self.output_dim != embed_dim else nn.Identity()
+        self.dropout = dropout
+
+    def forward(self, x: torch.Tensor, mask: torch.Tensor = None) -> torch.Tensor:
+        B, N, D = x.shape
+        assert D == self.embed_dim, f"Input dim {D} != expected {self.embed_dim}"
+        layer = self.transformer.layers[0]
+        train_drop = self.training and self.dropout > 0.0
+        drop_p, drop_seed = 0.0, 0
+        if train_drop:
+            drop_p = float(self.dropout)
+            drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        H, Dh = self.num_heads, D // self.num_heads
+        with torch.autocast("cuda", enabled=False):
+            W = layer.self_attn.in_proj_weight.float()
+            bias = layer.self_attn.in_proj_bias.float()
+            Wq, Wk, Wv = W[:D], W[D:2 * D], W[2 * D:]
+            bq, bv = bias[:D], bias[2 * D:]
+            c = self.cls_token.float().view(1, D)
+            q0 = F.linear(c, Wq, bq).view(H, Dh)
+            qt = torch.einsum("hkd,hk->hd", Wk.view(H, Dh, D), q0) * (1.0 / math.sqrt(Dh))      # [H, D]
+            # the key bias adds the same q0 . b_k to every score, CLS included: it cancels in the softmax
+            xbar, sa, lse = _StreamPool.apply(x, qt, mask, drop_p, drop_seed, True)             # [B,H,D], [B,H], [B,H]
+            s_c = (qt * c).sum(dim=1)                                                           # [H] score of the CLS key
+            tot = torch.logaddexp(lse, s_c.unsqueeze(0))                                        # [B, H]
+            w_x = torch.exp(lse - tot)                                                          # weight of the N tokens
+            w_c = torch.exp(s_c.unsqueeze(0) - tot)                                             # weight of the CLS key
+            if train_drop:                                                                      # attention dropout:
+                keep = (torch.rand(B, H, device=x.device) >= drop_p).to(w_c.dtype) / (1.0 - drop_p)  # the CLS key
+                w_c = w_c * keep
+                w_sum = w_x * sa + w_c
+            mix = w_x.unsqueeze(-1) * xbar + w_c.unsqueeze(-1) * c.view(1, 1, D)                # [B, H, D]
+            o = torch.einsum("bhd,hkd->bhk", mix, Wv.view(H, Dh, D))
+            o = (o + bv.view(1, H, Dh) * w_sum.unsqueeze(-1) if train_drop else o + bv.view(1, H, Dh)).reshape(B, D)
+            y = F.linear(o, layer.self_attn.out_proj.weight.float(), layer.self_attn.out_proj.bias.float())
+            y = F.dropout(y, drop_p, train_drop)
+            y = F.layer_norm(c + y, (D,), layer.norm1.weight.float(), layer.norm1.bias.float(), layer.norm1.eps)
+            f = F.relu(F.linear(y, layer.linear1.weight.float(), layer.linear1.bias.float()))
+            f = F.linear(F.dropout(f, drop_p, train_drop), layer.linear2.weight.float(), layer.linear2.bias.float())
+            y = F.layer_norm(y + F.dropout(f, drop_p, train_drop), (D,), layer.norm2.weight.float(),
+                             layer.norm2.bias.float(), layer.norm2.eps)
             y = F.layer_norm(y, (D,), self.norm.weight.float(), self.norm.bias.float(), self.norm.eps)
             if isinstance(self.proj, nn.Linear):
                 y = F.linear(y, self.proj.weight.float(), self.proj.bias.float())

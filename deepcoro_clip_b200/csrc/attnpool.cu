@@ -196,6 +196,7 @@ struct PoolBwdParams {
   int B, N, D, H;
   const float* sa; const float* dsa;   // [B, H] sum of dropped weights and its upstream gradient (dropout only)
   float drop_p; unsigned long long drop_seed;
+  const float* dlse;                   // [B, H] upstream gradient of lse_h = m_h + log l_h (may be null)
 };
 
 // warp = token. smem: qt [H][D], dxbar_b [H][D] (fp32), c_h = dxbar_h . xbar_h
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(256) pool_bwd_dx_kernel(PoolBwdParams p) {
     for (int d = lane; d < p.D; d += 32) c = fmaf(sd[h * p.D + d], p.xbar[((size_t)b * p.H + h) * p.D + d], c);
     c = warp_sum(c);
     if (p.dsa) c = fmaf(p.dsa[b * p.H + h], p.sa[b * p.H + h], c);      // c = sum_n a_n kappa_n (T_n + dsa)
+    if (p.dlse) c -= p.dlse[b * p.H + h];                                // d lse / d s_n = a_n
     if (lane == 0) {
       sc[h] = c;
       sm[h] = p.m[b * p.H + h];
@@ -390,13 +392,13 @@ static int pool_bwd_t(const PoolBwdParams& p, cudaStream_t s) {
 int attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                     const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
                     int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
-                    unsigned long long drop_seed, cudaStream_t s) {
+                    unsigned long long drop_seed, const float* dlse, cudaStream_t s) {
   if (!x || !qt || !dxbar || !xbar || !m || !l || !dx || !ds || H > 16) return B2_EINVAL;
   if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && (!sa || !dsa))) return B2_EINVAL;
   if (attnpool_mma_ok(x, dtype, sb, sn, D, H) && sb == (long long)N * sn && (reinterpret_cast<uintptr_t>(dx) % 16) == 0)
     return attnpool_bwd_dx_mma(x, dtype, sb, sn, mask, mb, qt, dxbar, xbar, m, l, B, N, D, H, dx, ds, sa, dsa, drop_p,
-                               drop_seed, s);
-  PoolBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, sa, dsa, drop_p, drop_seed};
+                               drop_seed, dlse, s);
+  PoolBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, sa, dsa, drop_p, drop_seed, dlse};
   switch (dtype) {
     case 0: return pool_bwd_t<float>(p, s);
     case 1: return pool_bwd_t<__nv_bfloat16>(p, s);

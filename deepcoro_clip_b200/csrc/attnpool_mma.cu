@@ -281,6 +281,7 @@ struct PmBwdParams {
   int B, N, D, H, S;      // S = token splits (gridDim.y)
   const float* sa; const float* dsa; float drop_p; unsigned long long drop_seed;
   int stages;
+  const float* dlse;      // [B, H] upstream gradient of lse_h = m_h + log l_h (may be null)
 };
 
 // shared memory: x / dx tiles 2 * 32 * D * 2 | qt hi, qt lo, dxbar hi, dxbar lo: 4 x [8][D+8] | Wt [D][24] 16-bit
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(NW * 32) pool_bwd_mma_kernel(const __grid_cons
         c = fmaf(p.dxbar[((size_t)b * p.H + h) * D + d], p.xbar[((size_t)b * p.H + h) * D + d], c);
     c = warp_sum(c);
     if (p.dsa && h < p.H) c = fmaf(p.dsa[b * p.H + h], p.sa[b * p.H + h], c);
+    if (p.dlse && h < p.H) c -= p.dlse[b * p.H + h];     // d lse / d s_n = a_n
     if (lane == 0) {
       s_c[h] = c;
       s_m[h] = h < p.H ? p.m[b * p.H + h] : 0.f;
@@ -514,13 +516,13 @@ static size_t pm_bwd_smem(int D, int stages) {
 int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                         const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
                         int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
-                        unsigned long long drop_seed, cudaStream_t s) {
+                        unsigned long long drop_seed, const float* dlse, cudaStream_t s) {
   int S = sm_count() / B;
   const int maxS = (N + 2 * PM_TT - 1) / (2 * PM_TT);
   if (S > maxS) S = maxS;
   if (S < 1) S = 1;
   const int stages = pm_stages(D, pm_bwd_smem(D, 0), D % 256 == 0);
-  PmBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, S, sa, dsa, drop_p, drop_seed, stages};
+  PmBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, S, sa, dsa, drop_p, drop_seed, stages, dlse};
   const size_t smem = pm_bwd_smem(D, stages);
   CUtensorMap tmx;
   {

@@ -60,7 +60,7 @@ int attnpool_fwd_mma(const void* x, int dtype, long long sb, long long sn, const
 int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                         const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
                         int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
-                        unsigned long long drop_seed, cudaStream_t s);
+                        unsigned long long drop_seed, const float* dlse, cudaStream_t s);
 
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
@@ -140,7 +140,7 @@ int attnpool_merge(const float* part_m, const float* part_l, const float* part_a
 int attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                     const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
                     int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
-                    unsigned long long drop_seed, cudaStream_t s);
+                    unsigned long long drop_seed, const float* dlse, cudaStream_t s);
 
 // querypool.cu
 int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,

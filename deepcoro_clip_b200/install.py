@@ -2,8 +2,9 @@
 
   * ``LossRegistry`` (utils/registry.py:18-24, plain dict overwrite — last registration wins) under the same
     ``LossType`` keys the reference registers;
-  * the module-level names ``models.video_encoder.Rope3D`` / ``AttentionPool`` / ``EnhancedVideoAggregator`` that
-    ``VideoEncoder.__init__`` instantiates (models/video_encoder.py:13, 115-140, 207-212);
+  * the module-level names ``models.video_encoder.Rope3D`` / ``AttentionPool`` / ``AttentionPoolWithCLS`` /
+    ``EnhancedVideoAggregator`` that ``VideoEncoder.__init__`` instantiates (models/video_encoder.py:12-13, 115-140,
+    207-219);
   * the function names ``compute_metrics_streaming`` / ``compute_recall_at_k_streaming`` imported by
     runners/multitask_runner.py:35, and the dense multi-label metrics of utils/retrieval_metrics.py.
 
@@ -82,10 +83,12 @@ def install(reference_root: str | None = None, semantics: str = "main", losses: 
             if mod is not None:
                 mod.Rope3D = rope_3d.Rope3D
                 mod.AttentionPool = attention_pool.AttentionPool
+                if hasattr(mod, "AttentionPoolWithCLS"):
+                    mod.AttentionPoolWithCLS = attention_pool.AttentionPoolWithCLS
                 if hasattr(mod, "EnhancedVideoAggregator"):
                     mod.EnhancedVideoAggregator = video_aggregator.EnhancedVideoAggregator
                 report["modules"].append(modname)
-        for modname, names in (("models.rope_3d", ("Rope3D", "apply_rope_qk")), ("models.attention_pool", ("AttentionPool",)),
+        for modname, names in (("models.rope_3d", ("Rope3D", "apply_rope_qk")), ("models.attention_pool", ("AttentionPool", "AttentionPoolWithCLS")),
                                ("models.video_aggregator", ("EnhancedVideoAggregator",))):
             mod = sys.modules.get(modname)
             if mod is not None:

@@ -317,7 +317,10 @@ int b200clip_rope3d_apply(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_s
  *                     out [heads, D] (caller zeroes).
  *   attnpool_bwd_dx : dx_n = sum_h a'_hn dxbar_h + ds_hn qt_h, ds_hn = a_hn (kappa_hn (dxbar_h . x_n + dsa_h) - c_h),
  *                     c_h = dxbar_h . xbar_h + dsa_h sa_h; writes dx [B, N, D] (input dtype, contiguous) and
- *                     ds [B, heads, N] fp32. sa / dsa [B, heads] may be NULL when drop_p = 0.
+ *                     ds [B, heads, N] fp32. sa / dsa [B, heads] may be NULL when drop_p = 0. dlse [B, heads] (or NULL)
+ *                     is the upstream gradient of lse_h = m_h + log l_h (d lse_h / d s_hn = a_hn, i.e. c_h -= dlse_h):
+ *                     AttentionPoolWithCLS (attention_pool.py:104-197) merges the CLS key with the streamed keys
+ *                     through lse.
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_attnpool_splits(int B, int N);
 int b200clip_attnpool_fwd(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
@@ -330,7 +333,7 @@ int b200clip_attnpool_merge(const float* part_m, const float* part_l, const floa
 int b200clip_attnpool_bwd_dx(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask, int64_t mask_sb,
                              const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l,
                              int B, int N, int D, int heads, void* dx, float* ds, const float* sa, const float* dsa,
-                             float drop_p, int64_t drop_seed, void* stream);
+                             float drop_p, int64_t drop_seed, const float* dlse, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).

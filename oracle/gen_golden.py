@@ -26,7 +26,7 @@ from utils.loss.siglip_pairwise import SiglipPairwiseFeatureLoss  # noqa: E402
 from utils.loss.siglip2_bce import SigLIP2BCELoss, SigLIP2MultiPositiveBCELoss  # noqa: E402
 from utils.retrieval_metrics_streaming import compute_metrics_streaming, compute_recall_at_k_streaming  # noqa: E402
 from models.rope_3d import Rope3D  # noqa: E402
-from models.attention_pool import AttentionPool  # noqa: E402
+from models.attention_pool import AttentionPool, AttentionPoolWithCLS  # noqa: E402
 from models.video_aggregator import EnhancedVideoAggregator  # noqa: E402
 
 
@@ -284,6 +284,61 @@ def attnpool():
         print(name, tuple(out.shape))
 
 
+CLS_POOL_PARAMS = {"cls_token": "cls_token", "in_proj_weight": "transformer.layers.0.self_attn.in_proj_weight",
+                   "in_proj_bias": "transformer.layers.0.self_attn.in_proj_bias",
+                   "out_proj_weight": "transformer.layers.0.self_attn.out_proj.weight",
+                   "out_proj_bias": "transformer.layers.0.self_attn.out_proj.bias",
+                   "linear1_weight": "transformer.layers.0.linear1.weight", "linear1_bias": "transformer.layers.0.linear1.bias",
+                   "linear2_weight": "transformer.layers.0.linear2.weight", "linear2_bias": "transformer.layers.0.linear2.bias",
+                   "norm1_weight": "transformer.layers.0.norm1.weight", "norm1_bias": "transformer.layers.0.norm1.bias",
+                   "norm2_weight": "transformer.layers.0.norm2.weight", "norm2_bias": "transformer.layers.0.norm2.bias",
+                   "norm_weight": "norm.weight", "norm_bias": "norm.bias", "proj_weight": "proj.weight", "proj_bias": "proj.bias"}
+
+
+def clspool():
+    """AttentionPoolWithCLS (models/attention_pool.py:104-197), fp64, train() so that autograd takes the plain
+    (non-fused) nn.TransformerEncoderLayer path; dropout = 0 makes train() and eval() the same function."""
+    for name, (B, N, D, heads, out_dim, use_mask) in {
+        "clspool_b3_n50_d128_h8": (3, 50, 128, 8, None, False),
+        "clspool_b4_n37_d128_h4_mask_proj": (4, 37, 128, 4, 32, True),
+    }.items():
+        torch.manual_seed(70)
+        mod = AttentionPoolWithCLS(D, num_heads=heads, output_dim=out_dim, dropout=0.0).double()
+        with torch.no_grad():       # default init zeroes the biases: randomise so every term is exercised
+            for k, p in mod.named_parameters():
+                if k.endswith("bias"):
+                    p.normal_(std=0.3)
+                elif "norm" in k:
+                    p.normal_(mean=1.0, std=0.2)
+            mod.cls_token.normal_(std=0.5)
+            for k, p in mod.named_parameters():     # the two [2048, D] matrices are stored as fp16: make that lossless
+                if "linear" in k and k.endswith("weight"):
+                    p.copy_(p.half().double())
+        g = torch.Generator().manual_seed(71)
+        x = torch.randn(B, N, D, generator=g).double().requires_grad_(True)
+        mask = None
+        if use_mask:
+            mask = torch.rand(B, N, generator=g) < 0.2
+            mask[:, 0] = False
+            mask[1, :] = True          # one sample with every token masked: the CLS key attends to itself only
+        out = mod(x, mask)
+        go = torch.randn(out.shape, generator=g).double()
+        (out * go).sum().backward()
+        rec = dict(x=_np(x), go=_np(go), out=_np(out), dx=_np(x.grad), heads=np.array(heads),
+                   mask=np.zeros((B, N), bool) if mask is None else mask.numpy(), has_mask=np.array(use_mask))
+        named = dict(mod.named_parameters())
+        for k, full in CLS_POOL_PARAMS.items():
+            if full in named:
+                rec["p_" + k] = _np(named[full])
+                rec["g_" + k] = _np(named[full].grad)
+        for k in ("linear1_weight", "linear2_weight"):          # keep the fixture small: fp16 values (exact, see above),
+            rec["p_" + k] = rec["p_" + k].astype(np.float16)    # gradient rows / columns subsampled by 16 along the
+        rec["g_linear1_weight"] = rec["g_linear1_weight"][::16]  # 2048-wide hidden dimension
+        rec["g_linear2_weight"] = rec["g_linear2_weight"][:, ::16]
+        np.savez_compressed(OUT / f"{name}.npz", **rec)
+        print(name, tuple(out.shape))
+
+
 def qpool():
     for name, (B, N, D, use_mask) in {"qpool_b5_n4_d64": (5, 4, 64, False), "qpool_b6_n5_d128_mask": (6, 5, 128, True)}.items():
         torch.manual_seed(60)
@@ -313,6 +368,6 @@ def qpool():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "dense_metrics", "retrieval", "rope", "attnpool", "qpool"]
+    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool"]
     for name in which:
         globals()[name]()

@@ -4,9 +4,13 @@ numpy restatements of the token-side modules, with closed-form backward passes:
   rope3d_*            /root/reference/models/rope_3d.py:13-44 (tables), :130-184 (3D grid), :208-252 (apply)
   attention_pool_*    /root/reference/models/attention_pool.py:73-101 (nn.MultiheadAttention with ONE query
                       token + LayerNorm + optional Linear), written in the folded form of SURVEY Appendix A.4
+  cls_pool_*          /root/reference/models/attention_pool.py:104-197 (AttentionPoolWithCLS: CLS token prepended,
+                      ONE post-LN nn.TransformerEncoderLayer [self-attention, residual + norm1, relu feed-forward,
+                      residual + norm2], CLS row -> norm -> optional Linear), written literally: K and V of all
+                      N + 1 rows, no folding -- the kernels' lse-merge form is checked against it
   query_pool_*        /root/reference/models/video_aggregator.py:119-123, 128-158 (pos-enc, final LN, masked
                       softmax pooling with uniform fallback)
-Pinned against the imported reference by tests/golden/{rope,attnpool,qpool}_*.npz (oracle/gen_golden.py).
+Pinned against the imported reference by tests/golden/{rope,attnpool,clspool,qpool}_*.npz (oracle/gen_golden.py).
 """
 from __future__ import annotations
 
@@ -163,6 +167,89 @@ def attention_pool_backward(dout, cache: dict, params: dict) -> dict:
     g["in_proj_bias"] = np.concatenate([dq0, np.zeros(D), dbv], 0)
     g["query"] = (c["Wq"].T @ dq0).reshape(1, 1, D)
     g["x"] = dx
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
+# AttentionPoolWithCLS (eval / dropout = 0); only row 0 of the layer output is used by the reference (:187-195)
+# ------------------------------------------------------------------------------------------------
+def cls_pool_forward(x, params: dict, num_heads: int, mask=None, want_cache=False):
+    """x [B,N,D]; params: cls_token(1,1,D), in_proj_weight(3D,D), in_proj_bias(3D), out_proj_weight, out_proj_bias,
+    linear1_weight(F,D), linear1_bias(F), linear2_weight(D,F), linear2_bias(D), norm1_*, norm2_* (layer), norm_*
+    (final, attention_pool.py:152), optional proj_weight(O,D), proj_bias(O)."""
+    f8 = lambda k: np.asarray(params[k], dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    B, N, D = x.shape
+    Hn, Dh = num_heads, D // num_heads
+    X = np.concatenate([np.broadcast_to(f8("cls_token").reshape(1, 1, D), (B, 1, D)), x], 1)      # :177-178
+    mk = np.zeros((B, N + 1), bool)
+    if mask is not None:
+        mk[:, 1:] = np.asarray(mask, dtype=bool)                                                   # :181-184
+    Wq, Wk, Wv = (f8("in_proj_weight")[i * D:(i + 1) * D] for i in range(3))
+    bq, bk, bv = (f8("in_proj_bias")[i * D:(i + 1) * D] for i in range(3))
+    scale = 1.0 / np.sqrt(Dh)
+    q = X[:, 0] @ Wq.T + bq                                           # [B,D]   (query row 0 only)
+    K = X @ Wk.T + bk                                                 # [B,N+1,D]
+    V = X @ Wv.T + bv
+    qh, Kh, Vh = q.reshape(B, Hn, Dh), K.reshape(B, N + 1, Hn, Dh), V.reshape(B, N + 1, Hn, Dh)
+    s = np.einsum("bhk,bnhk->bhn", qh, Kh) * scale
+    s = np.where(mk[:, None, :], -np.inf, s)
+    e = np.exp(s - s.max(-1, keepdims=True))
+    a = e / e.sum(-1, keepdims=True)                                  # [B,Hn,N+1]
+    oc = np.einsum("bhn,bnhk->bhk", a, Vh).reshape(B, D)
+    y0 = oc @ f8("out_proj_weight").T + f8("out_proj_bias")
+    z1, xh1, rstd1 = _layernorm(X[:, 0] + y0, f8("norm1_weight"), f8("norm1_bias"))
+    f1 = z1 @ f8("linear1_weight").T + f8("linear1_bias")
+    hid = np.maximum(f1, 0.0)
+    f2 = hid @ f8("linear2_weight").T + f8("linear2_bias")
+    z2, xh2, rstd2 = _layernorm(z1 + f2, f8("norm2_weight"), f8("norm2_bias"))
+    z3, xh3, rstd3 = _layernorm(z2, f8("norm_weight"), f8("norm_bias"))
+    out = z3
+    if params.get("proj_weight") is not None:
+        out = z3 @ f8("proj_weight").T + f8("proj_bias")
+    if want_cache:
+        return out, dict(X=X, a=a, qh=qh, Kh=Kh, Vh=Vh, oc=oc, z1=z1, xh1=xh1, rstd1=rstd1, f1=f1, hid=hid, xh2=xh2,
+                         rstd2=rstd2, z3=z3, xh3=xh3, rstd3=rstd3, Wq=Wq, Wk=Wk, Wv=Wv, scale=scale, Hn=Hn, Dh=Dh)
+    return out
+
+
+def cls_pool_backward(dout, cache: dict, params: dict) -> dict:
+    """Gradients w.r.t. x, cls_token and every layer parameter (chain rule through the literal forward above)."""
+    f8 = lambda k: np.asarray(params[k], dtype=np.float64)
+    c = cache
+    X, a, qh, Kh, Vh = c["X"], c["a"], c["qh"], c["Kh"], c["Vh"]
+    B, N1, D = X.shape
+    Hn, Dh, scale = c["Hn"], c["Dh"], c["scale"]
+    g = {}
+    dz3 = np.asarray(dout, np.float64)
+    if params.get("proj_weight") is not None:
+        g["proj_weight"] = dz3.T @ c["z3"]
+        g["proj_bias"] = dz3.sum(0)
+        dz3 = dz3 @ f8("proj_weight")
+    dz2, g["norm_weight"], g["norm_bias"] = _layernorm_backward(dz3, c["xh3"], c["rstd3"], f8("norm_weight"))
+    dr2, g["norm2_weight"], g["norm2_bias"] = _layernorm_backward(dz2, c["xh2"], c["rstd2"], f8("norm2_weight"))
+    g["linear2_weight"] = dr2.T @ c["hid"]
+    g["linear2_bias"] = dr2.sum(0)
+    df1 = (dr2 @ f8("linear2_weight")) * (c["f1"] > 0)
+    g["linear1_weight"] = df1.T @ c["z1"]
+    g["linear1_bias"] = df1.sum(0)
+    dz1 = dr2 + df1 @ f8("linear1_weight")
+    dr1, g["norm1_weight"], g["norm1_bias"] = _layernorm_backward(dz1, c["xh1"], c["rstd1"], f8("norm1_weight"))
+    g["out_proj_weight"] = dr1.T @ c["oc"]
+    g["out_proj_bias"] = dr1.sum(0)
+    do = (dr1 @ f8("out_proj_weight")).reshape(B, Hn, Dh)
+    dVh = np.einsum("bhn,bhk->bnhk", a, do)
+    da = np.einsum("bhk,bnhk->bhn", do, Vh)
+    ds = a * (da - (a * da).sum(-1, keepdims=True))
+    dq = (np.einsum("bhn,bnhk->bhk", ds, Kh) * scale).reshape(B, D)
+    dK = (np.einsum("bhn,bhk->bnhk", ds, qh) * scale).reshape(B, N1, D)
+    dV = dVh.reshape(B, N1, D)
+    dX = dK @ c["Wk"] + dV @ c["Wv"]
+    dX[:, 0] += dr1 + dq @ c["Wq"]
+    g["in_proj_weight"] = np.concatenate([dq.T @ X[:, 0], np.einsum("bnd,bne->de", dK, X), np.einsum("bnd,bne->de", dV, X)], 0)
+    g["in_proj_bias"] = np.concatenate([dq.sum(0), dK.sum((0, 1)), dV.sum((0, 1))], 0)
+    g["cls_token"] = dX[:, 0].sum(0).reshape(1, 1, D)
+    g["x"] = dX[:, 1:]
     return g
 
 

@@ -237,3 +237,140 @@ def test_attention_pool_cuda_graph_callable():
         assert float((xg.grad.float() - xe.grad.float()).abs().max()) <= 1e-2 * float(xe.grad.float().abs().max())
         for (n, a), (_, b) in zip(pool.named_parameters(), ref.named_parameters()):
             assert float((a.grad - b.grad).abs().max()) <= 1e-4 * float(b.grad.abs().max()) + 1e-8, n
+
+
+# ---- AttentionPoolWithCLS (reference models/attention_pool.py:104-197) ----
+def _cls_pool_replica(mod, x, mask, keep_x=None, keep_c=None, p=0.0):
+    """float64 autograd replica of the reference module's math (CLS row of one post-LN TransformerEncoderLayer over
+    [CLS; x], final norm, proj) with the attention-weight dropout mask given explicitly: keep_x [B, H, N] for the
+    tokens, keep_c [B, H] for the CLS key. Returns (out, x64, params64) with gradients attached to x64 / params64."""
+    F = torch.nn.functional
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mod.named_parameters()}
+    L = "transformer.layers.0."
+    xd = x.detach().double().requires_grad_(True)
+    B, N, D = xd.shape
+    H = mod.num_heads
+    Dh = D // H
+    X = torch.cat([P["cls_token"].expand(B, 1, D), xd], 1)
+    W, bias = P[L + "self_attn.in_proj_weight"], P[L + "self_attn.in_proj_bias"]
+    q = (X[:, 0] @ W[:D].T + bias[:D]).view(B, H, Dh)
+    K = (X @ W[D:2 * D].T + bias[D:2 * D]).view(B, N + 1, H, Dh)
+    V = (X @ W[2 * D:].T + bias[2 * D:]).view(B, N + 1, H, Dh)
+    s_ = torch.einsum("bhk,bnhk->bhn", q, K) / math.sqrt(Dh)
+    if mask is not None:
+        mk = torch.cat([torch.zeros(B, 1, dtype=torch.bool, device=mask.device), mask], 1)
+        s_ = s_.masked_fill(mk[:, None, :], float("-inf"))
+    a = torch.softmax(s_, dim=-1)
+    if keep_x is not None:
+        a = a * torch.cat([keep_c.unsqueeze(-1), keep_x], -1).double() / (1.0 - p)
+    o = torch.einsum("bhn,bnhk->bhk", a, V).reshape(B, D)
+    y = o @ P[L + "self_attn.out_proj.weight"].T + P[L + "self_attn.out_proj.bias"]
+    y = F.layer_norm(X[:, 0] + y, (D,), P[L + "norm1.weight"], P[L + "norm1.bias"], 1e-5)
+    f = torch.relu(y @ P[L + "linear1.weight"].T + P[L + "linear1.bias"]) @ P[L + "linear2.weight"].T + P[L + "linear2.bias"]
+    y = F.layer_norm(y + f, (D,), P[L + "norm2.weight"], P[L + "norm2.bias"], 1e-5)
+    y = F.layer_norm(y, (D,), P["norm.weight"], P["norm.bias"], 1e-5)
+    if "proj.weight" in P:
+        y = y @ P["proj.weight"].T + P["proj.bias"]
+    return y, xd, P
+
+
+@pytest.mark.parametrize("name", ["clspool_b3_n50_d128_h8", "clspool_b4_n37_d128_h4_mask_proj"])
+def test_cls_pool_golden(name):
+    """fp32 module on the GPU vs the imported reference's fp64 output and gradients (x, cls_token, every layer
+    parameter); the masked fixture contains a sample whose tokens are ALL masked."""
+    from deepcoro_clip_b200.attention_pool import AttentionPoolWithCLS
+    from tests.test_host_logic import load_cls_pool
+    g = np.load(GOLDEN / f"{name}.npz")
+    B, N, D = g["x"].shape
+    out_dim = g["out"].shape[1]
+    mod = AttentionPoolWithCLS(D, int(g["heads"]), output_dim=None if out_dim == D else out_dim).to(DEV).eval()
+    params = load_cls_pool(mod, g)
+    x = torch.tensor(g["x"], dtype=torch.float32, device=DEV, requires_grad=True)
+    mask = torch.tensor(g["mask"], device=DEV) if bool(g["has_mask"]) else None
+    from deepcoro_clip_b200 import _lib
+    n0 = _lib.LAUNCHES
+    out = mod(x, mask)
+    assert _lib.LAUNCHES >= n0 + 2                      # the streaming kernel + merge ran (no framework fallback)
+    assert out.shape == (B, out_dim) and bool(torch.isfinite(out).all())
+    assert _rel(out.detach().cpu().numpy(), g["out"]) < 2e-5
+    (out * torch.tensor(g["go"], dtype=torch.float32, device=DEV)).sum().backward()
+    assert bool(torch.isfinite(x.grad).all())
+    assert _rel(x.grad.cpu().numpy(), g["dx"]) < 5e-5
+    for k, prm in params.items():
+        got = prm.grad.cpu().numpy()
+        got = got[::16] if k == "linear1_weight" else got[:, ::16] if k == "linear2_weight" else got
+        ref = g["g_" + k]
+        assert np.abs(got - ref).max() <= 5e-5 * max(np.abs(ref).max(), 1e-3), k
+
+
+@pytest.mark.parametrize("B,N,use_mask", [(4, 393, False), (2, 3136, True)])
+def test_cls_pool_bf16_d512_vs_oracle(B, N, use_mask):
+    """Real call shapes (MViT-v2-S output 393 tokens / synthetic C3 3,136 tokens, D = 512, 8 heads, bf16 tokens):
+    tensor-core streaming kernels; oracle = literal numpy restatement (token_oracle.cls_pool_*)."""
+    from deepcoro_clip_b200.attention_pool import AttentionPoolWithCLS
+    from tests.test_host_logic import CLS_POOL_PARAMS
+    torch.manual_seed(3)
+    mod = AttentionPoolWithCLS(512, 8, dropout=0.1).to(DEV).eval()
+    with torch.no_grad():
+        mod.cls_token.normal_(std=0.5)
+    x = torch.randn(B, N, 512, device=DEV).bfloat16().requires_grad_(True)
+    mask = (torch.rand(B, N, device=DEV) < 0.1) if use_mask else None
+    out = mod(x, mask)
+    assert out.dtype == torch.bfloat16 and out.shape == (B, 512)
+    named = dict(mod.named_parameters())
+    pn = {}
+    for k, tail in CLS_POOL_PARAMS.items():
+        full = tail if tail.split(".")[0] in ("cls_token", "norm", "proj") else "transformer.layers.0." + tail
+        if full in named:
+            pn[k] = named[full].detach().double().cpu().numpy()
+    o, cache = to.cls_pool_forward(x.detach().float().cpu().numpy(), pn, 8, None if mask is None else mask.cpu().numpy(),
+                                   want_cache=True)
+    assert _rel(out.float().detach().cpu().numpy(), o) < 1e-2          # bf16 output rounding
+    go = torch.randn(B, 512, device=DEV)
+    (out.float() * go).sum().backward()
+    gr = to.cls_pool_backward(go.cpu().numpy(), cache, pn)
+    assert _rel(x.grad.float().cpu().numpy(), gr["x"]) < 1e-2           # dx is written in bf16
+    assert _rel(mod.cls_token.grad.cpu().numpy(), gr["cls_token"]) < 5e-3
+    layer = mod.transformer.layers[0]
+    assert _rel(layer.self_attn.in_proj_weight.grad.cpu().numpy(), gr["in_proj_weight"]) < 5e-3
+    assert _rel(layer.linear1.weight.grad.cpu().numpy(), gr["linear1_weight"]) < 5e-3
+
+
+@pytest.mark.parametrize("dtype,D,N", [(torch.float32, 128, 70), (torch.bfloat16, 512, 333)])
+def test_cls_pool_training_attention_dropout(dtype, D, N, monkeypatch):
+    """Training mode: attention-weight dropout over the N + 1 keys (token keys: the kernel's counter-based mask, CLS
+    key: one device draw per (sample, head)) against a float64 replica driven by the SAME masks. The three
+    activation dropouts of the layer (Philox, dtype-dependent) are switched off for the exact comparison and
+    exercised separately below."""
+    from deepcoro_clip_b200 import attention_pool as ap
+    B, H, p = 3, 8, 0.25
+    torch.manual_seed(11)
+    mod = ap.AttentionPoolWithCLS(D, H, dropout=p).to(DEV).train()
+    with torch.no_grad():
+        mod.cls_token.normal_(std=0.5)
+    x = torch.randn(B, N, D, device=DEV).to(dtype).requires_grad_(True)
+    mask = torch.rand(B, N, device=DEV) < 0.15
+    real_dropout = ap.F.dropout
+    monkeypatch.setattr(ap.F, "dropout", lambda t, p_=0.5, training=True, inplace=False: t)
+    torch.manual_seed(321)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # what forward() will draw
+    keep_c = torch.rand(B, H, device=DEV) >= p
+    torch.manual_seed(321)
+    out = mod(x, mask)
+    gout = torch.randn_like(out.float())
+    out.float().backward(gout)
+    keep_x = _keep_mask(seed, B, H, N, p, DEV)
+    y, xd, P = _cls_pool_replica(mod, x, mask, keep_x, keep_c, p)
+    y.backward(gout.double())
+    f32 = dtype == torch.float32
+    assert _rel(out.float().detach().cpu().numpy(), y.detach().cpu().numpy()) < (2e-5 if f32 else 1e-2)
+    assert _rel(x.grad.float().cpu().numpy(), xd.grad.cpu().numpy()) < (5e-5 if f32 else 1.5e-2)
+    assert _rel(mod.cls_token.grad.cpu().numpy(), P["cls_token"].grad.cpu().numpy()) < (5e-5 if f32 else 5e-3)
+    w = "transformer.layers.0.self_attn.in_proj_weight"
+    assert _rel(dict(mod.named_parameters())[w].grad.cpu().numpy(), P[w].grad.cpu().numpy()) < (5e-5 if f32 else 5e-3)
+    # all dropouts on: finite, different from call to call; eval mode deterministic
+    monkeypatch.setattr(ap.F, "dropout", real_dropout)
+    o1 = mod(x.detach(), mask); o2 = mod(x.detach(), mask)
+    assert bool(torch.isfinite(o1).all()) and not torch.equal(o1, o2)
+    mod.eval()
+    assert torch.equal(mod(x.detach(), mask), mod(x.detach(), mask))

@@ -49,9 +49,119 @@ def test_state_dict_names_match_reference():
     keys = set(AttentionPool(512, 8, output_dim=256).state_dict())
     assert keys == {"query", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",
                     "norm.weight", "norm.bias", "proj.weight", "proj.bias"}
+    from deepcoro_clip_b200.attention_pool import AttentionPoolWithCLS
+    cls_keys = set(AttentionPoolWithCLS(128, 8, output_dim=64).state_dict())
+    layer = "transformer.layers.0."
+    assert cls_keys == {"cls_token", "norm.weight", "norm.bias", "proj.weight", "proj.bias"} | {
+        layer + k for k in ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+                            "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias",
+                            "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")}
+    with pytest.raises(ValueError):
+        AttentionPoolWithCLS(128, 8, num_layers=2)
     agg = set(EnhancedVideoAggregator(64, num_heads=4, aggregator_depth=1, max_segments=8).state_dict())
     assert {"pos_encoding", "attn_query", "final_ln.weight", "final_ln.bias", "blocks.0.norm1.weight",
             "blocks.0.attn.in_proj_weight", "blocks.0.mlp.0.weight", "blocks.0.mlp.3.bias"} <= agg
+
+
+CLS_POOL_PARAMS = {"cls_token": "cls_token", "in_proj_weight": "self_attn.in_proj_weight",
+                   "in_proj_bias": "self_attn.in_proj_bias", "out_proj_weight": "self_attn.out_proj.weight",
+                   "out_proj_bias": "self_attn.out_proj.bias", "linear1_weight": "linear1.weight",
+                   "linear1_bias": "linear1.bias", "linear2_weight": "linear2.weight", "linear2_bias": "linear2.bias",
+                   "norm1_weight": "norm1.weight", "norm1_bias": "norm1.bias", "norm2_weight": "norm2.weight",
+                   "norm2_bias": "norm2.bias", "norm_weight": "norm.weight", "norm_bias": "norm.bias",
+                   "proj_weight": "proj.weight", "proj_bias": "proj.bias"}
+
+
+def load_cls_pool(mod, g):
+    """Copies the golden fixture's parameters into a (product) AttentionPoolWithCLS; returns {fixture key: Parameter}."""
+    named = dict(mod.named_parameters())
+    out = {}
+    with torch.no_grad():
+        for k, tail in CLS_POOL_PARAMS.items():
+            if "p_" + k not in g.files:
+                continue
+            full = tail if tail.split(".")[0] in ("cls_token", "norm", "proj") else "transformer.layers.0." + tail
+            named[full].copy_(torch.as_tensor(g["p_" + k].astype(np.float64)).to(named[full].dtype))
+            out[k] = named[full]
+    return out
+
+
+@pytest.mark.parametrize("name", ["clspool_b3_n50_d128_h8", "clspool_b4_n37_d128_h4_mask_proj"])
+def test_cls_pool_merge_algebra_with_torch_stand_in(name, monkeypatch):
+    """Host-side algebra of AttentionPoolWithCLS (lse merge of the CLS key, folded scores, feed-forward tail) against
+    the reference's fp64 output and gradients, with the streaming kernel replaced by a dense autograd stand-in that
+    has the kernel's contract (xbar, sa, lse). The kernel itself is covered by the -m gpu tests."""
+    from deepcoro_clip_b200 import attention_pool as ap
+    g = np.load(GOLDEN / f"{name}.npz")
+
+    def stand_in(x, qt, mask, drop_p, drop_seed, want_lse):
+        assert want_lse and drop_p == 0.0
+        s = torch.einsum("bnd,hd->bhn", x, qt.to(x.dtype))
+        if mask is not None:
+            s = s.masked_fill(mask[:, None, :], float("-inf"))
+        lse = torch.logsumexp(s, dim=-1)
+        a = torch.nan_to_num(torch.exp(s - lse.unsqueeze(-1)), nan=0.0)
+        return torch.einsum("bhn,bnd->bhd", a, x), torch.ones_like(lse), lse
+
+    monkeypatch.setattr(ap._StreamPool, "apply", staticmethod(stand_in))
+    monkeypatch.setattr(torch.Tensor, "float", lambda t: t)          # keep the fp64 fixture in fp64 end to end
+    out_dim = g["p_proj_weight"].shape[0] if "p_proj_weight" in g.files else None
+    mod = ap.AttentionPoolWithCLS(g["x"].shape[2], int(g["heads"]), output_dim=out_dim).double().eval()
+    params = load_cls_pool(mod, g)
+    x = torch.tensor(g["x"], requires_grad=True)
+    mask = torch.tensor(g["mask"]) if bool(g["has_mask"]) else None
+    out = mod(x, mask)
+    (out * torch.tensor(g["go"])).sum().backward()
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(x.grad.numpy(), g["dx"], rtol=1e-8, atol=1e-11)
+    for k, prm in params.items():
+        got = prm.grad.numpy()
+        got = got[::16] if k == "linear1_weight" else got[:, ::16] if k == "linear2_weight" else got
+        np.testing.assert_allclose(got, g["g_" + k], rtol=1e-8, atol=1e-10, err_msg=k)
+
+
+def test_cls_pool_dropout_algebra_with_torch_stand_in(monkeypatch):
+    """Training-mode algebra of AttentionPoolWithCLS (dropout over the N + 1 attention weights, value-bias weight
+    w_x * sa + w_c) against the float64 replica of the reference math with the same masks; the streaming kernel is
+    replaced by a dense stand-in that applies the kernel's counter-based mask."""
+    from deepcoro_clip_b200 import attention_pool as ap
+    from tests.test_gpu_tokens import _cls_pool_replica, _keep_mask
+    B, N, D, H, p = 3, 29, 128, 4, 0.25
+
+    def stand_in(x, qt, mask, drop_p, drop_seed, want_lse):
+        assert want_lse and drop_p == p
+        s = torch.einsum("bnd,hd->bhn", x, qt.to(x.dtype))
+        if mask is not None:
+            s = s.masked_fill(mask[:, None, :], float("-inf"))
+        lse = torch.logsumexp(s, dim=-1)
+        a = torch.exp(s - lse.unsqueeze(-1)) * _keep_mask(drop_seed, B, H, N, p, "cpu").to(x.dtype) / (1 - p)
+        return torch.einsum("bhn,bnd->bhd", a, x), a.sum(-1), lse
+
+    monkeypatch.setattr(ap._StreamPool, "apply", staticmethod(stand_in))
+    monkeypatch.setattr(torch.Tensor, "float", lambda t: t)
+    monkeypatch.setattr(ap.F, "dropout", lambda t, p_=0.5, training=True, inplace=False: t)
+    torch.manual_seed(5)
+    mod = ap.AttentionPoolWithCLS(D, H, output_dim=48, dropout=p).double().train()
+    with torch.no_grad():
+        mod.cls_token.normal_(std=0.5)
+        for k, prm in mod.named_parameters():
+            if k.endswith("bias"):
+                prm.normal_(std=0.3)
+    x = torch.randn(B, N, D, dtype=torch.float64, requires_grad=True)
+    mask = torch.rand(B, N) < 0.2
+    torch.manual_seed(99)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    keep_c = torch.rand(B, H) >= p
+    torch.manual_seed(99)
+    out = mod(x, mask)
+    go = torch.randn_like(out)
+    out.backward(go)
+    y, xd, P = _cls_pool_replica(mod, x, mask, _keep_mask(seed, B, H, N, p, "cpu"), keep_c, p)
+    y.backward(go)
+    np.testing.assert_allclose(out.detach().numpy(), y.detach().numpy(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(x.grad.numpy(), xd.grad.numpy(), rtol=1e-8, atol=1e-11)
+    for k, prm in mod.named_parameters():
+        np.testing.assert_allclose(prm.grad.numpy(), P[k].grad.numpy(), rtol=1e-8, atol=1e-10, err_msg=k)
 
 
 def test_no_cpu_fallback():
@@ -65,6 +175,10 @@ def test_no_cpu_fallback():
         SigLIPLoss()(v, t, torch.tensor(0.0))
     with pytest.raises(B200ClipError):
         compute_metrics_streaming(v, t, torch.arange(4))
+    from deepcoro_clip_b200.attention_pool import AttentionPool, AttentionPoolWithCLS
+    for cls in (AttentionPool, AttentionPoolWithCLS):
+        with pytest.raises(B200ClipError):
+            cls(128, 8)(torch.randn(2, 5, 128))
 
 
 def test_loss_module_signatures():
@@ -121,6 +235,10 @@ def test_install_into_reference_registry():
         import utils.loss.weighted_siglip as uws
         assert uws.WeightedSigLIPLoss is pkg.WeightedSigLIPLoss
         assert LossRegistry.get("multi_positive_infonce") is pkg.MultiPositiveInfoNCELoss
+        import models.attention_pool as map_
+        assert map_.AttentionPoolWithCLS is pkg.AttentionPoolWithCLS and map_.AttentionPool is pkg.AttentionPool
+        if "models.video_encoder" in sys.modules:
+            assert sys.modules["models.video_encoder"].AttentionPoolWithCLS is pkg.AttentionPoolWithCLS
         assert urm.compute_mrr is pkg.retrieval_metrics.compute_mrr and urm.compute_map is pkg.retrieval_metrics.compute_map
         assert "utils.retrieval_metrics" in rep["metrics"] or "utils.retrieval_metrics" in pkg.install("/root/reference")["metrics"]
     finally:

@@ -161,6 +161,24 @@ def test_attention_pool_oracle(name):
         _close(grads[k], g["g_" + k], 1e-9, 1e-11)
 
 
+@pytest.mark.parametrize("name", ["clspool_b3_n50_d128_h8", "clspool_b4_n37_d128_h4_mask_proj"])
+def test_cls_pool_oracle(name):
+    """AttentionPoolWithCLS: literal numpy restatement vs the imported reference's fp64 autograd;
+    the second fixture has one sample whose tokens are all masked (the CLS key attends to itself only)."""
+    g = _load(name)
+    params = {k[2:]: g[k] for k in g.files if k.startswith("p_")}
+    mask = g["mask"] if bool(g["has_mask"]) else None
+    out, cache = to.cls_pool_forward(g["x"], params, int(g["heads"]), mask, want_cache=True)
+    assert np.isfinite(out).all()
+    _close(out, g["out"], 1e-10, 1e-12)
+    grads = to.cls_pool_backward(g["go"], cache, params)
+    _close(grads["x"], g["dx"], 1e-9, 1e-12)
+    grads["linear1_weight"] = grads["linear1_weight"][::16]        # the fixture keeps every 16th hidden unit
+    grads["linear2_weight"] = grads["linear2_weight"][:, ::16]
+    for k in params:
+        _close(grads[k], g["g_" + k], 1e-9, 1e-11)
+
+
 @pytest.mark.parametrize("name", ["qpool_b5_n4_d64", "qpool_b6_n5_d128_mask"])
 def test_query_pool_oracle(name):
     g = _load(name)

@@ -88,7 +88,7 @@ ms_k = timeit(k_fwd, reps=20)
 res["attnpool_fwd_kernels_only"] = {"ms": ms_k, "splits": S, "GBps": bx / ms_k / 1e6, "frac_hbm": bx / ms_k / 1e6 / HBM}
 dxbar = torch.randn(Bp, 8, D, device=dev); dx = torch.empty_like(xd); ds = torch.empty((Bp, 8, Np), device=dev)
 def k_bwd():
-    call("attnpool_bwd_dx", xd, DTYPE_CODE[xd.dtype], i64(xd.stride(0)), i64(xd.stride(1)), None, i64(0), qt, dxbar, xbar, m, l, Bp, Np, D, 8, dx, ds, None, None, 0.0, 0, st)
+    call("attnpool_bwd_dx", xd, DTYPE_CODE[xd.dtype], i64(xd.stride(0)), i64(xd.stride(1)), None, i64(0), qt, dxbar, xbar, m, l, Bp, Np, D, 8, dx, ds, None, None, 0.0, 0, None, st)
 ms_k = timeit(k_bwd, reps=20)
 res["attnpool_bwd_dx_kernel_only"] = {"ms": ms_k, "GBps": 2 * bx / ms_k / 1e6, "frac_hbm": 2 * bx / ms_k / 1e6 / HBM, "algorithmic_bytes": 2 * bx}
 # ---- multi-view query pool: [8, 4, 512] fp32 ----
