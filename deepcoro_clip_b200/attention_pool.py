@@ -58,6 +58,8 @@ class _StreamPool(torch.autograd.Function):
             # fully masked rows: xbar is 0/0 there and the caller weighs it with exp(lse - LSE) = 0; keep 0 * NaN out of
             # both passes (AttentionPool itself keeps nn.MultiheadAttention's NaN for such rows)
             torch.nan_to_num_(xbar, nan=0.0)
+            if pl2 is not None:
+                torch.nan_to_num_(sa, nan=0.0)             # l2 / l of such a row
         ctx.save_for_backward(x, qt32, mk if mk is not None else torch.empty(0, device=dev), xbar, m, l, sa)
         ctx.has_mask = mk is not None
         ctx.S = S
