@@ -2,6 +2,7 @@
 retrieval metrics, Rope3D, AttentionPool and the multi-view query pool behind the reference's own interfaces.
 Hand-written CUDA (tcgen05 / TMEM / TMA) behind a C ABI (include/b200clip.h); no CPU or PyTorch fallback."""
 from .attention_pool import AttentionPool, AttentionPoolWithCLS
+from .diagnostics import alignment_diagnostics
 from .embedding_store import EmbeddingStore, epoch_end_retrieval_metrics, gather_tensor_along_batch
 from .host_pipeline import GraphedLossStep, HostBatchPrefetcher
 from .install import install, loss_table
@@ -16,6 +17,6 @@ from .video_aggregator import EnhancedVideoAggregator, query_pool
 
 __all__ = ["AttentionPool", "AttentionPoolWithCLS", "CLIPLoss", "GraphedLossStep", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EmbeddingStore", "EnhancedVideoAggregator",
            "InfoNCELoss", "MultiPositiveInfoNCELoss", "Rope3D", "SigLIP2BCELoss", "SigLIP2BCELossDDP", "SigLIP2MultiPositiveBCELoss", "SigLIPLoss",
-           "SiglipLoss", "SiglipLossDDP", "SiglipPairwiseFeatureLoss", "WeightedSigLIPLoss", "apply_rope_qk", "clip_loss",
+           "SiglipLoss", "SiglipLossDDP", "SiglipPairwiseFeatureLoss", "WeightedSigLIPLoss", "alignment_diagnostics", "apply_rope_qk", "clip_loss",
            "compute_metrics_streaming", "compute_recall_at_k_streaming", "epoch_end_retrieval_metrics", "gather_tensor_along_batch", "install", "loss_table", "query_pool",
            "streaming_topk"]

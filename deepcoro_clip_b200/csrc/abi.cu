@@ -65,6 +65,10 @@ int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* g
   return clip_dlogtemp(scal0, dyn, gmul, unif, n, out, S(stream));
 }
 
+int b200clip_alignment_diag(const float* sums, int n, const float* dyn, int gated, float* out, void* stream) {
+  return alignment_diag(sums, n, dyn, gated, out, S(stream));
+}
+
 int b200clip_gather_rows_bf16(const void* src, int lds, const int64_t* idx, int rows, int src_rows, int K, void* dst,
                               int ldd, void* stream) {
   if (!src || !idx || !dst) return B2_EINVAL;

@@ -73,6 +73,7 @@ int clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, cons
                   cudaStream_t s);
 int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots, double* acc,
              cudaStream_t s);
+int alignment_diag(const float* sums, int n, const float* dyn, int gated, float* out, cudaStream_t s);
 
 // siglip.cu
 int siglip_dense_fwd(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const float* dyn,

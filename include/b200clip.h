@@ -164,6 +164,12 @@ int b200clip_clip_finalize(const float* sums, int n, const float* dyn, float eps
                            float* rowscale, float* colscale, float* loss_out, double* acc_out, void* stream);
 int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
                            float* out, void* stream);
+/* Alignment diagnostics of a batch from the same forward statistics, instead of the dense [B, B] similarity +
+ * log_softmax the runner recomputes after every step (runners/video_constrative_learning_runner.py:1323-1335):
+ *   sums = [colsum (n) | rowsum (n) | S_ii (n)] from logits_lse_fwd of the LOCAL batch, dyn from dyn_prep;
+ *   out[0] = mean S_ii (alignment_cosine), out[1] = mean (f(S_ii) / tau - lse_row_i) (alignment_logprob),
+ *   out[2] = exp(out[1]) (alignment_prob); f = identity (gated = 0) or s * sigmoid(s) (gated = 1). fp64 inside. */
+int b200clip_alignment_diag(const float* sums, int n, const float* dyn, int gated, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SigLIP multi-positive loss pieces (utils/loss/contrastive.py:230-315). The dense term treats every pair as a

@@ -18,6 +18,9 @@ Follows, line by line:
   MultiPositiveInfoNCELoss    /root/reference/utils/loss/multi_positive_infonce.py:30-100
   ContrastiveLoss / DDP       /root/reference/utils/loss/losses.py:44-64, 132-158   (no tau clamp)
   SiglipLoss / DDP (gated)    /root/reference/utils/loss/losses.py:190-211, 241-276
+  per-step alignment diagnostics  /root/reference/runners/video_constrative_learning_runner.py:1323-1335
+      (an inline block of the runner's train step, not callable outside the training stack: its golden vectors come from
+       a torch transcription of those lines in oracle/gen_golden.py, not from an imported function)
 """
 from __future__ import annotations
 
@@ -222,6 +225,23 @@ def multipos_softmax_loss(logits, weights, *, mask=None, mode="weighted_siglip",
     if want_grads:
         out["dlogits"] = gr[:, None] * (np.exp(lr) * P[:, None] - w) + gc[None, :] * (np.exp(lc) * Q[None, :] - w)
     return out
+
+
+def alignment_diagnostics(video, text, log_temp, *, use_siglip: bool = False, dtype=np.float64) -> dict:
+    """runners/video_constrative_learning_runner.py:1323-1335: mean diagonal cosine, mean diagonal row-log-softmax of
+    the (gated when the loss name contains "siglip") logits at tau = exp(log_temp) (no clamp), and its exponential."""
+    v = np.asarray(video, dtype=dtype)
+    t = np.asarray(text, dtype=dtype)
+    vh, _ = l2_normalize(v)
+    th, _ = l2_normalize(t)
+    S = vh @ th.T                                                       # :1324-1326
+    cosine = np.diag(S).mean()                                          # :1327
+    base = S * _sigmoid(S) if use_siglip else S                         # :1328-1331
+    tau = np.exp(dtype(np.asarray(log_temp, dtype=np.float64).reshape(-1)[0]))   # :1332
+    L = base / tau
+    logprob = (np.diag(L) - _logsumexp(L, 1)).mean()                    # :1333-1334
+    return {"alignment_cosine": float(cosine), "alignment_logprob": float(logprob),
+            "alignment_prob": float(np.exp(logprob))}                   # :1335
 
 
 # ---- fp32 timing port used by bench.py (cpu_baseline / --impl reference); same algorithm, all host threads ----

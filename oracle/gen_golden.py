@@ -159,6 +159,39 @@ def multipos():
         print(name, {k: float(v) for k, v in rec.items() if k.endswith("_loss")})
 
 
+def alignment():
+    """SURVEY §8f #2 (logging half): the runner's per-step alignment diagnostics. The block is inline in the train step
+    (runners/video_constrative_learning_runner.py:1323-1335) and the runner does not import outside the training
+    stack, so the lines are transcribed here with the same torch calls, in fp32 (as the runner runs them) and fp64."""
+    import torch.nn.functional as F
+    for name, B, D, seed, lt, use_siglip in (("align_b64_d512", 64, 512, 60, math.log(0.07), False),
+                                             ("align_siglip_b130_d96", 130, 96, 61, math.log(0.087), True),
+                                             ("align_b300_d200", 300, 200, 62, math.log(0.05), False)):
+        g = torch.Generator().manual_seed(seed)
+        text = torch.randn(B, D, generator=g)
+        video = 0.6 * text + torch.randn(B, D, generator=g)            # aligned pairs, as after some training
+        rec = dict(video=video.numpy(), text=text.numpy(), log_temp=np.array([lt]), use_siglip=np.array(use_siglip))
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            video_emb, text_emb, log_temp = video.to(dt), text.to(dt), torch.tensor([lt], dtype=dt)
+            video_norm = F.normalize(video_emb, dim=1)
+            text_norm = F.normalize(text_emb, dim=1)
+            similarity = torch.matmul(video_norm, text_norm.t())
+            alignment_cosine_tensor = torch.diag(similarity).mean()
+            logits_base = similarity
+            if use_siglip:
+                logits_base = similarity * torch.sigmoid(similarity)
+            tau_value = torch.exp(log_temp.float() if dt == torch.float32 else log_temp)
+            logits_matrix = logits_base / tau_value
+            logprob_matrix = F.log_softmax(logits_matrix, dim=1)
+            alignment_logprob_tensor = torch.diag(logprob_matrix).mean()
+            alignment_prob_tensor = alignment_logprob_tensor.exp()
+            rec["cosine_" + tag] = _np(alignment_cosine_tensor)
+            rec["logprob_" + tag] = _np(alignment_logprob_tensor)
+            rec["prob_" + tag] = _np(alignment_prob_tensor)
+        np.savez_compressed(OUT / f"{name}.npz", **rec)
+        print(name, float(rec["cosine_f64"]), float(rec["logprob_f64"]), float(rec["prob_f64"]))
+
+
 def dense_metrics():
     """SURVEY §8f #1: utils/retrieval_metrics.py on tie-free Gaussian similarities with multi-label ground truth."""
     from utils.retrieval_metrics import (compute_map, compute_median_rank, compute_mrr, compute_ndcg_at_k,
@@ -368,6 +401,6 @@ def qpool():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool"]
+    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "alignment", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool"]
     for name in which:
         globals()[name]()

@@ -164,6 +164,61 @@ def test_cls_pool_dropout_algebra_with_torch_stand_in(monkeypatch):
         np.testing.assert_allclose(prm.grad.numpy(), P[k].grad.numpy(), rtol=1e-8, atol=1e-10, err_msg=k)
 
 
+@pytest.mark.parametrize("name", ["align_b64_d512", "align_siglip_b130_d96"])
+def test_alignment_diagnostics_wiring_with_torch_stand_in(name, monkeypatch):
+    """Host wiring of diagnostics.alignment_diagnostics (arena layout, argument order, dyn slots, the formula the scalar
+    kernel implements) against the golden vectors, with the C-ABI entry points replaced by torch stand-ins that follow
+    the contracts written in include/b200clip.h. The kernels themselves are covered by the -m gpu tests."""
+    from deepcoro_clip_b200 import diagnostics as dg, ops
+    g = np.load(GOLDEN / f"{name}.npz")
+    LOG2E, LN2 = 1.4426950408889634, 0.6931471805599453
+
+    def l2norm_operand(x, role=-1, normalize=True):
+        x = x.double()
+        return x / x.norm(dim=1, keepdim=True).clamp_min(1e-12), None, x.shape[1]
+
+    def dyn_prep(log_temp, bias, clamp_min, bound):
+        assert bias is None and clamp_min == 0.0
+        tau = float(torch.exp(log_temp.double().reshape(-1)[0]))
+        scale2 = LOG2E / tau
+        shift2 = scale2 * bound - min(max(2.0 * bound * scale2 - 120.0, 0.0), 100.0)
+        d = torch.zeros(16, dtype=torch.float64)
+        d[0], d[1], d[2], d[3], d[6], d[7] = scale2, shift2, 1.0 / tau, tau, LN2 * shift2, 1.0
+        return d
+
+    def call(fn, *a):
+        if fn == "logits_lse_fwd":
+            A, Bm, Ma, Nb, K, lda, ldb, s2, sh2, gated, dyn, rowsum, colsum, diag, diag_off, st = a
+            S = A @ Bm.T
+            P = torch.exp2((S * torch.sigmoid(S) if gated else S) * dyn[0] - dyn[1])
+            rowsum += P.sum(1)
+            colsum += P.sum(0)
+            diag.copy_(torch.diagonal(S, diag_off))
+        elif fn == "alignment_diag":
+            sums, n, dyn, gated, out, st = a
+            d = sums[2 * n:3 * n]
+            f = d * torch.sigmoid(d) if gated else d
+            lp = (f * dyn[2] - (torch.log(sums[n:2 * n]) + dyn[6])).mean()
+            out[0], out[1], out[2] = d.mean(), lp, torch.exp(lp)
+        else:
+            raise AssertionError(fn)
+
+    monkeypatch.setattr(ops, "require_cuda", lambda *t: torch.device("cpu"))
+    monkeypatch.setattr(ops, "stream_ptr", lambda dev=None: 0)
+    monkeypatch.setattr(ops, "l2norm_operand", l2norm_operand)
+    monkeypatch.setattr(ops, "dyn_prep", dyn_prep)
+    monkeypatch.setattr(ops, "call", call)
+    real_zeros = torch.zeros
+    monkeypatch.setattr(torch, "zeros", lambda *a, **k: real_zeros(*a, **{**k, "dtype": torch.float64}))
+    r = dg.alignment_diagnostics(torch.tensor(g["video"]), torch.tensor(g["text"]), torch.tensor(g["log_temp"]),
+                                 use_siglip=bool(g["use_siglip"]))
+    for key, ref in (("alignment_cosine", "cosine_f64"), ("alignment_logprob", "logprob_f64"),
+                     ("alignment_prob", "prob_f64")):
+        assert abs(float(r[key]) - float(g[ref])) <= 1e-10 * max(1.0, abs(float(g[ref]))), key
+    with pytest.raises(ValueError):
+        dg.alignment_diagnostics(torch.zeros(4, 8), torch.zeros(5, 8), 0.0)
+
+
 def test_no_cpu_fallback():
     from deepcoro_clip_b200._lib import B200ClipError
     from deepcoro_clip_b200.loss import CLIPLoss, SigLIPLoss

@@ -225,3 +225,16 @@ def test_multipos_oracle_matches_reference(name):
         ref = float(g[key + "_loss"])
         assert abs(r["loss"] - ref) <= 3e-6 * abs(ref), key
         _close(r["dlogits"], g[key + "_dlogits"], 3e-5, 1e-9)
+
+
+# ---- per-step alignment diagnostics (logging half): oracle pinned to the transcribed runner lines ----
+@pytest.mark.parametrize("name", ["align_b64_d512", "align_siglip_b130_d96", "align_b300_d200"])
+def test_alignment_diagnostics_oracle(name):
+    g = _load(name)
+    r = co.alignment_diagnostics(g["video"], g["text"], g["log_temp"], use_siglip=bool(g["use_siglip"]))
+    for key, ref in (("alignment_cosine", "cosine_f64"), ("alignment_logprob", "logprob_f64"),
+                     ("alignment_prob", "prob_f64")):
+        assert abs(r[key] - float(g[ref])) <= 1e-12 * max(1.0, abs(float(g[ref]))), key
+    r32 = co.alignment_diagnostics(g["video"], g["text"], g["log_temp"], use_siglip=bool(g["use_siglip"]),
+                                   dtype=np.float32)
+    assert abs(r32["alignment_logprob"] - float(g["logprob_f32"])) <= 2e-5 * max(1.0, abs(float(g["logprob_f32"])))
