@@ -34,6 +34,7 @@ UNIT = "samples/s"
 WORKLOADS = {"clip32k": (32768, 512), "clip32k_d768": (32768, 768), "clip8k": (8192, 512)}
 TAU = 0.0588   # config/clip/base_config.yaml:46
 L2_BYTES = 126e6
+CPU_PORT = "reference op sequence on torch CPU (fp32, all host threads; oracle/reference_torch_port.py)"
 
 
 def peaks():
@@ -107,21 +108,23 @@ class ClockSampler:
 
 
 def cpu_reference_step(N: int, D: int, steps: int, warmup: int):
-    """The reference's CPU path (oracle port: normalise, matmul, 2x CE, closed-form backward; fp32 numpy with all
-    BLAS threads) on a bounded sample of the workload."""
-    import numpy as np
-    from oracle import contrastive_oracle as co
-    rng = np.random.default_rng(5)
-    v = rng.standard_normal((N, D)).astype(np.float32)
-    t = rng.standard_normal((N, D)).astype(np.float32)
+    """The reference's CPU path on a bounded sample of the workload: the reference is PyTorch, so this is its own op
+    sequence (normalize, matmul, 2x cross_entropy, autograd backward) on ATen's CPU kernels with every host thread
+    (oracle/reference_torch_port.py, pinned to the imported reference's golden vectors). Returns (best s, mean s, threads)."""
+    import torch
+    from oracle import reference_torch_port as tp
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(5)
+    v = torch.randn(N, D, generator=g)
+    t = torch.randn(N, D, generator=g)
     for _ in range(warmup):
-        co.clip_fwd_bwd_f32(v, t, math.log(TAU))
+        tp.clip_loss_step(v, t, math.log(TAU))
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        co.clip_fwd_bwd_f32(v, t, math.log(TAU))
+        tp.clip_loss_step(v, t, math.log(TAU))
         ts.append(time.perf_counter() - t0)
-    return min(ts), sum(ts) / len(ts)
+    return min(ts), sum(ts) / len(ts), torch.get_num_threads()
 
 
 def retrieval_leg(dev, world, rank):
@@ -170,17 +173,16 @@ def run_reference(args, N, D):
     if rank != 0:
         return
     Ns = 4096                                  # bounded sample; the loss is O(N^2 D): extrapolate by (Ns/N)
-    best, mean = cpu_reference_step(Ns, D, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    best, mean, cores = cpu_reference_step(Ns, D, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
     sps_sample = Ns / best
     value = sps_sample * (Ns / N)               # samples/s the CPU path would reach at the full N (N^2 scaling)
-    cores = os.cpu_count()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3 * (N / Ns) ** 2,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "global_batch": N, "dim": D, "tau": TAU},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"oracle port (numpy fp32, BLAS threads) fwd+bwd at N={Ns}: {sps_sample:.0f} samples/s, "
+                         "sample": f"{CPU_PORT} fwd+bwd at N={Ns}: {sps_sample:.0f} samples/s, "
                                    f"N^2-extrapolated to N={N}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -392,9 +394,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Ns = 4096
-        best, _ = cpu_reference_step(Ns, D, 3, 1)
-        cpu = {"value": (Ns / best) * (Ns / N), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"oracle port (numpy fp32, BLAS threads) fwd+bwd at N={Ns}: {Ns / best:.0f} samples/s ({best * 1e3:.0f} ms), "
+        best, _, cores = cpu_reference_step(Ns, D, 3, 1)
+        cpu = {"value": (Ns / best) * (Ns / N), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{CPU_PORT} fwd+bwd at N={Ns}: {Ns / best:.0f} samples/s ({best * 1e3:.0f} ms), "
                          f"N^2-extrapolated to N={N}"}
 
     if rank == 0:

@@ -238,3 +238,18 @@ def test_alignment_diagnostics_oracle(name):
     r32 = co.alignment_diagnostics(g["video"], g["text"], g["log_temp"], use_siglip=bool(g["use_siglip"]),
                                    dtype=np.float32)
     assert abs(r32["alignment_logprob"] - float(g["logprob_f32"])) <= 2e-5 * max(1.0, abs(float(g["logprob_f32"])))
+
+
+# ---- the torch CPU transcription bench.py times as the reference arm ----
+@pytest.mark.parametrize("name,ls", [("clip_c1_b64_d512", 0.0), ("clip_ls_b48_d96", 0.1), ("clip_b300_d200", 0.0)])
+def test_torch_port_matches_reference(name, ls):
+    import torch
+    from oracle import reference_torch_port as tp
+    g = _load(name)
+    loss, dv, dt, dlt = tp.clip_loss_step(torch.tensor(g["video"], dtype=torch.float32),
+                                          torch.tensor(g["text"], dtype=torch.float32), float(g["log_temp"][0]), ls)
+    ref = float(g["f32_loss"])
+    assert abs(loss.item() - ref) <= 1e-6 * abs(ref)       # same ops in the same library: thread count is the only freedom
+    _close(dv.numpy(), g["f32_dvideo"], 1e-5, 1e-10)
+    _close(dt.numpy(), g["f32_dtext"], 1e-5, 1e-10)
+    assert abs(dlt.item() - float(g["f32_dlog_temp"].reshape(-1)[0])) <= 1e-5 * max(1.0, abs(dlt.item()))
