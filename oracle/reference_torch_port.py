@@ -35,3 +35,51 @@ def clip_loss_step(video, text, log_temp: float, label_smoothing: float = 0.0):
     loss = 0.5 * (loss_v2t + loss_t2v)                                                # :164
     loss.backward()
     return loss.detach(), video_features.grad, text_features.grad, lt.grad
+
+
+@torch.no_grad()
+def retrieval_metrics_step(video, text, gt, k_values=(1, 5, 10), video_chunk_size: int = 2048,
+                           text_chunk_size: int = 8192):
+    """The reference's CPU path for recall@k + MRR over a [n_videos] x [n_texts] sweep, op for op
+    (/root/reference/utils/retrieval_metrics_streaming.py:35-101 with device='cpu', then the MRR loop :141-172): chunked
+    matmul / topk / cat / topk / gather for the recalls, a second chunked matmul + full argsort + per-row Python loop for
+    the reciprocal ranks. Inputs are used as given (the caller normalises, as compute_metrics_streaming :128-131 does)."""
+    video_features = torch.as_tensor(video).float()
+    text_features = torch.as_tensor(text).detach().float()
+    ground_truth_indices = torch.as_tensor(gt)
+    n_videos, n_texts = video_features.size(0), text_features.size(0)
+    recalls = {k: 0 for k in k_values}
+    k_max = max(k_values)
+    for v_start in range(0, n_videos, video_chunk_size):                                   # :47
+        video_chunk = video_features[v_start:min(v_start + video_chunk_size, n_videos)]
+        best_scores = best_indices = None
+        for t_start in range(0, n_texts, text_chunk_size):                                 # :56
+            text_chunk = text_features[t_start:min(t_start + text_chunk_size, n_texts)]
+            similarity = torch.matmul(video_chunk, text_chunk.t())                         # :61
+            chunk_scores, chunk_indices = torch.topk(similarity, k=min(k_max, similarity.size(1)), dim=1)   # :64-65
+            chunk_indices = chunk_indices + t_start                                        # :68
+            if best_scores is None:
+                best_scores, best_indices = chunk_scores, chunk_indices
+            else:
+                all_scores = torch.cat([best_scores, chunk_scores], dim=1)                 # :76-77
+                all_indices = torch.cat([best_indices, chunk_indices], dim=1)
+                best_scores, top_idx = torch.topk(all_scores, k=min(k_max, all_scores.size(1)), dim=1)      # :80-81
+                best_indices = torch.gather(all_indices, 1, top_idx)                       # :82
+        chunk_gt = ground_truth_indices[v_start:v_start + video_chunk.size(0)]
+        for k in k_values:                                                                 # :89-93
+            if k <= best_indices.size(1):
+                recalls[k] += (best_indices[:, :k] == chunk_gt.unsqueeze(1)).any(dim=1).sum().item()
+    metrics = {f"Recall@{k}": (recalls[k] / n_videos) * 100 for k in k_values}            # :99
+    mrr_sum = 0.0
+    for v_start in range(0, n_videos, video_chunk_size):                                   # :143
+        video_chunk = video_features[v_start:min(v_start + video_chunk_size, n_videos)]
+        chunk_gt = ground_truth_indices[v_start:v_start + video_chunk.size(0)]
+        all_scores = [torch.matmul(video_chunk, text_features[t:min(t + text_chunk_size, n_texts)].t())
+                      for t in range(0, n_texts, text_chunk_size)]                         # :151-155
+        sorted_indices = torch.argsort(torch.cat(all_scores, dim=1), dim=1, descending=True)   # :158-161
+        for i in range(chunk_gt.size(0)):                                                  # :162-166
+            rank = (sorted_indices[i] == chunk_gt[i].item()).nonzero(as_tuple=True)[0]
+            if rank.numel() > 0:
+                mrr_sum += 1.0 / (rank[0].item() + 1)
+    metrics["MRR_V2T"] = mrr_sum / n_videos                                                # :172
+    return metrics

@@ -253,3 +253,17 @@ def test_torch_port_matches_reference(name, ls):
     _close(dv.numpy(), g["f32_dvideo"], 1e-5, 1e-10)
     _close(dt.numpy(), g["f32_dtext"], 1e-5, 1e-10)
     assert abs(dlt.item() - float(g["f32_dlog_temp"].reshape(-1)[0])) <= 1e-5 * max(1.0, abs(dlt.item()))
+
+
+def test_torch_port_retrieval_matches_reference():
+    import torch
+    from oracle import reference_torch_port as tp
+    g = _load("retrieval_gauss_300x200")
+    ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
+    v = torch.nn.functional.normalize(torch.tensor(g["video"]), dim=1)
+    t = torch.nn.functional.normalize(torch.tensor(g["text"]), dim=1)
+    r = tp.retrieval_metrics_step(v, t, torch.tensor(g["gt"]), k_values=(1, 5, 10, 50), video_chunk_size=128,
+                                  text_chunk_size=64)
+    for k in ("Recall@1", "Recall@5", "Recall@10", "Recall@50"):
+        assert r[k] == float(ref[k]), k
+    assert abs(r["MRR_V2T"] - float(ref["MRR_V2T"])) <= 1e-12
