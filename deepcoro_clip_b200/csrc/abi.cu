@@ -257,6 +257,24 @@ int b200clip_topk_merge(const float* part_score, const int32_t* part_idx, int ro
                     S(stream));
 }
 
+int b200clip_retrieval_colmax(const void* video, const void* text, int n_video, int n_text, int Kp, int ldv, int ldt,
+                              int segs, float* part_max, void* stream) {
+  if (!video || !text) return B2_EINVAL;
+  return retrieval_colmax(video, text, n_video, n_text, Kp, ldv, ldt, segs, part_max, S(stream));
+}
+
+int b200clip_kth_largest(const float* vals, int rows, int cand, int k, float* thr, void* stream) {
+  return kth_largest(vals, rows, cand, k, thr, S(stream));
+}
+
+int b200clip_retrieval_collect(const void* video, const void* text, int n_video, int n_text, int Kp, int ldv, int ldt,
+                               const float* thr, int col_offset, int segs, int32_t* cnt, float* buf_s, int32_t* buf_i,
+                               int cap, int32_t* overflow, void* stream) {
+  if (!video || !text) return B2_EINVAL;
+  return retrieval_collect(video, text, n_video, n_text, Kp, ldv, ldt, thr, col_offset, segs, cnt, buf_s, buf_i, cap,
+                           overflow, S(stream));
+}
+
 int b200clip_recall_hits(const int32_t* counts, int rows, const int32_t* k_values, int nk, uint64_t* hits,
                          void* stream) {
   if (!counts || !k_values || !hits) return B2_EINVAL;

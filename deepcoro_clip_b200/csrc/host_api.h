@@ -103,6 +103,12 @@ int retrieval_segments(int Ma, int Nb);
 int retrieval_sweep(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, const float* sgt,
                     const long long* gt, int col_offset, int* counts, int k, int segs, float* part_score,
                     int* part_idx, cudaStream_t stream);
+int retrieval_colmax(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, int segs, float* part_max,
+                     cudaStream_t stream);
+int kth_largest(const float* vals, int rows, int cand, int k, float* thr, cudaStream_t s);
+int retrieval_collect(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, const float* thr,
+                      int col_offset, int segs, int* cnt, float* buf_s, int* buf_i, int cap, int* overflow,
+                      cudaStream_t stream);
 int topk_merge(const float* ps, const int* pi, int rows, int cand, int k, float* out_s, long long* out_i,
                cudaStream_t s);
 int recall_hits(const int* counts, int rows, const int* kvals, int nk, unsigned long long* hits, cudaStream_t s);

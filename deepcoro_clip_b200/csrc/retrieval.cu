@@ -143,6 +143,94 @@ struct RetrEpi {
   }
 };
 
+// ---- two-sweep top-k (opt-in, B200CLIP_TOPK2=1): threshold first, then collect ----
+// The register lists of RetrEpi make the WHOLE warp pay for every insertion of any of its 32 rows (~84 insertions per list,
+// so nearly every 32-column chunk takes the slow path: 5x the counts-only sweep at k = 10). Two cheap sweeps instead:
+//   sweep 1 (ColMaxEpi): per (row, slot = segment x column half) the maximum of each of the 32 column residue classes
+//     (element e of every chunk) — one FMNMX per element, no branches. The subsets are disjoint, so the k-th largest of a
+//     row's subset maxima (kth_largest_kernel) is a LOWER BOUND tau_i of its k-th best score.
+//   sweep 2 (CollectEpi): every s_ij >= tau_i is appended to a per-row candidate buffer (one atomicAdd per chunk that
+//     has a hit; ~12 hits per row at k = 10 with 64 subsets), which contains the exact top-k set including all ties at
+//     the k-th score; topk_merge then orders it by (score desc, index asc). A row whose buffer overflows raises a flag
+//     and the caller falls back to the register-list sweep (exactness is never traded).
+struct ColMaxParams {
+  float* part_max;   // [Ma][slots][32]
+  int slots;
+};
+struct ColMaxEpi {
+  using Params = ColMaxParams;
+  struct State { float mx[32]; };
+  __device__ static __forceinline__ void init(State&, const Params&) {}
+  __device__ static __forceinline__ void begin_outer(State& st, const Params&, int, const TeCtx&) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) st.mx[e] = -INFINITY;
+  }
+  __device__ static __forceinline__ void chunk(State& st, const Params&, const TeCtx& ctx, int c,
+                                               const uint32_t (&acc)[32]) {
+    const int nvalid = ctx.Nb - (ctx.col0 + c * 32);
+    if (nvalid >= 32) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) st.mx[e] = fmaxf(st.mx[e], __uint_as_float(acc[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) st.mx[e] = fmaxf(st.mx[e], e < nvalid ? __uint_as_float(acc[e]) : -INFINITY);
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State&, const Params&, const TeCtx&) {}
+  __device__ static __forceinline__ void end_outer(State& st, const Params& p, int, const TeCtx& ctx) {
+    if (!ctx.row_ok) return;
+    float4* dst = reinterpret_cast<float4*>(p.part_max + ((size_t)ctx.row * p.slots + (ctx.seg * 2 + ctx.wg)) * 32);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dst[e] = make_float4(st.mx[4 * e], st.mx[4 * e + 1], st.mx[4 * e + 2], st.mx[4 * e + 3]);
+  }
+};
+
+struct CollectParams {
+  const float* thr;   // [Ma] per-row lower bound of the k-th best score
+  int col_offset;     // global index of B row 0 (text shard offset)
+  int* cnt;           // [Ma] candidates appended so far (zeroed by the caller)
+  float* buf_s;       // [Ma][cap]
+  int* buf_i;         // [Ma][cap], pre-filled with 0x7fffffff (= empty for topk_merge)
+  int cap;
+  int* overflow;      // set to 1 if any row had more than cap candidates
+};
+struct CollectEpi {
+  using Params = CollectParams;
+  struct State { float thr; };
+  __device__ static __forceinline__ void init(State&, const Params&) {}
+  __device__ static __forceinline__ void begin_outer(State& st, const Params& p, int, const TeCtx& ctx) {
+    st.thr = ctx.row_ok ? p.thr[ctx.row] : INFINITY;
+  }
+  __device__ static __forceinline__ void chunk(State& st, const Params& p, const TeCtx& ctx, int c,
+                                               const uint32_t (&acc)[32]) {
+    const int cbase = ctx.col0 + c * 32;
+    const int nvalid = ctx.Nb - cbase;
+    uint32_t m = 0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) m |= (__uint_as_float(acc[e]) >= st.thr) ? (1u << e) : 0u;
+    if (nvalid < 32) m = nvalid <= 0 ? 0u : (m & ((1u << nvalid) - 1u));
+    if (m != 0u && ctx.row_ok) {
+      const int n = __popc(m);
+      int pos = atomicAdd(p.cnt + ctx.row, n);
+      if (pos + n > p.cap) *p.overflow = 1;
+      float* bs = p.buf_s + (size_t)ctx.row * p.cap;
+      int* bi = p.buf_i + (size_t)ctx.row * p.cap;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        if ((m >> e) & 1u) {
+          if (pos < p.cap) {
+            bs[pos] = __uint_as_float(acc[e]);
+            bi[pos] = p.col_offset + cbase + e;
+          }
+          ++pos;
+        }
+      }
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State&, const Params&, const TeCtx&) {}
+  __device__ static __forceinline__ void end_outer(State&, const Params&, int, const TeCtx&) {}
+};
+
 // K6: out[row][0..k) = best k of the row's `slots * kin` candidates by (score desc, index asc). One warp per row.
 __device__ __forceinline__ unsigned long long retr_key(float s, int idx) {
   uint32_t u = __float_as_uint(s);
@@ -184,6 +272,40 @@ topk_merge_kernel(const float* __restrict__ ps, const int* __restrict__ pi, int 
         out_i[(size_t)warp * k + r] = (long long)(0x7fffffff - (uint32_t)(wbest & 0xffffffffu));
       }
     }
+  }
+}
+
+// thr[row] = k-th largest of the row's `cand` values counted with multiplicity (-inf when cand < k). One warp per row;
+// round r takes the largest (value, position) key below the previous winner, as topk_merge does.
+__global__ void __launch_bounds__(256)
+kth_largest_kernel(const float* __restrict__ vals, int rows, int cand, int k, float* __restrict__ thr) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* v = vals + (size_t)warp * cand;
+  unsigned long long last = ~0ull;
+  for (int r = 0; r < k; ++r) {
+    unsigned long long best = 0ull;
+    for (int c = lane; c < cand; c += 32) {
+      const unsigned long long key = retr_key(v[c], c);
+      if (key < last && key > best) best = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    last = best;
+    if (best == 0ull) break;            // fewer than k values
+  }
+  if (lane == 0) {
+    float t = -INFINITY;
+    if (last != 0ull && last != ~0ull) {
+      uint32_t u = (uint32_t)(last >> 32);
+      u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+      t = __uint_as_float(u);
+    }
+    thr[warp] = t;
   }
 }
 
@@ -234,9 +356,9 @@ using namespace b2;
 int make_shape(TeShape& g, int Ma, int Nb, int Kp);   // logits_fwd.cu
 bool te_pair_enabled(int Kp);                          // logits_fwd.cu
 
-template <int kMaxK>
-static int launch_retr(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, const RetrParams& p,
-                       int segs, cudaStream_t stream) {
+template <class Epi>
+static int launch_epi(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb,
+                      const typename Epi::Params& p, int segs, cudaStream_t stream) {
   TeShape g;
   int rc = make_shape(g, Ma, Nb, Kp);
   if (rc) return rc;
@@ -248,7 +370,7 @@ static int launch_retr(const void* A, const void* B, int Ma, int Nb, int Kp, int
     // CTA pairs: A tile (video rows) resident per CTA, text blocks streamed as halves (tile_engine2.cuh)
     CUtensorMap tmB2;
     if ((rc = make_tmap_bf16_2d(&tmB2, B, Nb, Kp, ldb, 128))) return rc;
-    auto kern2 = te2_kernel<RetrEpi<kMaxK>, false>;
+    auto kern2 = te2_kernel<Epi, false>;
     static bool attr2_done = false;
     if (!attr2_done) {
       if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, TE2_SMEM_BYTES) != cudaSuccess)
@@ -261,7 +383,7 @@ static int launch_retr(const void* A, const void* B, int Ma, int Nb, int Kp, int
     kern2<<<(int)(2 * clusters), TE_THREADS, TE2_SMEM_BYTES, stream>>>(tmA, tmB2, g, p);
     return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
   }
-  auto kern = te_kernel<RetrEpi<kMaxK>, false>;
+  auto kern = te_kernel<Epi, false>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
@@ -273,6 +395,12 @@ static int launch_retr(const void* A, const void* B, int Ma, int Nb, int Kp, int
   if (items < grid) grid = (int)items;
   kern<<<grid, TE_THREADS, TE_SMEM_BYTES, stream>>>(tmA, tmB, g, p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+template <int kMaxK>
+static int launch_retr(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, const RetrParams& p,
+                       int segs, cudaStream_t stream) {
+  return launch_epi<RetrEpi<kMaxK>>(A, B, Ma, Nb, Kp, lda, ldb, p, segs, stream);
 }
 
 int retrieval_segments(int Ma, int Nb) {
@@ -298,6 +426,27 @@ int retrieval_sweep(const void* V, const void* T, int Nv, int Mt, int Kp, int ld
   if (k == 0) return launch_retr<0>(V, T, Nv, Mt, Kp, ldv, ldt, p, segs, stream);
   if (k <= 16) return launch_retr<16>(V, T, Nv, Mt, Kp, ldv, ldt, p, segs, stream);
   return launch_retr<64>(V, T, Nv, Mt, Kp, ldv, ldt, p, segs, stream);
+}
+
+int retrieval_colmax(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, int segs, float* part_max,
+                     cudaStream_t stream) {
+  if (Nv <= 0 || Mt <= 0 || segs < 1 || !part_max || (reinterpret_cast<uintptr_t>(part_max) & 15)) return B2_EINVAL;
+  ColMaxParams p{part_max, 2 * segs};
+  return launch_epi<ColMaxEpi>(V, T, Nv, Mt, Kp, ldv, ldt, p, segs, stream);
+}
+
+int kth_largest(const float* vals, int rows, int cand, int k, float* thr, cudaStream_t s) {
+  if (rows <= 0 || cand <= 0 || cand > (1 << 20) || k <= 0 || !vals || !thr) return B2_EINVAL;
+  kth_largest_kernel<<<(rows + 7) / 8, 256, 0, s>>>(vals, rows, cand, k, thr);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int retrieval_collect(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, const float* thr,
+                      int col_offset, int segs, int* cnt, float* buf_s, int* buf_i, int cap, int* overflow,
+                      cudaStream_t stream) {
+  if (Nv <= 0 || Mt <= 0 || segs < 1 || cap < 1 || !thr || !cnt || !buf_s || !buf_i || !overflow) return B2_EINVAL;
+  CollectParams p{thr, col_offset, cnt, buf_s, buf_i, cap, overflow};
+  return launch_epi<CollectEpi>(V, T, Nv, Mt, Kp, ldv, ldt, p, segs, stream);
 }
 
 int topk_merge(const float* ps, const int* pi, int rows, int cand, int k, float* out_s, long long* out_i,

@@ -16,6 +16,7 @@ passes the same full ``text_features``), rank counts are all-reduced and the per
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -60,6 +61,39 @@ def _shard_rows(M: int, use_ddp: bool, group=None) -> Tuple[int, int, int, int]:
     return W, r, lo, hi
 
 
+def _topk2_enabled() -> bool:
+    """Two-sweep top-k (threshold, then collect) instead of the register lists. Opt-in: written after the GPU budget of
+    round 1 was spent, so it has not been measured yet (tests/test_gpu_z_topk_two_sweeps.py)."""
+    return os.environ.get("B200CLIP_TOPK2", "0") == "1"
+
+
+def _topk_two_sweeps(vop, top, lo: int, hi: int, k: int):
+    """Exact top-k of the text rows [lo, hi) for every video row, or (None, None) when a candidate buffer overflowed (the
+    caller then runs the register-list sweep). Sweep 1: maxima of 64 * segs disjoint column subsets per row -> their k-th
+    largest bounds the row's k-th best score from below; sweep 2: every s_ij >= that bound becomes a candidate (all ties
+    with the k-th score included); ``topk_merge`` orders them by (score desc, index asc)."""
+    dev = vop.device
+    N, K, Ms = vop.shape[0], vop.shape[1], hi - lo
+    st = stream_ptr(dev)
+    segs = ops._lib.lib().b200clip_retrieval_segments(N, Ms)
+    pm = torch.empty((N, 2 * segs, 32), dtype=torch.float32, device=dev)
+    call("retrieval_colmax", vop, top[lo:hi], N, Ms, K, vop.stride(0), top.stride(0), segs, pm, st)
+    thr = torch.empty(N, dtype=torch.float32, device=dev)
+    call("kth_largest", pm, N, 2 * segs * 32, k, thr, st)
+    cap = max(64, 8 * k)
+    cnt = torch.zeros(N + 1, dtype=torch.int32, device=dev)          # [N] candidate counts | overflow flag
+    bs = torch.empty((N, cap), dtype=torch.float32, device=dev)
+    bi = torch.full((N, cap), 0x7FFFFFFF, dtype=torch.int32, device=dev)
+    call("retrieval_collect", vop, top[lo:hi], N, Ms, K, vop.stride(0), top.stride(0), thr, lo, segs, cnt, bs, bi, cap,
+         cnt[N:], st)
+    if int(cnt[N].item()) != 0:
+        return None, None
+    out_s = torch.empty((N, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((N, k), dtype=torch.int64, device=dev)
+    call("topk_merge", bs, bi, N, cap, k, out_s, out_i, st)
+    return out_s, out_i
+
+
 def _sweep(vop, top, gt, k: int, use_ddp: bool, group=None, _shard=None):
     """Returns (counts [N] int32 or None, top-k scores [N,k] / indices [N,k] int64 or None).
     ``_shard=(lo, hi)`` restricts the sweep to text rows [lo, hi) of a single process (tests: shard additivity)."""
@@ -81,7 +115,11 @@ def _sweep(vop, top, gt, k: int, use_ddp: bool, group=None, _shard=None):
     k = min(k, M)
     Ms = hi - lo
     out_s = out_i = None
-    if Ms > 0:
+    if Ms > 0 and gt is None and 0 < k <= 16 and _topk2_enabled():
+        out_s, out_i = _topk_two_sweeps(vop, top, lo, hi, k)
+    if out_s is not None:
+        pass                                     # exact lists from the two-sweep path
+    elif Ms > 0:
         segs = ops._lib.lib().b200clip_retrieval_segments(N, Ms)
         ps = pi = None
         if k > 0:

@@ -292,6 +292,24 @@ int b200clip_topk_merge(const float* part_score, const int32_t* part_idx, int ro
                         float* out_score, int64_t* out_idx, void* stream);
 int b200clip_recall_hits(const int32_t* counts, int rows, const int32_t* k_values, int nk, uint64_t* hits,
                          void* stream);
+/* Two-sweep top-k (replaces the same chunked topk / cat / topk merges, retrieval_metrics_streaming.py:61-82, for k <= 16;
+ * opt-in on the host side with B200CLIP_TOPK2=1 until it has been measured): threshold first, then collect.
+ *   retrieval_colmax  : part_max[i][slot][e] = max of s_ij over the columns j of slot (segment x column half) whose
+ *                       position inside its 32-column chunk is e; part_max [n_video][2*segs][32] (16-byte aligned).
+ *                       The subsets are disjoint, so the k-th largest of row i's 64*segs values bounds its k-th best
+ *                       score from below.
+ *   kth_largest       : thr[row] = k-th largest (with multiplicity) of vals[row][0..cand); -inf when cand < k.
+ *   retrieval_collect : appends every (s_ij, col_offset + j) with s_ij >= thr[i] to row i's candidate buffer
+ *                       buf_s/buf_i [n_video][cap] (cnt [n_video] zeroed, buf_i pre-filled with INT32_MAX by the
+ *                       caller); *overflow = 1 if some row had more than cap candidates (the caller then falls back to
+ *                       retrieval_sweep's register lists). topk_merge(buf_s, buf_i, n_video, cap, k) gives the exact
+ *                       top-k by (score desc, index asc): every element tied with the k-th score is a candidate. */
+int b200clip_retrieval_colmax(const void* video, const void* text, int n_video, int n_text, int Kp, int ldv, int ldt,
+                              int segs, float* part_max, void* stream);
+int b200clip_kth_largest(const float* vals, int rows, int cand, int k, float* thr, void* stream);
+int b200clip_retrieval_collect(const void* video, const void* text, int n_video, int n_text, int Kp, int ldv, int ldt,
+                               const float* thr, int col_offset, int segs, int32_t* cnt, float* buf_s, int32_t* buf_i,
+                               int cap, int32_t* overflow, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K7  3D RoPE apply. Replaces Rope3D.forward's split / rotate_half / mul / add / cat graph and its autograd
