@@ -159,5 +159,6 @@ int querypool(int backward, const float* x, long long sb, long long sn, const fl
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                       uint32_t box_rows);
 int sm_count();
+int current_device();   // tmap.cu
 
 }  // namespace b2host

@@ -342,7 +342,8 @@ using namespace b2;
 
 template <int kMode, bool kXRes>
 static int launch_bw(const CUtensorMap& tmX, const CUtensorMap& tmY, const BwParams& p, int grid, cudaStream_t stream) {
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   constexpr int smem = BwSmem<kXRes>::kBytes;
   if (!attr_done) {
     if (cudaFuncSetAttribute(bw_kernel<kMode, kXRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)

@@ -339,7 +339,8 @@ using namespace b2;
 template <int kMode>
 static int launch_bw2(const CUtensorMap& tmX, const CUtensorMap& tmYs, const CUtensorMap& tmYo, const BwParams& p,
                       int grid, cudaStream_t stream) {
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   if (!attr_done) {
     if (cudaFuncSetAttribute(bw2_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM) != cudaSuccess)
       return B2_ECUDA;

@@ -529,7 +529,8 @@ using namespace b2;
 template <int kMode, int kNJ>
 static int launch_bw3(const CUtensorMap& tmX, const CUtensorMap& tmYs, const CUtensorMap& tmYo, const BwParams& p,
                       int grid, cudaStream_t stream) {
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   constexpr int smem = Bw3Cfg<kNJ>::kSmem;
   if (!attr_done) {
     if (cudaFuncSetAttribute(bw3_kernel<kMode, kNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)

@@ -176,7 +176,8 @@ static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int l
   if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, TE_BN))) return rc;
   auto kern = te_kernel<Epi, kOuterIsB>;
-  static bool attr_done = false;   // per template instantiation
+  static bool attr_done_dev[64] = {};   // per template instantiation
+  bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
       return B2_ECUDA;
@@ -207,7 +208,8 @@ static int launch_te2(const void* A, const void* B, int Ma, int Nb, int Kp, int 
   if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, 128))) return rc;      // each CTA loads 128 of the 256 block rows
   auto kern = te2_kernel<Epi, kOuterIsB>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE2_SMEM_BYTES) != cudaSuccess)
       return B2_ECUDA;

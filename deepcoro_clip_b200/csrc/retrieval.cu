@@ -371,7 +371,8 @@ static int launch_epi(const void* A, const void* B, int Ma, int Nb, int Kp, int 
     CUtensorMap tmB2;
     if ((rc = make_tmap_bf16_2d(&tmB2, B, Nb, Kp, ldb, 128))) return rc;
     auto kern2 = te2_kernel<Epi, false>;
-    static bool attr2_done = false;
+    static bool attr2_done_dev[64] = {};
+  bool& attr2_done = attr2_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
     if (!attr2_done) {
       if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, TE2_SMEM_BYTES) != cudaSuccess)
         return B2_ECUDA;
@@ -384,7 +385,8 @@ static int launch_epi(const void* A, const void* B, int Ma, int Nb, int Kp, int 
     return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
   }
   auto kern = te_kernel<Epi, false>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
       return B2_ECUDA;

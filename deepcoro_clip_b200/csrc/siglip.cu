@@ -376,7 +376,8 @@ int siglip_dense_fwd(const void* V, const void* T, int B, int Tn, int Kp, int ld
   if ((rc = make_tmap_bf16_2d(&tmA, V, B, Kp, ldv, TE_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, T, Tn, Kp, ldt, TE_BN))) return rc;
   auto kern = te_kernel<SoftplusEpi, true>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
       return B2_ECUDA;
@@ -400,7 +401,8 @@ static int launch_ent(const void* V, const void* T, int B, int Tn, int Kp, int l
   if ((rc = make_tmap_bf16_2d(&tmA, V, B, Kp, ldv, TE_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, T, Tn, Kp, ldt, TE_BN))) return rc;
   auto kern = te_kernel<EntEpi<kStats>, false>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
       return B2_ECUDA;

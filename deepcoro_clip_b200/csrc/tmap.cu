@@ -41,12 +41,16 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return r == CUDA_SUCCESS ? B2_OK : B2_EINVAL;
 }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
 int sm_count() {
-  static int n = 0;
+  static int n = 0;     // one device model per process (every GPU of a B200 box has the same SM count)
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
     if (n <= 0) n = 148;
   }
   return n;
