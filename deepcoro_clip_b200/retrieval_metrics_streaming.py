@@ -76,7 +76,8 @@ def _topk_two_sweeps(vop, top, lo: int, hi: int, k: int):
     N, K, Ms = vop.shape[0], vop.shape[1], hi - lo
     st = stream_ptr(dev)
     segs = ops._lib.lib().b200clip_retrieval_segments(N, Ms)
-    pm = torch.empty((N, 2 * segs, 32), dtype=torch.float32, device=dev)
+    # -inf: a (row, slot) the sweep never visits (empty segment) must not contribute a maximum
+    pm = torch.full((N, 2 * segs, 32), float("-inf"), dtype=torch.float32, device=dev)
     call("retrieval_colmax", vop, top[lo:hi], N, Ms, K, vop.stride(0), top.stride(0), segs, pm, st)
     thr = torch.empty(N, dtype=torch.float32, device=dev)
     call("kth_largest", pm, N, 2 * segs * 32, k, thr, st)
