@@ -77,6 +77,8 @@ inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); r
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
 struct float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
@@ -84,26 +86,29 @@ namespace emul {
 // Runs kernel body `f` (a callable without arguments) for a 1-D grid of 1-D blocks. Blocks are sequential; a thread that
 // returns leaves its barriers (so early-exiting warps do not block the rest of the block).
 template <class F>
-inline void launch(unsigned grid, unsigned block, F f) {
-  gridDim = Dim{grid, 1, 1};
+inline void launch(Dim grid, unsigned block, F f) {
+  gridDim = grid;
   blockDim = Dim{block, 1, 1};
-  for (unsigned b = 0; b < grid; ++b) {
-    Block bs(block);
-    // a partially filled last warp would need a smaller warp barrier: the library only launches multiples of 32
-    std::vector<std::thread> th;
-    th.reserve(block);
-    for (unsigned t = 0; t < block; ++t)
-      th.emplace_back([&, t, b] {
-        threadIdx = Dim{t, 0, 0};
-        blockIdx = Dim{b, 0, 0};
-        tl_block = &bs;
-        tl_warp = &bs.warps[t / 32];
-        tl_lane = (int)(t % 32);
-        f();
-        tl_warp->bar.arrive_and_drop();
-        bs.bar.arrive_and_drop();
-      });
-    for (auto& x : th) x.join();
-  }
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned b = 0; b < grid.x; ++b) {
+      Block bs(block);
+      // a partially filled last warp would need a smaller warp barrier: the library only launches multiples of 32
+      std::vector<std::thread> th;
+      th.reserve(block);
+      for (unsigned t = 0; t < block; ++t)
+        th.emplace_back([&, t, b, by] {
+          threadIdx = Dim{t, 0, 0};
+          blockIdx = Dim{b, by, 0};
+          tl_block = &bs;
+          tl_warp = &bs.warps[t / 32];
+          tl_lane = (int)(t % 32);
+          f();
+          tl_warp->bar.arrive_and_drop();
+          bs.bar.arrive_and_drop();
+        });
+      for (auto& x : th) x.join();
+    }
 }
+template <class F>
+inline void launch(unsigned grid, unsigned block, F f) { launch(Dim{grid, 1, 1}, block, f); }
 }  // namespace emul
