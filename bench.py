@@ -152,7 +152,6 @@ def retrieval_leg(dev, world, rank, cpu_baseline=False):
     k/128, exact in bf16, every dot product exact in fp32 in any order), text database sharded by rows across ranks.
     Timed through the public API (operand packing, tensor-core ground-truth similarity, sweep, rank counts all-reduced,
     recall hits and the fp64 MRR sum on the device, results read back every sweep)."""
-    import numpy as np
     import torch
     import torch.distributed as dist
     from deepcoro_clip_b200.retrieval_metrics_streaming import compute_recall_at_k_streaming, mrr_sum_from_counts

@@ -19,7 +19,6 @@ from __future__ import annotations
 import os
 from typing import Dict, List, Optional, Tuple
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
