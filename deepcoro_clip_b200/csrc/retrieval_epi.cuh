@@ -197,11 +197,17 @@ struct CollectEpi {
                                                const uint32_t (&acc)[32]) {
     const int cbase = ctx.col0 + c * 32;
     const int nvalid = ctx.Nb - cbase;
+    // cheap pre-test (one FMNMX per element): most chunks hold no candidate of this row; padded columns read 0 and can
+    // only make the pre-test pass spuriously — the exact mask below ignores them
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, __uint_as_float(acc[e]));
+    if (!(cmax >= st.thr) || !ctx.row_ok) return;
     uint32_t m = 0;
 #pragma unroll
     for (int e = 0; e < 32; ++e) m |= (__uint_as_float(acc[e]) >= st.thr) ? (1u << e) : 0u;
     if (nvalid < 32) m = nvalid <= 0 ? 0u : (m & ((1u << nvalid) - 1u));
-    if (m != 0u && ctx.row_ok) {
+    if (m != 0u) {
       const int n = __popc(m);
       int pos = atomicAdd(p.cnt + ctx.row, n);
       if (pos + n > p.cap) *p.overflow = 1;
