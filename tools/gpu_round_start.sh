@@ -13,7 +13,7 @@ timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
 echo "smoke rc=$? : $(tail -1 $OUT/${TAG}_smoke.log)"
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 echo "bench rc=$? : $(cut -c1-300 $OUT/${TAG}_bench.json)"
-for t in multipos clspool tokens; do
+for t in multipos clspool tokens topk; do
   timeout 300 python tools/gpu_bench_${t}.py > $OUT/${TAG}_${t}.log 2>&1
   echo "$t rc=$? : $(tail -2 $OUT/${TAG}_${t}.log | cut -c1-300)"
 done
