@@ -26,11 +26,17 @@ struct Dim { unsigned x = 1, y = 1, z = 1; };
 struct Warp {
   std::barrier<> bar{32};
   uint64_t slot[32];
+  uint32_t frag[32][8];      // mma / ldmatrix operand exchange (pool_mma_prims_emul.h)
 };
 struct Block {
-  explicit Block(unsigned n) : bar((std::ptrdiff_t)n), warps((n + 31) / 32) {}
+  explicit Block(unsigned n, size_t smem_bytes = 0)
+      : bar((std::ptrdiff_t)n), warps((n + 31) / 32), smem_store(smem_bytes + 2048) {
+    dyn_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_store.data()) + 1023) & ~uintptr_t(1023));
+  }
   std::barrier<> bar;
   std::vector<Warp> warps;
+  std::vector<unsigned char> smem_store;
+  unsigned char* dyn_smem;   // 1024-byte aligned dynamic shared memory of the running block
 };
 inline thread_local Warp* tl_warp = nullptr;
 inline thread_local Block* tl_block = nullptr;
@@ -79,6 +85,8 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }
+struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
@@ -86,12 +94,12 @@ namespace emul {
 // Runs kernel body `f` (a callable without arguments) for a 1-D grid of 1-D blocks. Blocks are sequential; a thread that
 // returns leaves its barriers (so early-exiting warps do not block the rest of the block).
 template <class F>
-inline void launch(Dim grid, unsigned block, F f) {
+inline void launch(Dim grid, unsigned block, F f, size_t smem_bytes = 0) {
   gridDim = grid;
   blockDim = Dim{block, 1, 1};
   for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned b = 0; b < grid.x; ++b) {
-      Block bs(block);
+      Block bs(block, smem_bytes);
       // a partially filled last warp would need a smaller warp barrier: the library only launches multiples of 32
       std::vector<std::thread> th;
       th.reserve(block);
