@@ -7,6 +7,7 @@ feed-forward block and the LayerNorms around it act on [B, D] vectors and stay o
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -14,6 +15,13 @@ import torch.nn.functional as F
 
 from . import ops
 from ._lib import DTYPE_CODE, call, i64, lib, stream_ptr
+
+
+def _fused_dq_enabled() -> bool:
+    """B200CLIP_POOL_FUSED_DQ=1: the backward accumulates the query gradient in the same pass over x instead of launching
+    the weighted-sum kernel over all of x again. Opt-in: written after the round-1 GPU budget was spent — executed under
+    the CPU emulation of the MMA kernels (tests/test_emulated_pool_kernels.py), not yet on hardware."""
+    return os.environ.get("B200CLIP_POOL_FUSED_DQ", "0") == "1"
 
 
 class _StreamPool(torch.autograd.Function):
@@ -81,10 +89,21 @@ class _StreamPool(torch.autograd.Function):
         dx = torch.empty((B, N, D), dtype=x.dtype, device=dev)
         ds = torch.empty((B, H, N), dtype=torch.float32, device=dev)
         mb = i64(mk.stride(0) if mk is not None else 0)
+        dqt = None
+        if (ctx.needs_input_grad[1] and _fused_dq_enabled() and x.dtype in (torch.bfloat16, torch.float16) and H <= 8
+                and D % 128 == 0 and D <= 1024 and x.data_ptr() % 16 == 0):
+            # query gradient from the SAME pass over x (kDq kernels): per-(b, split) partials, summed by the merge kernel
+            Sb = lib().b200clip_attnpool_bwd_splits(B, N)
+            pdq = torch.zeros((B, Sb, H, D), dtype=torch.float32, device=dev)
+            call("attnpool_bwd_dx_dq", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), mk, mb, qt32, dxbar,
+                 xbar, m, l, B, N, D, H, dx, ds, sa if dsa is not None else None, dsa,
+                 drop_p if dsa is not None else 0.0, drop_seed, dlse, pdq, st)
+            dqt = torch.zeros((H, D), dtype=torch.float32, device=dev)
+            call("attnpool_merge", None, None, pdq, B, Sb, H, D, dqt, None, None, 1, None, None, st)
+            return (dx if ctx.needs_input_grad[0] else None), dqt, None, None, None, None
         call("attnpool_bwd_dx", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), mk, mb, qt32, dxbar, xbar, m,
              l, B, N, D, H, dx, ds, sa if dsa is not None else None, dsa, drop_p if dsa is not None else 0.0, drop_seed,
              dlse, st)
-        dqt = None
         if ctx.needs_input_grad[1]:
             S = ctx.S
             pa = torch.empty((B, S, H, D), dtype=torch.float32, device=dev)

@@ -315,6 +315,17 @@ int b200clip_attnpool_bwd_dx(const void* x, int dtype, int64_t x_sb, int64_t x_s
                          drop_p, (unsigned long long)drop_seed, dlse, S(stream));
 }
 
+int b200clip_attnpool_bwd_splits(int B, int N) { return attnpool_bwd_splits(B, N); }
+
+int b200clip_attnpool_bwd_dx_dq(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask,
+                                int64_t mask_sb, const float* qt, const float* dxbar, const float* xbar, const float* m,
+                                const float* l, int B, int N, int D, int heads, void* dx, float* ds, const float* sa,
+                                const float* dsa, float drop_p, int64_t drop_seed, const float* dlse, float* part_dq,
+                                void* stream) {
+  return attnpool_bwd_dx_dq(x, dtype, x_sb, x_sn, mask, mask_sb, qt, dxbar, xbar, m, l, B, N, D, heads, dx, ds, sa, dsa,
+                            drop_p, (unsigned long long)drop_seed, dlse, part_dq, S(stream));
+}
+
 int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,
                        const float* ln_b, const float* query, const uint8_t* mask, int64_t mask_sb, int B, int N, int D,
                        float eps, float* out, const float* dout, float* dx, float* dpos, float* dln_w, float* dln_b,

@@ -407,4 +407,18 @@ int attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const 
   }
 }
 
+// attnpool_bwd_dx with the query gradient fused into the same pass over x (16-bit x on the MMA kernels only): part_dq
+// [B, attnpool_bwd_splits(B, N), H, D] zeroed by the caller, summed afterwards by attnpool_merge(sum_over_b = 1).
+int attnpool_bwd_dx_dq(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                       const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
+                       int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
+                       unsigned long long drop_seed, const float* dlse, float* part_dq, cudaStream_t s) {
+  if (!x || !qt || !dxbar || !xbar || !m || !l || !dx || !ds || !part_dq || H > 16) return B2_EINVAL;
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && (!sa || !dsa))) return B2_EINVAL;
+  if (!(attnpool_mma_ok(x, dtype, sb, sn, D, H) && sb == (long long)N * sn && (reinterpret_cast<uintptr_t>(dx) % 16) == 0))
+    return B2_ENOSYS;
+  return attnpool_bwd_dx_mma(x, dtype, sb, sn, mask, mb, qt, dxbar, xbar, m, l, B, N, D, H, dx, ds, sa, dsa, drop_p,
+                             drop_seed, dlse, s, part_dq);
+}
+
 }  // namespace b2host

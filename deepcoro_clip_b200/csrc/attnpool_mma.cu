@@ -75,17 +75,26 @@ static size_t pm_bwd_smem(int D, int stages) {
          64 + 2048;
 }
 
-int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
-                        const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
-                        int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
-                        unsigned long long drop_seed, const float* dlse, cudaStream_t s) {
+// token splits of the backward grid (B x S CTAs); part_dq of the fused-dq variant is [B, S, H, D]
+int attnpool_bwd_splits(int B, int N) {
+  if (B <= 0 || N <= 0) return 1;
   int S = sm_count() / B;
   const int maxS = (N + 2 * PM_TT - 1) / (2 * PM_TT);
   if (S > maxS) S = maxS;
   if (S < 1) S = 1;
-  const int stages = pm_stages(D, pm_bwd_smem(D, 0), D % 256 == 0);
-  PmBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, S, sa, dsa, drop_p, drop_seed, stages, dlse};
-  const size_t smem = pm_bwd_smem(D, stages);
+  return S;
+}
+
+int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                        const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
+                        int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
+                        unsigned long long drop_seed, const float* dlse, cudaStream_t s, float* part_dq) {
+  const int S = attnpool_bwd_splits(B, N);
+  const size_t dq_smem = part_dq ? 2 * 8 * (PM_TT + 8) * 2 : 0;
+  const int stages = pm_stages(D, pm_bwd_smem(D, 0) + dq_smem, D % 256 == 0);
+  PmBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, S, sa, dsa, drop_p, drop_seed, stages, dlse,
+                part_dq};
+  const size_t smem = pm_bwd_smem(D, stages) + dq_smem;
   CUtensorMap tmx;
   {
     int rc = make_tmap_bf16_2d(&tmx, x, (uint64_t)B * N, D, sn, PM_TT);
@@ -98,10 +107,22 @@ int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, co
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B2_ECUDA; \
     k<<<grid, NW_ * 32, smem, s>>>(tmx, p);                                                                          \
   }
+#define PM_LAUNCH_DQ(TT_, NW_)                                                                                       \
+  {                                                                                                                  \
+    auto k = pool_bwd_mma_kernel<TT_, NW_, true>;                                                                    \
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B2_ECUDA; \
+    k<<<grid, NW_ * 32, smem, s>>>(tmx, p);                                                                          \
+  }
   const bool wide = D % 256 == 0;
-  if (dtype == 1) { if (wide) PM_LAUNCH(__nv_bfloat16, 16) else PM_LAUNCH(__nv_bfloat16, 8) }
-  else { if (wide) PM_LAUNCH(__half, 16) else PM_LAUNCH(__half, 8) }
+  if (part_dq) {
+    if (dtype == 1) { if (wide) PM_LAUNCH_DQ(__nv_bfloat16, 16) else PM_LAUNCH_DQ(__nv_bfloat16, 8) }
+    else { if (wide) PM_LAUNCH_DQ(__half, 16) else PM_LAUNCH_DQ(__half, 8) }
+  } else {
+    if (dtype == 1) { if (wide) PM_LAUNCH(__nv_bfloat16, 16) else PM_LAUNCH(__nv_bfloat16, 8) }
+    else { if (wide) PM_LAUNCH(__half, 16) else PM_LAUNCH(__half, 8) }
+  }
 #undef PM_LAUNCH
+#undef PM_LAUNCH_DQ
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

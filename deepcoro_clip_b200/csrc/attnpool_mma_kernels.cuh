@@ -218,14 +218,20 @@ struct PmBwdParams {
   const float* sa; const float* dsa; float drop_p; unsigned long long drop_seed;
   int stages;
   const float* dlse;      // [B, H] upstream gradient of lse_h = m_h + log l_h (may be null)
+  float* part_dq;         // kDq kernels: [B, S, H, D] per-(b, split) partials of dqt = sum_n ds_hn x_n (zeroed by the caller)
 };
 
 // shared memory: x / dx tiles 2 * 32 * D * 2 | qt hi, qt lo, dxbar hi, dxbar lo: 4 x [8][D+8] | Wt [D][24] 16-bit
 //                (k-contiguous rows of [dxbar ; qt], 48-byte pitch) | C hi [32][16], C lo [32][16] |
-//                S/T partials [4][32][16] fp32 | c, m, 1/l [3][8] fp32
-template <typename T, int NW>
+//                S/T partials [4][32][16] fp32 | c, m, 1/l [3][8] fp32 | barriers | kDq: ds^T hi, lo [8][40] 16-bit
+// kDq = true additionally accumulates dqt = sum_n ds_hn x_n from the SAME pass over x (the forward's phase 2 with P := ds,
+// [D, 8] fp32 accumulator in registers, written as per-(b, split) partials): the separate "given weights" forward launch
+// that re-reads all of x for the query gradient disappears (bwd reads x once instead of twice).
+template <typename T, int NW, bool kDq = false>
 __global__ void __launch_bounds__(NW * 32) pool_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, PmBwdParams p) {
   constexpr int KS = NW / 2;
+  constexpr int MAXC = 128 / NW;        // 16-channel chunks per warp at D = 1024 (kDq accumulator)
+  constexpr int PP = PM_TT + 8;
   B2_DYN_SMEM(smem_raw);
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int D = p.D, row_bytes = D * 2, QP = D + 8;
@@ -243,6 +249,8 @@ __global__ void __launch_bounds__(NW * 32) pool_bwd_mma_kernel(const __grid_cons
   float* s_m = s_c + 8;
   float* s_il = s_m + 8;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_il + 8);
+  uint16_t* t_hi = reinterpret_cast<uint16_t*>(full_bar + 4);      // kDq only: ds^T [8][PP] hi / lo
+  uint16_t* t_lo = t_hi + 8 * PP;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.x, sp = blockIdx.y;
@@ -293,6 +301,11 @@ __global__ void __launch_bounds__(NW * 32) pool_bwd_mma_kernel(const __grid_cons
   const uint32_t qh_addr = smem_u32(q_hi), ql_addr = smem_u32(q_lo), dh_addr = smem_u32(d_hi), dl_addr = smem_u32(d_lo);
   const uint32_t wt_addr = smem_u32(wt), ch_addr = smem_u32(c_hi), cl_addr = smem_u32(c_lo);
   const int DW = D / NW;
+  const int nchunk = DW / 16;
+  const uint32_t th_addr = smem_u32(t_hi), tl_addr = smem_u32(t_lo);
+  float dq[kDq ? MAXC : 1][4];
+#pragma unroll
+  for (int c = 0; c < (kDq ? MAXC : 1); ++c) dq[c][0] = dq[c][1] = dq[c][2] = dq[c][3] = 0.f;
 
   int buf = 0;
   for (int t0 = n0; t0 < n1; t0 += PM_TT, buf = (buf + 1 == NS ? 0 : buf + 1)) {
@@ -357,8 +370,33 @@ __global__ void __launch_bounds__(NW * 32) pool_bwd_mma_kernel(const __grid_cons
       c_lo[lane * 16 + h] = PmT<T>::bits(a - PmT<T>::val(ah));
       c_hi[lane * 16 + 8 + h] = dh2;
       c_lo[lane * 16 + 8 + h] = PmT<T>::bits(dsv - PmT<T>::val(dh2));
+      if (kDq) {                              // the same ds, token-contiguous per head: B operand of the dq product
+        t_hi[h * PP + lane] = dh2;
+        t_lo[h * PP + lane] = PmT<T>::bits(dsv - PmT<T>::val(dh2));
+      }
     }
     __syncthreads();
+    if (kDq) {
+      // ---- phase 2b: dq[d, h] += sum_tok x[tok, d] ds[h, tok] (the forward's phase 2 with P := ds); the warp reads only
+      //      its own channels [warp*DW, +DW) of the x tile, the ones it overwrites with dx right below ----
+#pragma unroll
+      for (int ks = 0; ks < PM_TT / 16; ++ks) {
+        const uint32_t off = (uint32_t)(g * PP + ks * 16 + 2 * t) * 2;
+        const uint32_t bh0 = lds32(th_addr + off), bh1 = lds32(th_addr + off + 16);
+        const uint32_t bl0 = lds32(tl_addr + off), bl1 = lds32(tl_addr + off + 16);
+        const int trow = ks * 16 + (lane & 7) + (lane >> 4) * 8;
+#pragma unroll
+        for (int c = 0; c < (kDq ? MAXC : 1); ++c) {
+          if (c < nchunk) {
+            uint32_t a[4];
+            ldsm_x4_trans(a, tile_addr(tile, trow, ((warp * DW + c * 16) >> 3) + ((lane >> 3) & 1), row_bytes));
+            PmT<T>::mma(dq[c], a, bl0, bl1);
+            PmT<T>::mma(dq[c], a, bh0, bh1);
+          }
+        }
+      }
+      __syncwarp();                           // every lane's reads of the tile precede the dx staging stores of the warp
+    }
     // ---- phase 2: dx[tok, d] = C . Wt^T, warp owns channels [warp*DW, +DW); staged into the (now free) x tile ----
 #pragma unroll
     for (int tg = 0; tg < 2; ++tg) {
@@ -387,6 +425,20 @@ __global__ void __launch_bounds__(NW * 32) pool_bwd_mma_kernel(const __grid_cons
         const int r = i / cpr, c = i - r * cpr;
         const uint4 v = lds128v(tile_addr(tile, r, c, row_bytes));
         *reinterpret_cast<uint4*>(dxb + (size_t)(t0 + r) * D + c * 8) = v;
+      }
+    }
+  }
+  if (kDq && p.part_dq) {
+    // rows d = g / g + 8 of each chunk, heads 2t / 2t + 1 (the accumulator layout of the forward's phase 2)
+#pragma unroll
+    for (int c = 0; c < (kDq ? MAXC : 1); ++c) {
+      if (c < nchunk) {
+        const int d = warp * DW + c * 16 + g;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int h = 2 * t + (e & 1), dd = d + (e >> 1) * 8;
+          if (h < p.H) p.part_dq[(((size_t)b * p.S + sp) * p.H + h) * D + dd] = dq[c][e];
+        }
       }
     }
   }

@@ -57,10 +57,11 @@ int attnpool_fwd_mma(const void* x, int dtype, long long sb, long long sn, const
                      float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
                      float* part_l2, cudaStream_t s);
 
+int attnpool_bwd_splits(int B, int N);
 int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
                         const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
                         int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
-                        unsigned long long drop_seed, const float* dlse, cudaStream_t s);
+                        unsigned long long drop_seed, const float* dlse, cudaStream_t s, float* part_dq = nullptr);
 
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
@@ -148,6 +149,10 @@ int attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const 
                     const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
                     int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
                     unsigned long long drop_seed, const float* dlse, cudaStream_t s);
+int attnpool_bwd_dx_dq(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                       const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
+                       int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
+                       unsigned long long drop_seed, const float* dlse, float* part_dq, cudaStream_t s);
 
 // querypool.cu
 int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,

@@ -358,6 +358,16 @@ int b200clip_attnpool_bwd_dx(const void* x, int dtype, int64_t x_sb, int64_t x_s
                              const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l,
                              int B, int N, int D, int heads, void* dx, float* ds, const float* sa, const float* dsa,
                              float drop_p, int64_t drop_seed, const float* dlse, void* stream);
+/* attnpool_bwd_dx with the query gradient accumulated in the SAME pass over x (16-bit x, heads <= 8, D % 128 == 0: the
+ * MMA kernels; -38 otherwise and the caller uses the separate weighted-sum launch): part_dq [B, attnpool_bwd_splits(B, N),
+ * heads, D] fp32, zeroed by the caller; dqt[h, :] = sum over (b, split) = attnpool_merge(NULL, NULL, part_dq, ...,
+ * sum_over_b = 1). Opt-in on the host side (B200CLIP_POOL_FUSED_DQ=1) until it has been timed on hardware. */
+int b200clip_attnpool_bwd_splits(int B, int N);
+int b200clip_attnpool_bwd_dx_dq(const void* x, int dtype, int64_t x_sb, int64_t x_sn, const uint8_t* mask,
+                                int64_t mask_sb, const float* qt, const float* dxbar, const float* xbar, const float* m,
+                                const float* l, int B, int N, int D, int heads, void* dx, float* ds, const float* sa,
+                                const float* dsa, float drop_p, int64_t drop_seed, const float* dlse, float* part_dq,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).

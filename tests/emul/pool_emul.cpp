@@ -32,14 +32,25 @@ void emul_pool_fwd(const void* x, int dtype, const unsigned char* mask, const fl
   }
 }
 
+// part_dq != null: the fused-dq instantiation (kDq = true), part_dq [B, S, H, D] zeroed by the caller
 void emul_pool_bwd(const void* x, int dtype, const unsigned char* mask, const float* qt, const float* dxbar,
                    const float* xbar, const float* m, const float* l, int B, int N, int D, int H, int S, int NW, int stages,
-                   void* dx, float* ds, const float* dlse) {
+                   void* dx, float* ds, const float* dlse, float* part_dq) {
   PmBwdParams p{x, (long long)N * D, (long long)D, mask, (long long)N, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, S,
-                nullptr, nullptr, 0.f, 0ull, stages, dlse};
+                nullptr, nullptr, 0.f, 0ull, stages, dlse, part_dq};
   CUtensorMap tm{x, (uint64_t)B * N, (uint64_t)D, (long long)D};
   const emul::Dim grid{(unsigned)B, (unsigned)S, 1};
-  const size_t smem = bwd_smem(D, stages);
+  const size_t smem = bwd_smem(D, stages) + 2 * 8 * (PM_TT + 8) * 2;
+  if (part_dq) {
+    if (dtype == 1) {
+      if (NW == 8) emul::launch(grid, 256, [&] { pool_bwd_mma_kernel<__nv_bfloat16, 8, true>(tm, p); }, smem);
+      else emul::launch(grid, 512, [&] { pool_bwd_mma_kernel<__nv_bfloat16, 16, true>(tm, p); }, smem);
+    } else {
+      if (NW == 8) emul::launch(grid, 256, [&] { pool_bwd_mma_kernel<__half, 8, true>(tm, p); }, smem);
+      else emul::launch(grid, 512, [&] { pool_bwd_mma_kernel<__half, 16, true>(tm, p); }, smem);
+    }
+    return;
+  }
   if (dtype == 1) {
     if (NW == 8) emul::launch(grid, 256, [&] { pool_bwd_mma_kernel<__nv_bfloat16, 8>(tm, p); }, smem);
     else emul::launch(grid, 512, [&] { pool_bwd_mma_kernel<__nv_bfloat16, 16>(tm, p); }, smem);

@@ -91,8 +91,10 @@ def test_pool_forward_given_weights_under_emulation(emul):
     assert np.abs(pa.sum(1) - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6
 
 
-@pytest.mark.parametrize("B,N,D,H,S,NW,masked", [(2, 70, 128, 8, 2, 8, False), (1, 45, 256, 4, 1, 16, True)])
-def test_pool_backward_kernel_under_emulation(emul, B, N, D, H, S, NW, masked):
+@pytest.mark.parametrize("fused_dq", [False, True])
+@pytest.mark.parametrize("B,N,D,H,S,NW,masked", [(2, 70, 128, 8, 2, 8, False), (1, 45, 256, 4, 1, 16, True),
+                                                (2, 100, 384, 8, 3, 8, True)])
+def test_pool_backward_kernel_under_emulation(emul, B, N, D, H, S, NW, masked, fused_dq):
     xb, x, qt, mask = make_inputs(B, N, D, H, 4, masked)
     rng = np.random.default_rng(5)
     dxbar = rng.standard_normal((B, H, D)).astype(np.float32)
@@ -100,8 +102,9 @@ def test_pool_backward_kernel_under_emulation(emul, B, N, D, H, S, NW, masked):
     xbar = np.einsum("bhn,bnd->bhd", a, x)
     dx = np.zeros((B, N, D), np.uint16)
     ds = np.zeros((B, H, N), np.float32)
+    part_dq = np.zeros((B, S, H, D), np.float32) if fused_dq else None
     emul.emul_pool_bwd(ptr(xb), 1, ptr(mask), ptr(qt), ptr(dxbar), ptr(xbar.astype(np.float32)), ptr(m.astype(np.float32)),
-                       ptr(l.astype(np.float32)), B, N, D, H, S, NW, 2, ptr(dx), ptr(ds), None)
+                       ptr(l.astype(np.float32)), B, N, D, H, S, NW, 2, ptr(dx), ptr(ds), None, ptr(part_dq))
     c = np.einsum("bhd,bhd->bh", dxbar.astype(np.float64), xbar)
     tdot = np.einsum("bhd,bnd->bhn", dxbar.astype(np.float64), x)
     ds_ref = a * (tdot - c[..., None])
@@ -111,3 +114,8 @@ def test_pool_backward_kernel_under_emulation(emul, B, N, D, H, S, NW, masked):
     # dx leaves as bf16 and its product uses the 16-bit hi parts of dxbar / qt only: bf16-level accuracy by design
     assert np.abs(got - dx_ref).max() <= 1e-2 * np.abs(dx_ref).max()
     assert np.linalg.norm(got - dx_ref) <= 4e-3 * np.linalg.norm(dx_ref)
+    if fused_dq:
+        # the opt-in kDq instantiation: dqt = sum_{b, n} ds_hn x_n from the same pass (written after the GPU budget was spent)
+        dq_ref = np.einsum("bhn,bnd->hd", ds_ref, x)
+        got_dq = part_dq.sum((0, 1))
+        assert np.abs(got_dq - dq_ref).max() <= 2e-5 * np.abs(dq_ref).max() + 1e-6

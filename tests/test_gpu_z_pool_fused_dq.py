@@ -1,0 +1,55 @@
+"""GPU parity of the OPT-IN fused query gradient of the attention-pool backward (B200CLIP_POOL_FUSED_DQ=1: kDq kernels,
+b200clip_attnpool_bwd_dx_dq) against the default two-launch path and the float64 reference: dx identical bit for bit
+(same kernel body), the query / in-projection gradients equal to fp32 rounding.
+
+Written after round 1's GPU budget was spent; the kernels were executed under the CPU emulation of mma.sync / ldmatrix
+(tests/test_emulated_pool_kernels.py). Like the path itself, these tests are opt-in until it has run on hardware:
+B200CLIP_RUN_UNVERIFIED=1 (set by tools/gpu_round_start.sh)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B200CLIP_RUN_UNVERIFIED", "0") != "1",
+                                 reason="opt-in path not yet run on hardware: set B200CLIP_RUN_UNVERIFIED=1")]
+DEV = "cuda:0"
+
+
+def _grads(mod, x, mask, go):
+    for p in mod.parameters():
+        p.grad = None
+    xx = x.clone().requires_grad_(True)
+    out = mod(xx, mask)
+    (out.float() * go).sum().backward()
+    torch.cuda.synchronize()
+    return out.detach(), xx.grad.detach(), {n: p.grad.detach().clone() for n, p in mod.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("B,N,D,H,dtype,masked", [(4, 3136, 512, 8, torch.bfloat16, False), (3, 777, 256, 4, torch.float16, True),
+                                                   (2, 197, 384, 8, torch.bfloat16, True)])
+def test_fused_dq_matches_two_launch_path(B, N, D, H, dtype, masked, monkeypatch):
+    from deepcoro_clip_b200 import _lib
+    from deepcoro_clip_b200.attention_pool import AttentionPool
+    torch.manual_seed(B * 1000 + N)
+    mod = AttentionPool(D, H).to(DEV).eval()
+    x = torch.randn(B, N, D, device=DEV).to(dtype)
+    mask = None
+    if masked:
+        mask = torch.rand(B, N, device=DEV) < 0.1
+        mask[:, 0] = False
+    go = torch.randn(B, D, device=DEV)
+    monkeypatch.setenv("B200CLIP_POOL_FUSED_DQ", "0")
+    l0 = _lib.LAUNCHES
+    o0, dx0, g0 = _grads(mod, x, mask, go)
+    n_default = _lib.LAUNCHES - l0
+    monkeypatch.setenv("B200CLIP_POOL_FUSED_DQ", "1")
+    l0 = _lib.LAUNCHES
+    o1, dx1, g1 = _grads(mod, x, mask, go)
+    n_fused = _lib.LAUNCHES - l0
+    assert n_fused == n_default - 1                      # the weighted-sum pass over x is gone
+    assert torch.equal(o0, o1) and torch.equal(dx0, dx1)
+    assert set(g0) == set(g1)
+    for name in g0:
+        a, b = g0[name].double(), g1[name].double()
+        assert (a - b).norm() <= 2e-5 * a.norm() + 1e-9, name

@@ -13,6 +13,8 @@ timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
 echo "smoke rc=$? : $(tail -1 $OUT/${TAG}_smoke.log)"
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 echo "bench rc=$? : $(cut -c1-300 $OUT/${TAG}_bench.json)"
+B200CLIP_POOL_FUSED_DQ=1 timeout 300 python tools/gpu_bench_tokens.py > $OUT/${TAG}_tokens_fused_dq.log 2>&1
+echo "tokens (fused dq) rc=$? : $(tail -2 $OUT/${TAG}_tokens_fused_dq.log | cut -c1-300)"
 for t in multipos clspool tokens topk; do
   timeout 300 python tools/gpu_bench_${t}.py > $OUT/${TAG}_${t}.log 2>&1
   echo "$t rc=$? : $(tail -2 $OUT/${TAG}_${t}.log | cut -c1-300)"
