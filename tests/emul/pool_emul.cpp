@@ -2,6 +2,7 @@
 // libb200clip.so) against the emulated primitives. Launch geometry and shared-memory sizing follow attnpool_mma.cu.
 #include "pool_mma_prims_emul.h"
 #include "../../deepcoro_clip_b200/csrc/attnpool_mma_kernels.cuh"
+#include "../../deepcoro_clip_b200/csrc/attnpool_kernels.cuh"
 
 using namespace b2;
 
@@ -61,3 +62,150 @@ void emul_pool_bwd(const void* x, int dtype, const unsigned char* mask, const fl
 }
 
 }  // extern "C"
+
+// ---- the attention-pool entry points of include/b200clip.h with the library's own dispatch and launch geometry
+//      (attnpool.cu / attnpool_mma.cu on a 148-SM device), so the package's Python host code can run on top of the
+//      emulated kernels unchanged (tests/test_emulated_pool_module.py). `stream` is ignored. ----
+static const int kSms = 148;
+static bool mma_ok(const void* x, int dtype, long long sb, long long sn, int D, int H, int N) {
+  return (dtype == 1 || dtype == 2) && H <= 8 && D % 128 == 0 && D <= 1024 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
+         (sn % 8) == 0 && sb == (long long)N * sn;
+}
+static int stages_for(int D, size_t fixed, bool wide) {
+  if (!wide && (size_t)2 * PM_TT * D * 2 + fixed <= 112 * 1024) return 2;
+  int st = 4;
+  while (st > 2 && (size_t)st * PM_TT * D * 2 + fixed > 220 * 1024) --st;
+  return st;
+}
+extern "C" int b200clip_attnpool_splits(int B, int N) {
+  int S = (2 * kSms) / B;
+  const int maxS = (N + 4 * AP_TOK - 1) / (4 * AP_TOK);
+  if (S > maxS) S = maxS;
+  if (S < 1) S = 1;
+  if (S > 64) S = 64;
+  return S;
+}
+extern "C" int b200clip_attnpool_bwd_splits(int B, int N) {
+  int S = kSms / B;
+  const int maxS = (N + 2 * PM_TT - 1) / (2 * PM_TT);
+  if (S > maxS) S = maxS;
+  if (S < 1) S = 1;
+  return S;
+}
+
+template <typename T, int NCH>
+static void fwd_cc(const PoolFwdParams& p) {
+  emul::launch(emul::Dim{(unsigned)p.B, (unsigned)p.S, 1}, 32 * p.H, [&] { pool_fwd_kernel<T, NCH>(p); },
+               2 * (size_t)AP_TOK * p.D * sizeof(T));
+}
+template <typename T>
+static int fwd_t(const PoolFwdParams& p) {
+  const int VE = 16 / (int)sizeof(T);
+  if (p.D % (32 * VE)) return -22;
+  switch (p.D / (32 * VE)) {
+    case 1: fwd_cc<T, 1>(p); break;
+    case 2: fwd_cc<T, 2>(p); break;
+    case 3: fwd_cc<T, 3>(p); break;
+    case 4: fwd_cc<T, 4>(p); break;
+    case 6: fwd_cc<T, 6>(p); break;
+    case 8: fwd_cc<T, 8>(p); break;
+    default: return -22;
+  }
+  return 0;
+}
+extern "C" int b200clip_attnpool_fwd(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                          const float* qt, const float* w, long long wb, long long wh, int B, int N, int D, int H, int S,
+                          float* pm, float* pl, float* pa, float drop_p, long long seed, float* pl2, void*) {
+  if (mma_ok(x, dtype, sb, sn, D, H, N)) {
+    const bool wide = D % 256 == 0 && (size_t)2 * PM_TT * D * 2 + fwd_smem(D, 0) > 112 * 1024;
+    const int stages = stages_for(D, fwd_smem(D, 0), wide);
+    PmFwdParams p{x, sb, sn, mask, mb, qt, w, wb, wh, pm, pl, pa, B, N, D, H, S, drop_p, (unsigned long long)seed, pl2, stages};
+    CUtensorMap tm{x, (uint64_t)B * N, (uint64_t)D, sn};
+    const emul::Dim grid{(unsigned)B, (unsigned)S, 1};
+    const size_t smem = fwd_smem(D, stages);
+    if (dtype == 1) {
+      if (wide) emul::launch(grid, 512, [&] { pool_fwd_mma_kernel<__nv_bfloat16, 16>(tm, p); }, smem);
+      else emul::launch(grid, 256, [&] { pool_fwd_mma_kernel<__nv_bfloat16, 8>(tm, p); }, smem);
+    } else {
+      if (wide) emul::launch(grid, 512, [&] { pool_fwd_mma_kernel<__half, 16>(tm, p); }, smem);
+      else emul::launch(grid, 256, [&] { pool_fwd_mma_kernel<__half, 8>(tm, p); }, smem);
+    }
+    return 0;
+  }
+  PoolFwdParams p{x, sb, sn, mask, mb, qt, w, wb, wh, pm, pl, pa, B, N, D, H, S, drop_p, (unsigned long long)seed, pl2};
+  return dtype == 0 ? fwd_t<float>(p) : dtype == 1 ? fwd_t<__nv_bfloat16>(p) : dtype == 2 ? fwd_t<__half>(p) : -22;
+}
+
+extern "C" int b200clip_attnpool_merge(const float* pm, const float* pl, const float* pa, int B, int S, int H, int D, float* out,
+                            float* out_m, float* out_l, int sum_over_b, const float* pl2, float* out_sa, void*) {
+  emul::launch(B * H, 256, [&] { pool_merge_kernel(pm, pl, pa, B, S, H, D, out, out_m, out_l, sum_over_b, pl2, out_sa); });
+  return 0;
+}
+
+template <typename T, int NCH>
+static void bwd_cc(const PoolBwdParams& p, int gy) {
+  emul::launch(emul::Dim{(unsigned)p.B, (unsigned)gy, 1}, 256, [&] { pool_bwd_dx_kernel<T, NCH>(p); },
+               (2 * (size_t)p.H * p.D + 3 * p.H) * sizeof(float));
+}
+template <typename T>
+static int bwd_t(const PoolBwdParams& p) {
+  const int VE = 16 / (int)sizeof(T);
+  if (p.D % (32 * VE)) return -22;
+  int gy = (2 * kSms + p.B - 1) / p.B;
+  const int maxy = (p.N + 7) / 8;
+  if (gy > maxy) gy = maxy;
+  if (gy < 1) gy = 1;
+  switch (p.D / (32 * VE)) {
+    case 1: bwd_cc<T, 1>(p, gy); break;
+    case 2: bwd_cc<T, 2>(p, gy); break;
+    case 3: bwd_cc<T, 3>(p, gy); break;
+    case 4: bwd_cc<T, 4>(p, gy); break;
+    case 6: bwd_cc<T, 6>(p, gy); break;
+    case 8: bwd_cc<T, 8>(p, gy); break;
+    default: return -22;
+  }
+  return 0;
+}
+static int bwd_any(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                   const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N,
+                   int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p, long long seed,
+                   const float* dlse, float* part_dq, bool need_mma) {
+  if (mma_ok(x, dtype, sb, sn, D, H, N) && (reinterpret_cast<uintptr_t>(dx) % 16) == 0) {
+    const int S = b200clip_attnpool_bwd_splits(B, N);
+    const size_t dq_smem = part_dq ? 2 * 8 * (PM_TT + 8) * 2 : 0;
+    const int stages = stages_for(D, bwd_smem(D, 0) + dq_smem, D % 256 == 0);
+    PmBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, S, sa, dsa, drop_p, (unsigned long long)seed,
+                  stages, dlse, part_dq};
+    CUtensorMap tm{x, (uint64_t)B * N, (uint64_t)D, sn};
+    const emul::Dim grid{(unsigned)B, (unsigned)S, 1};
+    const size_t smem = bwd_smem(D, stages) + dq_smem;
+    const bool wide = D % 256 == 0;
+#define EM_BWD(TT_, NW_, DQ_) emul::launch(grid, NW_ * 32, [&] { pool_bwd_mma_kernel<TT_, NW_, DQ_>(tm, p); }, smem)
+    if (part_dq) {
+      if (dtype == 1) { if (wide) EM_BWD(__nv_bfloat16, 16, true); else EM_BWD(__nv_bfloat16, 8, true); }
+      else { if (wide) EM_BWD(__half, 16, true); else EM_BWD(__half, 8, true); }
+    } else {
+      if (dtype == 1) { if (wide) EM_BWD(__nv_bfloat16, 16, false); else EM_BWD(__nv_bfloat16, 8, false); }
+      else { if (wide) EM_BWD(__half, 16, false); else EM_BWD(__half, 8, false); }
+    }
+#undef EM_BWD
+    return 0;
+  }
+  if (need_mma) return -38;
+  PoolBwdParams p{x, sb, sn, mask, mb, qt, dxbar, xbar, m, l, dx, ds, B, N, D, H, sa, dsa, drop_p, (unsigned long long)seed, dlse};
+  return dtype == 0 ? bwd_t<float>(p) : dtype == 1 ? bwd_t<__nv_bfloat16>(p) : dtype == 2 ? bwd_t<__half>(p) : -22;
+}
+extern "C" int b200clip_attnpool_bwd_dx(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                             const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l, int B,
+                             int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
+                             long long seed, const float* dlse, void*) {
+  return bwd_any(x, dtype, sb, sn, mask, mb, qt, dxbar, xbar, m, l, B, N, D, H, dx, ds, sa, dsa, drop_p, seed, dlse, nullptr,
+                 false);
+}
+extern "C" int b200clip_attnpool_bwd_dx_dq(const void* x, int dtype, long long sb, long long sn, const unsigned char* mask, long long mb,
+                                const float* qt, const float* dxbar, const float* xbar, const float* m, const float* l,
+                                int B, int N, int D, int H, void* dx, float* ds, const float* sa, const float* dsa,
+                                float drop_p, long long seed, const float* dlse, float* part_dq, void*) {
+  return bwd_any(x, dtype, sb, sn, mask, mb, qt, dxbar, xbar, m, l, B, N, D, H, dx, ds, sa, dsa, drop_p, seed, dlse, part_dq,
+                 true);
+}

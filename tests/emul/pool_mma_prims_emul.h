@@ -18,9 +18,23 @@
 #define __grid_constant__
 using std::min;
 
+#define B2_DYN_SMEM16(name) unsigned char* name = emul::tl_block->dyn_smem
 struct uint4 { uint32_t x, y, z, w; };
 struct __nv_bfloat16 { uint16_t x; };
 struct __half { uint16_t x; };
+// CUDA conversion intrinsics and the cp.async pipeline primitives used by the CUDA-core kernels (attnpool_kernels.cuh)
+inline float __bfloat162float(__nv_bfloat16 v) { return __uint_as_float((uint32_t)v.x << 16); }
+inline __nv_bfloat16 __float2bfloat16_rn(float v) {
+  uint32_t u = __float_as_uint(v);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return __nv_bfloat16{(uint16_t)((u >> 16) | 0x40)};
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return __nv_bfloat16{(uint16_t)(u >> 16)};
+}
+inline float __half2float(__half v) { _Float16 h; std::memcpy(&h, &v.x, 2); return (float)h; }
+inline __half __float2half_rn(float v) { _Float16 h = (_Float16)v; __half r; std::memcpy(&r.x, &h, 2); return r; }
+inline void __pipeline_memcpy_async(void* dst, const void* src, size_t n) { std::memcpy(dst, src, n); }
+inline void __pipeline_commit() {}
+inline void __pipeline_wait_prior(int) {}
 struct CUtensorMap {          // what make_tmap_bf16_2d encodes: [rows, cols] 16-bit elements, row pitch in elements
   const void* base;
   uint64_t rows, cols;

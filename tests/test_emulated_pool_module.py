@@ -1,0 +1,126 @@
+"""CPU, end to end: the package's own AttentionPool / AttentionPoolWithCLS modules (Python host code, autograd glue,
+projection folding) running on top of the SHIPPED attention-pool kernels compiled for the host under the emulation
+(tests/emul/pool_emul.cpp exports the b200clip_attnpool_* entry points of include/b200clip.h with the library's own
+dispatch and launch geometry), checked against the golden vectors of the imported reference modules. The only stand-ins
+are the device plumbing (`require_cuda`, the stream handle) and the ctypes target; no math is replaced."""
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN
+from tests.test_host_logic import load_cls_pool
+
+EMUL = Path(__file__).resolve().parent / "emul"
+CSRC = EMUL.parents[1] / "deepcoro_clip_b200" / "csrc"
+
+
+@pytest.fixture()
+def on_emulated_kernels(monkeypatch):
+    so = EMUL / "libpoolemul.so"
+    srcs = [EMUL / "pool_emul.cpp", EMUL / "pool_mma_prims_emul.h", EMUL / "cuda_emul.h", CSRC / "attnpool_mma_kernels.cuh",
+            CSRC / "attnpool_kernels.cuh"]
+    if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", str(so), str(srcs[0])], check=True)
+    emul = ctypes.CDLL(str(so))
+    from deepcoro_clip_b200 import _lib, attention_pool as ap, ops
+    for name, (ret, types) in _lib._prototypes().items():          # the header's prototypes, as for the real library
+        fn = getattr(emul, name, None)
+        if fn is not None:
+            fn.restype, fn.argtypes = ret, types
+    calls = []
+
+    def call(name, *args):
+        calls.append(name)
+        rc = getattr(emul, "b200clip_" + name)(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args])
+        if rc != 0:
+            raise _lib.B200ClipError(f"emulated b200clip_{name} failed with {rc}")
+
+    monkeypatch.setattr(ops, "require_cuda", lambda *t: torch.device("cpu"))
+    monkeypatch.setattr(ap, "call", call)
+    monkeypatch.setattr(ap, "lib", lambda: emul)
+    monkeypatch.setattr(ap, "stream_ptr", lambda dev=None: 0)
+    return calls
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.mark.parametrize("name", ["attnpool_b3_n50_d128_h8", "attnpool_b4_n37_d256_h4_mask_proj"])
+def test_attention_pool_module_on_emulated_kernels(on_emulated_kernels, name):
+    from deepcoro_clip_b200.attention_pool import AttentionPool
+    g = np.load(GOLDEN / f"{name}.npz")
+    B, N, D = g["x"].shape
+    out_dim = g["out"].shape[1]
+    mod = AttentionPool(D, int(g["heads"]), output_dim=None if out_dim == D else out_dim)
+    sd = {"query": g["p_query"], "attn.in_proj_weight": g["p_in_proj_weight"], "attn.in_proj_bias": g["p_in_proj_bias"],
+          "attn.out_proj.weight": g["p_out_proj_weight"], "attn.out_proj.bias": g["p_out_proj_bias"],
+          "norm.weight": g["p_norm_weight"], "norm.bias": g["p_norm_bias"]}
+    if out_dim != D:
+        sd["proj.weight"], sd["proj.bias"] = g["p_proj_weight"], g["p_proj_bias"]
+    mod.load_state_dict({k: torch.tensor(v, dtype=torch.float32) for k, v in sd.items()})
+    x = torch.tensor(g["x"], dtype=torch.float32, requires_grad=True)
+    mask = torch.tensor(g["mask"]) if bool(g["has_mask"]) else None
+    out = mod(x, mask)
+    assert _rel(out.detach().numpy(), g["out"]) < 2e-5
+    (out * torch.tensor(g["go"], dtype=torch.float32)).sum().backward()
+    assert _rel(x.grad.numpy(), g["dx"]) < 5e-5
+    grads = {"query": mod.query.grad, "in_proj_weight": mod.attn.in_proj_weight.grad, "in_proj_bias": mod.attn.in_proj_bias.grad,
+             "out_proj_weight": mod.attn.out_proj.weight.grad, "out_proj_bias": mod.attn.out_proj.bias.grad,
+             "norm_weight": mod.norm.weight.grad, "norm_bias": mod.norm.bias.grad}
+    for k, v in grads.items():
+        ref = g["g_" + k]
+        assert np.abs(v.numpy() - ref).max() <= 5e-5 * max(np.abs(ref).max(), 1e-3), k
+    assert on_emulated_kernels == ["attnpool_fwd", "attnpool_merge", "attnpool_bwd_dx", "attnpool_fwd", "attnpool_merge"]
+
+
+@pytest.mark.parametrize("name", ["clspool_b3_n50_d128_h8", "clspool_b4_n37_d128_h4_mask_proj"])
+def test_cls_pool_module_on_emulated_kernels(on_emulated_kernels, name):
+    from deepcoro_clip_b200.attention_pool import AttentionPoolWithCLS
+    g = np.load(GOLDEN / f"{name}.npz")
+    out_dim = g["p_proj_weight"].shape[0] if "p_proj_weight" in g.files else None
+    mod = AttentionPoolWithCLS(g["x"].shape[2], int(g["heads"]), output_dim=out_dim).eval()
+    params = load_cls_pool(mod, g)
+    x = torch.tensor(g["x"], dtype=torch.float32, requires_grad=True)
+    mask = torch.tensor(g["mask"]) if bool(g["has_mask"]) else None
+    out = mod(x, mask)
+    assert _rel(out.detach().numpy(), g["out"]) < 2e-5
+    (out * torch.tensor(g["go"], dtype=torch.float32)).sum().backward()
+    assert _rel(x.grad.numpy(), g["dx"]) < 5e-5
+    for k, prm in params.items():
+        got = prm.grad.numpy()
+        got = got[::16] if k == "linear1_weight" else got[:, ::16] if k == "linear2_weight" else got
+        ref = g["g_" + k]
+        assert np.abs(got - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-3), k
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_bf16_module_matches_fp32_module_on_emulated_kernels(on_emulated_kernels, fused, monkeypatch):
+    """16-bit inputs take the MMA kernels (and, with B200CLIP_POOL_FUSED_DQ=1, the fused query-gradient variant): same
+    module, same parameters, bf16 x against the fp32 CUDA-core path on the rounded x."""
+    from deepcoro_clip_b200.attention_pool import AttentionPool
+    monkeypatch.setenv("B200CLIP_POOL_FUSED_DQ", fused)
+    torch.manual_seed(3)
+    mod = AttentionPool(256, 8).eval()
+    x16 = torch.randn(2, 90, 256).bfloat16()
+    mask = torch.rand(2, 90) < 0.15
+    mask[:, 0] = False
+    go = torch.randn(2, 256)
+    res = []
+    for x in (x16.clone().requires_grad_(True), x16.float().requires_grad_(True)):
+        for p in mod.parameters():
+            p.grad = None
+        out = mod(x, mask)
+        (out.float() * go).sum().backward()
+        res.append((out.detach().float(), x.grad.float(), mod.query.grad.clone(), mod.attn.in_proj_weight.grad.clone()))
+    (o16, dx16, dq16, dw16), (o32, dx32, dq32, dw32) = res
+    assert _rel(o16, o32) < 1e-2 and _rel(dx16, dx32) < 1e-2              # bf16 output / dx rounding
+    assert _rel(dq16, dq32) < 2e-3 and _rel(dw16, dw32) < 2e-3
+    n16 = [c for c in on_emulated_kernels[:len(on_emulated_kernels) // 2]]
+    assert ("attnpool_bwd_dx_dq" in n16) == (fused == "1")
+    assert n16.count("attnpool_fwd") == (1 if fused == "1" else 2)         # the second pass over x is gone
