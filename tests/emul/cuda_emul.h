@@ -83,6 +83,8 @@ inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); r
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }
 struct float2 { float x, y; };
@@ -97,6 +99,7 @@ template <class F>
 inline void launch(Dim grid, unsigned block, F f, size_t smem_bytes = 0) {
   gridDim = grid;
   blockDim = Dim{block, 1, 1};
+  for (unsigned bz = 0; bz < grid.z; ++bz)
   for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned b = 0; b < grid.x; ++b) {
       Block bs(block, smem_bytes);
@@ -104,9 +107,9 @@ inline void launch(Dim grid, unsigned block, F f, size_t smem_bytes = 0) {
       std::vector<std::thread> th;
       th.reserve(block);
       for (unsigned t = 0; t < block; ++t)
-        th.emplace_back([&, t, b, by] {
+        th.emplace_back([&, t, b, by, bz] {
           threadIdx = Dim{t, 0, 0};
-          blockIdx = Dim{b, by, 0};
+          blockIdx = Dim{b, by, bz};
           tl_block = &bs;
           tl_warp = &bs.warps[t / 32];
           tl_lane = (int)(t % 32);

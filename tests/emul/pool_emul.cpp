@@ -3,6 +3,7 @@
 #include "pool_mma_prims_emul.h"
 #include "../../deepcoro_clip_b200/csrc/attnpool_mma_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/attnpool_kernels.cuh"
+#include "../../deepcoro_clip_b200/csrc/rope3d_kernels.cuh"
 
 using namespace b2;
 
@@ -65,7 +66,7 @@ void emul_pool_bwd(const void* x, int dtype, const unsigned char* mask, const fl
 
 // ---- the attention-pool entry points of include/b200clip.h with the library's own dispatch and launch geometry
 //      (attnpool.cu / attnpool_mma.cu on a 148-SM device), so the package's Python host code can run on top of the
-//      emulated kernels unchanged (tests/test_emulated_pool_module.py). `stream` is ignored. ----
+//      emulated kernels unchanged (tests/test_emulated_token_modules.py). `stream` is ignored. ----
 static const int kSms = 148;
 static bool mma_ok(const void* x, int dtype, long long sb, long long sn, int D, int H, int N) {
   return (dtype == 1 || dtype == 2) && H <= 8 && D % 128 == 0 && D <= 1024 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
@@ -208,4 +209,52 @@ extern "C" int b200clip_attnpool_bwd_dx_dq(const void* x, int dtype, long long s
                                 float drop_p, long long seed, const float* dlse, float* part_dq, void*) {
   return bwd_any(x, dtype, sb, sn, mask, mb, qt, dxbar, xbar, m, l, B, N, D, H, dx, ds, sa, dsa, drop_p, seed, dlse, part_dq,
                  true);
+}
+
+// ---- b200clip_rope3d_apply with rope3d.cu's dispatch (plane fast path / generic kernel) ----
+template <typename T>
+static int rope_launch_emul(const RopeTensor& q, const RopeTensor& k, int ntens, const void* sin_t, const void* cos_t, int B,
+                            int Hh, int N, int Dh, float sgn) {
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = Dh % VEC == 0;
+  auto aligned = [&](const RopeTensor& t) {
+    return (reinterpret_cast<uintptr_t>(t.in) % 16 == 0) && (t.sb * sizeof(T)) % 16 == 0 && (t.sh * sizeof(T)) % 16 == 0 &&
+           (t.sn * sizeof(T)) % 16 == 0;
+  };
+  const long long plane = (long long)N * (Dh / VEC);
+  if (vec_ok && aligned(q) && (ntens == 1 || aligned(k))) {
+    const int rows = B * Hh;
+    const int pblocks = (int)((plane + 255) / 256);
+    int groups = (8 * kSms + pblocks * ntens - 1) / (pblocks * ntens);
+    if (groups < 1) groups = 1;
+    int rpb = (rows + groups - 1) / groups;
+    rpb = (rpb + ROPE_UNROLL - 1) / ROPE_UNROLL * ROPE_UNROLL;
+    groups = (rows + rpb - 1) / rpb;
+    emul::launch(emul::Dim{(unsigned)pblocks, (unsigned)groups, (unsigned)ntens}, 256, [&] {
+      rope3d_plane_kernel<T>(q, k, (const T*)sin_t, (const T*)cos_t, rows, Hh, N, Dh, rpb, sgn);
+    });
+    return 0;
+  }
+  const long long total = (long long)B * Hh * N * (vec_ok ? Dh / VEC : Dh / 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 64) blocks = 64;                 // grid-stride kernel: fewer CTAs than the device would get, same result
+  const emul::Dim grid{(unsigned)blocks, (unsigned)ntens, 1};
+  if (vec_ok) emul::launch(grid, 256, [&] { rope3d_kernel<T, VEC>(q, k, (const T*)sin_t, (const T*)cos_t, B, Hh, N, Dh, sgn); });
+  else emul::launch(grid, 256, [&] { rope3d_kernel<T, 2>(q, k, (const T*)sin_t, (const T*)cos_t, B, Hh, N, Dh, sgn); });
+  return 0;
+}
+extern "C" int b200clip_rope3d_apply(const void* q, long long qsb, long long qsh, long long qsn, void* q_out, const void* k,
+                                     long long ksb, long long ksh, long long ksn, void* k_out, const void* sin_t,
+                                     const void* cos_t, int dtype, int B, int Hh, int N, int Dh, int backward, void*) {
+  if (!q || !q_out || !sin_t || !cos_t || B <= 0 || Hh <= 0 || N <= 0 || Dh <= 0 || (Dh & 1)) return -22;
+  RopeTensor tq{q, q_out, qsb, qsh, qsn};
+  RopeTensor tk{k, k_out, ksb, ksh, ksn};
+  const int ntens = (k && k_out) ? 2 : 1;
+  const float sgn = backward ? -1.f : 1.f;
+  switch (dtype) {
+    case 0: return rope_launch_emul<float>(tq, tk, ntens, sin_t, cos_t, B, Hh, N, Dh, sgn);
+    case 1: return rope_launch_emul<__nv_bfloat16>(tq, tk, ntens, sin_t, cos_t, B, Hh, N, Dh, sgn);
+    case 2: return rope_launch_emul<__half>(tq, tk, ntens, sin_t, cos_t, B, Hh, N, Dh, sgn);
+    default: return -22;
+  }
 }

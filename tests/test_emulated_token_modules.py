@@ -22,7 +22,7 @@ CSRC = EMUL.parents[1] / "deepcoro_clip_b200" / "csrc"
 def on_emulated_kernels(monkeypatch):
     so = EMUL / "libpoolemul.so"
     srcs = [EMUL / "pool_emul.cpp", EMUL / "pool_mma_prims_emul.h", EMUL / "cuda_emul.h", CSRC / "attnpool_mma_kernels.cuh",
-            CSRC / "attnpool_kernels.cuh"]
+            CSRC / "attnpool_kernels.cuh", CSRC / "rope3d_kernels.cuh"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", str(so), str(srcs[0])], check=True)
     emul = ctypes.CDLL(str(so))
@@ -39,10 +39,12 @@ def on_emulated_kernels(monkeypatch):
         if rc != 0:
             raise _lib.B200ClipError(f"emulated b200clip_{name} failed with {rc}")
 
+    from deepcoro_clip_b200 import rope_3d
     monkeypatch.setattr(ops, "require_cuda", lambda *t: torch.device("cpu"))
-    monkeypatch.setattr(ap, "call", call)
+    for mod in (ap, rope_3d):
+        monkeypatch.setattr(mod, "call", call)
+        monkeypatch.setattr(mod, "stream_ptr", lambda dev=None: 0)
     monkeypatch.setattr(ap, "lib", lambda: emul)
-    monkeypatch.setattr(ap, "stream_ptr", lambda dev=None: 0)
     return calls
 
 
@@ -124,3 +126,30 @@ def test_bf16_module_matches_fp32_module_on_emulated_kernels(on_emulated_kernels
     n16 = [c for c in on_emulated_kernels[:len(on_emulated_kernels) // 2]]
     assert ("attnpool_bwd_dx_dq" in n16) == (fused == "1")
     assert n16.count("attnpool_fwd") == (1 if fused == "1" else 2)         # the second pass over x is gone
+
+
+@pytest.mark.parametrize("name,dtype", [("rope_f32_t3h2w2", torch.float32), ("rope_f32_t2h3w4_cls", torch.float32),
+                                        ("rope_bf16_t4h7w7_cls", torch.bfloat16)])
+def test_rope_on_emulated_kernels_bit_exact(on_emulated_kernels, name, dtype):
+    """apply_rope_qk (forward + autograd backward) and the Rope3D module through the shipped rope3d kernels on CPU:
+    BIT-EXACT against the reference module's outputs and gradients, contiguous and permuted (MViT-style) inputs."""
+    from deepcoro_clip_b200.rope_3d import Rope3D, apply_rope_qk
+    g = np.load(GOLDEN / f"{name}.npz")
+    t = lambda a: torch.tensor(a, dtype=torch.float32).to(dtype)
+    q, k = t(g["q"]).requires_grad_(True), t(g["k"]).requires_grad_(True)
+    qr, kr = apply_rope_qk(q, k, t(g["sin"]), t(g["cos"]))
+    assert (qr.detach().float().numpy() == g["q_rot"].astype(np.float32)).all()
+    assert (kr.detach().float().numpy() == g["k_rot"].astype(np.float32)).all()
+    ((qr * t(g["gq"])).sum() + (kr * t(g["gk"])).sum()).backward()
+    assert (q.grad.float().numpy() == g["dq"].astype(np.float32)).all()
+    assert (k.grad.float().numpy() == g["dk"].astype(np.float32)).all()
+    B, heads, T, H, W, cls = [int(x) for x in g["meta"]]
+    mod = Rope3D(q.shape[-1] * heads, heads).eval()
+    qd = q.detach()
+    qp = qd.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)           # non-contiguous view: generic-stride path
+    assert not qp.is_contiguous()
+    q1, k1 = mod(qd, k.detach(), T, H, W)
+    q2, _ = mod(qp, k.detach(), T, H, W)
+    assert torch.equal(q1, q2)
+    assert (q1.float().numpy() == g["q_rot"].astype(np.float32)).all()     # CPU-built tables == the reference's
+    assert on_emulated_kernels.count("rope3d_apply") == 4
