@@ -86,6 +86,7 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __expf(float x) { return expf(x); }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float __logf(float x) { return logf(x); }
 struct float2 { float x, y; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }

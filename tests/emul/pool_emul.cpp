@@ -4,6 +4,7 @@
 #include "../../deepcoro_clip_b200/csrc/attnpool_mma_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/attnpool_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/rope3d_kernels.cuh"
+#include "../../deepcoro_clip_b200/csrc/querypool_kernels.cuh"
 
 using namespace b2;
 
@@ -257,4 +258,22 @@ extern "C" int b200clip_rope3d_apply(const void* q, long long qsb, long long qsh
     case 2: return rope_launch_emul<__half>(tq, tk, ntens, sin_t, cos_t, B, Hh, N, Dh, sgn);
     default: return -22;
   }
+}
+
+// ---- b200clip_querypool (querypool.cu: one CTA per study, forward or backward) ----
+extern "C" int b200clip_querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,
+                                  const float* lnb, const float* q, const unsigned char* mask, long long mb, int B, int N,
+                                  int D, float eps, float* out, const float* dout, float* dx, float* dpos, float* dlnw,
+                                  float* dlnb, float* dq, void*) {
+  if (!x || !lnw || !lnb || !q || B <= 0 || N <= 0 || D <= 0) return -22;
+  const size_t smem = ((size_t)N * D + 5 * (size_t)N) * sizeof(float);
+  QpParams p{x, sb, sn, pos, lnw, lnb, q, mask, mb, B, N, D, eps, out, dout, dx, dpos, dlnw, dlnb, dq};
+  if (backward) {
+    if (!dout || !dx || !dlnw || !dlnb || !dq) return -22;
+    emul::launch(emul::Dim{(unsigned)B, 1, 1}, 256, [&] { querypool_kernel<true>(p); }, smem);
+  } else {
+    if (!out) return -22;
+    emul::launch(emul::Dim{(unsigned)B, 1, 1}, 256, [&] { querypool_kernel<false>(p); }, smem);
+  }
+  return 0;
 }

@@ -19,6 +19,7 @@
 using std::min;
 
 #define B2_DYN_SMEM16(name) unsigned char* name = emul::tl_block->dyn_smem
+#define B2_DYN_SMEM_F32(name) float* name = reinterpret_cast<float*>(emul::tl_block->dyn_smem)
 struct uint4 { uint32_t x, y, z, w; };
 struct __nv_bfloat16 { uint16_t x; };
 struct __half { uint16_t x; };

@@ -22,7 +22,7 @@ CSRC = EMUL.parents[1] / "deepcoro_clip_b200" / "csrc"
 def on_emulated_kernels(monkeypatch):
     so = EMUL / "libpoolemul.so"
     srcs = [EMUL / "pool_emul.cpp", EMUL / "pool_mma_prims_emul.h", EMUL / "cuda_emul.h", CSRC / "attnpool_mma_kernels.cuh",
-            CSRC / "attnpool_kernels.cuh", CSRC / "rope3d_kernels.cuh"]
+            CSRC / "attnpool_kernels.cuh", CSRC / "rope3d_kernels.cuh", CSRC / "querypool_kernels.cuh"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", str(so), str(srcs[0])], check=True)
     emul = ctypes.CDLL(str(so))
@@ -39,9 +39,9 @@ def on_emulated_kernels(monkeypatch):
         if rc != 0:
             raise _lib.B200ClipError(f"emulated b200clip_{name} failed with {rc}")
 
-    from deepcoro_clip_b200 import rope_3d
+    from deepcoro_clip_b200 import rope_3d, video_aggregator
     monkeypatch.setattr(ops, "require_cuda", lambda *t: torch.device("cpu"))
-    for mod in (ap, rope_3d):
+    for mod in (ap, rope_3d, video_aggregator):
         monkeypatch.setattr(mod, "call", call)
         monkeypatch.setattr(mod, "stream_ptr", lambda dev=None: 0)
     monkeypatch.setattr(ap, "lib", lambda: emul)
@@ -153,3 +153,28 @@ def test_rope_on_emulated_kernels_bit_exact(on_emulated_kernels, name, dtype):
     assert torch.equal(q1, q2)
     assert (q1.float().numpy() == g["q_rot"].astype(np.float32)).all()     # CPU-built tables == the reference's
     assert on_emulated_kernels.count("rope3d_apply") == 4
+
+
+@pytest.mark.parametrize("name", ["qpool_b5_n4_d64", "qpool_b6_n5_d128_mask"])
+def test_query_pool_module_on_emulated_kernels(on_emulated_kernels, name):
+    """EnhancedVideoAggregator's fused tail (position add, LayerNorm, masked query softmax, weighted sum) forward and
+    backward through the shipped querypool kernel on CPU, against the reference module's goldens."""
+    from deepcoro_clip_b200.video_aggregator import EnhancedVideoAggregator
+    g = np.load(GOLDEN / f"{name}.npz")
+    B, N, D = g["x"].shape
+    mod = EnhancedVideoAggregator(D, num_heads=4, dropout=0.0, aggregator_depth=0, max_segments=16)
+    mod.load_state_dict({"pos_encoding": torch.tensor(g["pos"], dtype=torch.float32),
+                         "final_ln.weight": torch.tensor(g["ln_w"], dtype=torch.float32),
+                         "final_ln.bias": torch.tensor(g["ln_b"], dtype=torch.float32),
+                         "attn_query": torch.tensor(g["attn_query"], dtype=torch.float32)})
+    x = torch.tensor(g["x"], dtype=torch.float32, requires_grad=True)
+    mask = torch.tensor(g["mask"]) if bool(g["has_mask"]) else None
+    out = mod(x, mask)
+    assert _rel(out.detach().numpy(), g["out"]) < 1e-5
+    (out * torch.tensor(g["go"], dtype=torch.float32)).sum().backward()
+    assert _rel(x.grad.numpy(), g["dx"]) < 2e-5
+    assert _rel(mod.pos_encoding.grad.numpy(), g["g_pos"]) < 2e-5
+    assert _rel(mod.final_ln.weight.grad.numpy(), g["g_ln_w"]) < 2e-5
+    assert _rel(mod.final_ln.bias.grad.numpy(), g["g_ln_b"]) < 2e-5
+    assert _rel(mod.attn_query.grad.numpy(), g["g_attn_query"]) < 2e-5
+    assert on_emulated_kernels == ["querypool", "querypool"]
