@@ -5,6 +5,7 @@
 #include "../../deepcoro_clip_b200/csrc/attnpool_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/rope3d_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/querypool_kernels.cuh"
+#include "../../deepcoro_clip_b200/csrc/multipos_kernels.cuh"
 
 using namespace b2;
 
@@ -275,5 +276,42 @@ extern "C" int b200clip_querypool(int backward, const float* x, long long sb, lo
     if (!out) return -22;
     emul::launch(emul::Dim{(unsigned)B, 1, 1}, 256, [&] { querypool_kernel<false>(p); }, smem);
   }
+  return 0;
+}
+
+// ---- b200clip_multipos_* (multipos.cu launch geometry on a 148-SM device) ----
+static int mp_chunks(int N, int M) {
+  const int col_blocks = (M + 127) / 128;
+  int ch = (4 * kSms + col_blocks - 1) / col_blocks;
+  if (ch > N / 32) ch = N / 32;
+  if (ch < 1) ch = 1;
+  if (ch > 256) ch = 256;
+  return ch;
+}
+extern "C" int b200clip_multipos_workspace_bytes(int N, int M) { return mp_chunks(N, M) * M * (int)sizeof(MpAcc); }
+extern "C" int b200clip_multipos_fwd(const float* L, long long ldl, const float* pw, const float* mk, long long ldw, int N, int M,
+                                     int mode, float eps, int reduce_sum, float* rstat, float* cstat, float* coef,
+                                     float* loss_out, void* workspace, void*) {
+  if (N <= 0 || M <= 0 || (mode != 0 && mode != 1) || (!pw && !mk)) return -22;
+  const int ch = mp_chunks(N, M);
+  emul::launch(N, 256, [&] { mp_row_stats_kernel(L, ldl, pw, mk, ldw, N, M, reinterpret_cast<float4*>(rstat)); });
+  emul::launch(emul::Dim{(unsigned)((M + 127) / 128), (unsigned)ch, 1}, 128,
+               [&] { mp_col_partial_kernel(L, ldl, pw, mk, ldw, N, M, ch, reinterpret_cast<MpAcc*>(workspace)); });
+  emul::launch((M + 127) / 128, 128,
+               [&] { mp_col_merge_kernel(reinterpret_cast<const MpAcc*>(workspace), M, ch, reinterpret_cast<float4*>(cstat)); });
+  emul::launch(1, 1024, [&] {
+    mp_finalize_kernel(reinterpret_cast<const float4*>(rstat), reinterpret_cast<const float4*>(cstat), N, M, mode, eps,
+                       reduce_sum, coef, loss_out);
+  });
+  return 0;
+}
+extern "C" int b200clip_multipos_bwd(const float* L, long long ldl, const float* pw, const float* mk, long long ldw, int N, int M,
+                                     const float* rstat, const float* cstat, const float* coef, const float* gmul, float* dL,
+                                     long long ldd, void*) {
+  if (N <= 0 || M <= 0) return -22;
+  emul::launch(N, 256, [&] {
+    mp_backward_kernel(L, ldl, pw, mk, ldw, N, M, reinterpret_cast<const float4*>(rstat), reinterpret_cast<const float4*>(cstat),
+                       coef, gmul, dL, ldd);
+  });
   return 0;
 }

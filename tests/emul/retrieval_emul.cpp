@@ -5,7 +5,6 @@
 #include "cuda_emul.h"
 #include "../../deepcoro_clip_b200/csrc/retrieval_epi.cuh"
 #include "../../deepcoro_clip_b200/csrc/alignment_diag.cuh"
-#include "../../deepcoro_clip_b200/csrc/multipos_kernels.cuh"
 
 using namespace b2;
 
@@ -83,25 +82,6 @@ void emul_rank_counts(const float* S, int N, int M, int segs, const float* sgt, 
 
 void emul_alignment_diag(const float* sums, int n, const float* dyn, int gated, float* out) {
   emul::launch(1, 1024, [&] { alignment_diag_kernel(sums, n, dyn, gated, out); });
-}
-
-// multipos_fwd / multipos_bwd of multipos.cu with the same launch geometry (chunks as multipos_chunks on 148 SMs).
-void emul_multipos(const float* L, const float* pw, const float* mk, int N, int M, int mode, float eps, int reduce_sum,
-                   float gmul, float* loss_out, float* dL) {
-  const int col_blocks = (M + 127) / 128;
-  int ch = (4 * 148 + col_blocks - 1) / col_blocks;
-  if (ch > N / 32) ch = N / 32;
-  if (ch < 1) ch = 1;
-  if (ch > 256) ch = 256;
-  std::vector<float4> rstat(N), cstat(M);
-  std::vector<MpAcc> ws((size_t)ch * M);
-  std::vector<float> coef(N + M);
-  emul::launch(N, 256, [&] { mp_row_stats_kernel(L, M, pw, mk, M, N, M, rstat.data()); });
-  emul::launch(emul::Dim{(unsigned)col_blocks, (unsigned)ch, 1}, 128,
-               [&] { mp_col_partial_kernel(L, M, pw, mk, M, N, M, ch, ws.data()); });
-  emul::launch(col_blocks, 128, [&] { mp_col_merge_kernel(ws.data(), M, ch, cstat.data()); });
-  emul::launch(1, 1024, [&] { mp_finalize_kernel(rstat.data(), cstat.data(), N, M, mode, eps, reduce_sum, coef.data(), loss_out); });
-  emul::launch(N, 256, [&] { mp_backward_kernel(L, M, pw, mk, M, N, M, rstat.data(), cstat.data(), coef.data(), &gmul, dL, M); });
 }
 
 }  // extern "C"

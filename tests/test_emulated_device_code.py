@@ -127,24 +127,3 @@ def test_alignment_scalar_kernel_device_code(emul, name):
     for got, key in zip(out[:3], ("cosine_f64", "logprob_f64", "prob_f64")):
         ref = float(g[key])
         assert abs(float(got) - ref) <= 5e-6 * max(1.0, abs(ref)), (key, float(got), ref)
-
-
-@pytest.mark.parametrize("name", ["multipos_48x64", "multipos_130x37"])
-def test_multipos_kernels_device_code(emul, name):
-    """csrc/multipos_kernels.cuh (GPU-validated in round 1) under the emulation, against the reference classes' goldens."""
-    g = np.load(GOLDEN / f"{name}.npz")
-    L = np.ascontiguousarray(g["logits"], np.float32)
-    mk = np.ascontiguousarray(g["mask"], np.float32)
-    pw = np.ascontiguousarray(g["pos_weights"], np.float32)
-    N, M = L.shape
-    wsl_w = np.ascontiguousarray(mk * pw - 0.2 * (1 - mk), np.float32)
-    cases = {"wsl": (wsl_w, None, 0, 1e-6, 0), "mpi_mean": (pw, mk, 1, 0.0, 0), "mpi_sum_noweights": (None, mk, 1, 0.0, 1)}
-    for key, (w, m, mode, eps, rsum) in cases.items():
-        loss = np.zeros(1, np.float32)
-        dL = np.zeros((N, M), np.float32)
-        emul.emul_multipos(_p(L, C_F), _p(w, C_F) if w is not None else None, _p(m, C_F) if m is not None else None, N, M,
-                           mode, ctypes.c_float(eps), rsum, ctypes.c_float(1.0), _p(loss, C_F), _p(dL, C_F))
-        ref = float(g[key + "_loss"])
-        assert abs(float(loss[0]) - ref) <= 1e-5 * abs(ref), key
-        d = g[key + "_dlogits"]
-        assert np.abs(dL - d).max() <= 1e-4 * np.abs(d).max() + 1e-9, key

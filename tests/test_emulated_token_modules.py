@@ -22,7 +22,8 @@ CSRC = EMUL.parents[1] / "deepcoro_clip_b200" / "csrc"
 def on_emulated_kernels(monkeypatch):
     so = EMUL / "libpoolemul.so"
     srcs = [EMUL / "pool_emul.cpp", EMUL / "pool_mma_prims_emul.h", EMUL / "cuda_emul.h", CSRC / "attnpool_mma_kernels.cuh",
-            CSRC / "attnpool_kernels.cuh", CSRC / "rope3d_kernels.cuh", CSRC / "querypool_kernels.cuh"]
+            CSRC / "attnpool_kernels.cuh", CSRC / "rope3d_kernels.cuh", CSRC / "querypool_kernels.cuh",
+            CSRC / "multipos_kernels.cuh"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", str(so), str(srcs[0])], check=True)
     emul = ctypes.CDLL(str(so))
@@ -39,12 +40,13 @@ def on_emulated_kernels(monkeypatch):
         if rc != 0:
             raise _lib.B200ClipError(f"emulated b200clip_{name} failed with {rc}")
 
-    from deepcoro_clip_b200 import rope_3d, video_aggregator
+    from deepcoro_clip_b200 import multipos_loss, rope_3d, video_aggregator
     monkeypatch.setattr(ops, "require_cuda", lambda *t: torch.device("cpu"))
-    for mod in (ap, rope_3d, video_aggregator):
+    for mod in (ap, rope_3d, video_aggregator, multipos_loss):
         monkeypatch.setattr(mod, "call", call)
         monkeypatch.setattr(mod, "stream_ptr", lambda dev=None: 0)
     monkeypatch.setattr(ap, "lib", lambda: emul)
+    monkeypatch.setattr(multipos_loss, "lib", lambda: emul)
     return calls
 
 
@@ -178,3 +180,24 @@ def test_query_pool_module_on_emulated_kernels(on_emulated_kernels, name):
     assert _rel(mod.final_ln.bias.grad.numpy(), g["g_ln_b"]) < 2e-5
     assert _rel(mod.attn_query.grad.numpy(), g["g_attn_query"]) < 2e-5
     assert on_emulated_kernels == ["querypool", "querypool"]
+
+
+@pytest.mark.parametrize("name", ["multipos_48x64", "multipos_130x37"])
+def test_multipos_loss_modules_on_emulated_kernels(on_emulated_kernels, name):
+    """WeightedSigLIPLoss / MultiPositiveInfoNCELoss (the package's nn.Modules and autograd function) through the shipped
+    multipos kernels on CPU, against the reference classes' fp32 autograd goldens."""
+    from deepcoro_clip_b200.multipos_loss import MultiPositiveInfoNCELoss, WeightedSigLIPLoss
+    g = np.load(GOLDEN / f"{name}.npz")
+    logits, mask, pw = (torch.tensor(g[k], dtype=torch.float32) for k in ("logits", "mask", "pos_weights"))
+    cases = {"wsl": lambda L: WeightedSigLIPLoss()(L, mask * pw - 0.2 * (1 - mask)),
+             "mpi_mean": lambda L: MultiPositiveInfoNCELoss()(L, mask, pw),
+             "mpi_sum_noweights": lambda L: MultiPositiveInfoNCELoss(reduction="sum")(L, mask)}
+    for key, fn in cases.items():
+        L = logits.clone().requires_grad_(True)
+        loss = fn(L)
+        assert loss.ndim == 0 and loss.requires_grad
+        loss.backward()
+        ref = float(g[key + "_loss"])
+        assert abs(loss.item() - ref) <= 1e-5 * abs(ref), key
+        d = g[key + "_dlogits"]
+        assert np.abs(L.grad.numpy() - d).max() <= 1e-4 * np.abs(d).max() + 1e-9, key
