@@ -71,6 +71,8 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
 inline void __syncwarp(unsigned = 0xffffffffu) { emul::tl_warp->bar.arrive_and_wait(); }
 inline void __syncthreads() { emul::tl_block->bar.arrive_and_wait(); }
 inline void __threadfence() {}
+template <class T>
+inline T __ldg(const T* p) { return *p; }
 
 template <class T>
 inline T atomicAdd(T* p, T v) {

@@ -6,6 +6,7 @@
 #include "../../deepcoro_clip_b200/csrc/rope3d_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/querypool_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/multipos_kernels.cuh"
+#include "../../deepcoro_clip_b200/csrc/dense_metrics_kernels.cuh"
 
 using namespace b2;
 
@@ -68,7 +69,7 @@ void emul_pool_bwd(const void* x, int dtype, const unsigned char* mask, const fl
 
 // ---- the attention-pool entry points of include/b200clip.h with the library's own dispatch and launch geometry
 //      (attnpool.cu / attnpool_mma.cu on a 148-SM device), so the package's Python host code can run on top of the
-//      emulated kernels unchanged (tests/test_emulated_token_modules.py). `stream` is ignored. ----
+//      emulated kernels unchanged (tests/test_emulated_modules.py). `stream` is ignored. ----
 static const int kSms = 148;
 static bool mma_ok(const void* x, int dtype, long long sb, long long sn, int D, int H, int N) {
   return (dtype == 1 || dtype == 2) && H <= 8 && D % 128 == 0 && D <= 1024 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
@@ -312,6 +313,34 @@ extern "C" int b200clip_multipos_bwd(const float* L, long long ldl, const float*
   emul::launch(N, 256, [&] {
     mp_backward_kernel(L, ldl, pw, mk, ldw, N, M, reinterpret_cast<const float4*>(rstat), reinterpret_cast<const float4*>(cstat),
                        coef, gmul, dL, ldd);
+  });
+  return 0;
+}
+
+// ---- b200clip_dense_gt_ranks / b200clip_dense_rank_metrics (dense_metrics.cu) ----
+template <typename T>
+static void ranks_emul(const void* sim, long long ld, int N, int M, const int* gt, int G, int sanitize, int* ranks) {
+  const T* p = reinterpret_cast<const T*>(sim);
+  if (G <= 1) emul::launch(N, 256, [&] { dense_gt_ranks_kernel<T, 1>(p, ld, N, M, gt, G, sanitize, ranks); });
+  else if (G <= 4) emul::launch(N, 256, [&] { dense_gt_ranks_kernel<T, 4>(p, ld, N, M, gt, G, sanitize, ranks); });
+  else if (G <= 8) emul::launch(N, 256, [&] { dense_gt_ranks_kernel<T, 8>(p, ld, N, M, gt, G, sanitize, ranks); });
+  else emul::launch(N, 256, [&] { dense_gt_ranks_kernel<T, 16>(p, ld, N, M, gt, G, sanitize, ranks); });
+}
+extern "C" int b200clip_dense_gt_ranks(const void* sim, int dtype, long long ld, int N, int M, const int* gt, int G,
+                                       int sanitize, int* ranks, void*) {
+  if (N <= 0 || M <= 0 || G <= 0 || G > 16) return -22;
+  if (dtype == 0) ranks_emul<float>(sim, ld, N, M, gt, G, sanitize, ranks);
+  else if (dtype == 1) ranks_emul<__nv_bfloat16>(sim, ld, N, M, gt, G, sanitize, ranks);
+  else if (dtype == 2) ranks_emul<__half>(sim, ld, N, M, gt, G, sanitize, ranks);
+  else return -22;
+  return 0;
+}
+extern "C" int b200clip_dense_rank_metrics(const int* ranks, const int* gsize, int N, int G, int M, const int* recall_k, int nrk,
+                                           const int* ndcg_k, int nnk, int* best, double* rr, double* ap, unsigned char* hit,
+                                           double* ndcg, void*) {
+  if (N <= 0 || G <= 0 || G > 16 || M <= 0) return -22;
+  emul::launch((N + 255) / 256, 256, [&] {
+    dense_rank_metrics_kernel(ranks, gsize, N, G, M, recall_k, nrk, ndcg_k, nnk, best, rr, ap, hit, ndcg);
   });
   return 0;
 }

@@ -23,7 +23,7 @@ def on_emulated_kernels(monkeypatch):
     so = EMUL / "libpoolemul.so"
     srcs = [EMUL / "pool_emul.cpp", EMUL / "pool_mma_prims_emul.h", EMUL / "cuda_emul.h", CSRC / "attnpool_mma_kernels.cuh",
             CSRC / "attnpool_kernels.cuh", CSRC / "rope3d_kernels.cuh", CSRC / "querypool_kernels.cuh",
-            CSRC / "multipos_kernels.cuh"]
+            CSRC / "multipos_kernels.cuh", CSRC / "dense_metrics_kernels.cuh"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", str(so), str(srcs[0])], check=True)
     emul = ctypes.CDLL(str(so))
@@ -40,9 +40,9 @@ def on_emulated_kernels(monkeypatch):
         if rc != 0:
             raise _lib.B200ClipError(f"emulated b200clip_{name} failed with {rc}")
 
-    from deepcoro_clip_b200 import multipos_loss, rope_3d, video_aggregator
+    from deepcoro_clip_b200 import multipos_loss, retrieval_metrics, rope_3d, video_aggregator
     monkeypatch.setattr(ops, "require_cuda", lambda *t: torch.device("cpu"))
-    for mod in (ap, rope_3d, video_aggregator, multipos_loss):
+    for mod in (ap, rope_3d, video_aggregator, multipos_loss, retrieval_metrics):
         monkeypatch.setattr(mod, "call", call)
         monkeypatch.setattr(mod, "stream_ptr", lambda dev=None: 0)
     monkeypatch.setattr(ap, "lib", lambda: emul)
@@ -201,3 +201,34 @@ def test_multipos_loss_modules_on_emulated_kernels(on_emulated_kernels, name):
         assert abs(loss.item() - ref) <= 1e-5 * abs(ref), key
         d = g[key + "_dlogits"]
         assert np.abs(L.grad.numpy() - d).max() <= 1e-4 * np.abs(d).max() + 1e-9, key
+
+
+@pytest.mark.parametrize("name", ["dense_metrics_64x7_g3", "dense_metrics_120x90_g1"])
+def test_dense_metrics_on_emulated_kernels(on_emulated_kernels, name):
+    """utils/retrieval_metrics.py drop-ins (recall with ground-truth sets, MRR, MAP, NDCG, median rank) through the shipped
+    rank-pass / per-row kernels on CPU, against the reference functions' goldens and the oracle on a tie-heavy matrix."""
+    from deepcoro_clip_b200 import retrieval_metrics as rm
+    from oracle import dense_metrics_oracle as dmo
+    g = np.load(GOLDEN / f"{name}.npz")
+    sim = torch.tensor(g["sim"])
+    gt = [[int(c) for c in row if c >= 0] for row in g["gt"]]
+    ks = [int(k) for k in g["k_values"]]
+    allm = rm.compute_all_dense_metrics(sim, gt, recall_k=ks, ndcg_k=ks)          # every metric from ONE rank pass
+    for i, k in enumerate(ks):
+        assert allm[f"Recall@{k}"] == float(g["recall"][i])
+        assert abs(allm[f"NDCG@{k}_V2T"] - float(g["ndcg"][i])) <= 1e-6
+    assert abs(allm["MRR_V2T"] - float(g["mrr"])) <= 1e-15
+    assert abs(allm["MAP"] - float(g["map"])) <= 1e-6
+    assert allm["MedianRank_V2T"] == int(g["median_rank"])
+    assert rm.compute_recall_at_k(sim, gt, ks) == {f"Recall@{k}": allm[f"Recall@{k}"] for k in ks}   # the reference API
+    if name == "dense_metrics_64x7_g3":
+        # ties (lowest index first), empty rows, out-of-range indices; bf16 input through the 16-bit instantiation
+        rng = np.random.default_rng(5)
+        q = torch.tensor((np.round(rng.standard_normal((40, 77)) * 4) / 4).astype(np.float32)).bfloat16()
+        gq = [[int(c) for c in rng.choice(80, size=int(rng.integers(0, 5)), replace=False)] for _ in range(40)]
+        qo = q.float().numpy()
+        a = rm.compute_all_dense_metrics(q, gq, recall_k=[1, 5, 10], ndcg_k=[5])
+        o = dmo.recall_at_k(qo, gq, [1, 5, 10])
+        assert all(a[k] == o[k] for k in o)
+        assert a["MedianRank_V2T"] == dmo.median_rank(qo, gq)
+        assert abs(a["MAP"] - dmo.mean_ap(qo, gq)) <= 1e-6
