@@ -80,7 +80,7 @@ static int launch_epi(const void* A, const void* B, int Ma, int Nb, int Kp, int 
     if ((rc = make_tmap_bf16_2d(&tmB2, B, Nb, Kp, ldb, 128))) return rc;
     auto kern2 = te2_kernel<Epi, false>;
     static bool attr2_done_dev[64] = {};
-  bool& attr2_done = attr2_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
+    bool& attr2_done = attr2_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
     if (!attr2_done) {
       if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, TE2_SMEM_BYTES) != cudaSuccess)
         return B2_ECUDA;
