@@ -1,0 +1,193 @@
+// Kernels of scalars.cu (device-side scalar plumbing of the losses; see there).
+// No inline PTX and no include: CUDA types / intrinsics and warp_sum come from the including translation unit
+// (common.cuh) or from the host emulation (tests/emul/).
+#pragma once
+
+namespace b2 {
+
+__global__ void dyn_prep_kernel(const float* __restrict__ log_temp, const float* __restrict__ bias, float clamp_min,
+                                float bound, float* __restrict__ dyn) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float tau = expf(log_temp[0]);
+  float clamped = 0.f;
+  if (clamp_min > 0.f && tau < clamp_min) {   // torch.clamp(min=1e-4): gradient is zero when active
+    tau = clamp_min;
+    clamped = 1.f;
+  }
+  const float scale2 = 1.4426950408889634f / tau;
+  // P = 2^(f(S)*scale2 - shift2) with f(S) <= bound. shift2 = scale2*bound - OFF keeps the largest term at
+  // 2^OFF; OFF > 0 only when the dynamic range 2*bound/tau would otherwise underflow fp32 (tau < ~0.023).
+  float off = 2.f * bound * scale2 - 120.f;
+  off = fminf(fmaxf(off, 0.f), 100.f);
+  const float shift2 = scale2 * bound - off;
+  dyn[0] = scale2;
+  dyn[1] = shift2;
+  dyn[2] = 1.f / tau;
+  dyn[3] = tau;
+  dyn[4] = clamped;
+  dyn[5] = bias ? bias[0] : 0.f;
+  dyn[6] = 0.6931471805599453f * shift2;
+  dyn[7] = 1.f - clamped;
+  dyn[8] = 30.f;
+  dyn[9] = 0.f;
+  dyn[10] = 0.f;
+}
+
+__global__ void dyn_set_siglip_kernel(float* __restrict__ dyn, float lclamp, float yneg) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  dyn[8] = lclamp;
+  dyn[9] = yneg;
+}
+
+// acc[slot] += sum_r ln( sums[r] ) + ln2*shift2 ;  scale_out[r] = c / sums[r]
+__global__ void __launch_bounds__(256)
+lse_finalize_kernel(const float* __restrict__ sums, int n, const float* __restrict__ dyn, float c,
+                    float* __restrict__ scale_out, double* __restrict__ acc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < n) {
+    const float s = sums[i];
+    v = (double)logf(s) + (double)dyn[6];
+    if (scale_out) scale_out[i] = c / s;
+  }
+  // block reduce in double
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    v = sh[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0 && acc) atomicAdd(acc, v);
+  }
+}
+
+// acc += sum_i f(v[i])
+__global__ void __launch_bounds__(256)
+vec_fsum_kernel(const float* __restrict__ v, int n, int gated, double* __restrict__ acc) {
+  double t = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double s = (double)v[i];
+    t += gated ? s / (1.0 + exp(-s)) : s;
+  }
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double u = 0.0;
+    for (int w = 0; w < 8; ++w) u += sh[w];
+    atomicAdd(acc, u);
+  }
+}
+
+// acc += sum_r f(a[r,:K] . b[r,:K]),  f = identity or s*sigmoid(s);  optionally stores the raw dots
+__global__ void __launch_bounds__(256)
+diag_sum_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b, int ldb, int rows,
+                int K, int gated, float* __restrict__ dots, double* __restrict__ acc) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  if (warp < rows) {
+    const __nv_bfloat162* ar = reinterpret_cast<const __nv_bfloat162*>(a + (size_t)warp * lda);
+    const __nv_bfloat162* br = reinterpret_cast<const __nv_bfloat162*>(b + (size_t)warp * ldb);
+    for (int c = lane; c < K / 2; c += 32) {
+      const float2 av = __bfloat1622float2(ar[c]);
+      const float2 bv = __bfloat1622float2(br[c]);
+      s = fmaf(av.x, bv.x, s);
+      s = fmaf(av.y, bv.y, s);
+    }
+  }
+  s = warp_sum(s);
+  __shared__ double sh[8];
+  if (lane == 0) {
+    if (warp < rows && dots) dots[warp] = s;
+    double f = 0.0;
+    if (warp < rows) f = gated ? (double)s / (1.0 + exp(-(double)s)) : (double)s;
+    sh[threadIdx.x >> 5] = f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(acc, t);
+  }
+}
+
+
+// One launch for the whole scalar tail of the softmax (CLIP / gated) loss forward (utils/loss/contrastive.py:155-164):
+//   sums = [colsum (N) | rowsum (N) | target dots (N)]  (already all-reduced across ranks)
+//   rowscale[i] = c / rowsum[i], colscale[j] = c / colsum[j]  (c = 0.5 / N, the backward's softmax denominators)
+//   loss = c * (sum_i ln rowsum_i + sum_j ln colsum_j + 2 N ln2 shift2) - ((1 - eps) / tau * sum_i f(dot_i) + unif) / N
+// Up to 64 CTAs; every CTA reduces its slice in fp64 and parks three partial sums in a device scratch block, the CTA that
+// draws the last ticket adds the partials in CTA order (deterministic) and writes the loss. (Was one CTA: 28 us at
+// N = 32k — 3 % of an 8-GPU step.) The scratch block is shared by all launches of the process: one stream at a time.
+constexpr int FIN_MAX_BLOCKS = 64;
+__device__ double g_fin_partial[3 * FIN_MAX_BLOCKS];
+__device__ unsigned int g_fin_ticket = 0;
+
+__global__ void __launch_bounds__(1024)
+clip_finalize_kernel(const float* __restrict__ sums, int n, const float* __restrict__ dyn, float eps, int gated,
+                     const double* __restrict__ unif, float* __restrict__ rowscale, float* __restrict__ colscale,
+                     float* __restrict__ loss_out, double* __restrict__ acc_out) {
+  const float c = 0.5f / (float)n;
+  const double shift = (double)dyn[6];
+  double a_row = 0.0, a_col = 0.0, a_dot = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float cs = sums[i], rs = sums[n + i];
+    const double d = (double)sums[2 * n + i];
+    colscale[i] = c / cs;
+    rowscale[i] = c / rs;
+    a_col += (double)logf(cs) + shift;
+    a_row += (double)logf(rs) + shift;
+    a_dot += gated ? d / (1.0 + exp(-d)) : d;
+  }
+  __shared__ double sh[3][32];
+  __shared__ bool last;
+  for (int o = 16; o > 0; o >>= 1) {
+    a_row += __shfl_xor_sync(0xffffffffu, a_row, o);
+    a_col += __shfl_xor_sync(0xffffffffu, a_col, o);
+    a_dot += __shfl_xor_sync(0xffffffffu, a_dot, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = a_row;
+    sh[1][threadIdx.x >> 5] = a_col;
+    sh[2][threadIdx.x >> 5] = a_dot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0, cc = 0.0, d = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { r += sh[0][w]; cc += sh[1][w]; d += sh[2][w]; }
+    g_fin_partial[3 * blockIdx.x] = r;
+    g_fin_partial[3 * blockIdx.x + 1] = cc;
+    g_fin_partial[3 * blockIdx.x + 2] = d;
+    __threadfence();
+    last = atomicAdd(&g_fin_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double r = 0.0, cc = 0.0, d = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) {
+      r += g_fin_partial[3 * b];
+      cc += g_fin_partial[3 * b + 1];
+      d += g_fin_partial[3 * b + 2];
+    }
+    g_fin_ticket = 0;                                   // ready for the next launch (stream order)
+    const double u = unif ? unif[0] : 0.0;
+    const double loss = (0.5 / n) * (r + cc) - ((1.0 - (double)eps) * d * (double)dyn[2] + u) / n;
+    loss_out[0] = (float)loss;
+    if (acc_out) { acc_out[0] = r; acc_out[1] = cc; acc_out[2] = d; }
+  }
+}
+
+// d loss / d log_temp = (unif / N - scal0 / tau) * [tau not clamped] * grad_out   (Appendix A.1: -sum G L)
+__global__ void clip_dlogtemp_kernel(const double* __restrict__ scal0, const float* __restrict__ dyn,
+                                     const float* __restrict__ gmul, const double* __restrict__ unif, int n,
+                                     float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double u = unif ? unif[0] : 0.0;
+  out[0] = (float)((u / n - scal0[0] * (double)dyn[2]) * (double)dyn[7] * (double)gmul[0]);
+}
+
+}  // namespace b2
