@@ -1,0 +1,144 @@
+// Host library with the C-ABI entry points the CLIP loss path calls (include/b200clip.h), for running the package's own
+// autograd function on CPU (tests/test_emulated_clip_loss.py, single process and 2-rank gloo):
+//   * the CUDA-core kernels are the SHIPPED device code (l2norm_kernels.cuh, scalars_kernels.cuh) under the emulation;
+//   * the two tcgen05 tile kernels cannot be emulated; b200clip_logits_lse_fwd / b200clip_logits_bwd are MODELS that follow
+//     the contracts written in include/b200clip.h operation by operation (bf16 operands, fp32 logits, G rounded to bf16
+//     (hi + lo when hp) before the output product, diagonal target subtracted in fp32 before the rounding, diag_corr,
+//     scal[0], gnorm / out_scale scaling). They exist to exercise the host code around the kernels, not to test the kernels.
+#include "pool_mma_prims_emul.h"
+#include "../../deepcoro_clip_b200/csrc/l2norm_kernels.cuh"
+#include "../../deepcoro_clip_b200/csrc/scalars_kernels.cuh"
+
+using namespace b2;
+using bf16 = __nv_bfloat16;
+
+static inline float bf(const void* base, long long idx) { return __bfloat162float(static_cast<const bf16*>(base)[idx]); }
+
+extern "C" int b200clip_l2norm_fwd(const void* x, int dtype, long long ldx, int rows, int dim, void* out, int ldo, int Kp,
+                                   int split3_role, float* inv_norm, float* xhat_f32, int ldh, int normalize, void*) {
+  if (rows <= 0 || dim <= 0 || Kp < dim || Kp % 64) return -22;
+  const int blocks = (rows + 7) / 8;
+  auto o = reinterpret_cast<bf16*>(out);
+  switch (dtype) {
+    case 0: emul::launch(blocks, 256, [&] { l2norm_fwd_kernel<float>((const float*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); }); break;
+    case 1: emul::launch(blocks, 256, [&] { l2norm_fwd_kernel<bf16>((const bf16*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); }); break;
+    case 2: emul::launch(blocks, 256, [&] { l2norm_fwd_kernel<__half>((const __half*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); }); break;
+    default: return -22;
+  }
+  return 0;
+}
+
+template <typename T>
+static int bwd_t(const float* dxh, int ldg, const T* x, long ldx, const float* inv_norm, const void* ox, int odtype, long ldox,
+                 const float* oinv, const bf16* ohi, int ldohi, const float2* dc, const float* usum, float gscale, float ucoef,
+                 const float* omul, const float* gmul, int rows, int dim, float* dx, long lddx) {
+  const int blocks = (rows + 7) / 8;
+  switch (ox ? odtype : 0) {
+    case 0: emul::launch(blocks, 256, [&] { l2norm_bwd_kernel<T, float>(dxh, ldg, x, ldx, inv_norm, (const float*)ox, ldox, oinv, ohi, ldohi, dc, usum, gscale, ucoef, omul, gmul, rows, dim, dx, lddx); }); break;
+    case 1: emul::launch(blocks, 256, [&] { l2norm_bwd_kernel<T, bf16>(dxh, ldg, x, ldx, inv_norm, (const bf16*)ox, ldox, oinv, ohi, ldohi, dc, usum, gscale, ucoef, omul, gmul, rows, dim, dx, lddx); }); break;
+    case 2: emul::launch(blocks, 256, [&] { l2norm_bwd_kernel<T, __half>(dxh, ldg, x, ldx, inv_norm, (const __half*)ox, ldox, oinv, ohi, ldohi, dc, usum, gscale, ucoef, omul, gmul, rows, dim, dx, lddx); }); break;
+    default: return -22;
+  }
+  return 0;
+}
+extern "C" int b200clip_l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long long ldx, const float* inv_norm,
+                                   const void* ox, int odtype, long long ldox, const float* oinv, const void* ohi, int ldohi,
+                                   const float* dc, const float* usum, float gscale, float ucoef, const float* omul,
+                                   const float* gmul, int rows, int dim, float* dx, long long lddx, void*) {
+  if (rows <= 0 || dim <= 0 || !dxh || !x || !inv_norm || !dx) return -22;
+  if (dc && (!ox || !oinv || !ohi)) return -22;
+  auto h = (const bf16*)ohi;
+  auto d2 = (const float2*)dc;
+  switch (dtype) {
+    case 0: return bwd_t<float>(dxh, ldg, (const float*)x, ldx, inv_norm, ox, odtype, ldox, oinv, h, ldohi, d2, usum, gscale, ucoef, omul, gmul, rows, dim, dx, lddx);
+    case 1: return bwd_t<bf16>(dxh, ldg, (const bf16*)x, ldx, inv_norm, ox, odtype, ldox, oinv, h, ldohi, d2, usum, gscale, ucoef, omul, gmul, rows, dim, dx, lddx);
+    case 2: return bwd_t<__half>(dxh, ldg, (const __half*)x, ldx, inv_norm, ox, odtype, ldox, oinv, h, ldohi, d2, usum, gscale, ucoef, omul, gmul, rows, dim, dx, lddx);
+    default: return -22;
+  }
+}
+
+extern "C" int b200clip_colsum_bf16(const void* xh, int ld, int rows, int dim, float* out, void*) {
+  if (rows <= 0 || dim <= 0 || !xh || !out) return -22;
+  emul::launch(emul::Dim{(unsigned)((dim + 255) / 256), rows < 256 ? 1u : 64u, 1}, 256,
+               [&] { colsum_bf16_kernel((const bf16*)xh, ld, rows, dim, out); });
+  return 0;
+}
+
+extern "C" int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, void*) {
+  emul::launch(1, 32, [&] { dyn_prep_kernel(log_temp, bias, clamp_min, bound, dyn); });
+  return 0;
+}
+extern "C" int b200clip_clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif,
+                                      float* rowscale, float* colscale, float* loss_out, double* acc_out, void*) {
+  if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out) return -22;
+  int blocks = (n + 1023) / 1024;
+  if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
+  emul::launch(blocks, 1024, [&] { clip_finalize_kernel(sums, n, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out); });
+  return 0;
+}
+extern "C" int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
+                                      float* out, void*) {
+  if (!scal0 || !dyn || !gmul || !out || n <= 0) return -22;
+  emul::launch(1, 32, [&] { clip_dlogtemp_kernel(scal0, dyn, gmul, unif, n, out); });
+  return 0;
+}
+
+// ---------------- models of the two tcgen05 tile kernels (contracts: include/b200clip.h K2 / K3) ----------------
+static inline float gate(float s) { return s / (1.f + expf(-s)); }
+
+extern "C" int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
+                                       float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag,
+                                       int diag_off, void*) {
+  if (dyn) { scale2 = dyn[0]; shift2 = dyn[1]; }
+  for (int i = 0; i < Ma; ++i)
+    for (int j = 0; j < Nb; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < Kp; ++k) s = fmaf(bf(A, (long long)i * lda + k), bf(B, (long long)j * ldb + k), s);
+      if (diag && i + diag_off == j) diag[i] = s;
+      const float p = exp2f(fmaf(gated ? gate(s) : s, scale2, -shift2));
+      rowsum[i] += p;
+      colsum[j] += p;
+    }
+  return 0;
+}
+
+extern "C" int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int hi_off,
+                                   int ldx, int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
+                                   const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
+                                   const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd,
+                                   double* scal, int, void*) {
+  if (mode != 0 && mode != 1) return -38;                  // the CLIP / gated softmax modes only
+  (void)inv_tau; (void)bias; (void)wneg_c; (void)Dp;
+  if (dyn) { scale2 = dyn[0]; shift2 = dyn[1]; out_scale = dyn[2]; }
+  if (!(gnorm > 0.f)) gnorm = 1.f;
+  const float ign = 1.f / gnorm, ydn = ydiag * gnorm;
+  double tsum = 0.0;
+  for (int i = 0; i < Nx; ++i) {
+    const float rs = rowscale[i] * gnorm;
+    for (int j = 0; j < Ny; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < Kp; ++k) s = fmaf(bf(X, (long long)i * ldx + k), bf(Y, (long long)j * ldy + k), s);
+      float f = s, fp = 1.f;
+      if (mode == 1) {
+        const float sig = 1.f / (1.f + expf(-s));
+        f = s * sig;
+        fp = sig * (1.f + s * (1.f - sig));
+      }
+      float g = exp2f(fmaf(f, scale2, -shift2)) * (rs + colscale[j] * gnorm);
+      const bool on_diag = ydiag != 0.f && i + diag_off == j;
+      if (on_diag) g -= ydn;
+      tsum += (double)g * (double)f;
+      if (mode == 1) g *= fp;
+      float gb = __bfloat162float(__float2bfloat16_rn(g));
+      if (hp) gb += __bfloat162float(__float2bfloat16_rn(g - gb));      // hi + lo: what the two TS-MMAs consume
+      if (on_diag && diag_corr) {
+        diag_corr[2 * i] = (g - gb) * ign;
+        diag_corr[2 * i + 1] = gb * ign;
+      }
+      const float ge = gb * out_scale * ign;
+      for (int d = 0; d < D; ++d) dX[(long long)i * ldd + d] += ge * bf(Y, (long long)j * ldy + hi_off + d);
+    }
+  }
+  if (scal) scal[0] += tsum * (double)ign;
+  return 0;
+}

@@ -33,6 +33,11 @@ inline __nv_bfloat16 __float2bfloat16_rn(float v) {
 }
 inline float __half2float(__half v) { _Float16 h; std::memcpy(&h, &v.x, 2); return (float)h; }
 inline __half __float2half_rn(float v) { _Float16 h = (_Float16)v; __half r; std::memcpy(&r.x, &h, 2); return r; }
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+inline float2 __bfloat1622float2(__nv_bfloat162 v) { return float2{__bfloat162float(v.x), __bfloat162float(v.y)}; }
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0u; }
+inline int atomicExch(int* p, int v) { std::lock_guard<std::mutex> g(emul::g_atomic_lock); const int o = *p; *p = v; return o; }
 inline void __pipeline_memcpy_async(void* dst, const void* src, size_t n) { std::memcpy(dst, src, n); }
 inline void __pipeline_commit() {}
 inline void __pipeline_wait_prior(int) {}
