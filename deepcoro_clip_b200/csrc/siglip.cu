@@ -179,187 +179,11 @@ __global__ void siglip_entropy_coef_kernel(const double* __restrict__ stats_all,
 //                    diag (optional, 7 floats) = {ent[0..5], bce loss} for get_entropy_diagnostics()
 //   siglip_scalar_grads: dlog_temp = -red[2] / tau * [tau not clamped] * grad_out ; dbias = red[1] * grad_out
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void siglip_combine_kernel(const double* __restrict__ acc, double wn_c, double* __restrict__ red) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  red[0] = wn_c * acc[1] + acc[4];
-  red[1] = acc[2] + acc[5];
-  red[2] = acc[0] + acc[6];
-}
-__global__ void siglip_loss_out_kernel(const double* __restrict__ red, const int* __restrict__ overflow,
-                                       const float* __restrict__ ent, float* __restrict__ loss_out,
-                                       float* __restrict__ diag) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double loss = red[0];
-  if (overflow && overflow[0] > 0) loss = nan("");
-  if (diag) {
-    for (int i = 0; i < 6; ++i) diag[i] = ent ? ent[i] : 0.f;
-    diag[6] = (float)loss;
-  }
-  if (ent) loss += (double)ent[5];
-  loss_out[0] = (float)loss;
-}
-__global__ void siglip_scalar_grads_kernel(const double* __restrict__ red, const float* __restrict__ dyn,
-                                           const float* __restrict__ gmul, float* __restrict__ dlt,
-                                           float* __restrict__ dbias) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double g = (double)gmul[0];
-  if (dlt) dlt[0] = (float)(-(red[2] * (double)dyn[2]) * (double)dyn[7] * g);
-  if (dbias) dbias[0] = (float)(red[1] * g);
-}
+}  // namespace b2
 
-// ---------------------------------------------------------------------------------------------------------------
-// positive-list compaction: one warp per video row scans pos_mask[row, :T] (and pos_weights) once.
-//   lists: col[row][cap] int32, y[row][cap] (= clamp(mask,0,1)), pw[row][cap] (raw pos_weights or 1)
-//   cnt[row] = number of entries, ysum[row] = sum_j y_ij (auto_balance), overflow flag if a row has > cap positives
-// mask == nullptr: diagonal targets (row i -> column i for i < min(B, T)), contrastive.py:274-278.
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-siglip_compact_kernel(const float* __restrict__ mask, long ldm, const float* __restrict__ pw, long ldw, int B, int T,
-                      int cap, int* __restrict__ col, float* __restrict__ y, float* __restrict__ w,
-                      int* __restrict__ cnt, float* __restrict__ ysum, int* __restrict__ overflow) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= B) return;
-  if (!mask) {
-    if (lane == 0) {
-      const bool has = row < T;
-      cnt[row] = has ? 1 : 0;
-      ysum[row] = has ? 1.f : 0.f;
-      if (has) {
-        col[(size_t)row * cap] = row;
-        y[(size_t)row * cap] = 1.f;
-        w[(size_t)row * cap] = 1.f;
-      }
-    }
-    return;
-  }
-  const float* mr = mask + (size_t)row * ldm;
-  const float* wr = pw ? pw + (size_t)row * ldw : nullptr;
-  int n = 0;
-  float ys = 0.f;
-  for (int c0 = 0; c0 < T; c0 += 32) {
-    const int c = c0 + lane;
-    float v = c < T ? mr[c] : 0.f;
-    v = fminf(fmaxf(v, 0.f), 1.f);
-    const bool pos = v > 0.f;
-    const unsigned b = __ballot_sync(0xffffffffu, pos);
-    if (pos) {
-      const int slot = n + __popc(b & ((1u << lane) - 1));
-      if (slot < cap) {
-        col[(size_t)row * cap + slot] = c;
-        y[(size_t)row * cap + slot] = v;
-        w[(size_t)row * cap + slot] = wr ? wr[c] : 1.f;
-      }
-    }
-    n += __popc(b);
-    ys += v;
-  }
-  ys = warp_sum(ys);
-  if (lane == 0) {
-    cnt[row] = n < cap ? n : cap;
-    ysum[row] = ys;
-    if (n > cap) atomicExch(overflow, 1);
-  }
-}
+#include "siglip_kernels.cuh"
 
-// ---------------------------------------------------------------------------------------------------------------
-// sparse corrections. One warp per video row; for each list entry (row i, column j):
-//   s = vhat_i . that_j (bf16 operands, all K panels), R = s/tau + b, L = clamp(R), sigma, softplus
-//   weight rule (contrastive.py:283-298): y > 0.5 -> positive weight (severity * positive_weight | positive_weight |
-//   auto-balance ratio), else negative_weight.
-//   loss   += w (sp - L y) - wn sp                                   (dense part already added wn * sp)
-//   dG      = [w (sigma - y) - rounded(wn sigma)] * inr * c             (dense MMA used the bf16-rounded gradient)
-//   dVhat_i += dG/tau * that_j(hi) ; dThat_j += dG/tau * vhat_i(hi)  (atomic: several rows may share a text)
-//   scalar sums use the unrounded dense value: dbias += [w(sigma-y) - wn sigma] inr c ; tsum += (same) * s
-// acc (double): [0] loss correction (already * c), [1] dbias correction, [2] sum dG_fp32 * s correction
-// ---------------------------------------------------------------------------------------------------------------
-struct PosParams {
-  const __nv_bfloat16* V; int ldv;
-  const __nv_bfloat16* T; int ldt;
-  int K, Dp, D, hi_off;
-  int B, Tn, cap;
-  const int* col; const float* y; const float* w; const int* cnt; const float* ysum;
-  const float* dyn;
-  float positive_weight, negative_weight, c, gnorm;
-  int hp;
-  int use_pw, auto_balance;  // use_pw: bit 0 = per-pair pos_weights, bit 1 = weight rule "mask > 0" instead of "target > 0.5"
-  float* dV; int lddv;     // may be null (loss only)
-  float* dT; int lddt;
-  double* acc;
-};
-
-__global__ void __launch_bounds__(256) siglip_pos_kernel(PosParams p) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  double a_loss = 0.0, a_bias = 0.0, a_t = 0.0;
-  if (row < p.B) {
-    const float inv_tau = p.dyn[2], bias = p.dyn[5], lc = p.dyn[8], yneg = p.dyn[9];
-    const bool use_pw = (p.use_pw & 1) != 0, rule_mask = (p.use_pw & 2) != 0;
-    const int n = p.cnt[row];
-    float ratio = 1.f;
-    if (p.auto_balance) {
-      const float pc = fmaxf(p.ysum[row], 1.f);
-      ratio = fmaxf(((float)p.Tn - pc) / pc, 1.f);
-    }
-    const __nv_bfloat16* vr = p.V + (size_t)row * p.ldv;
-    for (int e = 0; e < n; ++e) {
-      const int j = p.col[(size_t)row * p.cap + e];
-      const float yraw = p.y[(size_t)row * p.cap + e];
-      const float yv = fmaf(yraw, 1.f - 2.f * yneg, yneg);          // label smoothing: y (1 - eps) + eps / 2
-      const float pwv = p.w[(size_t)row * p.cap + e];
-      const __nv_bfloat16* tr = p.T + (size_t)j * p.ldt;
-      float s = 0.f;
-      for (int k = lane * 2; k < p.K; k += 64) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vr + k));
-        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tr + k));
-        s = fmaf(a.x, b.x, s);
-        s = fmaf(a.y, b.y, s);
-      }
-      s = warp_sum(s);
-      const float R = fmaf(s, inv_tau, bias);
-      const float L = fminf(fmaxf(R, -lc), lc);
-      const float ex = __expf(-fabsf(L));
-      const float sp = fmaxf(L, 0.f) + log1pf(ex);
-      const float sig = L >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
-      const float inr = fabsf(R) <= lc ? 1.f : 0.f;
-      float w = p.negative_weight;
-      if (rule_mask ? yraw > 0.f : yv > 0.5f)
-        w = p.auto_balance ? ratio : (use_pw ? pwv * p.positive_weight : p.positive_weight);
-      const float g_full = w * (sig - yv) * inr * p.c;
-      const float g_dense = p.negative_weight * p.c * (sig - yneg) * inr;
-      if (lane == 0) {
-        a_loss += (double)((w * (sp - L * yv) - p.negative_weight * (sp - L * yneg)) * p.c);
-        a_bias += (double)(g_full - g_dense);
-        a_t += (double)((g_full - g_dense) * s);
-      }
-      if (p.dV) {
-        // the dense tile kernel fed bf16(g_dense * gnorm) (+ the bf16 residual when hp) to the tensor core
-        const float gs = g_dense * p.gnorm;
-        float gr = __bfloat162float(__float2bfloat16_rn(gs));
-        if (p.hp) gr += __bfloat162float(__float2bfloat16_rn(gs - gr));
-        const float dg = (g_full - gr / p.gnorm) * inv_tau;
-        float* dv = p.dV + (size_t)row * p.lddv;
-        float* dt = p.dT + (size_t)j * p.lddt;
-        for (int d = lane; d < p.D; d += 32) {
-          dv[d] += dg * __bfloat162float(tr[p.hi_off + d]);                  // this warp owns row i
-          atomicAdd(dt + d, dg * __bfloat162float(vr[p.hi_off + d]));
-        }
-      }
-    }
-  }
-  __shared__ double sh[3][8];
-  if (lane == 0) {
-    sh[0][threadIdx.x >> 5] = a_loss;
-    sh[1][threadIdx.x >> 5] = a_bias;
-    sh[2][threadIdx.x >> 5] = a_t;
-  }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
-    if (t != 0.0) atomicAdd(p.acc + threadIdx.x, t);
-  }
-}
+namespace b2 {
 
 }  // namespace b2
 
