@@ -1,5 +1,5 @@
 // Host library with the C-ABI entry points the CLIP loss path calls (include/b200clip.h), for running the package's own
-// autograd function on CPU (tests/test_emulated_clip_loss.py, single process and 2-rank gloo):
+// autograd function on CPU (tests/test_emulated_losses.py, single process and 2-rank gloo):
 //   * the CUDA-core kernels are the SHIPPED device code (l2norm_kernels.cuh, scalars_kernels.cuh) under the emulation;
 //   * the two tcgen05 tile kernels cannot be emulated; b200clip_logits_lse_fwd / b200clip_logits_bwd are MODELS that follow
 //     the contracts written in include/b200clip.h operation by operation (bf16 operands, fp32 logits, G rounded to bf16
@@ -8,6 +8,7 @@
 #include "pool_mma_prims_emul.h"
 #include "../../deepcoro_clip_b200/csrc/l2norm_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/scalars_kernels.cuh"
+#include "../../deepcoro_clip_b200/csrc/siglip_kernels.cuh"
 
 using namespace b2;
 using bf16 = __nv_bfloat16;
@@ -107,11 +108,36 @@ extern "C" int b200clip_logits_bwd(int mode, const void* X, const void* Y, int N
                                    const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
                                    const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd,
                                    double* scal, int, void*) {
-  if (mode != 0 && mode != 1) return -38;                  // the CLIP / gated softmax modes only
-  (void)inv_tau; (void)bias; (void)wneg_c; (void)Dp;
-  if (dyn) { scale2 = dyn[0]; shift2 = dyn[1]; out_scale = dyn[2]; }
+  if (mode != 0 && mode != 1 && mode != 2) return -38;     // CLIP / gated softmax and plain SigLIP (no entropy mode)
+  (void)Dp;
+  float lclamp = 30.f, yneg = 0.f;
+  if (dyn) { scale2 = dyn[0]; shift2 = dyn[1]; inv_tau = dyn[2]; bias = dyn[5]; out_scale = dyn[2]; lclamp = dyn[8]; yneg = dyn[9]; }
   if (!(gnorm > 0.f)) gnorm = 1.f;
   const float ign = 1.f / gnorm, ydn = ydiag * gnorm;
+  if (mode == 2) {
+    // G = wneg_c (sigmoid(clamp(R)) - yneg) [|R| <= lc], R = S / tau + bias; scal: [0] sum G S, [1] sum softplus, [2] sum G
+    const float wn = wneg_c * gnorm;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int i = 0; i < Nx; ++i)
+      for (int j = 0; j < Ny; ++j) {
+        float sdot = 0.f;
+        for (int k = 0; k < Kp; ++k) sdot = fmaf(bf(X, (long long)i * ldx + k), bf(Y, (long long)j * ldy + k), sdot);
+        const float R = fmaf(sdot, inv_tau, bias);
+        const float Lc = fminf(fmaxf(R, -lclamp), lclamp);
+        const float ex = expf(-fabsf(Lc));
+        const float sig = Lc >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
+        const float g = fabsf(R) <= lclamp ? wn * (sig - yneg) : 0.f;
+        t1 += (double)(fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + log1pf(ex)));
+        t2 += (double)g;
+        t0 += (double)g * (double)sdot;
+        float gb = __bfloat162float(__float2bfloat16_rn(g));
+        if (hp) gb += __bfloat162float(__float2bfloat16_rn(g - gb));
+        const float ge = gb * out_scale * ign;
+        for (int d = 0; d < D; ++d) dX[(long long)i * ldd + d] += ge * bf(Y, (long long)j * ldy + hi_off + d);
+      }
+    if (scal) { scal[0] += t0 * (double)ign; scal[1] += t1; scal[2] += t2 * (double)ign; }
+    return 0;
+  }
   double tsum = 0.0;
   for (int i = 0; i < Nx; ++i) {
     const float rs = rowscale[i] * gnorm;
@@ -140,5 +166,56 @@ extern "C" int b200clip_logits_bwd(int mode, const void* X, const void* Y, int N
     }
   }
   if (scal) scal[0] += tsum * (double)ign;
+  return 0;
+}
+
+// ---------------- SigLIP pieces: shipped CUDA-core kernels + the model of the forward-only dense tile kernel ----------------
+extern "C" int b200clip_dyn_set_siglip(float* dyn, float lclamp, float yneg, void*) {
+  emul::launch(1, 32, [&] { dyn_set_siglip_kernel(dyn, lclamp, yneg); });
+  return 0;
+}
+extern "C" int b200clip_siglip_dense_fwd(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt, const float* dyn,
+                                         double* acc, void*) {
+  const float inv_tau = dyn[2], bias = dyn[5], lc = dyn[8], yneg = dyn[9];
+  double t = 0.0;
+  for (int i = 0; i < B; ++i)
+    for (int j = 0; j < Tn; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < Kp; ++k) s = fmaf(bf(V, (long long)i * ldv + k), bf(T, (long long)j * ldt + k), s);
+      const float L = fminf(fmaxf(fmaf(s, inv_tau, bias), -lc), lc);
+      t += (double)(fmaf(-yneg, L, fmaxf(L, 0.f) + log1pf(expf(-fabsf(L)))));
+    }
+  acc[0] += t;
+  return 0;
+}
+extern "C" int b200clip_siglip_combine(const double* acc, double wn_c, double* red, void*) {
+  emul::launch(1, 32, [&] { siglip_combine_kernel(acc, wn_c, red); });
+  return 0;
+}
+extern "C" int b200clip_siglip_loss_out(const double* red, const int* overflow, const float* ent, float* loss_out, float* diag,
+                                        void*) {
+  emul::launch(1, 32, [&] { siglip_loss_out_kernel(red, overflow, ent, loss_out, diag); });
+  return 0;
+}
+extern "C" int b200clip_siglip_scalar_grads(const double* red, const float* dyn, const float* gmul, float* dlt, float* dbias,
+                                            void*) {
+  emul::launch(1, 32, [&] { siglip_scalar_grads_kernel(red, dyn, gmul, dlt, dbias); });
+  return 0;
+}
+extern "C" int b200clip_siglip_compact(const float* mask, long long ldm, const float* pw, long long ldw, int B, int T, int cap,
+                                       int* col, float* y, float* w, int* cnt, float* ysum, int* overflow, void*) {
+  if (B <= 0 || T <= 0 || cap <= 0) return -22;
+  emul::launch((B + 7) / 8, 256, [&] { siglip_compact_kernel(mask, ldm, pw, ldw, B, T, cap, col, y, w, cnt, ysum, overflow); });
+  return 0;
+}
+extern "C" int b200clip_siglip_pos(const void* V, int ldv, const void* T, int ldt, int K, int Dp, int D, int hi_off, int B, int Tn,
+                                   int cap, const int* col, const float* y, const float* w, const int* cnt, const float* ysum,
+                                   const float* dyn, float positive_weight, float negative_weight, float c, float gnorm, int hp,
+                                   int use_pw, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc, void*) {
+  if (B <= 0 || K <= 0 || (K & 1)) return -22;
+  if ((dV == nullptr) != (dT == nullptr)) return -22;
+  PosParams p{(const bf16*)V, ldv, (const bf16*)T, ldt, K, Dp, D, hi_off, B, Tn, cap, col, y, w, cnt, ysum, dyn, positive_weight,
+              negative_weight, c, gnorm > 0.f ? gnorm : 1.f, hp ? 1 : 0, use_pw, auto_balance, dV, lddv, dT, lddt, acc};
+  emul::launch((B + 7) / 8, 256, [&] { siglip_pos_kernel(p); });
   return 0;
 }
