@@ -15,49 +15,6 @@
 #include "host_api.h"
 #include "retrieval_epi.cuh"
 
-namespace b2 {
-
-// hits[j] += #{rows: counts[row] < k_values[j]} (recall numerators, integer exact); mrr in double is done on the host
-__global__ void __launch_bounds__(256)
-recall_hits_kernel(const int* __restrict__ counts, int rows, const int* __restrict__ kvals, int nk,
-                   unsigned long long* __restrict__ hits) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int j = 0; j < nk; ++j) {
-    const bool hit = i < rows && counts[i] < kvals[j];
-    const unsigned b = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(hits + j, (unsigned long long)__popc(b));
-  }
-}
-
-// MRR numerator sum_i 1 / (counts[i] + 1) without a host pass over the rows: ranks are integers <= n_bins, so the sum is
-// sum_r hist[r] / (r + 1) over the rank histogram — accumulated in fp64 in increasing-rank order by ONE CTA with a fixed
-// reduction tree: deterministic and independent of the row order and of the text sharding (it differs from the
-// reference's row-order double sum, retrieval_metrics_streaming.py:162-172, only by fp64 rounding, ~1e-16 relative).
-__global__ void __launch_bounds__(256)
-rank_hist_kernel(const int* __restrict__ counts, int rows, int n_bins, int* __restrict__ hist) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < rows) {
-    int c = counts[i];
-    c = c < 0 ? 0 : (c >= n_bins ? n_bins - 1 : c);
-    atomicAdd(hist + c, 1);
-  }
-}
-__global__ void __launch_bounds__(1024)
-rank_hist_mrr_kernel(const int* __restrict__ hist, int n_bins, double* __restrict__ out) {
-  double a = 0.0;
-  for (int r = threadIdx.x; r < n_bins; r += blockDim.x) a += (double)hist[r] / (double)(r + 1);
-  __shared__ double sh[1024];
-  sh[threadIdx.x] = a;
-  __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = sh[0];
-}
-
-}  // namespace b2
-
 namespace b2host {
 using namespace b2;
 

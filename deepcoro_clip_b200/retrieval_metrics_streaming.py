@@ -138,12 +138,13 @@ def _sweep(vop, top, gt, k: int, use_ddp: bool, group=None, _shard=None):
         if counts is not None:
             dist.all_reduce(counts, group=group)
         if k > 0:
-            gs = torch.empty((W, N, k), dtype=torch.float32, device=dev)
-            gi = torch.empty((W, N, k), dtype=torch.int64, device=dev)
+            # concatenated [W * N, k] outputs: the form every backend accepts (gloo rejects the stacked [W, N, k] shape)
+            gs = torch.empty((W * N, k), dtype=torch.float32, device=dev)
+            gi = torch.empty((W * N, k), dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(gs, out_s, group=group)
             dist.all_gather_into_tensor(gi, out_i, group=group)
-            cs = gs.permute(1, 0, 2).reshape(N, W * k).contiguous()
-            ci = gi.permute(1, 0, 2).reshape(N, W * k)
+            cs = gs.view(W, N, k).permute(1, 0, 2).reshape(N, W * k).contiguous()
+            ci = gi.view(W, N, k).permute(1, 0, 2).reshape(N, W * k)
             ci = torch.where(ci < 0, torch.full_like(ci, 0x7FFFFFFF), ci).to(torch.int32).contiguous()
             call("topk_merge", cs, ci, N, W * k, k, out_s, out_i, st)
     return counts, out_s, out_i

@@ -9,6 +9,7 @@
 #include "../../deepcoro_clip_b200/csrc/l2norm_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/scalars_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/siglip_kernels.cuh"
+#include "../../deepcoro_clip_b200/csrc/retrieval_epi.cuh"
 
 using namespace b2;
 using bf16 = __nv_bfloat16;
@@ -217,5 +218,147 @@ extern "C" int b200clip_siglip_pos(const void* V, int ldv, const void* T, int ld
   PosParams p{(const bf16*)V, ldv, (const bf16*)T, ldt, K, Dp, D, hi_off, B, Tn, cap, col, y, w, cnt, ysum, dyn, positive_weight,
               negative_weight, c, gnorm > 0.f ? gnorm : 1.f, hp ? 1 : 0, use_pw, auto_balance, dV, lddv, dT, lddt, acc};
   emul::launch((B + 7) / 8, 256, [&] { siglip_pos_kernel(p); });
+  return 0;
+}
+
+// ---------------- streaming retrieval: shipped epilogue policies / selection kernels + a modelled GEMM ----------------
+// The tile engine is replaced by a driver that follows its epilogue contract (tile_engine.cuh: TileSeq item mode, TeCtx,
+// begin_outer / chunk x 4 / end_tile / end_outer per thread, zero-filled padding) and computes each similarity from the bf16
+// operands with an fp32 accumulator (exact for the exact-grid evaluation embeddings, as on the tensor core).
+static const int kSmsR = 148;
+static inline float sim_at(const void* V, int ldv, const void* T, int ldt, int K, int i, int j) {
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s = fmaf(bf(V, (long long)i * ldv + k), bf(T, (long long)j * ldt + k), s);
+  return s;
+}
+template <class Epi>
+static void run_epi(const std::vector<float>& S, int Ma, int Nb, int segs, const typename Epi::Params& p) {
+  const int m_tiles = (Ma + 127) / 128, n_blocks = (Nb + 255) / 256;
+  for (int m_tile = 0; m_tile < m_tiles; ++m_tile)
+    for (int seg = 0; seg < segs; ++seg) {
+      const int i0 = (int)((long long)n_blocks * seg / segs), i1 = (int)((long long)n_blocks * (seg + 1) / segs);
+      if (i0 >= i1) continue;
+      for (int wg = 0; wg < 2; ++wg)
+        for (int q = 0; q < 4; ++q)
+          for (int lane = 0; lane < 32; ++lane) {
+            typename Epi::State st;
+            Epi::init(st, p);
+            TeCtx ctx;
+            ctx.wg = wg; ctx.Nb = Nb; ctx.seg = seg; ctx.m_tile = m_tile;
+            ctx.row = m_tile * 128 + q * 32 + lane;
+            ctx.row_ok = ctx.row < Ma;
+            for (int nb = i0; nb < i1; ++nb) {
+              ctx.n_block = nb;
+              ctx.col0 = nb * 256 + wg * 128;
+              ctx.full = (m_tile * 128 + 128 <= Ma) && (nb * 256 + 256 <= Nb);
+              if (nb == i0) Epi::begin_outer(st, p, m_tile, ctx);
+              for (int c = 0; c < 4; ++c) {
+                uint32_t acc[32];
+                for (int e = 0; e < 32; ++e) {
+                  const int col = ctx.col0 + c * 32 + e;
+                  acc[e] = __float_as_uint((ctx.row_ok && col < Nb) ? S[(size_t)ctx.row * Nb + col] : 0.f);
+                }
+                Epi::chunk(st, p, ctx, c, acc);
+              }
+              Epi::end_tile(st, p, ctx);
+            }
+            Epi::end_outer(st, p, m_tile, ctx);
+          }
+    }
+}
+static std::vector<float> sim_matrix(const void* V, const void* T, int N, int M, int K, int ldv, int ldt) {
+  std::vector<float> S((size_t)N * M);
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < M; ++j) S[(size_t)i * M + j] = sim_at(V, ldv, T, ldt, K, i, j);
+  return S;
+}
+
+extern "C" int b200clip_retrieval_segments(int Ma, int Nb) {
+  const int m_tiles = (Ma + 127) / 128, n_blocks = (Nb + 255) / 256;
+  int segs = 1;
+  if (m_tiles < 4 * kSmsR) {
+    segs = (4 * kSmsR + m_tiles - 1) / m_tiles;
+    if (segs > n_blocks) segs = n_blocks;
+    if (segs > 64) segs = 64;
+    if (segs < 1) segs = 1;
+  }
+  return segs;
+}
+extern "C" int b200clip_retrieval_sweep(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, const float* sgt,
+                                        const long long* gt, int col_offset, int* counts, int k, int segs, float* part_score,
+                                        int* part_idx, void*) {
+  if (Nv <= 0 || Mt <= 0 || k < 0 || k > 64 || segs < 1) return -22;
+  if (k > 0 && (!part_score || !part_idx)) return -22;
+  if (sgt && (!gt || !counts)) return -22;
+  const std::vector<float> S = sim_matrix(V, T, Nv, Mt, Kp, ldv, ldt);
+  RetrParams p{sgt, gt, col_offset, counts, part_score, part_idx, 2 * segs, k};
+  if (k == 0) run_epi<RetrEpi<0>>(S, Nv, Mt, segs, p);
+  else if (k <= 16) run_epi<RetrEpi<16>>(S, Nv, Mt, segs, p);
+  else run_epi<RetrEpi<64>>(S, Nv, Mt, segs, p);
+  return 0;
+}
+extern "C" int b200clip_retrieval_colmax(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, int segs,
+                                         float* part_max, void*) {
+  if (Nv <= 0 || Mt <= 0 || segs < 1 || !part_max) return -22;
+  ColMaxParams p{part_max, 2 * segs};
+  run_epi<ColMaxEpi>(sim_matrix(V, T, Nv, Mt, Kp, ldv, ldt), Nv, Mt, segs, p);
+  return 0;
+}
+extern "C" int b200clip_retrieval_collect(const void* V, const void* T, int Nv, int Mt, int Kp, int ldv, int ldt, const float* thr,
+                                          int col_offset, int segs, int* cnt, float* buf_s, int* buf_i, int cap, int* overflow,
+                                          void*) {
+  if (Nv <= 0 || Mt <= 0 || segs < 1 || cap < 1 || !thr || !cnt || !buf_s || !buf_i || !overflow) return -22;
+  CollectParams p{thr, col_offset, cnt, buf_s, buf_i, cap, overflow};
+  run_epi<CollectEpi>(sim_matrix(V, T, Nv, Mt, Kp, ldv, ldt), Nv, Mt, segs, p);
+  return 0;
+}
+extern "C" int b200clip_kth_largest(const float* vals, int rows, int cand, int k, float* thr, void*) {
+  if (rows <= 0 || cand <= 0 || k <= 0 || !vals || !thr) return -22;
+  emul::launch((rows + 7) / 8, 256, [&] { kth_largest_kernel(vals, rows, cand, k, thr); });
+  return 0;
+}
+extern "C" int b200clip_topk_merge(const float* ps, const int* pi, int rows, int cand, int k, float* out_s, long long* out_i,
+                                   void*) {
+  if (rows <= 0 || cand <= 0 || k <= 0) return -22;
+  emul::launch((rows + 7) / 8, 256, [&] { topk_merge_kernel(ps, pi, rows, cand, k, out_s, out_i); });
+  return 0;
+}
+extern "C" int b200clip_recall_hits(const int* counts, int rows, const int* kvals, int nk, unsigned long long* hits, void*) {
+  if (rows <= 0 || nk <= 0) return -22;
+  emul::launch((rows + 255) / 256, 256, [&] { recall_hits_kernel(counts, rows, kvals, nk, hits); });
+  return 0;
+}
+extern "C" int b200clip_mrr_from_counts(const int* counts, int rows, int n_bins, int* hist, double* out, void*) {
+  if (rows <= 0 || n_bins <= 0) return -22;
+  emul::launch((rows + 255) / 256, 256, [&] { rank_hist_kernel(counts, rows, n_bins, hist); });
+  emul::launch(1, 1024, [&] { rank_hist_mrr_kernel(hist, n_bins, out); });
+  return 0;
+}
+// operand helpers of l2norm.cu (shipped kernels) and the tensor-core ground-truth dot (model: same fp32 dot as sim_at)
+extern "C" int b200clip_inexact_bf16(const void* x, int dtype, long long ld, int rows, int dim, int* flag, void*) {
+  if (rows <= 0 || dim <= 0) return -22;
+  long long blocks = ((long long)rows * dim + 255) / 256;
+  if (blocks > 32) blocks = 32;
+  if (dtype == 0) emul::launch((unsigned)blocks, 256, [&] { inexact_bf16_kernel<float>((const float*)x, ld, rows, dim, flag); });
+  else if (dtype == 2) emul::launch((unsigned)blocks, 256, [&] { inexact_bf16_kernel<__half>((const __half*)x, ld, rows, dim, flag); });
+  else return -22;
+  return 0;
+}
+extern "C" int b200clip_gather_rows_bf16(const void* src, int lds, const long long* idx, int rows, int src_rows, int K, void* dst,
+                                         int ldd, void*) {
+  if (rows <= 0 || K <= 0 || (K & 7) || (lds & 7) || (ldd & 7) || !src || !idx || !dst) return -22;
+  emul::launch((rows + 7) / 8, 256, [&] {
+    gather_rows_bf16_kernel((const uint4*)src, lds / 8, idx, rows, src_rows, K / 8, (uint4*)dst, ldd / 8);
+  });
+  return 0;
+}
+extern "C" int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const long long* idx, int rows, int b_rows,
+                                    int K, float* out, void*) {
+  if (rows <= 0 || K <= 0 || (K & 1) || !a || !b || !out) return -22;
+  emul::launch((rows + 7) / 8, 256, [&] { rowdot_bf16_kernel((const bf16*)a, lda, (const bf16*)b, ldb, idx, rows, b_rows, K, out); });
+  return 0;
+}
+extern "C" int b200clip_rowdot_tc(const void* a, int lda, const void* b, int ldb, int rows, int Kp, float* out, void*) {
+  for (int i = 0; i < rows; ++i) out[i] = sim_at(a, lda, b, ldb, Kp, i, i);
   return 0;
 }

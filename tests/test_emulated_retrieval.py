@@ -1,0 +1,105 @@
+"""CPU: the streaming retrieval API (deepcoro_clip_b200.retrieval_metrics_streaming: operand packing, precision probe,
+ground-truth similarity, sweep, rank counts -> recall@k / MRR, top-k lists and their merges, text sharding) executed end to
+end on CPU — single process against the reference goldens / the oracle, and on TWO RANKS over gloo with the text database
+sharded by rows.
+
+Underneath (tests/emul/loss_emul.cpp): the SHIPPED epilogue policies (rank counting, register top-k lists, the opt-in
+two-sweep threshold / collect policies) and selection kernels (topk_merge, kth_largest, recall_hits, the rank histogram)
+and the l2norm / gather / row-dot helpers under the host emulation; only the tcgen05 GEMM that feeds the policies is
+modelled (fp32 dot products of the bf16 operands, exact on the exact-grid embeddings)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import retrieval_oracle as ro
+from tests.conftest import GOLDEN
+from tests.test_emulated_losses import build_emul
+
+
+def patch_retrieval(so, setattr_=setattr):
+    import ctypes
+    from deepcoro_clip_b200 import _lib, ops, retrieval_metrics_streaming as rms
+    emul = ctypes.CDLL(str(so))
+    for name, (ret, types) in _lib._prototypes().items():
+        fn = getattr(emul, name, None)
+        if fn is not None:
+            fn.restype, fn.argtypes = ret, types
+
+    def call(name, *args):
+        rc = getattr(emul, "b200clip_" + name)(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args])
+        if rc != 0:
+            raise _lib.B200ClipError(f"emulated b200clip_{name} failed with {rc}")
+
+    setattr_(ops, "require_cuda", lambda *t: torch.device("cpu"))
+    for mod in (ops, rms):
+        setattr_(mod, "call", call)
+        setattr_(mod, "stream_ptr", lambda dev=None: 0)
+    setattr_(_lib, "lib", lambda: emul)
+    return rms
+
+
+def test_streaming_metrics_single_process(monkeypatch):
+    rms = patch_retrieval(build_emul(), monkeypatch.setattr)
+    g = np.load(GOLDEN / "retrieval_gauss_300x200.npz")
+    m = rms.compute_metrics_streaming(torch.tensor(g["video"]), torch.tensor(g["text"]), torch.tensor(g["gt"]),
+                                      k_values=[1, 5, 10, 50], video_chunk_size=128, text_chunk_size=64, device="cpu")
+    ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
+    for k in ("Recall@1", "Recall@5", "Recall@10", "Recall@50"):
+        assert m[k] == ref[k], (k, m[k], ref[k])
+    assert abs(m["MRR_V2T"] - ref["MRR_V2T"]) < 1e-9 and abs(m["alignment_score"] - ref["alignment_score"]) < 1e-6
+    assert set(m) == set(ref)
+    eye = torch.eye(5)
+    m = rms.compute_metrics_streaming(eye, eye, torch.arange(5), k_values=[1, 3, 5])
+    assert m["Recall@1"] == 100.0 and m["MRR_V2T"] == 1.0
+    m2 = rms.compute_metrics_streaming(eye, torch.flip(eye, dims=[1]), torch.arange(5), k_values=[1])
+    assert m2["Recall@1"] == 20.0
+
+
+@pytest.mark.parametrize("topk2", ["0", "1"])
+def test_exact_grid_topk_and_recall_bit_exact(monkeypatch, topk2):
+    monkeypatch.setenv("B200CLIP_TOPK2", topk2)
+    rms = patch_retrieval(build_emul(), monkeypatch.setattr)
+    g = np.load(GOLDEN / "retrieval_grid_257x300.npz")
+    v, t = torch.tensor(g["video"]), torch.tensor(g["text"])
+    r = rms.compute_recall_at_k_streaming(v, t, torch.tensor(g["gt"]), k_values=[1, 5, 10], device="cpu")
+    ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
+    assert r == {k: ref[k] for k in r}
+    s, i = rms.streaming_topk(v, t, 10)                       # precision "auto": the probe finds the grid exact in bf16
+    ov, oi = ro.topk_lowest_index(ro.similarity(g["video"], g["text"]), 10)
+    assert (i.numpy() == oi).all() and (s.numpy() == ov).all()
+
+
+def _rank(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rms = patch_retrieval(build_emul())
+        g = np.load(GOLDEN / "retrieval_grid_257x300.npz")
+        v, t = torch.tensor(g["video"]), torch.tensor(g["text"])
+        r = rms.compute_recall_at_k_streaming(v, t, torch.tensor(g["gt"]), k_values=[1, 5, 10], device="cpu")
+        s, i = rms.streaming_topk(v, t, 10)
+        out[rank] = (r, s.numpy(), i.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_text_shards_two_ranks_gloo():
+    """every rank sweeps its row shard of the text database; rank counts are all-reduced, the per-shard top-k
+    lists all-gathered and merged by (score desc, index asc): identical to the single-process result on every rank."""
+    build_emul()
+    world = 2
+    port = 32500 + (os.getpid() % 1500)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rank, args=(world, port, out), nprocs=world, join=True)
+    g = np.load(GOLDEN / "retrieval_grid_257x300.npz")
+    ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
+    ov, oi = ro.topk_lowest_index(ro.similarity(g["video"], g["text"]), 10)
+    for r in range(world):
+        rec, s, i = out[r]
+        assert rec == {k: ref[k] for k in rec}
+        assert (i == oi).all() and (s == ov).all()
