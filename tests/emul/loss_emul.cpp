@@ -10,6 +10,7 @@
 #include "../../deepcoro_clip_b200/csrc/scalars_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/siglip_kernels.cuh"
 #include "../../deepcoro_clip_b200/csrc/retrieval_epi.cuh"
+#include "../../deepcoro_clip_b200/csrc/alignment_diag.cuh"
 
 using namespace b2;
 using bf16 = __nv_bfloat16;
@@ -360,5 +361,11 @@ extern "C" int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int l
 }
 extern "C" int b200clip_rowdot_tc(const void* a, int lda, const void* b, int ldb, int rows, int Kp, float* out, void*) {
   for (int i = 0; i < rows; ++i) out[i] = sim_at(a, lda, b, ldb, Kp, i, i);
+  return 0;
+}
+
+extern "C" int b200clip_alignment_diag(const float* sums, int n, const float* dyn, int gated, float* out, void*) {
+  if (!sums || !dyn || !out || n <= 0) return -22;
+  emul::launch(1, 1024, [&] { alignment_diag_kernel(sums, n, dyn, gated, out); });
   return 0;
 }

@@ -27,7 +27,8 @@ CSRC = EMUL.parents[1] / "deepcoro_clip_b200" / "csrc"
 def build_emul():
     so = EMUL / "liblossemul.so"
     srcs = [EMUL / "loss_emul.cpp", EMUL / "pool_mma_prims_emul.h", EMUL / "cuda_emul.h", CSRC / "l2norm_kernels.cuh",
-            CSRC / "scalars_kernels.cuh", CSRC / "siglip_kernels.cuh"]
+            CSRC / "scalars_kernels.cuh", CSRC / "siglip_kernels.cuh",
+            CSRC / "retrieval_epi.cuh", CSRC / "alignment_diag.cuh"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", str(so), str(srcs[0])], check=True)
     return so
@@ -216,3 +217,18 @@ def test_siglip_loss_host_path_two_ranks_gloo(name):
         loss, dv, dt, dlt, db = out[r]
         _check_siglip(g, loss, dv, dt, dlt, db, rows=slice(r * B, (r + 1) * B))
     assert out[0][0] == out[1][0]
+
+
+@pytest.mark.parametrize("name", ["align_b64_d512", "align_siglip_b130_d96", "align_b300_d200"])
+def test_alignment_diagnostics_end_to_end(name, monkeypatch):
+    """deepcoro_clip_b200.alignment_diagnostics (logging half) through its real host code: shipped l2norm /
+    dyn_prep / alignment scalar kernels under the emulation + the contract model of the forward tile kernel, against the
+    transcribed runner lines (runners/video_constrative_learning_runner.py:1323-1335)."""
+    patch_package(build_emul(), monkeypatch.setattr)
+    from deepcoro_clip_b200.diagnostics import alignment_diagnostics
+    g = np.load(GOLDEN / f"{name}.npz")
+    r = alignment_diagnostics(torch.tensor(g["video"]), torch.tensor(g["text"]), torch.tensor(g["log_temp"].astype(np.float32)),
+                              use_siglip=bool(g["use_siglip"]))
+    for key, ref in (("alignment_cosine", "cosine_f64"), ("alignment_logprob", "logprob_f64"), ("alignment_prob", "prob_f64")):
+        want = float(g[ref])
+        assert abs(r[key].item() - want) <= 2e-5 * max(1.0, abs(want)), (key, r[key].item(), want)
