@@ -1,0 +1,180 @@
+"""CPU: edge cases of the host code around the kernels, run end to end on the emulated library (see
+tests/test_emulated_losses.py / test_emulated_retrieval.py for what is shipped device code and what is modelled) against the
+numpy oracle: input dtypes and layouts, partial gradient requests, log_temp forms, ragged / degenerate shapes, the
+positive-list overflow poison, tiny and clamped retrieval problems."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import contrastive_oracle as co
+from oracle import retrieval_oracle as ro
+from tests.test_emulated_losses import _rel, build_emul, patch_package
+from tests.test_emulated_retrieval import patch_retrieval
+
+
+@pytest.fixture()
+def loss_mod(monkeypatch):
+    return patch_package(build_emul(), monkeypatch.setattr)
+
+
+def _data(B, D, seed, T=None):
+    rng = np.random.default_rng(seed)
+    t = rng.standard_normal((T or B, D)).astype(np.float32)
+    v = (0.5 * t[:B] if T is None else 0.5 * t[rng.integers(0, T, size=B)]) + rng.standard_normal((B, D)).astype(np.float32)
+    return v.astype(np.float32), t
+
+
+def test_clip_loss_input_forms(loss_mod):
+    v, t = _data(40, 96, 1)
+    lt = math.log(0.07)
+    o = co.clip_loss(v, t, lt)
+    # non-contiguous fp32 views, 0-d log_temp, python-float log_temp, log_temp without grad, one-sided gradient requests
+    big = torch.zeros(40, 200)
+    big[:, ::2][:, :96] = torch.tensor(v)
+    vv = big[:, ::2][:, :96]
+    assert not vv.is_contiguous()
+    vv = vv.detach().requires_grad_(True)
+    tt = torch.tensor(t, requires_grad=True)
+    l0 = torch.tensor(lt, requires_grad=True)                        # 0-d parameter
+    loss = loss_mod.CLIPLoss()(video_features=vv, text_features=tt, log_temp=l0)
+    loss.backward()
+    assert abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"])
+    assert _rel(vv.grad.numpy(), o["dvideo"]) <= 2e-3 and _rel(tt.grad.numpy(), o["dtext"]) <= 2e-3
+    assert l0.grad.shape == () and abs(l0.grad.item() - o["dlog_temp"]) <= 2e-3 * abs(o["dlog_temp"])
+    # text frozen, temperature a plain float
+    v2 = torch.tensor(v, requires_grad=True)
+    loss = loss_mod.clip_loss(v2, torch.tensor(t), lt)
+    loss.backward()
+    assert _rel(v2.grad.numpy(), o["dvideo"]) <= 2e-3
+    # video frozen
+    t2 = torch.tensor(t, requires_grad=True)
+    loss_mod.clip_loss(torch.tensor(v), t2, torch.tensor([lt])).backward()
+    assert _rel(t2.grad.numpy(), o["dtext"]) <= 2e-3
+    # upstream scale
+    v3 = torch.tensor(v, requires_grad=True)
+    (3.0 * loss_mod.clip_loss(v3, torch.tensor(t), lt)).backward()
+    assert _rel(v3.grad.numpy(), 3.0 * o["dvideo"]) <= 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_clip_loss_16_bit_features(loss_mod, dtype):
+    v, t = _data(33, 64, 2)
+    v16, t16 = torch.tensor(v).to(dtype), torch.tensor(t).to(dtype)
+    o = co.clip_loss(v16.float().numpy(), t16.float().numpy(), math.log(0.1))       # the reference casts .float() first
+    vv, tt = v16.clone().requires_grad_(True), t16.clone().requires_grad_(True)
+    loss = loss_mod.CLIPLoss()(video_features=vv, text_features=tt, log_temp=torch.tensor([math.log(0.1)]))
+    loss.backward()
+    assert abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"])
+    assert vv.grad.dtype == dtype and _rel(vv.grad.float().numpy(), o["dvideo"]) <= 1e-2      # gradient rounded to 16 bits
+
+
+def test_clip_loss_shape_errors_and_tiny_batches(loss_mod):
+    with pytest.raises(ValueError):
+        loss_mod.CLIPLoss()(video_features=torch.zeros(4, 8), text_features=torch.zeros(5, 8), log_temp=torch.zeros(1))
+    for B in (1, 2, 3):
+        v, t = _data(B, 64, 10 + B)
+        o = co.clip_loss(v, t, math.log(0.2))
+        vv = torch.tensor(v, requires_grad=True)
+        loss = loss_mod.clip_loss(vv, torch.tensor(t), math.log(0.2))
+        loss.backward()
+        assert abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"]) + 1e-6, B     # B = 1: the loss is exactly 0
+        assert np.abs(vv.grad.numpy() - o["dvideo"]).max() <= 2e-3 * np.abs(o["dvideo"]).max() + 1e-6, B   # B = 1: exactly 0
+    # tau = 0.01 (the usual floor of a learnable CLIP temperature; logits up to +-100) is inside the fixed-shift range
+    v, t = _data(16, 64, 20)
+    lt = torch.tensor([math.log(0.01)], requires_grad=True)
+    loss = loss_mod.CLIPLoss()(video_features=torch.tensor(v), text_features=torch.tensor(t), log_temp=lt)
+    loss.backward()
+    o = co.clip_loss(v, t, math.log(0.01))
+    assert abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"])
+    assert abs(lt.grad.item() - o["dlog_temp"]) <= 2e-3 * abs(o["dlog_temp"])
+    # an active temperature clamp: the loss is evaluated at the floor and the temperature gradient is zero (:153)
+    lt = torch.tensor([math.log(0.02)], requires_grad=True)
+    loss = loss_mod.clip_loss(torch.tensor(v), torch.tensor(t), lt, clamp_min=0.05)
+    loss.backward()
+    o = co.clip_loss(v, t, math.log(0.02), clamp_min=0.05)
+    assert abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"]) and lt.grad.item() == 0.0
+
+
+def test_known_gap_fixed_shift_range_at_the_reference_clamp_floor(loss_mod):
+    """the forward uses ONE exponent shift tied to the bound S <= 1, not a per-row maximum. With the reference's
+    clamp floor tau = 1e-4 the logits span +-10^4 and every term of a row whose best cosine is below ~0.98 underflows fp32:
+    the loss is non-finite where the reference returns a finite value (golden clip_clamp_b8_d64). The failure is loud
+    (inf / NaN, never a wrong finite number); this test pins that, and the safe range, until the stable two-exponential
+    epilogue lands."""
+    from tests.conftest import GOLDEN
+    g = np.load(GOLDEN / "clip_clamp_b8_d64.npz")
+    loss = loss_mod.CLIPLoss()(video_features=torch.tensor(g["video"], dtype=torch.float32),
+                               text_features=torch.tensor(g["text"], dtype=torch.float32),
+                               log_temp=torch.tensor(g["log_temp"].astype(np.float32)))
+    assert not math.isfinite(loss.item())
+    assert math.isfinite(float(g["f32_loss"]))
+    # inside the range (1 - max cosine of the row) * log2(e) / tau <= ~226 bits the same inputs (uncorrelated pairs, best
+    # cosine of some rows only 0.05) are accurate to 1e-6: tau >= 0.006 here, far below every shipped config (0.0588 ... 0.1)
+    for tau in (0.006, 0.02):
+        o = co.clip_loss(g["video"], g["text"], math.log(tau))
+        ours = loss_mod.clip_loss(torch.tensor(g["video"], dtype=torch.float32), torch.tensor(g["text"], dtype=torch.float32),
+                                  math.log(tau))
+        assert abs(ours.item() - o["loss"]) <= 1e-5 * abs(o["loss"]), tau
+
+
+def test_siglip_ragged_rows_without_positives_and_frozen_bias(loss_mod):
+    B, T, D = 21, 50, 64
+    v, t = _data(B, D, 3, T=T)
+    rng = np.random.default_rng(4)
+    pm = (rng.random((B, T)) < 0.06).astype(np.float32)
+    pm[5] = 0.0                                                       # a video without any positive text
+    pw = (pm * rng.choice([1.0, 1.5, 2.5, 3.0], size=(B, T))).astype(np.float32)
+    lt = math.log(0.09)
+    o = co.siglip_loss(v, t, lt, bias=-6.0, pos_mask=pm, pos_weights=pw)
+    mod = loss_mod.SigLIPLoss(bias_init=-6.0, learnable_bias=False)
+    assert not isinstance(mod.bias, torch.nn.Parameter)
+    vv, tt = torch.tensor(v, requires_grad=True), torch.tensor(t, requires_grad=True)
+    l1 = torch.tensor([lt], requires_grad=True)
+    loss = mod(video_features=vv, text_features=tt, log_temp=l1, pos_mask=torch.tensor(pm), pos_weights=torch.tensor(pw))
+    loss.backward()
+    assert abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"])
+    assert _rel(vv.grad.numpy(), o["dvideo"]) <= 2e-3 and _rel(tt.grad.numpy(), o["dtext"]) <= 2e-3
+    assert abs(l1.grad.item() - o["dlog_temp"]) <= 2e-3 * max(abs(o["dlog_temp"]), 1e-4)
+    # boolean / integer masks are accepted like the reference's .float() cast
+    loss_b = mod(video_features=torch.tensor(v), text_features=torch.tensor(t), log_temp=lt,
+                 pos_mask=torch.tensor(pm).bool(), pos_weights=torch.tensor(pw))
+    assert abs(loss_b.item() - o["loss"]) <= 1e-5 * abs(o["loss"])
+    with pytest.raises(ValueError):
+        mod(video_features=torch.tensor(v), text_features=torch.tensor(t), log_temp=lt, pos_mask=torch.zeros(B, T + 1))
+
+
+def test_siglip_positive_list_overflow_poisons_the_loss(loss_mod):
+    v, t = _data(8, 64, 5, T=40)
+    pm = np.zeros((8, 40), np.float32)
+    pm[2, :9] = 1.0                                                   # 9 positives in a row, capacity 4
+    mod = loss_mod.SigLIPLoss(max_positives_per_row=4)
+    loss = mod(video_features=torch.tensor(v), text_features=torch.tensor(t), log_temp=math.log(0.1), pos_mask=torch.tensor(pm))
+    assert math.isnan(loss.item())                                    # never silently drops positives
+    ok = loss_mod.SigLIPLoss(max_positives_per_row=16)(video_features=torch.tensor(v), text_features=torch.tensor(t),
+                                                       log_temp=math.log(0.1), pos_mask=torch.tensor(pm))
+    o = co.siglip_loss(v, t, math.log(0.1), bias=-10.0, pos_mask=pm)
+    assert abs(ok.item() - o["loss"]) <= 1e-5 * abs(o["loss"])
+
+
+def test_retrieval_degenerate_shapes(monkeypatch):
+    rms = patch_retrieval(build_emul(), monkeypatch.setattr)
+    v = torch.tensor(ro.exact_grid_embeddings(7, 16, 1))
+    t = torch.tensor(ro.exact_grid_embeddings(3, 16, 2))
+    gt = torch.tensor([0, 1, 2, 0, 1, 2, 0])
+    sim = ro.similarity(v.numpy(), t.numpy())
+    # k larger than the database: the reference's best_indices has min(k, M) columns, larger k report 0 (:89-93)
+    r = rms.compute_recall_at_k_streaming(v, t, gt, k_values=[1, 2, 3, 5], device="cpu")
+    ranks = ro.gt_ranks(sim, gt.numpy())
+    assert r["Recall@5"] == 0.0
+    for k in (1, 2, 3):
+        assert r[f"Recall@{k}"] == float((ranks <= k).mean() * 100)
+    s, i = rms.streaming_topk(v, t, 10)                               # clamped to the 3 texts
+    ov, oi = ro.topk_lowest_index(sim, 3)
+    assert i.shape == (7, 3) and (i.numpy() == oi).all() and (s.numpy() == ov).all()
+    # one video, one text
+    m = rms.compute_metrics_streaming(v[:1], t[:1], torch.tensor([0]), k_values=[1])
+    assert m["Recall@1"] == 100.0 and m["MRR_V2T"] == 1.0
+    with pytest.raises(ValueError):
+        rms.streaming_topk(v, t, 0)
