@@ -232,3 +232,47 @@ def test_alignment_diagnostics_end_to_end(name, monkeypatch):
     for key, ref in (("alignment_cosine", "cosine_f64"), ("alignment_logprob", "logprob_f64"), ("alignment_prob", "prob_f64")):
         want = float(g[ref])
         assert abs(r[key].item() - want) <= 2e-5 * max(1.0, abs(want)), (key, r[key].item(), want)
+
+
+def _legacy_rank(rank, world, port, cls, name, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        loss_mod = patch_package(build_emul())
+        g = np.load(GOLDEN / f"{name}.npz")
+        B = g["video"].shape[0] // world
+        v = torch.tensor(g["video"][rank * B:(rank + 1) * B], dtype=torch.float32, requires_grad=True)
+        t = torch.tensor(g["text"][rank * B:(rank + 1) * B], dtype=torch.float32, requires_grad=True)
+        lt = torch.tensor(g["log_temp"].astype(np.float32).reshape(1), requires_grad=True)
+        mod = loss_mod.InfoNCELoss(use_ddp=True, loss_type=cls)               # the dispatcher picks the *DDP class
+        loss = mod(v, t, lt)
+        loss.backward()
+        out[rank] = (loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cls,name", [("contrastive", "contrastive_legacy_b32_d128"), ("siglip", "gated_siglip_legacy_b40_d128")])
+def test_legacy_ddp_losses_two_ranks_gloo(cls, name):
+    """utils/loss/losses.py:104-158, 213-276 through InfoNCELoss(use_ddp=True): ContrastiveLossDDP (no tau clamp) and the
+    gated SiglipLossDDP, which rounds the features to fp16 before the gather (:243-244) — compared with the oracle on the
+    fp16-rounded inputs."""
+    from oracle import contrastive_oracle as co
+    build_emul()
+    world = 2
+    port = 33500 + (os.getpid() % 1500)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_legacy_rank, args=(world, port, cls, name, out), nprocs=world, join=True)
+    g = np.load(GOLDEN / f"{name}.npz")
+    v, t = g["video"].astype(np.float32), g["text"].astype(np.float32)
+    if cls == "siglip":
+        v, t = v.astype(np.float16).astype(np.float32), t.astype(np.float16).astype(np.float32)
+    o = co.clip_loss(v, t, float(g["log_temp"].reshape(-1)[0]), clamp_min=None, gated=(cls == "siglip"))
+    B = v.shape[0] // world
+    for r in range(world):
+        loss, dv, dt, dlt = out[r]
+        assert abs(loss - o["loss"]) <= 1e-5 * abs(o["loss"]), (r, loss, o["loss"])
+        gtol = 2e-3 if cls == "contrastive" else 4e-3            # fp16 features: the gradient comes back rounded to fp16
+        assert _rel(dv, o["dvideo"][r * B:(r + 1) * B]) <= gtol and _rel(dt, o["dtext"][r * B:(r + 1) * B]) <= gtol
+        assert abs(dlt - o["dlog_temp"]) <= 2e-3 * max(abs(o["dlog_temp"]), 1e-3)
