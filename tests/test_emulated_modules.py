@@ -232,3 +232,43 @@ def test_dense_metrics_on_emulated_kernels(on_emulated_kernels, name):
         assert all(a[k] == o[k] for k in o)
         assert a["MedianRank_V2T"] == dmo.median_rank(qo, gq)
         assert abs(a["MAP"] - dmo.mean_ap(qo, gq)) <= 1e-6
+
+
+@pytest.mark.parametrize("dtype,D,N,fused", [(torch.float32, 128, 70, "0"), (torch.bfloat16, 256, 90, "0"), (torch.bfloat16, 256, 90, "1")])
+def test_attention_pool_training_dropout_on_emulated_kernels(on_emulated_kernels, monkeypatch, dtype, D, N, fused):
+    """Training-mode attention dropout (the reference's default attention_pool_dropout is 0.1, so this is the path a training
+    step takes): forward and backward equal a float64 autograd replica of nn.MultiheadAttention's math driven by the SAME
+    counter-based mask — CUDA-core fp32 kernels, the MMA kernels and the opt-in fused query gradient."""
+    import math
+    from deepcoro_clip_b200 import attention_pool as ap
+    from tests.test_gpu_tokens import _keep_mask
+    monkeypatch.setenv("B200CLIP_POOL_FUSED_DQ", fused)
+    B, H, p = 2, 8, 0.25
+    torch.manual_seed(7)
+    mod = ap.AttentionPool(D, H, dropout=p).train()
+    x = torch.randn(B, N, D).to(dtype).requires_grad_(True)
+    torch.manual_seed(123)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # what forward() will draw
+    torch.manual_seed(123)
+    out = mod(x)
+    gout = torch.randn(B, D)
+    out.float().backward(gout)
+    keep = _keep_mask(seed, B, H, N, p, "cpu")
+    xd = x.detach().double().requires_grad_(True)
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mod.named_parameters()}
+    Wd, bd = P["attn.in_proj_weight"], P["attn.in_proj_bias"]
+    Dh = D // H
+    q0 = (P["query"].view(1, D) @ Wd[:D].T + bd[:D]).view(H, Dh)
+    K = (xd @ Wd[D:2 * D].T + bd[D:2 * D]).view(B, N, H, Dh)
+    V = (xd @ Wd[2 * D:].T + bd[2 * D:]).view(B, N, H, Dh)
+    a = torch.softmax(torch.einsum("hk,bnhk->bhn", q0, K) / math.sqrt(Dh), dim=-1) * keep.double() / (1 - p)
+    o = torch.einsum("bhn,bnhk->bhk", a, V).reshape(B, D)
+    y = o @ P["attn.out_proj.weight"].T + P["attn.out_proj.bias"]
+    y = torch.nn.functional.layer_norm(y, (D,), P["norm.weight"], P["norm.bias"], mod.norm.eps)
+    y.backward(gout.double())
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert _rel(out.float().detach().numpy(), y.detach().numpy()) < tol
+    assert _rel(x.grad.float().numpy(), xd.grad.numpy()) < (5e-5 if dtype == torch.float32 else 1.5e-2)
+    for name, prm in mod.named_parameters():                  # parameter gradients incl. the query (dqt path) and biases
+        assert _rel(prm.grad.numpy(), P[name].grad.numpy()) < (1e-4 if dtype == torch.float32 else 2e-2), name
+    assert ("attnpool_bwd_dx_dq" in on_emulated_kernels) == (fused == "1")
