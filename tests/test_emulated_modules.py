@@ -272,3 +272,30 @@ def test_attention_pool_training_dropout_on_emulated_kernels(on_emulated_kernels
     for name, prm in mod.named_parameters():                  # parameter gradients incl. the query (dqt path) and biases
         assert _rel(prm.grad.numpy(), P[name].grad.numpy()) < (1e-4 if dtype == torch.float32 else 2e-2), name
     assert ("attnpool_bwd_dx_dq" in on_emulated_kernels) == (fused == "1")
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_cls_pool_bf16_matches_fp32_on_emulated_kernels(on_emulated_kernels, fused, monkeypatch):
+    """AttentionPoolWithCLS with 16-bit tokens (MMA kernels, lse output forward, dlse input backward — also through the
+    opt-in fused query gradient) against the same module on the fp32 CUDA-core kernels with the rounded tokens."""
+    from deepcoro_clip_b200.attention_pool import AttentionPoolWithCLS
+    monkeypatch.setenv("B200CLIP_POOL_FUSED_DQ", fused)
+    torch.manual_seed(11)
+    mod = AttentionPoolWithCLS(256, 8).eval()
+    x16 = torch.randn(2, 75, 256).bfloat16()
+    mask = torch.rand(2, 75) < 0.2
+    mask[:, 0] = False
+    go = torch.randn(2, 256)
+    res = []
+    for x in (x16.clone().requires_grad_(True), x16.float().requires_grad_(True)):
+        for p in mod.parameters():
+            p.grad = None
+        out = mod(x, mask)
+        (out.float() * go).sum().backward()
+        res.append((out.detach().float(), x.grad.float(), {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None}))
+    (o16, dx16, g16), (o32, dx32, g32) = res
+    assert _rel(o16, o32) < 1e-2 and _rel(dx16, dx32) < 1.5e-2
+    assert set(g16) == set(g32)
+    for n in g32:
+        assert _rel(g16[n], g32[n]) < 1e-2, n
+    assert ("attnpool_bwd_dx_dq" in on_emulated_kernels) == (fused == "1")
