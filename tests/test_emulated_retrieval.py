@@ -103,3 +103,39 @@ def test_text_shards_two_ranks_gloo():
         rec, s, i = out[r]
         assert rec == {k: ref[k] for k in rec}
         assert (i == oi).all() and (s == ov).all()
+
+
+def _store_rank(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        patch_retrieval(build_emul())
+        from deepcoro_clip_b200 import EmbeddingStore, epoch_end_retrieval_metrics
+        g = np.load(GOLDEN / "retrieval_gauss_300x200.npz")
+        # ragged validation shards: rank 0 holds 170 videos, rank 1 the other 130; every rank holds the whole text set once
+        lo, hi = (0, 170) if rank == 0 else (170, 300)
+        vs, ts = EmbeddingStore(64, capacity=32, device="cpu"), EmbeddingStore(64, capacity=16, device="cpu")
+        for a in range(lo, hi, 37):                                           # batches of uneven size, buffer growth
+            vs.append(torch.tensor(g["video"][a:min(a + 37, hi)]))
+        tlo, thi = (0, 120) if rank == 0 else (120, 200)
+        ts.append(torch.tensor(g["text"][tlo:thi]))
+        out[rank] = epoch_end_retrieval_metrics(vs, ts, torch.tensor(g["gt"][lo:hi]), k_values=(1, 5, 10, 50))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_epoch_end_embedding_stores_two_ranks_gloo():
+    """device-resident validation embeddings, the ragged two-collective gather and the streaming metrics on
+    the gathered result — identical dict on every rank, equal to the reference's golden metrics."""
+    build_emul()
+    world = 2
+    port = 34500 + (os.getpid() % 1500)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_store_rank, args=(world, port, out), nprocs=world, join=True)
+    g = np.load(GOLDEN / "retrieval_gauss_300x200.npz")
+    ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
+    assert out[0] == out[1]
+    for k in ("Recall@1", "Recall@5", "Recall@10", "Recall@50"):
+        assert out[0][k] == ref[k], (k, out[0][k], ref[k])
+    assert abs(out[0]["MRR_V2T"] - ref["MRR_V2T"]) < 1e-9 and abs(out[0]["alignment_score"] - ref["alignment_score"]) < 1e-6
