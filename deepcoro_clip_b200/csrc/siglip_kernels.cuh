@@ -5,6 +5,69 @@
 
 namespace b2 {
 
+// rowvec[i] = {1/Z_i, m_i = H_i - Q_i}; stats = {sum_i H_i, min_i H_i, max_i H_i} over the local rows. One CTA,
+// fixed reduction order (deterministic).
+__global__ void __launch_bounds__(1024)
+siglip_entropy_rows_kernel(const float* __restrict__ Z, const float* __restrict__ H, const float* __restrict__ Q, int B,
+                           float* __restrict__ rowvec, double* __restrict__ stats) {
+  double sum = 0.0;
+  float mn = 3.4e38f, mx = -3.4e38f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float h = H[i];
+    rowvec[2 * i] = 1.f / Z[i];
+    rowvec[2 * i + 1] = h - Q[i];
+    sum += (double)h;
+    mn = fminf(mn, h);
+    mx = fmaxf(mx, h);
+  }
+  __shared__ double ssum[32];
+  __shared__ float smn[32], smx[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ssum[threadIdx.x >> 5] = sum;
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      sum += ssum[w];
+      mn = fminf(mn, smn[w]);
+      mx = fmaxf(mx, smx[w]);
+    }
+    stats[0] = sum;
+    stats[1] = (double)mn;
+    stats[2] = (double)mx;
+  }
+}
+
+// stats_all [W][3] (one triple per rank) -> mean / min / max entropy over the B_global rows, the penalty and the gradient
+// coefficient: out = {mean, min, max, mean / ln T, deficit = relu(thr - mean), weight * deficit};
+// dyn[10] = deficit > 0 ? -weight / B_global : 0.
+__global__ void siglip_entropy_coef_kernel(const double* __restrict__ stats_all, int W, int Bg, int T, float weight,
+                                           float thr, float* __restrict__ dyn, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sum = 0.0, mn = 3.4e38, mx = -3.4e38;
+  for (int r = 0; r < W; ++r) {
+    sum += stats_all[3 * r];
+    mn = fmin(mn, stats_all[3 * r + 1]);
+    mx = fmax(mx, stats_all[3 * r + 2]);
+  }
+  const float mean = (float)(sum / (double)Bg);
+  const float deficit = fmaxf(thr - mean, 0.f);
+  out[0] = mean;
+  out[1] = (float)mn;
+  out[2] = (float)mx;
+  out[3] = mean / logf((float)T);
+  out[4] = deficit;
+  out[5] = weight * deficit;
+  dyn[10] = deficit > 0.f ? -weight / (float)Bg : 0.f;
+}
+
 __global__ void siglip_combine_kernel(const double* __restrict__ acc, double wn_c, double* __restrict__ red) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   red[0] = wn_c * acc[1] + acc[4];

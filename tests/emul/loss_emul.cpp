@@ -110,14 +110,17 @@ extern "C" int b200clip_logits_bwd(int mode, const void* X, const void* Y, int N
                                    const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
                                    const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd,
                                    double* scal, int, void*) {
-  if (mode != 0 && mode != 1 && mode != 2) return -38;     // CLIP / gated softmax and plain SigLIP (no entropy mode)
+  if (mode < 0 || mode > 3) return -38;
   (void)Dp;
   float lclamp = 30.f, yneg = 0.f;
   if (dyn) { scale2 = dyn[0]; shift2 = dyn[1]; inv_tau = dyn[2]; bias = dyn[5]; out_scale = dyn[2]; lclamp = dyn[8]; yneg = dyn[9]; }
   if (!(gnorm > 0.f)) gnorm = 1.f;
   const float ign = 1.f / gnorm, ydn = ydiag * gnorm;
-  if (mode == 2) {
+  if (mode == 2 || mode == 3) {
     // G = wneg_c (sigmoid(clamp(R)) - yneg) [|R| <= lc], R = S / tau + bias; scal: [0] sum G S, [1] sum softplus, [2] sum G
+    // mode 3 adds the entropy regulariser's gradient dyn[10] p_ij (h_ij - m_v) [|R| <= lc], p = exp(L - 30) / Z_v, with
+    // {1 / Z_v, m_v} per video: rowscale [Nx][2] when X holds the videos, colscale [Ny][2] when Y does
+    const float ent_coef = (mode == 3 && dyn) ? dyn[10] : 0.f;
     const float wn = wneg_c * gnorm;
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
     for (int i = 0; i < Nx; ++i)
@@ -128,7 +131,14 @@ extern "C" int b200clip_logits_bwd(int mode, const void* X, const void* Y, int N
         const float Lc = fminf(fmaxf(R, -lclamp), lclamp);
         const float ex = expf(-fabsf(Lc));
         const float sig = Lc >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
-        const float g = fabsf(R) <= lclamp ? wn * (sig - yneg) : 0.f;
+        float g = fabsf(R) <= lclamp ? wn * (sig - yneg) : 0.f;
+        if (mode == 3 && fabsf(R) <= lclamp) {
+          const float iz = colscale ? colscale[2 * j] : rowscale[2 * i];
+          const float mv = colscale ? colscale[2 * j + 1] : rowscale[2 * i + 1];
+          const float pij = expf(Lc - 30.f) * iz;
+          const float pe = pij + 1e-10f;
+          g = fmaf(ent_coef * gnorm, pij * (-logf(pe) - pij / pe - mv), g);
+        }
         t1 += (double)(fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + log1pf(ex)));
         t2 += (double)g;
         t0 += (double)g * (double)sdot;
@@ -367,5 +377,46 @@ extern "C" int b200clip_rowdot_tc(const void* a, int lda, const void* b, int ldb
 extern "C" int b200clip_alignment_diag(const float* sums, int n, const float* dyn, int gated, float* out, void*) {
   if (!sums || !dyn || !out || n <= 0) return -22;
   emul::launch(1, 1024, [&] { alignment_diag_kernel(sums, n, dyn, gated, out); });
+  return 0;
+}
+
+// ---------------- entropy regulariser (contrastive.py:19-68): models of the two row-statistics sweeps + shipped kernels ----------------
+extern "C" int b200clip_siglip_entropy_rowsum(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt,
+                                              const float* dyn, float* Z, void*) {
+  const float inv_tau = dyn[2], bias = dyn[5];
+  for (int i = 0; i < B; ++i)
+    for (int j = 0; j < Tn; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < Kp; ++k) s = fmaf(bf(V, (long long)i * ldv + k), bf(T, (long long)j * ldt + k), s);
+      Z[i] += expf(fminf(fmaxf(fmaf(s, inv_tau, bias), -30.f), 30.f) - 30.f);
+    }
+  return 0;
+}
+extern "C" int b200clip_siglip_entropy_stats(const void* V, const void* T, int B, int Tn, int Kp, int ldv, int ldt,
+                                             const float* dyn, const float* Z, float* H, float* Q, void*) {
+  const float inv_tau = dyn[2], bias = dyn[5];
+  for (int i = 0; i < B; ++i) {
+    const float iz = 1.f / Z[i];
+    for (int j = 0; j < Tn; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < Kp; ++k) s = fmaf(bf(V, (long long)i * ldv + k), bf(T, (long long)j * ldt + k), s);
+      const float pij = expf(fminf(fmaxf(fmaf(s, inv_tau, bias), -30.f), 30.f) - 30.f) * iz;
+      const float pe = pij + 1e-10f;
+      H[i] -= pij * logf(pe);
+      Q[i] += pij * (pij / pe);
+    }
+  }
+  return 0;
+}
+extern "C" int b200clip_siglip_entropy_rows(const float* Z, const float* H, const float* Q, int B, float* rowvec, double* stats,
+                                            void*) {
+  if (B <= 0) return -22;
+  emul::launch(1, 1024, [&] { siglip_entropy_rows_kernel(Z, H, Q, B, rowvec, stats); });
+  return 0;
+}
+extern "C" int b200clip_siglip_entropy_coef(const double* stats_all, int W, int Bg, int T, float weight, float thr, float* dyn,
+                                            float* out, void*) {
+  if (W <= 0 || Bg <= 0 || T <= 0) return -22;
+  emul::launch(1, 32, [&] { siglip_entropy_coef_kernel(stats_all, W, Bg, T, weight, thr, dyn, out); });
   return 0;
 }

@@ -137,6 +137,10 @@ SIGLIP_CASES = {
                                                                label_smoothing=0.2)),
     "mp2_diag_b18_t30_d64": ("SigLIP2MultiPositiveBCELoss", dict(bias_init=-5.0)),
     "siglip_diag_b32_t32_d64": ("SigLIPLoss", dict()),
+    # the entropy regulariser (contrastive.py:19-68, 306-313): row statistics, device-side coefficient, gradient mode 3
+    "siglip_entropy_b16_t32_d64": ("SigLIPLoss", dict(entropy_regularization=True, bias_init=-2.0, min_entropy_threshold=5.0)),
+    "pairwise_entropy_auto_b16_t48_d64": ("SiglipPairwiseFeatureLoss", dict(auto_positive_weight=True, entropy_regularization=True,
+                                                                           entropy_weight=0.2, min_entropy_threshold=6.0)),
     "siglip_mp_b32_t40_d64": ("SigLIPLoss", dict()),
     "siglip_mp_noweights_b24_t50_d96": ("SigLIPLoss", dict(positive_weight=2.0, negative_weight=0.5, use_severity_weights=False)),
     "siglip_autobalance_b16_t48_d64": ("SigLIPLoss", dict(auto_balance=True)),
@@ -179,6 +183,12 @@ def test_siglip_loss_host_path_single_process(name, monkeypatch):
     bias = getattr(mod, "bias", None)
     db = bias.grad.item() if isinstance(bias, torch.nn.Parameter) and bias.grad is not None else None
     _check_siglip(g, out.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item(), db)
+    if ckw.get("entropy_regularization"):
+        d = mod.get_entropy_diagnostics()                                     # the reference's seven keys, one host copy
+        assert set(d) == {"entropy_mean", "entropy_min", "entropy_max", "entropy_normalized", "entropy_deficit",
+                          "entropy_loss", "bce_loss"}
+        assert all(np.isfinite(x) for x in d.values()) and d["entropy_min"] <= d["entropy_mean"] <= d["entropy_max"]
+        assert abs(d["bce_loss"] + d["entropy_loss"] - out.item()) <= 1e-6 * abs(out.item())
     with torch.no_grad():                                                     # the no-grad (dense forward) route
         fwd_only = mod(video_features=v.detach(), text_features=t.detach(), log_temp=lt.detach(), **kw).item()
     assert abs(fwd_only - float(g["f32_loss"])) <= 1e-5 * abs(float(g["f32_loss"]))
@@ -201,7 +211,7 @@ def _siglip_rank(rank, world, port, name, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["siglip_mp_b32_t40_d64", "siglip_diag_b32_t32_d64"])
+@pytest.mark.parametrize("name", ["siglip_mp_b32_t40_d64", "siglip_diag_b32_t32_d64", "siglip_entropy_b16_t32_d64"])
 def test_siglip_loss_host_path_two_ranks_gloo(name):
     """video rows (and their mask / weight rows) sharded, text replicated; every rank returns the full loss, its
     own video-gradient rows, the FULL text gradient and the full scalar gradients."""
