@@ -82,34 +82,58 @@ def test_clip_loss_host_path_single_process(name, monkeypatch):
     assert abs(dlt - rlt) <= 2e-3 * max(abs(rlt), 1e-3)
 
 
-def _rank(rank, world, port, name, out):
+def _clip_body(rank, world, name):
+    loss_mod = patch_package(build_emul())
+    g = np.load(GOLDEN / f"{name}.npz")
+    cls, kw = CASES[name]
+    N = g["video"].shape[0]
+    B = N // world
+    lo, hi = rank * B, (rank + 1) * B
+    v = torch.tensor(g["video"][lo:hi], dtype=torch.float32, requires_grad=True)
+    t = torch.tensor(g["text"][lo:hi], dtype=torch.float32, requires_grad=True)
+    lt = torch.tensor(g["log_temp"].astype(np.float32).reshape(1), requires_grad=True)
+    loss = getattr(loss_mod, cls)(**kw)(video_features=v, text_features=t, log_temp=lt)
+    loss.backward()
+    return (loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item())
+
+
+GLOO_CLIP = ["clip_c1_b64_d512", "clip_ls_b48_d96"]
+GLOO_SIGLIP = ["siglip_mp_b32_t40_d64", "siglip_diag_b32_t32_d64", "siglip_entropy_b16_t32_d64"]
+GLOO_LEGACY = [("contrastive", "contrastive_legacy_b32_d128"), ("siglip", "gated_siglip_legacy_b40_d128")]
+
+
+def _all_rank(rank, world, port, out):
+    """ONE two-rank gloo job runs every distributed scenario of this file (a spawn costs ~7 s of interpreter start-up)."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        loss_mod = patch_package(build_emul())
-        g = np.load(GOLDEN / f"{name}.npz")
-        cls, kw = CASES[name]
-        N = g["video"].shape[0]
-        B = N // world
-        lo, hi = rank * B, (rank + 1) * B
-        v = torch.tensor(g["video"][lo:hi], dtype=torch.float32, requires_grad=True)
-        t = torch.tensor(g["text"][lo:hi], dtype=torch.float32, requires_grad=True)
-        lt = torch.tensor(g["log_temp"].astype(np.float32).reshape(1), requires_grad=True)
-        loss = getattr(loss_mod, cls)(**kw)(video_features=v, text_features=t, log_temp=lt)
-        loss.backward()
-        out[rank] = (loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item())
+        res = {}
+        for name in GLOO_CLIP:
+            res[("clip", name)] = _clip_body(rank, world, name)
+        for name in GLOO_SIGLIP:
+            res[("siglip", name)] = _siglip_body(rank, world, name)
+        for cls, name in GLOO_LEGACY:
+            res[("legacy", cls)] = _legacy_body(rank, world, cls, name)
+        out[rank] = res
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["clip_c1_b64_d512", "clip_ls_b48_d96"])
-def test_clip_loss_host_path_two_ranks_gloo(name):
+@pytest.fixture(scope="module")
+def gloo_results():
     build_emul()
     world = 2
     port = 29500 + (os.getpid() % 1500)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_rank, args=(world, port, name, out), nprocs=world, join=True)
+    mp.spawn(_all_rank, args=(world, port, out), nprocs=world, join=True)
+    return {r: out[r] for r in range(world)}
+
+
+@pytest.mark.parametrize("name", GLOO_CLIP)
+def test_clip_loss_host_path_two_ranks_gloo(name, gloo_results):
+    world = 2
+    out = {r: gloo_results[r][("clip", name)] for r in range(world)}
     g = np.load(GOLDEN / f"{name}.npz")
     ref = float(g["f32_loss"])
     B = g["video"].shape[0] // world
@@ -194,33 +218,24 @@ def test_siglip_loss_host_path_single_process(name, monkeypatch):
     assert abs(fwd_only - float(g["f32_loss"])) <= 1e-5 * abs(float(g["f32_loss"]))
 
 
-def _siglip_rank(rank, world, port, name, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        loss_mod = patch_package(build_emul())
-        g = np.load(GOLDEN / f"{name}.npz")
-        cls, ckw = SIGLIP_CASES[name]
-        B = g["video"].shape[0] // world
-        mod = getattr(loss_mod, cls)(**ckw)
-        v, t, lt, kw = _siglip_inputs(g, rank * B, (rank + 1) * B)          # video rows / mask rows sharded, text replicated
-        loss = mod(video_features=v, text_features=t, log_temp=lt, **kw)
-        loss.backward()
-        out[rank] = (loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item(), mod.bias.grad.item())
-    finally:
-        dist.destroy_process_group()
+def _siglip_body(rank, world, name):
+    loss_mod = patch_package(build_emul())
+    g = np.load(GOLDEN / f"{name}.npz")
+    cls, ckw = SIGLIP_CASES[name]
+    B = g["video"].shape[0] // world
+    mod = getattr(loss_mod, cls)(**ckw)
+    v, t, lt, kw = _siglip_inputs(g, rank * B, (rank + 1) * B)          # video rows / mask rows sharded, text replicated
+    loss = mod(video_features=v, text_features=t, log_temp=lt, **kw)
+    loss.backward()
+    return (loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item(), mod.bias.grad.item())
 
 
-@pytest.mark.parametrize("name", ["siglip_mp_b32_t40_d64", "siglip_diag_b32_t32_d64", "siglip_entropy_b16_t32_d64"])
-def test_siglip_loss_host_path_two_ranks_gloo(name):
+@pytest.mark.parametrize("name", GLOO_SIGLIP)
+def test_siglip_loss_host_path_two_ranks_gloo(name, gloo_results):
     """video rows (and their mask / weight rows) sharded, text replicated; every rank returns the full loss, its
     own video-gradient rows, the FULL text gradient and the full scalar gradients."""
-    build_emul()
     world = 2
-    port = 31000 + (os.getpid() % 1500)
-    mgr = mp.Manager()
-    out = mgr.dict()
-    mp.spawn(_siglip_rank, args=(world, port, name, out), nprocs=world, join=True)
+    out = {r: gloo_results[r][("siglip", name)] for r in range(world)}
     g = np.load(GOLDEN / f"{name}.npz")
     B = g["video"].shape[0] // world
     for r in range(world):
@@ -244,36 +259,27 @@ def test_alignment_diagnostics_end_to_end(name, monkeypatch):
         assert abs(r[key].item() - want) <= 2e-5 * max(1.0, abs(want)), (key, r[key].item(), want)
 
 
-def _legacy_rank(rank, world, port, cls, name, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        loss_mod = patch_package(build_emul())
-        g = np.load(GOLDEN / f"{name}.npz")
-        B = g["video"].shape[0] // world
-        v = torch.tensor(g["video"][rank * B:(rank + 1) * B], dtype=torch.float32, requires_grad=True)
-        t = torch.tensor(g["text"][rank * B:(rank + 1) * B], dtype=torch.float32, requires_grad=True)
-        lt = torch.tensor(g["log_temp"].astype(np.float32).reshape(1), requires_grad=True)
-        mod = loss_mod.InfoNCELoss(use_ddp=True, loss_type=cls)               # the dispatcher picks the *DDP class
-        loss = mod(v, t, lt)
-        loss.backward()
-        out[rank] = (loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item())
-    finally:
-        dist.destroy_process_group()
+def _legacy_body(rank, world, cls, name):
+    loss_mod = patch_package(build_emul())
+    g = np.load(GOLDEN / f"{name}.npz")
+    B = g["video"].shape[0] // world
+    v = torch.tensor(g["video"][rank * B:(rank + 1) * B], dtype=torch.float32, requires_grad=True)
+    t = torch.tensor(g["text"][rank * B:(rank + 1) * B], dtype=torch.float32, requires_grad=True)
+    lt = torch.tensor(g["log_temp"].astype(np.float32).reshape(1), requires_grad=True)
+    mod = loss_mod.InfoNCELoss(use_ddp=True, loss_type=cls)               # the dispatcher picks the *DDP class
+    loss = mod(v, t, lt)
+    loss.backward()
+    return (loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item())
 
 
-@pytest.mark.parametrize("cls,name", [("contrastive", "contrastive_legacy_b32_d128"), ("siglip", "gated_siglip_legacy_b40_d128")])
-def test_legacy_ddp_losses_two_ranks_gloo(cls, name):
+@pytest.mark.parametrize("cls,name", GLOO_LEGACY)
+def test_legacy_ddp_losses_two_ranks_gloo(cls, name, gloo_results):
     """utils/loss/losses.py:104-158, 213-276 through InfoNCELoss(use_ddp=True): ContrastiveLossDDP (no tau clamp) and the
     gated SiglipLossDDP, which rounds the features to fp16 before the gather (:243-244) — compared with the oracle on the
     fp16-rounded inputs."""
     from oracle import contrastive_oracle as co
-    build_emul()
     world = 2
-    port = 33500 + (os.getpid() % 1500)
-    mgr = mp.Manager()
-    out = mgr.dict()
-    mp.spawn(_legacy_rank, args=(world, port, cls, name, out), nprocs=world, join=True)
+    out = {r: gloo_results[r][("legacy", cls)] for r in range(world)}
     g = np.load(GOLDEN / f"{name}.npz")
     v, t = g["video"].astype(np.float32), g["text"].astype(np.float32)
     if cls == "siglip":

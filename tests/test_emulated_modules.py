@@ -182,7 +182,7 @@ def test_query_pool_module_on_emulated_kernels(on_emulated_kernels, name):
     assert on_emulated_kernels == ["querypool", "querypool"]
 
 
-@pytest.mark.parametrize("name", ["multipos_48x64", "multipos_130x37"])
+@pytest.mark.parametrize("name", ["multipos_48x64"])      # 130x37 is covered on the GPU; it costs 14 s of thread spawns here
 def test_multipos_loss_modules_on_emulated_kernels(on_emulated_kernels, name):
     """WeightedSigLIPLoss / MultiPositiveInfoNCELoss (the package's nn.Modules and autograd function) through the shipped
     multipos kernels on CPU, against the reference classes' fp32 autograd goldens."""
