@@ -61,6 +61,7 @@ def _rel(a, b):
 
 
 CASES = {"clip_c1_b64_d512": ("CLIPLoss", {}), "clip_ls_b48_d96": ("CLIPLoss", {"label_smoothing": 0.1}),
+         "clip_b300_d200": ("CLIPLoss", {}),                 # D not a multiple of 64, B not a multiple of the tile height
          "contrastive_legacy_b32_d128": ("ContrastiveLoss", {}), "gated_siglip_legacy_b40_d128": ("SiglipLoss", {})}
 
 
