@@ -127,3 +127,18 @@ def test_alignment_scalar_kernel_device_code(emul, name):
     for got, key in zip(out[:3], ("cosine_f64", "logprob_f64", "prob_f64")):
         ref = float(g[key])
         assert abs(float(got) - ref) <= 5e-6 * max(1.0, abs(ref)), (key, float(got), ref)
+
+
+def test_two_sweep_topk_seeded_fuzz(emul):
+    """Random (N, M, k, segments), every third case quantised to force ties at the k-th score: exact top-k, -1 padding."""
+    rng = np.random.default_rng(0)
+    for it in range(12):
+        N = int(rng.integers(1, 300)); M = int(rng.integers(1, 1500)); k = int(rng.integers(1, 17))
+        segs = int(rng.integers(1, (M + 255) // 256 + 1))
+        S = rng.standard_normal((N, M)).astype(np.float32)
+        if it % 3 == 0:
+            S = np.round(S * 3) / 3
+        ov, s, i, thr, cnt = two_sweeps(emul, S, k, segs, cap=4096)
+        kk = min(k, M)
+        es, ei = exact_topk(S, kk)
+        assert ov == 0 and (i[:, :kk] == ei).all() and (s[:, :kk] == es).all() and (i[:, kk:] == -1).all(), (N, M, k, segs)

@@ -119,3 +119,27 @@ def test_pool_backward_kernel_under_emulation(emul, B, N, D, H, S, NW, masked, f
         dq_ref = np.einsum("bhn,bnd->hd", ds_ref, x)
         got_dq = part_dq.sum((0, 1))
         assert np.abs(got_dq - dq_ref).max() <= 2e-5 * np.abs(dq_ref).max() + 1e-6
+
+
+def test_fused_dq_kernel_seeded_fuzz(emul):
+    """Random shapes of the opt-in kDq backward (D in {128 .. 512}, 1..8 heads, token counts below / across the 32-token
+    tile, more splits than tiles, masks, upstream dlse): ds and the fused query gradient against the closed forms."""
+    rng = np.random.default_rng(0)
+    for it in range(8):
+        D = int(rng.choice([128, 256, 384, 512])); H = int(rng.integers(1, 9)); B = int(rng.integers(1, 4))
+        N = int(rng.integers(1, 150)); S = int(rng.integers(1, 5)); masked = bool(rng.integers(0, 2))
+        NW = 16 if D % 256 == 0 else 8
+        xb, x, qt, mask = make_inputs(B, N, D, H, 100 + it, masked)
+        dxbar = rng.standard_normal((B, H, D)).astype(np.float32)
+        _, m, l, a = softmax_stats(x, qt, mask)
+        xbar = np.einsum("bhn,bnd->bhd", a, x)
+        dx = np.zeros((B, N, D), np.uint16); ds = np.zeros((B, H, N), np.float32); pdq = np.zeros((B, S, H, D), np.float32)
+        dlse = rng.standard_normal((B, H)).astype(np.float32) if it % 2 else None
+        emul.emul_pool_bwd(ptr(xb), 1, ptr(mask), ptr(qt), ptr(dxbar), ptr(xbar.astype(np.float32)), ptr(m.astype(np.float32)),
+                           ptr(l.astype(np.float32)), B, N, D, H, S, NW, 2, ptr(dx), ptr(ds), ptr(dlse), ptr(pdq))
+        c = np.einsum("bhd,bhd->bh", dxbar.astype(np.float64), xbar) - (dlse if dlse is not None else 0.0)
+        ds_ref = a * (np.einsum("bhd,bnd->bhn", dxbar.astype(np.float64), x) - c[..., None])
+        dq_ref = np.einsum("bhn,bnd->hd", ds_ref, x)
+        case = (B, N, D, H, S, masked, dlse is not None)
+        assert np.abs(ds - ds_ref).max() <= 2e-4 * np.abs(ds_ref).max() + 1e-9, case
+        assert np.abs(pdq.sum((0, 1)) - dq_ref).max() <= 5e-5 * np.abs(dq_ref).max() + 1e-9, case
