@@ -19,6 +19,33 @@ def test_library_loads_and_exports_every_header_symbol():
     assert b"invalid" in lib.b200clip_strerror(-22)
 
 
+def test_header_is_plain_c_and_a_c_host_can_bind_the_library(tmp_path):
+    """include/b200clip.h is the boundary: it must compile as C99 (no C++ / torch types) and a plain C program linked against
+    libb200clip.so must be able to call it (the GPU-free entry points only — no compute without a device)."""
+    import os
+    import shutil
+    import subprocess
+    from deepcoro_clip_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    _lib.lib()
+    root = _lib._PKG.parent
+    src = tmp_path / "host.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "b200clip.h"\n'
+                   'int main(void) {\n'
+                   '  if (b200clip_abi_version() != B200CLIP_ABI_VERSION) return 1;\n'
+                   '  if (strstr(b200clip_strerror(-22), "invalid") == NULL) return 2;\n'
+                   '  if (b200clip_l2norm_fwd(NULL, 0, 0, 4, 8, NULL, 64, 64, -1, NULL, NULL, 0, 1, NULL) != -22) return 3;\n'
+                   '  printf("abi %d\\n", b200clip_abi_version());\n  return 0;\n}\n')
+    exe = tmp_path / "host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{root / 'include'}", str(src), "-o", str(exe),
+                    f"-L{_lib._PKG}", "-lb200clip", f"-Wl,-rpath,{_lib._PKG}", "-Wl,--allow-shlib-undefined"], check=True)
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = f"/usr/local/cuda/lib64:{env.get('LD_LIBRARY_PATH', '')}"
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == "abi 1", (r.returncode, r.stdout, r.stderr)
+
+
 @pytest.mark.parametrize("name,dtype", [("rope_f32_t2h3w4_cls", torch.float32), ("rope_bf16_t4h7w7_cls", torch.bfloat16)])
 def test_rope_tables_bit_identical_to_reference(name, dtype):
     from deepcoro_clip_b200.rope_3d import Rope3D
