@@ -73,29 +73,55 @@ def test_exact_grid_topk_and_recall_bit_exact(monkeypatch, topk2):
     assert (i.numpy() == oi).all() and (s.numpy() == ov).all()
 
 
-def _rank(rank, world, port, out):
+def _shards_body(rank, world):
+    rms = patch_retrieval(build_emul())
+    g = np.load(GOLDEN / "retrieval_grid_257x300.npz")
+    v, t = torch.tensor(g["video"]), torch.tensor(g["text"])
+    r = rms.compute_recall_at_k_streaming(v, t, torch.tensor(g["gt"]), k_values=[1, 5, 10], device="cpu")
+    s, i = rms.streaming_topk(v, t, 10)
+    return (r, s.numpy(), i.numpy())
+
+
+def _store_body(rank, world):
+    patch_retrieval(build_emul())
+    from deepcoro_clip_b200 import EmbeddingStore, epoch_end_retrieval_metrics
+    g = np.load(GOLDEN / "retrieval_gauss_300x200.npz")
+    # ragged validation shards: rank 0 holds 170 videos, rank 1 the other 130; the text set is split 120 / 80
+    lo, hi = (0, 170) if rank == 0 else (170, 300)
+    vs, ts = EmbeddingStore(64, capacity=32, device="cpu"), EmbeddingStore(64, capacity=16, device="cpu")
+    for a in range(lo, hi, 37):                                           # batches of uneven size, buffer growth
+        vs.append(torch.tensor(g["video"][a:min(a + 37, hi)]))
+    tlo, thi = (0, 120) if rank == 0 else (120, 200)
+    ts.append(torch.tensor(g["text"][tlo:thi]))
+    return epoch_end_retrieval_metrics(vs, ts, torch.tensor(g["gt"][lo:hi]), k_values=(1, 5, 10, 50))
+
+
+def _all_rank(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        rms = patch_retrieval(build_emul())
-        g = np.load(GOLDEN / "retrieval_grid_257x300.npz")
-        v, t = torch.tensor(g["video"]), torch.tensor(g["text"])
-        r = rms.compute_recall_at_k_streaming(v, t, torch.tensor(g["gt"]), k_values=[1, 5, 10], device="cpu")
-        s, i = rms.streaming_topk(v, t, 10)
-        out[rank] = (r, s.numpy(), i.numpy())
+        out[rank] = {"shards": _shards_body(rank, world), "stores": _store_body(rank, world)}
     finally:
         dist.destroy_process_group()
 
 
-def test_text_shards_two_ranks_gloo():
-    """SURVEY §8e: every rank sweeps its row shard of the text database; rank counts are all-reduced, the per-shard top-k
-    lists all-gathered and merged by (score desc, index asc): identical to the single-process result on every rank."""
+@pytest.fixture(scope="module")
+def gloo_results():
+    """ONE two-rank gloo job for both distributed scenarios of this file (a spawn costs ~7 s of interpreter start-up)."""
     build_emul()
     world = 2
     port = 32500 + (os.getpid() % 1500)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_rank, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_all_rank, args=(world, port, out), nprocs=world, join=True)
+    return {r: out[r] for r in range(world)}
+
+
+def test_text_shards_two_ranks_gloo(gloo_results):
+    """SURVEY §8e: every rank sweeps its row shard of the text database; rank counts are all-reduced, the per-shard top-k
+    lists all-gathered and merged by (score desc, index asc): identical to the single-process result on every rank."""
+    world = 2
+    out = {r: gloo_results[r]["shards"] for r in range(world)}
     g = np.load(GOLDEN / "retrieval_grid_257x300.npz")
     ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
     ov, oi = ro.topk_lowest_index(ro.similarity(g["video"], g["text"]), 10)
@@ -105,34 +131,10 @@ def test_text_shards_two_ranks_gloo():
         assert (i == oi).all() and (s == ov).all()
 
 
-def _store_rank(rank, world, port, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        patch_retrieval(build_emul())
-        from deepcoro_clip_b200 import EmbeddingStore, epoch_end_retrieval_metrics
-        g = np.load(GOLDEN / "retrieval_gauss_300x200.npz")
-        # ragged validation shards: rank 0 holds 170 videos, rank 1 the other 130; every rank holds the whole text set once
-        lo, hi = (0, 170) if rank == 0 else (170, 300)
-        vs, ts = EmbeddingStore(64, capacity=32, device="cpu"), EmbeddingStore(64, capacity=16, device="cpu")
-        for a in range(lo, hi, 37):                                           # batches of uneven size, buffer growth
-            vs.append(torch.tensor(g["video"][a:min(a + 37, hi)]))
-        tlo, thi = (0, 120) if rank == 0 else (120, 200)
-        ts.append(torch.tensor(g["text"][tlo:thi]))
-        out[rank] = epoch_end_retrieval_metrics(vs, ts, torch.tensor(g["gt"][lo:hi]), k_values=(1, 5, 10, 50))
-    finally:
-        dist.destroy_process_group()
-
-
-def test_epoch_end_embedding_stores_two_ranks_gloo():
+def test_epoch_end_embedding_stores_two_ranks_gloo(gloo_results):
     """device-resident validation embeddings, the ragged two-collective gather and the streaming metrics on
     the gathered result — identical dict on every rank, equal to the reference's golden metrics."""
-    build_emul()
-    world = 2
-    port = 34500 + (os.getpid() % 1500)
-    mgr = mp.Manager()
-    out = mgr.dict()
-    mp.spawn(_store_rank, args=(world, port, out), nprocs=world, join=True)
+    out = {r: gloo_results[r]["stores"] for r in range(2)}
     g = np.load(GOLDEN / "retrieval_gauss_300x200.npz")
     ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
     assert out[0] == out[1]
