@@ -99,6 +99,11 @@ class _ClipLossFn(torch.autograd.Function):
                 v_work = None
             vsum = ops.colsum_bf16(vall[:, K - Kp:], N, D)      # hi panel (last in bf16x3 mode)
             tsum = ops.colsum_bf16(tall[:, K - Kp:], N, D)
+            if x3:
+                # bf16x3 operands: add the lo panels (video [lo|hi|hi], text [hi|lo|hi]) so the uniform-target term
+                # sum_ij S_ij keeps the fp32-level accuracy of the logits (it dominates the error at small N otherwise)
+                ops.colsum_bf16(vall[:, :Kp], N, D, out=vsum)
+                ops.colsum_bf16(tall[:, Kp:2 * Kp], N, D, out=tsum)
             unif_tgt = ((eps / N) * torch.dot(vsum.double(), tsum.double()) * dyn[2].double()).reshape(1)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         ops.call("clip_finalize", sums, N, dyn, eps, int(gated), unif_tgt, rowscale_all, colscale_all, loss, None, st)

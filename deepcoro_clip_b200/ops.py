@@ -101,8 +101,10 @@ def diag_sum(a, b, rows, K, gated, dots, acc_slot):
     call("diag_sum", a, a.stride(0), b, b.stride(0), rows, K, int(gated), dots, acc_slot, stream_ptr(a.device))
 
 
-def colsum_bf16(op, rows, dim):
-    out = torch.zeros(dim, dtype=torch.float32, device=op.device)
+def colsum_bf16(op, rows, dim, out=None):
+    """out[c] (+)= sum_r op[r, c]; pass ``out`` to accumulate a second panel into the same sums."""
+    if out is None:
+        out = torch.zeros(dim, dtype=torch.float32, device=op.device)
     call("colsum_bf16", op, op.stride(0), rows, dim, out, stream_ptr(op.device))
     return out
 

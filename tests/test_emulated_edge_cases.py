@@ -119,6 +119,23 @@ def test_known_gap_fixed_shift_range_at_the_reference_clamp_floor(loss_mod):
         assert abs(ours.item() - o["loss"]) <= 1e-5 * abs(o["loss"]), tau
 
 
+def test_label_smoothing_at_tiny_batches(loss_mod):
+    """The uniform-target term (eps / N) sum_ij L_ij dominates the error budget at small N: with bf16x3 operands its column
+    sums include the lo panels (hi-only sums were off by up to 3.6e-5 relative at N = 8, eps = 0.2)."""
+    for seed, N, D, eps, tau in ((1, 8, 64, 0.2, 0.05), (2, 8, 64, 0.2, 0.05), (1, 8, 512, 0.2, 0.05), (3, 5, 96, 0.3, 0.1)):
+        r = np.random.default_rng(seed)
+        v = r.standard_normal((N, D)).astype(np.float32)
+        t = r.standard_normal((N, D)).astype(np.float32)
+        o = co.clip_loss(v, t, math.log(tau), label_smoothing=eps)
+        vv, tt = torch.tensor(v, requires_grad=True), torch.tensor(t, requires_grad=True)
+        lt = torch.tensor([math.log(tau)], requires_grad=True)
+        loss = loss_mod.CLIPLoss(label_smoothing=eps)(video_features=vv, text_features=tt, log_temp=lt)
+        loss.backward()
+        assert abs(loss.item() - o["loss"]) <= 5e-6 * abs(o["loss"]), (seed, N, D, loss.item(), o["loss"])
+        assert _rel(vv.grad.numpy(), o["dvideo"]) <= 2e-3 and _rel(tt.grad.numpy(), o["dtext"]) <= 2e-3
+        assert abs(lt.grad.item() - o["dlog_temp"]) <= 2e-3 * max(abs(o["dlog_temp"]), 1e-3)
+
+
 def test_siglip_ragged_rows_without_positives_and_frozen_bias(loss_mod):
     B, T, D = 21, 50, 64
     v, t = _data(B, D, 3, T=T)
