@@ -163,7 +163,7 @@ def retrieval_leg(dev, world, rank, cpu_baseline=False):
 
     def once():
         keep = []
-        r = compute_recall_at_k_streaming(v, t, gt, k_values=[1, 5, 10], precision="bf16", _counts_out=keep)
+        r = compute_recall_at_k_streaming(v, t, gt, k_values=[1, 5, 10], precision="bf16", use_ddp=True, _counts_out=keep)
         r["MRR_V2T"] = float(mrr_sum_from_counts(keep[0], M).item() / Nv)
         return r
     once()

@@ -55,9 +55,14 @@ int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const i
   return rowdot_bf16(a, lda, b, ldb, reinterpret_cast<const long long*>(idx), rows, b_rows, K, out, S(stream));
 }
 
-int b200clip_clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif,
+int b200clip_rowdot_raw(const void* a, int a_dtype, int64_t lda, const float* a_inv_norm, const void* b, int b_dtype,
+                        int64_t ldb, const float* b_inv_norm, int rows, int dim, float* out, void* stream) {
+  return rowdot_raw(a, a_dtype, lda, a_inv_norm, b, b_dtype, ldb, b_inv_norm, rows, dim, out, S(stream));
+}
+
+int b200clip_clip_finalize(const float* sums, int n, int nvec, const float* dyn, float eps, int gated, const double* unif,
                            float* rowscale, float* colscale, float* loss_out, double* acc_out, void* stream) {
-  return clip_finalize(sums, n, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out, S(stream));
+  return clip_finalize(sums, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out, S(stream));
 }
 
 int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
@@ -81,11 +86,21 @@ int b200clip_rowdot_tc(const void* a, int lda, const void* b, int ldb, int rows,
 }
 
 int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                            float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag,
-                            int diag_off, void* stream) {
+                            float shift2, int gated, const float* dyn, int skip_if_stable, float* rowsum, float* colsum,
+                            float* diag, int diag_off, void* stream) {
   if (!A || !B || !rowsum || !colsum) return B2_EINVAL;
-  return logits_lse_fwd(A, B, Ma, Nb, Kp, lda, ldb, scale2, shift2, gated, dyn, rowsum, colsum, diag, diag_off,
-                        S(stream));
+  return logits_lse_fwd(A, B, Ma, Nb, Kp, lda, ldb, scale2, shift2, gated, dyn, skip_if_stable, rowsum, colsum, diag,
+                        diag_off, S(stream));
+}
+
+int b200clip_rowlse_slots(int Ma, int Nb, int Kp) { return rowlse_slots(Ma, Nb, Kp); }
+
+int b200clip_logits_rowlse(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, int gated,
+                           const float* dyn, int only_if_stable, float* part, int slots, int32_t* ticket, float* lse2,
+                           float* diag, int diag_off, float* gap, void* stream) {
+  if (!A || !B) return B2_EINVAL;
+  return logits_rowlse(A, B, Ma, Nb, Kp, lda, ldb, gated, dyn, only_if_stable, part, slots, ticket, lse2, diag, diag_off,
+                       gap, S(stream));
 }
 
 int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
@@ -113,6 +128,11 @@ int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min,
 int b200clip_dyn_set_siglip(float* dyn, float logit_clamp, float neg_target, void* stream) {
   if (!dyn || !(logit_clamp > 0.f)) return B2_EINVAL;
   return dyn_set_siglip(dyn, logit_clamp, neg_target, S(stream));
+}
+
+int b200clip_dyn_set_stable(float* dyn, int stable, void* stream) {
+  if (!dyn) return B2_EINVAL;
+  return dyn_set_stable(dyn, stable, S(stream));
 }
 
 int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc,
@@ -191,10 +211,14 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                         int T, int cap, const int32_t* col, const float* y, const float* w, const int32_t* cnt,
                         const float* ysum, const float* dyn, float positive_weight, float negative_weight, float c,
                         float gnorm, int hp, int use_pos_weights, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc,
+                        const void* video_raw, int video_dtype, int64_t ld_video_raw, const float* video_inv_norm,
+                        const void* text_raw, int text_dtype, int64_t ld_text_raw, const float* text_inv_norm,
                         void* stream) {
   if (!video || !text || !col || !y || !w || !cnt || !ysum || !dyn || !acc) return B2_EINVAL;
   return siglip_pos(video, ldv, text, ldt, K, Dp, D, hi_off, B, T, cap, col, y, w, cnt, ysum, dyn, positive_weight,
-                    negative_weight, c, gnorm, hp, use_pos_weights, auto_balance, dV, lddv, dT, lddt, acc, S(stream));
+                    negative_weight, c, gnorm, hp, use_pos_weights, auto_balance, dV, lddv, dT, lddt, acc, video_raw,
+                    video_dtype, ld_video_raw, video_inv_norm, text_raw, text_dtype, ld_text_raw, text_inv_norm,
+                    S(stream));
 }
 
 int b200clip_multipos_workspace_bytes(int n_rows, int n_cols) { return multipos_workspace_bytes(n_rows, n_cols); }

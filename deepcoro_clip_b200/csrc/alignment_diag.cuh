@@ -10,17 +10,20 @@ namespace b2 {
 //   out[0] = mean S_ii                                     (alignment_cosine: diag(similarity).mean())
 //   out[1] = mean (f(S_ii) / tau - ln rowsum_i - ln2 shift2)  (alignment_logprob: diag(log_softmax(logits, 1)).mean())
 //   out[2] = exp(out[1])                                   (alignment_prob)
+// Stable mode (dyn[11] != 0, temperatures below the fixed-shift window): the rowsum slot holds the log2-domain row
+// log-sum-exp written by logits_rowlse instead, and ln rowsum_i + ln2 shift2 is replaced by ln2 * lse2_i.
 // One CTA, fp64 accumulation with a fixed reduction tree (deterministic).
 __global__ void __launch_bounds__(1024)
 alignment_diag_kernel(const float* __restrict__ sums, int n, const float* __restrict__ dyn, int gated,
                       float* __restrict__ out) {
   const double shift = (double)dyn[6], inv_tau = (double)dyn[2];
+  const bool stable = dyn[11] != 0.f;
   double a_cos = 0.0, a_lp = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double d = (double)sums[2 * n + i];
     const double f = gated ? d / (1.0 + exp(-d)) : d;
     a_cos += d;
-    a_lp += f * inv_tau - ((double)logf(sums[n + i]) + shift);
+    a_lp += f * inv_tau - (stable ? 0.6931471805599453 * (double)sums[n + i] : (double)logf(sums[n + i]) + shift);
   }
   __shared__ double sh[2][1024];
   sh[0][threadIdx.x] = a_cos;

@@ -58,7 +58,28 @@ struct BwParams {
   int ldd;
   double* scal;                // [4] fp64 atomics: 0: sum G*f(S), 1: sum softplus(L), 2: sum G ; may be null
   const float* dyn;            // optional device block from dyn_prep: overrides scale2/shift2/inv_tau/bias/out_scale
+  int stable;                  // CLIP / gated only, read from dyn[11] inside the kernel: rowscale / colscale hold log2-domain
+                               // log-sum-exps (minus log2 c) and G = 2^(L2 - rowscale_i) + 2^(L2 - colscale_j), two
+                               // exponentials that are each <= c, instead of P * (c / rowsum_i + c / colsum_j) with the
+                               // fixed shift (tau below the window of dyn_prep, down to the reference's floor 1e-4)
 };
+
+// Row / column statistic in the form the epilogue consumes it. Fixed shift: scale * gnorm (0 outside the problem: no
+// contribution). Stable: lse2 - log2(gnorm) (+huge outside the problem: 2^(L2 - huge) = 0).
+__device__ __forceinline__ float bw_stat(const BwParams& p, const float* __restrict__ v, int i, bool ok) {
+  if (p.stable) return ok ? __ldg(v + i) - log2f(p.gnorm) : 3.0e38f;
+  return ok ? __ldg(v + i) * p.gnorm : 0.f;
+}
+
+// c * gnorm * (softmax over the row + softmax over the column) of one logit, f = f(S)
+template <bool kStable>
+__device__ __forceinline__ float bw_softmax_g(float f, float scale2, float nshift2, float rs, float cs) {
+  if (kStable) {
+    const float l2 = f * scale2;
+    return ex2_approx(l2 - rs) + ex2_approx(l2 - cs);
+  }
+  return ex2_approx(fmaf(f, scale2, nshift2)) * (rs + cs);
+}
 
 __device__ __forceinline__ void lds128(uint32_t addr, float (&v)[4]) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
@@ -77,6 +98,61 @@ struct BwThread {
   float ydn, wn, ign, nshift2;
   float ent_iz = 0.f, ent_m = 0.f;   // BW_SIGLIP_ENT with X = video: 1/Z_row, m_row
 };
+
+// Interior tile of bw_g_tile (no bounds / diagonal tests, single bf16 gradient operand): 64 S values of one thread ->
+// packed bf16 G, written back in place.
+template <int kMode, bool kStable>
+__device__ __forceinline__ void bw_g_fast(const BwParams& p, const BwThread& th, const uint32_t (&acc)[2][32],
+                                          uint32_t sbase, uint32_t cs_addr, bool want_scal, float& tacc, float& lacc,
+                                          float& bacc) {
+  constexpr bool kSig = BwIsSiglip<kMode>::value;
+  const float rs = th.rs, wn = th.wn, nshift2 = th.nshift2;
+  const float lc = p.lclamp, yneg = p.yneg;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t packed[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        float cs4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!kSig) lds128(cs_addr + (c * 32 + e) * 4, cs4);
+        float g4[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float s = __uint_as_float(acc[c][e + h]);
+          float g;
+          if (kSig) {
+            const float R = fmaf(s, p.inv_tau, p.bias);
+            const float Lc = fminf(fmaxf(R, -lc), lc);
+            const float ex = ex2_approx(-1.4426950408889634f * fabsf(Lc));
+            const float den = 1.f + ex;
+            const float r = __fdividef(1.f, den);
+            const float sig = Lc >= 0.f ? r : ex * r;
+            g = (fabsf(R) <= lc) ? wn * (sig - yneg) : 0.f;
+            if (want_scal) {
+              lacc += fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + log1p_ex(ex));
+              bacc += g;
+              tacc = fmaf(g, s, tacc);
+            }
+          } else if (kMode == BW_GATED) {
+            const float ex = ex2_approx(-1.4426950408889634f * s);
+            const float sig = __fdividef(1.f, 1.f + ex);
+            const float f = s * sig;
+            const float fp = sig * (1.f + s * (1.f - sig));
+            g = bw_softmax_g<kStable>(f, p.scale2, nshift2, rs, cs4[h]);
+            if (want_scal) tacc = fmaf(g, f, tacc);
+            g *= fp;
+          } else {
+            g = bw_softmax_g<kStable>(s, p.scale2, nshift2, rs, cs4[h]);
+            if (want_scal) tacc = fmaf(g, s, tacc);
+          }
+          g4[h] = g;
+        }
+        packed[e >> 1] = pack_bf16x2(g4[0], g4[1]);
+        packed[(e >> 1) + 1] = pack_bf16x2(g4[2], g4[3]);
+      }
+      tmem_st16(sbase + c * 16, packed);
+    }
+}
 
 // G tile of one step: S (fp32, TMEM) -> elementwise gradient -> bf16x2 packed IN PLACE (tcgen05.st).
 // sbase: TMEM address of this thread's 64 S columns; cs_addr / cs: staged colscale*gnorm of the tile (shared).
@@ -101,50 +177,10 @@ __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th,
   tc_wait_ld();
   if (full && !has_diag && !p.hp && !kEnt) {
     // -------- fast path: interior tile, no bounds / diagonal tests --------
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t packed[16];
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        float cs4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!kSig) lds128(cs_addr + (c * 32 + e) * 4, cs4);
-        float g4[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float s = __uint_as_float(acc[c][e + h]);
-          float g;
-          if (kSig) {
-            const float R = fmaf(s, p.inv_tau, p.bias);
-            const float Lc = fminf(fmaxf(R, -lc), lc);
-            const float ex = ex2_approx(-1.4426950408889634f * fabsf(Lc));
-            const float den = 1.f + ex;
-            const float r = __fdividef(1.f, den);
-            const float sig = Lc >= 0.f ? r : ex * r;
-            g = (fabsf(R) <= lc) ? wn * (sig - yneg) : 0.f;
-            if (want_scal) {
-              lacc += fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den));
-              bacc += g;
-              tacc = fmaf(g, s, tacc);
-            }
-          } else if (kMode == BW_GATED) {
-            const float ex = ex2_approx(-1.4426950408889634f * s);
-            const float sig = __fdividef(1.f, 1.f + ex);
-            const float f = s * sig;
-            const float fp = sig * (1.f + s * (1.f - sig));
-            g = ex2_approx(fmaf(f, p.scale2, nshift2)) * (rs + cs4[h]);
-            if (want_scal) tacc = fmaf(g, f, tacc);
-            g *= fp;
-          } else {
-            g = ex2_approx(fmaf(s, p.scale2, nshift2)) * (rs + cs4[h]);
-            if (want_scal) tacc = fmaf(g, s, tacc);
-          }
-          g4[h] = g;
-        }
-        packed[e >> 1] = pack_bf16x2(g4[0], g4[1]);
-        packed[(e >> 1) + 1] = pack_bf16x2(g4[2], g4[3]);
-      }
-      tmem_st16(sbase + c * 16, packed);
-    }
+    if (!kSig && p.stable)
+      bw_g_fast<kMode, true>(p, th, acc, sbase, cs_addr, want_scal, tacc, lacc, bacc);
+    else
+      bw_g_fast<kMode, false>(p, th, acc, sbase, cs_addr, want_scal, tacc, lacc, bacc);
   } else {
     // -------- general path: edge tiles, diagonal tiles, hi+lo gradient operand --------
 #pragma unroll
@@ -167,7 +203,7 @@ __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th,
             const float sig = Lc >= 0.f ? r : ex * r;
             const bool inr = fabsf(R) <= lc;
             g = inr ? wn * (sig - yneg) : 0.f;
-            float sp = fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den));
+            float sp = fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + log1p_ex(ex));
             if (kEnt) {
               // entropy regulariser: p = exp(L - 30) / Z_video, video = this row (rowscale) or this column (colscale)
               const int colg = j * BW_BN + cl;
@@ -194,8 +230,8 @@ __device__ __forceinline__ void bw_g_tile(const BwParams& p, const BwThread& th,
               f = s * sig;
               fp = sig * (1.f + s * (1.f - sig));
             }
-            const float pr = ex2_approx(fmaf(f, p.scale2, nshift2));
-            g = pr * (rs + cs[cl]);
+            g = p.stable ? bw_softmax_g<true>(f, p.scale2, nshift2, rs, cs[cl])
+                         : bw_softmax_g<false>(f, p.scale2, nshift2, rs, cs[cl]);
             if (has_diag && (c * 32 + e + h) == dcol) g -= ydn;
             if (!full && !(row_ok && (j * BW_BN + cl) < p.Ny)) g = 0.f;
             tacc = fmaf(g, f, tacc);

@@ -19,11 +19,17 @@ int gather_rows_bf16(const void* src, int lds, const long long* idx, int rows, i
                      cudaStream_t s);
 int rowdot_bf16(const void* a, int lda, const void* b, int ldb, const long long* idx, int rows, int b_rows, int K,
                 float* out, cudaStream_t s);
+int rowdot_raw(const void* a, int adtype, long long lda, const float* ainv, const void* b, int bdtype, long long ldb,
+               const float* binv, int rows, int dim, float* out, cudaStream_t s);
 
 // logits_fwd.cu
 int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                   float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag, int diag_off,
-                   cudaStream_t stream);
+                   float shift2, int gated, const float* dyn, int skip_if_stable, float* rowsum, float* colsum,
+                   float* diag, int diag_off, cudaStream_t stream);
+int rowlse_slots(int Ma, int Nb, int Kp);
+int logits_rowlse(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, int gated, const float* dyn,
+                  int only_if_stable, float* part, int slots, int* ticket, float* lse2, float* diag, int diag_off,
+                  float* gap, cudaStream_t stream);
 int rowdot_tc(const void* A, const void* B, int rows, int Kp, int lda, int ldb, float* out, cudaStream_t stream);
 int logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float* out, int ldo,
                 int max_ctas, cudaStream_t stream);
@@ -66,10 +72,11 @@ int attnpool_bwd_dx_mma(const void* x, int dtype, long long sb, long long sn, co
 // scalars.cu
 int dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, cudaStream_t s);
 int dyn_set_siglip(float* dyn, float lclamp, float yneg, cudaStream_t s);
+int dyn_set_stable(float* dyn, int stable, cudaStream_t s);
 int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s);
 int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s);
-int clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif, float* rowscale,
-                  float* colscale, float* loss_out, double* acc_out, cudaStream_t s);
+int clip_finalize(const float* sums, int n, int nvec, const float* dyn, float eps, int gated, const double* unif,
+                  float* rowscale, float* colscale, float* loss_out, double* acc_out, cudaStream_t s);
 int clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n, float* out,
                   cudaStream_t s);
 int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots, double* acc,
@@ -97,7 +104,8 @@ int siglip_compact(const float* mask, long ldm, const float* pw, long ldw, int B
 int siglip_pos(const void* V, int ldv, const void* T, int ldt, int K, int Dp, int D, int hi_off, int B, int Tn, int cap,
                const int* col, const float* y, const float* w, const int* cnt, const float* ysum, const float* dyn,
                float positive_weight, float negative_weight, float c, float gnorm, int hp, int use_pw, int auto_balance,
-               float* dV, int lddv, float* dT, int lddt, double* acc, cudaStream_t s);
+               float* dV, int lddv, float* dT, int lddt, double* acc, const void* Vraw, int v_dtype, long long ld_vraw,
+               const float* vinv, const void* Traw, int t_dtype, long long ld_traw, const float* tinv, cudaStream_t s);
 
 // retrieval.cu
 int retrieval_segments(int Ma, int Nb);

@@ -92,6 +92,30 @@ int gather_rows_bf16(const void* src, int lds, const long long* idx, int rows, i
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
+template <typename TA>
+static int rowdot_raw_t(const TA* a, long long lda, const float* ainv, const void* b, int bdtype, long long ldb,
+                        const float* binv, int rows, int dim, float* out, cudaStream_t s) {
+  const int blocks = (rows + 7) / 8;
+  switch (bdtype) {
+    case 0: rowdot_raw_kernel<TA, float><<<blocks, 256, 0, s>>>(a, lda, ainv, (const float*)b, ldb, binv, rows, dim, out); break;
+    case 1: rowdot_raw_kernel<TA, __nv_bfloat16><<<blocks, 256, 0, s>>>(a, lda, ainv, (const __nv_bfloat16*)b, ldb, binv, rows, dim, out); break;
+    case 2: rowdot_raw_kernel<TA, __half><<<blocks, 256, 0, s>>>(a, lda, ainv, (const __half*)b, ldb, binv, rows, dim, out); break;
+    default: return B2_EINVAL;
+  }
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int rowdot_raw(const void* a, int adtype, long long lda, const float* ainv, const void* b, int bdtype, long long ldb,
+               const float* binv, int rows, int dim, float* out, cudaStream_t s) {
+  if (rows <= 0 || dim <= 0 || !a || !b || !ainv || !binv || !out) return B2_EINVAL;
+  switch (adtype) {
+    case 0: return rowdot_raw_t<float>((const float*)a, lda, ainv, b, bdtype, ldb, binv, rows, dim, out, s);
+    case 1: return rowdot_raw_t<__nv_bfloat16>((const __nv_bfloat16*)a, lda, ainv, b, bdtype, ldb, binv, rows, dim, out, s);
+    case 2: return rowdot_raw_t<__half>((const __half*)a, lda, ainv, b, bdtype, ldb, binv, rows, dim, out, s);
+    default: return B2_EINVAL;
+  }
+}
+
 int rowdot_bf16(const void* a, int lda, const void* b, int ldb, const long long* idx, int rows, int b_rows, int K,
                 float* out, cudaStream_t s) {
   if (rows <= 0 || K <= 0 || (K & 1)) return B2_EINVAL;

@@ -134,6 +134,29 @@ rowdot_bf16_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bflo
   if (lane == 0) out[warp] = s;
 }
 
+// out[r] = (a[r, :dim] . b[r, :dim]) * ainv[r] * binv[r]: the cosine of a pair from the RAW features in fp32 (the target
+// logit of the softmax losses; the tensor-core value of the same pair carries the 2^-9 rounding of the bf16 operands, which
+// — unlike the errors inside the log-sum-exps — is not averaged over a row: it was the whole 1e-5 loss error at N <= 16k).
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+rowdot_raw_kernel(const TA* __restrict__ a, long long lda, const float* __restrict__ ainv, const TB* __restrict__ b,
+                  long long ldb, const float* __restrict__ binv, int rows, int dim, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const TA* ar = a + (size_t)warp * lda;
+  const TB* br = b + (size_t)warp * ldb;
+  float s0 = 0.f, s1 = 0.f;
+  int c = lane;
+  for (; c + 32 < dim; c += 64) {
+    s0 = fmaf(to_f32(ar[c]), to_f32(br[c]), s0);
+    s1 = fmaf(to_f32(ar[c + 32]), to_f32(br[c + 32]), s1);
+  }
+  if (c < dim) s0 = fmaf(to_f32(ar[c]), to_f32(br[c]), s0);
+  const float s = warp_sum(s0 + s1);
+  if (lane == 0) out[warp] = s * ainv[warp] * binv[warp];
+}
+
 // dst[r, :K] = src[idx[r], :K] (bf16 operand rows, 16-byte vectors; rows with an out-of-range index are zeroed)
 __global__ void __launch_bounds__(256)
 gather_rows_bf16_kernel(const uint4* __restrict__ src, int lds16, const long long* __restrict__ idx, int rows,

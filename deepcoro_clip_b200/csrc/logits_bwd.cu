@@ -98,6 +98,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
     p.lclamp = p.dyn[8];
     p.yneg = p.dyn[9];
     p.ent_coef = p.dyn[10];
+    p.stable = !BwIsSiglip<kMode>::value && p.dyn[11] != 0.f;
   }
 
   // item decode (identical in every role): item -> X tile, Y tile range [j0, j1)
@@ -259,7 +260,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
       const int row = xt * BW_BM + q * 32 + lane;
       const bool row_ok = row < p.Nx;
       float rs = 0.f, ent_iz = 0.f, ent_m = 0.f;
-      if (!BwIsSiglip<kMode>::value) rs = row_ok ? p.rowscale[row] * p.gnorm : 0.f;
+      if (!BwIsSiglip<kMode>::value) rs = bw_stat(p, p.rowscale, row, row_ok);
       if (kMode == BW_SIGLIP_ENT && p.rowscale && row_ok) {
         ent_iz = p.rowscale[2 * row];
         ent_m = p.rowscale[2 * row + 1];
@@ -273,7 +274,7 @@ bw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
         if (!BwIsSiglip<kMode>::value) {
           if (etid < 128) {
             const int col = j * BW_BN + etid;
-            col_s[buf * 128 + etid] = col < p.Ny ? p.colscale[col] * p.gnorm : 0.f;
+            col_s[buf * 128 + etid] = bw_stat(p, p.colscale, col, col < p.Ny);
           }
           named_bar_sync(1, 256);
         }
@@ -409,7 +410,7 @@ int logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, i
   p.rowscale = rowscale; p.colscale = colscale; p.out_scale = out_scale;
   p.gnorm = gnorm > 0.f ? gnorm : 1.f;
   p.hp = hp ? 1 : 0;
-  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f;
+  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f; p.stable = 0;
   p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
   CUtensorMap tmX, tmY;
   int rc;

@@ -98,6 +98,7 @@ bw2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     p.out_scale = p.dyn[2];
     p.lclamp = p.dyn[8];
     p.yneg = p.dyn[9];
+    p.stable = kMode != BW_SIGLIP && p.dyn[11] != 0.f;
   }
 
   auto decode = [&](int item, int& xp, int& j0, int& j1) {
@@ -266,7 +267,7 @@ bw2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       th.row = xt * BW_BM + q * 32 + lane;
       th.row_ok = th.row < p.Nx;
       th.rs = 0.f;
-      if (kMode != BW_SIGLIP) th.rs = th.row_ok ? p.rowscale[th.row] * p.gnorm : 0.f;
+      if (kMode != BW_SIGLIP) th.rs = bw_stat(p, p.rowscale, th.row, th.row_ok);
       double dtacc = 0.0, dlacc = 0.0, dbacc = 0.0;
       for (int t = 0; t < T; ++t, ++tile_ctr) {
         const int dp = t / nj, jr = t - dp * nj, j = j0 + jr;
@@ -276,7 +277,7 @@ bw2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         if (kMode != BW_SIGLIP) {
           if (etid < 128) {
             const int col = j * BW_BN + etid;
-            col_s[buf * 128 + etid] = col < p.Ny ? p.colscale[col] * p.gnorm : 0.f;
+            col_s[buf * 128 + etid] = bw_stat(p, p.colscale, col, col < p.Ny);
           }
           named_bar_sync(1, 256);
         }
@@ -383,7 +384,7 @@ int logits_bwd_pair(int mode, const void* X, const void* Y, int Nx, int Ny, int 
   p.rowscale = rowscale; p.colscale = colscale; p.out_scale = out_scale;
   p.gnorm = gnorm > 0.f ? gnorm : 1.f;
   p.hp = 0;
-  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f;
+  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f; p.stable = 0;
   p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
   CUtensorMap tmX, tmYs, tmYo;
   int rc;

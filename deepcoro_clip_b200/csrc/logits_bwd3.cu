@@ -58,7 +58,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 
 // 32 S values of one thread (row th.row, tile columns c0 .. c0+31) -> 32 gradient values, packed bf16x2.
 // cs_addr: shared address of the 32 staged colscale*gnorm values; colg0: global column of element 0.
-template <int kMode, bool kFast>
+template <int kMode, bool kFast, bool kStable>
 __device__ __forceinline__ void bw3_g32(const BwParams& p, const BwThread& th, const uint32_t (&acc)[32], uint32_t cs_addr,
                                         int colg0, int dcol, float& tacc, float& lacc, float& bacc,
                                         uint32_t (&packed)[16]) {
@@ -82,7 +82,7 @@ __device__ __forceinline__ void bw3_g32(const BwParams& p, const BwThread& th, c
         const float r = __fdividef(1.f, den);
         const float sig = Lc >= 0.f ? r : ex * r;
         g = (fabsf(R) <= lc) ? th.wn * (sig - yneg) : 0.f;
-        float sp = fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + 0.6931471805599453f * lg2_approx(den));
+        float sp = fmaf(-yneg, Lc, fmaxf(Lc, 0.f) + log1p_ex(ex));
         if (!ok) { g = 0.f; sp = 0.f; }
         lacc += sp;
         bacc += g;
@@ -95,7 +95,7 @@ __device__ __forceinline__ void bw3_g32(const BwParams& p, const BwThread& th, c
           f = s * sig;
           fp = sig * (1.f + s * (1.f - sig));
         }
-        g = ex2_approx(fmaf(f, p.scale2, th.nshift2)) * (th.rs + cs4[h]);
+        g = bw_softmax_g<kStable>(f, p.scale2, th.nshift2, th.rs, cs4[h]);
         if (!kFast) {
           if (e + h == dcol) g -= th.ydn;
           if (!ok) g = 0.f;
@@ -224,6 +224,7 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     p.out_scale = p.dyn[2];
     p.lclamp = p.dyn[8];
     p.yneg = p.dyn[9];
+    p.stable = !BwIsSiglip<kMode>::value && p.dyn[11] != 0.f;
   }
 
   if (warp == 0) {
@@ -383,14 +384,14 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       th.row = xt * BW_BM + BW3_XROWS * (int)rank + rloc;
       th.row_ok = th.row < p.Nx;
       th.rs = 0.f;
-      if (!BwIsSiglip<kMode>::value) th.rs = th.row_ok ? p.rowscale[th.row] * p.gnorm : 0.f;
+      if (!BwIsSiglip<kMode>::value) th.rs = bw_stat(p, p.rowscale, th.row, th.row_ok);
       const bool rows_full = xt * BW_BM + BW_BM <= p.Nx;
       double dtacc = 0.0, dlacc = 0.0, dbacc = 0.0;
       // column scales: lane e of every warp fetches the scale of the warp's e-th column one tile ahead (registers),
       // stages it in a warp-private 32-float slot (__syncwarp only, no CTA barrier) and reads it back broadcast
       auto load_cs = [&](int jt, int c) -> float {
         const int col = jt * kNJ + ctile + 32 * c + lane;
-        return col < p.Ny ? __ldg(p.colscale + col) * p.gnorm : 0.f;
+        return bw_stat(p, p.colscale, col, col < p.Ny);
       };
       float cs_next[NC];
 #pragma unroll
@@ -430,10 +431,17 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             dcol = (d >= 0 && d < 32) ? d : -1;
           }
           uint32_t packed[16];
-          if (full && !has_diag)
-            bw3_g32<kMode, true>(p, th, acc, cs_addr, colg0, -1, tacc, lacc, bacc, packed);
-          else
-            bw3_g32<kMode, false>(p, th, acc, cs_addr, colg0, dcol, tacc, lacc, bacc, packed);
+          // (the stable-softmax variants exist for the CLIP / gated modes only; the branch is grid-uniform)
+          if (!BwIsSiglip<kMode>::value && p.stable) {
+            if (full && !has_diag)
+              bw3_g32<kMode, true, !BwIsSiglip<kMode>::value>(p, th, acc, cs_addr, colg0, -1, tacc, lacc, bacc, packed);
+            else
+              bw3_g32<kMode, false, !BwIsSiglip<kMode>::value>(p, th, acc, cs_addr, colg0, dcol, tacc, lacc, bacc, packed);
+          } else if (full && !has_diag) {
+            bw3_g32<kMode, true, false>(p, th, acc, cs_addr, colg0, -1, tacc, lacc, bacc, packed);
+          } else {
+            bw3_g32<kMode, false, false>(p, th, acc, cs_addr, colg0, dcol, tacc, lacc, bacc, packed);
+          }
           const uint32_t gc = ga + (cc >> 6) * BW3_XCHUNK;
           const int u0 = (cc & 63) >> 3;
 #pragma unroll
@@ -568,7 +576,7 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
   p.rowscale = rowscale; p.colscale = colscale; p.out_scale = out_scale;
   p.gnorm = gnorm > 0.f ? gnorm : 1.f;
   p.hp = 0;
-  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f;
+  p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f; p.stable = 0;
   p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
   CUtensorMap tmX, tmYs, tmYo;
   int rc;

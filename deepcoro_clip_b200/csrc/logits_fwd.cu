@@ -102,6 +102,104 @@ struct LseEpi {
   }
 };
 
+// Stable mode of the softmax losses (dyn[11] != 0: tau below the fixed-shift window, down to the reference's clamp floor
+// 1e-4, utils/loss/contrastive.py:153): per-row log-sum-exp with a RUNNING MAXIMUM. Tile order outer = A tile, so the
+// epilogue thread owns its row across the whole sweep of B blocks and keeps (m, s) in two registers (online softmax in the
+// log2 domain: s = sum_j 2^(L2_ij - m), L2 = f(S) * log2(e) / tau); one exponential per element, a rescale only when the
+// maximum moves. Every (row, sweep segment, column half) writes its (m, s) pair; the LAST writer of a row (ticket counter)
+// merges the pairs into lse2[row] = M + log2(sum_k s_k 2^(m_k - M)), so no second launch is needed. The column
+// log-sum-exps of the symmetric loss are the row log-sum-exps of the role-swapped problem (A = text, B = video).
+struct RowLseParams {
+  const float* dyn;
+  float2* part;      // [Ma][slots] (m, s) pairs
+  int* ticket;       // [Ma], zero on entry
+  float* lse2;       // [Ma] out
+  float* diag;       // optional [Ma]: S[i, i + diag_off] with the tensor core's own rounding (the target logit)
+  int diag_off;
+  int slots;         // 2 * segs
+  float* gap;        // optional [Ma] (needs diag): lse2[i] - L2_ii formed as (M - L2_ii) + log2(sum): no cancellation between
+                     // two numbers of the size of the logits (up to 1.4e4 at tau = 1e-4), exactly log2(sum) when the target is
+                     // the row maximum — the loss term of an almost separated batch keeps its relative accuracy, like the
+                     // reference's log_softmax (x - max - log sum exp(x - max))
+};
+
+template <bool kGated>
+struct RowLseEpi {
+  using Params = RowLseParams;
+  struct State {
+    float m, s, scale2;
+  };
+  __device__ static __forceinline__ void init(State& st, const Params& p) {
+    st.scale2 = p.dyn[0];
+    st.m = -INFINITY;
+    st.s = 0.f;
+  }
+  __device__ static __forceinline__ void begin_outer(State& st, const Params&, int, const TeCtx&) {
+    st.m = -INFINITY;
+    st.s = 0.f;
+  }
+  __device__ static __forceinline__ void chunk(State& st, const Params& p, const TeCtx& ctx, int c,
+                                               const uint32_t (&acc)[32]) {
+    if (p.diag) {
+      const int d = ctx.row + p.diag_off - (ctx.col0 + c * 32);
+      if (d >= 0 && d < 32 && ctx.row_ok) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v = (e == d) ? acc[e] : v;
+        p.diag[ctx.row] = __uint_as_float(v);
+      }
+    }
+    const int cbase = ctx.col0 + c * 32;
+    float l[32];
+    float cm = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      float s = __uint_as_float(acc[e]);
+      if (kGated) s = __fdividef(s, 1.f + ex2_approx(-1.4426950408889634f * s));
+      float v = s * st.scale2;
+      if (!ctx.full) v = (cbase + e) < ctx.Nb ? v : -INFINITY;
+      l[e] = v;
+      cm = fmaxf(cm, v);
+    }
+    if (cm > -INFINITY) {                     // at least one valid column in this chunk
+      if (cm > st.m) {
+        st.s *= ex2_approx(st.m - cm);        // m = -inf on the first chunk: 0 * 0
+        st.m = cm;
+      }
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) a += ex2_approx(l[e] - st.m);
+      st.s += a;
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State&, const Params&, const TeCtx&) {}
+  __device__ static __forceinline__ void end_outer(State& st, const Params& p, int, const TeCtx& ctx) {
+    if (!ctx.row_ok) return;
+    float2* pr = p.part + (size_t)ctx.row * p.slots;
+    __stcg(pr + ctx.seg * 2 + ctx.wg, make_float2(st.m, st.s));
+    __threadfence();
+    if (atomicAdd(p.ticket + ctx.row, 1) == p.slots - 1) {
+      __threadfence();
+      float M = -INFINITY;
+      for (int k = 0; k < p.slots; ++k) M = fmaxf(M, __ldcg(pr + k).x);
+      float S = 0.f;
+      for (int k = 0; k < p.slots; ++k) {
+        const float2 v = __ldcg(pr + k);
+        if (v.y > 0.f) S += v.y * ex2_approx(v.x - M);
+      }
+      const float lg = log2f(S);
+      p.lse2[ctx.row] = M + lg;
+      if (p.gap) {
+        // the target logit exactly as chunk() formed it (same instructions on the same tensor-core value)
+        float d = __ldcg(p.diag + ctx.row);
+        if (kGated) d = __fdividef(d, 1.f + ex2_approx(-1.4426950408889634f * d));
+        p.gap[ctx.row] = (M - d * st.scale2) + lg;
+      }
+      p.ticket[ctx.row] = 0;                  // re-armed for a replay of the same buffers (CUDA graph)
+    }
+  }
+};
+
 // out[i] = S[i, i] exactly as the tensor core produces it (used with TeShape::diag: only the diagonal tiles run).
 struct DiagParams {
   float* out;
@@ -162,16 +260,21 @@ int make_shape(TeShape& g, int Ma, int Nb, int Kp) {
   g.n_blocks = (Nb + TE_BN - 1) / TE_BN;
   g.segs = 0;
   g.diag = 0;
+  g.gate = nullptr;
+  g.gate_on = 0;
   return B2_OK;
 }
 
 template <class Epi, bool kOuterIsB>
 static int launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb,
-                     const typename Epi::Params& ep, int max_ctas, cudaStream_t stream, int diag = 0) {
+                     const typename Epi::Params& ep, int max_ctas, cudaStream_t stream, int diag = 0,
+                     const float* gate = nullptr, int gate_on = 0) {
   TeShape g;
   int rc = make_shape(g, Ma, Nb, Kp);
   if (rc) return rc;
   g.diag = diag;
+  g.gate = gate;
+  g.gate_on = gate_on;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, TE_BN))) return rc;
@@ -200,10 +303,13 @@ bool te_pair_enabled(int Kp) {
 
 template <class Epi, bool kOuterIsB>
 static int launch_te2(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb,
-                      const typename Epi::Params& ep, cudaStream_t stream) {
+                      const typename Epi::Params& ep, cudaStream_t stream, const float* gate = nullptr,
+                      int gate_on = 0) {
   TeShape g;
   int rc = make_shape(g, Ma, Nb, Kp);
   if (rc) return rc;
+  g.gate = gate;
+  g.gate_on = gate_on;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, 128))) return rc;      // each CTA loads 128 of the 256 block rows
@@ -223,15 +329,88 @@ static int launch_te2(const void* A, const void* B, int Ma, int Nb, int Kp, int 
 }
 
 int logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                   float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag, int diag_off,
-                   cudaStream_t stream) {
+                   float shift2, int gated, const float* dyn, int skip_if_stable, float* rowsum, float* colsum,
+                   float* diag, int diag_off, cudaStream_t stream) {
   LseParams p{scale2, shift2, rowsum, colsum, gated, dyn, diag, diag_off};
+  const float* gate = (dyn && skip_if_stable) ? dyn + 11 : nullptr;     // run only while dyn[11] == 0
   if (te_pair_enabled(Kp)) {
-    if (gated) return launch_te2<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, stream);
-    return launch_te2<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, stream);
+    if (gated) return launch_te2<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, stream, gate, 0);
+    return launch_te2<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, stream, gate, 0);
   }
-  if (gated) return launch_te<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
-  return launch_te<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream);
+  if (gated) return launch_te<LseEpi<true>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream, 0, gate, 0);
+  return launch_te<LseEpi<false>, true>(A, B, Ma, Nb, Kp, lda, ldb, p, 0, stream, 0, gate, 0);
+}
+
+// Sweep segments of the row-LSE pass: outer = A tile (pair), so few row tiles leave SMs idle unless the sweep over the B
+// blocks is split (same rule as the retrieval sweep, never more segments than B blocks: every segment is non-empty).
+int rowlse_slots(int Ma, int Nb, int Kp) {
+  const int m_tiles = (Ma + TE_BM - 1) / TE_BM, n_blocks = (Nb + TE_BN - 1) / TE_BN;
+  const int units = te_pair_enabled(Kp) ? sm_count() / 2 : sm_count();
+  const int outer = te_pair_enabled(Kp) ? (m_tiles + 1) / 2 : m_tiles;
+  int segs = 1;
+  if (outer < 4 * units) {
+    segs = (4 * units + outer - 1) / outer;
+    if (segs > n_blocks) segs = n_blocks;
+    if (segs > 64) segs = 64;
+    if (segs < 1) segs = 1;
+  }
+  return 2 * segs;
+}
+
+template <bool kGated>
+static int launch_rowlse(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, const RowLseParams& p,
+                         int segs, const float* gate, cudaStream_t stream) {
+  using Epi = RowLseEpi<kGated>;
+  TeShape g;
+  int rc = make_shape(g, Ma, Nb, Kp);
+  if (rc) return rc;
+  g.segs = segs;
+  g.gate = gate;
+  g.gate_on = 1;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, lda, TE_BM))) return rc;
+  if (te_pair_enabled(Kp)) {
+    if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, 128))) return rc;
+    auto kern2 = te2_kernel<Epi, false>;
+    static bool attr2_done_dev[64] = {};
+    bool& attr2_done = attr2_done_dev[current_device() & 63];
+    if (!attr2_done) {
+      if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, TE2_SMEM_BYTES) != cudaSuccess)
+        return B2_ECUDA;
+      attr2_done = true;
+    }
+    const long long items2 = (long long)((g.m_tiles + 1) / 2) * segs;
+    long long clusters = sm_count() / 2;
+    if (items2 < clusters) clusters = items2;
+    kern2<<<(int)(2 * clusters), TE_THREADS, TE2_SMEM_BYTES, stream>>>(tmA, tmB, g, p);
+    return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+  }
+  if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, ldb, TE_BN))) return rc;
+  auto kern = te_kernel<Epi, false>;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess)
+      return B2_ECUDA;
+    attr_done = true;
+  }
+  const long long items = (long long)g.m_tiles * segs;
+  int grid = sm_count();
+  if (items < grid) grid = (int)items;
+  kern<<<grid, TE_THREADS, TE_SMEM_BYTES, stream>>>(tmA, tmB, g, p);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int logits_rowlse(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, int gated, const float* dyn,
+                  int only_if_stable, float* part, int slots, int* ticket, float* lse2, float* diag, int diag_off,
+                  float* gap, cudaStream_t stream) {
+  if (!dyn || !part || !ticket || !lse2 || slots != rowlse_slots(Ma, Nb, Kp) ||
+      (reinterpret_cast<uintptr_t>(part) & 7) || (gap && !diag))
+    return B2_EINVAL;
+  RowLseParams p{dyn, reinterpret_cast<float2*>(part), ticket, lse2, diag, diag_off, slots, gap};
+  const float* gate = only_if_stable ? dyn + 11 : nullptr;
+  if (gated) return launch_rowlse<true>(A, B, Ma, Nb, Kp, lda, ldb, p, slots / 2, gate, stream);
+  return launch_rowlse<false>(A, B, Ma, Nb, Kp, lda, ldb, p, slots / 2, gate, stream);
 }
 
 // out[i] = (A[i,:] . B[i,:]) with the tensor core's own rounding: bit-identical to the value any S = A B^T tile of the

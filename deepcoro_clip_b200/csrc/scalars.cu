@@ -26,6 +26,11 @@ int dyn_set_siglip(float* dyn, float lclamp, float yneg, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
+int dyn_set_stable(float* dyn, int stable, cudaStream_t s) {
+  dyn_set_stable_kernel<<<1, 32, 0, s>>>(dyn, stable);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
 int lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc, cudaStream_t s) {
   if (n <= 0) return B2_EINVAL;
   lse_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(sums, n, dyn, c, scale_out, acc);
@@ -40,12 +45,13 @@ int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
-int clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif, float* rowscale,
-                  float* colscale, float* loss_out, double* acc_out, cudaStream_t s) {
-  if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out) return B2_EINVAL;
+int clip_finalize(const float* sums, int n, int nvec, const float* dyn, float eps, int gated, const double* unif,
+                  float* rowscale, float* colscale, float* loss_out, double* acc_out, cudaStream_t s) {
+  if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out || (nvec != 3 && nvec != 7)) return B2_EINVAL;
   int blocks = (n + 1023) / 1024;
   if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
-  clip_finalize_kernel<<<blocks, 1024, 0, s>>>(sums, n, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out);
+  clip_finalize_kernel<<<blocks, 1024, 0, s>>>(sums, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out,
+                                               acc_out);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -5,6 +5,8 @@
 
 namespace b2 {
 
+constexpr float kStableWindowBits = 224.f;
+
 __global__ void dyn_prep_kernel(const float* __restrict__ log_temp, const float* __restrict__ bias, float clamp_min,
                                 float bound, float* __restrict__ dyn) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -31,12 +33,26 @@ __global__ void dyn_prep_kernel(const float* __restrict__ log_temp, const float*
   dyn[8] = 30.f;
   dyn[9] = 0.f;
   dyn[10] = 0.f;
+  // Stable softmax mode (selected here, on the device, from tau alone so that every rank of a job takes the same path and
+  // the host never reads tau): the fixed shift keeps every term of every row / column representable only while the whole
+  // range 2*bound*scale2 of the scaled logits fits into the fp32 exponent range next to the offset above
+  // (100 + 126 bits), i.e. tau >= ~0.0128 for unit vectors. Below that (down to the reference's clamp floor 1e-4,
+  // utils/loss/contrastive.py:153, and without any floor for the legacy classes, utils/loss/losses.py:53, 146) the
+  // forward runs per-row / per-column maxima (logits_rowlse) and the backward forms two exponentials that are each <= 1.
+  dyn[11] = (2.f * bound * scale2 > kStableWindowBits) ? 1.f : 0.f;
 }
 
 __global__ void dyn_set_siglip_kernel(float* __restrict__ dyn, float lclamp, float yneg) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   dyn[8] = lclamp;
   dyn[9] = yneg;
+}
+
+// Overrides the mode dyn_prep chose from tau: stable = 1 forces the running-maximum sweeps / two-exponential gradient (valid
+// for every tau), stable = 0 forces the fixed shift (valid only inside its window). For A/B runs and the parity tests.
+__global__ void dyn_set_stable_kernel(float* __restrict__ dyn, int stable) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  dyn[11] = stable ? 1.f : 0.f;
 }
 
 // acc[slot] += sum_r ln( sums[r] ) + ln2*shift2 ;  scale_out[r] = c / sums[r]
@@ -115,11 +131,22 @@ diag_sum_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat1
 }
 
 
-// One launch for the whole scalar tail of the softmax (CLIP / gated) loss forward (utils/loss/contrastive.py:155-164):
-//   sums = [colsum (N) | rowsum (N) | target dots (N)]  (already all-reduced across ranks)
-//   rowscale[i] = c / rowsum[i], colscale[j] = c / colsum[j]  (c = 0.5 / N, the backward's softmax denominators)
-//   loss = c * (sum_i ln rowsum_i + sum_j ln colsum_j + 2 N ln2 shift2) - ((1 - eps) / tau * sum_i f(dot_i) + unif) / N
-// Up to 64 CTAs; every CTA reduces its slice in fp64 and parks three partial sums in a device scratch block, the CTA that
+// One launch for the whole scalar tail of the softmax (CLIP / gated) loss forward (utils/loss/contrastive.py:155-164).
+//   sums = nvec vectors of n floats (already all-reduced across ranks):
+//     [0] colsum            [1] rowsum            [2] target dots S_ii (tensor-core rounding)              (nvec >= 3)
+//     [3] lse2 of the rows  [4] lse2 of the columns (log2 domain, logits_rowlse)
+//     [5] S_ii from the raw features in fp32 (rowdot_raw)   [6] S_ii as the column sweep's tensor core saw it  (nvec == 7)
+//   In the stable mode (dyn[11] != 0, nvec == 7) slots [0] / [1] hold the column / row GAPS lse2 - L2_ii of logits_rowlse.
+// Fixed-shift mode: rowscale[i] = c / rowsum[i], colscale[j] = c / colsum[j] (c = 0.5 / N, the backward's softmax
+//   denominators); row term t_i = ln rowsum_i + ln2 shift2 - L_ii.
+// Stable mode: rowscale[i] = lse2_row[i] - log2 c, colscale likewise (the backward forms c * softmax as
+//   2^(L2 - rowscale) + 2^(L2 - colscale), every exponential <= c); t_i = ln2 * gap_i.
+// Both: L_ii above is the TENSOR-CORE value (it cancels against the same term inside the log-sum-exp when the softmax is
+//   peaked); the fp32 target logit enters as a first-order correction, t_i -= (1 - p_ii) * (L_ii^fp32 - L_ii^tc) with
+//   p_ii = exp(-t_i): the 2^-9 operand rounding of the target pair is not averaged over a row like the errors inside the
+//   log-sum-exp, it was the whole 1e-5 loss error of plain bf16 operands at N <= 16k.
+//   loss = c * sum_i (t_row_i + t_col_i + 2 eps L_ii^fp32) - unif / N        (eps: label smoothing; fp64 inside)
+// Up to 64 CTAs; every CTA reduces its slice in fp64 and parks its partial sums in a device scratch block, the CTA that
 // draws the last ticket adds the partials in CTA order (deterministic) and writes the loss. (Was one CTA: 28 us at
 // N = 32k — 3 % of an 8-GPU step.) The scratch block is shared by all launches of the process: one stream at a time.
 constexpr int FIN_MAX_BLOCKS = 64;
@@ -127,20 +154,43 @@ __device__ double g_fin_partial[3 * FIN_MAX_BLOCKS];
 __device__ unsigned int g_fin_ticket = 0;
 
 __global__ void __launch_bounds__(1024)
-clip_finalize_kernel(const float* __restrict__ sums, int n, const float* __restrict__ dyn, float eps, int gated,
+clip_finalize_kernel(const float* __restrict__ sums, int n, int nvec, const float* __restrict__ dyn, float eps, int gated,
                      const double* __restrict__ unif, float* __restrict__ rowscale, float* __restrict__ colscale,
                      float* __restrict__ loss_out, double* __restrict__ acc_out) {
   const float c = 0.5f / (float)n;
-  const double shift = (double)dyn[6];
+  const double shift = (double)dyn[6], inv_tau = (double)dyn[2];
+  const bool ext = nvec >= 7;
+  const bool stable = ext && dyn[11] != 0.f;
+  const float l2c = log2f(c);
   double a_row = 0.0, a_col = 0.0, a_dot = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float cs = sums[i], rs = sums[n + i];
     const double d = (double)sums[2 * n + i];
-    colscale[i] = c / cs;
-    rowscale[i] = c / rs;
-    a_col += (double)logf(cs) + shift;
-    a_row += (double)logf(rs) + shift;
-    a_dot += gated ? d / (1.0 + exp(-d)) : d;
+    const double fd = gated ? d / (1.0 + exp(-d)) : d;
+    double fx = fd, fdc = fd;                                // fp32 target logit / the column sweep's tensor-core value
+    if (ext) {
+      const double dx = (double)sums[5 * n + i];
+      fx = gated ? dx / (1.0 + exp(-dx)) : dx;
+    }
+    double tr, tc;
+    if (stable) {
+      rowscale[i] = sums[3 * n + i] - l2c;
+      colscale[i] = sums[4 * n + i] - l2c;
+      tr = 0.6931471805599453 * (double)sums[n + i];
+      tc = 0.6931471805599453 * (double)sums[i];
+      const double dc = (double)sums[6 * n + i];
+      fdc = gated ? dc / (1.0 + exp(-dc)) : dc;
+    } else {
+      const float cs = sums[i], rs = sums[n + i];
+      colscale[i] = c / cs;
+      rowscale[i] = c / rs;
+      tr = (double)logf(rs) + shift - fd * inv_tau;
+      tc = (double)logf(cs) + shift - fd * inv_tau;
+    }
+    tr -= (1.0 - exp(-tr)) * (fx - fd) * inv_tau;
+    tc -= (1.0 - exp(-tc)) * (fx - fdc) * inv_tau;
+    a_row += tr;
+    a_col += tc;
+    a_dot += fx;
   }
   __shared__ double sh[3][32];
   __shared__ bool last;
@@ -175,7 +225,7 @@ clip_finalize_kernel(const float* __restrict__ sums, int n, const float* __restr
     }
     g_fin_ticket = 0;                                   // ready for the next launch (stream order)
     const double u = unif ? unif[0] : 0.0;
-    const double loss = (0.5 / n) * (r + cc) - ((1.0 - (double)eps) * d * (double)dyn[2] + u) / n;
+    const double loss = (0.5 / n) * (r + cc) + ((double)eps * d * inv_tau - u) / n;
     loss_out[0] = (float)loss;
     if (acc_out) { acc_out[0] = r; acc_out[1] = cc; acc_out[2] = d; }
   }

@@ -39,7 +39,7 @@ struct SoftplusEpi {
       const float R = fmaf(__uint_as_float(acc[e]), st.inv_tau, st.bias);
       const float L = fminf(fmaxf(R, -st.lc), st.lc);
       const float ex = ex2_approx(-1.4426950408889634f * fabsf(L));
-      const float sp = fmaf(-st.yneg, L, fmaxf(L, 0.f) + 0.6931471805599453f * lg2_approx(1.f + ex));
+      const float sp = fmaf(-st.yneg, L, fmaxf(L, 0.f) + log1p_ex(ex));
       part += (ctx.full || e < nvalid) ? sp : 0.f;
     }
     st.total += (double)part;
@@ -227,12 +227,14 @@ int siglip_compact(const float* mask, long ldm, const float* pw, long ldw, int B
 int siglip_pos(const void* V, int ldv, const void* T, int ldt, int K, int Dp, int D, int hi_off, int B, int Tn, int cap,
                const int* col, const float* y, const float* w, const int* cnt, const float* ysum, const float* dyn,
                float positive_weight, float negative_weight, float c, float gnorm, int hp, int use_pw, int auto_balance,
-               float* dV, int lddv, float* dT, int lddt, double* acc, cudaStream_t s) {
+               float* dV, int lddv, float* dT, int lddt, double* acc, const void* Vraw, int v_dtype, long long ld_vraw,
+               const float* vinv, const void* Traw, int t_dtype, long long ld_traw, const float* tinv, cudaStream_t s) {
   if (B <= 0 || K <= 0 || (K & 1)) return B2_EINVAL;
   if ((dV == nullptr) != (dT == nullptr)) return B2_EINVAL;
+  if ((Vraw && (!vinv || v_dtype < 0 || v_dtype > 2)) || (Traw && (!tinv || t_dtype < 0 || t_dtype > 2))) return B2_EINVAL;
   PosParams p{(const __nv_bfloat16*)V, ldv, (const __nv_bfloat16*)T, ldt, K, Dp, D, hi_off, B, Tn, cap, col, y, w, cnt,
               ysum, dyn, positive_weight, negative_weight, c, gnorm > 0.f ? gnorm : 1.f, hp ? 1 : 0, use_pw, auto_balance, dV, lddv, dT,
-              lddt, acc};
+              lddt, acc, Vraw, v_dtype, ld_vraw, vinv, Traw, t_dtype, ld_traw, tinv};
   siglip_pos_kernel<<<(B + 7) / 8, 256, 0, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }

@@ -175,7 +175,19 @@ struct PosParams {
   float* dV; int lddv;     // may be null (loss only)
   float* dT; int lddt;
   double* acc;
+  // Optional raw features (dtype code 0 fp32 / 1 bf16 / 2 fp16) + 1/max(||x||, eps): the gradient of a positive pair
+  // is then formed with the fp32 normalised partner row x * inv instead of its bf16 operand. A video row has a handful of
+  // positives carrying almost all of its gradient, so the 2^-9 rounding of the operand rows is not averaged away as it is
+  // over the thousands of negatives: it was a flat 1.7e-3 relative gradient error at every size (north_star: 2e-3).
+  const void* Vraw; int v_dtype; long long ld_vraw; const float* vinv;
+  const void* Traw; int t_dtype; long long ld_traw; const float* tinv;
 };
+
+__device__ __forceinline__ float pos_ld(const void* base, int dtype, long long idx) {
+  if (dtype == 0) return static_cast<const float*>(base)[idx];
+  if (dtype == 1) return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[idx]);
+  return __half2float(static_cast<const __half*>(base)[idx]);
+}
 
 __global__ void __launch_bounds__(256) siglip_pos_kernel(PosParams p) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -205,33 +217,53 @@ __global__ void __launch_bounds__(256) siglip_pos_kernel(PosParams p) {
         s = fmaf(a.y, b.y, s);
       }
       s = warp_sum(s);
+      // what the dense pass saw (bf16 operands): removed again below
       const float R = fmaf(s, inv_tau, bias);
       const float L = fminf(fmaxf(R, -lc), lc);
       const float ex = __expf(-fabsf(L));
       const float sp = fmaxf(L, 0.f) + log1pf(ex);
       const float sig = L >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
       const float inr = fabsf(R) <= lc ? 1.f : 0.f;
+      // the pair's true term: cosine from the raw features in fp32 when they are given
+      float sx = s, Lx = L, spx = sp, sigx = sig, inrx = inr;
+      if (p.Vraw && p.Traw) {
+        float a = 0.f;
+        for (int d = lane; d < p.D; d += 32)
+          a = fmaf(pos_ld(p.Vraw, p.v_dtype, (long long)row * p.ld_vraw + d),
+                   pos_ld(p.Traw, p.t_dtype, (long long)j * p.ld_traw + d), a);
+        sx = warp_sum(a) * p.vinv[row] * p.tinv[j];
+        const float Rx = fmaf(sx, inv_tau, bias);
+        Lx = fminf(fmaxf(Rx, -lc), lc);
+        const float exx = __expf(-fabsf(Lx));
+        spx = fmaxf(Lx, 0.f) + log1pf(exx);
+        sigx = Lx >= 0.f ? 1.f / (1.f + exx) : exx / (1.f + exx);
+        inrx = fabsf(Rx) <= lc ? 1.f : 0.f;
+      }
       float w = p.negative_weight;
       if (rule_mask ? yraw > 0.f : yv > 0.5f)
         w = p.auto_balance ? ratio : (use_pw ? pwv * p.positive_weight : p.positive_weight);
-      const float g_full = w * (sig - yv) * inr * p.c;
+      const float g_full = w * (sigx - yv) * inrx * p.c;
       const float g_dense = p.negative_weight * p.c * (sig - yneg) * inr;
       if (lane == 0) {
-        a_loss += (double)((w * (sp - L * yv) - p.negative_weight * (sp - L * yneg)) * p.c);
+        a_loss += (double)((w * (spx - Lx * yv) - p.negative_weight * (sp - L * yneg)) * p.c);
         a_bias += (double)(g_full - g_dense);
-        a_t += (double)((g_full - g_dense) * s);
+        a_t += (double)(g_full * sx - g_dense * s);
       }
       if (p.dV) {
         // the dense tile kernel fed bf16(g_dense * gnorm) (+ the bf16 residual when hp) to the tensor core
         const float gs = g_dense * p.gnorm;
         float gr = __bfloat162float(__float2bfloat16_rn(gs));
         if (p.hp) gr += __bfloat162float(__float2bfloat16_rn(gs - gr));
-        const float dg = (g_full - gr / p.gnorm) * inv_tau;
+        const float dgf = g_full * inv_tau, dgd = gr / p.gnorm * inv_tau;
         float* dv = p.dV + (size_t)row * p.lddv;
         float* dt = p.dT + (size_t)j * p.lddt;
+        const float ti = p.Traw ? p.tinv[j] : 0.f, vi = p.Vraw ? p.vinv[row] : 0.f;
         for (int d = lane; d < p.D; d += 32) {
-          dv[d] += dg * __bfloat162float(tr[p.hi_off + d]);                  // this warp owns row i
-          atomicAdd(dt + d, dg * __bfloat162float(vr[p.hi_off + d]));
+          const float th = __bfloat162float(tr[p.hi_off + d]), vh = __bfloat162float(vr[p.hi_off + d]);
+          const float tx = p.Traw ? pos_ld(p.Traw, p.t_dtype, (long long)j * p.ld_traw + d) * ti : th;
+          const float vx = p.Vraw ? pos_ld(p.Vraw, p.v_dtype, (long long)row * p.ld_vraw + d) * vi : vh;
+          dv[d] += dgf * tx - dgd * th;                                        // this warp owns row i
+          atomicAdd(dt + d, dgf * vx - dgd * vh);
         }
       }
     }

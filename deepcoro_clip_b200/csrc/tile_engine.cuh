@@ -46,7 +46,15 @@ struct TeShape {
   int segs;      // 0: each CTA takes one contiguous range of the (outer, inner) tile order (long sweeps);
                  // s > 0: work items = (outer, segment of the inner sweep), items dealt round-robin to CTAs
   int diag;      // 1: only the tiles crossed by the main diagonal (tile t = A tile t x B block t/2); segs must be 0
+  // Device-side launch gate (optional): the whole grid returns at once unless (*gate != 0) == (gate_on != 0). Lets the host
+  // enqueue both variants of a pass whose choice depends on a device scalar (dyn[11]: stable softmax mode, decided from a
+  // learnable temperature) without ever reading that scalar.
+  const float* gate;
+  int gate_on;
 };
+__device__ __forceinline__ bool te_gate_closed(const TeShape& g) {
+  return g.gate != nullptr && ((*g.gate != 0.f) != (g.gate_on != 0));
+}
 
 // Identical tile sequence for the producer, MMA and epilogue roles of one CTA.
 struct TileSeq {
@@ -106,6 +114,7 @@ template <class Epi, bool kOuterIsB>
 __global__ void __launch_bounds__(TE_THREADS, 1)
 te_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TeShape g,
           typename Epi::Params ep) {
+  if (te_gate_closed(g)) return;     // grid-uniform: before any barrier / TMEM allocation
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

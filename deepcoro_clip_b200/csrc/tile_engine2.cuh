@@ -58,6 +58,7 @@ template <class Epi, bool kOuterIsB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TE_THREADS, 1)
 te2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TeShape g,
            typename Epi::Params ep) {
+  if (te_gate_closed(g)) return;     // grid-uniform (both CTAs of every cluster): before any barrier / TMEM allocation
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res = smem;                             // resident operand panel

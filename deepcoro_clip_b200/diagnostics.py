@@ -45,11 +45,19 @@ def alignment_diagnostics(video_features: torch.Tensor, text_features: torch.Ten
     vop, _, _ = ops.l2norm_operand(video_features.detach(), 0 if x3 else -1)
     K = vop.shape[1]
     dyn = ops.dyn_prep(log_temp, None, 0.0, ops.GATED_BOUND if gated else 1.0)
-    # [colsum (B) | rowsum (B) | S_ii (B)] zeroed (the forward accumulates into the sums) | out (3, padded to 4)
-    ws = torch.zeros(3 * B + 4, dtype=torch.float32, device=dev)
+    # [colsum (B) | rowsum (B) | S_ii (B)] zeroed (the forward accumulates into the sums) | out (3, padded to 4) | row
+    # tickets of the stable sweep (B int32, zero)
+    ws = torch.zeros(4 * B + 4, dtype=torch.float32, device=dev)
     st = ops.stream_ptr(dev)
-    ops.call("logits_lse_fwd", vop, top, B, B, K, vop.stride(0), top.stride(0), 0.0, 0.0, gated, dyn, ws[B:2 * B],
+    # both variants are enqueued, dyn[11] (set from tau on the device) lets exactly one run: the fixed-shift sweep, or the
+    # running-maximum row sweep that leaves the log2-domain row log-sum-exp in the rowsum slot (tau below ~0.013; the
+    # runner applies no temperature floor here, :1332)
+    ops.call("logits_lse_fwd", vop, top, B, B, K, vop.stride(0), top.stride(0), 0.0, 0.0, gated, dyn, 1, ws[B:2 * B],
              ws[:B], ws[2 * B:3 * B], 0, st)
+    slots = ops._lib.lib().b200clip_rowlse_slots(B, B, K)
+    part = torch.empty(2 * B * slots, dtype=torch.float32, device=dev)
+    ops.call("logits_rowlse", vop, top, B, B, K, vop.stride(0), top.stride(0), gated, dyn, 1, part, slots,
+             ws[3 * B + 4:].view(torch.int32), ws[B:2 * B], ws[2 * B:3 * B], 0, None, st)
     out = ws[3 * B:3 * B + 3]
     ops.call("alignment_diag", ws, B, dyn, gated, out, st)
     return {"alignment_cosine": out[0], "alignment_logprob": out[1], "alignment_prob": out[2]}

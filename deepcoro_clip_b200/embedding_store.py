@@ -82,4 +82,4 @@ def epoch_end_retrieval_metrics(video: EmbeddingStore, text: EmbeddingStore, gro
     v = video.gather(group)
     t = text.gather(group)
     gt = gather_tensor_along_batch(ground_truth_indices, group=group)
-    return compute_metrics_streaming(v, t, gt, k_values=list(k_values), group=group)
+    return compute_metrics_streaming(v, t, gt, k_values=list(k_values), use_ddp=True, group=group)

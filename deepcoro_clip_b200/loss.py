@@ -56,7 +56,7 @@ class _ClipLossFn(torch.autograd.Function):
     per pass, ONE all-reduce of [colsum | rowsum | target dots] (3N floats), one finalize kernel for the scalar tail."""
 
     @staticmethod
-    def forward(ctx, video, text, log_temp, label_smoothing, gated, clamp_min, precision, use_ddp, group):
+    def forward(ctx, video, text, log_temp, label_smoothing, gated, clamp_min, precision, use_ddp, group, stable=None):
         dev = ops.require_cuda(video, text, log_temp)
         if video.dim() != 2 or text.dim() != 2 or video.shape != text.shape:
             raise ValueError(
@@ -77,19 +77,41 @@ class _ClipLossFn(torch.autograd.Function):
         vall, v_work = dist_plan.gather_rows_async(vop, W, group)
         K = vop.shape[1]
         dyn = ops.dyn_prep(log_temp, None, clamp_min, ops.GATED_BOUND if gated else 1.0)
+        if stable is not None:              # A/B override of the device-side choice (tests, tools)
+            ops.call("dyn_set_stable", dyn, int(bool(stable)), st)
 
-        # arena: [colsum (N) | rowsum (N) | dots (N)] zeroed (other ranks' slices stay 0 for the all-reduce) | scales (2N)
-        ws = torch.zeros(5 * N + 2, dtype=torch.float32, device=dev)
-        sums = ws[:3 * N]
+        # arena: [colsum (N) | rowsum (N) | dots (N) | lse2 rows (N) | lse2 columns (N) | fp32 dots (N) | column-sweep dots
+        # (N)] zeroed (other ranks' slices stay 0 for the all-reduce) | scales (2N) | tickets of the stable sweeps (2B int32)
+        ws = torch.zeros(9 * N + 2 * B + 2, dtype=torch.float32, device=dev)
+        sums = ws[:7 * N]
         lo = rank * B
+        # target logits S_ii from the raw features in fp32 (local pairs: video row r <-> text row r)
+        vraw, traw = ops._rowmajor(video.detach()), ops._rowmajor(text.detach())
+        ops.call("rowdot_raw", vraw, ops.DTYPE_CODE[vraw.dtype], ops.i64(vraw.stride(0)), vinv, traw,
+                 ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), tinv, B, D, ws[5 * N + lo:5 * N + lo + B], st)
         if t_work is not None:
             t_work.wait()
-        ops.call("logits_lse_fwd", vop, tall, B, N, K, vop.stride(0), tall.stride(0), 0.0, 0.0, int(gated), dyn,
+        # Fixed-shift sweep (row + column sums in one pass) and the stable pair of row-LSE sweeps (running maxima; the
+        # column statistics are the row statistics of the role-swapped problem) are BOTH enqueued: dyn[11], written by
+        # dyn_prep from tau on the device, lets exactly one variant run (the other grid returns at once), so a learnable
+        # temperature is never read by the host. tau >= ~0.013 (every shipped config): fixed shift.
+        ops.call("logits_lse_fwd", vop, tall, B, N, K, vop.stride(0), tall.stride(0), 0.0, 0.0, int(gated), dyn, 1,
                  ws[N + lo:N + lo + B], ws[:N], ws[2 * N + lo:2 * N + lo + B], lo, st)
+        slots = ops._lib.lib().b200clip_rowlse_slots(B, N, K)
+        part = torch.empty(2 * B * slots * 2, dtype=torch.float32, device=dev)
+        tick = ws[9 * N:9 * N + 2 * B].view(torch.int32)
+        ops.call("logits_rowlse", vop, tall, B, N, K, vop.stride(0), tall.stride(0), int(gated), dyn, 1, part[:2 * B * slots],
+                 slots, tick[:B], ws[3 * N + lo:3 * N + lo + B], ws[2 * N + lo:2 * N + lo + B], lo,
+                 ws[N + lo:N + lo + B], st)
+        if v_work is not None:
+            v_work.wait()
+            v_work = None
+        ops.call("logits_rowlse", top, vall, B, N, K, top.stride(0), vall.stride(0), int(gated), dyn, 1, part[2 * B * slots:],
+                 slots, tick[B:], ws[4 * N + lo:4 * N + lo + B], ws[6 * N + lo:6 * N + lo + B], lo, ws[lo:lo + B], st)
         if W > 1:
             dist.all_reduce(sums, group=group)
-        rowscale_all = ws[3 * N:4 * N]
-        colscale_all = ws[4 * N:5 * N]
+        rowscale_all = ws[7 * N:8 * N]
+        colscale_all = ws[8 * N:9 * N]
         unif_tgt = vsum = tsum = None
         if eps != 0.0:
             if gated:
@@ -106,7 +128,7 @@ class _ClipLossFn(torch.autograd.Function):
                 ops.colsum_bf16(tall[:, Kp:2 * Kp], N, D, out=tsum)
             unif_tgt = ((eps / N) * torch.dot(vsum.double(), tsum.double()) * dyn[2].double()).reshape(1)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
-        ops.call("clip_finalize", sums, N, dyn, eps, int(gated), unif_tgt, rowscale_all, colscale_all, loss, None, st)
+        ops.call("clip_finalize", sums, N, 7, dyn, eps, int(gated), unif_tgt, rowscale_all, colscale_all, loss, None, st)
         if v_work is not None:
             v_work.wait()                  # vall is read by the backward only
 
@@ -165,18 +187,22 @@ class _ClipLossFn(torch.autograd.Function):
             dlt = torch.empty(1, dtype=torch.float32, device=dev)
             ops.call("clip_dlogtemp", scal, dyn, gmul, unif_tgt, N, dlt, ops.stream_ptr(dev))
             dLT = (dlt if lt_dtype == torch.float32 else dlt.to(lt_dtype)).reshape(lt_shape)
-        return dV, dT, dLT, None, None, None, None, None, None
+        return dV, dT, dLT, None, None, None, None, None, None, None
 
 
 def clip_loss(video_features, text_features, log_temp, *, label_smoothing: float = 0.0, gated: bool = False,
-              clamp_min: float = 1e-4, precision: str = "auto", use_ddp: bool = True, group=None) -> torch.Tensor:
-    """Functional form of the fused softmax contrastive loss (forward + custom backward)."""
+              clamp_min: float = 1e-4, precision: str = "auto", use_ddp: bool = True, group=None,
+              stable=None) -> torch.Tensor:
+    """Functional form of the fused softmax contrastive loss (forward + custom backward).
+
+    ``stable``: None (default) lets the device choose between the fixed-shift sweep and the running-maximum (stable) sweeps
+    from tau; True / False force one of them (False is only valid inside the fixed-shift window, tau >= ~0.013)."""
     if not isinstance(log_temp, torch.Tensor):
         log_temp = torch.tensor(float(log_temp), device=video_features.device)
     if log_temp.device != video_features.device:
         log_temp = log_temp.to(video_features.device)
     return _ClipLossFn.apply(video_features, text_features, log_temp, label_smoothing, gated, clamp_min, precision,
-                             use_ddp, group)
+                             use_ddp, group, stable)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -387,9 +413,13 @@ class _SigLIPFn(torch.autograd.Function):
         else:
             ops.call("siglip_dense_fwd", vop, top, B, T, K, vop.stride(0), top.stride(0), dyn, acc[1:2], st)
         flags = int(pw is not None) | (2 if cfg["pos_rule_mask"] else 0)
+        # positives: gradient formed with the fp32 normalised partner rows (raw features x 1/norm), not the bf16 operands
+        vraw, traw = ops._rowmajor(video.detach()), ops._rowmajor(text.detach())
         ops.call("siglip_pos", vop, vop.stride(0), top, top.stride(0), K, Kp, D, K - Kp, B, T, cap, col, yv, wv, cnt,
                  ysum, dyn, float(wp), float(wn), float(c), float(gn), int(x3), flags, int(cfg["auto_balance"]), dVh,
-                 D if dVh is not None else 0, dTh, D if dTh is not None else 0, acc[4:7], st)
+                 D if dVh is not None else 0, dTh, D if dTh is not None else 0, acc[4:7],
+                 vraw, ops.DTYPE_CODE[vraw.dtype], ops.i64(vraw.stride(0)), vinv,
+                 traw, ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), tinv, st)
         # local sums -> global (every rank returns the full loss, reference DDP semantics); scalar tails on the device
         red = torch.empty(3, dtype=torch.float64, device=dev)           # loss, dbias, sum G*s
         ops.call("siglip_combine", acc, float(wn * c), red, st)

@@ -85,7 +85,7 @@ def dyn_prep(log_temp: torch.Tensor, bias, clamp_min: float, bound: float) -> to
 
 
 def lse_fwd(A, B, Ma, Nb, K, dyn, gated, rowsum, colsum, diag=None, diag_off=0, diag_corr=None, gnorm=1.0, hp=False):
-    call("logits_lse_fwd", A, B, Ma, Nb, K, A.stride(0), B.stride(0), 0.0, 0.0, int(gated), dyn, rowsum, colsum,
+    call("logits_lse_fwd", A, B, Ma, Nb, K, A.stride(0), B.stride(0), 0.0, 0.0, int(gated), dyn, 0, rowsum, colsum,
          diag, int(diag_off), stream_ptr(A.device))
 
 

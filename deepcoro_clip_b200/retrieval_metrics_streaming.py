@@ -11,8 +11,12 @@ Precision: similarities are fp32-accumulated products of bf16 operands. ``precis
 every input value is exactly representable in bf16 (e.g. the exact-grid evaluation embeddings: results are then
 bit-exact in any summation order) and the error-compensated bf16x3 operands (≈fp32) otherwise.
 
-Multi-GPU: when a process group is initialised the text database is sharded by rows across ranks (every rank
-passes the same full ``text_features``), rank counts are all-reduced and the per-shard top-k lists merged.
+Multi-GPU: the reference calls these functions on RANK 0 ONLY (``if self.config.is_ref_device:`` in
+runners/multitask_runner.py:642 -> :1276), so the reference-signature entry points default to ``use_ddp=False``: one
+process sweeps the whole text set and no collective is issued (a collective here would hang rank 0 forever). Callers
+that invoke them on EVERY rank of a process group (``embedding_store.epoch_end_retrieval_metrics``, ``bench.py``) pass
+``use_ddp=True``: the text database is then sharded by rows across ranks (every rank passes the same full
+``text_features``), rank counts are all-reduced and the per-shard top-k lists merged.
 """
 from __future__ import annotations
 
@@ -152,7 +156,7 @@ def _sweep(vop, top, gt, k: int, use_ddp: bool, group=None, _shard=None):
 
 @torch.no_grad()
 def streaming_topk(video_features, text_features, k: int, *, normalize: bool = False, precision: str = "auto",
-                   use_ddp: bool = True, group=None):
+                   use_ddp: bool = False, group=None):
     """Top-k text indices per video by (similarity desc, index asc): (scores [N,k] fp32, indices [N,k] int64)."""
     ops.require_cuda(video_features, text_features)
     if k < 1 or k > 64:
@@ -166,7 +170,7 @@ def streaming_topk(video_features, text_features, k: int, *, normalize: bool = F
 def compute_recall_at_k_streaming(video_features: torch.Tensor, text_features: torch.Tensor,
                                   ground_truth_indices: torch.Tensor, k_values: List[int] = [1, 5, 10, 50],
                                   video_chunk_size: int = 2048, text_chunk_size: int = 8192, device: str = "cuda",
-                                  *, precision: str = "auto", use_ddp: bool = True, group=None,
+                                  *, precision: str = "auto", use_ddp: bool = False, group=None,
                                   _counts_out: Optional[list] = None) -> Dict[str, float]:
     """Reference :10-101 — Recall@k in PERCENT; inputs are used as given (not normalised)."""
     ops.require_cuda(video_features, text_features)
@@ -202,7 +206,7 @@ def _recall_from_operands(vop, top, gt, k_values, use_ddp, group, counts_out=Non
 def compute_metrics_streaming(video_features: torch.Tensor, text_features: torch.Tensor,
                               ground_truth_indices: torch.Tensor, k_values: List[int] = [1, 5, 10, 50],
                               video_chunk_size: int = 2048, text_chunk_size: int = 8192, device: str = "cuda",
-                              *, precision: str = "auto", use_ddp: bool = True, group=None) -> Dict[str, float]:
+                              *, precision: str = "auto", use_ddp: bool = False, group=None) -> Dict[str, float]:
     """Reference :104-197 — normalises both sides, then Recall@k, MRR_V2T, alignment_score, norms, median_rank."""
     ops.require_cuda(video_features, text_features)
     dev = video_features.device

@@ -68,6 +68,10 @@ int b200clip_l2norm_bwd(const float* dxhat, int ldg, const void* x, int dtype, i
 
 /* out[c] += sum_r operand[r, c]  (label-smoothing helper; out must be zeroed by the caller) */
 int b200clip_colsum_bf16(const void* operand, int ld, int rows, int dim, float* out, void* stream);
+/* out[r] = (a[r, :dim] . b[r, :dim]) * a_inv_norm[r] * b_inv_norm[r]: cosine of pair r from the RAW features in fp32
+ * (the target logit S_ii of utils/loss/contrastive.py:150-162 at fp32 accuracy; dtype codes as in l2norm_fwd). */
+int b200clip_rowdot_raw(const void* a, int a_dtype, int64_t lda, const float* a_inv_norm, const void* b, int b_dtype,
+                        int64_t ldb, const float* b_inv_norm, int rows, int dim, float* out, void* stream);
 /* out[r] = a[r, :K] . b[idx ? idx[r] : r, :K]  (diagonal / ground-truth logits; idx int64 or NULL) */
 int b200clip_rowdot_bf16(const void* a, int lda, const void* b, int ldb, const int64_t* idx, int rows,
                          int b_rows, int K, float* out, void* stream);
@@ -91,10 +95,31 @@ int b200clip_rowdot_tc(const void* a, int lda, const void* b, int ldb, int rows,
  *   it on the device, so a learnable temperature never forces a host synchronisation.
  *   diag (may be NULL): diag[i] = S[i, i + diag_off] as produced by the tensor core (the target logit of row i;
  *   diag_off = rank * B_local under DDP), so target and LSE share one rounding and cancel in the loss.
+ *   skip_if_stable != 0 (with dyn): the launch returns at once when dyn[11] != 0, i.e. when the temperature left the
+ *   window the fixed shift covers and b200clip_logits_rowlse computes the statistics instead (both are enqueued; the
+ *   choice is made on the device, the host never reads tau).
  * ------------------------------------------------------------------------------------------------ */
 int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                            float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag,
-                            int diag_off, void* stream);
+                            float shift2, int gated, const float* dyn, int skip_if_stable, float* rowsum, float* colsum,
+                            float* diag, int diag_off, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2s Stable row log-sum-exp: lse2[i] = log2 sum_j 2^(f(S_ij) * log2(e) / tau) with a running per-row maximum (online
+ *     softmax, tile order outer = A tile so the epilogue thread owns its row), for temperatures down to the reference's
+ *     clamp floor tau = 1e-4 (utils/loss/contrastive.py:153: logits up to +-1e4) and the unclamped legacy classes
+ *     (utils/loss/losses.py:53, 146), where log_softmax's own max subtraction keeps the reference finite. The column
+ *     statistics of the symmetric loss are the row statistics of the role-swapped call (A = text, B = video).
+ *   part  : float[Ma][slots][2] scratch, slots = b200clip_rowlse_slots(Ma, Nb, Kp); ticket: int32[Ma], ZERO on entry
+ *           (left zero on exit); the last partial of a row merges them, so lse2 is complete when the launch ends.
+ *   only_if_stable != 0: the launch returns at once unless dyn[11] != 0 (see b200clip_dyn_prep).
+ *   diag (may be NULL): diag[i] = S[i, i + diag_off] with the tensor core's rounding, as in logits_lse_fwd.
+ *   gap (may be NULL; needs diag): gap[i] = lse2[i] - L2_ii formed as (max - L2_ii) + log2(sum) — no cancellation between
+ *           two numbers of the size of the logits; this is the loss term of row i in the log2 domain.
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_rowlse_slots(int Ma, int Nb, int Kp);
+int b200clip_logits_rowlse(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, int gated,
+                           const float* dyn, int only_if_stable, float* part, int slots, int32_t* ticket, float* lse2,
+                           float* diag, int diag_off, float* gap, void* stream);
 
 /* Validation hook: out[i, j] = S_ij (fp32, row pitch ldo) computed by the same tcgen05 tile engine.
  * max_ctas > 0 limits the grid (exercises the multi-tile-per-CTA schedule). Used by the tests only. */
@@ -107,6 +132,10 @@ int b200clip_logits_dump(const void* A, const void* B, int Ma, int Nb, int Kp, i
  *       dX[i, :D] += out_scale * sum_j G_ij * Y[j, :D],   S = X Y^T recomputed per 128x128 tile.
  *     mode 0 (CLIP)   : G = 2^(S*scale2 - shift2) * (rowscale[i] + colscale[j])
  *     mode 1 (gated)  : same with f(S) = S*sigmoid(S) inside the exponent and G *= f'(S)
+ *     modes 0/1 in the stable mode (dyn given and dyn[11] != 0, see b200clip_dyn_prep / b200clip_clip_finalize):
+ *                       G = 2^(f(S)*scale2 - rowscale[i]) + 2^(f(S)*scale2 - colscale[j]) — rowscale / colscale then
+ *                       hold log2-domain log-sum-exps, each exponential is a softmax probability times c <= c
+ *                       (utils/loss/contrastive.py:153-162 at tau down to 1e-4; the choice is made on the device)
  *     mode 2 (SigLIP) : R = S*inv_tau + bias, G = wneg_c * (sigmoid(clamp(R,+-lc)) - yneg) * [|R| <= lc]; lc = dyn[8]
  *                       (30), yneg = dyn[9] (label-smoothing target of the non-positive pairs, default 0)
  *     mode 3 (SigLIP + entropy regulariser, utils/loss/contrastive.py:19-68, 306-313): mode 2 plus
@@ -137,8 +166,8 @@ int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, 
  * Device-side scalar plumbing (no host sync on log_temp / bias).
  *   dyn_prep     : tau = exp(log_temp) [clamped at clamp_min if > 0: contrastive.py:153, 266]; bound = max of
  *                  f(S) (1 for plain, 0.7311 for gated). dyn = {log2e/tau, shift2, 1/tau, tau, clamped, bias,
- *                  ln2*shift2, 1-clamped, logit clamp = 30, negative target = 0, entropy coefficient = 0, ...}
- *                  (float[16]).
+ *                  ln2*shift2, 1-clamped, logit clamp = 30, negative target = 0, entropy coefficient = 0,
+ *                  stable softmax mode = [2 * bound * log2e / tau > 224 bits], ...} (float[16]).
  *   dyn_set_siglip : overrides dyn[8] (logit clamp; 3e38 = the SigLIP2 BCE variants that do not clamp,
  *                  utils/loss/siglip2_bce.py:88-90) and dyn[9] (label smoothing eps/2, siglip2_bce.py:98-99).
  *   lse_finalize : acc[0] += sum_r (ln sums[r] + ln2*shift2)  (double) ; scale_out[r] = c / sums[r]
@@ -147,6 +176,9 @@ int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, 
 int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn,
                       void* stream);
 int b200clip_dyn_set_siglip(float* dyn, float logit_clamp, float neg_target, void* stream);
+/* Overrides the softmax mode dyn_prep chose from tau (dyn[11]): stable = 1 is valid for every tau, stable = 0 only inside
+ * the fixed-shift window. For A/B measurements and the parity tests of the two modes against each other. */
+int b200clip_dyn_set_stable(float* dyn, int stable, void* stream);
 int b200clip_lse_finalize(const float* sums, int n, const float* dyn, float c, float* scale_out, double* acc,
                           void* stream);
 /* acc[0] += sum_i f(v[i]) in double, f = identity (gated = 0) or s*sigmoid(s) (gated = 1) */
@@ -154,13 +186,20 @@ int b200clip_vec_fsum(const float* v, int n, int gated, double* acc, void* strea
 int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots,
                       double* acc, void* stream);
 /* The whole scalar tail of the softmax-CE forward in ONE launch (replaces 2x cross_entropy's reductions and the
- * scalar arithmetic of utils/loss/contrastive.py:155-164; losses.py:56-62):
- *   sums = [colsum (n) | rowsum (n) | target dots S_ii (n)] as produced by logits_lse_fwd (all-reduced across ranks);
- *   rowscale[i] = c / rowsum[i], colscale[j] = c / colsum[j], c = 0.5 / n;
- *   loss_out[0] = c * (sum ln rowsum + sum ln colsum) - ((1 - eps) / tau * sum f(S_ii) + unif[0]) / n  (fp64 inside);
+ * scalar arithmetic of utils/loss/contrastive.py:155-164; losses.py:56-62). sums = nvec vectors of n floats, all-reduced
+ * across ranks by the caller:
+ *   [0] colsum  [1] rowsum  [2] target dots S_ii with the tensor core's rounding         (logits_lse_fwd; nvec = 3 or 7)
+ *   [3] lse2 rows  [4] lse2 columns (logits_rowlse)  [5] S_ii from the raw features in fp32 (rowdot_raw)
+ *   [6] S_ii as the column sweep's tensor core produced it                                               (nvec = 7)
+ *   Stable mode (nvec = 7 and dyn[11] != 0): [0] / [1] hold the column / row gaps of logits_rowlse instead of the sums.
+ * Fixed shift: rowscale[i] = c / rowsum[i], colscale[j] = c / colsum[j], c = 0.5 / n; row term t_i = ln rowsum_i +
+ *   ln2 shift2 - L_ii. Stable: rowscale[i] = lse2_row[i] - log2 c, colscale likewise (b200clip_logits_bwd then forms
+ *   c * softmax as 2^(L2 - rowscale) + 2^(L2 - colscale), every exponential <= c); t_i = ln2 gap_i.
+ * nvec = 7: the fp32 target logit enters as t_i -= (1 - exp(-t_i)) (L_ii^fp32 - L_ii^tensor-core).
+ *   loss_out[0] = c sum_i (t_row_i + t_col_i + 2 eps L_ii) - unif[0] / n   (fp64 inside);
  *   unif (may be NULL): label-smoothing uniform-target term; acc_out (may be NULL): the three fp64 sums.
  * clip_dlogtemp: out[0] = (unif / n - scal0[0] / tau) * [tau not clamped] * gmul[0]  (d loss / d log_temp). */
-int b200clip_clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif,
+int b200clip_clip_finalize(const float* sums, int n, int nvec, const float* dyn, float eps, int gated, const double* unif,
                            float* rowscale, float* colscale, float* loss_out, double* acc_out, void* stream);
 int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
                            float* out, void* stream);
@@ -185,6 +224,10 @@ int b200clip_alignment_diag(const float* sums, int n, const float* dyn, int gate
  *                      use_pos_weights: bit 0 = multiply by the per-pair pos_weights; bit 1 = weight rule
  *                      "pos_mask > 0" (utils/loss/siglip_pairwise.py:352) instead of "target > 0.5". Targets are
  *                      smoothed with dyn[9]: y (1 - 2 yneg) + yneg.
+ *                      video_raw / text_raw (may be NULL; dtype codes as in l2norm_fwd) with their inv_norm vectors: the
+ *                      gradient of a positive pair is formed with the fp32 normalised partner row instead of its bf16
+ *                      operand (a row's few positives carry most of its gradient; their operand rounding is not
+ *                      averaged away like that of the negatives).
  *   Entropy regulariser (contrastive.py:19-68; compute_entropy_regularization), three passes over L = clamp(R):
  *   siglip_entropy_rowsum : Z[i] += sum_j exp(L_ij - 30)                                  (caller zeroes Z)
  *   siglip_entropy_stats  : p = exp(L - 30) / Z_i ; H[i] += -sum_j p ln(p + 1e-10) ; Q[i] += sum_j p^2 / (p + 1e-10)
@@ -223,6 +266,8 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
                         int T, int cap, const int32_t* col, const float* y, const float* w, const int32_t* cnt,
                         const float* ysum, const float* dyn, float positive_weight, float negative_weight, float c,
                         float gnorm, int hp, int use_pos_weights, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc,
+                        const void* video_raw, int video_dtype, int64_t ld_video_raw, const float* video_inv_norm,
+                        const void* text_raw, int text_dtype, int64_t ld_text_raw, const float* text_inv_norm,
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------

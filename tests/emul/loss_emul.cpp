@@ -67,16 +67,44 @@ extern "C" int b200clip_colsum_bf16(const void* xh, int ld, int rows, int dim, f
   return 0;
 }
 
+template <typename TA>
+static int rowdot_raw_t(const TA* a, long long lda, const float* ainv, const void* b, int bdtype, long long ldb,
+                        const float* binv, int rows, int dim, float* out) {
+  const int blocks = (rows + 7) / 8;
+  switch (bdtype) {
+    case 0: emul::launch(blocks, 256, [&] { rowdot_raw_kernel<TA, float>(a, lda, ainv, (const float*)b, ldb, binv, rows, dim, out); }); break;
+    case 1: emul::launch(blocks, 256, [&] { rowdot_raw_kernel<TA, bf16>(a, lda, ainv, (const bf16*)b, ldb, binv, rows, dim, out); }); break;
+    case 2: emul::launch(blocks, 256, [&] { rowdot_raw_kernel<TA, __half>(a, lda, ainv, (const __half*)b, ldb, binv, rows, dim, out); }); break;
+    default: return -22;
+  }
+  return 0;
+}
+extern "C" int b200clip_rowdot_raw(const void* a, int adtype, long long lda, const float* ainv, const void* b, int bdtype,
+                                   long long ldb, const float* binv, int rows, int dim, float* out, void*) {
+  if (rows <= 0 || dim <= 0 || !a || !b || !ainv || !binv || !out) return -22;
+  switch (adtype) {
+    case 0: return rowdot_raw_t<float>((const float*)a, lda, ainv, b, bdtype, ldb, binv, rows, dim, out);
+    case 1: return rowdot_raw_t<bf16>((const bf16*)a, lda, ainv, b, bdtype, ldb, binv, rows, dim, out);
+    case 2: return rowdot_raw_t<__half>((const __half*)a, lda, ainv, b, bdtype, ldb, binv, rows, dim, out);
+    default: return -22;
+  }
+}
+
 extern "C" int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn, void*) {
   emul::launch(1, 32, [&] { dyn_prep_kernel(log_temp, bias, clamp_min, bound, dyn); });
   return 0;
 }
-extern "C" int b200clip_clip_finalize(const float* sums, int n, const float* dyn, float eps, int gated, const double* unif,
-                                      float* rowscale, float* colscale, float* loss_out, double* acc_out, void*) {
-  if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out) return -22;
+extern "C" int b200clip_dyn_set_stable(float* dyn, int stable, void*) {
+  emul::launch(1, 32, [&] { dyn_set_stable_kernel(dyn, stable); });
+  return 0;
+}
+extern "C" int b200clip_clip_finalize(const float* sums, int n, int nvec, const float* dyn, float eps, int gated,
+                                      const double* unif, float* rowscale, float* colscale, float* loss_out, double* acc_out,
+                                      void*) {
+  if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out || (nvec != 3 && nvec != 7)) return -22;
   int blocks = (n + 1023) / 1024;
   if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
-  emul::launch(blocks, 1024, [&] { clip_finalize_kernel(sums, n, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out); });
+  emul::launch(blocks, 1024, [&] { clip_finalize_kernel(sums, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out); });
   return 0;
 }
 extern "C" int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
@@ -90,9 +118,10 @@ extern "C" int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, con
 static inline float gate(float s) { return s / (1.f + expf(-s)); }
 
 extern "C" int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, float scale2,
-                                       float shift2, int gated, const float* dyn, float* rowsum, float* colsum, float* diag,
-                                       int diag_off, void*) {
+                                       float shift2, int gated, const float* dyn, int skip_if_stable, float* rowsum,
+                                       float* colsum, float* diag, int diag_off, void*) {
   if (dyn) { scale2 = dyn[0]; shift2 = dyn[1]; }
+  if (dyn && skip_if_stable && dyn[11] != 0.f) return 0;          // launch gate: the stable sweeps run instead
   for (int i = 0; i < Ma; ++i)
     for (int j = 0; j < Nb; ++j) {
       float s = 0.f;
@@ -102,6 +131,36 @@ extern "C" int b200clip_logits_lse_fwd(const void* A, const void* B, int Ma, int
       rowsum[i] += p;
       colsum[j] += p;
     }
+  return 0;
+}
+
+// Model of the stable row log-sum-exp sweep (contract: include/b200clip.h K2s): lse2[i] = log2 sum_j 2^(f(S_ij) scale2),
+// with a per-row maximum; the ticket array must arrive zeroed and is left zeroed.
+extern "C" int b200clip_rowlse_slots(int, int, int) { return 2; }
+extern "C" int b200clip_logits_rowlse(const void* A, const void* B, int Ma, int Nb, int Kp, int lda, int ldb, int gated,
+                                      const float* dyn, int only_if_stable, float* part, int slots, int* ticket, float* lse2,
+                                      float* diag, int diag_off, float* gap, void*) {
+  if (!dyn || !part || !ticket || !lse2 || slots != 2 || (gap && !diag)) return -22;
+  if (only_if_stable && dyn[11] == 0.f) return 0;
+  const float scale2 = dyn[0];
+  std::vector<float> l(Nb);
+  for (int i = 0; i < Ma; ++i) {
+    if (ticket[i] != 0) return -22;
+    float m = -INFINITY;
+    for (int j = 0; j < Nb; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < Kp; ++k) s = fmaf(bf(A, (long long)i * lda + k), bf(B, (long long)j * ldb + k), s);
+      if (diag && i + diag_off == j) diag[i] = s;
+      l[j] = (gated ? gate(s) : s) * scale2;
+      m = fmaxf(m, l[j]);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < Nb; ++j) sum += exp2f(l[j] - m);
+    part[(size_t)i * 4] = m;
+    part[(size_t)i * 4 + 1] = sum;
+    lse2[i] = m + log2f(sum);
+    if (gap) gap[i] = (m - (gated ? gate(diag[i]) : diag[i]) * scale2) + log2f(sum);
+  }
   return 0;
 }
 
@@ -151,8 +210,10 @@ extern "C" int b200clip_logits_bwd(int mode, const void* X, const void* Y, int N
     return 0;
   }
   double tsum = 0.0;
+  const bool stable = dyn && dyn[11] != 0.f;          // rowscale / colscale hold log2-domain log-sum-exps (minus log2 c)
+  const float lg = log2f(gnorm);
   for (int i = 0; i < Nx; ++i) {
-    const float rs = rowscale[i] * gnorm;
+    const float rs = stable ? rowscale[i] - lg : rowscale[i] * gnorm;
     for (int j = 0; j < Ny; ++j) {
       float s = 0.f;
       for (int k = 0; k < Kp; ++k) s = fmaf(bf(X, (long long)i * ldx + k), bf(Y, (long long)j * ldy + k), s);
@@ -162,7 +223,8 @@ extern "C" int b200clip_logits_bwd(int mode, const void* X, const void* Y, int N
         f = s * sig;
         fp = sig * (1.f + s * (1.f - sig));
       }
-      float g = exp2f(fmaf(f, scale2, -shift2)) * (rs + colscale[j] * gnorm);
+      float g = stable ? exp2f(f * scale2 - rs) + exp2f(f * scale2 - (colscale[j] - lg))
+                       : exp2f(fmaf(f, scale2, -shift2)) * (rs + colscale[j] * gnorm);
       const bool on_diag = ydiag != 0.f && i + diag_off == j;
       if (on_diag) g -= ydn;
       tsum += (double)g * (double)f;
@@ -223,11 +285,14 @@ extern "C" int b200clip_siglip_compact(const float* mask, long long ldm, const f
 extern "C" int b200clip_siglip_pos(const void* V, int ldv, const void* T, int ldt, int K, int Dp, int D, int hi_off, int B, int Tn,
                                    int cap, const int* col, const float* y, const float* w, const int* cnt, const float* ysum,
                                    const float* dyn, float positive_weight, float negative_weight, float c, float gnorm, int hp,
-                                   int use_pw, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc, void*) {
+                                   int use_pw, int auto_balance, float* dV, int lddv, float* dT, int lddt, double* acc,
+                                   const void* Vraw, int v_dtype, long long ld_vraw, const float* vinv, const void* Traw,
+                                   int t_dtype, long long ld_traw, const float* tinv, void*) {
   if (B <= 0 || K <= 0 || (K & 1)) return -22;
   if ((dV == nullptr) != (dT == nullptr)) return -22;
   PosParams p{(const bf16*)V, ldv, (const bf16*)T, ldt, K, Dp, D, hi_off, B, Tn, cap, col, y, w, cnt, ysum, dyn, positive_weight,
-              negative_weight, c, gnorm > 0.f ? gnorm : 1.f, hp ? 1 : 0, use_pw, auto_balance, dV, lddv, dT, lddt, acc};
+              negative_weight, c, gnorm > 0.f ? gnorm : 1.f, hp ? 1 : 0, use_pw, auto_balance, dV, lddv, dT, lddt, acc,
+              Vraw, v_dtype, ld_vraw, vinv, Traw, t_dtype, ld_traw, tinv};
   emul::launch((B + 7) / 8, 256, [&] { siglip_pos_kernel(p); });
   return 0;
 }

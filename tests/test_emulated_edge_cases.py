@@ -97,26 +97,38 @@ def test_clip_loss_shape_errors_and_tiny_batches(loss_mod):
     assert abs(loss.item() - o["loss"]) <= 1e-5 * abs(o["loss"]) and lt.grad.item() == 0.0
 
 
-def test_known_gap_fixed_shift_range_at_the_reference_clamp_floor(loss_mod):
-    """the forward uses ONE exponent shift tied to the bound S <= 1, not a per-row maximum. With the reference's
-    clamp floor tau = 1e-4 the logits span +-10^4 and every term of a row whose best cosine is below ~0.98 underflows fp32:
-    the loss is non-finite where the reference returns a finite value (golden clip_clamp_b8_d64). The failure is loud
-    (inf / NaN, never a wrong finite number); this test pins that, and the safe range, until the stable two-exponential
-    epilogue lands."""
+def test_stable_mode_at_the_reference_clamp_floor(loss_mod):
+    """The reference clamps tau only at 1e-4 (utils/loss/contrastive.py:153): logits span +-10^4 and log_softmax's own max
+    subtraction keeps it finite (golden clip_clamp_b8_d64, loss 1367.8). The fixed exponent shift of the fast sweep cannot
+    represent that range, so dyn_prep switches (on the device, from tau) to the stable mode: running-maximum row sweeps in the
+    forward, two exponentials <= 1 in the backward. Host flow + shipped scalar kernels + contract models here; the kernels
+    themselves are checked by tests/test_gpu_clip_loss.py on the same golden."""
     from tests.conftest import GOLDEN
     g = np.load(GOLDEN / "clip_clamp_b8_d64.npz")
-    loss = loss_mod.CLIPLoss()(video_features=torch.tensor(g["video"], dtype=torch.float32),
-                               text_features=torch.tensor(g["text"], dtype=torch.float32),
-                               log_temp=torch.tensor(g["log_temp"].astype(np.float32)))
-    assert not math.isfinite(loss.item())
-    assert math.isfinite(float(g["f32_loss"]))
-    # inside the range (1 - max cosine of the row) * log2(e) / tau <= ~226 bits the same inputs (uncorrelated pairs, best
-    # cosine of some rows only 0.05) are accurate to 1e-6: tau >= 0.006 here, far below every shipped config (0.0588 ... 0.1)
-    for tau in (0.006, 0.02):
-        o = co.clip_loss(g["video"], g["text"], math.log(tau))
-        ours = loss_mod.clip_loss(torch.tensor(g["video"], dtype=torch.float32), torch.tensor(g["text"], dtype=torch.float32),
-                                  math.log(tau))
+    v = torch.tensor(g["video"], dtype=torch.float32, requires_grad=True)
+    t = torch.tensor(g["text"], dtype=torch.float32, requires_grad=True)
+    lt = torch.tensor(g["log_temp"].astype(np.float32), requires_grad=True)
+    loss = loss_mod.CLIPLoss()(video_features=v, text_features=t, log_temp=lt)
+    loss.backward()
+    ref = float(g["f32_loss"])
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref), (loss.item(), ref)
+    for got, key in ((v.grad, "f32_dvideo"), (t.grad, "f32_dtext")):
+        assert np.linalg.norm(got.numpy() - g[key]) <= 2e-3 * np.linalg.norm(g[key]), key
+    assert lt.grad.item() == 0.0                                  # the clamp is active: no temperature gradient
+    # both sides of the switch (tau = 0.0128 for unit vectors), the unclamped legacy class far below it, label smoothing
+    for tau, kw in ((0.006, {}), (0.012, {}), (0.014, {}), (0.02, {}), (0.001, {"clamp_min": 0.0}),
+                    (0.004, {"label_smoothing": 0.1})):
+        o = co.clip_loss(g["video"], g["text"], math.log(tau), label_smoothing=kw.get("label_smoothing", 0.0),
+                         clamp_min=None if kw.get("clamp_min") == 0.0 else 1e-4)
+        v = torch.tensor(g["video"], dtype=torch.float32, requires_grad=True)
+        t = torch.tensor(g["text"], dtype=torch.float32, requires_grad=True)
+        lt = torch.tensor([math.log(tau)], dtype=torch.float32, requires_grad=True)
+        ours = loss_mod.clip_loss(v, t, lt, **kw)
+        ours.backward()
         assert abs(ours.item() - o["loss"]) <= 1e-5 * abs(o["loss"]), tau
+        assert np.linalg.norm(v.grad.numpy() - o["dvideo"]) <= 2e-3 * np.linalg.norm(o["dvideo"]), tau
+        assert np.linalg.norm(t.grad.numpy() - o["dtext"]) <= 2e-3 * np.linalg.norm(o["dtext"]), tau
+        assert abs(lt.grad.item() - o["dlog_temp"]) <= 2e-3 * max(abs(o["dlog_temp"]), 1e-3), tau
 
 
 def test_label_smoothing_at_tiny_batches(loss_mod):

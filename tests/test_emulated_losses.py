@@ -52,6 +52,7 @@ def patch_package(so, setattr_=setattr):
     setattr_(ops, "require_cuda", lambda *t: torch.device("cpu"))
     setattr_(ops, "call", call)
     setattr_(ops, "stream_ptr", lambda dev=None: 0)
+    setattr_(_lib, "lib", lambda: emul)          # size queries (b200clip_rowlse_slots) go to the emulated library as well
     return loss
 
 

@@ -77,9 +77,18 @@ def _shards_body(rank, world):
     rms = patch_retrieval(build_emul())
     g = np.load(GOLDEN / "retrieval_grid_257x300.npz")
     v, t = torch.tensor(g["video"]), torch.tensor(g["text"])
-    r = rms.compute_recall_at_k_streaming(v, t, torch.tensor(g["gt"]), k_values=[1, 5, 10], device="cpu")
-    s, i = rms.streaming_topk(v, t, 10)
-    return (r, s.numpy(), i.numpy())
+    r = rms.compute_recall_at_k_streaming(v, t, torch.tensor(g["gt"]), k_values=[1, 5, 10], device="cpu", use_ddp=True)
+    s, i = rms.streaming_topk(v, t, 10, use_ddp=True)
+    # the reference calls the metrics on rank 0 ONLY (runners/multitask_runner.py:642 -> :1276): with the default
+    # arguments the installed function must not enter a collective, and must sweep the WHOLE text set on its own
+    solo = None
+    if rank == 0:
+        solo = rms.compute_recall_at_k_streaming(v, t, torch.tensor(g["gt"]), k_values=[1, 5, 10], video_chunk_size=64,
+                                                 text_chunk_size=64, device="cpu")
+        m = rms.compute_metrics_streaming(v, t, torch.tensor(g["gt"]), k_values=[1, 5])      # must not hang either
+        assert set(m) >= {"Recall@1", "MRR_V2T", "alignment_score"}
+    dist.barrier()
+    return (r, s.numpy(), i.numpy(), solo)
 
 
 def _store_body(rank, world):
@@ -126,9 +135,12 @@ def test_text_shards_two_ranks_gloo(gloo_results):
     ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
     ov, oi = ro.topk_lowest_index(ro.similarity(g["video"], g["text"]), 10)
     for r in range(world):
-        rec, s, i = out[r]
+        rec, s, i, solo = out[r]
         assert rec == {k: ref[k] for k in rec}
         assert (i == oi).all() and (s == ov).all()
+    solo = out[0][3]                   # rank-0-only call inside the initialised group: full sweep, no hang
+    assert out[1][3] is None and {k: solo[k] for k in ("Recall@1", "Recall@5", "Recall@10")} == \
+        {k: ref[k] for k in ("Recall@1", "Recall@5", "Recall@10")}
 
 
 def test_epoch_end_embedding_stores_two_ranks_gloo(gloo_results):

@@ -38,6 +38,8 @@ def _run(mod, v, t, lt):
 CASES = {
     "clip_c1_b64_d512": ("CLIPLoss", {}),
     "clip_ls_b48_d96": ("CLIPLoss", {"label_smoothing": 0.1}),
+    # tau clamped at the reference's floor 1e-4 (contrastive.py:153): logits +-1e4, stable softmax mode on the device
+    "clip_clamp_b8_d64": ("CLIPLoss", {}),
     "clip_b300_d200": ("CLIPLoss", {}),
     "contrastive_legacy_b32_d128": ("ContrastiveLoss", {}),
     "gated_siglip_legacy_b40_d128": ("SiglipLoss", {}),
@@ -69,13 +71,76 @@ def test_clip_vs_oracle(N, D, tau, prec):
     lt = math.log(tau)
     loss, dv, dt, dlt = _run(CLIPLoss(precision=prec), v, t, lt)
     o = co.clip_loss(v, t, lt)
-    # plain bf16 operands perturb each logit by ~1e-4/tau; the N-average keeps the loss within a few 1e-5
-    tol = LOSS_RTOL if prec != "bf16" else 1e-4
-    assert abs(loss - o["loss"]) <= tol * abs(o["loss"]), (loss, o["loss"])
-    gt = GRAD_RTOL if prec != "bf16" else 6e-3
+    # plain bf16 operands perturb each logit by ~1e-4/tau, but the target logits enter in fp32 and the errors inside the
+    # log-sum-exps average out: 1e-5 for every precision
+    assert abs(loss - o["loss"]) <= LOSS_RTOL * abs(o["loss"]), (loss, o["loss"])
+    gt = GRAD_RTOL
     assert _rel(dv, o["dvideo"]) <= gt
     assert _rel(dt, o["dtext"]) <= gt
     assert abs(dlt - o["dlog_temp"]) <= gt * max(abs(o["dlog_temp"]), 1e-3)
+
+
+def _small_tau_tol(ref, tau):
+    """1e-5 relative (north_star) plus ONE fp32 ulp of the largest logit 1/tau: the loss of an almost separated batch is a
+    difference of logits of that size, which the fp32 reference itself resolves no better than this (its log_softmax
+    subtracts fp32 logits S / tau). The checker is the float64 oracle."""
+    return LOSS_RTOL * abs(ref) + 2.0 ** -23 / tau
+
+
+@pytest.mark.parametrize("N,D,tau,kw", [
+    (300, 200, 0.012, {}), (300, 200, 0.004, {}), (257, 64, 0.001, {}), (64, 512, 2e-4, {}),
+    (130, 96, 0.005, {"label_smoothing": 0.1}), (1500, 512, 0.006, {}),
+])
+def test_small_tau_stable_mode_vs_oracle(N, D, tau, kw):
+    """Temperatures below the fixed-shift window (tau < ~0.0128), down to the reference's floor: the device switches to
+    the running-maximum forward sweeps and the two-exponential backward. bf16x3 operands (precision='auto' at these
+    sizes): at 1/tau up to 5000 the operand rounding of plain bf16 alone would move every logit by ~0.1-1."""
+    from deepcoro_clip_b200.loss import CLIPLoss
+    rng = np.random.default_rng(N + D)
+    v = rng.standard_normal((N, D)).astype(np.float32)
+    t = (0.5 * v + rng.standard_normal((N, D))).astype(np.float32)
+    lt = math.log(tau)
+    loss, dv, dt, dlt = _run(CLIPLoss(**kw), v, t, lt)
+    o = co.clip_loss(v, t, lt, **kw)
+    assert math.isfinite(loss) and abs(loss - o["loss"]) <= _small_tau_tol(o["loss"], tau), (loss, o["loss"])
+    assert _rel(dv, o["dvideo"]) <= GRAD_RTOL and _rel(dt, o["dtext"]) <= GRAD_RTOL
+    assert abs(dlt - o["dlog_temp"]) <= GRAD_RTOL * max(abs(o["dlog_temp"]), 1e-3)
+
+
+@pytest.mark.parametrize("cls,tau", [("ContrastiveLoss", 0.003), ("SiglipLoss", 0.002), ("SiglipLoss", 0.0005)])
+def test_small_tau_legacy_classes(cls, tau):
+    """The legacy classes apply no temperature floor at all (utils/loss/losses.py:53, 146, 198)."""
+    from deepcoro_clip_b200 import loss as L
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal((200, 128)).astype(np.float32)
+    t = (0.5 * v + rng.standard_normal((200, 128))).astype(np.float32)
+    loss, dv, dt, dlt = _run(getattr(L, cls)(), v, t, math.log(tau))
+    o = co.clip_loss(v, t, math.log(tau), clamp_min=None, gated=cls == "SiglipLoss")
+    assert math.isfinite(loss) and abs(loss - o["loss"]) <= _small_tau_tol(o["loss"], tau), (loss, o["loss"])
+    assert _rel(dv, o["dvideo"]) <= GRAD_RTOL and _rel(dt, o["dtext"]) <= GRAD_RTOL
+    assert abs(dlt - o["dlog_temp"]) <= GRAD_RTOL * max(abs(o["dlog_temp"]), 1e-3)
+
+
+@pytest.mark.parametrize("N,D,prec", [(2048, 512, "bf16"), (1000, 768, "bf16"), (700, 128, "bf16"), (500, 200, "bf16x3"),
+                                      (900, 384, "bf16")])
+def test_stable_mode_equals_fixed_shift_mode_inside_the_window(N, D, prec):
+    """Both modes are valid at tau = 0.0588: forcing the stable sweeps / two-exponential gradient through every backward
+    kernel family (64-row pairs, 128-row pairs, single CTA) must reproduce the fixed-shift results on the same operands."""
+    from deepcoro_clip_b200.loss import clip_loss
+    g = torch.Generator().manual_seed(N)
+    v0 = torch.randn(N, D, generator=g); t0 = 0.5 * v0 + torch.randn(N, D, generator=g)
+    res = []
+    for stable in (False, True):
+        v = v0.to(DEV).requires_grad_(True); t = t0.to(DEV).requires_grad_(True)
+        lt = torch.tensor([math.log(0.0588)], device=DEV, requires_grad=True)
+        loss = clip_loss(v, t, lt, precision=prec, stable=stable)
+        loss.backward()
+        res.append((loss.item(), v.grad.clone(), t.grad.clone(), lt.grad.item()))
+    (l0, dv0, dt0, g0), (l1, dv1, dt1, g1) = res
+    assert abs(l0 - l1) <= 2e-6 * abs(l0), (l0, l1)
+    # the same bf16 gradient operand up to the rounding of two differently formed fp32 values
+    assert ((dv0 - dv1).norm() / dv0.norm()).item() <= 1e-3 and ((dt0 - dt1).norm() / dt0.norm()).item() <= 1e-3
+    assert abs(g0 - g1) <= 1e-4 * abs(g0)
 
 
 def test_clip_no_grad_and_bf16_inputs():

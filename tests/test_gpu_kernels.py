@@ -70,7 +70,7 @@ def test_logits_lse_fwd_sums_and_diag(Ma, Nb, D, gated):
     diag = torch.zeros(Ma, device=DEV)
     bound = 0.7310585786300049 if gated else 1.0
     scale2 = LOG2E / tau
-    L.call("logits_lse_fwd", a, b, Ma, Nb, Kp, Kp, Kp, scale2, scale2 * bound, gated, None, rowsum, colsum, diag, 0,
+    L.call("logits_lse_fwd", a, b, Ma, Nb, Kp, Kp, Kp, scale2, scale2 * bound, gated, None, 0, rowsum, colsum, diag, 0,
            L.stream_ptr())
     torch.cuda.synchronize()
     S = a.double() @ b.double().T

@@ -78,8 +78,7 @@ def test_siglip_vs_oracle(B, T, D, tau, bias, prec):
     pw = pm * rng.choice([1.0, 1.5, 2.5, 3.0], size=(B, T)).astype(np.float32)
     loss, dv, dt, dlt, db = _run(SigLIPLoss(bias_init=bias, precision=prec), v, t, math.log(tau), pm, pw)
     o = co.siglip_loss(v, t, math.log(tau), bias=bias, pos_mask=pm, pos_weights=pw)
-    ltol = 1e-5 if prec != "bf16" else 2e-4
-    gtol = 2e-3 if prec != "bf16" else 6e-3
+    ltol, gtol = 1e-5, 2e-3          # north_star tolerances for every operand precision
     assert abs(loss - o["loss"]) <= ltol * abs(o["loss"]), (loss, o["loss"])
     assert _rel(dv, o["dvideo"]) <= gtol
     assert _rel(dt, o["dtext"]) <= gtol
@@ -160,8 +159,7 @@ def test_siglip_entropy_vs_oracle(B, T, D, tau, bias, thr, prec):
     o = co.siglip_loss(v, t, math.log(tau), bias=bias, pos_mask=pm, entropy_regularization_on=True, entropy_weight=0.3,
                        min_entropy_threshold=thr)
     assert o["entropy_diagnostics"]["entropy_deficit"] > 0.05          # the regulariser is really active
-    ltol = 1e-5 if prec != "bf16" else 2e-4
-    gtol = 2e-3 if prec != "bf16" else 6e-3
+    ltol, gtol = 1e-5, 2e-3          # north_star tolerances for every operand precision
     assert abs(loss - o["loss"]) <= ltol * abs(o["loss"]), (loss, o["loss"])
     assert _rel(dv, o["dvideo"]) <= gtol
     assert _rel(dt, o["dtext"]) <= gtol

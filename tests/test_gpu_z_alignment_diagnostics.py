@@ -24,7 +24,7 @@ def test_alignment_diagnostics_match_runner_golden(name):
     lt = torch.tensor(g["log_temp"].astype(np.float32), device=DEV, requires_grad=True)
     before = _lib.LAUNCHES
     r = alignment_diagnostics(v, t, lt, use_siglip=bool(g["use_siglip"]))
-    assert _lib.LAUNCHES - before == 5            # 2 normalise, dyn_prep, forward sweep, scalar tail: no dense pass
+    assert _lib.LAUNCHES - before == 6            # 2 normalise, dyn_prep, forward sweep (+ its gated stable twin), scalar tail
     for key, ref in KEYS:
         x = r[key]
         assert x.ndim == 0 and x.device.type == "cuda" and not x.requires_grad

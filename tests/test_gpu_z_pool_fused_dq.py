@@ -27,7 +27,7 @@ def _grads(mod, x, mask, go):
 
 
 @pytest.mark.parametrize("B,N,D,H,dtype,masked", [(4, 3136, 512, 8, torch.bfloat16, False), (3, 777, 256, 4, torch.float16, True),
-                                                   (2, 197, 384, 8, torch.bfloat16, True)])
+                                                   (2, 197, 768, 8, torch.bfloat16, True)])
 def test_fused_dq_matches_two_launch_path(B, N, D, H, dtype, masked, monkeypatch):
     from deepcoro_clip_b200 import _lib
     from deepcoro_clip_b200.attention_pool import AttentionPool

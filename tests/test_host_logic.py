@@ -215,12 +215,15 @@ def test_alignment_diagnostics_wiring_with_torch_stand_in(name, monkeypatch):
 
     def call(fn, *a):
         if fn == "logits_lse_fwd":
-            A, Bm, Ma, Nb, K, lda, ldb, s2, sh2, gated, dyn, rowsum, colsum, diag, diag_off, st = a
+            A, Bm, Ma, Nb, K, lda, ldb, s2, sh2, gated, dyn, skip_if_stable, rowsum, colsum, diag, diag_off, st = a
+            assert skip_if_stable == 1 and dyn[11] == 0
             S = A @ Bm.T
             P = torch.exp2((S * torch.sigmoid(S) if gated else S) * dyn[0] - dyn[1])
             rowsum += P.sum(1)
             colsum += P.sum(0)
             diag.copy_(torch.diagonal(S, diag_off))
+        elif fn == "logits_rowlse":
+            assert a[9] == 1 and a[8][11] == 0            # only_if_stable; dyn[11] == 0: the launch gate stays closed
         elif fn == "alignment_diag":
             sums, n, dyn, gated, out, st = a
             d = sums[2 * n:3 * n]

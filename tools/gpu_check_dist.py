@@ -125,18 +125,18 @@ def main():
     gt = np.random.default_rng(5).integers(0, M, size=Nv); gt[:4] = [5, 700, 640, 1236]
     keep = []
     r = compute_recall_at_k_streaming(torch.tensor(vv, device=dev), torch.tensor(tx, device=dev), torch.tensor(gt, device=dev),
-                                      k_values=[1, 5, 10, 50], _counts_out=keep)
+                                      k_values=[1, 5, 10, 50], use_ddp=True, _counts_out=keep)
     sim = ro.similarity(vv, tx)
     ranks = ro.gt_ranks(sim, gt)
     check("retrieval rank counts bit-exact (text shards all-reduced)", bool((keep[0].cpu().numpy() + 1 == ranks).all()),
           int((keep[0].cpu().numpy() + 1 != ranks).sum()))
     check("retrieval recall == oracle", r == ro.recall_at_k_streaming(vv, tx, gt, [1, 5, 10, 50]), r)
     m = compute_metrics_streaming(torch.tensor(vv, device=dev), torch.tensor(tx, device=dev), torch.tensor(gt, device=dev),
-                                  k_values=[1, 5, 10, 50])
+                                  k_values=[1, 5, 10, 50], use_ddp=True)
     om = ro.metrics_streaming(vv, tx, gt, k_values=(1, 5, 10, 50))
     # normalised inputs are no longer exact: near-ties may swap one rank (fp32 numpy vs bf16x3 tensor core)
     check("retrieval MRR_V2T (normalised inputs)", abs(m["MRR_V2T"] - om["MRR_V2T"]) <= 1e-5, (m["MRR_V2T"], om["MRR_V2T"]))
-    s, i = streaming_topk(torch.tensor(vv, device=dev), torch.tensor(tx, device=dev), 10)
+    s, i = streaming_topk(torch.tensor(vv, device=dev), torch.tensor(tx, device=dev), 10, use_ddp=True)
     os_, oi = ro.topk_lowest_index(sim, 10)
     check("retrieval top-10 indices bit-exact", bool((i.cpu().numpy() == oi).all()), int((i.cpu().numpy() != oi).sum()))
     check("retrieval top-10 scores bit-exact", bool((s.cpu().numpy() == os_).all()), "")

@@ -38,7 +38,7 @@ def lse(N, M, K, tau, gated=0):
     scale2 = math.log2(math.e) / tau
     mx = (0.7311 if gated else 1.0) / tau
     shift2 = mx * math.log2(math.e)
-    L.call("logits_lse_fwd", a, b, N, M, K, K, K, scale2, shift2, gated, None, rs, cs, None, 0, st)
+    L.call("logits_lse_fwd", a, b, N, M, K, K, K, scale2, shift2, gated, None, 0, rs, cs, None, 0, st)
     torch.cuda.synchronize()
     S = a.double() @ b.double().t()
     if gated: S = S * torch.sigmoid(S)
@@ -60,12 +60,12 @@ b = torch.nn.functional.normalize(torch.randn(N, K, device=dev), dim=-1).bfloat1
 rs = torch.zeros(N, device=dev); cs = torch.zeros(N, device=dev)
 tau = 0.0588
 for it in range(3):
-    L.call("logits_lse_fwd", a, b, N, N, K, K, K, 1.4427/tau, 1.4427/tau, 0, None, rs, cs, None, 0, st)
+    L.call("logits_lse_fwd", a, b, N, N, K, K, K, 1.4427/tau, 1.4427/tau, 0, None, 0, rs, cs, None, 0, st)
 torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 e0.record()
 for it in range(10):
-    L.call("logits_lse_fwd", a, b, N, N, K, K, K, 1.4427/tau, 1.4427/tau, 0, None, rs, cs, None, 0, st)
+    L.call("logits_lse_fwd", a, b, N, N, K, K, K, 1.4427/tau, 1.4427/tau, 0, None, 0, rs, cs, None, 0, st)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print("lse_fwd 32k x 32k x 512: %.3f ms  -> %.1f TFLOP/s" % (ms, 2 * N * N * K / ms / 1e9), flush=True)

@@ -34,11 +34,11 @@ def step():
     lo = rank * B
     if tw is not None: tw.wait()
     mark("wait_gather_t")
-    ops.call("logits_lse_fwd", vop, tall, B, N, K, vop.stride(0), tall.stride(0), 0.0, 0.0, 0, dyn, ws[N + lo:N + lo + B], ws[:N], ws[2 * N + lo:2 * N + lo + B], lo, st); mark("fwd")
+    ops.call("logits_lse_fwd", vop, tall, B, N, K, vop.stride(0), tall.stride(0), 0.0, 0.0, 0, dyn, 0, ws[N + lo:N + lo + B], ws[:N], ws[2 * N + lo:2 * N + lo + B], lo, st); mark("fwd")
     if W > 1: dist.all_reduce(ws[:3 * N])
     mark("allreduce_sums")
     loss = torch.empty(1, device=dev)
-    ops.call("clip_finalize", ws[:3 * N], N, dyn, 0.0, 0, None, ws[3 * N:4 * N], ws[4 * N:5 * N], loss, None, st); mark("finalize")
+    ops.call("clip_finalize", ws[:3 * N], N, 3, dyn, 0.0, 0, None, ws[3 * N:4 * N], ws[4 * N:5 * N], loss, None, st); mark("finalize")
     if vw is not None: vw.wait()
     mark("wait_gather_v")
     nbd = B * D
