@@ -182,15 +182,16 @@ int b200clip_siglip_entropy_coef(const double* stats_all, int W, int B_global, i
   return siglip_entropy_coef(stats_all, W, B_global, T, weight, threshold, dyn, out, S(stream));
 }
 
-int b200clip_siglip_combine(const double* acc, double wn_c, double* red, void* stream) {
-  if (!acc || !red) return B2_EINVAL;
-  return siglip_combine(acc, wn_c, red, S(stream));
+int b200clip_siglip_combine(const double* acc, double wn_c, const float* text_inv_norm, int T, double* red,
+                            void* stream) {
+  if (!acc || !red || (text_inv_norm && T <= 0)) return B2_EINVAL;
+  return siglip_combine(acc, wn_c, text_inv_norm, T, red, S(stream));
 }
 
-int b200clip_siglip_loss_out(const double* red, const int32_t* overflow, const float* ent, float* loss_out, float* diag,
-                             void* stream) {
+int b200clip_siglip_loss_out(const double* red, const int32_t* overflow, const float* ent, int world, float* loss_out,
+                             float* diag, void* stream) {
   if (!red || !loss_out) return B2_EINVAL;
-  return siglip_loss_out(red, overflow, ent, loss_out, diag, S(stream));
+  return siglip_loss_out(red, overflow, ent, world, loss_out, diag, S(stream));
 }
 
 int b200clip_siglip_scalar_grads(const double* red, const float* dyn, const float* grad_out, float* dlog_temp,

@@ -94,8 +94,8 @@ int siglip_entropy_rows(const float* Z, const float* H, const float* Q, int B, f
                         cudaStream_t s);
 int siglip_entropy_coef(const double* stats_all, int W, int Bg, int T, float weight, float thr, float* dyn, float* out,
                         cudaStream_t s);
-int siglip_combine(const double* acc, double wn_c, double* red, cudaStream_t s);
-int siglip_loss_out(const double* red, const int* overflow, const float* ent, float* loss_out, float* diag,
+int siglip_combine(const double* acc, double wn_c, const float* tinv, int T, double* red, cudaStream_t s);
+int siglip_loss_out(const double* red, const int* overflow, const float* ent, int world, float* loss_out, float* diag,
                     cudaStream_t s);
 int siglip_scalar_grads(const double* red, const float* dyn, const float* gmul, float* dlt, float* dbias,
                         cudaStream_t s);

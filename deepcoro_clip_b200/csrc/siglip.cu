@@ -202,13 +202,13 @@ int siglip_entropy_coef(const double* stats_all, int W, int Bg, int T, float wei
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
-int siglip_combine(const double* acc, double wn_c, double* red, cudaStream_t s) {
-  siglip_combine_kernel<<<1, 32, 0, s>>>(acc, wn_c, red);
+int siglip_combine(const double* acc, double wn_c, const float* tinv, int T, double* red, cudaStream_t s) {
+  siglip_combine_kernel<<<1, 256, 0, s>>>(acc, wn_c, tinv, T, red);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
-int siglip_loss_out(const double* red, const int* overflow, const float* ent, float* loss_out, float* diag,
+int siglip_loss_out(const double* red, const int* overflow, const float* ent, int world, float* loss_out, float* diag,
                     cudaStream_t s) {
-  siglip_loss_out_kernel<<<1, 32, 0, s>>>(red, overflow, ent, loss_out, diag);
+  siglip_loss_out_kernel<<<1, 32, 0, s>>>(red, overflow, ent, world, loss_out, diag);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 int siglip_scalar_grads(const double* red, const float* dyn, const float* gmul, float* dlt, float* dbias,

@@ -68,18 +68,40 @@ __global__ void siglip_entropy_coef_kernel(const double* __restrict__ stats_all,
   dyn[10] = deficit > 0.f ? -weight / (float)Bg : 0.f;
 }
 
-__global__ void siglip_combine_kernel(const double* __restrict__ acc, double wn_c, double* __restrict__ red) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// red[0..2] = loss, dbias, sum G*s of this rank; red[3] / red[4] = a position-weighted fp64 checksum of the text operand's
+// inverse norms and its square: after the all-reduce over W ranks, W * sum c^2 == (sum c)^2 exactly when every rank
+// held the same texts (Cauchy-Schwarz) — siglip_loss_out turns the loss into NaN otherwise (text_replicated contract).
+// One block of 256 threads, fixed reduction order (bit-identical on every rank for identical texts).
+__global__ void __launch_bounds__(256)
+siglip_combine_kernel(const double* __restrict__ acc, double wn_c, const float* __restrict__ tinv, int T,
+                      double* __restrict__ red) {
+  double c = 0.0;
+  if (tinv)
+    for (int j = threadIdx.x; j < T; j += 256) c += (double)tinv[j] * (1.0 + (double)(j & 1023) * (1.0 / 1024.0));
+  __shared__ double sh[256];
+  sh[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
   red[0] = wn_c * acc[1] + acc[4];
   red[1] = acc[2] + acc[5];
   red[2] = acc[0] + acc[6];
+  red[3] = sh[0];
+  red[4] = sh[0] * sh[0];
 }
 __global__ void siglip_loss_out_kernel(const double* __restrict__ red, const int* __restrict__ overflow,
-                                       const float* __restrict__ ent, float* __restrict__ loss_out,
+                                       const float* __restrict__ ent, int world, float* __restrict__ loss_out,
                                        float* __restrict__ diag) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double loss = red[0];
   if (overflow && overflow[0] > 0) loss = nan("");
+  if (world > 1) {
+    const double s2 = red[3] * red[3];
+    if (fabs((double)world * red[4] - s2) > 1e-11 * s2) loss = nan("");      // the ranks' texts differ
+  }
   if (diag) {
     for (int i = 0; i < 6; ++i) diag[i] = ent ? ent[i] : 0.f;
     diag[6] = (float)loss;

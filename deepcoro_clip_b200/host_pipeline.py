@@ -72,7 +72,13 @@ class GraphedLossStep:
     buffers: ``step(video, text)`` copies the new batch in (device or pinned-host tensors), replays, and returns
     ``(loss, dvideo, dtext, dlog_temp)`` — views of static tensors, valid until the next call. Shapes, dtypes and the loss
     configuration are fixed at construction; the parity of a replayed step with the eager module is covered by
-    tests/test_gpu_clip_loss.py::test_graphed_step_matches_eager."""
+    tests/test_gpu_clip_loss.py::test_graphed_step_matches_eager.
+
+    Parameters: the temperature is held in a PRIVATE static tensor (a clone of the ``log_temp`` given at construction), so
+    a learnable temperature must be handed to every step — ``step(video, text, log_temp=param)`` copies its current value
+    in (device copy, no sync) before the replay; ``dlog_temp`` is the gradient for the caller's parameter. The loss
+    module's own parameters (SigLIP ``bias``) are captured in place: update them in place (every torch optimizer does) and
+    read their ``.grad`` after the step."""
 
     def __init__(self, loss_module, video: torch.Tensor, text: torch.Tensor, log_temp: torch.Tensor, warmup: int = 3,
                  **forward_kwargs):
@@ -107,12 +113,14 @@ class GraphedLossStep:
         return self.loss_module(video_features=self.video, text_features=self.text, log_temp=self.log_temp,
                                 **self.kwargs)
 
-    def step(self, video: torch.Tensor = None, text: torch.Tensor = None):
+    def step(self, video: torch.Tensor = None, text: torch.Tensor = None, log_temp: torch.Tensor = None):
         with torch.no_grad():
             if video is not None:
                 self.video.copy_(video, non_blocking=True)
             if text is not None:
                 self.text.copy_(text, non_blocking=True)
+            if log_temp is not None:
+                self.log_temp.copy_(log_temp.detach().reshape(self.log_temp.shape), non_blocking=True)
         self.graph.replay()
         return self.loss, self.video.grad, self.text.grad, self.log_temp.grad
 

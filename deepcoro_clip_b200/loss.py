@@ -306,7 +306,8 @@ _NO_CLAMP = 3.0e38   # logit clamp of the variants that do not clamp (utils/loss
 def _siglip_cfg(**kw) -> dict:
     cfg = dict(positive_weight=1.0, negative_weight=1.0, use_severity_weights=True, auto_balance=False,
                precision="auto", max_positives=64, group=None, tau_clamp=1e-4, logit_clamp=30.0, label_smoothing=0.0,
-               pos_rule_mask=False, entropy=False, entropy_weight=0.1, entropy_threshold=2.0, ent_holder=None)
+               pos_rule_mask=False, entropy=False, entropy_weight=0.1, entropy_threshold=2.0, ent_holder=None,
+               text_replicated=False)
     cfg.update(kw)
     return cfg
 
@@ -318,7 +319,18 @@ class _SigLIPFn(torch.autograd.Function):
 
     ``cfg`` selects the reference variant: ``tau_clamp`` (1e-4 | 0), ``logit_clamp`` (30 | none), ``label_smoothing``
     (y (1 - eps) + eps / 2 on every pair, siglip2_bce.py:98-99), ``pos_rule_mask`` (positive weight where
-    pos_mask > 0, siglip_pairwise.py:352), ``entropy`` (contrastive.py:19-68, 306-313)."""
+    pos_mask > 0, siglip_pairwise.py:352), ``entropy`` (contrastive.py:19-68, 306-313).
+
+    Process groups. The reference gathers video, pos_mask and pos_weights and multiplies against THE RANK'S OWN text
+    (contrastive.py:252-256, 263): every rank holds the loss over [B_global, T_local], computed W times over when the ranks
+    happen to hold the same texts. Default (``text_replicated=False``): exactly that — the raw video rows and the dense
+    masks are all-gathered, the rank evaluates its [B_global, T_local] problem, keeps its own rows of the video gradient
+    (the gather's backward, :87-91) and the full gradient of its own text; no result is reduced across ranks, texts may
+    differ per rank. ``text_replicated=True`` is the sharded fast path for callers that pass the SAME text matrix on every
+    rank (BASELINE config 2: the global text batch all-gathered by the caller): each rank computes only its
+    [B_local, T] row slab — 1/W of the reference's per-rank work — and the loss scalars and the text gradient are
+    all-reduced; a checksum of the text operand rides in the same all-reduce and the loss is NaN when the ranks' texts
+    differ (loud, no host sync)."""
 
     @staticmethod
     def forward(ctx, video, text, log_temp, bias, pos_mask, pos_weights, cfg):
@@ -334,6 +346,19 @@ class _SigLIPFn(torch.autograd.Function):
             raise ValueError(f"pos_mask must be [B, T] = {(B, T)}, got {tuple(pos_mask.shape)}")
         if pos_weights is not None and tuple(pos_weights.shape) != (B, T):
             raise ValueError(f"pos_weights must be [B, T] = {(B, T)}, got {tuple(pos_weights.shape)}")
+        own = None
+        video_in = video
+        if W > 1 and not cfg["text_replicated"]:
+            # reference semantics for per-rank texts (:252-256): gather video / mask / weights, evaluate the
+            # [B_global, T_local] problem locally, keep the own rows of the video gradient
+            grp = cfg["group"]
+            video = dist_plan.gather_rows(ops._rowmajor(video.detach()), W, grp)
+            if pos_mask is not None:
+                pos_mask = dist_plan.gather_rows(pos_mask.detach().float().contiguous(), W, grp)
+            if pos_weights is not None:
+                pos_weights = dist_plan.gather_rows(pos_weights.detach().float().contiguous(), W, grp)
+            own = (rank * B, (rank + 1) * B)
+            B, W, rank = Bg, 1, 0
         x3 = _pick_precision(cfg["precision"], Bg, T)
         vop, vinv, Kp = ops.l2norm_operand(video, 0 if x3 else -1)
         top, tinv, _ = ops.l2norm_operand(text, 1 if x3 else -1)
@@ -421,21 +446,29 @@ class _SigLIPFn(torch.autograd.Function):
                  vraw, ops.DTYPE_CODE[vraw.dtype], ops.i64(vraw.stride(0)), vinv,
                  traw, ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), tinv, st)
         # local sums -> global (every rank returns the full loss, reference DDP semantics); scalar tails on the device
-        red = torch.empty(3, dtype=torch.float64, device=dev)           # loss, dbias, sum G*s
-        ops.call("siglip_combine", acc, float(wn * c), red, st)
+        # loss, dbias, sum G*s | checksum of the text operand and its square (replication check, see the class docstring)
+        red = torch.empty(5, dtype=torch.float64, device=dev)
+        ops.call("siglip_combine", acc, float(wn * c), tinv, T, red, st)
         if W > 1:
             dist.all_reduce(red, group=cfg["group"])
             if dTh is not None:
                 dist.all_reduce(dTh, group=cfg["group"])      # text is replicated: every rank gets the full text grad
             dist.all_reduce(overflow, group=cfg["group"])
+        elif own is not None:
+            dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=cfg["group"])
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         diag = None
         if ent is not None and cfg["ent_holder"] is not None:
             diag = torch.empty(7, dtype=torch.float32, device=dev)
-        ops.call("siglip_loss_out", red, overflow, ent, loss, diag, st)   # NaN on overflow: never silently drop positives
+        # NaN on overflow (never silently drop positives) and when the ranks of a text_replicated job hold different texts
+        ops.call("siglip_loss_out", red, overflow, ent, W, loss, diag, st)
         if diag is not None:
             cfg["ent_holder"]["raw"] = diag
-        ctx.save_for_backward(video, text, vinv, tinv, dyn, dVh, dTh, red)
+        if own is not None:             # the gather's backward keeps this rank's rows (contrastive.py:87-91)
+            if dVh is not None:
+                dVh = dVh[own[0]:own[1]]
+            vinv = vinv[own[0]:own[1]]
+        ctx.save_for_backward(video_in, text, vinv, tinv, dyn, dVh, dTh, red)
         ctx.meta = (log_temp.shape, log_temp.dtype, None if bias is None else (bias.shape, bias.dtype))
         return loss.reshape(())
 
@@ -488,8 +521,10 @@ class SigLIPLoss(nn.Module):
     def __init__(self, bias_init: float = -10.0, learnable_bias: bool = True, positive_weight: float = 1.0,
                  negative_weight: float = 1.0, use_severity_weights: bool = True, auto_balance: bool = False,
                  entropy_regularization: bool = False, entropy_weight: float = 0.1,
-                 min_entropy_threshold: float = 2.0, precision: str = "auto", max_positives_per_row: int = 64):
+                 min_entropy_threshold: float = 2.0, precision: str = "auto", max_positives_per_row: int = 64,
+                 text_replicated: bool = False):
         super().__init__()
+        self.text_replicated = bool(text_replicated)     # see _SigLIPFn: sharded fast path for identical texts on all ranks
         self.positive_weight = max(float(positive_weight), 1e-6)
         self.negative_weight = max(float(negative_weight), 1e-6)
         self.use_severity_weights = use_severity_weights
@@ -515,7 +550,8 @@ class SigLIPLoss(nn.Module):
                           use_severity_weights=self.use_severity_weights, auto_balance=self.auto_balance,
                           precision=self.precision, max_positives=self.max_positives_per_row,
                           entropy=bool(self.entropy_regularization), entropy_weight=self.entropy_weight,
-                          entropy_threshold=self.min_entropy_threshold, ent_holder=holder)
+                          entropy_threshold=self.min_entropy_threshold, ent_holder=holder,
+                          text_replicated=self.text_replicated)
         loss = _SigLIPFn.apply(video_features, text_features, log_temp, bias, pos_mask, pos_weights, cfg)
         if self.entropy_regularization:
             self._last_entropy_diagnostics = _entropy_diagnostics(holder)
@@ -532,8 +568,10 @@ class SiglipPairwiseFeatureLoss(nn.Module):
 
     def __init__(self, *, positive_weight: float = 1.0, negative_weight: float = 1.0, use_positive_weights: bool = True,
                  auto_positive_weight: bool = False, entropy_regularization: bool = False, entropy_weight: float = 0.1,
-                 min_entropy_threshold: float = 2.0, precision: str = "auto", max_positives_per_row: int = 64) -> None:
+                 min_entropy_threshold: float = 2.0, precision: str = "auto", max_positives_per_row: int = 64,
+                 text_replicated: bool = False) -> None:
         super().__init__()
+        self.text_replicated = bool(text_replicated)
         self.positive_weight = max(float(positive_weight), 1e-6)
         self.negative_weight = max(float(negative_weight), 0.0)
         self.use_positive_weights = use_positive_weights
@@ -554,7 +592,7 @@ class SiglipPairwiseFeatureLoss(nn.Module):
                           precision=self.precision, max_positives=self.max_positives_per_row, tau_clamp=0.0,
                           pos_rule_mask=True, entropy=bool(self.entropy_regularization),
                           entropy_weight=self.entropy_weight, entropy_threshold=self.min_entropy_threshold,
-                          ent_holder=holder)
+                          ent_holder=holder, text_replicated=self.text_replicated)
         loss = _SigLIPFn.apply(video_features, text_features, _as_log_temp(log_temp, dev), None, pos_mask, pos_weights,
                                cfg)
         if self.entropy_regularization:
@@ -609,8 +647,10 @@ class SigLIP2BCELoss(nn.Module):
         ddp = self._gather and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if ddp:
             text_features = _GatherTextRows.apply(text_features, None)
+        # the DDP variant gathers the text itself (one line above): replicated by construction
         cfg = _siglip_cfg(precision=self.precision, tau_clamp=0.0, logit_clamp=_NO_CLAMP,
-                          label_smoothing=float(self.label_smoothing), group=None if ddp else _LOCAL)
+                          label_smoothing=float(self.label_smoothing), group=None if ddp else _LOCAL,
+                          text_replicated=True)
         return _SigLIPFn.apply(video_features, text_features, _as_log_temp(log_temp, dev), bias, None, None, cfg)
 
 

@@ -247,16 +247,19 @@ int b200clip_siglip_entropy_rows(const float* Z, const float* H, const float* Q,
 int b200clip_siglip_entropy_coef(const double* stats_all, int W, int B_global, int T, float weight, float threshold,
                                  float* dyn, float* out, void* stream);
 /* Scalar tails of the SigLIP loss (one launch each instead of ~20 single-element framework launches per step):
- *   siglip_combine      : red[3] = {wn_c * acc[1] + acc[4], acc[2] + acc[5], acc[0] + acc[6]} = {loss, dbias, sum G*s}
- *                         (acc[0..2] dense sums of logits_bwd / siglip_dense_fwd, acc[4..6] corrections of siglip_pos);
- *                         all-reduced across ranks by the caller;
- *   siglip_loss_out     : loss_out[0] = red[0], NaN if overflow[0] > 0, + ent[5] when the entropy block is given;
+ *   siglip_combine      : red[5]: red[0..2] = {wn_c * acc[1] + acc[4], acc[2] + acc[5], acc[0] + acc[6]} = {loss, dbias,
+ *                         sum G*s} (acc[0..2] dense sums of logits_bwd / siglip_dense_fwd, acc[4..6] corrections of
+ *                         siglip_pos); red[3] = c, red[4] = c^2, c = a position-weighted fp64 checksum of text_inv_norm
+ *                         [T] (0 when NULL); all-reduced (SUM) across ranks by the caller in the sharded fast path;
+ *   siglip_loss_out     : loss_out[0] = red[0], NaN if overflow[0] > 0 or (world > 1 and world * red[4] != red[3]^2, i.e.
+ *                         the ranks of a "text replicated" job held different texts), + ent[5] with the entropy block;
  *                         diag (may be NULL) = {ent[0..5], bce loss} for get_entropy_diagnostics();
  *   siglip_scalar_grads : dlog_temp[0] = -red[2] / tau * [tau not clamped] * grad_out[0], dbias[0] = red[1] * grad_out[0]
  *                         (either output may be NULL). */
-int b200clip_siglip_combine(const double* acc, double wn_c, double* red, void* stream);
-int b200clip_siglip_loss_out(const double* red, const int32_t* overflow, const float* ent, float* loss_out, float* diag,
-                             void* stream);
+int b200clip_siglip_combine(const double* acc, double wn_c, const float* text_inv_norm, int T, double* red,
+                            void* stream);
+int b200clip_siglip_loss_out(const double* red, const int32_t* overflow, const float* ent, int world, float* loss_out,
+                             float* diag, void* stream);
 int b200clip_siglip_scalar_grads(const double* red, const float* dyn, const float* grad_out, float* dlog_temp,
                                  float* dbias, void* stream);
 int b200clip_siglip_compact(const float* pos_mask, int64_t ld_mask, const float* pos_weights, int64_t ld_weights, int B,

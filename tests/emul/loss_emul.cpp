@@ -262,13 +262,13 @@ extern "C" int b200clip_siglip_dense_fwd(const void* V, const void* T, int B, in
   acc[0] += t;
   return 0;
 }
-extern "C" int b200clip_siglip_combine(const double* acc, double wn_c, double* red, void*) {
-  emul::launch(1, 32, [&] { siglip_combine_kernel(acc, wn_c, red); });
+extern "C" int b200clip_siglip_combine(const double* acc, double wn_c, const float* tinv, int T, double* red, void*) {
+  emul::launch(1, 256, [&] { siglip_combine_kernel(acc, wn_c, tinv, T, red); });
   return 0;
 }
-extern "C" int b200clip_siglip_loss_out(const double* red, const int* overflow, const float* ent, float* loss_out, float* diag,
-                                        void*) {
-  emul::launch(1, 32, [&] { siglip_loss_out_kernel(red, overflow, ent, loss_out, diag); });
+extern "C" int b200clip_siglip_loss_out(const double* red, const int* overflow, const float* ent, int world, float* loss_out,
+                                        float* diag, void*) {
+  emul::launch(1, 32, [&] { siglip_loss_out_kernel(red, overflow, ent, world, loss_out, diag); });
   return 0;
 }
 extern "C" int b200clip_siglip_scalar_grads(const double* red, const float* dyn, const float* gmul, float* dlt, float* dbias,

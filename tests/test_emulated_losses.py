@@ -18,6 +18,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from oracle import contrastive_oracle as co
 from tests.conftest import GOLDEN
 
 EMUL = Path(__file__).resolve().parent / "emul"
@@ -225,11 +226,34 @@ def _siglip_body(rank, world, name):
     g = np.load(GOLDEN / f"{name}.npz")
     cls, ckw = SIGLIP_CASES[name]
     B = g["video"].shape[0] // world
+    res = []
+    # video rows / mask rows sharded, the same text on every rank: the sharded fast path (text_replicated=True: row slab per
+    # rank, scalars and text gradient all-reduced) and the default reference-faithful path (video / masks gathered, the
+    # [B_global, T] problem evaluated by every rank, nothing reduced) must both reproduce the full-batch golden
+    for replicated in (True, False):
+        mod = getattr(loss_mod, cls)(text_replicated=replicated, **ckw)
+        v, t, lt, kw = _siglip_inputs(g, rank * B, (rank + 1) * B)
+        loss = mod(video_features=v, text_features=t, log_temp=lt, **kw)
+        loss.backward()
+        res.append((loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item(), mod.bias.grad.item()))
+    # per-rank DIFFERENT texts (what the reference's runner passes: each rank's own text batch): rank r holds half of the
+    # texts and the matching half of the mask columns; reference semantics = the [B_global, T_r] problem on rank r
+    T = g["text"].shape[0]
+    Th = T // world
+    cols = slice(rank * Th, (rank + 1) * Th)
     mod = getattr(loss_mod, cls)(**ckw)
-    v, t, lt, kw = _siglip_inputs(g, rank * B, (rank + 1) * B)          # video rows / mask rows sharded, text replicated
+    v, _, lt, kw = _siglip_inputs(g, rank * B, (rank + 1) * B)
+    t = torch.tensor(g["text"][cols], dtype=torch.float32, requires_grad=True)
+    kw = {k: x[:, cols].contiguous() for k, x in kw.items()}
     loss = mod(video_features=v, text_features=t, log_temp=lt, **kw)
     loss.backward()
-    return (loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item(), mod.bias.grad.item())
+    res.append((loss.item(), v.grad.numpy(), t.grad.numpy(), lt.grad.item(), mod.bias.grad.item()))
+    # the fast path's contract check: different texts under text_replicated=True poison the loss (NaN), loudly
+    mod = getattr(loss_mod, cls)(text_replicated=True, **ckw)
+    with torch.no_grad():
+        bad = mod(video_features=v.detach(), text_features=t.detach(), log_temp=lt.detach(), **kw).item()
+    res.append(bad)
+    return res
 
 
 @pytest.mark.parametrize("name", GLOO_SIGLIP)
@@ -239,11 +263,34 @@ def test_siglip_loss_host_path_two_ranks_gloo(name, gloo_results):
     world = 2
     out = {r: gloo_results[r][("siglip", name)] for r in range(world)}
     g = np.load(GOLDEN / f"{name}.npz")
+    cls, ckw = SIGLIP_CASES[name]
     B = g["video"].shape[0] // world
+    for mode in (0, 1):                                  # sharded fast path, reference-faithful gathered path
+        for r in range(world):
+            loss, dv, dt, dlt, db = out[r][mode]
+            _check_siglip(g, loss, dv, dt, dlt, db, rows=slice(r * B, (r + 1) * B))
+    assert out[0][0][0] == out[1][0][0]
+    # per-rank texts: the oracle evaluates rank r's [B_global, T_r] problem (utils/loss/contrastive.py:252-263)
+    T = g["text"].shape[0]
+    Th = T // world
+    okw = {k: v for k, v in ckw.items() if k not in ("entropy_regularization",)}
+    # the gathered mask is the same on every rank: rank q's rows carry rank q's own column slice (its local texts)
+    def gathered(key):
+        if key not in g.files:
+            return None
+        return np.concatenate([g[key][q * B:(q + 1) * B, q * Th:(q + 1) * Th] for q in range(world)], axis=0)
     for r in range(world):
-        loss, dv, dt, dlt, db = out[r]
-        _check_siglip(g, loss, dv, dt, dlt, db, rows=slice(r * B, (r + 1) * B))
-    assert out[0][0] == out[1][0]
+        cols = slice(r * Th, (r + 1) * Th)
+        o = co.siglip_loss(g["video"], g["text"][cols], g["log_temp"], bias=ckw.get("bias_init", -10.0),
+                           pos_mask=gathered("in_pos_mask"), pos_weights=gathered("in_pos_weights"),
+                           entropy_regularization_on=bool(ckw.get("entropy_regularization", False)),
+                           min_entropy_threshold=ckw.get("min_entropy_threshold", 2.0))
+        loss, dv, dt, dlt, db = out[r][2]
+        assert abs(loss - o["loss"]) <= 1e-5 * abs(o["loss"]), (r, loss, o["loss"])
+        assert _rel(dv, o["dvideo"][r * B:(r + 1) * B]) <= 2e-3 and _rel(dt, o["dtext"]) <= 2e-3
+        assert abs(dlt - o["dlog_temp"]) <= 2e-3 * max(abs(o["dlog_temp"]), 1e-4)
+        assert abs(db - o["dbias"]) <= 2e-3 * max(abs(o["dbias"]), 1e-4)
+        assert np.isnan(out[r][3])
 
 
 @pytest.mark.parametrize("name", ["align_b64_d512", "align_siglip_b130_d96", "align_b300_d200"])

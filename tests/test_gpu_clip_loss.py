@@ -218,3 +218,8 @@ def test_graphed_step_matches_eager():
         assert float((dv - ve.grad).abs().max()) <= 2e-5 * float(ve.grad.abs().max())
         assert float((dt - te.grad).abs().max()) <= 2e-5 * float(te.grad.abs().max())
         assert abs(dlt.item() - le.grad.item()) <= 1e-6 * abs(le.grad.item())
+    # a learnable temperature is handed to every step (the graph holds a private copy): new value, new loss
+    lt2 = torch.tensor([math.log(0.1)], device=DEV)
+    loss2 = gs.step(v, t, log_temp=lt2)[0].item()
+    ref2 = mod(video_features=v, text_features=t, log_temp=lt2).item()
+    assert abs(loss2 - ref2) <= 1e-6 * abs(ref2) and abs(loss2 - le_loss.item()) > 1e-3
