@@ -76,6 +76,11 @@ def build_oracle(force: bool = False) -> None:
     if mk.exists():
         subprocess.run(["make", "-C", str(ROOT / "oracle")] + (["-B"] if force else []), check=True,
                        capture_output=True)
+    # oracle/_ref: the unmodified reference files of the path, copied where /root/reference exists (build container) so
+    # that bench.py's reference arm / cpu_baseline legs can time the real classes on the GPU box (oracle/make_ref.py)
+    rec = ROOT / "oracle" / "make_ref.py"
+    if rec.exists():
+        subprocess.run([sys.executable, str(rec)], check=True, capture_output=True)
 
 
 if __name__ == "__main__":

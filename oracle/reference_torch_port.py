@@ -37,6 +37,27 @@ def clip_loss_step(video, text, log_temp: float, label_smoothing: float = 0.0):
     return loss.detach(), video_features.grad, text_features.grad, lt.grad
 
 
+def siglip_loss_step(video, text, log_temp: float, pos_mask, pos_weights, bias: float = -10.0):
+    """One forward + backward of the reference SigLIPLoss (default constructor) on CPU tensors, op for op
+    (/root/reference/utils/loss/contrastive.py:259-303, single process). Returns (loss, dvideo, dtext)."""
+    video_features = torch.as_tensor(video).detach().clone().requires_grad_(True)
+    text_features = torch.as_tensor(text).detach().clone().requires_grad_(True)
+    lt = torch.tensor([float(log_temp)], dtype=torch.float32, requires_grad=True)
+    b = torch.tensor(float(bias), requires_grad=True)
+    v = F.normalize(video_features.float(), dim=-1)                                   # :259
+    t = F.normalize(text_features.float(), dim=-1)                                    # :260
+    similarity = torch.matmul(v, t.t())                                               # :263
+    temp = torch.exp(lt.float()).clamp(min=1e-4)                                      # :266
+    logits = (similarity / temp + b).clamp(-30, 30)                                   # :267-270
+    targets = torch.as_tensor(pos_mask).float().clamp(0, 1)                           # :274
+    weight_matrix = torch.ones_like(targets)                                          # :283 (negative_weight = 1)
+    positive_contrib = torch.as_tensor(pos_weights).float() * 1.0                     # :287-289 (positive_weight = 1)
+    weight_matrix = torch.where(targets > 0.5, positive_contrib, weight_matrix)       # :298
+    loss = F.binary_cross_entropy_with_logits(logits, targets, weight=weight_matrix, reduction="mean")   # :301-303
+    loss.backward()
+    return loss.detach(), video_features.grad, text_features.grad
+
+
 @torch.no_grad()
 def retrieval_metrics_step(video, text, gt, k_values=(1, 5, 10), video_chunk_size: int = 2048,
                            text_chunk_size: int = 8192):
