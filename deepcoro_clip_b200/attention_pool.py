@@ -155,6 +155,37 @@ class AttentionPool(nn.Module):
         return y.to(x.dtype)
 
 
+def token_mean_pool(token_feats: torch.Tensor, mask: torch.Tensor = None) -> torch.Tensor:
+    """The mean branch of ``VideoEncoder._pool_video_tokens`` (models/video_encoder.py:603): ``token_feats.mean(dim=2)``,
+    [B, N_views, L, D] -> [B, N_views, D] (also accepts [B, L, D] -> [B, D]).
+
+    It is the streaming pool kernel in its uniform-weights mode: one head with a zero query makes every score 0, the
+    softmax is exactly 1 / L, so x is read once, accumulated in fp32 and never re-materialised; the backward writes
+    dx = dout / L in the same kernel family. With a key-padding ``mask`` ([.., L] bool, True = ignore) it is the mean over the
+    unmasked tokens (the reference's branch has no mask)."""
+    shape = token_feats.shape
+    if token_feats.dim() not in (3, 4):
+        raise ValueError(f"token_feats must be [B, N, L, D] or [B, L, D], got {tuple(shape)}")
+    L, D = shape[-2], shape[-1]
+    x = token_feats.reshape(-1, L, D)
+    mk = mask.reshape(-1, L) if mask is not None else None
+    qt = torch.zeros((1, D), dtype=torch.float32, device=x.device)
+    xbar, _, _ = _StreamPool.apply(x, qt, mk, 0.0, 0, False)          # [B * N, 1, D] fp32
+    return xbar[:, 0, :].reshape(*shape[:-2], D).to(token_feats.dtype)
+
+
+def pool_video_tokens(encoder, token_feats: torch.Tensor) -> torch.Tensor:
+    """Drop-in body of ``VideoEncoder._pool_video_tokens`` (models/video_encoder.py:589-603): [B, N, L, D] -> [B, N, D].
+    The reference loops over the N views in Python and concatenates; here the views are folded into the batch — ONE pass
+    of the pool kernel over all B * N views (same parameters for every view, so the result is identical) — and the
+    ``attention_pool is None`` case is the uniform-weights mode (``token_mean_pool``). ``install(modules=True)`` binds it."""
+    B, N, L, D = token_feats.shape
+    pool = getattr(encoder, "attention_pool", None)
+    if pool is not None:
+        return pool(token_feats.reshape(B * N, L, D)).reshape(B, N, -1)
+    return token_mean_pool(token_feats)
+
+
 class AttentionPoolWithCLS(nn.Module):
     """models/attention_pool.py:104-197 (built by VideoEncoder for ``token_pooling_mode == "cls_token"``,
     models/video_encoder.py:214-219): a learnable CLS token is prepended, one post-LN ``nn.TransformerEncoderLayer``

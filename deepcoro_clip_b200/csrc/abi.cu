@@ -65,6 +65,21 @@ int b200clip_clip_finalize(const float* sums, int n, int nvec, const float* dyn,
   return clip_finalize(sums, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out, S(stream));
 }
 
+int b200clip_clip_finalize_peers(const void* const* peer_sums_host, int world, int n, int nvec, const float* dyn, float eps,
+                                 int gated, const double* unif, float* rowscale, float* colscale, float* loss_out,
+                                 double* acc_out, void* stream) {
+  return clip_finalize_peers(reinterpret_cast<const float* const*>(peer_sums_host), world, n, nvec, dyn, eps, gated, unif,
+                             rowscale, colscale, loss_out, acc_out, S(stream));
+}
+
+int b200clip_l2norm_fwd_multi(const void* x, int dtype, int64_t ldx, int rows, int dim, void* const* operands_host,
+                              int n_operands, int64_t row_offset, int ld_out, int Kp, float* inv_norm, int normalize,
+                              void* stream) {
+  if (!x) return B2_EINVAL;
+  return l2norm_fwd_multi(x, dtype, (long)ldx, rows, dim, operands_host, n_operands, row_offset, ld_out, Kp, inv_norm,
+                          normalize, S(stream));
+}
+
 int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
                            float* out, void* stream) {
   return clip_dlogtemp(scal0, dyn, gmul, unif, n, out, S(stream));

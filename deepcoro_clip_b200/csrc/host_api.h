@@ -9,6 +9,8 @@ namespace b2host {
 // l2norm.cu
 int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out, int ldo, int Kp, int split3_role,
                float* inv_norm, float* xhat_f32, int ldh, int normalize, cudaStream_t s);
+int l2norm_fwd_multi(const void* x, int dtype, long ldx, int rows, int dim, void* const* outs_host, int n_out,
+                     long long row_offset, int ldo, int Kp, float* inv_norm, int normalize, cudaStream_t s);
 int l2norm_bwd(const float* dxh, int ldg, const void* x, int dtype, long ldx, const float* inv_norm, const void* ox,
                int odtype, long ldox, const float* oinv, const void* ohi, int ldohi, const float* dc,
                const float* usum, float gscale, float ucoef, const float* dev_omul, const float* dev_gmul, int rows,
@@ -77,6 +79,9 @@ int lse_finalize(const float* sums, int n, const float* dyn, float c, float* sca
 int vec_fsum(const float* v, int n, int gated, double* acc, cudaStream_t s);
 int clip_finalize(const float* sums, int n, int nvec, const float* dyn, float eps, int gated, const double* unif,
                   float* rowscale, float* colscale, float* loss_out, double* acc_out, cudaStream_t s);
+int clip_finalize_peers(const float* const* peer_sums_host, int world, int n, int nvec, const float* dyn, float eps, int gated,
+                        const double* unif, float* rowscale, float* colscale, float* loss_out, double* acc_out,
+                        cudaStream_t s);
 int clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n, float* out,
                   cudaStream_t s);
 int diag_sum(const void* a, int lda, const void* b, int ldb, int rows, int K, int gated, float* dots, double* acc,

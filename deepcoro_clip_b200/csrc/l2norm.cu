@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 #include "l2norm_kernels.cuh"
+#include "l2norm_multi_kernels.cuh"
 
 namespace b2host {
 using namespace b2;
@@ -41,6 +42,29 @@ int l2norm_fwd(const void* x, int dtype, long ldx, int rows, int dim, void* out,
     case 0: l2norm_fwd_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); break;
     case 1: l2norm_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); break;
     case 2: l2norm_fwd_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)x, ldx, rows, dim, o, ldo, Kp, split3_role, inv_norm, xhat_f32, ldh, normalize); break;
+    default: return B2_EINVAL;
+  }
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int l2norm_fwd_multi(const void* x, int dtype, long ldx, int rows, int dim, void* const* outs_host, int n_out,
+                     long long row_offset, int ldo, int Kp, float* inv_norm, int normalize, cudaStream_t s) {
+  if (rows <= 0 || dim <= 0 || Kp < dim || Kp % 64 || Kp > 1024 || dim % 8 || n_out < 1 || n_out > L2N_MAX_DEST ||
+      !outs_host || (ldo & 7) || row_offset < 0)
+    return B2_EINVAL;
+  const int esz = dtype == 0 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || ((ldx * esz) & 15)) return B2_EINVAL;
+  L2nDests d;
+  d.n = n_out;
+  for (int i = 0; i < L2N_MAX_DEST; ++i) {
+    d.ptr[i] = i < n_out ? reinterpret_cast<__nv_bfloat16*>(outs_host[i]) : nullptr;
+    if (i < n_out && (!outs_host[i] || (reinterpret_cast<uintptr_t>(outs_host[i]) & 15))) return B2_EINVAL;
+  }
+  const int blocks = (rows + 7) / 8;
+  switch (dtype) {
+    case 0: l2norm_fwd_multi_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, ldx, rows, dim, d, (long)row_offset, ldo, Kp, inv_norm, normalize); break;
+    case 1: l2norm_fwd_multi_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, rows, dim, d, (long)row_offset, ldo, Kp, inv_norm, normalize); break;
+    case 2: l2norm_fwd_multi_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)x, ldx, rows, dim, d, (long)row_offset, ldo, Kp, inv_norm, normalize); break;
     default: return B2_EINVAL;
   }
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;

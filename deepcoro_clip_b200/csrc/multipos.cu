@@ -31,13 +31,15 @@ int multipos_workspace_bytes(int N, int M) { return multipos_chunks(N, M) * M * 
 int multipos_fwd(const float* L, long long ldl, const float* pw, const float* mk, long long ldw, int N, int M, int mode,
                  float eps, int reduce_sum, float* rstat, float* cstat, float* coef, float* loss_out, void* workspace,
                  cudaStream_t s) {
-  if (N <= 0 || M <= 0 || (mode != 0 && mode != 1) || (!pw && !mk)) return B2_EINVAL;
+  if (N <= 0 || M <= 0 || mode < 0 || mode > 2 || (!pw && !mk)) return B2_EINVAL;
   const int ch = multipos_chunks(N, M);
-  mp_row_stats_kernel<<<N, 256, 0, s>>>(L, ldl, pw, mk, ldw, N, M, reinterpret_cast<float4*>(rstat));
+  float* imp_r = mode == 2 ? coef : nullptr;          // importance sums travel in coef (finalize reads, then overwrites)
+  float* imp_c = mode == 2 ? coef + N : nullptr;
+  mp_row_stats_kernel<<<N, 256, 0, s>>>(L, ldl, pw, mk, ldw, N, M, reinterpret_cast<float4*>(rstat), imp_r);
   mp_col_partial_kernel<<<dim3((M + 127) / 128, ch), 128, 0, s>>>(L, ldl, pw, mk, ldw, N, M, ch,
-                                                                 reinterpret_cast<MpAcc*>(workspace));
+                                                                 reinterpret_cast<MpAcc*>(workspace), mode == 2);
   mp_col_merge_kernel<<<(M + 127) / 128, 128, 0, s>>>(reinterpret_cast<const MpAcc*>(workspace), M, ch,
-                                                      reinterpret_cast<float4*>(cstat));
+                                                      reinterpret_cast<float4*>(cstat), imp_c);
   mp_finalize_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const float4*>(rstat), reinterpret_cast<const float4*>(cstat), N,
                                         M, mode, eps, reduce_sum, coef, loss_out);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;

@@ -50,8 +50,30 @@ int clip_finalize(const float* sums, int n, int nvec, const float* dyn, float ep
   if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out || (nvec != 3 && nvec != 7)) return B2_EINVAL;
   int blocks = (n + 1023) / 1024;
   if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
-  clip_finalize_kernel<<<blocks, 1024, 0, s>>>(sums, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out,
-                                               acc_out);
+  FinPeers ps{};
+  ps.ptr[0] = sums;
+  ps.world = 0;
+  ps.rows_per_rank = n;
+  clip_finalize_kernel<<<blocks, 1024, 0, s>>>(ps, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int clip_finalize_peers(const float* const* peer_sums_host, int world, int n, int nvec, const float* dyn, float eps, int gated,
+                        const double* unif, float* rowscale, float* colscale, float* loss_out, double* acc_out,
+                        cudaStream_t s) {
+  if (n <= 0 || !peer_sums_host || world < 1 || world > FIN_MAX_PEERS || n % world || !dyn || !rowscale || !colscale ||
+      !loss_out || (nvec != 3 && nvec != 7))
+    return B2_EINVAL;
+  int blocks = (n + 1023) / 1024;
+  if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
+  FinPeers ps{};
+  for (int r = 0; r < world; ++r) {
+    if (!peer_sums_host[r]) return B2_EINVAL;
+    ps.ptr[r] = peer_sums_host[r];
+  }
+  ps.world = world;
+  ps.rows_per_rank = n / world;
+  clip_finalize_kernel<<<blocks, 1024, 0, s>>>(ps, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -153,8 +153,28 @@ constexpr int FIN_MAX_BLOCKS = 64;
 __device__ double g_fin_partial[3 * FIN_MAX_BLOCKS];
 __device__ unsigned int g_fin_ticket = 0;
 
+// Peer view of the statistics (multi-GPU one-shot exchange, replaces the NCCL all-reduce of the nvec * n floats): every rank
+// accumulates into its OWN symmetric-memory block; after a cross-rank barrier the finalize kernel of every rank reads the
+// blocks of all W peers directly (ld.global over NVLink): vector 0 (partial column sums of every rank's row slab) is summed
+// over the peers, the other vectors are read from the one rank that owns the row (rows_per_rank = n / W).
+constexpr int FIN_MAX_PEERS = 8;
+struct FinPeers {
+  const float* ptr[FIN_MAX_PEERS];
+  int world;            // 0: single block (ptr[0] holds fully reduced sums)
+  int rows_per_rank;
+};
+__device__ __forceinline__ float fin_ld(const FinPeers& ps, int n, int vec, int i) {
+  if (ps.world <= 1) return ps.ptr[0][(size_t)vec * n + i];
+  if (vec == 0) {
+    float s = 0.f;
+    for (int r = 0; r < ps.world; ++r) s += ps.ptr[r][i];          // fixed order: bit-identical on every rank
+    return s;
+  }
+  return ps.ptr[i / ps.rows_per_rank][(size_t)vec * n + i];
+}
+
 __global__ void __launch_bounds__(1024)
-clip_finalize_kernel(const float* __restrict__ sums, int n, int nvec, const float* __restrict__ dyn, float eps, int gated,
+clip_finalize_kernel(FinPeers sums, int n, int nvec, const float* __restrict__ dyn, float eps, int gated,
                      const double* __restrict__ unif, float* __restrict__ rowscale, float* __restrict__ colscale,
                      float* __restrict__ loss_out, double* __restrict__ acc_out) {
   const float c = 0.5f / (float)n;
@@ -164,23 +184,23 @@ clip_finalize_kernel(const float* __restrict__ sums, int n, int nvec, const floa
   const float l2c = log2f(c);
   double a_row = 0.0, a_col = 0.0, a_dot = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double d = (double)sums[2 * n + i];
+    const double d = (double)fin_ld(sums, n, 2, i);
     const double fd = gated ? d / (1.0 + exp(-d)) : d;
     double fx = fd, fdc = fd;                                // fp32 target logit / the column sweep's tensor-core value
     if (ext) {
-      const double dx = (double)sums[5 * n + i];
+      const double dx = (double)fin_ld(sums, n, 5, i);
       fx = gated ? dx / (1.0 + exp(-dx)) : dx;
     }
     double tr, tc;
     if (stable) {
-      rowscale[i] = sums[3 * n + i] - l2c;
-      colscale[i] = sums[4 * n + i] - l2c;
-      tr = 0.6931471805599453 * (double)sums[n + i];
-      tc = 0.6931471805599453 * (double)sums[i];
-      const double dc = (double)sums[6 * n + i];
+      rowscale[i] = fin_ld(sums, n, 3, i) - l2c;
+      colscale[i] = fin_ld(sums, n, 4, i) - l2c;
+      tr = 0.6931471805599453 * (double)fin_ld(sums, n, 1, i);
+      tc = 0.6931471805599453 * (double)fin_ld(sums, n, 0, i);
+      const double dc = (double)fin_ld(sums, n, 6, i);
       fdc = gated ? dc / (1.0 + exp(-dc)) : dc;
     } else {
-      const float cs = sums[i], rs = sums[n + i];
+      const float cs = fin_ld(sums, n, 0, i), rs = fin_ld(sums, n, 1, i);
       colscale[i] = c / cs;
       rowscale[i] = c / rs;
       tr = (double)logf(rs) + shift - fd * inv_tau;

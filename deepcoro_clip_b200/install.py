@@ -87,6 +87,17 @@ def install(reference_root: str | None = None, semantics: str = "main", losses: 
                     mod.AttentionPoolWithCLS = attention_pool.AttentionPoolWithCLS
                 if hasattr(mod, "EnhancedVideoAggregator"):
                     mod.EnhancedVideoAggregator = video_aggregator.EnhancedVideoAggregator
+                # token pooling over the views (models/video_encoder.py:589-603): one batched pass instead of a Python loop
+                # over the views; the mean branch (:603) becomes the pool kernel's uniform-weights mode
+                enc = getattr(mod, "VideoEncoder", None)
+                if enc is not None and hasattr(enc, "_pool_video_tokens") and not hasattr(enc._pool_video_tokens, "reference"):
+                    def _pool(self, token_feats):
+                        if token_feats.is_cuda and token_feats.dim() == 4:
+                            return attention_pool.pool_video_tokens(self, token_feats)
+                        return _pool.reference(self, token_feats)
+                    _pool.reference = enc._pool_video_tokens
+                    enc._pool_video_tokens = _pool
+                    report["modules"].append(modname + ".VideoEncoder._pool_video_tokens")
                 report["modules"].append(modname)
         for modname, names in (("models.rope_3d", ("Rope3D", "apply_rope_qk")), ("models.attention_pool", ("AttentionPool", "AttentionPoolWithCLS")),
                                ("models.video_aggregator", ("EnhancedVideoAggregator",))):

@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import dist_plan, ops
+from . import dist_plan, ops, symm
 from ._lib import B200ClipError
 
 BW_CLIP, BW_GATED, BW_SIGLIP, BW_SIGLIP_ENT = 0, 1, 2, 3
@@ -49,6 +49,15 @@ def _pick_precision(precision: str, n_rows: int, n_cols: int) -> bool:
     return n_rows * n_cols <= 4096 * 4096
 
 
+class _SymmToken:
+    """Lives as long as the autograd graph of one forward: the symmetric operand slot it used stays reserved."""
+    __slots__ = ("__weakref__",)
+
+
+def _symm_eligible(x: torch.Tensor) -> bool:
+    return x.stride(1) == 1 and x.data_ptr() % 16 == 0 and (x.stride(0) * x.element_size()) % 16 == 0
+
+
 class _ClipLossFn(torch.autograd.Function):
     """Softmax-CE both directions, diagonal targets.
 
@@ -69,26 +78,59 @@ class _ClipLossFn(torch.autograd.Function):
         mode = BW_GATED if gated else BW_CLIP
         st = ops.stream_ptr(dev)
 
-        # text operands first: their all-gather overlaps the video normalise; the video all-gather (needed only by the
-        # backward's text-side pass) overlaps the forward tile kernel
-        top, tinv, Kp = ops.l2norm_operand(text, 1 if x3 else -1)
-        tall, t_work = dist_plan.gather_rows_async(top, W, group)
-        vop, vinv, _ = ops.l2norm_operand(video, 0 if x3 else -1)
-        vall, v_work = dist_plan.gather_rows_async(vop, W, group)
-        K = vop.shape[1]
+        lo = rank * B
+        vraw, traw = ops._rowmajor(video.detach()), ops._rowmajor(text.detach())
+        # Multi-GPU exchange over symmetric memory (symm.py): the normalise kernel stores the operand rows into every rank's
+        # [N, ld] buffer (normalise + all-gather in one launch), the statistics are read from the peers by the finalize
+        # kernel (one-shot exchange instead of an all-reduce). Falls back to the NCCL collectives when unavailable.
+        plan = slot = token = None
+        if W > 1 and not x3 and D % 8 == 0 and ops.round_up(D, 64) <= 1024 and _symm_eligible(vraw) and _symm_eligible(traw):
+            plan = symm.get_plan(group, N, ops.round_up(D, 64), dev)
+            if plan is not None:
+                token = _SymmToken()
+                slot = plan.acquire(token)
+                if slot is None:
+                    plan = None
+        if plan is not None:
+            Kp = K = ops.round_up(D, 64)
+            if torch.cuda.is_current_stream_capturing():
+                plan.barrier_ops()        # a replayed graph reuses THIS slot every step: wait until every rank left the last one
+            vall, tall = plan.ops[slot, 0], plan.ops[slot, 1]
+            tinv = torch.empty(B, dtype=torch.float32, device=dev)
+            vinv = torch.empty(B, dtype=torch.float32, device=dev)
+            ops.call("l2norm_fwd_multi", traw, ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), B, D,
+                     plan.op_ptrs[slot][1], W, ops.i64(lo), K, Kp, tinv, 1, st)
+            ops.call("l2norm_fwd_multi", vraw, ops.DTYPE_CODE[vraw.dtype], ops.i64(vraw.stride(0)), B, D,
+                     plan.op_ptrs[slot][0], W, ops.i64(lo), K, Kp, vinv, 1, st)
+            plan.barrier_ops()            # every rank's rows have landed in every buffer
+            vop, top = vall[lo:lo + B], tall[lo:lo + B]
+            t_work = v_work = None
+        else:
+            # text operands first: their all-gather overlaps the video normalise; the video all-gather (needed only by
+            # the backward's text-side pass) overlaps the forward tile kernel
+            top, tinv, Kp = ops.l2norm_operand(text, 1 if x3 else -1)
+            tall, t_work = dist_plan.gather_rows_async(top, W, group)
+            vop, vinv, _ = ops.l2norm_operand(video, 0 if x3 else -1)
+            vall, v_work = dist_plan.gather_rows_async(vop, W, group)
+            K = vop.shape[1]
         dyn = ops.dyn_prep(log_temp, None, clamp_min, ops.GATED_BOUND if gated else 1.0)
         if stable is not None:              # A/B override of the device-side choice (tests, tools)
             ops.call("dyn_set_stable", dyn, int(bool(stable)), st)
 
-        # arena: [colsum (N) | rowsum (N) | dots (N) | lse2 rows (N) | lse2 columns (N) | fp32 dots (N) | column-sweep dots
-        # (N)] zeroed (other ranks' slices stay 0 for the all-reduce) | scales (2N) | tickets of the stable sweeps (2B int32)
-        ws = torch.zeros(9 * N + 2 * B + 2, dtype=torch.float32, device=dev)
-        sums = ws[:7 * N]
-        lo = rank * B
+        # statistics: [colsum (N) | rowsum (N) | dots (N) | lse2 rows (N) | lse2 columns (N) | fp32 dots (N) | column-sweep
+        # dots (N)] zeroed (other ranks' slices stay 0) — this rank's symmetric block, or a local arena that is all-reduced —
+        # then scales (2N) | tickets of the stable sweeps (2B int32)
+        if plan is not None:
+            sums = plan.stats[slot]
+            sums.zero_()
+            ws = torch.zeros(2 * N + 2 * B + 2, dtype=torch.float32, device=dev)
+        else:
+            ws_all = torch.zeros(9 * N + 2 * B + 2, dtype=torch.float32, device=dev)
+            sums = ws_all[:7 * N]
+            ws = ws_all[7 * N:]
         # target logits S_ii from the raw features in fp32 (local pairs: video row r <-> text row r)
-        vraw, traw = ops._rowmajor(video.detach()), ops._rowmajor(text.detach())
         ops.call("rowdot_raw", vraw, ops.DTYPE_CODE[vraw.dtype], ops.i64(vraw.stride(0)), vinv, traw,
-                 ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), tinv, B, D, ws[5 * N + lo:5 * N + lo + B], st)
+                 ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), tinv, B, D, sums[5 * N + lo:5 * N + lo + B], st)
         if t_work is not None:
             t_work.wait()
         # Fixed-shift sweep (row + column sums in one pass) and the stable pair of row-LSE sweeps (running maxima; the
@@ -96,29 +138,26 @@ class _ClipLossFn(torch.autograd.Function):
         # dyn_prep from tau on the device, lets exactly one variant run (the other grid returns at once), so a learnable
         # temperature is never read by the host. tau >= ~0.013 (every shipped config): fixed shift.
         ops.call("logits_lse_fwd", vop, tall, B, N, K, vop.stride(0), tall.stride(0), 0.0, 0.0, int(gated), dyn, 1,
-                 ws[N + lo:N + lo + B], ws[:N], ws[2 * N + lo:2 * N + lo + B], lo, st)
+                 sums[N + lo:N + lo + B], sums[:N], sums[2 * N + lo:2 * N + lo + B], lo, st)
         slots = ops._lib.lib().b200clip_rowlse_slots(B, N, K)
         part = torch.empty(2 * B * slots * 2, dtype=torch.float32, device=dev)
-        tick = ws[9 * N:9 * N + 2 * B].view(torch.int32)
+        tick = ws[2 * N:2 * N + 2 * B].view(torch.int32)
         ops.call("logits_rowlse", vop, tall, B, N, K, vop.stride(0), tall.stride(0), int(gated), dyn, 1, part[:2 * B * slots],
-                 slots, tick[:B], ws[3 * N + lo:3 * N + lo + B], ws[2 * N + lo:2 * N + lo + B], lo,
-                 ws[N + lo:N + lo + B], st)
+                 slots, tick[:B], sums[3 * N + lo:3 * N + lo + B], sums[2 * N + lo:2 * N + lo + B], lo,
+                 sums[N + lo:N + lo + B], st)
         if v_work is not None:
             v_work.wait()
             v_work = None
         ops.call("logits_rowlse", top, vall, B, N, K, top.stride(0), vall.stride(0), int(gated), dyn, 1, part[2 * B * slots:],
-                 slots, tick[B:], ws[4 * N + lo:4 * N + lo + B], ws[6 * N + lo:6 * N + lo + B], lo, ws[lo:lo + B], st)
-        if W > 1:
+                 slots, tick[B:], sums[4 * N + lo:4 * N + lo + B], sums[6 * N + lo:6 * N + lo + B], lo, sums[lo:lo + B], st)
+        if W > 1 and plan is None:
             dist.all_reduce(sums, group=group)
-        rowscale_all = ws[7 * N:8 * N]
-        colscale_all = ws[8 * N:9 * N]
+        rowscale_all = ws[:N]
+        colscale_all = ws[N:2 * N]
         unif_tgt = vsum = tsum = None
         if eps != 0.0:
             if gated:
                 raise B200ClipError("label_smoothing is not defined for the gated legacy loss")
-            if v_work is not None:
-                v_work.wait()
-                v_work = None
             vsum = ops.colsum_bf16(vall[:, K - Kp:], N, D)      # hi panel (last in bf16x3 mode)
             tsum = ops.colsum_bf16(tall[:, K - Kp:], N, D)
             if x3:
@@ -128,9 +167,13 @@ class _ClipLossFn(torch.autograd.Function):
                 ops.colsum_bf16(tall[:, Kp:2 * Kp], N, D, out=tsum)
             unif_tgt = ((eps / N) * torch.dot(vsum.double(), tsum.double()) * dyn[2].double()).reshape(1)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
-        ops.call("clip_finalize", sums, N, 7, dyn, eps, int(gated), unif_tgt, rowscale_all, colscale_all, loss, None, st)
-        if v_work is not None:
-            v_work.wait()                  # vall is read by the backward only
+        if plan is not None:
+            plan.barrier_stats()          # every rank's block is complete: read the peers' blocks directly
+            ops.call("clip_finalize_peers", plan.stat_ptrs[slot], W, N, 7, dyn, eps, int(gated), unif_tgt, rowscale_all,
+                     colscale_all, loss, None, st)
+        else:
+            ops.call("clip_finalize", sums, N, 7, dyn, eps, int(gated), unif_tgt, rowscale_all, colscale_all, loss, None, st)
+        ctx.symm = (plan, slot, token)
 
         ctx.save_for_backward(video, text, vop, top, vall, tall, vinv, tinv, dyn, rowscale_all, colscale_all, vsum, tsum,
                               unif_tgt)
@@ -187,6 +230,9 @@ class _ClipLossFn(torch.autograd.Function):
             dlt = torch.empty(1, dtype=torch.float32, device=dev)
             ops.call("clip_dlogtemp", scal, dyn, gmul, unif_tgt, N, dlt, ops.stream_ptr(dev))
             dLT = (dlt if lt_dtype == torch.float32 else dlt.to(lt_dtype)).reshape(lt_shape)
+        plan, slot, token = ctx.symm
+        if plan is not None:
+            plan.release(slot, token)      # the operand slot may be overwritten by the step after next
         return dV, dT, dLT, None, None, None, None, None, None, None
 
 

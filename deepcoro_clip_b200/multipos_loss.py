@@ -86,9 +86,6 @@ class MultiPositiveInfoNCELoss(nn.Module):
         super().__init__()
         if reduction not in {"mean", "sum"}:
             raise ValueError(f"Unsupported reduction '{reduction}'. Expected 'mean' or 'sum'.")
-        if use_importance_weighting:
-            raise NotImplementedError("use_importance_weighting=True is not provided by the B200 kernels (the registry "
-                                      "constructs the class with the default False)")
         self.reduction = reduction
         self.use_importance_weighting = use_importance_weighting
 
@@ -100,4 +97,6 @@ class MultiPositiveInfoNCELoss(nn.Module):
             raise ValueError("pos_mask must match logits shape.")
         if pos_weights is not None and pos_weights.shape != logits.shape:
             raise ValueError("pos_weights must match logits shape.")
-        return _MultiPosFn.apply(logits, pos_weights, pos_mask, 1, 0.0, int(self.reduction == "sum"))
+        # mode 2: rows / columns weighted by their summed raw importance (pos_weights, else pos_mask), :57-93
+        return _MultiPosFn.apply(logits, pos_weights, pos_mask, 2 if self.use_importance_weighting else 1, 0.0,
+                                 int(self.reduction == "sum"))

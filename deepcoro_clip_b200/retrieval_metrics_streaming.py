@@ -167,6 +167,22 @@ def streaming_topk(video_features, text_features, k: int, *, normalize: bool = F
 
 
 @torch.no_grad()
+def inference_topk_indices(video_embeddings: torch.Tensor, text_embeddings: torch.Tensor, topk: int, **kw) -> torch.Tensor:
+    """``inference()``'s retrieval step (runners/video_constrative_learning_runner.py:1757-1758):
+    ``torch.topk(video_embeddings @ text_embeddings.t(), k=topk, dim=1)[1]`` — [N, topk] int64 indices, without the
+    [N, M] similarity matrix. Ties go to the lowest index (torch.topk leaves them unspecified)."""
+    return streaming_topk(video_embeddings, text_embeddings, min(int(topk), text_embeddings.shape[0]), **kw)[1]
+
+
+@torch.no_grad()
+def top5_predictions(video_embeddings: torch.Tensor, text_embeddings: torch.Tensor, k: int = 5, **kw):
+    """The per-row ``torch.topk(similarity_matrix[i], k=min(5, M))`` of ``save_retrieval_results``
+    (utils/wandb_logger.py:951-957) for ALL rows at once from the embeddings: (scores [N, k] fp32, indices [N, k] int64);
+    one sweep instead of N host-driven top-k calls with two ``.item()`` per entry."""
+    return streaming_topk(video_embeddings, text_embeddings, min(int(k), text_embeddings.shape[0]), **kw)
+
+
+@torch.no_grad()
 def compute_recall_at_k_streaming(video_features: torch.Tensor, text_features: torch.Tensor,
                                   ground_truth_indices: torch.Tensor, k_values: List[int] = [1, 5, 10, 50],
                                   video_chunk_size: int = 2048, text_chunk_size: int = 8192, device: str = "cuda",

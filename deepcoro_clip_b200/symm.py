@@ -1,0 +1,116 @@
+"""Symmetric-memory plan of the multi-GPU row-slab CLIP path (one 8 x B200 box, NVLink 5 / NVSwitch).
+
+The NCCL version of the step had three collectives on its critical path: the all-gather of the text operands in front of
+the forward, the all-gather of the video operands, and the latency-bound all-reduce of the per-row / per-column statistics
+in front of the finalize kernel (~100 us of a 0.75 ms step at 8 ranks). Here the exchange is done by
+the producing / consuming kernels themselves over peer memory:
+
+  * operands : the normalise kernel stores every bf16 operand row into the [N, ld] operand buffer of EVERY rank
+               (b200clip_l2norm_fwd_multi: st.global to the peers' symmetric-memory blocks) - normalise + all-gather in one
+               launch, followed by ONE cross-rank barrier for both operands;
+  * statistics: every rank accumulates into its own block; after a second barrier the finalize kernel of every rank reads
+               the W blocks directly (b200clip_clip_finalize_peers) - a one-shot exchange instead of an all-reduce.
+
+Buffers are allocated once per (group, N, ld) with torch.distributed._symmetric_memory (PyTorch supplies the allocation,
+the peer pointers and the barrier kernel: plumbing) and DOUBLE-BUFFERED by step parity: step k + 2 may overwrite the slot
+of step k only after the barriers of step k + 1, which every rank reaches after finishing step k in stream order. A third
+forward before the backward of the first (three live autograd graphs on the same plan) would break that; the plan counts
+live slots and falls back to the NCCL path instead.
+
+Opt-out: B200CLIP_SYMM=0 keeps the NCCL collectives (the A/B baseline; also used automatically when symmetric memory
+cannot be set up - e.g. gloo / CPU tests, bf16x3 operands, odd embedding widths)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import weakref
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+_PLANS: Dict[Tuple, "SymmPlan"] = {}
+_FAILED = set()
+
+
+def enabled() -> bool:
+    return os.environ.get("B200CLIP_SYMM", "1") != "0"
+
+
+class SymmPlan:
+    """Symmetric operand / statistics buffers of one (process group, N, ld) CLIP problem."""
+
+    NVEC = 7
+
+    def __init__(self, group, N: int, ld: int, dev: torch.device):
+        import torch.distributed._symmetric_memory as symm_mem
+        pg = group if group is not None else dist.group.WORLD
+        self.W, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
+        self.N, self.ld = N, ld
+        # [slot][video | text][N, ld] bf16 operands; [slot][NVEC * N] fp32 statistics
+        self.ops = symm_mem.empty((2, 2, N, ld), dtype=torch.bfloat16, device=dev)
+        self.stats = symm_mem.empty((2, self.NVEC * N), dtype=torch.float32, device=dev)
+        self.h_ops = symm_mem.rendezvous(self.ops, pg)
+        self.h_stats = symm_mem.rendezvous(self.stats, pg)
+        self.step = 0
+        self.live = [None, None]              # weak references to the autograd contexts that still need a slot's operands
+        op_bytes = N * ld * 2
+        st_bytes = self.NVEC * N * 4
+
+        def arr(ptrs):
+            return (ctypes.c_void_p * len(ptrs))(*ptrs)
+        # peer pointer tables (host arrays handed to the C ABI): [slot][video | text] and [slot]
+        self.op_ptrs = [[arr([int(p) + (2 * s + side) * op_bytes for p in self.h_ops.buffer_ptrs]) for side in (0, 1)]
+                        for s in (0, 1)]
+        self.stat_ptrs = [arr([int(p) + s * st_bytes for p in self.h_stats.buffer_ptrs]) for s in (0, 1)]
+
+    def acquire(self, owner) -> Optional[int]:
+        """Next slot, or None when the slot is still referenced by a live autograd graph (caller uses the NCCL path)."""
+        s = self.step & 1
+        ref = self.live[s]
+        if ref is not None and ref() is not None:
+            return None
+        self.live[s] = weakref.ref(owner) if owner is not None else None
+        self.step += 1
+        return s
+
+    def release(self, slot: int, owner) -> None:
+        ref = self.live[slot]
+        if ref is not None and ref() is owner:
+            self.live[slot] = None
+
+    def barrier_ops(self) -> None:
+        self.h_ops.barrier(channel=0)
+
+    def barrier_stats(self) -> None:
+        self.h_stats.barrier(channel=0)
+
+
+def get_plan(group, N: int, ld: int, dev: torch.device) -> Optional[SymmPlan]:
+    """The cached plan, created collectively on first use (every rank of the group reaches this call with the same
+    arguments: the loss is called by all ranks in lock step). None when symmetric memory is unavailable."""
+    if not enabled() or not dist.is_available() or not dist.is_initialized():
+        return None
+    pg = group if group is not None else dist.group.WORLD
+    if dist.get_backend(pg) != "nccl" or dist.get_world_size(pg) > 8:
+        return None
+    key = (id(pg), N, ld, dev.index)
+    if key in _PLANS:
+        return _PLANS[key]
+    if (id(pg), dev.index) in _FAILED:
+        return None
+    ok = torch.ones(1, device=dev)
+    plan = None
+    try:
+        plan = SymmPlan(pg, N, ld, dev)
+    except Exception as e:       # noqa: BLE001 - any failure of the optional fast path selects the NCCL path on ALL ranks
+        ok.zero_()
+        if dist.get_rank(pg) == 0:
+            print(f"[deepcoro_clip_b200] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL collectives",
+                  flush=True)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=pg)      # one-time agreement (set-up only, never per step)
+    if ok.item() == 0:
+        _FAILED.add((id(pg), dev.index))
+        return None
+    _PLANS[key] = plan
+    return plan

@@ -52,6 +52,16 @@ int b200clip_l2norm_fwd(const void* x, int dtype, int64_t ldx, int rows, int dim
                         int Kp, int split3_role, float* inv_norm, float* xhat_f32, int ld_hat, int normalize,
                         void* stream);
 
+/* K1m Normalise + all-gather in ONE kernel (multi-GPU row-slab path; replaces F.normalize followed by gather_with_gradient's
+ *     all_gather, utils/loss/contrastive.py:75-101, 142-147): every bf16 operand row r is stored at row row_offset + r of
+ *     EACH of the n_operands [N, ld_out] buffers listed in the HOST array operands_host — the same symmetric-memory
+ *     allocation on every rank of the job, remote ones written with plain stores over NVLink / NVSwitch. The caller runs a
+ *     cross-rank barrier after the launch. Plain bf16 operands only; dim % 8 == 0, Kp <= 1024, 16-byte aligned rows;
+ *     n_operands <= 8. */
+int b200clip_l2norm_fwd_multi(const void* x, int dtype, int64_t ldx, int rows, int dim, void* const* operands_host,
+                              int n_operands, int64_t row_offset, int ld_out, int Kp, float* inv_norm, int normalize,
+                              void* stream);
+
 /* K4  normalise backward (autograd of F.normalize) fused with the rank-sparse gradient corrections:
  *   g  = gmul * ( gscale * dxhat[r] + omul * (res_r * yh_r + gb_r * (yh_r - yhi_r)) + (ucoef * omul) * usum )
  *   dx = (g - (g . xhat) xhat) * inv_norm,   xhat = x * inv_norm (recomputed in fp32 from the caller's input)
@@ -201,6 +211,13 @@ int b200clip_diag_sum(const void* a, int lda, const void* b, int ldb, int rows, 
  * clip_dlogtemp: out[0] = (unif / n - scal0[0] / tau) * [tau not clamped] * gmul[0]  (d loss / d log_temp). */
 int b200clip_clip_finalize(const float* sums, int n, int nvec, const float* dyn, float eps, int gated, const double* unif,
                            float* rowscale, float* colscale, float* loss_out, double* acc_out, void* stream);
+/* clip_finalize over the PEERS' statistics blocks (one-shot exchange instead of an all-reduce): peer_sums_host is a HOST
+ * array of `world` device pointers (<= 8), block r = the nvec * n floats rank r accumulated (symmetric memory; the caller
+ * runs a cross-rank barrier first). Vector 0 is summed over the peers in rank order, vectors 1.. are read from the rank
+ * that owns the row (n / world rows per rank). Everything else as b200clip_clip_finalize. */
+int b200clip_clip_finalize_peers(const void* const* peer_sums_host, int world, int n, int nvec, const float* dyn, float eps,
+                                 int gated, const double* unif, float* rowscale, float* colscale, float* loss_out,
+                                 double* acc_out, void* stream);
 int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
                            float* out, void* stream);
 /* Alignment diagnostics of a batch from the same forward statistics, instead of the dense [B, B] similarity +
@@ -276,7 +293,8 @@ int b200clip_siglip_pos(const void* video, int ldv, const void* text, int ldt, i
 /* ------------------------------------------------------------------------------------------------
  * Multi-positive softmax cross-entropy over MATERIALISED fp32 logits [n_rows, n_cols]. Replaces
  * WeightedSigLIPLoss.forward (utils/loss/weighted_siglip.py:18-51; mode 0, eps) and MultiPositiveInfoNCELoss.forward
- * (utils/loss/multi_positive_infonce.py:30-100; mode 1, reduce_sum = 0 mean / 1 sum, no importance weighting).
+ * (utils/loss/multi_positive_infonce.py:30-100; mode 1, reduce_sum = 0 mean / 1 sum; mode 2 = the same with
+ * use_importance_weighting=True, :57-93: selected rows / columns weighted by their summed raw pos_weights / pos_mask).
  *   w_ij = max(0, pos_weights_ij [* pos_mask_ij]) (either may be NULL, not both; same row stride ld_w).
  *   multipos_fwd : rstat [n_rows][4] / cstat [n_cols][4] = {logsumexp, sum w L, sum w, #mask > 0} per row / column (one
  *                  read of logits and weights per direction), coef [n_rows + n_cols] gradient coefficients, loss_out[0];

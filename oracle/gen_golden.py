@@ -149,7 +149,11 @@ def multipos():
         rec = dict(logits=logits.numpy(), mask=mask.numpy(), pos_weights=pw.numpy())
         for key, fn in (("wsl", lambda L: WeightedSigLIPLoss()(L, mask * pw - 0.2 * (1 - mask))),      # negatives clamp to 0
                         ("mpi_mean", lambda L: MultiPositiveInfoNCELoss()(L, mask, pw)),
-                        ("mpi_sum_noweights", lambda L: MultiPositiveInfoNCELoss(reduction="sum")(L, mask))):
+                        ("mpi_sum_noweights", lambda L: MultiPositiveInfoNCELoss(reduction="sum")(L, mask)),
+                        # use_importance_weighting (:57-93): rows / columns weighted by their summed raw pos_weights / mask
+                        ("mpi_imp_mean", lambda L: MultiPositiveInfoNCELoss(use_importance_weighting=True)(L, mask, pw)),
+                        ("mpi_imp_sum_noweights", lambda L: MultiPositiveInfoNCELoss(
+                            reduction="sum", use_importance_weighting=True)(L, mask))):
             L = logits.clone().requires_grad_(True)
             loss = fn(L)
             loss.backward()
@@ -157,6 +161,21 @@ def multipos():
             rec[key + "_dlogits"] = _np(L.grad)
         np.savez_compressed(OUT / f"{name}.npz", **rec)
         print(name, {k: float(v) for k, v in rec.items() if k.endswith("_loss")})
+
+
+def tokenmean():
+    """the mean branch of VideoEncoder._pool_video_tokens (models/video_encoder.py:589-603), called as
+    the UNBOUND reference method on a stub whose attention_pool is None (the encoder itself needs backbone weights)."""
+    import types
+    from models.video_encoder import VideoEncoder
+    for name, B, N, L, D, seed in (("tokenmean_b2_n3_l50_d128", 2, 3, 50, 128, 70), ("tokenmean_b1_n2_l197_d256", 1, 2, 197, 256, 71)):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(B, N, L, D, generator=g, requires_grad=True)
+        dout = torch.randn(B, N, D, generator=g)
+        y = VideoEncoder._pool_video_tokens(types.SimpleNamespace(attention_pool=None), x)
+        y.backward(dout)
+        np.savez_compressed(OUT / f"{name}.npz", x=x.detach().numpy(), dout=dout.numpy(), out=_np(y), dx=_np(x.grad))
+        print(name, float(y.abs().mean()))
 
 
 def alignment():
@@ -401,6 +420,6 @@ def qpool():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "alignment", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool"]
+    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "tokenmean", "alignment", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool"]
     for name in which:
         globals()[name]()

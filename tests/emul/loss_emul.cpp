@@ -104,7 +104,11 @@ extern "C" int b200clip_clip_finalize(const float* sums, int n, int nvec, const 
   if (n <= 0 || !sums || !dyn || !rowscale || !colscale || !loss_out || (nvec != 3 && nvec != 7)) return -22;
   int blocks = (n + 1023) / 1024;
   if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
-  emul::launch(blocks, 1024, [&] { clip_finalize_kernel(sums, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out); });
+  FinPeers ps{};
+  ps.ptr[0] = sums;
+  ps.world = 0;
+  ps.rows_per_rank = n;
+  emul::launch(blocks, 1024, [&] { clip_finalize_kernel(ps, n, nvec, dyn, eps, gated, unif, rowscale, colscale, loss_out, acc_out); });
   return 0;
 }
 extern "C" int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,

@@ -293,13 +293,16 @@ extern "C" int b200clip_multipos_workspace_bytes(int N, int M) { return mp_chunk
 extern "C" int b200clip_multipos_fwd(const float* L, long long ldl, const float* pw, const float* mk, long long ldw, int N, int M,
                                      int mode, float eps, int reduce_sum, float* rstat, float* cstat, float* coef,
                                      float* loss_out, void* workspace, void*) {
-  if (N <= 0 || M <= 0 || (mode != 0 && mode != 1) || (!pw && !mk)) return -22;
+  if (N <= 0 || M <= 0 || mode < 0 || mode > 2 || (!pw && !mk)) return -22;
   const int ch = mp_chunks(N, M);
-  emul::launch(N, 256, [&] { mp_row_stats_kernel(L, ldl, pw, mk, ldw, N, M, reinterpret_cast<float4*>(rstat)); });
+  float* imp_r = mode == 2 ? coef : nullptr;
+  float* imp_c = mode == 2 ? coef + N : nullptr;
+  emul::launch(N, 256, [&] { mp_row_stats_kernel(L, ldl, pw, mk, ldw, N, M, reinterpret_cast<float4*>(rstat), imp_r); });
   emul::launch(emul::Dim{(unsigned)((M + 127) / 128), (unsigned)ch, 1}, 128,
-               [&] { mp_col_partial_kernel(L, ldl, pw, mk, ldw, N, M, ch, reinterpret_cast<MpAcc*>(workspace)); });
-  emul::launch((M + 127) / 128, 128,
-               [&] { mp_col_merge_kernel(reinterpret_cast<const MpAcc*>(workspace), M, ch, reinterpret_cast<float4*>(cstat)); });
+               [&] { mp_col_partial_kernel(L, ldl, pw, mk, ldw, N, M, ch, reinterpret_cast<MpAcc*>(workspace), mode == 2); });
+  emul::launch((M + 127) / 128, 128, [&] {
+    mp_col_merge_kernel(reinterpret_cast<const MpAcc*>(workspace), M, ch, reinterpret_cast<float4*>(cstat), imp_c);
+  });
   emul::launch(1, 1024, [&] {
     mp_finalize_kernel(reinterpret_cast<const float4*>(rstat), reinterpret_cast<const float4*>(cstat), N, M, mode, eps,
                        reduce_sum, coef, loss_out);

@@ -83,6 +83,18 @@ def test_attention_pool_module_on_emulated_kernels(on_emulated_kernels, name):
     assert on_emulated_kernels == ["attnpool_fwd", "attnpool_merge", "attnpool_bwd_dx", "attnpool_fwd", "attnpool_merge"]
 
 
+def test_token_mean_pool_on_emulated_kernels(on_emulated_kernels):
+    """SURVEY row a12 — the mean branch of VideoEncoder._pool_video_tokens (models/video_encoder.py:603) as the pool kernel's
+    uniform-weights mode, against the golden produced by the reference method itself."""
+    from deepcoro_clip_b200.attention_pool import token_mean_pool
+    g = np.load(GOLDEN / "tokenmean_b2_n3_l50_d128.npz")
+    x = torch.tensor(g["x"], dtype=torch.float32, requires_grad=True)
+    out = token_mean_pool(x)
+    assert out.shape == g["out"].shape and _rel(out.detach().numpy(), g["out"]) < 2e-6
+    out.backward(torch.tensor(g["dout"], dtype=torch.float32))
+    assert _rel(x.grad.numpy(), g["dx"]) < 2e-6
+
+
 @pytest.mark.parametrize("name", ["clspool_b3_n50_d128_h8", "clspool_b4_n37_d128_h4_mask_proj"])
 def test_cls_pool_module_on_emulated_kernels(on_emulated_kernels, name):
     from deepcoro_clip_b200.attention_pool import AttentionPoolWithCLS
@@ -191,7 +203,10 @@ def test_multipos_loss_modules_on_emulated_kernels(on_emulated_kernels, name):
     logits, mask, pw = (torch.tensor(g[k], dtype=torch.float32) for k in ("logits", "mask", "pos_weights"))
     cases = {"wsl": lambda L: WeightedSigLIPLoss()(L, mask * pw - 0.2 * (1 - mask)),
              "mpi_mean": lambda L: MultiPositiveInfoNCELoss()(L, mask, pw),
-             "mpi_sum_noweights": lambda L: MultiPositiveInfoNCELoss(reduction="sum")(L, mask)}
+             "mpi_sum_noweights": lambda L: MultiPositiveInfoNCELoss(reduction="sum")(L, mask),
+             "mpi_imp_mean": lambda L: MultiPositiveInfoNCELoss(use_importance_weighting=True)(L, mask, pw),
+             "mpi_imp_sum_noweights": lambda L: MultiPositiveInfoNCELoss(reduction="sum",
+                                                                         use_importance_weighting=True)(L, mask)}
     for key, fn in cases.items():
         L = logits.clone().requires_grad_(True)
         loss = fn(L)

@@ -35,6 +35,8 @@ def test_multipos_losses_match_reference_golden(name):
         "wsl": lambda L: WeightedSigLIPLoss()(L, mk * pw - 0.2 * (1 - mk)),
         "mpi_mean": lambda L: MultiPositiveInfoNCELoss()(L, mk, pw),
         "mpi_sum_noweights": lambda L: MultiPositiveInfoNCELoss(reduction="sum")(L, mk),
+        "mpi_imp_mean": lambda L: MultiPositiveInfoNCELoss(use_importance_weighting=True)(L, mk, pw),
+        "mpi_imp_sum_noweights": lambda L: MultiPositiveInfoNCELoss(reduction="sum", use_importance_weighting=True)(L, mk),
     }
     for key, fn in cases.items():
         loss, dl = _run(fn, g["logits"])

@@ -158,3 +158,43 @@ def test_exact_in_bf16_probe():
     h[5, 5] = float("nan")
     assert not _exact_in_bf16(h)
     assert not _exact_in_bf16(torch.randn(64, 64, device="cuda:0"))
+
+
+def test_inference_topk_and_top5_bindings():
+    """inference()'s torch.topk over the dense similarity matrix (runners/video_constrative_learning_runner.py:1757-1758)
+    and save_retrieval_results' per-row top-5 (utils/wandb_logger.py:951-957) through streaming_topk: same indices on
+    tie-free inputs, without the [N, M] matrix."""
+    from deepcoro_clip_b200 import inference_topk_indices, top5_predictions
+    g = torch.Generator().manual_seed(11)
+    v = torch.nn.functional.normalize(torch.randn(700, 512, generator=g), dim=-1).to(DEV)
+    t = torch.nn.functional.normalize(torch.randn(1500, 512, generator=g), dim=-1).to(DEV)
+    sim = v @ t.T
+    ref_s, ref_i = torch.topk(sim, k=6, dim=1)
+    clear = (ref_s[:, :-1] - ref_s[:, 1:]).min(dim=1).values > 1e-5          # rows whose top-6 margins exceed the operand error
+    idx = inference_topk_indices(v, t, 5)
+    assert idx.shape == (700, 5) and idx.dtype == torch.int64 and clear.float().mean().item() > 0.9
+    assert (idx[clear] == ref_i[clear][:, :5]).all()
+    s5, i5 = top5_predictions(v, t)
+    assert (i5 == idx).all() and (s5[clear] - ref_s[clear][:, :5]).abs().max().item() <= 2e-5
+    assert inference_topk_indices(v, t[:3], 5).shape == (700, 3)             # k clamps to the number of texts (:951)
+
+
+def test_embedding_store_on_device_single_process():
+    """SURVEY 8f #3 on hardware: validation embeddings appended batch by batch into the device-resident store (buffer growth
+    included), then the epoch-end metrics straight from the device buffers — the reference's golden values. The ragged
+    multi-rank gather over NCCL is part of tools/gpu_check_dist.py (tests/test_gpu_multi.py)."""
+    from deepcoro_clip_b200 import EmbeddingStore, epoch_end_retrieval_metrics
+    g = np.load(GOLDEN / "retrieval_gauss_300x200.npz")
+    vs, ts = EmbeddingStore(64, capacity=32, device=DEV), EmbeddingStore(64, capacity=16, device=DEV)
+    for a in range(0, 300, 37):
+        vs.append(_t(g["video"][a:a + 37]))
+    for a in range(0, 200, 64):
+        ts.append(torch.tensor(g["text"][a:a + 64]))                 # host batches are accepted as well
+    assert vs.local().is_cuda and vs.local().shape == (300, 64) and ts.local().shape == (200, 64)
+    m = epoch_end_retrieval_metrics(vs, ts, _t(g["gt"]), k_values=(1, 5, 10, 50))
+    ref = dict(zip([str(k) for k in g["keys"]], g["values"]))
+    for k in ("Recall@1", "Recall@5", "Recall@10", "Recall@50"):
+        assert m[k] == ref[k], (k, m[k], ref[k])
+    assert abs(m["MRR_V2T"] - ref["MRR_V2T"]) < 1e-9 and abs(m["alignment_score"] - ref["alignment_score"]) < 1e-6
+    vs.reset()
+    assert vs.local().shape[0] == 0

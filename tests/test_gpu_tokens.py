@@ -374,3 +374,44 @@ def test_cls_pool_training_attention_dropout(dtype, D, N, monkeypatch):
     assert bool(torch.isfinite(o1).all()) and not torch.equal(o1, o2)
     mod.eval()
     assert torch.equal(mod(x.detach(), mask), mod(x.detach(), mask))
+
+
+@pytest.mark.parametrize("name", ["tokenmean_b2_n3_l50_d128", "tokenmean_b1_n2_l197_d256"])
+def test_token_mean_pool_matches_reference_golden(name):
+    """VideoEncoder._pool_video_tokens' mean branch (models/video_encoder.py:603) = the pool kernel with
+    uniform weights; golden from the reference method."""
+    from deepcoro_clip_b200 import token_mean_pool
+    g = np.load(GOLDEN / f"{name}.npz")
+    x = torch.tensor(g["x"], dtype=torch.float32, device=DEV, requires_grad=True)
+    out = token_mean_pool(x)
+    assert out.shape == g["out"].shape
+    assert np.abs(out.detach().cpu().numpy() - g["out"]).max() <= 2e-6 * np.abs(g["out"]).max()
+    out.backward(torch.tensor(g["dout"], dtype=torch.float32, device=DEV))
+    assert np.abs(x.grad.cpu().numpy() - g["dx"]).max() <= 2e-6 * np.abs(g["dx"]).max()
+
+
+def test_token_mean_pool_bf16_mask_and_batched_view_pooling():
+    """bf16 tokens at the study-mode shape (mean over 3,136 tokens, fp32 accumulation), the masked mean, and
+    pool_video_tokens: all views in ONE pass of the attention pool equal the reference's per-view Python loop."""
+    import types
+    from deepcoro_clip_b200 import AttentionPool, pool_video_tokens, token_mean_pool
+    torch.manual_seed(0)
+    x = torch.randn(2, 4, 3136, 512, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    out = token_mean_pool(x)
+    ref = x.detach().float().mean(dim=2)
+    assert out.dtype == torch.bfloat16 and (out.float() - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item()
+    go = torch.randn_like(out)
+    out.backward(go)
+    assert (x.grad.float() - (go.float() / 3136).unsqueeze(2).expand_as(x)).abs().max().item() <= 2.0 ** -8 * go.abs().max().item() / 3136
+    xs = torch.randn(3, 100, 256, device=DEV)
+    mask = torch.rand(3, 100, device=DEV) < 0.3
+    got = token_mean_pool(xs, mask)
+    want = (xs * (~mask).unsqueeze(-1)).sum(1) / (~mask).sum(1, keepdim=True)
+    assert (got - want).abs().max().item() <= 1e-5
+    pool = AttentionPool(256, 4).to(DEV).eval()
+    tf = torch.randn(2, 3, 77, 256, device=DEV)
+    enc = types.SimpleNamespace(attention_pool=pool)
+    batched = pool_video_tokens(enc, tf)
+    looped = torch.cat([pool(tf[:, i]).unsqueeze(1) for i in range(3)], dim=1)      # models/video_encoder.py:598-602
+    assert batched.shape == (2, 3, 256) and (batched - looped).abs().max().item() <= 1e-5
+    assert (pool_video_tokens(types.SimpleNamespace(attention_pool=None), tf) - tf.mean(dim=2)).abs().max().item() <= 1e-6

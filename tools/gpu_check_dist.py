@@ -166,6 +166,24 @@ def main():
     check("retrieval top-10 indices bit-exact", bool((i.cpu().numpy() == oi).all()), int((i.cpu().numpy() != oi).sum()))
     check("retrieval top-10 scores bit-exact", bool((s.cpu().numpy() == os_).all()), "")
 
+    # ---------------- epoch-end embedding stores: ragged NCCL gather feeding the sharded sweep ----------------
+    from pathlib import Path
+    from deepcoro_clip_b200 import EmbeddingStore, epoch_end_retrieval_metrics
+    gg = np.load(Path(__file__).resolve().parent.parent / "tests" / "golden" / "retrieval_gauss_300x200.npz")
+    cut_v = [0] + [int(300 * (q + 1) / world) + (7 if q % 2 == 0 and q + 1 < world else 0) for q in range(world)]
+    cut_v[-1] = 300
+    cut_t = [int(200 * q / world) for q in range(world)] + [200]
+    vs, ts = EmbeddingStore(64, capacity=32, device=dev), EmbeddingStore(64, capacity=16, device=dev)
+    for a in range(cut_v[rank], cut_v[rank + 1], 37):                     # uneven batches, buffer growth on the device
+        vs.append(torch.tensor(gg["video"][a:min(a + 37, cut_v[rank + 1])], device=dev))
+    ts.append(torch.tensor(gg["text"][cut_t[rank]:cut_t[rank + 1]], device=dev))
+    mets = epoch_end_retrieval_metrics(vs, ts, torch.tensor(gg["gt"][cut_v[rank]:cut_v[rank + 1]], device=dev),
+                                       k_values=(1, 5, 10, 50))
+    refm = dict(zip([str(k) for k in gg["keys"]], gg["values"]))
+    check("embedding stores: ragged gather + sharded metrics == reference golden",
+          all(mets[k] == refm[k] for k in ("Recall@1", "Recall@5", "Recall@10", "Recall@50")) and
+          abs(mets["MRR_V2T"] - refm["MRR_V2T"]) < 1e-9, {k: mets[k] for k in ("Recall@1", "Recall@10", "MRR_V2T")})
+
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.destroy_process_group()
