@@ -24,6 +24,15 @@ def _fused_dq_enabled() -> bool:
     return os.environ.get("B200CLIP_POOL_FUSED_DQ", "0") == "1"
 
 
+def _tc_splits(x: torch.Tensor, B: int, N: int, D: int, H: int) -> int:
+    """Token splits of the tcgen05 pool kernels for this problem, 0 when they do not apply (fp32 x, wide rows, > 8 heads)
+    or are switched off (B200CLIP_POOL_TC=0: the mma.sync / CUDA-core kernels, kept as the A/B baseline)."""
+    if x.dtype not in (torch.bfloat16, torch.float16) or os.environ.get("B200CLIP_POOL_TC", "1") == "0":
+        return 0
+    return int(lib().b200clip_attnpool_tc_splits(x.data_ptr(), DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)),
+                                                 B, N, D, H))
+
+
 class _StreamPool(torch.autograd.Function):
     """xbar[b, h, :] = sum_n a'[b, h, n] x[b, n],  a = softmax_n(x[b, n] . qt[h]),  a' = dropout(a)  (fp32 [B, H, D]);
     second output sa[b, h] = sum_n a'[b, h, n] (== 1 without dropout; it multiplies the value bias); third output (only
@@ -39,22 +48,28 @@ class _StreamPool(torch.autograd.Function):
         B, N, D = x.shape
         H = qt.shape[0]
         dev = x.device
-        if (D * x.element_size()) % 512 != 0 or H > 16:
-            raise ValueError(f"AttentionPool kernel needs embed_dim*itemsize % 512 == 0 and heads <= 16 (got D={D}, "
-                             f"{x.dtype}, heads={H})")
         qt32 = qt.detach().float().contiguous()
         mk = None
         if mask is not None:
             mk = mask.to(torch.bool).contiguous().view(torch.uint8)
-        S = lib().b200clip_attnpool_splits(B, N)
+        # tcgen05 path (csrc/attnpool_tc.cu) when the shape allows it: 0 = not applicable
+        S_tc = _tc_splits(x, B, N, D, H)
+        if S_tc == 0 and ((D * x.element_size()) % 512 != 0 or H > 16):
+            raise ValueError(f"AttentionPool kernel needs embed_dim*itemsize % 512 == 0 and heads <= 16 (got D={D}, "
+                             f"{x.dtype}, heads={H})")
+        S = S_tc if S_tc > 0 else lib().b200clip_attnpool_splits(B, N)
         pm = torch.empty((B, S, H), dtype=torch.float32, device=dev)
         pl = torch.empty((B, S, H), dtype=torch.float32, device=dev)
         pl2 = torch.empty((B, S, H), dtype=torch.float32, device=dev) if drop_p > 0.0 else None
         pa = torch.empty((B, S, H, D), dtype=torch.float32, device=dev)
         st = stream_ptr(dev)
-        call("attnpool_fwd", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), mk,
-             i64(mk.stride(0) if mk is not None else 0), qt32, None, i64(0), i64(0), B, N, D, H, S, pm, pl, pa,
-             float(drop_p), int(drop_seed), pl2, st)
+        if S_tc > 0:
+            call("attnpool_tc_fwd", x, DTYPE_CODE[x.dtype], mk, i64(mk.stride(0) if mk is not None else 0), qt32, B, N, D,
+                 H, S, pm, pl, pa, float(drop_p), int(drop_seed), pl2, st)
+        else:
+            call("attnpool_fwd", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), mk,
+                 i64(mk.stride(0) if mk is not None else 0), qt32, None, i64(0), i64(0), B, N, D, H, S, pm, pl, pa,
+                 float(drop_p), int(drop_seed), pl2, st)
         xbar = torch.empty((B, H, D), dtype=torch.float32, device=dev)
         m = torch.empty((B, H), dtype=torch.float32, device=dev)
         l = torch.empty((B, H), dtype=torch.float32, device=dev)
@@ -71,6 +86,7 @@ class _StreamPool(torch.autograd.Function):
         ctx.save_for_backward(x, qt32, mk if mk is not None else torch.empty(0, device=dev), xbar, m, l, sa)
         ctx.has_mask = mk is not None
         ctx.S = S
+        ctx.S_tc = S_tc
         ctx.drop = (float(drop_p), int(drop_seed))
         return xbar, sa, lse
 
@@ -87,9 +103,19 @@ class _StreamPool(torch.autograd.Function):
         dsa = dsa.float().contiguous() if (dsa is not None and drop_p > 0.0) else None
         dlse = dlse.float().contiguous() if dlse is not None else None
         dx = torch.empty((B, N, D), dtype=x.dtype, device=dev)
-        ds = torch.empty((B, H, N), dtype=torch.float32, device=dev)
         mb = i64(mk.stride(0) if mk is not None else 0)
         dqt = None
+        if ctx.S_tc > 0:
+            # one pass over x: dx and the per-split partials of the query gradient (no ds tensor, no second read of x)
+            S = ctx.S_tc
+            pdq = torch.empty((B, S, H, D), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+            call("attnpool_tc_bwd", x, DTYPE_CODE[x.dtype], mk, mb, qt32, dxbar, xbar, m, l, B, N, D, H, S, dx,
+                 sa if dsa is not None else None, dsa, drop_p if dsa is not None else 0.0, drop_seed, dlse, pdq, st)
+            if pdq is not None:
+                dqt = torch.zeros((H, D), dtype=torch.float32, device=dev)
+                call("attnpool_merge", None, None, pdq, B, S, H, D, dqt, None, None, 1, None, None, st)
+            return (dx if ctx.needs_input_grad[0] else None), dqt, None, None, None, None
+        ds = torch.empty((B, H, N), dtype=torch.float32, device=dev)
         if (ctx.needs_input_grad[1] and _fused_dq_enabled() and x.dtype in (torch.bfloat16, torch.float16) and H <= 8
                 and D % 128 == 0 and D <= 1024 and x.data_ptr() % 16 == 0):
             # query gradient from the SAME pass over x (kDq kernels): per-(b, split) partials, summed by the merge kernel

@@ -366,6 +366,28 @@ int b200clip_attnpool_bwd_dx_dq(const void* x, int dtype, int64_t x_sb, int64_t 
                             drop_p, (unsigned long long)drop_seed, dlse, part_dq, S(stream));
 }
 
+int b200clip_attnpool_tc_splits(const void* x, int dtype, int64_t x_sb, int64_t x_sn, int B, int N, int D, int heads) {
+  return attnpool_tc_ok(x, dtype, x_sb, x_sn, N, D, heads) ? attnpool_tc_splits(B, N) : 0;
+}
+
+int b200clip_attnpool_tc_fwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt, int B, int N,
+                             int D, int heads, int splits, float* part_m, float* part_l, float* part_acc, float drop_p,
+                             int64_t drop_seed, float* part_l2, void* stream) {
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !part_l2)) return B2_EINVAL;
+  if (!attnpool_tc_ok(x, dtype, (int64_t)N * D, D, N, D, heads)) return B2_ENOSYS;
+  return attnpool_tc_fwd(x, dtype, mask, mask_sb, qt, B, N, D, heads, splits, part_m, part_l, part_acc, drop_p,
+                         (unsigned long long)drop_seed, part_l2, S(stream));
+}
+
+int b200clip_attnpool_tc_bwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt,
+                             const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N, int D,
+                             int heads, int splits, void* dx, const float* sa, const float* dsa, float drop_p,
+                             int64_t drop_seed, const float* dlse, float* part_dq, void* stream) {
+  if (!attnpool_tc_ok(x, dtype, (int64_t)N * D, D, N, D, heads)) return B2_ENOSYS;
+  return attnpool_tc_bwd(x, dtype, mask, mask_sb, qt, dxbar, xbar, m, l, B, N, D, heads, splits, dx, sa, dsa, drop_p,
+                         (unsigned long long)drop_seed, dlse, part_dq, S(stream));
+}
+
 int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,
                        const float* ln_b, const float* query, const uint8_t* mask, int64_t mask_sb, int B, int N, int D,
                        float eps, float* out, const float* dout, float* dx, float* dpos, float* dln_w, float* dln_b,

@@ -167,6 +167,17 @@ int attnpool_bwd_dx_dq(const void* x, int dtype, long long sb, long long sn, con
                        int D, int H, void* dx, float* ds, const float* sa, const float* dsa, float drop_p,
                        unsigned long long drop_seed, const float* dlse, float* part_dq, cudaStream_t s);
 
+// attnpool_tc.cu: 16-bit contiguous x, heads <= 8, D % 128 == 0, D <= 512 on tcgen05 tiles (TMEM accumulators)
+bool attnpool_tc_ok(const void* x, int dtype, long long sb, long long sn, int N, int D, int H);
+int attnpool_tc_splits(int B, int N);
+int attnpool_tc_fwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, int B, int N, int D,
+                    int H, int S, float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
+                    float* part_l2, cudaStream_t s);
+int attnpool_tc_bwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, const float* dxbar,
+                    const float* xbar, const float* m, const float* l, int B, int N, int D, int H, int S, void* dx,
+                    const float* sa, const float* dsa, float drop_p, unsigned long long drop_seed, const float* dlse,
+                    float* part_dq, cudaStream_t s);
+
 // querypool.cu
 int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,
               const float* lnb, const float* q, const unsigned char* mask, long long mb, int B, int N, int D, float eps,

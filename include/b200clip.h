@@ -435,6 +435,25 @@ int b200clip_attnpool_bwd_dx_dq(const void* x, int dtype, int64_t x_sb, int64_t 
                                 const float* dsa, float drop_p, int64_t drop_seed, const float* dlse, float* part_dq,
                                 void* stream);
 
+/* K8 on tcgen05 tiles (csrc/attnpool_tc.cu): contiguous 16-bit x [B, N, D], heads <= 8, D % 128 == 0, D <= 512 (the C3
+ * shape). 64-token tiles staged once by TMA and read by the tensor core K-major (scores) and MN-major (weighted sums),
+ * accumulators in TMEM, softmax arithmetic by four epilogue warps; the backward also accumulates the query gradient in
+ * the same pass (part_dq), so x is read once forward and once backward and no [B, heads, N] tensor is written.
+ *   attnpool_tc_splits : token splits per batch row for this problem, or 0 when the tcgen05 path does not apply (the
+ *                        caller then uses attnpool_fwd / attnpool_bwd_dx above).
+ *   attnpool_tc_fwd    : partials in the format of attnpool_fwd (merged by attnpool_merge), splits = attnpool_tc_splits.
+ *   attnpool_tc_bwd    : dx [B, N, D] (input dtype) and, when part_dq [B, splits, heads, D] is given, the per-split
+ *                        partials of dqt = sum_n ds_hn x_n (every slot is written; summed by attnpool_merge(NULL, NULL,
+ *                        part_dq, ..., sum_over_b = 1)). Same c_h / dsa / dlse conventions as attnpool_bwd_dx. */
+int b200clip_attnpool_tc_splits(const void* x, int dtype, int64_t x_sb, int64_t x_sn, int B, int N, int D, int heads);
+int b200clip_attnpool_tc_fwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt, int B, int N,
+                             int D, int heads, int splits, float* part_m, float* part_l, float* part_acc, float drop_p,
+                             int64_t drop_seed, float* part_l2, void* stream);
+int b200clip_attnpool_tc_bwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt,
+                             const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N, int D,
+                             int heads, int splits, void* dx, const float* sa, const float* dsa, float drop_p,
+                             int64_t drop_seed, const float* dlse, float* part_dq, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).
  *   x [B, N, D] fp32 (strides sb, sn), pos [>=N, D] or NULL, final LayerNorm (ln_w, ln_b, eps), attn_query [D],

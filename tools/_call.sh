@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-python tools/gpu_bench_tokens.py > gpurun_out/r02_tokens_plain.log 2>&1 || { echo plain failed; tail -5 gpurun_out/r02_tokens_plain.log; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:pool_fwd_mma -s 4 -c 1 -f -o gpurun_out/r02_poolfwd python tools/gpu_bench_tokens.py > gpurun_out/r02_poolfwd_ncu.log 2>&1; echo "fwd capture rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:pool_bwd_mma -s 4 -c 1 -f -o gpurun_out/r02_poolbwd python tools/gpu_bench_tokens.py > gpurun_out/r02_poolbwd_ncu.log 2>&1; echo "bwd capture rc=$?"
+T=r02d
+timeout 300 python tools/gpu_check_pool_tc.py > gpurun_out/${T}_pool_tc.log 2>&1
+echo "pool tc rc=$? : $(tail -8 gpurun_out/${T}_pool_tc.log | cut -c1-250)"
+timeout 300 python tools/gpu_check_pool_tc.py --fp16 > gpurun_out/${T}_pool_tc_fp16.log 2>&1
+echo "pool tc fp16 rc=$? : $(tail -4 gpurun_out/${T}_pool_tc_fp16.log | cut -c1-250)"
