@@ -43,6 +43,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// TMEM -> registers in the MMA accumulator-fragment layout: 16 lanes x 64 columns; thread t receives, for each 8-column
+// group j, r[4j], r[4j+1] = (lane t/4, columns 8j + 2(t%4), +1) and r[4j+2], r[4j+3] = (lane t/4 + 8, same columns)
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// four 8x8 16-bit matrices, stored TRANSPOSED: register i of thread t holds M_i[2(t%4)][t/4] (low) and M_i[2(t%4)+1][t/4]
+// (high); row r of matrix i goes to the 16 bytes at the address supplied by thread 8i + r
+__device__ __forceinline__ void stsm_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+               ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // CTA-uniform OR over the `nthreads` threads of named barrier `id`
 __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
   uint32_t r;
@@ -122,6 +151,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
     mbar_init(acc_done, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmx);
+    // the first NS tiles start loading before anything else is set up
+    for (int i = 0; i < NS && i < T; ++i) {
+      mbar_expect_tx(&full[i], tile_bytes);
+      for (int kc = 0; kc < KC; ++kc)
+        tma_load_3d(ring + i * tile_bytes + kc * PT_BOX, &tmx, &full[i], kc * 64, (tile0 + i) * PT_TT, b);
+    }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
   // qt -> [qt_hi (rows 0..7) ; qt_lo (rows 8..15)] K-major operand, heads >= H zero
@@ -143,7 +178,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      for (int i = 0; i < T; ++i) {
+      for (int i = NS; i < T; ++i) {
         const int slot = i % NS;
         mbar_wait(&empty[slot], ((i / NS) & 1) ^ 1);
         mbar_expect_tx(&full[slot], tile_bytes);
@@ -318,7 +353,8 @@ struct PtBwdParams {
 // dynamic shared memory: ring NS x (D/64) boxes | W operand (D/64) x [32 x 64] (4 KB each: rows qt_hi, dxbar_hi, qt_lo,
 // dxbar_lo) | C operand 2 x [32 x 64] (4 KB each: rows ds_hi, a_hi, ds_lo, a_lo) | c, m, 1/l, dsa [4][8] fp32 | barriers
 template <int NS>
-__global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, PtBwdParams p) {
+__global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                                    const __grid_constant__ CUtensorMap tmdx, PtBwdParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int D = p.D, KC = D / 64, MB = D / 128;
@@ -326,7 +362,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
   const uint32_t ring = smem_u32(smem);
   const uint32_t w_op = ring + NS * tile_bytes;
   const uint32_t c_op = w_op + KC * 4096;
-  float* s_c = reinterpret_cast<float*>(smem + (size_t)NS * tile_bytes + KC * 4096 + 2 * 4096);
+  const uint32_t stage = c_op + 2 * 4096;          // 2 x [64 tokens x 128 channels] (two 8 KB boxes each): dx staging
+  float* s_c = reinterpret_cast<float*>(smem + (size_t)NS * tile_bytes + KC * 4096 + 2 * 4096 + 2 * 2 * PT_BOX);
   float* s_m = s_c + 8;
   float* s_il = s_m + 8;
   float* s_dsa = s_il + 8;
@@ -352,6 +389,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
     mbar_init(dx_empty, 128);
     fence_mbar_init();
     tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmdx);
+    for (int i = 0; i < NS && i < T; ++i) {
+      mbar_expect_tx(&full[i], tile_bytes);
+      for (int kc = 0; kc < KC; ++kc)
+        tma_load_3d(ring + i * tile_bytes + kc * PT_BOX, &tmx, &full[i], kc * 64, (tile0 + i) * PT_TT, b);
+    }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   for (int i = threadIdx.x; i < 8 * D; i += PT_THREADS) {
@@ -392,7 +435,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
 
   if (warp == 0) {
     if (elect_one()) {
-      for (int i = 0; i < T; ++i) {
+      for (int i = NS; i < T; ++i) {
         const int slot = i % NS;
         mbar_wait(&empty[slot], ((i / NS) & 1) ^ 1);
         mbar_expect_tx(&full[slot], tile_bytes);
@@ -454,7 +497,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
     const int r = q * 16 + lane;
     const unsigned char* mk = p.mask ? p.mask + (long long)b * p.mb : nullptr;
     const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    uint16_t* dx16 = reinterpret_cast<uint16_t*>(p.dx) + (size_t)b * p.N * D;
+    int blk = 0;
     for (int i = 0; i < T; ++i) {
       const int sb = i & 1;
       mbar_wait(&st_full[sb], (i >> 1) & 1);
@@ -486,35 +529,47 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&c_ready[sb]);
-      // ---- drain dx^T of this tile: thread = channel d, columns = tokens; lane pairs swap so that each lane stores two
-      //      adjacent channels of one token (32-bit stores, 64 contiguous bytes per token and half-warp) ----
+      // ---- drain dx^T of this tile: per 128-channel block, TMEM (fragment layout) -> 16-bit pairs -> stmatrix.trans into
+      //      a [64 tokens x 128 channels] staging block (rows = tokens) -> TMA store (rows past N are clipped) ----
       mbar_wait(dx_full, i & 1);
       tc_fence_after();
-      for (int mb = 0; mb < MB; ++mb) {
-        const int d = mb * 128 + q * 32 + lane;
+      for (int mb = 0; mb < MB; ++mb, ++blk) {
+        const uint32_t sbuf = stage + (blk & 1) * (2 * PT_BOX);
+        if (threadIdx.x == 64) bulk_wait_read<1>();        // the store that last read this buffer (two blocks ago) is done
+        named_bar_sync(2, 128);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int g = 0; g < 2; ++g) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + DX_COL + mb * 64 + half * 32 + lane_off, v);
+          tmem_ld_16x256b_x8(tmem_base + DX_COL + mb * 64 + (uint32_t(q * 32 + g * 16) << 16), v);
           tc_wait_ld();
+          // matrix mi = lane / 8 of each stmatrix: channels (mi & 1) * 8 .. + 7 of this 16-lane group, tokens 8 (2 jj + mi / 2) ..
+          const int mi = lane >> 3, chunk = q * 4 + g * 2 + (mi & 1);          // 16-byte chunk (8 channels) of the 128
+          const uint32_t cbase = sbuf + (chunk >> 3) * PT_BOX;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            // even lane keeps token j (its own value + the odd neighbour's), odd lane keeps token j + 1
-            const uint32_t send = (lane & 1) ? v[j] : v[j + 1];
-            const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 1);
-            const float lo = (lane & 1) ? __uint_as_float(got) : __uint_as_float(v[j]);
-            const float hi = (lane & 1) ? __uint_as_float(v[j + 1]) : __uint_as_float(got);
-            const int tok = tok0 + half * 32 + j + (lane & 1);
-            if (tok < p.N) {
-              const uint32_t packed = p.fp16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
-              *reinterpret_cast<uint32_t*>(dx16 + (size_t)tok * D + (d & ~1)) = packed;
+          for (int jj = 0; jj < 4; ++jj) {
+            const int tok = 8 * (2 * jj + (mi >> 1)) + (lane & 7);
+            uint32_t r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(v[4 * (2 * jj + (e >> 1)) + 2 * (e & 1)]);
+              const float hi = __uint_as_float(v[4 * (2 * jj + (e >> 1)) + 2 * (e & 1) + 1]);
+              r[e] = p.fp16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
             }
+            stsm_x4_trans(cbase + tok * 128 + ((((chunk & 7) ^ tok) & 7) << 4), r[0], r[1], r[2], r[3]);
           }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (threadIdx.x == 64) {
+          tma_store_3d(&tmdx, sbuf, mb * 128, tok0, b);
+          tma_store_3d(&tmdx, sbuf + PT_BOX, mb * 128 + 64, tok0, b);
+          bulk_commit();
         }
       }
       tc_fence_before();
       mbar_arrive(dx_empty);
     }
+    if (threadIdx.x == 64) bulk_wait_all();
     if (p.part_dq) {
       const int last = T - 1;
       mbar_wait(&empty[last % NS], (last / NS) & 1);        // P3 of the last tile (and everything before) complete
@@ -595,7 +650,9 @@ int attnpool_tc_splits(int B, int N) {
 }
 
 static size_t pt_fwd_smem(int D, int ns) { return (size_t)ns * (D / 64) * PT_BOX + (D / 64) * 2048 + 2 * 2048 + 64 * 4 + 16 * 8 + 16 + 1024; }
-static size_t pt_bwd_smem(int D, int ns) { return (size_t)ns * (D / 64) * PT_BOX + (D / 64) * 4096 + 2 * 4096 + 32 * 4 + 16 * 8 + 16 + 1024; }
+static size_t pt_bwd_smem(int D, int ns) {
+  return (size_t)ns * (D / 64) * PT_BOX + (D / 64) * 4096 + 2 * 4096 + 2 * 2 * PT_BOX + 32 * 4 + 16 * 8 + 16 + 1024;
+}
 
 int attnpool_tc_fwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, int B, int N, int D,
                     int H, int S, float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
@@ -620,13 +677,15 @@ int attnpool_tc_bwd(const void* x, int dtype, const unsigned char* mask, long lo
   if (!x || !qt || !dxbar || !xbar || !m || !l || !dx || S < 1 || S > (N + PT_TT - 1) / PT_TT) return B2_EINVAL;
   CUtensorMap tmx;
   if (int rc = make_tmap_x3d(&tmx, x, B, N, D)) return rc;
+  CUtensorMap tmdx;
+  if (int rc = make_tmap_x3d(&tmdx, dx, B, N, D)) return rc;
   PtBwdParams p{mask, mb, qt, dxbar, xbar, m, l, dx, part_dq, sa, dsa, dlse, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed};
   dim3 grid(B, S);
   const int ns = pt_bwd_smem(D, 3) <= 227 * 1024 ? 3 : 2;
   const size_t smem = pt_bwd_smem(D, ns);
   auto k = ns == 3 ? pool_bwd_tc_kernel<3> : pool_bwd_tc_kernel<2>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B2_ECUDA;
-  k<<<grid, PT_THREADS, smem, s>>>(tmx, p);
+  k<<<grid, PT_THREADS, smem, s>>>(tmx, tmdx, p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
