@@ -64,8 +64,8 @@ class _StreamPool(torch.autograd.Function):
         pa = torch.empty((B, S, H, D), dtype=torch.float32, device=dev)
         st = stream_ptr(dev)
         if S_tc > 0:
-            call("attnpool_tc_fwd", x, DTYPE_CODE[x.dtype], mk, i64(mk.stride(0) if mk is not None else 0), qt32, B, N, D,
-                 H, S, pm, pl, pa, float(drop_p), int(drop_seed), pl2, st)
+            call("attnpool_tc_fwd", x, DTYPE_CODE[x.dtype], mk, i64(mk.stride(0) if mk is not None else 0), qt32, None, B, N,
+                 D, H, S, pm, pl, pa, float(drop_p), int(drop_seed), pl2, st)
         else:
             call("attnpool_fwd", x, DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)), mk,
                  i64(mk.stride(0) if mk is not None else 0), qt32, None, i64(0), i64(0), B, N, D, H, S, pm, pl, pa,
@@ -109,7 +109,7 @@ class _StreamPool(torch.autograd.Function):
             # one pass over x: dx and the per-split partials of the query gradient (no ds tensor, no second read of x)
             S = ctx.S_tc
             pdq = torch.empty((B, S, H, D), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
-            call("attnpool_tc_bwd", x, DTYPE_CODE[x.dtype], mk, mb, qt32, dxbar, xbar, m, l, B, N, D, H, S, dx,
+            call("attnpool_tc_bwd", x, DTYPE_CODE[x.dtype], mk, mb, qt32, dxbar, xbar, None, None, m, l, B, N, D, H, S, dx,
                  sa if dsa is not None else None, dsa, drop_p if dsa is not None else 0.0, drop_seed, dlse, pdq, st)
             if pdq is not None:
                 dqt = torch.zeros((H, D), dtype=torch.float32, device=dev)
@@ -140,6 +140,113 @@ class _StreamPool(torch.autograd.Function):
         return (dx if ctx.needs_input_grad[0] else None), dqt, None, None, None, None
 
 
+def _al(n: int) -> int:
+    return (n + 63) // 64 * 64          # workspace segments start on 256-byte boundaries
+
+
+class _FusedPool(torch.autograd.Function):
+    """The whole AttentionPool forward / backward in 3 + 4 launches of the library (csrc/pooltail.cu + csrc/attnpool_tc.cu):
+    pool_prep -> attnpool_tc_fwd -> pool_tail_fwd, and pool_tail_bwd -> pool_param_grads -> attnpool_tc_bwd -> pool_qgrads.
+    Every intermediate lives in one fp32 workspace per pass; parameter gradients are views of one flat buffer."""
+
+    @staticmethod
+    def forward(ctx, x, mask, query, in_w, in_b, out_w, out_b, ln_w, ln_b, proj_w, proj_b, H, eps, drop_p, drop_seed, S):
+        B, N, D = x.shape
+        dev = x.device
+        st = stream_ptr(dev)
+        KC = D // 64
+        Do = proj_w.shape[0] if proj_w is not None else D
+        mk = mask.to(torch.bool).contiguous().view(torch.uint8) if mask is not None else None
+        mb = i64(mk.stride(0)) if mk is not None else i64(0)
+        code = DTYPE_CODE[x.dtype]
+        fp16 = 1 if x.dtype == torch.float16 else 0
+        # workspace layout (floats)
+        off, cur = {}, 0
+        for name, n in (("q0", D), ("qt", H * D), ("img", KC * 512), ("pm", B * S * H), ("pl", B * S * H),
+                        ("pl2", B * S * H if drop_p > 0.0 else 0), ("pa", B * S * H * D), ("xbar", B * H * D), ("m", B * H),
+                        ("l", B * H), ("sa", B * H), ("o", B * D), ("yhat", B * D), ("rstd", B),
+                        ("yln", B * D if proj_w is not None else 0)):
+            off[name] = cur
+            cur += _al(n)
+        ws = torch.empty(cur, dtype=torch.float32, device=dev)
+        base = ws.data_ptr()
+        P = {k: base + 4 * v for k, v in off.items()}
+        out = torch.empty((B, Do), dtype=x.dtype, device=dev)
+        call("pool_prep", query, in_w, in_b, D, H, P["q0"], P["qt"], P["img"], fp16, st)
+        call("attnpool_tc_fwd", x, code, mk, mb, None, P["img"], B, N, D, H, S, P["pm"], P["pl"], P["pa"], float(drop_p),
+             int(drop_seed), P["pl2"] if drop_p > 0.0 else None, st)
+        call("pool_tail_fwd", P["pm"], P["pl"], P["pl2"] if drop_p > 0.0 else None, P["pa"], B, S, H, D,
+             in_w.data_ptr() + 8 * D * D, in_b.data_ptr() + 8 * D, out_w, out_b, ln_w, ln_b, float(eps), proj_w, proj_b,
+             Do if proj_w is not None else 0, P["xbar"], P["m"], P["l"], P["sa"], P["o"], P["yhat"], P["rstd"],
+             P["yln"] if proj_w is not None else None, out, code, st)
+        ctx.save_for_backward(x, mk if mk is not None else torch.empty(0, device=dev), ws, query, in_w, in_b, out_w, ln_w,
+                              proj_w if proj_w is not None else torch.empty(0, device=dev))
+        ctx.cfg = (B, N, D, H, S, Do, mask is not None, proj_w is not None, float(drop_p), int(drop_seed), off)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mk, ws, query, in_w, in_b, out_w, ln_w, proj_w = ctx.saved_tensors
+        B, N, D, H, S, Do, has_mask, has_proj, drop_p, drop_seed, off = ctx.cfg
+        dev = x.device
+        st = stream_ptr(dev)
+        KC = D // 64
+        mk = mk if has_mask else None
+        mb = i64(mk.stride(0)) if mk is not None else i64(0)
+        code = DTYPE_CODE[x.dtype]
+        fp16 = 1 if x.dtype == torch.float16 else 0
+        if dout.dtype not in DTYPE_CODE:
+            dout = dout.float()
+        dout = dout.contiguous()
+        P = {k: ws.data_ptr() + 4 * v for k, v in off.items()}
+        o2, cur = {}, 0
+        for name, n in (("dyln", B * D), ("dy", B * D), ("do", B * D), ("dxbar", B * H * D), ("dsa", B * H), ("cdot", B * H),
+                        ("wimg", B * KC * 1024), ("pdq", B * S * H * D), ("dqt", H * D)):
+            o2[name] = cur
+            cur += _al(n)
+        ws2 = torch.empty(cur, dtype=torch.float32, device=dev)
+        Q = {k: ws2.data_ptr() + 4 * v for k, v in o2.items()}
+        # parameter gradients: views of one flat buffer
+        sizes = [("query", D), ("in_w", 3 * D * D), ("in_b", 3 * D), ("out_w", D * D), ("out_b", D), ("ln_w", D), ("ln_b", D)]
+        if has_proj:
+            sizes += [("proj_w", Do * D), ("proj_b", Do)]
+        g, cur = {}, 0
+        for name, n in sizes:
+            g[name] = (cur, n)
+            cur += _al(n)
+        gbuf = torch.empty(cur, dtype=torch.float32, device=dev)
+        G = {k: gbuf.data_ptr() + 4 * v[0] for k, v in g.items()}
+        dx = torch.empty((B, N, D), dtype=x.dtype, device=dev)
+        use_sa = 1 if drop_p > 0.0 else 0
+        call("pool_tail_bwd", dout, DTYPE_CODE[dout.dtype], P["yhat"], P["rstd"], P["xbar"], P["sa"],
+             in_w.data_ptr() + 8 * D * D, in_b.data_ptr() + 8 * D, out_w, ln_w, proj_w if has_proj else None,
+             Do if has_proj else 0, P["qt"], B, H, D, Q["dyln"], Q["dy"], Q["do"], Q["dxbar"], Q["dsa"] if use_sa else None,
+             Q["cdot"], Q["wimg"], fp16, st)
+        call("pool_param_grads", Q["dy"], P["o"], Q["do"], P["xbar"], P["sa"], use_sa, Q["dyln"], P["yhat"], dout,
+             DTYPE_CODE[dout.dtype], P["yln"] if has_proj else None, Do if has_proj else 0, B, H, D, G["out_w"], G["out_b"],
+             G["in_w"] + 8 * D * D, G["in_b"] + 8 * D, G["ln_w"], G["ln_b"], G["proj_w"] if has_proj else None,
+             G["proj_b"] if has_proj else None, st)
+        call("attnpool_tc_bwd", x, code, mk, mb, None, None, None, Q["wimg"], Q["cdot"], P["m"], P["l"], B, N, D, H, S, dx,
+             P["sa"] if use_sa else None, Q["dsa"] if use_sa else None, drop_p, drop_seed, None, Q["pdq"], st)
+        call("pool_qgrads", Q["pdq"], B * S, P["q0"], query, in_w, H, D, Q["dqt"], G["in_w"], G["in_b"], G["query"], st)
+
+        def view(name, shape):
+            o, n = g[name]
+            return gbuf[o:o + n].view(shape)
+        return (dx, None, view("query", query.shape), view("in_w", (3 * D, D)), view("in_b", (3 * D,)),
+                view("out_w", (D, D)), view("out_b", (D,)), view("ln_w", (D,)), view("ln_b", (D,)),
+                view("proj_w", (Do, D)) if has_proj else None, view("proj_b", (Do,)) if has_proj else None,
+                None, None, None, None, None)
+
+
+def _fused_ok(x, params, D, H, Do) -> bool:
+    if os.environ.get("B200CLIP_POOL_FUSED", "1") == "0":
+        return False
+    if not all(p is None or (p.dtype == torch.float32 and p.is_contiguous() and p.is_cuda) for p in params):
+        return False
+    return bool(lib().b200clip_pooltail_ok(D, H, Do))
+
+
 class AttentionPool(nn.Module):
     def __init__(self, embed_dim: int, num_heads: int = 8, output_dim: int = None, dropout: float = 0.0):
         super().__init__()
@@ -164,6 +271,15 @@ class AttentionPool(nn.Module):
             drop_p = float(self.dropout)
             drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         H, Dh = self.num_heads, D // self.num_heads
+        has_proj = isinstance(self.proj, nn.Linear)
+        params = (self.query, self.attn.in_proj_weight, self.attn.in_proj_bias, self.attn.out_proj.weight,
+                  self.attn.out_proj.bias, self.norm.weight, self.norm.bias,
+                  self.proj.weight if has_proj else None, self.proj.bias if has_proj else None)
+        if x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and _fused_ok(x, params, D, H, self.output_dim if has_proj else 0):
+            xc = x.contiguous()
+            S = _tc_splits(xc, B, N, D, H)
+            if S > 0:
+                return _FusedPool.apply(xc, mask, *params, H, self.norm.eps, drop_p, drop_seed, S)
         with torch.autocast("cuda", enabled=False):
             W = self.attn.in_proj_weight.float()
             bias = self.attn.in_proj_bias.float()

@@ -370,22 +370,60 @@ int b200clip_attnpool_tc_splits(const void* x, int dtype, int64_t x_sb, int64_t 
   return attnpool_tc_ok(x, dtype, x_sb, x_sn, N, D, heads) ? attnpool_tc_splits(B, N) : 0;
 }
 
-int b200clip_attnpool_tc_fwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt, int B, int N,
-                             int D, int heads, int splits, float* part_m, float* part_l, float* part_acc, float drop_p,
-                             int64_t drop_seed, float* part_l2, void* stream) {
+int b200clip_attnpool_tc_fwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt,
+                             const void* qt_img, int B, int N, int D, int heads, int splits, float* part_m, float* part_l,
+                             float* part_acc, float drop_p, int64_t drop_seed, float* part_l2, void* stream) {
   if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !part_l2)) return B2_EINVAL;
   if (!attnpool_tc_ok(x, dtype, (int64_t)N * D, D, N, D, heads)) return B2_ENOSYS;
-  return attnpool_tc_fwd(x, dtype, mask, mask_sb, qt, B, N, D, heads, splits, part_m, part_l, part_acc, drop_p,
+  return attnpool_tc_fwd(x, dtype, mask, mask_sb, qt, qt_img, B, N, D, heads, splits, part_m, part_l, part_acc, drop_p,
                          (unsigned long long)drop_seed, part_l2, S(stream));
 }
 
 int b200clip_attnpool_tc_bwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt,
-                             const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N, int D,
-                             int heads, int splits, void* dx, const float* sa, const float* dsa, float drop_p,
-                             int64_t drop_seed, const float* dlse, float* part_dq, void* stream) {
+                             const float* dxbar, const float* xbar, const void* w_img, const float* cdot, const float* m,
+                             const float* l, int B, int N, int D, int heads, int splits, void* dx, const float* sa,
+                             const float* dsa, float drop_p, int64_t drop_seed, const float* dlse, float* part_dq,
+                             void* stream) {
   if (!attnpool_tc_ok(x, dtype, (int64_t)N * D, D, N, D, heads)) return B2_ENOSYS;
-  return attnpool_tc_bwd(x, dtype, mask, mask_sb, qt, dxbar, xbar, m, l, B, N, D, heads, splits, dx, sa, dsa, drop_p,
-                         (unsigned long long)drop_seed, dlse, part_dq, S(stream));
+  return attnpool_tc_bwd(x, dtype, mask, mask_sb, qt, dxbar, xbar, w_img, cdot, m, l, B, N, D, heads, splits, dx, sa, dsa,
+                         drop_p, (unsigned long long)drop_seed, dlse, part_dq, S(stream));
+}
+
+int b200clip_pooltail_ok(int D, int heads, int out_dim) { return pooltail_ok(D, heads, out_dim) ? 1 : 0; }
+
+int b200clip_pool_prep(const float* query, const float* in_proj_weight, const float* in_proj_bias, int D, int heads,
+                       float* q0, float* qt, void* qt_img, int img_fp16, void* stream) {
+  return pool_prep(query, in_proj_weight, in_proj_bias, D, heads, q0, qt, qt_img, img_fp16, S(stream));
+}
+
+int b200clip_pool_tail_fwd(const float* part_m, const float* part_l, const float* part_l2, const float* part_acc, int B,
+                           int splits, int heads, int D, const float* w_v, const float* b_v, const float* w_o,
+                           const float* b_o, const float* ln_w, const float* ln_b, float eps, const float* w_p,
+                           const float* b_p, int out_dim, float* xbar, float* m, float* l, float* sa, float* o, float* yhat,
+                           float* rstd, float* yln, void* out, int out_dtype, void* stream) {
+  return pool_tail_fwd(part_m, part_l, part_l2, part_acc, B, splits, heads, D, w_v, b_v, w_o, b_o, ln_w, ln_b, eps, w_p, b_p,
+                       out_dim, xbar, m, l, sa, o, yhat, rstd, yln, out, out_dtype, S(stream));
+}
+
+int b200clip_pool_tail_bwd(const void* dout, int dout_dtype, const float* yhat, const float* rstd, const float* xbar,
+                           const float* sa, const float* w_v, const float* b_v, const float* w_o, const float* ln_w,
+                           const float* w_p, int out_dim, const float* qt, int B, int heads, int D, float* dyln, float* dy,
+                           float* d_o, float* dxbar, float* dsa, float* cdot, void* w_img, int img_fp16, void* stream) {
+  return pool_tail_bwd(dout, dout_dtype, yhat, rstd, xbar, sa, w_v, b_v, w_o, ln_w, w_p, out_dim, qt, B, heads, D, dyln, dy,
+                       d_o, dxbar, dsa, cdot, w_img, img_fp16, S(stream));
+}
+
+int b200clip_pool_param_grads(const float* dy, const float* o, const float* d_o, const float* xbar, const float* sa,
+                              int use_sa, const float* dyln, const float* yhat, const void* dout, int dout_dtype,
+                              const float* yln, int out_dim, int B, int heads, int D, float* dw_o, float* db_o, float* dw_v,
+                              float* db_v, float* dln_w, float* dln_b, float* dw_p, float* db_p, void* stream) {
+  return pool_param_grads(dy, o, d_o, xbar, sa, use_sa, dyln, yhat, dout, dout_dtype, yln, out_dim, B, heads, D, dw_o, db_o,
+                          dw_v, db_v, dln_w, dln_b, dw_p, db_p, S(stream));
+}
+
+int b200clip_pool_qgrads(const float* part_dq, int nparts, const float* q0, const float* query, const float* in_proj_weight,
+                         int heads, int D, float* dqt, float* dw_in, float* db_in, float* dquery, void* stream) {
+  return pool_qgrads(part_dq, nparts, q0, query, in_proj_weight, heads, D, dqt, dw_in, db_in, dquery, S(stream));
 }
 
 int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,

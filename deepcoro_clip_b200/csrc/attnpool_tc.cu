@@ -26,6 +26,7 @@ namespace b2 {
 
 constexpr int PT_TT = 64;          // tokens per tile
 constexpr int PT_THREADS = 192;    // warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..5 epilogue
+constexpr int PT_BWD_THREADS = 320;   // backward: + warps 6..9 that drain dx^T while warps 2..5 work on the next tile
 constexpr int PT_BOX = PT_TT * 128;   // one [64 tokens x 64 channels] 16-bit box
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
@@ -111,12 +112,28 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int col) {
 // MN-major operand spanning two adjacent 64-element blocks `lbo` bytes apart
 __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo) { return make_smem_desc_sw128(addr, lbo); }
 
+// One tile = D/64 boxes of [64 tokens x 64 channels]; loaded as sub-boxes of `br` token rows in (token group, channel box)
+// order, so that the requests to one 1 KB token row arrive close together at the memory controller
+__device__ __forceinline__ void pt_load_tile(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int KC, int br, int tok, int b) {
+  for (int tg = 0; tg < PT_TT; tg += br)
+    for (int kc = 0; kc < KC; ++kc) tma_load_3d(dst + kc * PT_BOX + tg * 128, tm, bar, kc * 64, tok + tg, b);
+}
+
+// plain bulk copy global -> shared (both 16-byte aligned, size % 16 == 0), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 struct PtFwdParams {
   const unsigned char* mask; long long mb;
   const float* qt;                     // [H, D]
+  const void* qt_img;                  // or: the prepared operand image (pool_prep), D/64 x [16 x 64] 16-bit, swizzled
   float* part_m; float* part_l; float* part_l2; float* part_acc;
   int B, N, D, H, S, fp16;
   float drop_p; unsigned long long drop_seed;
+  int br;       // token rows per TMA load box
+  int dbg;      // timing experiments only (B200CLIP_POOL_DBG): 1 = no P2 MMAs, 2 = no softmax arithmetic, 4 = one P1 MMA per box
 };
 
 // dynamic shared memory (1024-aligned): ring NS x (D/64) boxes of 8 KB | qt operand (D/64) x [16 x 64] (2 KB each) |
@@ -137,7 +154,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
   uint64_t* s_full = bars + 2 * NS; // [2]  scores ready (commit)
   uint64_t* p_ready = s_full + 2;   // [2]  P written (128 epilogue threads)
   uint64_t* acc_done = p_ready + 2; // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  uint64_t* op_full = acc_done + 1; // [1]  operand image landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x, sp = blockIdx.y;
@@ -149,18 +167,22 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
     for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
     mbar_init(acc_done, 1);
+    mbar_init(op_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmx);
+    if (p.qt_img) {
+      mbar_expect_tx(op_full, KC * 2048);
+      bulk_load(qt_op, p.qt_img, KC * 2048, op_full);
+    }
     // the first NS tiles start loading before anything else is set up
     for (int i = 0; i < NS && i < T; ++i) {
       mbar_expect_tx(&full[i], tile_bytes);
-      for (int kc = 0; kc < KC; ++kc)
-        tma_load_3d(ring + i * tile_bytes + kc * PT_BOX, &tmx, &full[i], kc * 64, (tile0 + i) * PT_TT, b);
+      pt_load_tile(ring + i * tile_bytes, &tmx, &full[i], KC, p.br, (tile0 + i) * PT_TT, b);
     }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
-  // qt -> [qt_hi (rows 0..7) ; qt_lo (rows 8..15)] K-major operand, heads >= H zero
-  for (int i = threadIdx.x; i < 8 * D; i += PT_THREADS) {
+  // qt -> [qt_hi (rows 0..7) ; qt_lo (rows 8..15)] K-major operand, heads >= H zero (unless the image was prepared)
+  for (int i = threadIdx.x; i < (p.qt_img ? 0 : 8 * D); i += PT_THREADS) {
     const int h = i / D, d = i - h * D;
     const float v = h < p.H ? p.qt[(size_t)h * D + d] : 0.f;
     const uint16_t hi = op_bits(v, p.fp16);
@@ -182,8 +204,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
         const int slot = i % NS;
         mbar_wait(&empty[slot], ((i / NS) & 1) ^ 1);
         mbar_expect_tx(&full[slot], tile_bytes);
-        for (int kc = 0; kc < KC; ++kc)
-          tma_load_3d(ring + slot * tile_bytes + kc * PT_BOX, &tmx, &full[slot], kc * 64, (tile0 + i) * PT_TT, b);
+        pt_load_tile(ring + slot * tile_bytes, &tmx, &full[slot], KC, p.br, (tile0 + i) * PT_TT, b);
       }
     }
   } else if (warp == 1) {
@@ -200,10 +221,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
           const uint64_t adesc = make_smem_desc_sw128(ring + slot * tile_bytes + kc * PT_BOX, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(qt_op + kc * 2048, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc1, (kc | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            if (k == 0 || !(p.dbg & 4)) mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc1, (kc | k) != 0);
         }
         tc_commit(&s_full[i & 1]);
       };
+      if (p.qt_img) mbar_wait(op_full, 0);
       p1(0);
       for (int i = 0; i < T; ++i) {
         if (i + 1 < T) p1(i + 1);
@@ -212,7 +235,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
         const int slot = i % NS;
         const uint32_t tile = ring + slot * tile_bytes;
         const uint64_t bdesc = make_smem_desc_sw128(p_op + (i & 1) * 2048, 1024);
-        for (int mb = 0; mb < MB; ++mb) {
+        for (int mb = 0; mb < MB && !(p.dbg & 1); ++mb) {
           const uint64_t adesc = desc_mn(tile + 2 * mb * PT_BOX, PT_BOX);
 #pragma unroll
           for (int ks = 0; ks < PT_TT / 16; ++ks)
@@ -281,7 +304,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
           tc_wait_st();
         }
       }
-      if (lane < 16) {
+      if (lane < 16 && !(p.dbg & 2)) {
         const uint32_t pb = p_op + sb * 2048;
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
@@ -342,18 +365,21 @@ struct PtBwdParams {
   const float* qt;        // [H, D]
   const float* dxbar;     // [B, H, D]
   const float* xbar;      // [B, H, D]
+  const void* w_img;      // or: prepared operand images (pool_tail_bwd), [B][D/64][32 x 64] 16-bit, swizzled ...
+  const float* cdot;      // ... with c_h = dxbar_h . xbar_h [B, H]
   const float* m; const float* l;   // [B, H]
   void* dx;               // [B, N, D] contiguous, 16-bit
   float* part_dq;         // [B, S, H, D] or null
   const float* sa; const float* dsa; const float* dlse;
   int B, N, D, H, S, fp16;
   float drop_p; unsigned long long drop_seed;
+  int br;
 };
 
 // dynamic shared memory: ring NS x (D/64) boxes | W operand (D/64) x [32 x 64] (4 KB each: rows qt_hi, dxbar_hi, qt_lo,
 // dxbar_lo) | C operand 2 x [32 x 64] (4 KB each: rows ds_hi, a_hi, ds_lo, a_lo) | c, m, 1/l, dsa [4][8] fp32 | barriers
 template <int NS>
-__global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx,
+__global__ void __launch_bounds__(PT_BWD_THREADS, 1) pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                     const __grid_constant__ CUtensorMap tmdx, PtBwdParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -374,7 +400,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
   uint64_t* c_ready = st_full + 2;     // [2]  (128 epilogue threads)
   uint64_t* dx_full = c_ready + 2;     // [1]  P2 (+ P3) of the tile complete
   uint64_t* dx_empty = dx_full + 1;    // [1]  dx^T drained out of TMEM (128 epilogue threads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_empty + 1);
+  uint64_t* op_full = dx_empty + 1;    // [1]  operand image landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x, sp = blockIdx.y;
@@ -387,17 +414,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
     for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 1); mbar_init(&c_ready[i], 128); }
     mbar_init(dx_full, 1);
     mbar_init(dx_empty, 128);
+    mbar_init(op_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmdx);
+    if (p.w_img) {
+      mbar_expect_tx(op_full, KC * 4096);
+      bulk_load(w_op, reinterpret_cast<const unsigned char*>(p.w_img) + (size_t)b * KC * 4096, KC * 4096, op_full);
+    }
     for (int i = 0; i < NS && i < T; ++i) {
       mbar_expect_tx(&full[i], tile_bytes);
-      for (int kc = 0; kc < KC; ++kc)
-        tma_load_3d(ring + i * tile_bytes + kc * PT_BOX, &tmx, &full[i], kc * 64, (tile0 + i) * PT_TT, b);
+      pt_load_tile(ring + i * tile_bytes, &tmx, &full[i], KC, p.br, (tile0 + i) * PT_TT, b);
     }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  for (int i = threadIdx.x; i < 8 * D; i += PT_THREADS) {
+  for (int i = threadIdx.x; i < (p.w_img ? 0 : 8 * D); i += PT_BWD_THREADS) {
     const int h = i / D, d = i - h * D;
     const float qv = h < p.H ? p.qt[(size_t)h * D + d] : 0.f;
     const float dv = h < p.H ? p.dxbar[((size_t)b * p.H + h) * D + d] : 0.f;
@@ -409,13 +440,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
     sts16(base + sw128_off(24 + h, d & 63), op_bits(dv - op_val(dh, p.fp16), p.fp16));
   }
   if (warp >= 2) {
-    // c_h = dxbar_h . xbar_h (+ dsa_h sa_h) (- dlse_h): warps 2..5 take heads (warp - 2) and (warp - 2) + 4
-    for (int h = warp - 2; h < 8; h += 4) {
+    // c_h = dxbar_h . xbar_h (+ dsa_h sa_h) (- dlse_h): warp 2 + h takes head h
+    for (int h = warp - 2; h < 8; h += 8) {
       float c = 0.f;
-      if (h < p.H)
-        for (int d = lane; d < D; d += 32)
-          c = fmaf(p.dxbar[((size_t)b * p.H + h) * D + d], p.xbar[((size_t)b * p.H + h) * D + d], c);
-      c = warp_sum(c);
+      if (p.cdot) {
+        c = h < p.H ? p.cdot[b * p.H + h] : 0.f;
+      } else {
+        if (h < p.H)
+          for (int d = lane; d < D; d += 32)
+            c = fmaf(p.dxbar[((size_t)b * p.H + h) * D + d], p.xbar[((size_t)b * p.H + h) * D + d], c);
+        c = warp_sum(c);
+      }
       if (p.dsa && h < p.H) c = fmaf(p.dsa[b * p.H + h], p.sa[b * p.H + h], c);
       if (p.dlse && h < p.H) c -= p.dlse[b * p.H + h];
       if (lane == 0) {
@@ -439,8 +474,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
         const int slot = i % NS;
         mbar_wait(&empty[slot], ((i / NS) & 1) ^ 1);
         mbar_expect_tx(&full[slot], tile_bytes);
-        for (int kc = 0; kc < KC; ++kc)
-          tma_load_3d(ring + slot * tile_bytes + kc * PT_BOX, &tmx, &full[slot], kc * 64, (tile0 + i) * PT_TT, b);
+        pt_load_tile(ring + slot * tile_bytes, &tmx, &full[slot], KC, p.br, (tile0 + i) * PT_TT, b);
       }
     }
   } else if (warp == 1) {
@@ -461,6 +495,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
         }
         tc_commit(&st_full[i & 1]);
       };
+      if (p.w_img) mbar_wait(op_full, 0);
       p1(0);
       for (int i = 0; i < T; ++i) {
         if (i + 1 < T) p1(i + 1);
@@ -491,13 +526,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
         tc_commit(&empty[slot]);
       }
     }
-  } else {
+  } else if (warp < 6) {
+    // ===================== warps 2..5: attention weights and score gradients of tile i -> C operand =====================
     const int q = warp & 3;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const int r = q * 16 + lane;
     const unsigned char* mk = p.mask ? p.mask + (long long)b * p.mb : nullptr;
     const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    int blk = 0;
     for (int i = 0; i < T; ++i) {
       const int sb = i & 1;
       mbar_wait(&st_full[sb], (i >> 1) & 1);
@@ -529,13 +564,36 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&c_ready[sb]);
-      // ---- drain dx^T of this tile: per 128-channel block, TMEM (fragment layout) -> 16-bit pairs -> stmatrix.trans into
-      //      a [64 tokens x 128 channels] staging block (rows = tokens) -> TMA store (rows past N are clipped) ----
+    }
+    if (p.part_dq) {
+      const int last = T - 1;
+      mbar_wait(&empty[last % NS], (last / NS) & 1);        // P3 of the last tile (and everything before) complete
+      tc_fence_after();
+      const size_t slot = (size_t)b * p.S + sp;
+      for (int mb = 0; mb < MB; ++mb) {
+        uint32_t a[16];
+        tmem_ld16(tmem_base + DQ_COL + mb * 16 + lane_off, a);
+        tc_wait_ld();
+        const int d = mb * 128 + q * 32 + lane;
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+          if (h < p.H) p.part_dq[(slot * p.H + h) * D + d] = __uint_as_float(a[h]) + __uint_as_float(a[8 + h]);
+      }
+      tc_fence_before();
+    }
+  } else {
+    // ===================== warps 6..9: drain dx^T of tile i while warps 2..5 are on tile i + 1 =====================
+    const int q = warp & 3;
+    int blk = 0;
+    for (int i = 0; i < T; ++i) {
+      const int tok0 = (tile0 + i) * PT_TT;
+      // ---- per 128-channel block: TMEM (fragment layout) -> 16-bit pairs -> stmatrix.trans into a
+      //      [64 tokens x 128 channels] staging block (rows = tokens) -> TMA store (rows past N are clipped) ----
       mbar_wait(dx_full, i & 1);
       tc_fence_after();
       for (int mb = 0; mb < MB; ++mb, ++blk) {
         const uint32_t sbuf = stage + (blk & 1) * (2 * PT_BOX);
-        if (threadIdx.x == 64) bulk_wait_read<1>();        // the store that last read this buffer (two blocks ago) is done
+        if (threadIdx.x == 192) bulk_wait_read<1>();        // the store that last read this buffer (two blocks ago) is done
         named_bar_sync(2, 128);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -560,7 +618,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
-        if (threadIdx.x == 64) {
+        if (threadIdx.x == 192) {
           tma_store_3d(&tmdx, sbuf, mb * 128, tok0, b);
           tma_store_3d(&tmdx, sbuf + PT_BOX, mb * 128 + 64, tok0, b);
           bulk_commit();
@@ -569,23 +627,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_bwd_tc_kernel(const __grid
       tc_fence_before();
       mbar_arrive(dx_empty);
     }
-    if (threadIdx.x == 64) bulk_wait_all();
-    if (p.part_dq) {
-      const int last = T - 1;
-      mbar_wait(&empty[last % NS], (last / NS) & 1);        // P3 of the last tile (and everything before) complete
-      tc_fence_after();
-      const size_t slot = (size_t)b * p.S + sp;
-      for (int mb = 0; mb < MB; ++mb) {
-        uint32_t a[16];
-        tmem_ld16(tmem_base + DQ_COL + mb * 16 + lane_off, a);
-        tc_wait_ld();
-        const int d = mb * 128 + q * 32 + lane;
-#pragma unroll
-        for (int h = 0; h < 8; ++h)
-          if (h < p.H) p.part_dq[(slot * p.H + h) * D + d] = __uint_as_float(a[h]) + __uint_as_float(a[8 + h]);
-      }
-      tc_fence_before();
-    }
+    if (threadIdx.x == 192) bulk_wait_all();
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
@@ -601,7 +643,17 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // [B, N, D] 16-bit tensor (contiguous), box [1, 64 tokens, 64 channels], SWIZZLE_128B; tokens past N are zero-filled
-static int make_tmap_x3d(CUtensorMap* out, const void* base, int B, int N, int D) {
+static int pt_box_rows() {
+  static int br = 0;
+  if (br == 0) {
+    const char* e = getenv("B200CLIP_POOL_BOXROWS");
+    br = e ? atoi(e) : PT_TT;
+    if (br != 8 && br != 16 && br != 32 && br != 64) br = PT_TT;
+  }
+  return br;
+}
+
+static int make_tmap_x3d(CUtensorMap* out, const void* base, int B, int N, int D, int box_rows = PT_TT) {
   static EncodeTiledFn3 enc = nullptr;
   if (!enc) {
     void* fp = nullptr;
@@ -613,7 +665,7 @@ static int make_tmap_x3d(CUtensorMap* out, const void* base, int B, int N, int D
   }
   cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
-  cuuint32_t box[3] = {64, PT_TT, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -654,13 +706,15 @@ static size_t pt_bwd_smem(int D, int ns) {
   return (size_t)ns * (D / 64) * PT_BOX + (D / 64) * 4096 + 2 * 4096 + 2 * 2 * PT_BOX + 32 * 4 + 16 * 8 + 16 + 1024;
 }
 
-int attnpool_tc_fwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, int B, int N, int D,
-                    int H, int S, float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
-                    float* part_l2, cudaStream_t s) {
-  if (!x || !qt || !part_m || !part_l || !part_acc || S < 1 || S > (N + PT_TT - 1) / PT_TT) return B2_EINVAL;
+int attnpool_tc_fwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, const void* qt_img,
+                    int B, int N, int D, int H, int S, float* part_m, float* part_l, float* part_acc, float drop_p,
+                    unsigned long long drop_seed, float* part_l2, cudaStream_t s) {
+  if (!x || (!qt && !qt_img) || (reinterpret_cast<uintptr_t>(qt_img) & 15) || !part_m || !part_l || !part_acc || S < 1 || S > (N + PT_TT - 1) / PT_TT) return B2_EINVAL;
   CUtensorMap tmx;
-  if (int rc = make_tmap_x3d(&tmx, x, B, N, D)) return rc;
-  PtFwdParams p{mask, mb, qt, part_m, part_l, part_l2, part_acc, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed};
+  if (int rc = make_tmap_x3d(&tmx, x, B, N, D, pt_box_rows())) return rc;
+  const char* dbg = getenv("B200CLIP_POOL_DBG");
+  PtFwdParams p{mask, mb, qt, qt_img, part_m, part_l, part_l2, part_acc, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed,
+                pt_box_rows(), dbg ? atoi(dbg) : 0};
   dim3 grid(B, S);
   const int ns = pt_fwd_smem(D, 4) <= 227 * 1024 ? 4 : 3;
   const size_t smem = pt_fwd_smem(D, ns);
@@ -671,21 +725,22 @@ int attnpool_tc_fwd(const void* x, int dtype, const unsigned char* mask, long lo
 }
 
 int attnpool_tc_bwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, const float* dxbar,
-                    const float* xbar, const float* m, const float* l, int B, int N, int D, int H, int S, void* dx,
-                    const float* sa, const float* dsa, float drop_p, unsigned long long drop_seed, const float* dlse,
-                    float* part_dq, cudaStream_t s) {
-  if (!x || !qt || !dxbar || !xbar || !m || !l || !dx || S < 1 || S > (N + PT_TT - 1) / PT_TT) return B2_EINVAL;
+                    const float* xbar, const void* w_img, const float* cdot, const float* m, const float* l, int B, int N,
+                    int D, int H, int S, void* dx, const float* sa, const float* dsa, float drop_p,
+                    unsigned long long drop_seed, const float* dlse, float* part_dq, cudaStream_t s) {
+  if (!x || (!w_img && (!qt || !dxbar || !xbar)) || (w_img && !cdot) || (reinterpret_cast<uintptr_t>(w_img) & 15) || !m || !l || !dx || S < 1 || S > (N + PT_TT - 1) / PT_TT) return B2_EINVAL;
   CUtensorMap tmx;
-  if (int rc = make_tmap_x3d(&tmx, x, B, N, D)) return rc;
+  if (int rc = make_tmap_x3d(&tmx, x, B, N, D, pt_box_rows())) return rc;
   CUtensorMap tmdx;
   if (int rc = make_tmap_x3d(&tmdx, dx, B, N, D)) return rc;
-  PtBwdParams p{mask, mb, qt, dxbar, xbar, m, l, dx, part_dq, sa, dsa, dlse, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed};
+  PtBwdParams p{mask, mb, qt, dxbar, xbar, w_img, cdot, m, l, dx, part_dq, sa, dsa, dlse, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed,
+                pt_box_rows()};
   dim3 grid(B, S);
   const int ns = pt_bwd_smem(D, 3) <= 227 * 1024 ? 3 : 2;
   const size_t smem = pt_bwd_smem(D, ns);
   auto k = ns == 3 ? pool_bwd_tc_kernel<3> : pool_bwd_tc_kernel<2>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B2_ECUDA;
-  k<<<grid, PT_THREADS, smem, s>>>(tmx, tmdx, p);
+  k<<<grid, PT_BWD_THREADS, smem, s>>>(tmx, tmdx, p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -170,13 +170,32 @@ int attnpool_bwd_dx_dq(const void* x, int dtype, long long sb, long long sn, con
 // attnpool_tc.cu: 16-bit contiguous x, heads <= 8, D % 128 == 0, D <= 512 on tcgen05 tiles (TMEM accumulators)
 bool attnpool_tc_ok(const void* x, int dtype, long long sb, long long sn, int N, int D, int H);
 int attnpool_tc_splits(int B, int N);
-int attnpool_tc_fwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, int B, int N, int D,
-                    int H, int S, float* part_m, float* part_l, float* part_acc, float drop_p, unsigned long long drop_seed,
-                    float* part_l2, cudaStream_t s);
+int attnpool_tc_fwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, const void* qt_img,
+                    int B, int N, int D, int H, int S, float* part_m, float* part_l, float* part_acc, float drop_p,
+                    unsigned long long drop_seed, float* part_l2, cudaStream_t s);
 int attnpool_tc_bwd(const void* x, int dtype, const unsigned char* mask, long long mb, const float* qt, const float* dxbar,
-                    const float* xbar, const float* m, const float* l, int B, int N, int D, int H, int S, void* dx,
-                    const float* sa, const float* dsa, float drop_p, unsigned long long drop_seed, const float* dlse,
-                    float* part_dq, cudaStream_t s);
+                    const float* xbar, const void* w_img, const float* cdot, const float* m, const float* l, int B, int N,
+                    int D, int H, int S, void* dx, const float* sa, const float* dsa, float drop_p,
+                    unsigned long long drop_seed, const float* dlse, float* part_dq, cudaStream_t s);
+
+// pooltail.cu: the [B, D]-vector work around the streaming pool kernels (fp32 parameters, D % 128 == 0, D <= 512, heads | 8)
+bool pooltail_ok(int D, int H, int Do);
+int pool_prep(const float* query, const float* w_in, const float* b_in, int D, int H, float* q0, float* qt, void* qt_img,
+              int fp16, cudaStream_t s);
+int pool_tail_fwd(const float* pm, const float* pl, const float* pl2, const float* pa, int B, int S, int H, int D,
+                  const float* w_v, const float* b_v, const float* w_o, const float* b_o, const float* gamma,
+                  const float* beta, float eps, const float* w_p, const float* b_p, int Do, float* xbar, float* m, float* l,
+                  float* sa, float* o, float* yhat, float* rstd, float* yln, void* out, int out_dtype, cudaStream_t s);
+int pool_tail_bwd(const void* dout, int dout_dtype, const float* yhat, const float* rstd, const float* xbar, const float* sa,
+                  const float* w_v, const float* b_v, const float* w_o, const float* gamma, const float* w_p, int Do,
+                  const float* qt, int B, int H, int D, float* dyln, float* dy, float* do_, float* dxbar, float* dsa,
+                  float* cdot, void* w_img, int fp16, cudaStream_t s);
+int pool_param_grads(const float* dy, const float* o, const float* do_, const float* xbar, const float* sa, int use_sa,
+                     const float* dyln, const float* yhat, const void* dout, int dout_dtype, const float* yln, int Do, int B,
+                     int H, int D, float* dw_o, float* db_o, float* dw_v, float* db_v, float* dgamma, float* dbeta, float* dw_p,
+                     float* db_p, cudaStream_t s);
+int pool_qgrads(const float* part_dq, int nparts, const float* q0, const float* query, const float* w_in, int H, int D,
+                float* dqt, float* dw_in, float* db_in, float* dquery, cudaStream_t s);
 
 // querypool.cu
 int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,

@@ -446,13 +446,48 @@ int b200clip_attnpool_bwd_dx_dq(const void* x, int dtype, int64_t x_sb, int64_t 
  *                        partials of dqt = sum_n ds_hn x_n (every slot is written; summed by attnpool_merge(NULL, NULL,
  *                        part_dq, ..., sum_over_b = 1)). Same c_h / dsa / dlse conventions as attnpool_bwd_dx. */
 int b200clip_attnpool_tc_splits(const void* x, int dtype, int64_t x_sb, int64_t x_sn, int B, int N, int D, int heads);
-int b200clip_attnpool_tc_fwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt, int B, int N,
-                             int D, int heads, int splits, float* part_m, float* part_l, float* part_acc, float drop_p,
-                             int64_t drop_seed, float* part_l2, void* stream);
+int b200clip_attnpool_tc_fwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt,
+                             const void* qt_img, int B, int N, int D, int heads, int splits, float* part_m, float* part_l,
+                             float* part_acc, float drop_p, int64_t drop_seed, float* part_l2, void* stream);
 int b200clip_attnpool_tc_bwd(const void* x, int dtype, const uint8_t* mask, int64_t mask_sb, const float* qt,
-                             const float* dxbar, const float* xbar, const float* m, const float* l, int B, int N, int D,
-                             int heads, int splits, void* dx, const float* sa, const float* dsa, float drop_p,
-                             int64_t drop_seed, const float* dlse, float* part_dq, void* stream);
+                             const float* dxbar, const float* xbar, const void* w_img, const float* cdot, const float* m,
+                             const float* l, int B, int N, int D, int heads, int splits, void* dx, const float* sa,
+                             const float* dsa, float drop_p, int64_t drop_seed, const float* dlse, float* part_dq,
+                             void* stream);
+
+/* The [B, D]-vector work of AttentionPool around the streaming kernels (csrc/pooltail.cu; reference
+ * models/attention_pool.py:77-99 = nn.MultiheadAttention with one query + LayerNorm + optional Linear), fp32 parameters,
+ * D % 128 == 0, D <= 512, heads in {1, 2, 4, 8}, out_dim % 8 == 0 (pooltail_ok = 1), forward and backward in 7 launches:
+ *   pool_prep        : q0 = W_q query + b_q [D], qt_h = W_k,h^T q0_h / sqrt(Dh) [heads, D], and (qt_img != NULL) the 16-bit
+ *                      hi / lo operand image of qt, D/64 x [16 x 64] with the 128-byte swizzle, which attnpool_tc_fwd
+ *                      bulk-copies instead of converting qt in every CTA (img_fp16 = 1 for fp16 x, 0 for bf16).
+ *   pool_tail_fwd    : merge of the partials of attnpool(_tc)_fwd -> xbar, m, l, sa; o = W_v,h xbar_h + b_v sa; y = W_o o + b_o;
+ *                      LayerNorm -> yhat (normalised), rstd, yln = yhat ln_w + ln_b; out = yln or W_p yln + b_p, stored as
+ *                      out_dtype (0 fp32 / 1 bf16 / 2 fp16). Clusters of 8 CTAs x 4 batch rows, rows exchanged over DSMEM.
+ *   pool_tail_bwd    : from dout: dyln, dy (before the LayerNorm), d_o = W_o^T dy, dxbar_h = W_v,h^T d_o_h, dsa (NULL unless
+ *                      attention dropout), cdot[b, h] = dxbar_h . xbar_h and (w_img != NULL) the per-row operand images
+ *                      [B][D/64][32 x 64] that attnpool_tc_bwd bulk-copies (with cdot).
+ *   pool_param_grads : dW_o = dy^T o, db_o, dW_v (per head: d_o_h^T xbar_h), db_v, dln_w, dln_b (dW_p, db_p when given).
+ *   pool_qgrads      : dqt = sum of the nparts = B * splits partials of attnpool_tc_bwd, then rows [0, 2D) of the
+ *                      in_proj_weight / in_proj_bias gradients (W_q, W_k; b_k gets 0) and dquery. */
+int b200clip_pooltail_ok(int D, int heads, int out_dim);
+int b200clip_pool_prep(const float* query, const float* in_proj_weight, const float* in_proj_bias, int D, int heads,
+                       float* q0, float* qt, void* qt_img, int img_fp16, void* stream);
+int b200clip_pool_tail_fwd(const float* part_m, const float* part_l, const float* part_l2, const float* part_acc, int B,
+                           int splits, int heads, int D, const float* w_v, const float* b_v, const float* w_o,
+                           const float* b_o, const float* ln_w, const float* ln_b, float eps, const float* w_p,
+                           const float* b_p, int out_dim, float* xbar, float* m, float* l, float* sa, float* o, float* yhat,
+                           float* rstd, float* yln, void* out, int out_dtype, void* stream);
+int b200clip_pool_tail_bwd(const void* dout, int dout_dtype, const float* yhat, const float* rstd, const float* xbar,
+                           const float* sa, const float* w_v, const float* b_v, const float* w_o, const float* ln_w,
+                           const float* w_p, int out_dim, const float* qt, int B, int heads, int D, float* dyln, float* dy,
+                           float* d_o, float* dxbar, float* dsa, float* cdot, void* w_img, int img_fp16, void* stream);
+int b200clip_pool_param_grads(const float* dy, const float* o, const float* d_o, const float* xbar, const float* sa,
+                              int use_sa, const float* dyln, const float* yhat, const void* dout, int dout_dtype,
+                              const float* yln, int out_dim, int B, int heads, int D, float* dw_o, float* db_o, float* dw_v,
+                              float* db_v, float* dln_w, float* dln_b, float* dw_p, float* db_p, void* stream);
+int b200clip_pool_qgrads(const float* part_dq, int nparts, const float* q0, const float* query, const float* in_proj_weight,
+                         int heads, int D, float* dqt, float* dw_in, float* db_in, float* dquery, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).

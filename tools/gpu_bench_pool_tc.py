@@ -41,12 +41,12 @@ for S in cands:
     pm = torch.empty((B, S, H), device=dev); pl = torch.empty((B, S, H), device=dev); pa = torch.empty((B, S, H, D), device=dev)
     xbar = torch.empty((B, H, D), device=dev); m = torch.empty((B, H), device=dev); l = torch.empty((B, H), device=dev)
     pdq = torch.empty((B, S, H, D), device=dev); dqt = torch.zeros((H, D), device=dev)
-    f = lambda i: call("attnpool_tc_fwd", xs[i % 3], 1, None, i64(0), qt, B, N, D, H, S, pm, pl, pa, 0.0, 0, None, st)
+    f = lambda i: call("attnpool_tc_fwd", xs[i % 3], 1, None, i64(0), qt, None, B, N, D, H, S, pm, pl, pa, 0.0, 0, None, st)
     mg = lambda i: call("attnpool_merge", pm, pl, pa, B, S, H, D, xbar, m, l, 0, None, None, st)
     t_f = timeit(f); t_m = timeit(mg)
-    bw = lambda i: call("attnpool_tc_bwd", xs[i % 3], 1, None, i64(0), qt, dxbar, xbar, m, l, B, N, D, H, S, dxs[i % 3], None, None,
+    bw = lambda i: call("attnpool_tc_bwd", xs[i % 3], 1, None, i64(0), qt, dxbar, xbar, None, None, m, l, B, N, D, H, S, dxs[i % 3], None, None,
                         0.0, 0, None, pdq, st)
-    bw_nodq = lambda i: call("attnpool_tc_bwd", xs[i % 3], 1, None, i64(0), qt, dxbar, xbar, m, l, B, N, D, H, S, dxs[i % 3], None,
+    bw_nodq = lambda i: call("attnpool_tc_bwd", xs[i % 3], 1, None, i64(0), qt, dxbar, xbar, None, None, m, l, B, N, D, H, S, dxs[i % 3], None,
                              None, 0.0, 0, None, None, st)
     mq = lambda i: call("attnpool_merge", None, None, pdq, B, S, H, D, dqt, None, None, 1, None, None, st)
     t_b = timeit(bw); t_b0 = timeit(bw_nodq); t_mq = timeit(mq)
