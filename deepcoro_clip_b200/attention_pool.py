@@ -27,7 +27,7 @@ def _fused_dq_enabled() -> bool:
 def _tc_splits(x: torch.Tensor, B: int, N: int, D: int, H: int) -> int:
     """Token splits of the tcgen05 pool kernels for this problem, 0 when they do not apply (fp32 x, wide rows, > 8 heads)
     or are switched off (B200CLIP_POOL_TC=0: the mma.sync / CUDA-core kernels, kept as the A/B baseline)."""
-    if x.dtype not in (torch.bfloat16, torch.float16) or os.environ.get("B200CLIP_POOL_TC", "1") == "0":
+    if x.dtype not in (torch.bfloat16, torch.float16) or not x.is_cuda or os.environ.get("B200CLIP_POOL_TC", "1") == "0":
         return 0
     return int(lib().b200clip_attnpool_tc_splits(x.data_ptr(), DTYPE_CODE[x.dtype], i64(x.stride(0)), i64(x.stride(1)),
                                                  B, N, D, H))
@@ -144,106 +144,105 @@ def _al(n: int) -> int:
     return (n + 63) // 64 * 64          # workspace segments start on 256-byte boundaries
 
 
+_LAYOUTS: dict = {}
+
+
+def _layout(key, segments):
+    """Byte offsets of the named fp32 segments of one workspace (cached per problem configuration) + total floats."""
+    lay = _LAYOUTS.get(key)
+    if lay is None:
+        off, cur = {}, 0
+        for name, n in segments():
+            off[name] = 4 * cur
+            cur += _al(n)
+        lay = _LAYOUTS[key] = (off, cur)
+    return lay
+
+
 class _FusedPool(torch.autograd.Function):
     """The whole AttentionPool forward / backward in 3 + 4 launches of the library (csrc/pooltail.cu + csrc/attnpool_tc.cu):
     pool_prep -> attnpool_tc_fwd -> pool_tail_fwd, and pool_tail_bwd -> pool_param_grads -> attnpool_tc_bwd -> pool_qgrads.
-    Every intermediate lives in one fp32 workspace per pass; parameter gradients are views of one flat buffer."""
+    Every intermediate lives in one fp32 workspace per pass."""
 
     @staticmethod
     def forward(ctx, x, mask, query, in_w, in_b, out_w, out_b, ln_w, ln_b, proj_w, proj_b, H, eps, drop_p, drop_seed, S):
         B, N, D = x.shape
         dev = x.device
         st = stream_ptr(dev)
-        KC = D // 64
-        Do = proj_w.shape[0] if proj_w is not None else D
+        has_proj = proj_w is not None
+        Do = proj_w.shape[0] if has_proj else D
+        drop = drop_p > 0.0
         mk = mask.to(torch.bool).contiguous().view(torch.uint8) if mask is not None else None
-        mb = i64(mk.stride(0)) if mk is not None else i64(0)
+        mb = mk.stride(0) if mk is not None else 0
         code = DTYPE_CODE[x.dtype]
         fp16 = 1 if x.dtype == torch.float16 else 0
-        # workspace layout (floats)
-        off, cur = {}, 0
-        for name, n in (("q0", D), ("qt", H * D), ("img", KC * 512), ("pm", B * S * H), ("pl", B * S * H),
-                        ("pl2", B * S * H if drop_p > 0.0 else 0), ("pa", B * S * H * D), ("xbar", B * H * D), ("m", B * H),
-                        ("l", B * H), ("sa", B * H), ("o", B * D), ("yhat", B * D), ("rstd", B),
-                        ("yln", B * D if proj_w is not None else 0)):
-            off[name] = cur
-            cur += _al(n)
-        ws = torch.empty(cur, dtype=torch.float32, device=dev)
-        base = ws.data_ptr()
-        P = {k: base + 4 * v for k, v in off.items()}
+        off, total = _layout(("f", B, D, H, S, drop, has_proj), lambda: (
+            ("q0", D), ("qt", H * D), ("img", D * 8), ("pm", B * S * H), ("pl", B * S * H), ("pl2", B * S * H if drop else 0),
+            ("pa", B * S * H * D), ("xbar", B * H * D), ("m", B * H), ("l", B * H), ("sa", B * H), ("o", B * D),
+            ("yhat", B * D), ("rstd", B), ("yln", B * D if has_proj else 0)))
+        ws = torch.empty(total, dtype=torch.float32, device=dev)
+        w = ws.data_ptr()
         out = torch.empty((B, Do), dtype=x.dtype, device=dev)
-        call("pool_prep", query, in_w, in_b, D, H, P["q0"], P["qt"], P["img"], fp16, st)
-        call("attnpool_tc_fwd", x, code, mk, mb, None, P["img"], B, N, D, H, S, P["pm"], P["pl"], P["pa"], float(drop_p),
-             int(drop_seed), P["pl2"] if drop_p > 0.0 else None, st)
-        call("pool_tail_fwd", P["pm"], P["pl"], P["pl2"] if drop_p > 0.0 else None, P["pa"], B, S, H, D,
-             in_w.data_ptr() + 8 * D * D, in_b.data_ptr() + 8 * D, out_w, out_b, ln_w, ln_b, float(eps), proj_w, proj_b,
-             Do if proj_w is not None else 0, P["xbar"], P["m"], P["l"], P["sa"], P["o"], P["yhat"], P["rstd"],
-             P["yln"] if proj_w is not None else None, out, code, st)
-        ctx.save_for_backward(x, mk if mk is not None else torch.empty(0, device=dev), ws, query, in_w, in_b, out_w, ln_w,
-                              proj_w if proj_w is not None else torch.empty(0, device=dev))
-        ctx.cfg = (B, N, D, H, S, Do, mask is not None, proj_w is not None, float(drop_p), int(drop_seed), off)
+        wv, bv = in_w.data_ptr() + 8 * D * D, in_b.data_ptr() + 8 * D
+        pl2 = w + off["pl2"] if drop else None
+        call("pool_prep", query, in_w, in_b, D, H, w + off["q0"], w + off["qt"], w + off["img"], fp16, st)
+        call("attnpool_tc_fwd", x, code, mk, mb, None, w + off["img"], B, N, D, H, S, w + off["pm"], w + off["pl"],
+             w + off["pa"], drop_p, drop_seed, pl2, st)
+        call("pool_tail_fwd", w + off["pm"], w + off["pl"], pl2, w + off["pa"], B, S, H, D, wv, bv, out_w, out_b, ln_w, ln_b,
+             eps, proj_w, proj_b, Do if has_proj else 0, w + off["xbar"], w + off["m"], w + off["l"], w + off["sa"],
+             w + off["o"], w + off["yhat"], w + off["rstd"], w + off["yln"] if has_proj else None, out, code, st)
+        ctx.save_for_backward(x, mk, ws, query, in_w, in_b, out_w, ln_w, proj_w)
+        ctx.cfg = (B, N, D, H, S, Do, has_proj, drop_p, drop_seed, off)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, mk, ws, query, in_w, in_b, out_w, ln_w, proj_w = ctx.saved_tensors
-        B, N, D, H, S, Do, has_mask, has_proj, drop_p, drop_seed, off = ctx.cfg
+        B, N, D, H, S, Do, has_proj, drop_p, drop_seed, off = ctx.cfg
         dev = x.device
         st = stream_ptr(dev)
-        KC = D // 64
-        mk = mk if has_mask else None
-        mb = i64(mk.stride(0)) if mk is not None else i64(0)
+        mb = mk.stride(0) if mk is not None else 0
         code = DTYPE_CODE[x.dtype]
         fp16 = 1 if x.dtype == torch.float16 else 0
         if dout.dtype not in DTYPE_CODE:
             dout = dout.float()
-        dout = dout.contiguous()
-        P = {k: ws.data_ptr() + 4 * v for k, v in off.items()}
-        o2, cur = {}, 0
-        for name, n in (("dyln", B * D), ("dy", B * D), ("do", B * D), ("dxbar", B * H * D), ("dsa", B * H), ("cdot", B * H),
-                        ("wimg", B * KC * 1024), ("pdq", B * S * H * D), ("dqt", H * D)):
-            o2[name] = cur
-            cur += _al(n)
-        ws2 = torch.empty(cur, dtype=torch.float32, device=dev)
-        Q = {k: ws2.data_ptr() + 4 * v for k, v in o2.items()}
-        # parameter gradients: views of one flat buffer
-        sizes = [("query", D), ("in_w", 3 * D * D), ("in_b", 3 * D), ("out_w", D * D), ("out_b", D), ("ln_w", D), ("ln_b", D)]
-        if has_proj:
-            sizes += [("proj_w", Do * D), ("proj_b", Do)]
-        g, cur = {}, 0
-        for name, n in sizes:
-            g[name] = (cur, n)
-            cur += _al(n)
-        gbuf = torch.empty(cur, dtype=torch.float32, device=dev)
-        G = {k: gbuf.data_ptr() + 4 * v[0] for k, v in g.items()}
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dcode = DTYPE_CODE[dout.dtype]
+        w = ws.data_ptr()
+        o2, total2 = _layout(("b", B, D, H, S), lambda: (
+            ("dyln", B * D), ("dy", B * D), ("do", B * D), ("dxbar", B * H * D), ("dsa", B * H), ("cdot", B * H),
+            ("wimg", B * D * 16), ("pdq", B * S * H * D), ("dqt", H * D)))
+        ws2 = torch.empty(total2, dtype=torch.float32, device=dev)
+        q = ws2.data_ptr()
+        # parameter gradients: fresh tensors (AccumulateGrad takes them over without a copy)
+        gq, gw, gb = torch.empty_like(query), torch.empty_like(in_w), torch.empty_like(in_b)
+        gow, gob = torch.empty_like(out_w), torch.empty((D,), dtype=torch.float32, device=dev)
+        glw, glb = torch.empty_like(ln_w), torch.empty_like(ln_w)
+        gpw = torch.empty_like(proj_w) if has_proj else None
+        gpb = torch.empty((Do,), dtype=torch.float32, device=dev) if has_proj else None
         dx = torch.empty((B, N, D), dtype=x.dtype, device=dev)
         use_sa = 1 if drop_p > 0.0 else 0
-        call("pool_tail_bwd", dout, DTYPE_CODE[dout.dtype], P["yhat"], P["rstd"], P["xbar"], P["sa"],
-             in_w.data_ptr() + 8 * D * D, in_b.data_ptr() + 8 * D, out_w, ln_w, proj_w if has_proj else None,
-             Do if has_proj else 0, P["qt"], B, H, D, Q["dyln"], Q["dy"], Q["do"], Q["dxbar"], Q["dsa"] if use_sa else None,
-             Q["cdot"], Q["wimg"], fp16, st)
-        call("pool_param_grads", Q["dy"], P["o"], Q["do"], P["xbar"], P["sa"], use_sa, Q["dyln"], P["yhat"], dout,
-             DTYPE_CODE[dout.dtype], P["yln"] if has_proj else None, Do if has_proj else 0, B, H, D, G["out_w"], G["out_b"],
-             G["in_w"] + 8 * D * D, G["in_b"] + 8 * D, G["ln_w"], G["ln_b"], G["proj_w"] if has_proj else None,
-             G["proj_b"] if has_proj else None, st)
-        call("attnpool_tc_bwd", x, code, mk, mb, None, None, None, Q["wimg"], Q["cdot"], P["m"], P["l"], B, N, D, H, S, dx,
-             P["sa"] if use_sa else None, Q["dsa"] if use_sa else None, drop_p, drop_seed, None, Q["pdq"], st)
-        call("pool_qgrads", Q["pdq"], B * S, P["q0"], query, in_w, H, D, Q["dqt"], G["in_w"], G["in_b"], G["query"], st)
-
-        def view(name, shape):
-            o, n = g[name]
-            return gbuf[o:o + n].view(shape)
-        return (dx, None, view("query", query.shape), view("in_w", (3 * D, D)), view("in_b", (3 * D,)),
-                view("out_w", (D, D)), view("out_b", (D,)), view("ln_w", (D,)), view("ln_b", (D,)),
-                view("proj_w", (Do, D)) if has_proj else None, view("proj_b", (Do,)) if has_proj else None,
-                None, None, None, None, None)
+        wv, bv = in_w.data_ptr() + 8 * D * D, in_b.data_ptr() + 8 * D
+        call("pool_tail_bwd", dout, dcode, w + off["yhat"], w + off["rstd"], w + off["xbar"], w + off["sa"], wv, bv, out_w,
+             ln_w, proj_w, Do if has_proj else 0, w + off["qt"], B, H, D, q + o2["dyln"], q + o2["dy"], q + o2["do"],
+             q + o2["dxbar"], q + o2["dsa"] if use_sa else None, q + o2["cdot"], q + o2["wimg"], fp16, st)
+        call("pool_param_grads", q + o2["dy"], w + off["o"], q + o2["do"], w + off["xbar"], w + off["sa"], use_sa,
+             q + o2["dyln"], w + off["yhat"], dout, dcode, w + off["yln"] if has_proj else None, Do if has_proj else 0, B, H,
+             D, gow, gob, gw.data_ptr() + 8 * D * D, gb.data_ptr() + 8 * D, glw, glb, gpw, gpb, st)
+        call("attnpool_tc_bwd", x, code, mk, mb, None, None, None, q + o2["wimg"], q + o2["cdot"], w + off["m"], w + off["l"],
+             B, N, D, H, S, dx, w + off["sa"] if use_sa else None, q + o2["dsa"] if use_sa else None, drop_p, drop_seed, None,
+             q + o2["pdq"], st)
+        call("pool_qgrads", q + o2["pdq"], B * S, w + off["q0"], query, in_w, H, D, q + o2["dqt"], gw, gb, gq, st)
+        return dx, None, gq, gw, gb, gow, gob, glw, glb, gpw, gpb, None, None, None, None, None
 
 
 def _fused_ok(x, params, D, H, Do) -> bool:
     if os.environ.get("B200CLIP_POOL_FUSED", "1") == "0":
         return False
-    if not all(p is None or (p.dtype == torch.float32 and p.is_contiguous() and p.is_cuda) for p in params):
-        return False
+    for p in params:
+        if p is not None and (p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda):
+            return False
     return bool(lib().b200clip_pooltail_ok(D, H, Do))
 
 

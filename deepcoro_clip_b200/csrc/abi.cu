@@ -426,6 +426,23 @@ int b200clip_pool_qgrads(const float* part_dq, int nparts, const float* q0, cons
   return pool_qgrads(part_dq, nparts, q0, query, in_proj_weight, heads, D, dqt, dw_in, db_in, dquery, S(stream));
 }
 
+int b200clip_inline_mp_fwd(const float* video, int64_t ldv, const float* text, int64_t ldt, const float* targets,
+                           const float* pos_weights, int64_t ldm, const float* abnormal, float margin,
+                           const float* log_temp, int B, int M, int D, int mode, float eps, float neg_weight, float* row_stat,
+                           float* col_stat, float* scalars, int* flag, void* stream) {
+  return inline_mp_fwd(video, ldv, text, ldt, targets, pos_weights, ldm, abnormal, margin, log_temp, B, M, D, mode, eps,
+                       neg_weight, row_stat, col_stat, scalars, flag, S(stream));
+}
+
+int b200clip_inline_mp_bwd(const float* video, int64_t ldv, const float* text, int64_t ldt, const float* targets,
+                           const float* pos_weights, int64_t ldm, const float* abnormal, float margin,
+                           const float* log_temp, int B, int M, int D, int mode, float eps, float neg_weight,
+                           const float* row_stat, const float* col_stat, const float* scalars, const int* flag,
+                           const float* grad_out, float* dvideo, float* dtext, double* dlog_temp_acc, void* stream) {
+  return inline_mp_bwd(video, ldv, text, ldt, targets, pos_weights, ldm, abnormal, margin, log_temp, B, M, D, mode, eps,
+                       neg_weight, row_stat, col_stat, scalars, flag, grad_out, dvideo, dtext, dlog_temp_acc, S(stream));
+}
+
 int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,
                        const float* ln_b, const float* query, const uint8_t* mask, int64_t mask_sb, int B, int N, int D,
                        float eps, float* out, const float* dout, float* dx, float* dpos, float* dln_w, float* dln_b,

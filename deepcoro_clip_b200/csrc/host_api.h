@@ -197,6 +197,15 @@ int pool_param_grads(const float* dy, const float* o, const float* do_, const fl
 int pool_qgrads(const float* part_dq, int nparts, const float* q0, const float* query, const float* w_in, int H, int D,
                 float* dqt, float* dw_in, float* db_in, float* dquery, cudaStream_t s);
 
+// inline_mp.cu: the runner's inline multi-positive branch from features (fp32 rows, D <= 1024)
+int inline_mp_fwd(const float* v, long long ldv, const float* t, long long ldt, const float* targets, const float* pw,
+                  long long ldm, const float* abn, float margin, const float* log_temp, int B, int M, int D, int mode,
+                  float eps, float neg_w, float* rstat, float* cstat, float* scal, int* flag, cudaStream_t s);
+int inline_mp_bwd(const float* v, long long ldv, const float* t, long long ldt, const float* targets, const float* pw,
+                  long long ldm, const float* abn, float margin, const float* log_temp, int B, int M, int D, int mode,
+                  float eps, float neg_w, const float* rstat, const float* cstat, const float* scal, const int* flag,
+                  const float* gout, float* dv, float* dt, double* dlt_acc, cudaStream_t s);
+
 // querypool.cu
 int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,
               const float* lnb, const float* q, const unsigned char* mask, long long mb, int B, int N, int D, float eps,

@@ -489,6 +489,29 @@ int b200clip_pool_param_grads(const float* dy, const float* o, const float* d_o,
 int b200clip_pool_qgrads(const float* part_dq, int nparts, const float* q0, const float* query, const float* in_proj_weight,
                          int heads, int D, float* dqt, float* dw_in, float* db_in, float* dquery, void* stream);
 
+/* The runner's inline multi-positive branch FROM FEATURES (runners/video_constrative_learning_runner.py:1256-1322, validation
+ * twin :1585-1641): video [B, D], text [M, D] raw fp32 rows (D <= 1024) -> L2-normalised, gated logits
+ * L_ij = s sigmoid(s) / exp(log_temp) + margin * abnormal_j, then
+ *   mode 0: WeightedSigLIPLoss (utils/loss/weighted_siglip.py:38-51) with pos = clamp_min(targets [* pos_weights], 0)
+ *           (the product only when pos_weights is given and not all zero: `flag`, set on the device, no host read);
+ *   mode 1: sum_ij w_ij BCEWithLogits(L_ij, targets_ij) / max(1, sum targets), w = where(targets > 0, pos_weights, neg_weight)
+ *           (neg_weight everywhere without pos_weights);
+ * plus the alignment scalars the runner logs (:1296-1311). No [B, M] matrix is written: one CTA per row recomputes its
+ * similarity row in fp32 per sweep (the branch is rank-local, B and M are batch sized).
+ *   inline_mp_fwd : row_stat [B, 8], col_stat [M, 8], scalars[8] = {loss, sum targets, alignment_logprob, alignment_prob,
+ *                   alignment_cosine, BCE denominator, valid rows, -}; flag: one int of device scratch.
+ *   inline_mp_bwd : dvideo [B, D], dtext [M, D] (either may be NULL ... dvideo must be given when dlog_temp_acc is),
+ *                   dlog_temp_acc: one fp64 (zeroed here) receiving d loss / d log_temp; grad_out: device scalar or NULL (= 1). */
+int b200clip_inline_mp_fwd(const float* video, int64_t ldv, const float* text, int64_t ldt, const float* targets,
+                           const float* pos_weights, int64_t ldm, const float* abnormal, float margin,
+                           const float* log_temp, int B, int M, int D, int mode, float eps, float neg_weight, float* row_stat,
+                           float* col_stat, float* scalars, int* flag, void* stream);
+int b200clip_inline_mp_bwd(const float* video, int64_t ldv, const float* text, int64_t ldt, const float* targets,
+                           const float* pos_weights, int64_t ldm, const float* abnormal, float margin,
+                           const float* log_temp, int B, int M, int D, int mode, float eps, float neg_weight,
+                           const float* row_stat, const float* col_stat, const float* scalars, const int* flag,
+                           const float* grad_out, float* dvideo, float* dtext, double* dlog_temp_acc, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).
  *   x [B, N, D] fp32 (strides sb, sn), pos [>=N, D] or NULL, final LayerNorm (ln_w, ln_b, eps), attn_query [D],

@@ -244,6 +244,53 @@ def alignment_diagnostics(video, text, log_temp, *, use_siglip: bool = False, dt
             "alignment_prob": float(np.exp(logprob))}                   # :1335
 
 
+def inline_multipositive(video, text, log_temp, targets, pos_weights=None, *, abnormal=None, margin: float = 0.0,
+                         weighted: bool = True, eps: float = 1e-6, neg_weight: float = 1.0, dtype=np.float64) -> dict:
+    """runners/video_constrative_learning_runner.py:1256-1322, the inline branch for batches with a positive mask: gated
+    logits s*sigmoid(s)/tau (:1258-1263) + margin on abnormal text columns (:1265-1273), then WeightedSigLIPLoss
+    (utils/loss/weighted_siglip.py:38-51; :1275-1283) or BCE-sum / max(1, sum targets) (:1284-1296); closed-form gradients
+    w.r.t. the raw features and log_temp; alignment scalars of :1298-1311."""
+    v = np.asarray(video, dtype=dtype); t = np.asarray(text, dtype=dtype)
+    tg = np.asarray(targets, dtype=dtype)
+    pw = None if pos_weights is None else np.asarray(pos_weights, dtype=dtype)
+    vh, vn = l2_normalize(v); th, tn = l2_normalize(t)
+    S = vh @ th.T
+    sg = _sigmoid(S)
+    G = S * sg
+    tau = np.exp(dtype(np.asarray(log_temp, dtype=np.float64).reshape(-1)[0]))
+    L = G / tau
+    if abnormal is not None and margin > 0 and np.count_nonzero(abnormal) > 0:
+        L = L + np.asarray(abnormal, dtype=dtype)[None, :] * margin
+    B, M = L.shape
+    use_pw = pw is not None and np.count_nonzero(pw) > 0
+    lse_r = _logsumexp(L, 1); lse_c = _logsumexp(L, 0)
+    if weighted:
+        pos = np.maximum(tg * pw if use_pw else tg, 0.0)
+        R = pos.sum(1); C = pos.sum(0)
+        dr = np.maximum(R, eps); dc = np.maximum(C, eps)
+        l_r = (lse_r * R - (pos * L).sum(1)) / dr
+        l_c = (lse_c * C - (pos * L).sum(0)) / dc
+        loss = 0.5 * (l_r.mean() + l_c.mean())
+        dL = 0.5 / B * (R[:, None] * np.exp(L - lse_r[:, None]) - pos) / dr[:, None] \
+            + 0.5 / M * (C[None, :] * np.exp(L - lse_c[None, :]) - pos) / dc[None, :]
+    else:
+        w = np.where(tg > 0, pw, neg_weight) if pw is not None else np.full_like(tg, neg_weight)
+        bce = np.maximum(L, 0) - L * tg + np.log1p(np.exp(-np.abs(L)))
+        denom = max(1.0, float(tg.sum()))
+        loss = (w * bce).sum() / denom
+        dL = w * (_sigmoid(L) - tg) / denom
+    dS = dL / tau * sg * (1 + S * (1 - sg))
+    dvh = dS @ th; dth = dS.T @ vh
+    pwm = pw * tg if use_pw else tg
+    rs = pwm.sum(1); valid = rs > 0
+    logp = L - lse_r[:, None]
+    alp = ((logp * pwm).sum(1)[valid] / rs[valid]).mean() if valid.any() else float("nan")
+    cos = S[tg != 0].mean() if (tg != 0).any() else float("nan")
+    return {"loss": float(loss), "dvideo": _normalize_backward(dvh, vh, vn), "dtext": _normalize_backward(dth, th, tn),
+            "dlog_temp": float(-(dL * G / tau).sum()), "alignment_logprob": float(alp), "alignment_prob": float(np.exp(alp)),
+            "alignment_cosine": float(cos)}
+
+
 # ---- fp32 timing port used by bench.py (cpu_baseline / --impl reference); same algorithm, all host threads ----
 def clip_fwd_bwd_f32(video: np.ndarray, text: np.ndarray, log_temp: float):
     """The reference step (normalize, matmul, 2x cross-entropy, backward) in fp32 numpy (BLAS threads)."""

@@ -211,6 +211,94 @@ def alignment():
         print(name, float(rec["cosine_f64"]), float(rec["logprob_f64"]), float(rec["prob_f64"]))
 
 
+def inline_multipos():
+    """SURVEY §8f #2 (loss half): the runner's inline multi-positive branch. The block is inline in the train step
+    (runners/video_constrative_learning_runner.py:1256-1322) and the runner does not import outside the training stack, so the
+    lines are transcribed here with the same torch calls (the WeightedSigLIPLoss it calls IS the imported reference class), in
+    fp32 (as the runner runs them) and fp64, with autograd for the gradients."""
+    import torch.nn.functional as F
+    from utils.loss.weighted_siglip import WeightedSigLIPLoss
+    cases = (("inline_mp_weighted_b48_m64_d128", 48, 64, 128, 70, math.log(0.1), True, True, 0.0, 1.0),
+             ("inline_mp_weighted_noweights_b33_m20_d96", 33, 20, 96, 71, math.log(0.07), True, False, 0.0, 1.0),
+             ("inline_mp_weighted_margin_b40_m56_d512", 40, 56, 512, 72, math.log(0.087), True, True, 0.5, 1.0),
+             ("inline_mp_bce_b48_m64_d128", 48, 64, 128, 73, math.log(0.1), False, True, 0.0, 0.5),
+             ("inline_mp_bce_noweights_b20_m35_d200", 20, 35, 200, 74, math.log(0.2), False, False, 0.25, 1.0))
+    for name, B, M, D, seed, lt, weighted, with_pw, margin, neg_w in cases:
+        g = torch.Generator().manual_seed(seed)
+        text = torch.randn(M, D, generator=g)
+        owner = torch.randint(0, M, (B,), generator=g)
+        video = 0.7 * text[owner] + torch.randn(B, D, generator=g)
+        targets = torch.zeros(B, M)
+        targets[torch.arange(B), owner] = 1.0
+        for _ in range(2):
+            targets[torch.arange(B), torch.randint(0, M, (B,), generator=g)] = 1.0
+        targets[B - 1] = 0.0                                           # one row without any positive
+        pw = None
+        if with_pw:
+            pw = targets * torch.tensor([1.0, 1.5, 2.5, 3.0])[torch.randint(0, 4, (B, M), generator=g)]
+        abn = (torch.rand(M, generator=g) < 0.3).float() if margin > 0 else None
+        rec = dict(video=video.numpy(), text=text.numpy(), log_temp=np.array([lt]), targets=targets.numpy(),
+                   weighted=np.array(weighted), margin=np.array(margin), neg_weight=np.array(neg_w))
+        if pw is not None:
+            rec["pos_weights"] = pw.numpy()
+        if abn is not None:
+            rec["abnormal"] = abn.numpy()
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            video_emb = video.to(dt).clone().requires_grad_(True)
+            text_emb = text.to(dt).clone().requires_grad_(True)
+            log_temp = torch.tensor([lt], dtype=dt, requires_grad=True)
+            positive_mask = targets.to(dt)
+            positive_weights = pw.to(dt) if pw is not None else None
+            # ---- runner lines :1256-1303 ----
+            tg = positive_mask
+            video_norm = F.normalize(video_emb, dim=1)
+            text_norm = F.normalize(text_emb, dim=1)
+            similarity = torch.matmul(video_norm, text_norm.t())
+            gated = similarity * torch.sigmoid(similarity)
+            temp_value = torch.exp(log_temp.float() if dt == torch.float32 else log_temp)
+            logits_matrix = gated / temp_value
+            if margin > 0 and abn is not None:
+                abnormal_vector = abn.to(dt)
+                if torch.count_nonzero(abnormal_vector) > 0:
+                    logits_matrix = logits_matrix + abnormal_vector.unsqueeze(0) * margin
+            if weighted:
+                pos_weights_for_loss = tg
+                if positive_weights is not None and torch.count_nonzero(positive_weights) > 0:
+                    pos_weights_for_loss = tg * positive_weights
+                clip_loss = WeightedSigLIPLoss()(logits=logits_matrix, positive_weights=pos_weights_for_loss)
+            else:
+                weight_matrix = torch.full_like(tg, neg_w)
+                if positive_weights is not None:
+                    weight_matrix = torch.where(tg > 0, positive_weights, weight_matrix)
+                loss_sum = F.binary_cross_entropy_with_logits(logits_matrix, tg, weight=weight_matrix, reduction='sum')
+                denom = max(1.0, float(tg.sum().item()))
+                clip_loss = loss_sum / denom
+            # ---- runner lines :1305-1322 ----
+            with torch.no_grad():
+                logprob_matrix = F.log_softmax(logits_matrix, dim=1)
+                if positive_weights is not None and torch.count_nonzero(positive_weights) > 0:
+                    pos_weight_mask = positive_weights * tg
+                else:
+                    pos_weight_mask = tg
+                row_sums = pos_weight_mask.sum(dim=1)
+                valid_rows = row_sums > 0
+                normalized_weights = torch.zeros_like(pos_weight_mask)
+                normalized_weights[valid_rows] = pos_weight_mask[valid_rows] / row_sums[valid_rows].unsqueeze(1)
+                alignment_logprob_tensor = (logprob_matrix * normalized_weights).sum(dim=1)[valid_rows].mean()
+                alignment_prob_tensor = alignment_logprob_tensor.exp()
+                alignment_cosine_tensor = similarity[tg.bool()].mean()
+            clip_loss.backward()
+            rec["loss_" + tag] = _np(clip_loss)
+            rec["dvideo_" + tag] = _np(video_emb.grad)
+            rec["dtext_" + tag] = _np(text_emb.grad)
+            rec["dlog_temp_" + tag] = _np(log_temp.grad)
+            rec["logprob_" + tag] = _np(alignment_logprob_tensor)
+            rec["prob_" + tag] = _np(alignment_prob_tensor)
+            rec["cosine_" + tag] = _np(alignment_cosine_tensor)
+        np.savez_compressed(OUT / f"{name}.npz", **rec)
+        print(name, float(rec["loss_f64"]), float(rec["logprob_f64"]), float(rec["cosine_f64"]))
+
+
 def dense_metrics():
     """SURVEY §8f #1: utils/retrieval_metrics.py on tie-free Gaussian similarities with multi-label ground truth."""
     from utils.retrieval_metrics import (compute_map, compute_median_rank, compute_mrr, compute_ndcg_at_k,
@@ -420,6 +508,6 @@ def qpool():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "tokenmean", "alignment", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool"]
+    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "inline_multipos", "tokenmean", "alignment", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool"]
     for name in which:
         globals()[name]()

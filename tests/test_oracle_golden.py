@@ -267,3 +267,31 @@ def test_torch_port_retrieval_matches_reference():
     for k in ("Recall@1", "Recall@5", "Recall@10", "Recall@50"):
         assert r[k] == float(ref[k]), k
     assert abs(r["MRR_V2T"] - float(ref["MRR_V2T"])) <= 1e-12
+
+
+INLINE_MP = ["inline_mp_weighted_b48_m64_d128", "inline_mp_weighted_noweights_b33_m20_d96",
+             "inline_mp_weighted_margin_b40_m56_d512", "inline_mp_bce_b48_m64_d128", "inline_mp_bce_noweights_b20_m35_d200"]
+
+
+def inline_mp_oracle(g):
+    return co.inline_multipositive(g["video"], g["text"], g["log_temp"], g["targets"],
+                                   g["pos_weights"] if "pos_weights" in g else None,
+                                   abnormal=g["abnormal"] if "abnormal" in g else None, margin=float(g["margin"]),
+                                   weighted=bool(g["weighted"]), neg_weight=float(g["neg_weight"]))
+
+
+@pytest.mark.parametrize("name", INLINE_MP)
+def test_inline_multipositive_oracle_matches_runner_transcription(name):
+    """closed forms of oracle.inline_multipositive against the autograd results of the transcribed runner lines
+    (runners/video_constrative_learning_runner.py:1256-1322) with the imported WeightedSigLIPLoss, fp64 and fp32."""
+    g = _load(name)
+    o = inline_mp_oracle(g)
+    assert abs(o["loss"] - float(g["loss_f64"])) <= 1e-12 * abs(float(g["loss_f64"]))
+    _close(o["dvideo"], g["dvideo_f64"], 1e-11, 0)
+    _close(o["dtext"], g["dtext_f64"], 1e-11, 0)
+    assert abs(o["dlog_temp"] - float(g["dlog_temp_f64"][0])) <= 1e-11 * max(1.0, abs(float(g["dlog_temp_f64"][0])))
+    assert abs(o["alignment_logprob"] - float(g["logprob_f64"])) <= 1e-12
+    assert abs(o["alignment_cosine"] - float(g["cosine_f64"])) <= 1e-12
+    # the runner's own fp32 arithmetic is within the north-star tolerances of the fp64 oracle
+    assert abs(o["loss"] - float(g["loss_f32"])) <= 1e-5 * abs(o["loss"])
+    _close(o["dvideo"], g["dvideo_f32"], 2e-3, 0)

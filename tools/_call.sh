@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-T=r02i
-timeout 300 python tools/gpu_check_pool_fused.py > gpurun_out/${T}_pool_fused.log 2>&1
-echo "pool fused rc=$? : $(tail -12 gpurun_out/${T}_pool_fused.log | cut -c1-400)"
-timeout 300 python tools/gpu_check_pool_tc.py > gpurun_out/${T}_pool_tc.log 2>&1
-echo "pool tc rc=$? : $(tail -2 gpurun_out/${T}_pool_tc.log | cut -c1-250)"
+T=r02k
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+timeout 300 $TR --master-port 29541 bench.py --gpus 8 > gpurun_out/${T}_bench_n8.json 2> gpurun_out/${T}_bench_n8.err
+echo "bench n8 rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n8.json)"
+timeout 300 $TR --master-port 29542 tools/gpu_check_dist.py > gpurun_out/${T}_dist_check_n8.log 2>&1
+echo "dist check n8 rc=$? : $(tail -2 gpurun_out/${T}_dist_check_n8.log | cut -c1-300)"
+B200CLIP_SYMM=0 timeout 300 $TR --master-port 29543 bench.py --gpus 8 --legs none --no-cpu-baseline > gpurun_out/${T}_bench_n8_nccl.json 2> gpurun_out/${T}_bench_n8_nccl.err
+echo "bench n8 nccl rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n8_nccl.json)"
