@@ -443,6 +443,19 @@ int b200clip_inline_mp_bwd(const float* video, int64_t ldv, const float* text, i
                        neg_weight, row_stat, col_stat, scalars, flag, grad_out, dvideo, dtext, dlog_temp_acc, S(stream));
 }
 
+int b200clip_xfblock_ok(int N, int D, int heads, int F) { return xfblock_ok(N, D, heads, F) ? 1 : 0; }
+
+int b200clip_xfblock(int backward, const void* const* ptrs, int B, int N, int D, int heads, int F, float eps1, float eps2,
+                     float drop_p, int64_t seed, int64_t mask_sb, void* stream) {
+  if (drop_p < 0.f || drop_p >= 1.f) return B2_EINVAL;
+  return xfblock(backward, ptrs, B, N, D, heads, F, eps1, eps2, drop_p, (unsigned long long)seed, mask_sb, S(stream));
+}
+
+int b200clip_xfblock_wgrad(const float* a, int64_t lda, const float* b, int64_t ldb, float* dw, float* db, int J, int I,
+                           int R, const float* a2, const float* xhat, float* dgamma, float* dbeta, int D2, void* stream) {
+  return xfblock_wgrad(a, lda, b, ldb, dw, db, J, I, R, a2, xhat, dgamma, dbeta, D2, S(stream));
+}
+
 int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,
                        const float* ln_b, const float* query, const uint8_t* mask, int64_t mask_sb, int B, int N, int D,
                        float eps, float* out, const float* dout, float* dx, float* dpos, float* dln_w, float* dln_b,

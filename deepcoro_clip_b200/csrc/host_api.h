@@ -206,6 +206,13 @@ int inline_mp_bwd(const float* v, long long ldv, const float* t, long long ldt, 
                   float eps, float neg_w, const float* rstat, const float* cstat, const float* scal, const int* flag,
                   const float* gout, float* dv, float* dt, double* dlt_acc, cudaStream_t s);
 
+// xfblock.cu: pre-LN transformer block over the views of a study (fp32, N <= 16, D <= 512, F = 4D <= 2048)
+bool xfblock_ok(int N, int D, int H, int F);
+int xfblock(int backward, const void* const* ptrs, int B, int N, int D, int H, int F, float eps1, float eps2, float drop_p,
+            unsigned long long seed, long long mask_sb, cudaStream_t s);
+int xfblock_wgrad(const float* a, long long lda, const float* bm, long long ldb, float* dw, float* db, int J, int I, int R,
+                  const float* a2, const float* xh, float* dg, float* dbeta, int D2, cudaStream_t s);
+
 // querypool.cu
 int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,
               const float* lnb, const float* q, const unsigned char* mask, long long mb, int B, int N, int D, float eps,

@@ -512,6 +512,30 @@ int b200clip_inline_mp_bwd(const float* video, int64_t ldv, const float* text, i
                            const float* row_stat, const float* col_stat, const float* scalars, const int* flag,
                            const float* grad_out, float* dvideo, float* dtext, double* dlog_temp_acc, void* stream);
 
+/* Pre-LN transformer block over the N <= 16 views of a study (models/video_aggregator.py:7-54: the blocks of
+ * EnhancedVideoAggregator), fp32, D % 128 == 0, D <= 512, F = hidden width (4 D) <= 2048, heads | 8
+ * (xfblock_ok = 1): one cluster of 8 CTAs per study, column slices per CTA, rows exchanged over distributed shared memory.
+ *   xfblock(backward = 0): out = x + drop(attn(LN1 x)); out += drop(W2 drop(gelu(W1 LN2(.) + b1)) + b2), saving what the
+ *                          backward reads;  xfblock(backward = 1): dx and the row-level gradients.
+ *   ptrs: HOST array of 35 device pointers —
+ *     [0] x [B,N,D]  [1] out [B,N,D]  [2] key_padding_mask [B,N] bytes, non-zero = ignore (or NULL; row pitch mask_sb)
+ *     [3] ln1.weight [4] ln1.bias [5] in_proj_weight [3D,D] [6] in_proj_bias [7] out_proj.weight [8] out_proj.bias
+ *     [9] ln2.weight [10] ln2.bias [11] mlp.0.weight [F,D] [12] mlp.0.bias [13] mlp.3.weight [D,F] [14] mlp.3.bias
+ *     saved: [15] xhat1 [R,D] [16] rstd1 [R] [17] h1 [R,D] [18] qkv [R,3D] [19] attn [B,heads,N,N] [20] o [R,D] [21] x1 [R,D]
+ *            [22] xhat2 [R,D] [23] rstd2 [R] [24] h2 [R,D] [25] z [R,F] [26] u [R,F]                    (R = B N)
+ *     backward: [27] dout [B,N,D] [28] dx [B,N,D] [29] d_f2 [R,D] [30] d_z [R,F] [31] d_ao [R,D] [32] d_qkv [R,3D]
+ *               [33] d_h2 [R,D] [34] d_h1 [R,D]
+ *   drop_p / seed: dropout of the four sites with the counter-based keep mask (0 = none).
+ *   xfblock_wgrad : dw[j, i] = sum_r a[r, j] b[r, i] (J x I, I <= 2048), db[j] = sum_r a[r, j]; with a2 / xhat / dgamma /
+ *                   dbeta also the LayerNorm sums dgamma[i] = sum_r a2[r, i] xhat[r, i], dbeta[i] = sum_r a2[r, i] (width D2).
+ *                   Four calls give every parameter gradient of the block: (d_f2, u) -> mlp.3; (d_z, h2; d_h2, xhat2) ->
+ *                   mlp.0 + ln2; (d_ao, o) -> out_proj; (d_qkv, h1; d_h1, xhat1) -> in_proj + ln1. */
+int b200clip_xfblock_ok(int N, int D, int heads, int F);
+int b200clip_xfblock(int backward, const void* const* ptrs, int B, int N, int D, int heads, int F, float eps1, float eps2,
+                     float drop_p, int64_t seed, int64_t mask_sb, void* stream);
+int b200clip_xfblock_wgrad(const float* a, int64_t lda, const float* b, int64_t ldb, float* dw, float* db, int J, int I,
+                           int R, const float* a2, const float* xhat, float* dgamma, float* dbeta, int D2, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).
  *   x [B, N, D] fp32 (strides sb, sn), pos [>=N, D] or NULL, final LayerNorm (ln_w, ln_b, eps), attn_query [D],

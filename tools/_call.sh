@@ -1,9 +1,6 @@
 mkdir -p gpurun_out
-T=r02k
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-timeout 300 $TR --master-port 29541 bench.py --gpus 8 > gpurun_out/${T}_bench_n8.json 2> gpurun_out/${T}_bench_n8.err
-echo "bench n8 rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n8.json)"
-timeout 300 $TR --master-port 29542 tools/gpu_check_dist.py > gpurun_out/${T}_dist_check_n8.log 2>&1
-echo "dist check n8 rc=$? : $(tail -2 gpurun_out/${T}_dist_check_n8.log | cut -c1-300)"
-B200CLIP_SYMM=0 timeout 300 $TR --master-port 29543 bench.py --gpus 8 --legs none --no-cpu-baseline > gpurun_out/${T}_bench_n8_nccl.json 2> gpurun_out/${T}_bench_n8_nccl.err
-echo "bench n8 nccl rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n8_nccl.json)"
+T=r02m
+timeout 300 python tools/gpu_check_xfblock.py > gpurun_out/${T}_xfblock.log 2>&1
+echo "xfblock rc=$? : $(tail -14 gpurun_out/${T}_xfblock.log | cut -c1-400)"
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/${T}_pytest_gpu.log 2>&1
+echo "pytest rc=$? : $(tail -1 gpurun_out/${T}_pytest_gpu.log)"; grep -E "^FAILED|^ERROR" gpurun_out/${T}_pytest_gpu.log | head -20
