@@ -563,7 +563,7 @@ def retrieval_leg(ctx: Ctx, prob, cpu_baseline: bool):
         r = compute_recall_at_k_streaming(v, t, gt, k_values=[1, 5, 10], precision="bf16", use_ddp=True, _counts_out=keep)
         r["MRR_V2T"] = float(mrr_sum_from_counts(keep[0], M).item() / Nv)
         box["r"], box["counts"] = r, keep[0]
-    ms = timed(ctx, once, 3, 1)
+    ms = timed(ctx, once, 5, 3)
     r = box["r"]
     # parity at full size: brute-force ranks of a sample of rows (fp32 matmul of exact-grid values is exact)
     rows = torch.randint(0, Nv, (512,), device=ctx.dev, generator=torch.Generator(device=ctx.dev).manual_seed(7))
@@ -585,7 +585,7 @@ def retrieval_leg(ctx: Ctx, prob, cpu_baseline: bool):
            "parity": {"rank_counts_bit_exact_on_sampled_rows": exact, "sampled_rows": 512,
                       "checker": "brute-force fp32 similarity rows (exact for grid embeddings), lowest-index tie rule"}}
     if cpu_baseline and ctx.rank == 0 and ctx.world == 1:
-        out["cpu_baseline"] = cpu_retrieval_baseline(M, D)
+        out["cpu_baseline_fn"] = lambda: cpu_retrieval_baseline(M, D)
     return out
 
 
@@ -599,7 +599,7 @@ def topk_leg(ctx: Ctx, prob):
 
     def once():
         box["s"], box["i"] = streaming_topk(v, t, 10, precision="bf16", use_ddp=True)
-    ms = timed(ctx, once, 3, 1)
+    ms = timed(ctx, once, 5, 2)
     st, it = torch.topk(v[:1024] @ t.T, 11, dim=1)
     tie_free = (st[:, :-1] != st[:, 1:]).all(dim=1)
     exact = bool((box["s"][:1024] == st[:, :10]).all().item() and
@@ -677,7 +677,7 @@ def siglip_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
                                 "all-reduces); the mask pass alone is HBM-bound"},
            "parity_fn": parity_fn}
     if cpu_baseline and rank == 0 and world == 1:
-        out["cpu_baseline"] = cpu_siglip_baseline(Bg, T, D)
+        out["cpu_baseline_fn"] = lambda: cpu_siglip_baseline(Bg, T, D)
     return out
 
 
@@ -749,7 +749,7 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
                         "note": "algorithmic bytes of the whole step (RoPE 2 x 4*B*H*N*Dh*2, pool 4 x B*N*D*2) over its time; "
                                 "per-kernel fractions under `kernels`"}}
     if cpu_baseline and ctx.rank == 0 and ctx.world == 1:
-        out["cpu_baseline"] = cpu_tokens_baseline()
+        out["cpu_baseline_fn"] = cpu_tokens_baseline
     return out
 
 
@@ -824,7 +824,7 @@ def main():
                                "value": 32768 / (d["eager_ms"] * 1e-3), "unit": UNIT, "ms_per_step": d["eager_ms"],
                                "n_gpus": world, "parity_fn": d["parity_fn"], "roofline": d.get("roofline")}
                 if want_cpu and rank == 0 and world == 1:
-                    extras[leg]["cpu_baseline"] = cpu_clip_baseline(32768, 768)
+                    extras[leg]["cpu_baseline_fn"] = lambda: cpu_clip_baseline(32768, 768)
         except Exception as e:      # a failing extra leg must not take the headline line down with it
             if world > 1:
                 raise
@@ -835,6 +835,10 @@ def main():
     for leg in extras.values():
         if "parity_fn" in leg:
             leg["parity"] = leg.pop("parity_fn")()
+    # ---- CPU baselines last: seconds of host work between GPU legs would let the GPU clocks fall before the next timing ----
+    for leg in extras.values():
+        if "cpu_baseline_fn" in leg:
+            leg["cpu_baseline"] = leg.pop("cpu_baseline_fn")()
 
     cpu = cpu_clip_baseline(N, D) if (rank == 0 and world == 1 and want_cpu) else None
 

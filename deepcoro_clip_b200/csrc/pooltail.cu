@@ -51,45 +51,71 @@ __device__ __forceinline__ void st_any(void* p, size_t i, int dtype, float v) {
 }
 
 // out[r * ostride + j] = bias[j0 + j] * bscale[r] + sum_i W[(j0 + j) * ldw + i] v[r * vstride + i]   (j < nj, i < K, K % 128 == 0)
-// v in shared memory; one warp per output column, lanes over i (float4), the weight slice is read exactly once.
+// v in shared memory. A warp takes four output columns at a time (four independent weight-row requests in flight per step —
+// these kernels are latency-bound on the weight reads — sharing the reads of v); the weight slice is read exactly once.
 __device__ void slice_matvec(const float* __restrict__ W, long long ldw, int j0, int nj, int K, const float* v, int vstride,
                              float* out, int ostride, const float* __restrict__ bias, const float* bscale) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = TL_THREADS / 32;
-  for (int j = warp; j < nj; j += nw) {
-    float acc[TL_RB];
+  for (int jb = warp * 4; jb < nj; jb += nw * 4) {
+    float acc[4][TL_RB];
 #pragma unroll
-    for (int r = 0; r < TL_RB; ++r) acc[r] = 0.f;
-    const float* wr = W + (long long)(j0 + j) * ldw;
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < TL_RB; ++r) acc[q][r] = 0.f;
+    const float* wr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wr[q] = W + (long long)(j0 + min(jb + q, nj - 1)) * ldw;
+#pragma unroll 2
     for (int i = lane * 4; i < K; i += 128) {
-      const float4 w = *reinterpret_cast<const float4*>(wr + i);
+      float4 w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const float4*>(wr[q] + i);
 #pragma unroll
       for (int r = 0; r < TL_RB; ++r) {
         const float4 x = *reinterpret_cast<const float4*>(v + r * vstride + i);
-        acc[r] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[r]))));
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          acc[q][r] = fmaf(w[q].x, x.x, fmaf(w[q].y, x.y, fmaf(w[q].z, x.z, fmaf(w[q].w, x.w, acc[q][r]))));
       }
     }
 #pragma unroll
-    for (int r = 0; r < TL_RB; ++r) {
-      const float s = warp_sum(acc[r]);
-      if (lane == 0) out[r * ostride + j] = s + (bias ? bias[j0 + j] * (bscale ? bscale[r] : 1.f) : 0.f);
-    }
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < TL_RB; ++r) {
+        const float s = warp_sum(acc[q][r]);
+        if (lane == 0 && jb + q < nj)
+          out[r * ostride + jb + q] = s + (bias ? bias[j0 + jb + q] * (bscale ? bscale[r] : 1.f) : 0.f);
+      }
   }
 }
 
 // out[r * ostride + i] = sum_{j in [ja, jb)} W[j * ldw + i0 + i] u[r * ustride + j]   (i < ni <= 64); u in shared memory.
-// thread = (column i, one of 4 row groups); `scratch` holds 4 * TL_RB * 64 floats. Ends with a __syncthreads.
+// thread = (column i, one of 4 row groups), eight weight loads in flight per thread; `scratch` holds 4 * TL_RB * 64 floats.
+// Ends with a __syncthreads.
 __device__ void slice_matvec_t(const float* __restrict__ W, long long ldw, int i0, int ni, int ja, int jb, const float* u,
                                int ustride, float* out, int ostride, float* scratch) {
   const int i = threadIdx.x & 63, jp = threadIdx.x >> 6;
   float acc[TL_RB];
 #pragma unroll
   for (int r = 0; r < TL_RB; ++r) acc[r] = 0.f;
-  if (i < ni)
-    for (int j = ja + jp; j < jb; j += 4) {
-      const float w = W[(long long)j * ldw + i0 + i];
+  if (i < ni) {
+    const float* wc = W + i0 + i;
+    int j = ja + jp;
+    for (; j + 28 < jb; j += 32) {
+      float w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = wc[(long long)(j + 4 * e) * ldw];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int r = 0; r < TL_RB; ++r) acc[r] = fmaf(w[e], u[r * ustride + j + 4 * e], acc[r]);
+    }
+    for (; j < jb; j += 4) {
+      const float w = wc[(long long)j * ldw];
 #pragma unroll
       for (int r = 0; r < TL_RB; ++r) acc[r] = fmaf(w, u[r * ustride + j], acc[r]);
     }
+  }
 #pragma unroll
   for (int r = 0; r < TL_RB; ++r) scratch[(jp * TL_RB + r) * 64 + i] = acc[r];
   __syncthreads();
@@ -144,18 +170,26 @@ __global__ void __launch_bounds__(TL_THREADS) pool_prep_kernel(PrepParams p) {
   __syncthreads();
   // q0_h[k] = W_q[h Dh + k, :] . query + b_q[h Dh + k]: one warp per row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < Dh; k += TL_THREADS / 32) {
-    const float* wr = p.w_in + (size_t)(h * Dh + k) * D;
-    float a = 0.f;
+  for (int kb = warp * 4; kb < Dh; kb += TL_THREADS / 32 * 4) {       // four rows per warp and step: four requests in flight
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wr[q] = p.w_in + (size_t)(h * Dh + min(kb + q, Dh - 1)) * D;
     for (int i = lane * 4; i < D; i += 128) {
-      const float4 w = *reinterpret_cast<const float4*>(wr + i);
-      a = fmaf(w.x, s_q[i], fmaf(w.y, s_q[i + 1], fmaf(w.z, s_q[i + 2], fmaf(w.w, s_q[i + 3], a))));
+      float4 w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const float4*>(wr[q] + i);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        a[q] = fmaf(w[q].x, s_q[i], fmaf(w[q].y, s_q[i + 1], fmaf(w[q].z, s_q[i + 2], fmaf(w[q].w, s_q[i + 3], a[q]))));
     }
-    a = warp_sum(a);
-    if (lane == 0) {
-      a += p.b_in[h * Dh + k];
-      s_q0[k] = a;
-      if (kc == 0) p.q0[h * Dh + k] = a;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float v = warp_sum(a[q]) + p.b_in[h * Dh + min(kb + q, Dh - 1)];
+      if (lane == 0 && kb + q < Dh) {
+        s_q0[kb + q] = v;
+        if (kc == 0) p.q0[h * Dh + kb + q] = v;
+      }
     }
   }
   __syncthreads();
@@ -163,6 +197,7 @@ __global__ void __launch_bounds__(TL_THREADS) pool_prep_kernel(PrepParams p) {
   const int dl = threadIdx.x & 63, kp = threadIdx.x >> 6;
   const float* wk = p.w_in + (size_t)D * D + (size_t)(h * Dh) * D + kc * 64 + dl;
   float a = 0.f;
+#pragma unroll 8
   for (int k = kp; k < Dh; k += 4) a = fmaf(wk[(size_t)k * D], s_q0[k], a);
   s_part[kp][dl] = a;
   __syncthreads();
@@ -483,6 +518,7 @@ __global__ void __launch_bounds__(TL_THREADS) pool_param_grads_kernel(ParamGradP
       coef[r][b - bc] = c;
     }
     __syncthreads();
+#pragma unroll 4
     for (int b = 0; b < nb; ++b) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -544,12 +580,34 @@ __global__ void __cluster_dims__(TL_CL, 1, 1) __launch_bounds__(TL_THREADS) pool
   const int D = p.D, w8 = D / TL_CL, Dh = D / p.H;
   const int rank = (int)cluster_ctarank(), j0 = rank * w8, h = j0 / Dh;
   const float isq = rsqrtf((float)Dh);
-  // dqt[h, :] = sum over the partials
-  for (int d = threadIdx.x; d < D; d += TL_THREADS) {
-    float a = 0.f;
-    for (int s = 0; s < p.nparts; ++s) a += p.part_dq[((size_t)s * p.H + h) * D + d];
-    s_dqt[d] = a;
-    if (j0 % Dh == 0) p.dqt[(size_t)h * D + d] = a;
+  // dqt[h, :] = sum over the partials: thread = (4 channels, one of TL_THREADS / (D / 4) partial groups), 8 loads in flight
+  {
+    const int nv = D / 4, v4 = threadIdx.x % nv, grp = threadIdx.x / nv, ngrp = TL_THREADS / nv;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grp < ngrp) {
+      const float4* src = reinterpret_cast<const float4*>(p.part_dq + (size_t)h * D) + v4;
+      const size_t stride = (size_t)p.H * D / 4;
+      int sidx = grp;
+      for (; sidx + 7 * ngrp < p.nparts; sidx += 8 * ngrp) {
+        float4 t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = src[(size_t)(sidx + e * ngrp) * stride];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a.x += t[e].x; a.y += t[e].y; a.z += t[e].z; a.w += t[e].w; }
+      }
+      for (; sidx < p.nparts; sidx += ngrp) {
+        const float4 t = src[(size_t)sidx * stride];
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      reinterpret_cast<float4*>(s_full)[grp * nv + v4] = a;       // s_full is free until the dq0 stage
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += TL_THREADS) {
+      float t = 0.f;
+      for (int g2 = 0; g2 < ngrp; ++g2) t += s_full[g2 * D + d];
+      s_dqt[d] = t;
+      if (j0 % Dh == 0) p.dqt[(size_t)h * D + d] = t;
+    }
   }
   __syncthreads();
   // dW_k[j, :] = q0[j] dqt[h, :] / sqrt(Dh);  dq0[j] = W_k[j, :] . dqt[h, :] / sqrt(Dh)   (j in the slice; b_k gets no gradient)

@@ -36,35 +36,49 @@ __device__ __forceinline__ float xb_gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-// out[r * ostride + j] = bias[j0 + j] + sum_i W[(j0 + j) * ldw + i] v[r * vstride + i]   (j < nj, K % 128 == 0), one warp per j
+// out[r * ostride + j] = bias[j0 + j] + sum_i W[(j0 + j) * ldw + i] v[r * vstride + i]   (j < nj, K % 128 == 0).
+// A warp takes FOUR output columns at a time: the four weight rows are loaded together (4 independent 512-byte requests per
+// warp and step in flight instead of one — these kernels are latency-bound on the weight reads) and share the reads of v.
 template <int RB>
 __device__ void xb_matvec(const float* __restrict__ W, long long ldw, int j0, int nj, int K, const float* v, int vstride,
                           float* out, int ostride, const float* __restrict__ bias) {
+  constexpr int JU = RB <= 8 ? 4 : 2;      // output columns per warp and step (register budget at RB = 16)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = XB_THREADS / 32;
-  for (int j = warp; j < nj; j += nw) {
-    float acc[RB];
+  for (int jb = warp * JU; jb < nj; jb += nw * JU) {
+    float acc[JU][RB];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-    const float* wr = W + (long long)(j0 + j) * ldw;
+    for (int q = 0; q < JU; ++q)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) acc[q][r] = 0.f;
+    const float* wr[JU];
+#pragma unroll
+    for (int q = 0; q < JU; ++q) wr[q] = W + (long long)(j0 + min(jb + q, nj - 1)) * ldw;
+#pragma unroll 2
     for (int i = lane * 4; i < K; i += 128) {
-      const float4 w = *reinterpret_cast<const float4*>(wr + i);
+      float4 w[JU];
+#pragma unroll
+      for (int q = 0; q < JU; ++q) w[q] = *reinterpret_cast<const float4*>(wr[q] + i);
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const float4 x = *reinterpret_cast<const float4*>(v + r * vstride + i);
-        acc[r] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[r]))));
+#pragma unroll
+        for (int q = 0; q < JU; ++q)
+          acc[q][r] = fmaf(w[q].x, x.x, fmaf(w[q].y, x.y, fmaf(w[q].z, x.z, fmaf(w[q].w, x.w, acc[q][r]))));
       }
     }
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const float s = warp_sum(acc[r]);
-      if (lane == 0) out[r * ostride + j] = s + (bias ? bias[j0 + j] : 0.f);
-    }
+    for (int q = 0; q < JU; ++q)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float s = warp_sum(acc[q][r]);
+        if (lane == 0 && jb + q < nj) out[r * ostride + jb + q] = s + (bias ? bias[j0 + jb + q] : 0.f);
+      }
   }
   __syncthreads();
 }
 
 // out[r * ostride + i] (+)= sum_{j < J} W[j * ldw + i0 + i] u[r * ustride + j]   (i < ni <= 64): thread = (column, 1 of 4 row
-// groups), `scratch` = 4 * RB * 64 floats. Ends with __syncthreads.
+// groups), eight weight loads in flight per thread; `scratch` = 4 * RB * 64 floats. Ends with __syncthreads.
 template <int RB>
 __device__ void xb_matvec_t(const float* __restrict__ W, long long ldw, int i0, int ni, int J, const float* u, int ustride,
                             float* out, int ostride, float* scratch, bool accumulate) {
@@ -72,12 +86,24 @@ __device__ void xb_matvec_t(const float* __restrict__ W, long long ldw, int i0, 
   float acc[RB];
 #pragma unroll
   for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-  if (i < ni)
-    for (int j = jp; j < J; j += 4) {
-      const float w = W[(long long)j * ldw + i0 + i];
+  if (i < ni) {
+    const float* wc = W + i0 + i;
+    int j = jp;
+    for (; j + 28 < J; j += 32) {
+      float w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = wc[(long long)(j + 4 * e) * ldw];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = fmaf(w[e], u[r * ustride + j + 4 * e], acc[r]);
+    }
+    for (; j < J; j += 4) {
+      const float w = wc[(long long)j * ldw];
 #pragma unroll
       for (int r = 0; r < RB; ++r) acc[r] = fmaf(w, u[r * ustride + j], acc[r]);
     }
+  }
 #pragma unroll
   for (int r = 0; r < RB; ++r) scratch[(jp * RB + r) * 64 + i] = acc[r];
   __syncthreads();
@@ -146,7 +172,7 @@ struct XbSmem {
 };
 
 template <int RB>
-__global__ void __cluster_dims__(XB_CL, 1, 1) __launch_bounds__(XB_THREADS) xfblock_fwd_kernel(XbParams p) {
+__global__ void __cluster_dims__(XB_CL, 1, 1) __launch_bounds__(XB_THREADS, 1) xfblock_fwd_kernel(XbParams p) {
   extern __shared__ __align__(16) float xb_smem[];
   using L = XbSmem<RB>;
   const int D = p.D, F = p.F, N = p.N, w8 = D / XB_CL, f8 = F / XB_CL, Dh = D / p.H;
@@ -297,7 +323,7 @@ __global__ void __cluster_dims__(XB_CL, 1, 1) __launch_bounds__(XB_THREADS) xfbl
 }
 
 template <int RB>
-__global__ void __cluster_dims__(XB_CL, 1, 1) __launch_bounds__(XB_THREADS) xfblock_bwd_kernel(XbParams p) {
+__global__ void __cluster_dims__(XB_CL, 1, 1) __launch_bounds__(XB_THREADS, 1) xfblock_bwd_kernel(XbParams p) {
   extern __shared__ __align__(16) float xb_smem[];
   using L = XbSmem<RB>;
   const int D = p.D, F = p.F, N = p.N, w8 = D / XB_CL, f8 = F / XB_CL, Dh = D / p.H;
@@ -476,7 +502,7 @@ struct WgParams {
 __global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
   __shared__ float coef[8][128];
   if (blockIdx.y == 1) {
-    if (!p.dg) return;
+    if (!p.dg || blockIdx.z != 0) return;
     const int i = blockIdx.x * XB_THREADS + threadIdx.x;
     if (i < p.D2) {
       float g = 0.f, bb = 0.f;
@@ -487,7 +513,8 @@ __global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
   }
   const int j0 = blockIdx.x * 8;
   if (j0 >= p.J) return;
-  constexpr int MAXE = 8;                 // I <= 2048
+  constexpr int MAXE = 4;                 // 1024 columns per CTA (blockIdx.z selects the column block)
+  const int ibase = blockIdx.z * MAXE * XB_THREADS;
   float acc[8][MAXE];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
@@ -502,10 +529,11 @@ __global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
       coef[jj][r - rc] = j0 + jj < p.J ? p.a[(size_t)r * p.lda + j0 + jj] : 0.f;
     }
     __syncthreads();
+#pragma unroll 2
     for (int r = 0; r < nr; ++r) {
 #pragma unroll
       for (int e = 0; e < MAXE; ++e) {
-        const int i = threadIdx.x + e * XB_THREADS;
+        const int i = ibase + threadIdx.x + e * XB_THREADS;
         if (i < p.I) {
           const float v = p.bm[(size_t)(rc + r) * p.ldb + i];
 #pragma unroll
@@ -518,13 +546,13 @@ __global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
   }
 #pragma unroll
   for (int e = 0; e < MAXE; ++e) {
-    const int i = threadIdx.x + e * XB_THREADS;
+    const int i = ibase + threadIdx.x + e * XB_THREADS;
     if (i < p.I)
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj)
         if (j0 + jj < p.J) p.dw[(size_t)(j0 + jj) * p.I + i] = acc[jj][e];
   }
-  if (threadIdx.x < 8 && j0 + threadIdx.x < p.J && p.db) p.db[j0 + threadIdx.x] = bsum;
+  if (blockIdx.z == 0 && threadIdx.x < 8 && j0 + threadIdx.x < p.J && p.db) p.db[j0 + threadIdx.x] = bsum;
 }
 
 }  // namespace b2
@@ -577,7 +605,7 @@ int xfblock_wgrad(const float* a, long long lda, const float* bm, long long ldb,
   if (!a || !bm || !dw || J <= 0 || I <= 0 || I > 2048 || R <= 0) return B2_EINVAL;
   WgParams p{a, lda, bm, ldb, dw, db, J, I, R, a2, xh, dg, dbeta, D2};
   const int gx = max((J + 7) / 8, dg ? (D2 + XB_THREADS - 1) / XB_THREADS : 1);
-  xfblock_wgrad_kernel<<<dim3(gx, dg ? 2 : 1), XB_THREADS, 0, s>>>(p);
+  xfblock_wgrad_kernel<<<dim3(gx, dg ? 2 : 1, (I + 4 * XB_THREADS - 1) / (4 * XB_THREADS)), XB_THREADS, 0, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
