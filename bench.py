@@ -730,6 +730,39 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
                                "frac_hbm": 4 * bx / ms / 1e6 / hbm,
                                "note": "algorithmic: x read once forward, read + dx written backward (SURVEY 8d: 1 + 3 passes)"}
 
+    # the two streaming kernels alone (C ABI, back-to-back launches on three rotating copies of x so that nothing stays in L2)
+    try:
+        from deepcoro_clip_b200._lib import call, i64, lib, stream_ptr
+        xs = [x.detach()] + [torch.randn_like(x) for _ in range(2)]
+        Sp = lib().b200clip_attnpool_tc_splits(xs[0].data_ptr(), 1, i64(L * D), i64(D), S * V, L, D, 8)
+        if Sp > 0:
+            qt = torch.randn(8, D, device=dev) * 0.05
+            pm = torch.empty((S * V, Sp, 8), device=dev); pl = torch.empty_like(pm); pa = torch.empty((S * V, Sp, 8, D), device=dev)
+            xb_ = torch.randn(S * V, 8, D, device=dev); mm = torch.zeros((S * V, 8), device=dev); ll = torch.ones((S * V, 8), device=dev)
+            dxb = torch.randn(S * V, 8, D, device=dev); pdq = torch.empty((S * V, Sp, 8, D), device=dev)
+            dxs = [torch.empty_like(xs[0]) for _ in range(3)]
+            st = stream_ptr(dev)
+            it = {"i": 0}
+
+            def k_fwd():
+                it["i"] += 1
+                call("attnpool_tc_fwd", xs[it["i"] % 3], 1, None, i64(0), qt, None, S * V, L, D, 8, Sp, pm, pl, pa, 0.0, 0, None, st)
+
+            def k_bwd():
+                it["i"] += 1
+                call("attnpool_tc_bwd", xs[it["i"] % 3], 1, None, i64(0), qt, dxb, xb_, None, None, mm, ll, S * V, L, D, 8, Sp,
+                     dxs[it["i"] % 3], None, None, 0.0, 0, None, pdq, st)
+            ms = t_ms(k_fwd, 20)
+            res["pool_fwd_tc_kernel"] = {"ms": ms, "algorithmic_bytes": bx, "GBps": bx / ms / 1e6, "frac_hbm": bx / ms / 1e6 / hbm,
+                                         "note": "csrc/attnpool_tc.cu, operand image built in the kernel (module calls use pool_prep's)"}
+            ms = t_ms(k_bwd, 20)
+            res["pool_bwd_tc_kernel"] = {"ms": ms, "algorithmic_bytes": 2 * bx, "GBps": 2 * bx / ms / 1e6,
+                                         "frac_hbm": 2 * bx / ms / 1e6 / hbm,
+                                         "note": "reads x once, writes dx and the query-gradient partials in the same pass"}
+            del xs, dxs, pa, pdq
+    except Exception as e:      # the module-level numbers above stand on their own
+        res["pool_tc_kernels"] = {"error": f"{type(e).__name__}: {e}"}
+
     xa = torch.randn(S, V, D, device=dev, requires_grad=True)
     ga = torch.randn(S, D, device=dev)
 
@@ -739,6 +772,12 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
         torch.autograd.backward((qo, ko), (gq, gk))
         pool(x).backward(gy)
         agg(xa).backward(ga)
+    def agg_fb():
+        xa.grad = None
+        agg(xa).backward(ga)
+    ms = t_ms(agg_fb)
+    res["aggregator_fwd_bwd"] = {"ms": ms, "note": "EnhancedVideoAggregator (depth 2, train mode): 2 x (1 + 5) cluster-kernel launches "
+                                                   "+ the query-pool tail; latency-bound, [8, 4, 512] fp32"}
     ms = t_ms(whole, steps)
     total_bytes = 2 * b_rope + 4 * bx
     out = {"metric": "study-mode token path fwd+bwd (config 3)", "value": S * ctx.world / (ms * 1e-3), "unit": "studies/s",

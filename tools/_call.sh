@@ -1,8 +1,10 @@
 mkdir -p gpurun_out
-T=r02q
-timeout 300 python tools/gpu_check_xfblock.py > gpurun_out/${T}_xfblock.log 2>&1
-echo "xfblock rc=$? : $(tail -4 gpurun_out/${T}_xfblock.log | cut -c1-300)"
-timeout 300 python tools/gpu_check_pool_fused.py > gpurun_out/${T}_pool_fused.log 2>&1
-echo "pool fused rc=$? : $(tail -4 gpurun_out/${T}_pool_fused.log | cut -c1-300)"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_tokens_launches.csv python tools/gpu_tokens_step.py 4 > gpurun_out/${T}_ncu.log 2>&1
-echo "launch list rc=$?"
+T=r02r
+NG=$(nvidia-smi -L | wc -l)
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
+timeout 300 $TR --master-port 29541 bench.py --gpus $NG --no-cpu-baseline > gpurun_out/${T}_bench_n${NG}.json 2> gpurun_out/${T}_bench_n${NG}.err
+echo "bench n$NG rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n${NG}.json)"
+timeout 300 $TR --master-port 29542 tools/gpu_check_dist.py > gpurun_out/${T}_dist_check_n${NG}.log 2>&1
+echo "dist check n$NG rc=$? : $(tail -2 gpurun_out/${T}_dist_check_n${NG}.log | cut -c1-300)"
+B200CLIP_SYMM=0 timeout 300 $TR --master-port 29543 bench.py --gpus $NG --legs none --no-cpu-baseline > gpurun_out/${T}_bench_n${NG}_nccl.json 2> gpurun_out/${T}_bench_n${NG}_nccl.err
+echo "bench n$NG nccl rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n${NG}_nccl.json)"
