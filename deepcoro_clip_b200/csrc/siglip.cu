@@ -224,6 +224,169 @@ int siglip_compact(const float* mask, long ldm, const float* pw, long ldw, int B
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
+}  // namespace b2host
+
+namespace b2 {
+
+// siglip_pos_kernel (siglip_kernels.cuh) for the common layout — fp32 raw features, D % 256 == 0, 16-byte aligned rows: the
+// scalar kernel walks every positive with 2-byte / 4-byte loads and one atomic per element (186 us for the 32 K positives of
+// config 2, the longest kernel of that step). Here a lane owns 8 contiguous channels per 256-channel chunk: the row's own
+// operand / raw values stay in registers across its positives, the partner rows come in as 16-byte loads issued together,
+// dV is accumulated in registers and written once, dT goes out as red.global.add.v4.f32. Same arithmetic, same order of
+// the per-pair scalar work.
+template <int NC>
+__global__ void __launch_bounds__(256) siglip_pos_vec_kernel(PosParams p) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  double a_loss = 0.0, a_bias = 0.0, a_t = 0.0;
+  if (row < p.B) {
+    const float inv_tau = p.dyn[2], bias = p.dyn[5], lc = p.dyn[8], yneg = p.dyn[9];
+    const bool use_pw = (p.use_pw & 1) != 0, rule_mask = (p.use_pw & 2) != 0;
+    const int n = p.cnt[row];
+    constexpr int nc = NC;                             // 256-channel chunks
+    float ratio = 1.f;
+    if (p.auto_balance) {
+      const float pc = fmaxf(p.ysum[row], 1.f);
+      ratio = fmaxf(((float)p.Tn - pc) / pc, 1.f);
+    }
+    const __nv_bfloat16* vr = p.V + (size_t)row * p.ldv;
+    const float* vraw = static_cast<const float*>(p.Vraw) + (long long)row * p.ld_vraw;
+    const float vi = p.vinv[row];
+    float vx[NC][8], vh[NC][8], dv[NC][8];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c < nc) {
+        const int d0 = (lane + 32 * c) * 8;
+        const float4 a = *reinterpret_cast<const float4*>(vraw + d0), b = *reinterpret_cast<const float4*>(vraw + d0 + 4);
+        vx[c][0] = a.x * vi; vx[c][1] = a.y * vi; vx[c][2] = a.z * vi; vx[c][3] = a.w * vi;
+        vx[c][4] = b.x * vi; vx[c][5] = b.y * vi; vx[c][6] = b.z * vi; vx[c][7] = b.w * vi;
+        const uint4 h = *reinterpret_cast<const uint4*>(vr + p.hi_off + d0);
+        const __nv_bfloat162* hp2 = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp2[q]); vh[c][2 * q] = f.x; vh[c][2 * q + 1] = f.y; }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dv[c][q] = 0.f;
+    }
+    for (int e = 0; e < n; ++e) {
+      const int j = p.col[(size_t)row * p.cap + e];
+      const float yraw = p.y[(size_t)row * p.cap + e];
+      const float yv = fmaf(yraw, 1.f - 2.f * yneg, yneg);
+      const float pwv = p.w[(size_t)row * p.cap + e];
+      const __nv_bfloat16* tr = p.T + (size_t)j * p.ldt;
+      const float* traw = static_cast<const float*>(p.Traw) + (long long)j * p.ld_traw;
+      const float ti = p.tinv[j];
+      // partner row: raw (fp32) and hi operand (bf16), all loads first
+      float tx[NC][8], th[NC][8];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c < nc) {
+          const int d0 = (lane + 32 * c) * 8;
+          const float4 a = *reinterpret_cast<const float4*>(traw + d0), b = *reinterpret_cast<const float4*>(traw + d0 + 4);
+          const uint4 h = *reinterpret_cast<const uint4*>(tr + p.hi_off + d0);
+          tx[c][0] = a.x * ti; tx[c][1] = a.y * ti; tx[c][2] = a.z * ti; tx[c][3] = a.w * ti;
+          tx[c][4] = b.x * ti; tx[c][5] = b.y * ti; tx[c][6] = b.z * ti; tx[c][7] = b.w * ti;
+          const __nv_bfloat162* hp2 = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hp2[q]); th[c][2 * q] = f.x; th[c][2 * q + 1] = f.y; }
+        }
+      // what the dense pass saw: the dot product of the bf16 operands over all K columns (all panels of bf16x3 operands)
+      float s = 0.f;
+      for (int k = lane * 8; k < p.K; k += 256) {
+        const uint4 a = *reinterpret_cast<const uint4*>(vr + k), b = *reinterpret_cast<const uint4*>(tr + k);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fa = __bfloat1622float2(a2[q]), fb = __bfloat1622float2(b2[q]);
+          s = fmaf(fa.x, fb.x, s);
+          s = fmaf(fa.y, fb.y, s);
+        }
+      }
+      float sx = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c < nc)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sx = fmaf(vx[c][q], tx[c][q], sx);
+      s = warp_sum(s);
+      sx = warp_sum(sx);
+      const float R = fmaf(s, inv_tau, bias);
+      const float L = fminf(fmaxf(R, -lc), lc);
+      const float ex = __expf(-fabsf(L));
+      const float sp = fmaxf(L, 0.f) + log1pf(ex);
+      const float sig = L >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
+      const float inr = fabsf(R) <= lc ? 1.f : 0.f;
+      const float Rx = fmaf(sx, inv_tau, bias);
+      const float Lx = fminf(fmaxf(Rx, -lc), lc);
+      const float exx = __expf(-fabsf(Lx));
+      const float spx = fmaxf(Lx, 0.f) + log1pf(exx);
+      const float sigx = Lx >= 0.f ? 1.f / (1.f + exx) : exx / (1.f + exx);
+      const float inrx = fabsf(Rx) <= lc ? 1.f : 0.f;
+      float w = p.negative_weight;
+      if (rule_mask ? yraw > 0.f : yv > 0.5f)
+        w = p.auto_balance ? ratio : (use_pw ? pwv * p.positive_weight : p.positive_weight);
+      const float g_full = w * (sigx - yv) * inrx * p.c;
+      const float g_dense = p.negative_weight * p.c * (sig - yneg) * inr;
+      if (lane == 0) {
+        a_loss += (double)((w * (spx - Lx * yv) - p.negative_weight * (sp - L * yneg)) * p.c);
+        a_bias += (double)(g_full - g_dense);
+        a_t += (double)(g_full * sx - g_dense * s);
+      }
+      if (p.dV) {
+        const float gs = g_dense * p.gnorm;
+        float gr = __bfloat162float(__float2bfloat16_rn(gs));
+        if (p.hp) gr += __bfloat162float(__float2bfloat16_rn(gs - gr));
+        const float dgf = g_full * inv_tau, dgd = gr / p.gnorm * inv_tau;
+        float* dt = p.dT + (size_t)j * p.lddt;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (c < nc) {
+            const int d0 = (lane + 32 * c) * 8;
+            float o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              dv[c][q] += dgf * tx[c][q] - dgd * th[c][q];
+              o[q] = dgf * vx[c][q] - dgd * vh[c][q];
+            }
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dt + d0), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dt + d0 + 4), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+          }
+      }
+    }
+    if (p.dV && n > 0) {
+      float* dvr = p.dV + (size_t)row * p.lddv;                // this warp owns row i
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c < nc) {
+          const int d0 = (lane + 32 * c) * 8;
+          float4 a = *reinterpret_cast<float4*>(dvr + d0), b = *reinterpret_cast<float4*>(dvr + d0 + 4);
+          a.x += dv[c][0]; a.y += dv[c][1]; a.z += dv[c][2]; a.w += dv[c][3];
+          b.x += dv[c][4]; b.y += dv[c][5]; b.z += dv[c][6]; b.w += dv[c][7];
+          *reinterpret_cast<float4*>(dvr + d0) = a;
+          *reinterpret_cast<float4*>(dvr + d0 + 4) = b;
+        }
+    }
+  }
+  __shared__ double sh[3][8];
+  if (lane == 0) {
+    sh[0][threadIdx.x >> 5] = a_loss;
+    sh[1][threadIdx.x >> 5] = a_bias;
+    sh[2][threadIdx.x >> 5] = a_t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    if (t != 0.0) atomicAdd(p.acc + threadIdx.x, t);
+  }
+}
+
+}  // namespace b2
+
+namespace b2host {
+using namespace b2;
+
 int siglip_pos(const void* V, int ldv, const void* T, int ldt, int K, int Dp, int D, int hi_off, int B, int Tn, int cap,
                const int* col, const float* y, const float* w, const int* cnt, const float* ysum, const float* dyn,
                float positive_weight, float negative_weight, float c, float gnorm, int hp, int use_pw, int auto_balance,
@@ -235,7 +398,20 @@ int siglip_pos(const void* V, int ldv, const void* T, int ldt, int K, int Dp, in
   PosParams p{(const __nv_bfloat16*)V, ldv, (const __nv_bfloat16*)T, ldt, K, Dp, D, hi_off, B, Tn, cap, col, y, w, cnt,
               ysum, dyn, positive_weight, negative_weight, c, gnorm > 0.f ? gnorm : 1.f, hp ? 1 : 0, use_pw, auto_balance, dV, lddv, dT,
               lddt, acc, Vraw, v_dtype, ld_vraw, vinv, Traw, t_dtype, ld_traw, tinv};
-  siglip_pos_kernel<<<(B + 7) / 8, 256, 0, s>>>(p);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = Vraw && Traw && v_dtype == 0 && t_dtype == 0 && D % 256 == 0 && D <= 1024 && K % 256 == 0 && hi_off % 8 == 0 &&
+                   ldv % 8 == 0 && ldt % 8 == 0 && ld_vraw % 4 == 0 && ld_traw % 4 == 0 && al16(V) && al16(T) && al16(Vraw) &&
+                   al16(Traw) && (!dV || (al16(dV) && al16(dT) && lddv % 4 == 0 && lddt % 4 == 0));
+  if (vec) {
+    switch (D / 256) {
+      case 1: siglip_pos_vec_kernel<1><<<(B + 7) / 8, 256, 0, s>>>(p); break;
+      case 2: siglip_pos_vec_kernel<2><<<(B + 7) / 8, 256, 0, s>>>(p); break;
+      case 3: siglip_pos_vec_kernel<3><<<(B + 7) / 8, 256, 0, s>>>(p); break;
+      default: siglip_pos_vec_kernel<4><<<(B + 7) / 8, 256, 0, s>>>(p); break;
+    }
+  } else {
+    siglip_pos_kernel<<<(B + 7) / 8, 256, 0, s>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
