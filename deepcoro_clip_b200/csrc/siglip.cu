@@ -217,10 +217,22 @@ int siglip_scalar_grads(const double* red, const float* dyn, const float* gmul, 
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
+}  // namespace b2host
+namespace b2 {
+__global__ void siglip_compact_vec_kernel(const float* __restrict__ mask, long ldm, const float* __restrict__ pw, long ldw, int B,
+                                          int T, int cap, int* __restrict__ col, float* __restrict__ y, float* __restrict__ w,
+                                          int* __restrict__ cnt, float* __restrict__ ysum, int* __restrict__ overflow);
+}
+namespace b2host {
+using namespace b2;
+
 int siglip_compact(const float* mask, long ldm, const float* pw, long ldw, int B, int T, int cap, int* col, float* y,
                    float* w, int* cnt, float* ysum, int* overflow, cudaStream_t s) {
   if (B <= 0 || T <= 0 || cap <= 0) return B2_EINVAL;
-  siglip_compact_kernel<<<(B + 7) / 8, 256, 0, s>>>(mask, ldm, pw, ldw, B, T, cap, col, y, w, cnt, ysum, overflow);
+  if (mask && T % 4 == 0 && ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0)
+    siglip_compact_vec_kernel<<<(B + 7) / 8, 256, 0, s>>>(mask, ldm, pw, ldw, B, T, cap, col, y, w, cnt, ysum, overflow);
+  else
+    siglip_compact_kernel<<<(B + 7) / 8, 256, 0, s>>>(mask, ldm, pw, ldw, B, T, cap, col, y, w, cnt, ysum, overflow);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
@@ -234,6 +246,69 @@ namespace b2 {
 // operand / raw values stay in registers across its positives, the partner rows come in as 16-byte loads issued together,
 // dV is accumulated in registers and written once, dT goes out as red.global.add.v4.f32. Same arithmetic, same order of
 // the per-pair scalar work.
+// siglip_compact_kernel (siglip_kernels.cuh) with 16-byte loads, four of them in flight per lane: the scalar kernel streams the
+// dense fp32 mask at 2 TB/s (one 4-byte load per lane and ballot step). Same lists in the same (column) order.
+__global__ void __launch_bounds__(256) siglip_compact_vec_kernel(const float* __restrict__ mask, long ldm,
+                                                                  const float* __restrict__ pw, long ldw, int B, int T, int cap,
+                                                                  int* __restrict__ col, float* __restrict__ y,
+                                                                  float* __restrict__ w, int* __restrict__ cnt,
+                                                                  float* __restrict__ ysum, int* __restrict__ overflow) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* mr = mask + (size_t)row * ldm;
+  const float* wr = pw ? pw + (size_t)row * ldw : nullptr;
+  const unsigned lt = (1u << lane) - 1;
+  int n = 0;
+  float ys = 0.f;
+  auto emit = [&](const float4& v4, int cbase) {          // the 128 columns cbase .. cbase + 127, lane owns cbase + 4 lane + q
+    const float v[4] = {fminf(fmaxf(v4.x, 0.f), 1.f), fminf(fmaxf(v4.y, 0.f), 1.f), fminf(fmaxf(v4.z, 0.f), 1.f),
+                        fminf(fmaxf(v4.w, 0.f), 1.f)};
+    ys += (v[0] + v[1]) + (v[2] + v[3]);
+    const bool any = v[0] > 0.f || v[1] > 0.f || v[2] > 0.f || v[3] > 0.f;
+    if (__ballot_sync(0xffffffffu, any) == 0u) return;
+    int before = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned b = __ballot_sync(0xffffffffu, v[q] > 0.f);
+      before += __popc(b & lt);
+      total += __popc(b);
+    }
+    int slot = n + before;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (v[q] > 0.f) {
+        const int c = cbase + 4 * lane + q;
+        if (slot < cap) {
+          col[(size_t)row * cap + slot] = c;
+          y[(size_t)row * cap + slot] = v[q];
+          w[(size_t)row * cap + slot] = wr ? wr[c] : 1.f;
+        }
+        ++slot;
+      }
+    n += total;
+  };
+  int c0 = 0;
+  for (; c0 + 512 <= T; c0 += 512) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(mr + c0 + u * 128 + lane * 4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(v[u], c0 + u * 128);
+  }
+  for (; c0 < T; c0 += 128) {                             // tail: T % 4 == 0 is guaranteed by the caller, not T % 128
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 + lane * 4 < T) v = *reinterpret_cast<const float4*>(mr + c0 + lane * 4);
+    emit(v, c0);
+  }
+  ys = warp_sum(ys);
+  if (lane == 0) {
+    cnt[row] = n < cap ? n : cap;
+    ysum[row] = ys;
+    if (n > cap) atomicExch(overflow, 1);
+  }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(256) siglip_pos_vec_kernel(PosParams p) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

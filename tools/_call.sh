@@ -1,8 +1,6 @@
 mkdir -p gpurun_out
-T=r02u
-timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/${T}_pytest_gpu.log 2>&1
-echo "pytest rc=$? : $(tail -1 gpurun_out/${T}_pytest_gpu.log)"; grep -E "^FAILED|^ERROR" gpurun_out/${T}_pytest_gpu.log | head -20
-timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1
-( time timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err ) 2> gpurun_out/${T}_bench.time
-echo "bench rc=$? $(tail -3 gpurun_out/${T}_bench.time | head -1)"
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err; echo "ref rc=$? $(cut -c1-200 gpurun_out/${T}_bench_ref.json)"
+T=r02v
+timeout 600 python -m pytest tests/test_gpu_siglip.py tests/test_gpu_fullsize.py -m gpu -q -p no:cacheprovider > gpurun_out/${T}_pytest.log 2>&1
+echo "pytest rc=$? : $(tail -1 gpurun_out/${T}_pytest.log)"; grep -E "^FAILED|^ERROR" gpurun_out/${T}_pytest.log | head
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_siglip_launches.csv python tools/gpu_siglip_step.py 4 > gpurun_out/${T}_ncu1.log 2>&1; echo "siglip list rc=$?"
+grep -E "siglip_compact|siglip_pos" gpurun_out/${T}_siglip_launches.csv | tail -2 | cut -c1-70,200-400
