@@ -1,6 +1,11 @@
 mkdir -p gpurun_out
-T=r02v
-timeout 600 python -m pytest tests/test_gpu_siglip.py tests/test_gpu_fullsize.py -m gpu -q -p no:cacheprovider > gpurun_out/${T}_pytest.log 2>&1
-echo "pytest rc=$? : $(tail -1 gpurun_out/${T}_pytest.log)"; grep -E "^FAILED|^ERROR" gpurun_out/${T}_pytest.log | head
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_siglip_launches.csv python tools/gpu_siglip_step.py 4 > gpurun_out/${T}_ncu1.log 2>&1; echo "siglip list rc=$?"
-grep -E "siglip_compact|siglip_pos" gpurun_out/${T}_siglip_launches.csv | tail -2 | cut -c1-70,200-400
+T=r02w
+NG=$(nvidia-smi -L | wc -l)
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
+timeout 300 $TR --master-port 29541 bench.py --gpus $NG --no-cpu-baseline > gpurun_out/${T}_bench_n${NG}.json 2> gpurun_out/${T}_bench_n${NG}.err
+echo "bench n$NG rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n${NG}.json)"
+timeout 300 $TR --master-port 29542 tools/gpu_check_dist.py > gpurun_out/${T}_dist_check_n${NG}.log 2>&1
+echo "dist check n$NG rc=$? : $(tail -1 gpurun_out/${T}_dist_check_n${NG}.log | cut -c1-300)"
+B200CLIP_SYMM=0 timeout 300 $TR --master-port 29543 bench.py --gpus $NG --legs none --no-cpu-baseline > gpurun_out/${T}_bench_n${NG}_nccl.json 2> gpurun_out/${T}_bench_n${NG}_nccl.err
+echo "bench n$NG nccl rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n${NG}_nccl.json)"
+timeout 120 $TR --master-port 29544 tools/gpu_dist_phases.py > gpurun_out/${T}_phases_n${NG}.log 2>&1; echo "phases: $(tail -1 gpurun_out/${T}_phases_n${NG}.log | cut -c1-400)"
