@@ -97,7 +97,7 @@ def call(name: str, *args) -> None:
         finally:
             torch.cuda.nvtx.range_pop()
     else:
-        rc = fn(*[a.data_ptr() if type(a) is _Tensor or isinstance(a, _Tensor) else a for a in args])
+        rc = fn(*[a.data_ptr() if isinstance(a, _Tensor) else a for a in args])
     if name not in _NO_LAUNCH:
         LAUNCHES += 1
     if rc != 0:

@@ -456,6 +456,20 @@ int b200clip_xfblock_wgrad(const float* a, int64_t lda, const float* b, int64_t 
   return xfblock_wgrad(a, lda, b, ldb, dw, db, J, I, R, a2, xhat, dgamma, dbeta, D2, S(stream));
 }
 
+int b200clip_symm_barrier(void* const* flags_host, int world, int rank, int channel, void* stream) {
+  return symm_barrier(flags_host, world, rank, channel, S(stream));
+}
+
+int b200clip_clip_dlogtemp_peers(const void* const* scal_host, int world, const float* dyn, const float* gmul,
+                                 const double* unif, int n, float* out, void* stream) {
+  return clip_dlogtemp_peers(scal_host, world, dyn, gmul, unif, n, out, S(stream));
+}
+
+int b200clip_l2norm_fwd_mc(const void* x, int dtype, int64_t ldx, int rows, int dim, void* mc_operand, int64_t row_offset,
+                           int ld_out, int Kp, float* inv_norm, int normalize, void* stream) {
+  return l2norm_fwd_mc(x, dtype, (long)ldx, rows, dim, mc_operand, row_offset, ld_out, Kp, inv_norm, normalize, S(stream));
+}
+
 int b200clip_querypool(int backward, const float* x, int64_t x_sb, int64_t x_sn, const float* pos, const float* ln_w,
                        const float* ln_b, const float* query, const uint8_t* mask, int64_t mask_sb, int B, int N, int D,
                        float eps, float* out, const float* dout, float* dx, float* dpos, float* dln_w, float* dln_b,

@@ -213,6 +213,14 @@ int xfblock(int backward, const void* const* ptrs, int B, int N, int D, int H, i
 int xfblock_wgrad(const float* a, long long lda, const float* bm, long long ldb, float* dw, float* db, int J, int I, int R,
                   const float* a2, const float* xh, float* dg, float* dbeta, int D2, cudaStream_t s);
 
+// scalars.cu: symmetric-memory plumbing of the multi-GPU CLIP path
+int symm_barrier(void* const* flags_host, int world, int rank, int channel, cudaStream_t s);
+int clip_dlogtemp_peers(const void* const* scal_host, int world, const float* dyn, const float* gmul, const double* unif, int n,
+                        float* out, cudaStream_t s);
+
+int l2norm_fwd_mc(const void* x, int dtype, long ldx, int rows, int dim, void* mc_out, long long row_offset, int ldo, int Kp,
+                  float* inv_norm, int normalize, cudaStream_t s);
+
 // querypool.cu
 int querypool(int backward, const float* x, long long sb, long long sn, const float* pos, const float* lnw,
               const float* lnb, const float* q, const unsigned char* mask, long long mb, int B, int N, int D, float eps,

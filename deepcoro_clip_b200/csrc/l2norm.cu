@@ -70,6 +70,26 @@ int l2norm_fwd_multi(const void* x, int dtype, long ldx, int rows, int dim, void
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
+int l2norm_fwd_mc(const void* x, int dtype, long ldx, int rows, int dim, void* mc_out, long long row_offset, int ldo, int Kp,
+                  float* inv_norm, int normalize, cudaStream_t s) {
+  if (rows <= 0 || dim <= 0 || Kp < dim || Kp % 64 || Kp > 1024 || dim % 8 || !mc_out || (ldo & 7) || row_offset < 0 ||
+      (reinterpret_cast<uintptr_t>(mc_out) & 15))
+    return B2_EINVAL;
+  const int esz = dtype == 0 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || ((ldx * esz) & 15)) return B2_EINVAL;
+  L2nDests d{};
+  d.n = 1;
+  d.ptr[0] = reinterpret_cast<__nv_bfloat16*>(mc_out);
+  const int blocks = (rows + 7) / 8;
+  switch (dtype) {
+    case 0: l2norm_fwd_multi_kernel<float, true><<<blocks, 256, 0, s>>>((const float*)x, ldx, rows, dim, d, (long)row_offset, ldo, Kp, inv_norm, normalize); break;
+    case 1: l2norm_fwd_multi_kernel<__nv_bfloat16, true><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, rows, dim, d, (long)row_offset, ldo, Kp, inv_norm, normalize); break;
+    case 2: l2norm_fwd_multi_kernel<__half, true><<<blocks, 256, 0, s>>>((const __half*)x, ldx, rows, dim, d, (long)row_offset, ldo, Kp, inv_norm, normalize); break;
+    default: return B2_EINVAL;
+  }
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
 template <typename T>
 static int l2norm_bwd_t(const float* dxh, int ldg, const T* x, long ldx, const float* inv_norm, const void* ox,
                         int odtype, long ldox, const float* oinv, const __nv_bfloat16* ohi, int ldohi, const float2* dc,

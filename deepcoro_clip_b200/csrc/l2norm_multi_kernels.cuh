@@ -38,7 +38,10 @@ __device__ __forceinline__ void l2n_load8<__half>(const __half* p, float (&v)[8]
   for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 
-template <typename T>
+// kMc: dst.ptr[0] is the MULTICAST address of the symmetric operand buffer (NVSwitch replicates one multimem.st to every
+// rank of the group, this rank included): each row leaves the GPU once instead of once per peer — 4 MB instead of 29 MB per
+// operand and rank at 8 ranks, which was ~50 us of NVLink time per operand in front of the forward.
+template <typename T, bool kMc = false>
 __global__ void __launch_bounds__(256)
 l2norm_fwd_multi_kernel(const T* __restrict__ x, long ldx, int rows, int dim, L2nDests dst, long row_offset, int ldo,
                         int Kp, float* __restrict__ inv_norm, int normalize) {
@@ -73,7 +76,12 @@ l2norm_fwd_multi_kernel(const T* __restrict__ x, long ldx, int rows, int dim, L2
 #pragma unroll
       for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[i][2 * e] * inv, v[i][2 * e + 1] * inv);
       const size_t off = (size_t)(row_offset + warp) * ldo + c;
-      for (int d = 0; d < dst.n; ++d) *reinterpret_cast<uint4*>(dst.ptr[d] + off) = pk;
+      if (kMc) {
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst.ptr[0] + off), "f"(__uint_as_float(pk.x)),
+                     "f"(__uint_as_float(pk.y)), "f"(__uint_as_float(pk.z)), "f"(__uint_as_float(pk.w)) : "memory");
+      } else {
+        for (int d = 0; d < dst.n; ++d) *reinterpret_cast<uint4*>(dst.ptr[d] + off) = pk;
+      }
     }
   }
 }

@@ -98,10 +98,16 @@ class _ClipLossFn(torch.autograd.Function):
             vall, tall = plan.ops[slot, 0], plan.ops[slot, 1]
             tinv = torch.empty(B, dtype=torch.float32, device=dev)
             vinv = torch.empty(B, dtype=torch.float32, device=dev)
-            ops.call("l2norm_fwd_multi", traw, ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), B, D,
-                     plan.op_ptrs[slot][1], W, ops.i64(lo), K, Kp, tinv, 1, st)
-            ops.call("l2norm_fwd_multi", vraw, ops.DTYPE_CODE[vraw.dtype], ops.i64(vraw.stride(0)), B, D,
-                     plan.op_ptrs[slot][0], W, ops.i64(lo), K, Kp, vinv, 1, st)
+            if plan.mc_op is not None:        # one multicast store per row (NVSwitch replicates it to every rank)
+                ops.call("l2norm_fwd_mc", traw, ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), B, D,
+                         plan.mc_op[slot][1], ops.i64(lo), K, Kp, tinv, 1, st)
+                ops.call("l2norm_fwd_mc", vraw, ops.DTYPE_CODE[vraw.dtype], ops.i64(vraw.stride(0)), B, D,
+                         plan.mc_op[slot][0], ops.i64(lo), K, Kp, vinv, 1, st)
+            else:
+                ops.call("l2norm_fwd_multi", traw, ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), B, D,
+                         plan.op_ptrs[slot][1], W, ops.i64(lo), K, Kp, tinv, 1, st)
+                ops.call("l2norm_fwd_multi", vraw, ops.DTYPE_CODE[vraw.dtype], ops.i64(vraw.stride(0)), B, D,
+                         plan.op_ptrs[slot][0], W, ops.i64(lo), K, Kp, vinv, 1, st)
             plan.barrier_ops()            # every rank's rows have landed in every buffer
             vop, top = vall[lo:lo + B], tall[lo:lo + B]
             t_work = v_work = None
@@ -121,8 +127,8 @@ class _ClipLossFn(torch.autograd.Function):
         # dots (N)] zeroed (other ranks' slices stay 0) — this rank's symmetric block, or a local arena that is all-reduced —
         # then scales (2N) | tickets of the stable sweeps (2B int32)
         if plan is not None:
-            sums = plan.stats[slot]
-            sums.zero_()
+            plan.stats[slot].zero_()          # statistics + the backward's fp64 scalar sums of this slot
+            sums = plan.stats[slot][:7 * N]
             ws = torch.zeros(2 * N + 2 * B + 2, dtype=torch.float32, device=dev)
         else:
             ws_all = torch.zeros(9 * N + 2 * B + 2, dtype=torch.float32, device=dev)
@@ -194,8 +200,16 @@ class _ClipLossFn(torch.autograd.Function):
         dV = dT = dLT = None
         # arena: dVhat [B, D] | dThat [B, D] | diag corrections 2 x [B, 2] | fp64 scalars (8 floats)
         nbd = B * D
+        plan, slot, token = ctx.symm
         ws = torch.zeros(2 * nbd + 4 * B + 8, dtype=torch.float32, device=dev)
-        scal = ws[2 * nbd + 4 * B:].view(torch.float64)
+        # fp64 scalar sums: in the rank's symmetric block when the exchange runs over peer memory (zeroed by the forward),
+        # so that d log_temp needs no all-reduce: every rank reads the W partials after one more barrier
+        peers_lt = plan is not None and W > 1 and need_lt
+        scal = plan.stats[slot][7 * N:7 * N + 8].view(torch.float64) if peers_lt else ws[2 * nbd + 4 * B:].view(torch.float64)
+        if peers_lt:
+            if getattr(ctx, "scal_used", False):
+                scal.zero_()                   # a second backward through the same graph (retain_graph)
+            ctx.scal_used = True
         ydiag = (1.0 - eps) / N
         lt_work = None
         if need_v or need_lt:
@@ -203,7 +217,7 @@ class _ClipLossFn(torch.autograd.Function):
             dcv = ws[2 * nbd:2 * nbd + 2 * B]
             ops.logits_bwd(mode, vop, tall, B, N, K, Kp, D, dyn, rowscale_all[lo:hi], colscale_all, dVh, scal,
                            ydiag=ydiag, diag_off=lo, diag_corr=dcv, gnorm=2.0 * N, hp=(K != Kp))
-            if need_lt and W > 1:
+            if need_lt and W > 1 and not peers_lt:
                 # sum_ij G_ij L_ij is complete after the video-side pass: its all-reduce overlaps the text-side pass
                 lt_work = dist.all_reduce(scal[0:1], group=group, async_op=True)
             if need_v:
@@ -228,9 +242,12 @@ class _ClipLossFn(torch.autograd.Function):
             # d loss / d log_temp = -sum_ij G_ij L_ij  (zero while the tau clamp is active); the kernel's sum already
             # contains the diagonal target, only the uniform label-smoothing part is added
             dlt = torch.empty(1, dtype=torch.float32, device=dev)
-            ops.call("clip_dlogtemp", scal, dyn, gmul, unif_tgt, N, dlt, ops.stream_ptr(dev))
+            if peers_lt:
+                plan.barrier_scal()            # every rank's video-side pass (enqueued before its text-side pass) has finished
+                ops.call("clip_dlogtemp_peers", plan.scal_ptrs[slot], W, dyn, gmul, unif_tgt, N, dlt, ops.stream_ptr(dev))
+            else:
+                ops.call("clip_dlogtemp", scal, dyn, gmul, unif_tgt, N, dlt, ops.stream_ptr(dev))
             dLT = (dlt if lt_dtype == torch.float32 else dlt.to(lt_dtype)).reshape(lt_shape)
-        plan, slot, token = ctx.symm
         if plan is not None:
             plan.release(slot, token)      # the operand slot may be overwritten by the step after next
         return dV, dT, dLT, None, None, None, None, None, None, None

@@ -29,6 +29,8 @@ from typing import Dict, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from ._lib import call as _call, stream_ptr as _stream_ptr
+
 _PLANS: Dict[Tuple, "SymmPlan"] = {}
 _FAILED = set()
 
@@ -47,15 +49,22 @@ class SymmPlan:
         pg = group if group is not None else dist.group.WORLD
         self.W, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
         self.N, self.ld = N, ld
+        self.dev_index = dev.index
         # [slot][video | text][N, ld] bf16 operands; [slot][NVEC * N] fp32 statistics
         self.ops = symm_mem.empty((2, 2, N, ld), dtype=torch.bfloat16, device=dev)
-        self.stats = symm_mem.empty((2, self.NVEC * N), dtype=torch.float32, device=dev)
+        # per slot: NVEC * N fp32 statistics + 16 floats (8 fp64: the backward's scalar sums, sum G L first)
+        self.stats = symm_mem.empty((2, self.NVEC * N + 16), dtype=torch.float32, device=dev)
+        self.flags = symm_mem.empty((64,), dtype=torch.int32, device=dev)      # barrier epochs (b200clip_symm_barrier)
+        self.flags.zero_()
         self.h_ops = symm_mem.rendezvous(self.ops, pg)
         self.h_stats = symm_mem.rendezvous(self.stats, pg)
+        self.h_flags = symm_mem.rendezvous(self.flags, pg)
+        self.h_flags.barrier(channel=0)       # every rank's flags are zero before the first epoch is written
+        self.own_barrier = os.environ.get("B200CLIP_SYMM_BARRIER", "own") != "torch"
         self.step = 0
         self.live = [None, None]              # weak references to the autograd contexts that still need a slot's operands
         op_bytes = N * ld * 2
-        st_bytes = self.NVEC * N * 4
+        st_bytes = (self.NVEC * N + 16) * 4
 
         def arr(ptrs):
             return (ctypes.c_void_p * len(ptrs))(*ptrs)
@@ -63,6 +72,11 @@ class SymmPlan:
         self.op_ptrs = [[arr([int(p) + (2 * s + side) * op_bytes for p in self.h_ops.buffer_ptrs]) for side in (0, 1)]
                         for s in (0, 1)]
         self.stat_ptrs = [arr([int(p) + s * st_bytes for p in self.h_stats.buffer_ptrs]) for s in (0, 1)]
+        # multicast mapping of the operand buffer (NVLS), when the platform provides one: rows leave the GPU once
+        mc = int(getattr(self.h_ops, "multicast_ptr", 0) or 0) if os.environ.get("B200CLIP_SYMM_MC", "1") != "0" else 0
+        self.mc_op = [[mc + (2 * s + side) * op_bytes for side in (0, 1)] for s in (0, 1)] if mc else None
+        self.scal_ptrs = [arr([int(p) + s * st_bytes + self.NVEC * N * 4 for p in self.h_stats.buffer_ptrs]) for s in (0, 1)]
+        self.flag_ptrs = arr([int(p) for p in self.h_flags.buffer_ptrs])
 
     def acquire(self, owner) -> Optional[int]:
         """Next slot, or None when the slot is still referenced by a live autograd graph (caller uses the NCCL path)."""
@@ -79,11 +93,20 @@ class SymmPlan:
         if ref is not None and ref() is owner:
             self.live[slot] = None
 
+    def _barrier(self, channel: int, handle) -> None:
+        if self.own_barrier:
+            _call("symm_barrier", self.flag_ptrs, self.W, self.rank, channel, _stream_ptr(self.dev_index))
+        else:
+            handle.barrier(channel=0)
+
     def barrier_ops(self) -> None:
-        self.h_ops.barrier(channel=0)
+        self._barrier(0, self.h_ops)
 
     def barrier_stats(self) -> None:
-        self.h_stats.barrier(channel=0)
+        self._barrier(1, self.h_stats)
+
+    def barrier_scal(self) -> None:
+        self._barrier(2, self.h_stats)
 
 
 def get_plan(group, N: int, ld: int, dev: torch.device) -> Optional[SymmPlan]:

@@ -62,6 +62,12 @@ int b200clip_l2norm_fwd_multi(const void* x, int dtype, int64_t ldx, int rows, i
                               int n_operands, int64_t row_offset, int ld_out, int Kp, float* inv_norm, int normalize,
                               void* stream);
 
+/* l2norm_fwd_multi through the MULTICAST mapping of the symmetric operand buffer (NVLink SHARP / NVLS: one multimem.st per
+ * 16 bytes, replicated by the switch into the buffer of every rank of the group, the caller's included): mc_operand = the
+ * multicast address of the [N, ld_out] operand buffer. Same constraints and the same cross-rank barrier afterwards. */
+int b200clip_l2norm_fwd_mc(const void* x, int dtype, int64_t ldx, int rows, int dim, void* mc_operand, int64_t row_offset,
+                           int ld_out, int Kp, float* inv_norm, int normalize, void* stream);
+
 /* K4  normalise backward (autograd of F.normalize) fused with the rank-sparse gradient corrections:
  *   g  = gmul * ( gscale * dxhat[r] + omul * (res_r * yh_r + gb_r * (yh_r - yhi_r)) + (ucoef * omul) * usum )
  *   dx = (g - (g . xhat) xhat) * inv_norm,   xhat = x * inv_norm (recomputed in fp32 from the caller's input)
@@ -220,6 +226,16 @@ int b200clip_clip_finalize_peers(const void* const* peer_sums_host, int world, i
                                  double* acc_out, void* stream);
 int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* gmul, const double* unif, int n,
                            float* out, void* stream);
+/* Multi-GPU plumbing over symmetric memory (deepcoro_clip_b200/symm.py; one process per GPU, <= 8 ranks of one NVLink domain):
+ *   symm_barrier        : cross-rank barrier on `channel` (0..3). flags_host: HOST array of `world` device pointers, entry r =
+ *                         rank r's flag block (48 x int32, zeroed once at set-up: [4 channels][8 sources] arrival epochs + 4
+ *                         local epoch counters) as mapped into THIS process. Epochs are counted on the device, so the call is
+ *                         CUDA-graph safe; every rank must enqueue the same sequence of barriers per channel.
+ *   clip_dlogtemp_peers : clip_dlogtemp with scal0 = sum over ranks of scal_host[r][0] (each rank's fp64 partial of sum G L in
+ *                         its symmetric block; call after a barrier that follows the video-side backward of every rank). */
+int b200clip_symm_barrier(void* const* flags_host, int world, int rank, int channel, void* stream);
+int b200clip_clip_dlogtemp_peers(const void* const* scal_host, int world, const float* dyn, const float* gmul,
+                                 const double* unif, int n, float* out, void* stream);
 /* Alignment diagnostics of a batch from the same forward statistics, instead of the dense [B, B] similarity +
  * log_softmax the runner recomputes after every step (runners/video_constrative_learning_runner.py:1323-1335):
  *   sums = [colsum (n) | rowsum (n) | S_ii (n)] from logits_lse_fwd of the LOCAL batch, dyn from dyn_prep;

@@ -1,11 +1,10 @@
 mkdir -p gpurun_out
-T=r02w
+T=r02ab
 NG=$(nvidia-smi -L | wc -l)
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
-timeout 300 $TR --master-port 29541 bench.py --gpus $NG --no-cpu-baseline > gpurun_out/${T}_bench_n${NG}.json 2> gpurun_out/${T}_bench_n${NG}.err
-echo "bench n$NG rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n${NG}.json)"
 timeout 300 $TR --master-port 29542 tools/gpu_check_dist.py > gpurun_out/${T}_dist_check_n${NG}.log 2>&1
-echo "dist check n$NG rc=$? : $(tail -1 gpurun_out/${T}_dist_check_n${NG}.log | cut -c1-300)"
-B200CLIP_SYMM=0 timeout 300 $TR --master-port 29543 bench.py --gpus $NG --legs none --no-cpu-baseline > gpurun_out/${T}_bench_n${NG}_nccl.json 2> gpurun_out/${T}_bench_n${NG}_nccl.err
-echo "bench n$NG nccl rc=$? : $(cut -c1-300 gpurun_out/${T}_bench_n${NG}_nccl.json)"
-timeout 120 $TR --master-port 29544 tools/gpu_dist_phases.py > gpurun_out/${T}_phases_n${NG}.log 2>&1; echo "phases: $(tail -1 gpurun_out/${T}_phases_n${NG}.log | cut -c1-400)"
+echo "dist check n$NG rc=$? : $(tail -1 gpurun_out/${T}_dist_check_n${NG}.log | cut -c1-300)"; grep -i "mismatch\|error\|timeout" gpurun_out/${T}_dist_check_n${NG}.log | head -5
+timeout 300 $TR --master-port 29541 bench.py --gpus $NG --legs none --no-cpu-baseline > gpurun_out/${T}_bench_n${NG}.json 2> gpurun_out/${T}_bench_n${NG}.err
+echo "bench n$NG rc=$? : $(cut -c1-260 gpurun_out/${T}_bench_n${NG}.json)"
+timeout 300 $TR --master-port 29551 tools/gpu_host_profile_dist.py 2>&1 | grep "host enqueue\|symmetric plans"
+B200CLIP_SYMM_MC=0 timeout 300 $TR --master-port 29553 tools/gpu_host_profile_dist.py 2>&1 | grep "host enqueue\|symmetric plans"

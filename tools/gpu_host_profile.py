@@ -22,3 +22,24 @@ for name, fn in (("aggregator", fa), ("attention pool", fp)):
     pr.disable(); torch.cuda.synchronize()
     s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18)
     print("=====", name, "(200 iterations)"); print("\n".join(s.getvalue().splitlines()[:40]))
+# CLIP loss step at the per-rank size of the 8-GPU point (4096 rows): host time of the eager plugin path
+import math
+from deepcoro_clip_b200.loss import CLIPLoss
+v = torch.randn(4096, 512, device=dev, requires_grad=True); t = torch.randn(4096, 512, device=dev, requires_grad=True)
+lt = torch.tensor([math.log(0.0588)], device=dev, requires_grad=True)
+mod = CLIPLoss(precision="bf16")
+def fc():
+    v.grad = None; t.grad = None; lt.grad = None
+    mod(video_features=v, text_features=t, log_temp=lt).backward()
+for _ in range(20): fc()
+torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+for _ in range(200): fc()
+t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"CLIP step 4096 x 4096: host enqueue {(t1 - t0) / 200 * 1e6:.0f} us, wall {(t2 - t0) / 200 * 1e6:.0f} us")
+pr = cProfile.Profile(); pr.enable()
+for _ in range(200): fc()
+pr.disable(); torch.cuda.synchronize()
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22)
+print("===== CLIP step (200 iterations)"); print("\n".join(s.getvalue().splitlines()[:44]))
