@@ -648,7 +648,6 @@ def siglip_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
     ms = timed(ctx, step, steps, warmup, flush)
     loss_val = box["loss"].item()
     dv_own, dt_own = v.grad.double(), t.grad.double()
-
     def parity_fn():
         # float64 autograd restatement of utils/loss/contrastive.py:259-303 on the global problem
         v2 = v_all.double().requires_grad_(True); t2 = t_all.double().requires_grad_(True)
@@ -779,30 +778,9 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
     res["aggregator_fwd_bwd"] = {"ms": ms, "note": "EnhancedVideoAggregator (depth 2, train mode): 2 x (1 + 5) cluster-kernel launches "
                                                    "+ the query-pool tail; latency-bound, [8, 4, 512] fp32"}
     ms = t_ms(whole, steps)
-    # the same step replayed from a CUDA graph (kernels only: what is left when the host work of the eager modules is removed)
-    graphed_ms = None
-    try:
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                whole()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        q.grad = None; k.grad = None; x.grad = None; xa.grad = None
-        for m_ in (pool, agg):
-            m_.zero_grad(set_to_none=True)
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            whole()
-        graphed_ms = t_ms(gr.replay, steps)
-        del gr
-    except Exception as e:
-        graphed_ms = f"{type(e).__name__}: {e}"
     total_bytes = 2 * b_rope + 4 * bx
     out = {"metric": "study-mode token path fwd+bwd (config 3)", "value": S * ctx.world / (ms * 1e-3), "unit": "studies/s",
-           "ms_per_step": ms, "graphed_ms_per_step": graphed_ms, "execution": "eager module calls (value); graphed_ms_per_step = "
-           "the same step replayed from one CUDA graph", "studies_per_gpu": S, "views": V, "tokens_per_view": L, "n_gpus": ctx.world,
+           "ms_per_step": ms, "execution": "eager module calls", "studies_per_gpu": S, "views": V, "tokens_per_view": L, "n_gpus": ctx.world,
            "parallelism": "replicas only (no collective on this path)", "kernels": res,
            "roofline": {"bound": "hbm", "achieved": total_bytes / ms / 1e6, "peak": hbm, "unit": "GB/s",
                         "frac": total_bytes / ms / 1e6 / hbm, "peak_source": src,

@@ -510,13 +510,14 @@ class _SigLIPFn(torch.autograd.Function):
                  traw, ops.DTYPE_CODE[traw.dtype], ops.i64(traw.stride(0)), tinv, st)
         # local sums -> global (every rank returns the full loss, reference DDP semantics); scalar tails on the device
         # loss, dbias, sum G*s | checksum of the text operand and its square (replication check, see the class docstring)
-        red = torch.empty(5, dtype=torch.float64, device=dev)
+        red = torch.empty(6, dtype=torch.float64, device=dev)      # [5] carries the overflow flag through the same all-reduce
         ops.call("siglip_combine", acc, float(wn * c), tinv, T, red, st)
         if W > 1:
+            red[5:6].copy_(overflow)
             dist.all_reduce(red, group=cfg["group"])
             if dTh is not None:
                 dist.all_reduce(dTh, group=cfg["group"])      # text is replicated: every rank gets the full text grad
-            dist.all_reduce(overflow, group=cfg["group"])
+            overflow.copy_(red[5:6])
         elif own is not None:
             dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=cfg["group"])
         loss = torch.empty(1, dtype=torch.float32, device=dev)
