@@ -46,6 +46,9 @@ def env():
     (3, 500, 512, 8, 256, torch.bfloat16, True),        # output Linear
     (9, 200, 512, 4, 512, torch.float16, False),
     (2, 3136, 512, 8, 512, torch.bfloat16, False),      # one C3 view pair
+    (7, 130, 128, 4, 128, torch.bfloat16, True),        # narrowest supported width
+    (4, 333, 384, 8, 384, torch.float16, True),         # head_dim 48
+    (1, 65, 512, 2, 64, torch.bfloat16, False),         # one batch row, head_dim 256, narrow output Linear
 ])
 def test_fused_attention_pool_matches_float64_reference_module(env, B, N, D, H, Do, dtype, masked):
     from deepcoro_clip_b200 import AttentionPool, _lib

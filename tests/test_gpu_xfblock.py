@@ -26,7 +26,8 @@ def env():
 
 
 @pytest.mark.parametrize("B,N,D,H,masked", [(3, 4, 512, 4, False), (5, 4, 512, 4, True), (4, 7, 512, 8, True),
-                                            (2, 15, 512, 4, True), (3, 3, 256, 4, False), (2, 11, 384, 8, False)])
+                                            (2, 15, 512, 4, True), (3, 3, 256, 4, False), (2, 11, 384, 8, False),
+                                            (5, 1, 128, 8, False), (2, 16, 512, 2, True), (9, 2, 512, 1, False)])
 def test_fused_block_matches_float64_pytorch_block(env, B, N, D, H, masked):
     from deepcoro_clip_b200 import _lib
     from deepcoro_clip_b200.video_aggregator import TransformerBlock
