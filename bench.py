@@ -742,22 +742,35 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
             dxs = [torch.empty_like(xs[0]) for _ in range(3)]
             st = stream_ptr(dev)
             it = {"i": 0}
+            # operand images exactly as the module prepares them: pool_prep (query side) and pool_tail_bwd (per-row gradient side)
+            R = S * V
+            prm = {k_: torch.randn(n_, device=dev) * 0.05 for k_, n_ in (("query", D), ("w_in", 3 * D * D), ("b_in", 3 * D),
+                                                                       ("w_o", D * D), ("gamma", D))}
+            q0 = torch.empty(D, device=dev); qimg = torch.empty(D * 8, device=dev)
+            call("pool_prep", prm["query"], prm["w_in"], prm["b_in"], D, 8, q0, qt, qimg, 0, st)
+            yh = torch.randn(R, D, device=dev); rs = torch.ones(R, device=dev); sa1 = torch.ones(R, 8, device=dev)
+            dy_ = torch.randn(R, D, device=dev).bfloat16()
+            tmp = [torch.empty(R * D, device=dev) for _ in range(3)]
+            cdot = torch.empty(R, 8, device=dev); wimg = torch.empty(R * D * 16, device=dev)
+            call("pool_tail_bwd", dy_, 1, yh, rs, xb_, sa1, prm["w_in"].data_ptr() + 8 * D * D, prm["b_in"].data_ptr() + 8 * D,
+                 prm["w_o"], prm["gamma"], None, 0, qt, R, 8, D, tmp[0], tmp[1], tmp[2], dxb, None, cdot, wimg, 0, st)
 
             def k_fwd():
                 it["i"] += 1
-                call("attnpool_tc_fwd", xs[it["i"] % 3], 1, None, i64(0), qt, None, S * V, L, D, 8, Sp, pm, pl, pa, 0.0, 0, None, st)
+                call("attnpool_tc_fwd", xs[it["i"] % 3], 1, None, i64(0), None, qimg, R, L, D, 8, Sp, pm, pl, pa, 0.0, 0, None, st)
 
             def k_bwd():
                 it["i"] += 1
-                call("attnpool_tc_bwd", xs[it["i"] % 3], 1, None, i64(0), qt, dxb, xb_, None, None, mm, ll, S * V, L, D, 8, Sp,
+                call("attnpool_tc_bwd", xs[it["i"] % 3], 1, None, i64(0), None, None, None, wimg, cdot, mm, ll, R, L, D, 8, Sp,
                      dxs[it["i"] % 3], None, None, 0.0, 0, None, pdq, st)
             ms = t_ms(k_fwd, 20)
             res["pool_fwd_tc_kernel"] = {"ms": ms, "algorithmic_bytes": bx, "GBps": bx / ms / 1e6, "frac_hbm": bx / ms / 1e6 / hbm,
-                                         "note": "csrc/attnpool_tc.cu, operand image built in the kernel (module calls use pool_prep's)"}
+                                         "note": "csrc/attnpool_tc.cu as the module launches it (operand image from pool_prep)"}
             ms = t_ms(k_bwd, 20)
             res["pool_bwd_tc_kernel"] = {"ms": ms, "algorithmic_bytes": 2 * bx, "GBps": 2 * bx / ms / 1e6,
                                          "frac_hbm": 2 * bx / ms / 1e6 / hbm,
-                                         "note": "reads x once, writes dx and the query-gradient partials in the same pass"}
+                                         "note": "as the module launches it (operand images + c_h from pool_tail_bwd): reads x once, "
+                                                 "writes dx and the query-gradient partials in the same pass"}
             del xs, dxs, pa, pdq
     except Exception as e:      # the module-level numbers above stand on their own
         res["pool_tc_kernels"] = {"error": f"{type(e).__name__}: {e}"}
