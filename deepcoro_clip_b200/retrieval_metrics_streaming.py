@@ -111,10 +111,23 @@ def _sweep(vop, top, gt, k: int, use_ddp: bool, group=None, _shard=None):
     if gt is not None:
         gt64 = gt.to(device=dev, dtype=torch.int64).contiguous()
         # ground-truth similarity with the tensor core's own rounding (ties with duplicate texts stay exact ties)
-        sgt = torch.empty(N, dtype=torch.float32, device=dev)
-        tg = torch.empty((N, K), dtype=torch.bfloat16, device=dev)
-        call("gather_rows_bf16", top, top.stride(0), gt64, N, M, K, tg, K, st)
-        call("rowdot_tc", vop, vop.stride(0), tg, K, N, K, sgt, st)
+        if W > 1 and N >= 1024 * W:
+            # every rank holds all video rows and the whole text database: the ground-truth dots are sharded by VIDEO rows
+            # (each rank gathers / multiplies N / W rows) and all-gathered, instead of W identical copies of the work
+            ch = (N + W - 1) // W
+            a, b = min(rank * ch, N), min((rank + 1) * ch, N)
+            sg_all = torch.zeros(W * ch, dtype=torch.float32, device=dev)
+            if b > a:
+                tg = torch.empty((b - a, K), dtype=torch.bfloat16, device=dev)
+                call("gather_rows_bf16", top, top.stride(0), gt64[a:b], b - a, M, K, tg, K, st)
+                call("rowdot_tc", vop[a:b], vop.stride(0), tg, K, b - a, K, sg_all[rank * ch:rank * ch + (b - a)], st)
+            dist.all_gather_into_tensor(sg_all, sg_all[rank * ch:(rank + 1) * ch].clone(), group=group)
+            sgt = sg_all[:N]
+        else:
+            sgt = torch.empty(N, dtype=torch.float32, device=dev)
+            tg = torch.empty((N, K), dtype=torch.bfloat16, device=dev)
+            call("gather_rows_bf16", top, top.stride(0), gt64, N, M, K, tg, K, st)
+            call("rowdot_tc", vop, vop.stride(0), tg, K, N, K, sgt, st)
         counts = torch.zeros(N, dtype=torch.int32, device=dev)
     k = min(k, M)
     Ms = hi - lo
