@@ -460,6 +460,14 @@ int b200clip_symm_barrier(void* const* flags_host, int world, int rank, int chan
   return symm_barrier(flags_host, world, rank, channel, S(stream));
 }
 
+int b200clip_symm_allreduce_f32(void* const* bufs_host, int64_t n, int world, int rank, void* stream) {
+  return symm_allreduce_f32(bufs_host, n, world, rank, S(stream));
+}
+
+int b200clip_symm_sum_f64(const void* const* peers_host, int n, int world, double* out, void* stream) {
+  return symm_sum_f64(peers_host, n, world, out, S(stream));
+}
+
 int b200clip_clip_dlogtemp_peers(const void* const* scal_host, int world, const float* dyn, const float* gmul,
                                  const double* unif, int n, float* out, void* stream) {
   return clip_dlogtemp_peers(scal_host, world, dyn, gmul, unif, n, out, S(stream));

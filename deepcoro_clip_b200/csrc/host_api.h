@@ -215,6 +215,8 @@ int xfblock_wgrad(const float* a, long long lda, const float* bm, long long ldb,
 
 // scalars.cu: symmetric-memory plumbing of the multi-GPU CLIP path
 int symm_barrier(void* const* flags_host, int world, int rank, int channel, cudaStream_t s);
+int symm_allreduce_f32(void* const* bufs_host, long long n, int world, int rank, cudaStream_t s);
+int symm_sum_f64(const void* const* peers_host, int n, int world, double* out, cudaStream_t s);
 int clip_dlogtemp_peers(const void* const* scal_host, int world, const float* dyn, const float* gmul, const double* unif, int n,
                         float* out, cudaStream_t s);
 

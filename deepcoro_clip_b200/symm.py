@@ -137,3 +137,81 @@ def get_plan(group, N: int, ld: int, dev: torch.device) -> Optional[SymmPlan]:
         return None
     _PLANS[key] = plan
     return plan
+
+
+class SymmReducePlan:
+    """Symmetric buffers for an in-place sum-all-reduce of one fp32 tensor + a few fp64 scalars per step (the replicated-text
+    SigLIP path: the [T, D] text gradient and the loss / bias / temperature sums), without any NCCL call in the step: every
+    rank accumulates into its own copy, `b200clip_symm_allreduce_f32` reduces slice r on rank r and writes it back into every
+    copy, `b200clip_symm_sum_f64` adds the scalars, both bracketed by `b200clip_symm_barrier`. Double-buffered by step parity
+    like SymmPlan (the reduced tensor is a saved tensor of the autograd graph until its backward has run)."""
+
+    NSCAL = 32          # floats reserved behind the tensor (16 fp64 scalars)
+
+    def __init__(self, group, nfloat: int, dev: torch.device):
+        import torch.distributed._symmetric_memory as symm_mem
+        pg = group if group is not None else dist.group.WORLD
+        self.W, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
+        self.n = nfloat
+        self.dev_index = dev.index
+        self.per = (nfloat + self.NSCAL + 63) // 64 * 64
+        self.buf = symm_mem.empty((2, self.per), dtype=torch.float32, device=dev)
+        self.flags = symm_mem.empty((64,), dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.h_buf = symm_mem.rendezvous(self.buf, pg)
+        self.h_flags = symm_mem.rendezvous(self.flags, pg)
+        self.h_flags.barrier(channel=0)
+        self.step = 0
+        self.live = [None, None]
+
+        def arr(ptrs):
+            return (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self.buf_ptrs = [arr([int(p) + s * self.per * 4 for p in self.h_buf.buffer_ptrs]) for s in (0, 1)]
+        self.scal_ptrs = [arr([int(p) + (s * self.per + nfloat) * 4 for p in self.h_buf.buffer_ptrs]) for s in (0, 1)]
+        self.flag_ptrs = arr([int(p) for p in self.h_flags.buffer_ptrs])
+
+    acquire = SymmPlan.acquire
+    release = SymmPlan.release
+
+    def barrier(self, channel: int) -> None:
+        _call("symm_barrier", self.flag_ptrs, self.W, self.rank, channel, _stream_ptr(self.dev_index))
+
+    def allreduce(self, slot: int, nscal: int, scal_out: torch.Tensor) -> None:
+        """Tensor of `slot` summed in place on every rank, its first `nscal` fp64 scalars summed into `scal_out`."""
+        st = _stream_ptr(self.dev_index)
+        self.barrier(0)                                   # every rank's partial sums are complete
+        _call("symm_sum_f64", self.scal_ptrs[slot], nscal, self.W, scal_out, st)
+        _call("symm_allreduce_f32", self.buf_ptrs[slot], self.n, self.W, self.rank, st)
+        self.barrier(1)                                   # every slice has been written back everywhere
+
+
+_RPLANS: Dict[Tuple, "SymmReducePlan"] = {}
+
+
+def get_reduce_plan(group, nfloat: int, dev: torch.device) -> Optional[SymmReducePlan]:
+    """Cached SymmReducePlan, created collectively on first use; None when symmetric memory is unavailable / switched off."""
+    if not enabled() or not dist.is_available() or not dist.is_initialized() or nfloat % 4:
+        return None
+    pg = group if group is not None else dist.group.WORLD
+    if dist.get_backend(pg) != "nccl" or dist.get_world_size(pg) > 8:
+        return None
+    key = (id(pg), nfloat, dev.index)
+    if key in _RPLANS:
+        return _RPLANS[key]
+    if (id(pg), dev.index) in _FAILED:
+        return None
+    ok = torch.ones(1, device=dev)
+    plan = None
+    try:
+        plan = SymmReducePlan(pg, nfloat, dev)
+    except Exception as e:       # noqa: BLE001
+        ok.zero_()
+        if dist.get_rank(pg) == 0:
+            print(f"[deepcoro_clip_b200] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL collectives",
+                  flush=True)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=pg)
+    if ok.item() == 0:
+        _FAILED.add((id(pg), dev.index))
+        return None
+    _RPLANS[key] = plan
+    return plan

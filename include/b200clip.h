@@ -234,6 +234,13 @@ int b200clip_clip_dlogtemp(const double* scal0, const float* dyn, const float* g
  *   clip_dlogtemp_peers : clip_dlogtemp with scal0 = sum over ranks of scal_host[r][0] (each rank's fp64 partial of sum G L in
  *                         its symmetric block; call after a barrier that follows the video-side backward of every rank). */
 int b200clip_symm_barrier(void* const* flags_host, int world, int rank, int channel, void* stream);
+/*   symm_allreduce_f32  : in-place sum-all-reduce of an fp32 buffer of n elements (n % 4 == 0, 16-byte aligned) that every rank
+ *                         holds in symmetric memory (bufs_host[r] = rank r's copy): rank r reduces slice r over the peers and
+ *                         writes it back into every copy; bracket with symm_barrier (before: partial sums complete, after:
+ *                         every slice broadcast). Replaces dist.all_reduce of the replicated SigLIP text gradient.
+ *   symm_sum_f64        : out[i] = sum_r peers_host[r][i], i < n <= 32 (fp64 scalar tails, rank order, after a barrier). */
+int b200clip_symm_allreduce_f32(void* const* bufs_host, int64_t n, int world, int rank, void* stream);
+int b200clip_symm_sum_f64(const void* const* peers_host, int n, int world, double* out, void* stream);
 int b200clip_clip_dlogtemp_peers(const void* const* scal_host, int world, const float* dyn, const float* gmul,
                                  const double* unif, int n, float* out, void* stream);
 /* Alignment diagnostics of a batch from the same forward statistics, instead of the dense [B, B] similarity +
