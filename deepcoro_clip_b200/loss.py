@@ -441,7 +441,7 @@ class _SigLIPFn(torch.autograd.Function):
         # replicated text on several ranks: the [T, D] text gradient and the scalar sums are reduced over symmetric memory
         # (symm.SymmReducePlan) instead of two NCCL all-reduces, whose HOST cost (150-350 us each) bounds the eager step
         rplan = rslot = rtoken = None
-        if W > 1 and need_grad and not torch.cuda.is_current_stream_capturing():
+        if W > 1 and need_grad and video.is_cuda and not torch.cuda.is_current_stream_capturing():
             rplan = symm.get_reduce_plan(cfg["group"], T * D, dev)
             if rplan is not None:
                 rtoken = _SymmToken()
