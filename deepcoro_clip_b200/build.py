@@ -71,11 +71,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_oracle(force: bool = False) -> None:
-    """Compiles oracle/'s C restatement (checker only; never linked into the product library)."""
-    mk = ROOT / "oracle" / "Makefile"
-    if mk.exists():
-        subprocess.run(["make", "-C", str(ROOT / "oracle")] + (["-B"] if force else []), check=True,
-                       capture_output=True)
+    """Prepares the checker side (never linked into the product library): the oracle itself is numpy / torch (the reference is
+    Python: nothing to compile), the only artefact is oracle/_ref."""
     # oracle/_ref: the unmodified reference files of the path, copied where /root/reference exists (build container) so
     # that bench.py's reference arm / cpu_baseline legs can time the real classes on the GPU box (oracle/make_ref.py)
     rec = ROOT / "oracle" / "make_ref.py"

@@ -112,11 +112,10 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int col) {
 // MN-major operand spanning two adjacent 64-element blocks `lbo` bytes apart
 __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo) { return make_smem_desc_sw128(addr, lbo); }
 
-// One tile = D/64 boxes of [64 tokens x 64 channels]; loaded as sub-boxes of `br` token rows in (token group, channel box)
-// order, so that the requests to one 1 KB token row arrive close together at the memory controller
-__device__ __forceinline__ void pt_load_tile(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int KC, int br, int tok, int b) {
-  for (int tg = 0; tg < PT_TT; tg += br)
-    for (int kc = 0; kc < KC; ++kc) tma_load_3d(dst + kc * PT_BOX + tg * 128, tm, bar, kc * 64, tok + tg, b);
+// One tile = D/64 TMA boxes of [64 tokens x 64 channels] (the tallest box the tile allows: 32 / 16 / 8-row boxes measured
+// 1 / 6 / 23 % slower — the issue cost per box outweighs any DRAM-locality gain)
+__device__ __forceinline__ void pt_load_tile(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int KC, int tok, int b) {
+  for (int kc = 0; kc < KC; ++kc) tma_load_3d(dst + kc * PT_BOX, tm, bar, kc * 64, tok, b);
 }
 
 // plain bulk copy global -> shared (both 16-byte aligned, size % 16 == 0), completion on an mbarrier
@@ -132,8 +131,6 @@ struct PtFwdParams {
   float* part_m; float* part_l; float* part_l2; float* part_acc;
   int B, N, D, H, S, fp16;
   float drop_p; unsigned long long drop_seed;
-  int br;       // token rows per TMA load box
-  int dbg;      // timing experiments only (B200CLIP_POOL_DBG): 1 = no P2 MMAs, 2 = no softmax arithmetic, 4 = one P1 MMA per box
 };
 
 // dynamic shared memory (1024-aligned): ring NS x (D/64) boxes of 8 KB | qt operand (D/64) x [16 x 64] (2 KB each) |
@@ -177,7 +174,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
     // the first NS tiles start loading before anything else is set up
     for (int i = 0; i < NS && i < T; ++i) {
       mbar_expect_tx(&full[i], tile_bytes);
-      pt_load_tile(ring + i * tile_bytes, &tmx, &full[i], KC, p.br, (tile0 + i) * PT_TT, b);
+      pt_load_tile(ring + i * tile_bytes, &tmx, &full[i], KC, (tile0 + i) * PT_TT, b);
     }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
@@ -204,7 +201,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
         const int slot = i % NS;
         mbar_wait(&empty[slot], ((i / NS) & 1) ^ 1);
         mbar_expect_tx(&full[slot], tile_bytes);
-        pt_load_tile(ring + slot * tile_bytes, &tmx, &full[slot], KC, p.br, (tile0 + i) * PT_TT, b);
+        pt_load_tile(ring + slot * tile_bytes, &tmx, &full[slot], KC, (tile0 + i) * PT_TT, b);
       }
     }
   } else if (warp == 1) {
@@ -221,8 +218,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
           const uint64_t adesc = make_smem_desc_sw128(ring + slot * tile_bytes + kc * PT_BOX, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(qt_op + kc * 2048, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k == 0 || !(p.dbg & 4)) mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc1, (kc | k) != 0);
+          for (int k = 0; k < 4; ++k) mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc1, (kc | k) != 0);
         }
         tc_commit(&s_full[i & 1]);
       };
@@ -235,7 +231,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
         const int slot = i % NS;
         const uint32_t tile = ring + slot * tile_bytes;
         const uint64_t bdesc = make_smem_desc_sw128(p_op + (i & 1) * 2048, 1024);
-        for (int mb = 0; mb < MB && !(p.dbg & 1); ++mb) {
+        for (int mb = 0; mb < MB; ++mb) {
           const uint64_t adesc = desc_mn(tile + 2 * mb * PT_BOX, PT_BOX);
 #pragma unroll
           for (int ks = 0; ks < PT_TT / 16; ++ks)
@@ -304,7 +300,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pool_fwd_tc_kernel(const __grid
           tc_wait_st();
         }
       }
-      if (lane < 16 && !(p.dbg & 2)) {
+      if (lane < 16) {
         const uint32_t pb = p_op + sb * 2048;
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
@@ -373,7 +369,6 @@ struct PtBwdParams {
   const float* sa; const float* dsa; const float* dlse;
   int B, N, D, H, S, fp16;
   float drop_p; unsigned long long drop_seed;
-  int br;
 };
 
 // dynamic shared memory: ring NS x (D/64) boxes | W operand (D/64) x [32 x 64] (4 KB each: rows qt_hi, dxbar_hi, qt_lo,
@@ -424,7 +419,7 @@ __global__ void __launch_bounds__(PT_BWD_THREADS, 1) pool_bwd_tc_kernel(const __
     }
     for (int i = 0; i < NS && i < T; ++i) {
       mbar_expect_tx(&full[i], tile_bytes);
-      pt_load_tile(ring + i * tile_bytes, &tmx, &full[i], KC, p.br, (tile0 + i) * PT_TT, b);
+      pt_load_tile(ring + i * tile_bytes, &tmx, &full[i], KC, (tile0 + i) * PT_TT, b);
     }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -474,7 +469,7 @@ __global__ void __launch_bounds__(PT_BWD_THREADS, 1) pool_bwd_tc_kernel(const __
         const int slot = i % NS;
         mbar_wait(&empty[slot], ((i / NS) & 1) ^ 1);
         mbar_expect_tx(&full[slot], tile_bytes);
-        pt_load_tile(ring + slot * tile_bytes, &tmx, &full[slot], KC, p.br, (tile0 + i) * PT_TT, b);
+        pt_load_tile(ring + slot * tile_bytes, &tmx, &full[slot], KC, (tile0 + i) * PT_TT, b);
       }
     }
   } else if (warp == 1) {
@@ -643,17 +638,7 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // [B, N, D] 16-bit tensor (contiguous), box [1, 64 tokens, 64 channels], SWIZZLE_128B; tokens past N are zero-filled
-static int pt_box_rows() {
-  static int br = 0;
-  if (br == 0) {
-    const char* e = getenv("B200CLIP_POOL_BOXROWS");
-    br = e ? atoi(e) : PT_TT;
-    if (br != 8 && br != 16 && br != 32 && br != 64) br = PT_TT;
-  }
-  return br;
-}
-
-static int make_tmap_x3d(CUtensorMap* out, const void* base, int B, int N, int D, int box_rows = PT_TT) {
+static int make_tmap_x3d(CUtensorMap* out, const void* base, int B, int N, int D) {
   static EncodeTiledFn3 enc = nullptr;
   if (!enc) {
     void* fp = nullptr;
@@ -665,7 +650,7 @@ static int make_tmap_x3d(CUtensorMap* out, const void* base, int B, int N, int D
   }
   cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {64, PT_TT, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -711,10 +696,8 @@ int attnpool_tc_fwd(const void* x, int dtype, const unsigned char* mask, long lo
                     unsigned long long drop_seed, float* part_l2, cudaStream_t s) {
   if (!x || (!qt && !qt_img) || (reinterpret_cast<uintptr_t>(qt_img) & 15) || !part_m || !part_l || !part_acc || S < 1 || S > (N + PT_TT - 1) / PT_TT) return B2_EINVAL;
   CUtensorMap tmx;
-  if (int rc = make_tmap_x3d(&tmx, x, B, N, D, pt_box_rows())) return rc;
-  const char* dbg = getenv("B200CLIP_POOL_DBG");
-  PtFwdParams p{mask, mb, qt, qt_img, part_m, part_l, part_l2, part_acc, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed,
-                pt_box_rows(), dbg ? atoi(dbg) : 0};
+  if (int rc = make_tmap_x3d(&tmx, x, B, N, D)) return rc;
+  PtFwdParams p{mask, mb, qt, qt_img, part_m, part_l, part_l2, part_acc, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed};
   dim3 grid(B, S);
   const int ns = pt_fwd_smem(D, 4) <= 227 * 1024 ? 4 : 3;
   const size_t smem = pt_fwd_smem(D, ns);
@@ -730,11 +713,10 @@ int attnpool_tc_bwd(const void* x, int dtype, const unsigned char* mask, long lo
                     unsigned long long drop_seed, const float* dlse, float* part_dq, cudaStream_t s) {
   if (!x || (!w_img && (!qt || !dxbar || !xbar)) || (w_img && !cdot) || (reinterpret_cast<uintptr_t>(w_img) & 15) || !m || !l || !dx || S < 1 || S > (N + PT_TT - 1) / PT_TT) return B2_EINVAL;
   CUtensorMap tmx;
-  if (int rc = make_tmap_x3d(&tmx, x, B, N, D, pt_box_rows())) return rc;
+  if (int rc = make_tmap_x3d(&tmx, x, B, N, D)) return rc;
   CUtensorMap tmdx;
   if (int rc = make_tmap_x3d(&tmdx, dx, B, N, D)) return rc;
-  PtBwdParams p{mask, mb, qt, dxbar, xbar, w_img, cdot, m, l, dx, part_dq, sa, dsa, dlse, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed,
-                pt_box_rows()};
+  PtBwdParams p{mask, mb, qt, dxbar, xbar, w_img, cdot, m, l, dx, part_dq, sa, dsa, dlse, B, N, D, H, S, dtype == 2 ? 1 : 0, drop_p, drop_seed};
   dim3 grid(B, S);
   const int ns = pt_bwd_smem(D, 3) <= 227 * 1024 ? 3 : 2;
   const size_t smem = pt_bwd_smem(D, ns);

@@ -24,10 +24,6 @@ def world(use_ddp: bool = True, group=None) -> Tuple[int, int]:
     return 1, 0
 
 
-def row_slab(rank: int, rows_per_rank: int) -> Tuple[int, int]:
-    return rank * rows_per_rank, (rank + 1) * rows_per_rank
-
-
 def text_shard(n_text: int, world_size: int, rank: int) -> Tuple[int, int]:
     per = (n_text + world_size - 1) // world_size
     lo = min(rank * per, n_text)
@@ -51,14 +47,3 @@ def gather_rows_async(x: torch.Tensor, world_size: int, group=None):
     out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     work = dist.all_gather_into_tensor(out, x.contiguous(), group=group, async_op=True)
     return out, work
-
-
-def reduce_sum_(x: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
-    if world_size > 1:
-        dist.all_reduce(x, group=group)
-    return x
-
-
-def clip_loss_from_sums(sum_row_lse, sum_col_lse, sum_tgt, n_global: int):
-    """loss = 0.5 * [mean_i(r_i - tgt_i) + mean_j(c_j - tgt_j)], with sum_i tgt_i == sum_j tgt_j == sum_tgt."""
-    return (0.5 / n_global) * (sum_row_lse + sum_col_lse) - sum_tgt / n_global

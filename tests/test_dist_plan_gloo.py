@@ -13,6 +13,22 @@ from oracle import contrastive_oracle as co
 from oracle import retrieval_oracle as ro
 
 
+# the arithmetic of the plan, spelled out here (the package itself does it inside its kernels)
+def row_slab(rank, rows_per_rank):
+    return rank * rows_per_rank, (rank + 1) * rows_per_rank
+
+
+def reduce_sum_(x, world_size, group=None):
+    if world_size > 1:
+        dist.all_reduce(x, group=group)
+    return x
+
+
+def clip_loss_from_sums(sum_row_lse, sum_col_lse, sum_tgt, n_global):
+    """loss = 0.5 * [mean_i(r_i - tgt_i) + mean_j(c_j - tgt_j)], with sum_i tgt_i == sum_j tgt_j == sum_tgt."""
+    return (0.5 / n_global) * (sum_row_lse + sum_col_lse) - sum_tgt / n_global
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -23,7 +39,7 @@ def _worker(rank, world, port, out):
         N = B * world
         rng = np.random.default_rng(0)                        # identical global data on every rank
         v = rng.standard_normal((N, D)); t = rng.standard_normal((N, D))
-        lo, hi = dp.row_slab(rank, B)
+        lo, hi = row_slab(rank, B)
         vh, _ = co.l2_normalize(v); th, _ = co.l2_normalize(t)
         # --- what the rank's kernels would produce for its row slab (oracle stand-in) ---
         vall = dp.gather_rows(torch.tensor(vh[lo:hi]), world)
@@ -35,12 +51,12 @@ def _worker(rank, world, port, out):
         colsum = torch.tensor(np.exp(L - shift).sum(0))
         diag = torch.tensor([L[np.arange(B), lo + np.arange(B)].sum()])
         # --- the plan's collectives + assembly ---
-        dp.reduce_sum_(colsum, world)
+        reduce_sum_(colsum, world)
         rowsum_all = dp.gather_rows(rowsum, world)
-        dp.reduce_sum_(diag, world)
+        reduce_sum_(diag, world)
         sum_r = (torch.log(rowsum_all) + shift).sum()
         sum_c = (torch.log(colsum) + shift).sum()
-        loss = dp.clip_loss_from_sums(sum_r, sum_c, diag[0], N)
+        loss = clip_loss_from_sums(sum_r, sum_c, diag[0], N)
         ref = co.clip_loss(v, t, math.log(tau), want_grads=False)["loss"]
         assert abs(float(loss) - ref) < 1e-10, (float(loss), ref)
         # --- retrieval: text shards, rank counts all-reduced ---
@@ -54,7 +70,7 @@ def _worker(rank, world, port, out):
         cols = np.arange(M)[None, :]
         better = (sim > sg) | ((sim == sg) & (cols < gt[:, None]))
         counts = torch.tensor(better[:, s_lo:s_hi].sum(1))
-        dp.reduce_sum_(counts, world)
+        reduce_sum_(counts, world)
         assert (counts.numpy() + 1 == ro.gt_ranks(sim, gt)).all()
         covered = dp.gather_rows(torch.tensor([[s_lo, s_hi]]), world).numpy()
         assert covered[0, 0] == 0 and covered[-1, 1] == M and (covered[1:, 0] == covered[:-1, 1]).all()
@@ -75,7 +91,7 @@ def test_two_rank_gloo_plan():
 def test_shard_helpers_single_process():
     from deepcoro_clip_b200 import dist_plan as dp
     assert dp.world() == (1, 0)
-    assert dp.row_slab(3, 128) == (384, 512)
+    assert row_slab(3, 128) == (384, 512)
     spans = [dp.text_shard(32473, 8, r) for r in range(8)]
     assert spans[0][0] == 0 and spans[-1][1] == 32473 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     assert dp.text_shard(3, 8, 7) == (3, 3)                # more ranks than rows: empty shard
