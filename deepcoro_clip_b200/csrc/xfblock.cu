@@ -17,7 +17,12 @@
 
 namespace b2 {
 
+constexpr int XB_UNROLL = 2;
+// 8 warps. Measured with 16 warps (r02_xfblock_variants.log): one block fwd + bwd 253 us instead of 269 us at 8 studies x 4
+// views, 598 instead of 722 us at 16 views, but 595 instead of 455 us at 32 studies (one CTA per SM: 256 CTAs take two waves).
 constexpr int XB_THREADS = 256;
+constexpr int XB_TG = XB_THREADS / 64;  // row groups of the transposed mat-vec
+constexpr int WG_THREADS = 256;         // weight-gradient kernel
 constexpr int XB_CL = 8;
 constexpr int XB_W = 64;         // widest D slice (D <= 512)
 constexpr int XB_FW = 256;       // widest hidden slice (F <= 2048)
@@ -53,7 +58,7 @@ __device__ void xb_matvec(const float* __restrict__ W, long long ldw, int j0, in
     const float* wr[JU];
 #pragma unroll
     for (int q = 0; q < JU; ++q) wr[q] = W + (long long)(j0 + min(jb + q, nj - 1)) * ldw;
-#pragma unroll 2
+#pragma unroll XB_UNROLL
     for (int i = lane * 4; i < K; i += 128) {
       float4 w[JU];
 #pragma unroll
@@ -77,8 +82,8 @@ __device__ void xb_matvec(const float* __restrict__ W, long long ldw, int j0, in
   __syncthreads();
 }
 
-// out[r * ostride + i] (+)= sum_{j < J} W[j * ldw + i0 + i] u[r * ustride + j]   (i < ni <= 64): thread = (column, 1 of 4 row
-// groups), eight weight loads in flight per thread; `scratch` = 4 * RB * 64 floats. Ends with __syncthreads.
+// out[r * ostride + i] (+)= sum_{j < J} W[j * ldw + i0 + i] u[r * ustride + j]   (i < ni <= 64): thread = (column, 1 of XB_TG
+// row groups), eight weight loads in flight per thread; `scratch` = XB_TG * RB * 64 floats. Ends with __syncthreads.
 template <int RB>
 __device__ void xb_matvec_t(const float* __restrict__ W, long long ldw, int i0, int ni, int J, const float* u, int ustride,
                             float* out, int ostride, float* scratch, bool accumulate) {
@@ -89,16 +94,16 @@ __device__ void xb_matvec_t(const float* __restrict__ W, long long ldw, int i0, 
   if (i < ni) {
     const float* wc = W + i0 + i;
     int j = jp;
-    for (; j + 28 < J; j += 32) {
+    for (; j + 7 * XB_TG < J; j += 8 * XB_TG) {
       float w[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) w[e] = wc[(long long)(j + 4 * e) * ldw];
+      for (int e = 0; e < 8; ++e) w[e] = wc[(long long)(j + XB_TG * e) * ldw];
 #pragma unroll
       for (int e = 0; e < 8; ++e)
 #pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r] = fmaf(w[e], u[r * ustride + j + 4 * e], acc[r]);
+        for (int r = 0; r < RB; ++r) acc[r] = fmaf(w[e], u[r * ustride + j + XB_TG * e], acc[r]);
     }
-    for (; j < J; j += 4) {
+    for (; j < J; j += XB_TG) {
       const float w = wc[(long long)j * ldw];
 #pragma unroll
       for (int r = 0; r < RB; ++r) acc[r] = fmaf(w, u[r * ustride + j], acc[r]);
@@ -110,8 +115,9 @@ __device__ void xb_matvec_t(const float* __restrict__ W, long long ldw, int i0, 
   for (int t = threadIdx.x; t < RB * 64; t += XB_THREADS) {
     const int r = t >> 6, ii = t & 63;
     if (ii < ni) {
-      const float s = scratch[(0 * RB + r) * 64 + ii] + scratch[(1 * RB + r) * 64 + ii] + scratch[(2 * RB + r) * 64 + ii] +
-                      scratch[(3 * RB + r) * 64 + ii];
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < XB_TG; ++g) s += scratch[(g * RB + r) * 64 + ii];
       out[r * ostride + ii] = accumulate ? out[r * ostride + ii] + s : s;
     }
   }
@@ -158,7 +164,7 @@ struct XbParams {
 };
 
 // shared memory (floats): BIG [RB][F] (x rows | LN rows / gathered rows; later the gathered hidden rows) |
-// qs, ks, vs, os, x1s, ts [RB][64] | zs [RB][256] | sp, aa [RB][RB] | stat1, stat2 [RB] | scratch [4][RB][64]
+// qs, ks, vs, os, x1s, ts [RB][64] | zs [RB][256] | sp, aa [RB][RB] | stat1, stat2 [RB] | scratch [XB_TG][RB][64]
 template <int RB>
 struct XbSmem {
   static constexpr int big = 0;
@@ -168,7 +174,7 @@ struct XbSmem {
   static constexpr int aa = sp + RB * RB;
   static constexpr int st = aa + RB * RB;
   static constexpr int scratch = st + 2 * RB;
-  static constexpr int total = scratch + 4 * RB * 64;
+  static constexpr int total = scratch + XB_TG * RB * 64;
 };
 
 template <int RB>
@@ -499,11 +505,11 @@ struct WgParams {
   const float* a; long long lda; const float* bm; long long ldb; float* dw; float* db; int J, I, R;
   const float* a2; const float* xh; float* dg; float* dbeta; int D2;
 };
-__global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
+__global__ void __launch_bounds__(WG_THREADS) xfblock_wgrad_kernel(WgParams p) {
   __shared__ float coef[8][128];
   if (blockIdx.y == 1) {
     if (!p.dg || blockIdx.z != 0) return;
-    const int i = blockIdx.x * XB_THREADS + threadIdx.x;
+    const int i = blockIdx.x * WG_THREADS + threadIdx.x;
     if (i < p.D2) {
       float g = 0.f, bb = 0.f;
       for (int r = 0; r < p.R; ++r) { const float v = p.a2[(size_t)r * p.D2 + i]; g = fmaf(v, p.xh[(size_t)r * p.D2 + i], g); bb += v; }
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
   const int j0 = blockIdx.x * 8;
   if (j0 >= p.J) return;
   constexpr int MAXE = 4;                 // 1024 columns per CTA (blockIdx.z selects the column block)
-  const int ibase = blockIdx.z * MAXE * XB_THREADS;
+  const int ibase = blockIdx.z * MAXE * WG_THREADS;
   float acc[8][MAXE];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
   for (int rc = 0; rc < p.R; rc += 128) {
     const int nr = min(128, p.R - rc);
     __syncthreads();
-    for (int t = threadIdx.x; t < 8 * nr; t += XB_THREADS) {
+    for (int t = threadIdx.x; t < 8 * nr; t += WG_THREADS) {
       const int jj = t / nr, r = rc + t - jj * nr;
       coef[jj][r - rc] = j0 + jj < p.J ? p.a[(size_t)r * p.lda + j0 + jj] : 0.f;
     }
@@ -533,7 +539,7 @@ __global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
     for (int r = 0; r < nr; ++r) {
 #pragma unroll
       for (int e = 0; e < MAXE; ++e) {
-        const int i = ibase + threadIdx.x + e * XB_THREADS;
+        const int i = ibase + threadIdx.x + e * WG_THREADS;
         if (i < p.I) {
           const float v = p.bm[(size_t)(rc + r) * p.ldb + i];
 #pragma unroll
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(XB_THREADS) xfblock_wgrad_kernel(WgParams p) {
   }
 #pragma unroll
   for (int e = 0; e < MAXE; ++e) {
-    const int i = ibase + threadIdx.x + e * XB_THREADS;
+    const int i = ibase + threadIdx.x + e * WG_THREADS;
     if (i < p.I)
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj)
@@ -604,8 +610,8 @@ int xfblock_wgrad(const float* a, long long lda, const float* bm, long long ldb,
                   const float* a2, const float* xh, float* dg, float* dbeta, int D2, cudaStream_t s) {
   if (!a || !bm || !dw || J <= 0 || I <= 0 || I > 2048 || R <= 0) return B2_EINVAL;
   WgParams p{a, lda, bm, ldb, dw, db, J, I, R, a2, xh, dg, dbeta, D2};
-  const int gx = max((J + 7) / 8, dg ? (D2 + XB_THREADS - 1) / XB_THREADS : 1);
-  xfblock_wgrad_kernel<<<dim3(gx, dg ? 2 : 1, (I + 4 * XB_THREADS - 1) / (4 * XB_THREADS)), XB_THREADS, 0, s>>>(p);
+  const int gx = max((J + 7) / 8, dg ? (D2 + WG_THREADS - 1) / WG_THREADS : 1);
+  xfblock_wgrad_kernel<<<dim3(gx, dg ? 2 : 1, (I + 4 * WG_THREADS - 1) / (4 * WG_THREADS)), WG_THREADS, 0, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

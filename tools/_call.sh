@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-T=r02al
-timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/${T}_pytest_gpu.log 2>&1
-echo "pytest rc=$? : $(tail -1 gpurun_out/${T}_pytest_gpu.log)"; grep -E "^FAILED|^ERROR" gpurun_out/${T}_pytest_gpu.log | head -20
-timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1
-timeout 300 python tools/gpu_check_pool_tc.py 2>&1 | tail -3 | cut -c1-200
+for v in 256_2 256_4 512_2 512_4; do
+  cp build/variants/lib_$v.so deepcoro_clip_b200/libb200clip.so
+  timeout 200 python tools/gpu_xfblock_time.py $v 2>&1 | grep -v Warning | tail -2
+done 2>&1 | tee gpurun_out/xfblock_variants.log
+timeout 300 python tools/gpu_check_xfblock.py 2>&1 | grep -v Warning | tail -12
