@@ -10,13 +10,14 @@ from .loss import (CLIPLoss, ContrastiveLoss, ContrastiveLossDDP, InfoNCELoss, S
                    SigLIP2MultiPositiveBCELoss, SigLIPLoss, SiglipLoss, SiglipLossDDP, SiglipPairwiseFeatureLoss,
                    clip_loss)
 from . import retrieval_metrics
+from .mil_pooling import GatedAttentionPooling, gated_attention_pool
 from .multipos_loss import MultiPositiveInfoNCELoss, WeightedSigLIPLoss, inline_multipositive_loss
 from .retrieval_metrics_streaming import (compute_metrics_streaming, compute_recall_at_k_streaming, inference_topk_indices,
                                           streaming_topk, top5_predictions)
 from .rope_3d import Rope3D, apply_rope_qk
 from .video_aggregator import EnhancedVideoAggregator, query_pool
 
-__all__ = ["AttentionPool", "AttentionPoolWithCLS", "CLIPLoss", "GraphedLossStep", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EmbeddingStore", "EnhancedVideoAggregator",
+__all__ = ["AttentionPool", "GatedAttentionPooling", "gated_attention_pool", "AttentionPoolWithCLS", "CLIPLoss", "GraphedLossStep", "HostBatchPrefetcher", "ContrastiveLoss", "ContrastiveLossDDP", "EmbeddingStore", "EnhancedVideoAggregator",
            "InfoNCELoss", "MultiPositiveInfoNCELoss", "inline_multipositive_loss", "Rope3D", "SigLIP2BCELoss", "SigLIP2BCELossDDP", "SigLIP2MultiPositiveBCELoss", "SigLIPLoss",
            "SiglipLoss", "SiglipLossDDP", "SiglipPairwiseFeatureLoss", "WeightedSigLIPLoss", "alignment_diagnostics", "apply_rope_qk", "clip_loss",
            "compute_metrics_streaming", "compute_recall_at_k_streaming", "epoch_end_retrieval_metrics", "gather_tensor_along_batch", "install", "loss_table", "query_pool",

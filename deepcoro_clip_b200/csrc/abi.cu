@@ -456,6 +456,30 @@ int b200clip_xfblock_wgrad(const float* a, int64_t lda, const float* b, int64_t 
   return xfblock_wgrad(a, lda, b, ldb, dw, db, J, I, R, a2, xhat, dgamma, dbeta, D2, S(stream));
 }
 
+int b200clip_milpool_ok(int L, int D, int Hd) { return milpool_ok(L, D, Hd) ? 1 : 0; }
+
+int b200clip_milpool_plan(int S, int L, int D, int Hd, int* plan) {
+  if (!plan || S < 1 || !milpool_ok(L, D, Hd)) return B2_EINVAL;
+  milpool_plan(S, L, D, Hd, plan);
+  return B2_OK;
+}
+
+int b200clip_milpool_fwd(const float* x, int64_t x_sseq, int64_t x_stok, const uint8_t* valid, int64_t valid_sseq,
+                         const float* V, const float* bV, const float* U, const float* bU, const float* w, const float* bw,
+                         int S, int L, int D, int Hd, float drop_p, int64_t seed, float* tg, float* spart, float* attn,
+                         float* opart, float* out, void* stream) {
+  return milpool_fwd(x, x_sseq, x_stok, valid, valid_sseq, V, bV, U, bU, w, bw, S, L, D, Hd, drop_p,
+                     (unsigned long long)seed, tg, spart, attn, opart, out, S(stream));
+}
+
+int b200clip_milpool_bwd(const float* x, int64_t x_sseq, int64_t x_stok, const float* V, const float* U, const float* w,
+                         int S, int L, int D, int Hd, float drop_p, int64_t seed, const float* tg, const float* attn,
+                         const float* dout, float* ds, float* dx, float* dpre, float* wpart, float* fpart, float* dW,
+                         float* dsmall, void* stream) {
+  return milpool_bwd(x, x_sseq, x_stok, V, U, w, S, L, D, Hd, drop_p, (unsigned long long)seed, tg, attn, dout, ds, dx,
+                     dpre, wpart, fpart, dW, dsmall, S(stream));
+}
+
 int b200clip_symm_barrier(void* const* flags_host, int world, int rank, int channel, void* stream) {
   return symm_barrier(flags_host, world, rank, channel, S(stream));
 }

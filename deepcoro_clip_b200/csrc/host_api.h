@@ -213,6 +213,18 @@ int xfblock(int backward, const void* const* ptrs, int B, int N, int D, int H, i
 int xfblock_wgrad(const float* a, long long lda, const float* bm, long long ldb, float* dw, float* db, int J, int I, int R,
                   const float* a2, const float* xh, float* dg, float* dbeta, int D2, cudaStream_t s);
 
+// milpool.cu: gated-attention pooling of the multi-instance probing head (fp32)
+bool milpool_ok(int L, int D, int Hd);
+void milpool_plan(int S, int L, int D, int Hd, int* plan);
+int milpool_fwd(const float* x, long long sx_seq, long long sx_tok, const uint8_t* mask, long long smask, const float* V,
+                const float* bV, const float* U, const float* bU, const float* w, const float* bw, int S, int L, int D,
+                int Hd, float drop_p, unsigned long long seed, float* tg, float* spart, float* attn, float* opart, float* out,
+                cudaStream_t s);
+int milpool_bwd(const float* x, long long sx_seq, long long sx_tok, const float* V, const float* U, const float* w, int S,
+                int L, int D, int Hd, float drop_p, unsigned long long seed, const float* tg, const float* attn,
+                const float* dout, float* ds, float* dx, float* dpre, float* wpart, float* fpart, float* dW, float* dsmall,
+                cudaStream_t s);
+
 // scalars.cu: symmetric-memory plumbing of the multi-GPU CLIP path
 int symm_barrier(void* const* flags_host, int world, int rank, int channel, cudaStream_t s);
 int symm_allreduce_f32(void* const* bufs_host, long long n, int world, int rank, cudaStream_t s);

@@ -4,7 +4,8 @@
     ``LossType`` keys the reference registers;
   * the module-level names ``models.video_encoder.Rope3D`` / ``AttentionPool`` / ``AttentionPoolWithCLS`` /
     ``EnhancedVideoAggregator`` that ``VideoEncoder.__init__`` instantiates (models/video_encoder.py:12-13, 115-140,
-    207-219);
+    207-219); the gated-attention pooling methods of ``MultiInstanceLinearProbing``
+    (models/multi_instance_linear_probing.py:493-536) for CUDA inputs;
   * the function names ``compute_metrics_streaming`` / ``compute_recall_at_k_streaming`` imported by
     runners/multitask_runner.py:35, and the dense multi-label metrics of utils/retrieval_metrics.py.
 
@@ -16,7 +17,8 @@ import importlib
 import sys
 from typing import Dict
 
-from . import attention_pool, loss, multipos_loss, retrieval_metrics, retrieval_metrics_streaming, rope_3d, video_aggregator
+from . import (attention_pool, loss, mil_pooling, multipos_loss, retrieval_metrics, retrieval_metrics_streaming, rope_3d,
+               video_aggregator)
 
 # key -> class, for the two import orders the reference can end up with (SURVEY §8b "registration order hazard")
 _MAIN = {          # scripts/main.py order: utils/loss/contrastive.py registers last
@@ -108,6 +110,23 @@ def install(reference_root: str | None = None, semantics: str = "main", losses: 
                 for n in names:
                     setattr(mod, n, getattr(src, n))
                 report["modules"].append(modname)
+        # gated-attention MIL pooling (models/multi_instance_linear_probing.py:493-536): the two methods of the probing head
+        mod = sys.modules.get("models.multi_instance_linear_probing")
+        if mod is None:
+            try:
+                mod = importlib.import_module("models.multi_instance_linear_probing")
+            except Exception:
+                mod = None
+        mil = getattr(mod, "MultiInstanceLinearProbing", None) if mod is not None else None
+        if mil is not None and not hasattr(mil._attention_pooling, "reference"):
+            def _att(self, x, mask):
+                return mil_pooling.attention_pooling(self, x, mask) if x.is_cuda else _att.reference(self, x, mask)
+
+            def _hier(self, x, mask):
+                return mil_pooling.hierarchical_attention_pooling(self, x, mask) if x.is_cuda else _hier.reference(self, x, mask)
+            _att.reference, _hier.reference = mil._attention_pooling, mil._hierarchical_attention_pooling
+            mil._attention_pooling, mil._hierarchical_attention_pooling = _att, _hier
+            report["modules"].append("models.multi_instance_linear_probing.MultiInstanceLinearProbing._attention_pooling")
     if metrics:
         for modname in ("utils.retrieval_metrics_streaming", "runners.multitask_runner"):
             mod = sys.modules.get(modname)

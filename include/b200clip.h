@@ -560,6 +560,32 @@ int b200clip_xfblock_wgrad(const float* a, int64_t lda, const float* b, int64_t 
                            int R, const float* a2, const float* xhat, float* dgamma, float* dbeta, int D2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K11  Gated-attention MIL pooling (models/multi_instance_linear_probing.py:493-507 `_attention_pooling`, and each of the
+ *      two levels of :509-536 `_hierarchical_attention_pooling`), fp32:
+ *        a_l = w . (tanh(V x_l + bV) * sigmoid(U x_l + bU)) + bw ; A = softmax_l(a, invalid -> -inf) ; out = sum_l drop(A_l) x_l
+ *   x: S sequences of L instances of width D (element strides x_sseq / x_stok, rows contiguous, 16-byte aligned);
+ *   valid [S, L] bytes, non-zero = instance present (row pitch valid_sseq) or NULL; V, U [Hd, D]; bV, bU, w [Hd]; bw [1].
+ *   milpool_ok: D % 16 == 0, Hd % 8 == 0, L <= 49152.  milpool_plan fills plan[4] = {P, Z, chunks, unit_tiles}, the sizes of
+ *   the caller-allocated work buffers (R = S L):
+ *     forward : tg [R, 2 Hd] (tanh | sigmoid, kept for the backward), spart [unit_tiles, R], attn [R] (softmax before
+ *               dropout, kept), opart [S, P, D] (only read when P > 1), out [S, D].
+ *     backward: dout [S, D] -> ds [R], dpre [R, 2 Hd], wpart [Z, 2 Hd, D], fpart [chunks, 3 Hd + 4] (work), dx [R, D] (written),
+ *               dW [2 Hd, D] = [dV; dU], dsmall [3 Hd + 1] = [dbV | dbU | dw | dbw] (written; sums in a fixed order).
+ *   drop_p / seed: dropout of A with the counter-based keep mask (0 = none). A sequence without a valid instance gives NaN
+ *   (softmax of an all -inf row), as in the reference.
+ * ------------------------------------------------------------------------------------------------ */
+int b200clip_milpool_ok(int L, int D, int Hd);
+int b200clip_milpool_plan(int S, int L, int D, int Hd, int* plan);
+int b200clip_milpool_fwd(const float* x, int64_t x_sseq, int64_t x_stok, const uint8_t* valid, int64_t valid_sseq,
+                         const float* V, const float* bV, const float* U, const float* bU, const float* w, const float* bw,
+                         int S, int L, int D, int Hd, float drop_p, int64_t seed, float* tg, float* spart, float* attn,
+                         float* opart, float* out, void* stream);
+int b200clip_milpool_bwd(const float* x, int64_t x_sseq, int64_t x_stok, const float* V, const float* U, const float* w,
+                         int S, int L, int D, int Hd, float drop_p, int64_t seed, const float* tg, const float* attn,
+                         const float* dout, float* ds, float* dx, float* dpre, float* wpart, float* fpart, float* dW,
+                         float* dsmall, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).
  *   x [B, N, D] fp32 (strides sb, sn), pos [>=N, D] or NULL, final LayerNorm (ln_w, ln_b, eps), attn_query [D],
  *   mask [B, N] bytes (non-zero = masked view) or NULL. backward = 0: out [B, D]. backward = 1: dx [B, N, D] written,

@@ -507,7 +507,39 @@ def qpool():
         print(name, tuple(out.shape))
 
 
+def milpool():
+    """MultiInstanceLinearProbing(pooling_mode="attention")._pool_instances on [B, N, D] and [B, N, L, D] inputs."""
+    from models.multi_instance_linear_probing import MultiInstanceLinearProbing
+    cases = {"milpool_b5_n6_d64_h32_mask": ((5, 6, 64), 32, True), "milpool_b3_n4_d128_h128": ((3, 4, 128), 128, False),
+             "milpool_b2_n3_l20_d64_h24_mask": ((2, 3, 20, 64), 24, True)}
+    for name, (shape, hd, use_mask) in cases.items():
+        torch.manual_seed(70)
+        mod = MultiInstanceLinearProbing(shape[-1], {"head": 3}, pooling_mode="attention", attention_hidden=hd).double()
+        with torch.no_grad():
+            for lin in (mod.attention_V, mod.attention_U, mod.attention_w):
+                lin.bias.normal_(std=0.3)
+            mod.attention_w.weight.mul_(3.0)
+        g = torch.Generator().manual_seed(71)
+        x = torch.randn(*shape, generator=g).double().requires_grad_(True)
+        B, N = shape[:2]
+        mask = None
+        if use_mask:
+            mask = torch.rand(B, N, generator=g) > 0.35
+            mask[:, 0] = True
+        out = mod._pool_instances(x, mask)
+        go = torch.randn(out.shape, generator=g).double()
+        (out * go).sum().backward()
+        np.savez_compressed(OUT / f"{name}.npz", x=_np(x), go=_np(go), out=_np(out), dx=_np(x.grad),
+                            mask=np.ones((B, N), bool) if mask is None else mask.numpy(), has_mask=np.array(use_mask),
+                            V=_np(mod.attention_V.weight), bV=_np(mod.attention_V.bias), U=_np(mod.attention_U.weight),
+                            bU=_np(mod.attention_U.bias), w=_np(mod.attention_w.weight), bw=_np(mod.attention_w.bias),
+                            g_V=_np(mod.attention_V.weight.grad), g_bV=_np(mod.attention_V.bias.grad),
+                            g_U=_np(mod.attention_U.weight.grad), g_bU=_np(mod.attention_U.bias.grad),
+                            g_w=_np(mod.attention_w.weight.grad), g_bw=_np(mod.attention_w.bias.grad))
+        print(name, tuple(out.shape))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "inline_multipos", "tokenmean", "alignment", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool"]
+    which = sys.argv[1:] or ["losses", "siglip_variants", "multipos", "inline_multipos", "tokenmean", "alignment", "dense_metrics", "retrieval", "rope", "attnpool", "clspool", "qpool", "milpool"]
     for name in which:
         globals()[name]()

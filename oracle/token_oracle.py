@@ -305,3 +305,57 @@ def query_pool_backward(dout, cache, ln_w):
         dln = np.where(c["mask"][..., None], 0.0, dln)
     dx, dlw, dlb = _layernorm_backward(dln, c["xh"], c["rstd"], np.asarray(ln_w, np.float64))
     return dict(x=dx, pos=dx.sum(0), ln_w=dlw, ln_b=dlb, attn_query=dq.reshape(1, 1, -1))
+
+
+# ------------------------------------------------------------------------------------------------
+# Gated-attention MIL pooling (models/multi_instance_linear_probing.py:493-536)
+# ------------------------------------------------------------------------------------------------
+def mil_gated_pool_forward(x, mask, V, bV, U, bU, w, bw, want_cache=False):
+    """One level (:499-507): x [S,L,D]; mask [S,L] True = valid (or None). A = softmax_l(w.(tanh(Vx+bV)*sigmoid(Ux+bU))+bw
+    with invalid -> -inf); out = sum_l A_l x_l. A sequence without a valid instance gives NaN, as torch's softmax does."""
+    x = np.asarray(x, np.float64)
+    V, U = np.asarray(V, np.float64), np.asarray(U, np.float64)
+    w = np.asarray(w, np.float64).reshape(-1)
+    t = np.tanh(x @ V.T + np.asarray(bV, np.float64))
+    g = 1.0 / (1.0 + np.exp(-(x @ U.T + np.asarray(bU, np.float64))))
+    a = (t * g) @ w + float(np.asarray(bw).reshape(-1)[0])                 # [S,L]
+    if mask is not None:
+        a = np.where(np.asarray(mask, bool), a, -np.inf)
+    with np.errstate(invalid="ignore"):
+        e = np.exp(a - a.max(-1, keepdims=True))
+        A = e / e.sum(-1, keepdims=True)
+    out = np.einsum("sl,sld->sd", A, x)
+    if want_cache:
+        return out, dict(x=x, t=t, g=g, A=A, V=V, U=U, w=w)
+    return out
+
+
+def mil_gated_pool_backward(dout, c):
+    x, t, g, A, V, U, w = c["x"], c["t"], c["g"], c["A"], c["V"], c["U"], c["w"]
+    dout = np.asarray(dout, np.float64)
+    dA = np.einsum("sd,sld->sl", dout, x)
+    ds = A * (dA - (A * dA).sum(-1, keepdims=True))
+    dpv = ds[..., None] * w * g * (1.0 - t * t)
+    dpu = ds[..., None] * w * t * g * (1.0 - g)
+    dx = A[..., None] * dout[:, None, :] + dpv @ V + dpu @ U
+    return dict(x=dx, V=np.einsum("slh,sld->hd", dpv, x), bV=dpv.sum((0, 1)), U=np.einsum("slh,sld->hd", dpu, x),
+                bU=dpu.sum((0, 1)), w=np.einsum("sl,slh->h", ds, t * g).reshape(1, -1), bw=np.array([ds.sum()]))
+
+
+def mil_hierarchical_pool_forward(x, mask, V, bV, U, bU, w, bw, want_cache=False):
+    """Two levels (:509-536): patch level over L per (b, n) without a mask, then the video level with the mask."""
+    x = np.asarray(x, np.float64)
+    B, N, L, D = x.shape
+    emb, c1 = mil_gated_pool_forward(x.reshape(B * N, L, D), None, V, bV, U, bU, w, bw, want_cache=True)
+    out, c2 = mil_gated_pool_forward(emb.reshape(B, N, D), mask, V, bV, U, bU, w, bw, want_cache=True)
+    return (out, (c1, c2)) if want_cache else out
+
+
+def mil_hierarchical_pool_backward(dout, caches):
+    c1, c2 = caches
+    g2 = mil_gated_pool_backward(dout, c2)
+    S, L, D = c1["x"].shape
+    g1 = mil_gated_pool_backward(g2["x"].reshape(S, D), c1)
+    out = {k: g1[k] + g2[k] for k in ("V", "bV", "U", "bU", "w", "bw")}
+    out["x"] = g1["x"].reshape(c2["x"].shape[0], c2["x"].shape[1], L, D)
+    return out

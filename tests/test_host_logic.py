@@ -324,6 +324,13 @@ def test_install_into_reference_registry():
         assert map_.AttentionPoolWithCLS is pkg.AttentionPoolWithCLS and map_.AttentionPool is pkg.AttentionPool
         if "models.video_encoder" in sys.modules:
             assert sys.modules["models.video_encoder"].AttentionPoolWithCLS is pkg.AttentionPoolWithCLS
+        # the gated-attention pooling methods of the probing head are rebound; CPU inputs keep the reference's
+        import models.multi_instance_linear_probing as mil
+        assert hasattr(mil.MultiInstanceLinearProbing._attention_pooling, "reference")
+        assert hasattr(mil.MultiInstanceLinearProbing._hierarchical_attention_pooling, "reference")
+        probe = mil.MultiInstanceLinearProbing(32, {"h": 2}, pooling_mode="attention", attention_hidden=8)
+        xs = torch.randn(2, 3, 32)
+        assert torch.equal(probe._pool_instances(xs), type(probe)._attention_pooling.reference(probe, xs, torch.ones(2, 3, dtype=torch.bool)))
         assert urm.compute_mrr is pkg.retrieval_metrics.compute_mrr and urm.compute_map is pkg.retrieval_metrics.compute_map
         assert "utils.retrieval_metrics" in rep["metrics"] or "utils.retrieval_metrics" in pkg.install("/root/reference")["metrics"]
     finally:

@@ -194,6 +194,28 @@ def test_query_pool_oracle(name):
     _close(grads["attn_query"], g["g_attn_query"], 1e-9, 1e-12)
 
 
+MILPOOL = ["milpool_b5_n6_d64_h32_mask", "milpool_b3_n4_d128_h128", "milpool_b2_n3_l20_d64_h24_mask"]
+
+
+@pytest.mark.parametrize("name", MILPOOL)
+def test_mil_gated_pool_oracle(name):
+    """Oracle of the gated-attention MIL pooling against MultiInstanceLinearProbing._pool_instances of the reference
+    (models/multi_instance_linear_probing.py:493-536; [B, N, D] and the two-level [B, N, L, D] case)."""
+    g = _load(name)
+    mask = g["mask"] if bool(g["has_mask"]) else None
+    args = (g["x"], mask, g["V"], g["bV"], g["U"], g["bU"], g["w"], g["bw"])
+    if g["x"].ndim == 4:
+        out, cache = to.mil_hierarchical_pool_forward(*args, want_cache=True)
+        grads = to.mil_hierarchical_pool_backward(g["go"], cache)
+    else:
+        out, cache = to.mil_gated_pool_forward(*args, want_cache=True)
+        grads = to.mil_gated_pool_backward(g["go"], cache)
+    _close(out, g["out"], 1e-10, 1e-12)
+    _close(grads["x"], g["dx"], 1e-9, 1e-12)
+    for k in ("V", "bV", "U", "bU", "w", "bw"):
+        _close(grads[k], g["g_" + k], 1e-9, 1e-11)
+
+
 # ---- dense multi-label retrieval metrics (SURVEY §8f #1): oracle pinned to utils/retrieval_metrics.py ----
 @pytest.mark.parametrize("name", ["dense_metrics_120x90_g1", "dense_metrics_200x300_g4", "dense_metrics_64x7_g3"])
 def test_dense_metrics_oracle_matches_reference(name):

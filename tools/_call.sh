@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-for v in 256_2 256_4 512_2 512_4; do
-  cp build/variants/lib_$v.so deepcoro_clip_b200/libb200clip.so
-  timeout 200 python tools/gpu_xfblock_time.py $v 2>&1 | grep -v Warning | tail -2
-done 2>&1 | tee gpurun_out/xfblock_variants.log
-timeout 300 python tools/gpu_check_xfblock.py 2>&1 | grep -v Warning | tail -12
+timeout 600 python -m pytest tests/test_gpu_milpool.py -x -q 2>&1 | tail -8
+timeout 600 python tools/gpu_check_milpool.py 2>&1 | grep -v Warning | tee gpurun_out/r02_milpool_check.log | tail -12
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mil_(gate_fwd|dx|dw|dpre|pool_fwd|dA)_kernel" -c 6 -f -o gpurun_out/r02_milpool python tools/gpu_milpool_step.py 128 1 > gpurun_out/ncu_mil.log 2>&1; tail -3 gpurun_out/ncu_mil.log
