@@ -456,6 +456,23 @@ int b200clip_xfblock_wgrad(const float* a, int64_t lda, const float* b, int64_t 
   return xfblock_wgrad(a, lda, b, ldb, dw, db, J, I, R, a2, xhat, dgamma, dbeta, D2, S(stream));
 }
 
+int b200clip_aggregator_sizes(int B, int N, int D, int heads, int F, int64_t* sizes) {
+  if (!sizes || B < 1 || !xfblock_ok(N, D, heads, F)) return B2_EINVAL;
+  long long t[3];
+  aggregator_sizes(B, N, D, heads, F, t);
+  for (int i = 0; i < 3; ++i) sizes[i] = t[i];
+  return B2_OK;
+}
+
+int b200clip_aggregator(int backward, const void* const* ptrs, int depth, int B, int N, int D, int heads, int F,
+                        const float* eps_host, float drop_p, const int64_t* seeds_host, int64_t mask_sb, int64_t x_sb,
+                        int64_t x_sn, int pos_rows, void* stream) {
+  if (drop_p < 0.f || drop_p >= 1.f || depth < 1 || depth > 64) return B2_EINVAL;
+  long long seeds[64];
+  for (int i = 0; i < depth; ++i) seeds[i] = seeds_host ? seeds_host[i] : 0;
+  return aggregator(backward, ptrs, depth, B, N, D, heads, F, eps_host, drop_p, seeds, mask_sb, x_sb, x_sn, pos_rows, S(stream));
+}
+
 int b200clip_milpool_ok(int L, int D, int Hd) { return milpool_ok(L, D, Hd) ? 1 : 0; }
 
 int b200clip_milpool_plan(int S, int L, int D, int Hd, int* plan) {

@@ -213,6 +213,11 @@ int xfblock(int backward, const void* const* ptrs, int B, int N, int D, int H, i
 int xfblock_wgrad(const float* a, long long lda, const float* bm, long long ldb, float* dw, float* db, int J, int I, int R,
                   const float* a2, const float* xh, float* dg, float* dbeta, int D2, cudaStream_t s);
 
+void aggregator_sizes(int B, int N, int D, int H, int F, long long* sizes);
+int aggregator(int backward, const void* const* ptrs, int depth, int B, int N, int D, int H, int F, const float* eps,
+               float drop_p, const long long* seeds, long long mask_sb, long long x_sb, long long x_sn, int pos_rows,
+               cudaStream_t s);
+
 // milpool.cu: gated-attention pooling of the multi-instance probing head (fp32)
 bool milpool_ok(int L, int D, int Hd);
 void milpool_plan(int S, int L, int D, int Hd, int* plan);

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) mil_ds_kernel(MilParams p) {
 }
 
 // ---- dx = drop(A) dout + dpre [V; U] : 128 rows x 128 columns per CTA, K = 2 Hd ------------------------------------------
-__global__ void __launch_bounds__(MG_THREADS) mil_dx_kernel(MilParams p) {
+__global__ void __launch_bounds__(MG_THREADS, 2) mil_dx_kernel(MilParams p) {
   __shared__ __align__(16) float sA[2 * MG_BK * MG_LD], sB[2 * MG_BK * MG_LD];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const long long r0 = (long long)blockIdx.x * MG_BM;
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(MG_THREADS) mil_dx_kernel(MilParams p) {
 }
 
 // ---- d[V; U] partial products over the row range of blockIdx.z : 128 gate columns x 128 input columns --------------------
-__global__ void __launch_bounds__(MG_THREADS) mil_dw_kernel(MilParams p) {
+__global__ void __launch_bounds__(MG_THREADS, 2) mil_dw_kernel(MilParams p) {
   __shared__ __align__(16) float sA[2 * MG_BK * MG_LD], sB[2 * MG_BK * MG_LD];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int c0 = blockIdx.x * 128, n0 = blockIdx.y * 128, Hd = p.Hd;
@@ -355,13 +355,28 @@ __global__ void __launch_bounds__(MG_THREADS) mil_dw_kernel(MilParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  // rows of slab kt are fetched in order, so (sequence, instance) of a thread's two rows advance by 16 per call instead of
+  // a 64-bit division per load
+  long long rs[2];
+  int rl[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const long long r = rbeg + krow + 8 * h;
+    rs[h] = r / p.L;
+    rl[h] = (int)(r % p.L);
+  }
   auto fetch = [&](int kt) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const long long r = rbeg + (long long)kt * MG_BK + krow + 8 * h;
       const bool rok = r < rend;
       ra[h] = rok && cok ? mg_ld4(p.dpre + r * (2ll * Hd) + c0 + q * 4) : zero;
-      rb[h] = rok && nok ? mg_ld4(mil_xrow(p, r) + n0 + q * 4) : zero;
+      rb[h] = rok && nok ? mg_ld4(p.x + rs[h] * p.sx_seq + rl[h] * p.sx_tok + n0 + q * 4) : zero;
+      rl[h] += MG_BK;
+      while (rl[h] >= p.L) {
+        rl[h] -= p.L;
+        ++rs[h];
+      }
     }
   };
   auto commit = [&](float* As, float* Bs) {
@@ -486,7 +501,8 @@ void milpool_plan(int S, int L, int D, int Hd, int* plan) {
   int P = 1;
   if (L >= 256 && S < 296) P = (int)std::max(1ll, std::min<long long>(std::min(16, L / 128), (296 + S - 1) / S));
   const int tiles = ((2 * Hd + 127) / 128) * ((D + 127) / 128);
-  const int Z = (int)std::max(1ll, std::min<long long>(std::min<long long>((R + 255) / 256, (444 + tiles - 1) / tiles), 64));
+  // one full wave of the weight-gradient product: 2 CTAs per SM x 148 SMs = 296 tiles (a partial second wave costs a whole one)
+  const int Z = (int)std::max(1ll, std::min<long long>((R + 255) / 256, std::max(1, 296 / tiles)));
   plan[0] = P;
   plan[1] = Z;
   plan[2] = (int)((R + MG_FCH - 1) / MG_FCH);

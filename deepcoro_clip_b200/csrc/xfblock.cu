@@ -561,6 +561,27 @@ __global__ void __launch_bounds__(WG_THREADS) xfblock_wgrad_kernel(WgParams p) {
   if (blockIdx.z == 0 && threadIdx.x < 8 && j0 + threadIdx.x < p.J && p.db) p.db[j0 + threadIdx.x] = bsum;
 }
 
+
+// acts0[b, n, :] = x[b, n, :] (+ pos[n, :]): the positional add in front of the first block
+__global__ void agg_addpos_kernel(const float* __restrict__ x, long long sb, long long sn, const float* __restrict__ pos,
+                                  float* __restrict__ out, int B, int N, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N * D) return;
+  const int d = (int)(i % D), n = (int)((i / D) % N);
+  const long long b = i / ((long long)N * D);
+  out[i] = x[b * sb + n * sn + d] + (pos ? pos[(long long)n * D + d] : 0.f);
+}
+
+// gpos[n, :] = sum_b dx[b, n, :] for n < N, 0 for the unused rows of the positional table
+__global__ void agg_posgrad_kernel(const float* __restrict__ dx, float* __restrict__ gpos, int B, int N, int D, int rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * D) return;
+  float t = 0.f;
+  if (i < (long long)N * D)
+    for (int b = 0; b < B; ++b) t += dx[(long long)b * N * D + i];
+  gpos[i] = t;
+}
+
 }  // namespace b2
 
 namespace b2host {
@@ -612,6 +633,85 @@ int xfblock_wgrad(const float* a, long long lda, const float* bm, long long ldb,
   WgParams p{a, lda, bm, ldb, dw, db, J, I, R, a2, xh, dg, dbeta, D2};
   const int gx = max((J + 7) / 8, dg ? (D2 + WG_THREADS - 1) / WG_THREADS : 1);
   xfblock_wgrad_kernel<<<dim3(gx, dg ? 2 : 1, (I + 4 * WG_THREADS - 1) / (4 * WG_THREADS)), WG_THREADS, 0, s>>>(p);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+
+// ---- the whole aggregator step as one host call (EnhancedVideoAggregator.forward with depth >= 1, reference
+// models/video_aggregator.py:128-158): positional add, the blocks, final LayerNorm + query pool; and its backward --------
+static long long al64(long long n) { return (n + 63) / 64 * 64; }
+
+// sizes[0] = floats saved per block by the forward, [1] = floats of backward work space, [2] = parameter-gradient floats
+// per block (packed in the order ln1.w ln1.b in_proj.w in_proj.b out_proj.w out_proj.b ln2.w ln2.b fc1.w fc1.b fc2.w fc2.b)
+void aggregator_sizes(int B, int N, int D, int H, int F, long long* sizes) {
+  const long long R = (long long)B * N;
+  sizes[0] = 6 * al64(R * D) + 2 * al64(R) + al64(3 * R * D) + al64((long long)B * H * N * N) + 2 * al64(R * F);
+  sizes[1] = 4 * al64(R * D) + al64(R * F) + al64(3 * R * D);
+  sizes[2] = 4ll * D * D + 2ll * F * D + 9ll * D + F;
+}
+
+int aggregator(int backward, const void* const* q, int depth, int B, int N, int D, int H, int F, const float* eps,
+               float drop_p, const long long* seeds, long long mask_sb, long long x_sb, long long x_sn, int pos_rows,
+               cudaStream_t s) {
+  if (!q || !eps || !seeds || depth < 1 || B < 1 || !xfblock_ok(N, D, H, F)) return B2_EINVAL;
+  auto f = [&](int i) { return const_cast<float*>(reinterpret_cast<const float*>(q[i])); };
+  for (int i : {3, 4, 6, 7, 8})
+    if (!q[i]) return B2_EINVAL;
+  for (int i = 15; i < 15 + 12 * depth; ++i)
+    if (!q[i]) return B2_EINVAL;
+  if (backward ? (!q[9] || !q[10] || !q[11] || !q[12] || !q[14] || (q[1] && !q[13])) : (!q[0] || !q[5])) return B2_EINVAL;
+  const long long R = (long long)B * N, act = R * D;
+  long long sz[3];
+  aggregator_sizes(B, N, D, H, F, sz);
+  const unsigned char* mask = reinterpret_cast<const unsigned char*>(q[2]);
+  auto block = [&](int i, XbParams& p) {
+    const void* const* w = q + 15 + 12 * i;
+    auto g = [&](int j) { return reinterpret_cast<const float*>(w[j]); };
+    float* c = f(4) + (long long)i * sz[0];
+    p = XbParams{};
+    p.x = f(3) + (long long)i * act; p.out = f(3) + (long long)(i + 1) * act; p.mask = mask; p.mb = mask_sb;
+    p.ln1w = g(0); p.ln1b = g(1); p.w_in = g(2); p.b_in = g(3); p.w_o = g(4); p.b_o = g(5);
+    p.ln2w = g(6); p.ln2b = g(7); p.w1 = g(8); p.b1 = g(9); p.w2 = g(10); p.b2 = g(11);
+    p.eps1 = eps[2 * i]; p.eps2 = eps[2 * i + 1];
+    p.xhat1 = c; c += al64(R * D); p.rstd1 = c; c += al64(R); p.h1 = c; c += al64(R * D); p.qkv = c; c += al64(3 * R * D);
+    p.attn = c; c += al64((long long)B * H * N * N); p.o = c; c += al64(R * D); p.x1 = c; c += al64(R * D);
+    p.xhat2 = c; c += al64(R * D); p.rstd2 = c; c += al64(R); p.h2 = c; c += al64(R * D); p.z = c; c += al64(R * F); p.u = c;
+    p.B = B; p.N = N; p.D = D; p.H = H; p.F = F; p.drop_p = drop_p; p.seed = (unsigned long long)seeds[i];
+  };
+  XbParams p;
+  if (!backward) {
+    agg_addpos_kernel<<<(unsigned)((act + 255) / 256), 256, 0, s>>>(f(0), x_sb, x_sn, f(1), f(3), B, N, D);
+    for (int i = 0; i < depth; ++i) {
+      block(i, p);
+      if (int rc = xfblock_run(0, p, s)) return rc;
+    }
+    return querypool(0, f(3) + (long long)depth * act, (long long)N * D, D, nullptr, f(6), f(7), f(8), mask, mask_sb, B, N, D,
+                     eps[2 * depth], f(5), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s);
+  }
+  float* dact = f(10);
+  float* tail = f(12);
+  if (cudaMemsetAsync(tail, 0, 3ull * D * sizeof(float), s) != cudaSuccess) return B2_ECUDA;
+  if (int rc = querypool(1, f(3) + (long long)depth * act, (long long)N * D, D, nullptr, f(6), f(7), f(8), mask, mask_sb, B, N, D,
+                         eps[2 * depth], nullptr, f(9), dact + (depth & 1) * act, nullptr, tail, tail + D, tail + 2 * D, s))
+    return rc;
+  for (int i = depth - 1; i >= 0; --i) {
+    block(i, p);
+    float* c = f(11);
+    p.dout = dact + ((i + 1) & 1) * act; p.dx = dact + (i & 1) * act;
+    p.d_f2 = c; c += al64(R * D); p.d_z = c; c += al64(R * F); p.d_ao = c; c += al64(R * D); p.d_qkv = c; c += al64(3 * R * D);
+    p.d_h2 = c; c += al64(R * D); p.d_h1 = c;
+    if (int rc = xfblock_run(1, p, s)) return rc;
+    float* g = f(14) + (long long)i * sz[2];
+    float *ln1w = g, *ln1b = ln1w + D, *w_in = ln1b + D, *b_in = w_in + 3ll * D * D, *w_o = b_in + 3 * D, *b_o = w_o + (long long)D * D,
+          *ln2w = b_o + D, *ln2b = ln2w + D, *w1 = ln2b + D, *b1 = w1 + (long long)F * D, *w2 = b1 + F, *b2 = w2 + (long long)D * F;
+    int rc = xfblock_wgrad(p.d_f2, D, p.u, F, w2, b2, D, F, (int)R, nullptr, nullptr, nullptr, nullptr, 0, s);
+    if (!rc) rc = xfblock_wgrad(p.d_z, F, p.h2, D, w1, b1, F, D, (int)R, p.d_h2, p.xhat2, ln2w, ln2b, D, s);
+    if (!rc) rc = xfblock_wgrad(p.d_ao, D, p.o, D, w_o, b_o, D, D, (int)R, nullptr, nullptr, nullptr, nullptr, 0, s);
+    if (!rc) rc = xfblock_wgrad(p.d_qkv, 3 * D, p.h1, D, w_in, b_in, 3 * D, D, (int)R, p.d_h1, p.xhat1, ln1w, ln1b, D, s);
+    if (rc) return rc;
+  }
+  if (q[13])
+    agg_posgrad_kernel<<<(unsigned)(((long long)pos_rows * D + 255) / 256), 256, 0, s>>>(dact, f(13), B, N, D, pos_rows);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -9,6 +9,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+import ctypes
 import os
 
 from . import ops
@@ -69,73 +70,179 @@ def _al(n: int) -> int:
     return (n + 63) // 64 * 64
 
 
+_SAVED = ("xhat1", "rstd1", "h1", "qkv", "attn", "o", "x1", "xhat2", "rstd2", "h2", "z", "u")
+_WORK = ("d_f2", "d_z", "d_ao", "d_qkv", "d_h2", "d_h1")
+_LAYOUTS: dict = {}
+
+
+def _xf_layout(B: int, N: int, D: int, H: int, F_: int):
+    """Byte offsets of the saved tensors / backward work buffers of one block inside their flat fp32 workspaces."""
+    key = (B, N, D, H, F_)
+    lay = _LAYOUTS.get(key)
+    if lay is None:
+        R = B * N
+        sizes = dict(xhat1=R * D, rstd1=R, h1=R * D, qkv=3 * R * D, attn=B * H * N * N, o=R * D, x1=R * D, xhat2=R * D, rstd2=R,
+                     h2=R * D, z=R * F_, u=R * F_, d_f2=R * D, d_z=R * F_, d_ao=R * D, d_qkv=3 * R * D, d_h2=R * D, d_h1=R * D)
+        off, cur = {}, 0
+        for k in _SAVED:
+            off[k] = 4 * cur
+            cur += _al(sizes[k])
+        n_saved, cur = cur, 0
+        for k in _WORK:
+            off[k] = 4 * cur
+            cur += _al(sizes[k])
+        lay = _LAYOUTS[key] = (off, n_saved, cur)
+    return lay
+
+
+def _xf_forward(x_ptr, out_ptr, mk, params, ws_ptr, off, dims, eps1, eps2, drop_p, seed, st):
+    B, N, D, H, F_ = dims
+    table = (ctypes.c_void_p * 35)(x_ptr, out_ptr, mk.data_ptr() if mk is not None else None, *[t.data_ptr() for t in params],
+                                   *[ws_ptr + off[k] for k in _SAVED], *([None] * 8))
+    call("xfblock", 0, table, B, N, D, H, F_, eps1, eps2, drop_p, seed, i64(mk.stride(0) if mk is not None else 0), st)
+
+
+# element counts of the twelve parameter gradients of a block, in _fused_params order
+def _xf_grad_sizes(D: int, F_: int):
+    return (D, D, 3 * D * D, 3 * D, D * D, D, D, D, F_ * D, F_, D * F_, D)
+
+
+def _xf_backward(x_ptr, dout_ptr, dx_ptr, mk, params, ws_ptr, ws2_ptr, off, dims, eps1, eps2, drop_p, seed, g_ptr, st):
+    """Backward cluster kernel + the four weight-gradient launches; the twelve gradients are written at g_ptr in
+    _fused_params order (fp32, packed)."""
+    B, N, D, H, F_ = dims
+    R = B * N
+    table = (ctypes.c_void_p * 35)(x_ptr, None, mk.data_ptr() if mk is not None else None, *[t.data_ptr() for t in params],
+                                   *[ws_ptr + off[k] for k in _SAVED], dout_ptr, dx_ptr, *[ws2_ptr + off[k] for k in _WORK])
+    call("xfblock", 1, table, B, N, D, H, F_, eps1, eps2, drop_p, seed, i64(mk.stride(0) if mk is not None else 0), st)
+    g, cur = [], g_ptr
+    for n in _xf_grad_sizes(D, F_):
+        g.append(cur)
+        cur += 4 * n
+    ln1w, ln1b, w_in, b_in, w_o, b_o, ln2w, ln2b, w1, b1, w2, b2 = g
+    w, q = ws_ptr, ws2_ptr
+    call("xfblock_wgrad", q + off["d_f2"], i64(D), w + off["u"], i64(F_), w2, b2, D, F_, R, None, None, None, None, 0, st)
+    call("xfblock_wgrad", q + off["d_z"], i64(F_), w + off["h2"], i64(D), w1, b1, F_, D, R, q + off["d_h2"], w + off["xhat2"],
+         ln2w, ln2b, D, st)
+    call("xfblock_wgrad", q + off["d_ao"], i64(D), w + off["o"], i64(D), w_o, b_o, D, D, R, None, None, None, None, 0, st)
+    call("xfblock_wgrad", q + off["d_qkv"], i64(3 * D), w + off["h1"], i64(D), w_in, b_in, 3 * D, D, R, q + off["d_h1"],
+         w + off["xhat1"], ln1w, ln1b, D, st)
+
+
+def _grad_views(flat, params):
+    """Views of the packed gradient buffer with the shapes of ``params`` (one split + reshapes)."""
+    return [v.view(p.shape) for v, p in zip(torch.split(flat, [p.numel() for p in params]), params)]
+
+
 class _XfBlockFn(torch.autograd.Function):
     """One transformer block of the aggregator in 1 + 5 library launches (csrc/xfblock.cu): the forward cluster kernel,
     the backward cluster kernel and four rank-(B N) weight-gradient updates."""
 
     @staticmethod
-    def forward(ctx, x, mask, ln1w, ln1b, w_in, b_in, w_o, b_o, ln2w, ln2b, w1, b1, w2, b2, H, eps1, eps2, drop_p, seed):
+    def forward(ctx, x, mask, H, eps1, eps2, drop_p, seed, *params):
         B, N, D = x.shape
-        F_ = w1.shape[0]
+        dims = (B, N, D, H, params[8].shape[0])
         dev = x.device
-        R = B * N
         xc = x.detach().contiguous()
         mk = mask.to(torch.bool).contiguous().view(torch.uint8) if mask is not None else None
-        seg = (("xhat1", R * D), ("rstd1", R), ("h1", R * D), ("qkv", 3 * R * D), ("attn", B * H * N * N), ("o", R * D),
-               ("x1", R * D), ("xhat2", R * D), ("rstd2", R), ("h2", R * D), ("z", R * F_), ("u", R * F_))
-        off, cur = {}, 0
-        for name, n in seg:
-            off[name] = 4 * cur
-            cur += _al(n)
-        ws = torch.empty(cur, dtype=torch.float32, device=dev)
+        off, n_saved, _ = _xf_layout(*dims)
+        ws = torch.empty(n_saved, dtype=torch.float32, device=dev)
         out = torch.empty((B, N, D), dtype=torch.float32, device=dev)
-        w = ws.data_ptr()
-        ptrs = [xc.data_ptr(), out.data_ptr(), mk.data_ptr() if mk is not None else None] + \
-               [t.data_ptr() for t in (ln1w, ln1b, w_in, b_in, w_o, b_o, ln2w, ln2b, w1, b1, w2, b2)] + \
-               [w + off[k] for k, _ in seg] + [None] * 8
-        import ctypes
-        table = (ctypes.c_void_p * 35)(*ptrs)
-        call("xfblock", 0, table, B, N, D, H, F_, float(eps1), float(eps2), float(drop_p), int(seed),
-             i64(mk.stride(0) if mk is not None else 0), stream_ptr(dev))
-        ctx.save_for_backward(xc, mk, ws, ln1w, ln1b, w_in, b_in, w_o, b_o, ln2w, ln2b, w1, b1, w2, b2)
-        ctx.cfg = (B, N, D, H, F_, float(eps1), float(eps2), float(drop_p), int(seed), off, [k for k, _ in seg])
+        _xf_forward(xc.data_ptr(), out.data_ptr(), mk, params, ws.data_ptr(), off, dims, float(eps1), float(eps2), float(drop_p),
+                    int(seed), stream_ptr(dev))
+        ctx.save_for_backward(xc, mk, ws, *params)
+        ctx.cfg = (dims, float(eps1), float(eps2), float(drop_p), int(seed))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        import ctypes
-        xc, mk, ws, ln1w, ln1b, w_in, b_in, w_o, b_o, ln2w, ln2b, w1, b1, w2, b2 = ctx.saved_tensors
-        B, N, D, H, F_, eps1, eps2, drop_p, seed, off, names = ctx.cfg
+        xc, mk, ws, *params = ctx.saved_tensors
+        dims, eps1, eps2, drop_p, seed = ctx.cfg
+        B, N, D, H, F_ = dims
         dev = xc.device
-        R = B * N
-        st = stream_ptr(dev)
+        off, _, n_work = _xf_layout(*dims)
         dout = dout.float().contiguous()
-        seg2 = (("d_f2", R * D), ("d_z", R * F_), ("d_ao", R * D), ("d_qkv", 3 * R * D), ("d_h2", R * D), ("d_h1", R * D))
-        o2, cur = {}, 0
-        for name, n in seg2:
-            o2[name] = 4 * cur
-            cur += _al(n)
-        ws2 = torch.empty(cur, dtype=torch.float32, device=dev)
+        ws2 = torch.empty(n_work, dtype=torch.float32, device=dev)
         dx = torch.empty((B, N, D), dtype=torch.float32, device=dev)
-        w, q = ws.data_ptr(), ws2.data_ptr()
-        ptrs = [xc.data_ptr(), None, mk.data_ptr() if mk is not None else None] + \
-               [t.data_ptr() for t in (ln1w, ln1b, w_in, b_in, w_o, b_o, ln2w, ln2b, w1, b1, w2, b2)] + \
-               [w + off[k] for k in names] + [dout.data_ptr(), dx.data_ptr()] + [q + o2[k] for k, _ in seg2]
-        table = (ctypes.c_void_p * 35)(*ptrs)
-        call("xfblock", 1, table, B, N, D, H, F_, eps1, eps2, drop_p, seed, i64(mk.stride(0) if mk is not None else 0), st)
-        g = {k: torch.empty_like(t) for k, t in (("ln1w", ln1w), ("ln1b", ln1b), ("w_in", w_in), ("b_in", b_in), ("w_o", w_o),
-                                                 ("b_o", b_o), ("ln2w", ln2w), ("ln2b", ln2b), ("w1", w1), ("b1", b1),
-                                                 ("w2", w2), ("b2", b2))}
-        call("xfblock_wgrad", q + o2["d_f2"], i64(D), w + off["u"], i64(F_), g["w2"], g["b2"], D, F_, R, None, None, None,
-             None, 0, st)
-        call("xfblock_wgrad", q + o2["d_z"], i64(F_), w + off["h2"], i64(D), g["w1"], g["b1"], F_, D, R, q + o2["d_h2"],
-             w + off["xhat2"], g["ln2w"], g["ln2b"], D, st)
-        call("xfblock_wgrad", q + o2["d_ao"], i64(D), w + off["o"], i64(D), g["w_o"], g["b_o"], D, D, R, None, None, None,
-             None, 0, st)
-        call("xfblock_wgrad", q + o2["d_qkv"], i64(3 * D), w + off["h1"], i64(D), g["w_in"], g["b_in"], 3 * D, D, R,
-             q + o2["d_h1"], w + off["xhat1"], g["ln1w"], g["ln1b"], D, st)
-        return (dx, None, g["ln1w"], g["ln1b"], g["w_in"], g["b_in"], g["w_o"], g["b_o"], g["ln2w"], g["ln2b"], g["w1"],
-                g["b1"], g["w2"], g["b2"], None, None, None, None, None)
+        flat = torch.empty(sum(_xf_grad_sizes(D, F_)), dtype=torch.float32, device=dev)
+        _xf_backward(xc.data_ptr(), dout.data_ptr(), dx.data_ptr(), mk, params, ws.data_ptr(), ws2.data_ptr(), off, dims, eps1,
+                     eps2, drop_p, seed, flat.data_ptr(), stream_ptr(dev))
+        return (dx, None, None, None, None, None, None, *_grad_views(flat, params))
+
+
+_AGG_SIZES: dict = {}
+
+
+def _agg_sizes(B: int, N: int, D: int, H: int, F_: int):
+    key = (B, N, D, H, F_)
+    sz = _AGG_SIZES.get(key)
+    if sz is None:
+        buf = (ctypes.c_int64 * 3)()
+        call("aggregator_sizes", B, N, D, H, F_, buf)
+        sz = _AGG_SIZES[key] = tuple(buf)
+    return sz
+
+
+class _AggregatorFn(torch.autograd.Function):
+    """The whole EnhancedVideoAggregator.forward with depth >= 1 as ONE autograd node and ONE library call per direction
+    (b200clip_aggregator: positional add, the blocks of csrc/xfblock.cu, LayerNorm + query-pool tail of csrc/querypool.cu;
+    2 + depth kernels forward, 2 + 5 depth + 2 backward). Same kernels as the per-module path; what it removes is the Python /
+    autograd / allocator work between the launches, which bounded the eager step (840-950 us eager against 556 us
+    graph-replayed at 8 studies x 4 views, depth 2)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, pos, ln_w, ln_b, query, H, eps, drop_p, seeds, *params):
+        B, N, D = x.shape
+        depth = len(params) // 12
+        dims = (B, N, D, H, params[8].shape[0])
+        dev = x.device
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        mk = mask.to(torch.bool).contiguous().view(torch.uint8) if mask is not None else None
+        n_saved, _, _ = _agg_sizes(*dims)
+        acts = torch.empty((depth + 1, B, N, D), dtype=torch.float32, device=dev)
+        ws = torch.empty(depth * n_saved, dtype=torch.float32, device=dev)
+        out = torch.empty((B, D), dtype=torch.float32, device=dev)
+        table = (ctypes.c_void_p * (15 + 12 * depth))(
+            x.data_ptr(), None if pos is None else pos.data_ptr(), None if mk is None else mk.data_ptr(), acts.data_ptr(),
+            ws.data_ptr(), out.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), query.data_ptr(), None, None, None, None, None, None,
+            *[t.data_ptr() for t in params])
+        eps_c = (ctypes.c_float * len(eps))(*eps)
+        seeds_c = (ctypes.c_int64 * depth)(*seeds)
+        mask_sb = mk.stride(0) if mk is not None else 0
+        pos_rows = pos.shape[1] if pos is not None else 0
+        call("aggregator", 0, table, depth, *dims, eps_c, drop_p, seeds_c, mask_sb, x.stride(0), x.stride(1), pos_rows,
+             stream_ptr(dev))
+        ctx.save_for_backward(acts, mk, ws, pos, ln_w, ln_b, query, *params)
+        ctx.cfg = (dims, depth, eps_c, drop_p, seeds_c, mask_sb, pos_rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        acts, mk, ws, pos, ln_w, ln_b, query, *params = ctx.saved_tensors
+        dims, depth, eps_c, drop_p, seeds_c, mask_sb, pos_rows = ctx.cfg
+        B, N, D, H, F_ = dims
+        dev = acts.device
+        _, n_work, per_block = _agg_sizes(*dims)
+        n_pos = pos_rows * D if pos is not None else 0
+        # returned gradients: d(final_ln.weight | final_ln.bias | attn_query) | d pos_encoding | block gradients
+        grads = torch.empty(3 * D + n_pos + depth * per_block, dtype=torch.float32, device=dev)
+        scratch = torch.empty(2 * B * N * D + n_work, dtype=torch.float32, device=dev)        # dact [2, B, N, D] | work
+        if dout.dtype != torch.float32 or not dout.is_contiguous():
+            dout = dout.float().contiguous()
+        gp, sp = grads.data_ptr(), scratch.data_ptr()
+        table = (ctypes.c_void_p * (15 + 12 * depth))(
+            None, None if pos is None else pos.data_ptr(), None if mk is None else mk.data_ptr(), acts.data_ptr(), ws.data_ptr(),
+            None, ln_w.data_ptr(), ln_b.data_ptr(), query.data_ptr(), dout.data_ptr(), sp, sp + 8 * B * N * D, gp,
+            gp + 12 * D if pos is not None else None, gp + 4 * (3 * D + n_pos), *[t.data_ptr() for t in params])
+        call("aggregator", 1, table, depth, *dims, eps_c, drop_p, seeds_c, mask_sb, 0, 0, pos_rows, stream_ptr(dev))
+        dx = scratch[:B * N * D].view(B, N, D)
+        sizes = [D, D, D] + ([n_pos] if pos is not None else []) + [t.numel() for t in params]
+        parts = torch.split(grads, sizes)
+        k = 4 if pos is not None else 3
+        gpos = parts[3].view(pos.shape) if pos is not None else None
+        gparams = [v if t.dim() == 1 else v.view(t.shape) for v, t in zip(parts[k:], params)]
+        return (dx, None, gpos, parts[0], parts[1], parts[2].view(query.shape), None, None, None, None, *gparams)
 
 
 class TransformerBlock(nn.Module):
@@ -160,16 +267,22 @@ class TransformerBlock(nn.Module):
                 self.attn.out_proj.weight, self.attn.out_proj.bias, self.norm2.weight, self.norm2.bias,
                 self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight, self.mlp[3].bias)
 
+    def _fused_eligible(self, x) -> bool:
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and os.environ.get("B200CLIP_XFBLOCK", "1") != "0"):
+            return False
+        params = self._fused_params()
+        return bool(lib().b200clip_xfblock_ok(x.shape[1], x.shape[2], self.attn.num_heads, self.mlp[0].out_features)
+                    and all(p is not None and p.dtype == torch.float32 and p.is_contiguous() for p in params))
+
+    def _drop_seed(self):
+        drop_p = float(self.dropout1.p) if self.training else 0.0
+        return drop_p, (int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0.0 else 0)
+
     def forward(self, x, key_padding_mask: Optional[torch.Tensor] = None):
-        if x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and os.environ.get("B200CLIP_XFBLOCK", "1") != "0":
-            B, N, D = x.shape
-            params = self._fused_params()
-            if (lib().b200clip_xfblock_ok(N, D, self.attn.num_heads, self.mlp[0].out_features)
-                    and all(p is not None and p.dtype == torch.float32 and p.is_contiguous() for p in params)):
-                drop_p = float(self.dropout1.p) if self.training else 0.0
-                seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0.0 else 0
-                return _XfBlockFn.apply(x, key_padding_mask, *params, self.attn.num_heads, self.norm1.eps, self.norm2.eps,
-                                        drop_p, seed)
+        if self._fused_eligible(x):
+            drop_p, seed = self._drop_seed()
+            return _XfBlockFn.apply(x, key_padding_mask, self.attn.num_heads, self.norm1.eps, self.norm2.eps, drop_p, seed,
+                                    *self._fused_params())
         h = self.norm1(x)
         a, _ = self.attn(h, h, h, key_padding_mask=key_padding_mask)
         x = x + self.dropout1(a)
@@ -200,6 +313,32 @@ class EnhancedVideoAggregator(nn.Module):
             mask = mask.to(torch.bool)
         pos = self.pos_encoding
         if len(self.blocks) > 0:
+            if x.is_cuda and x.dtype == torch.float32 and os.environ.get("B200CLIP_AGG_FUSED", "1") != "0" \
+                    and os.environ.get("B200CLIP_XFBLOCK", "1") != "0":
+                plan = self.__dict__.get("_plan")
+                if plan is None:       # (module, parameter name) of everything the fused step reads; heads, widths, eps
+                    blk0 = self.blocks[0]
+                    owners = []
+                    for b in self.blocks:
+                        owners += [(b.norm1, "weight"), (b.norm1, "bias"), (b.attn, "in_proj_weight"), (b.attn, "in_proj_bias"),
+                                   (b.attn.out_proj, "weight"), (b.attn.out_proj, "bias"), (b.norm2, "weight"), (b.norm2, "bias"),
+                                   (b.mlp[0], "weight"), (b.mlp[0], "bias"), (b.mlp[3], "weight"), (b.mlp[3], "bias")]
+                    uniform = all(b.attn.num_heads == blk0.attn.num_heads and b.mlp[0].out_features == blk0.mlp[0].out_features
+                                  and b.dropout1.p == blk0.dropout1.p for b in self.blocks)
+                    eps = tuple(float(e) for b in self.blocks for e in (b.norm1.eps, b.norm2.eps)) + (float(self.final_ln.eps),)
+                    plan = self.__dict__["_plan"] = (owners, uniform, blk0.attn.num_heads, blk0.mlp[0].out_features, eps,
+                                                     float(blk0.dropout1.p), self.final_ln, list(self.blocks))
+                owners, uniform, heads, width, eps, p_drop, fln, blocks = plan
+                params = [m._parameters[n] for m, n in owners]
+                tail = (fln._parameters["weight"], fln._parameters["bias"], self.attn_query)
+                if (uniform and lib().b200clip_xfblock_ok(N, D, heads, width)
+                        and all(t is not None and t.dtype == torch.float32 and t.is_contiguous() for t in params)
+                        and all(t is not None and t.dtype == torch.float32 and t.is_contiguous() for t in tail)
+                        and (pos is None or (pos.dtype == torch.float32 and pos.is_contiguous()))):
+                    drop_p = p_drop if self.training else 0.0
+                    # one draw per block, like TransformerBlock._drop_seed: the same seeds as the per-module path
+                    seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0.0 else 0 for _ in blocks]
+                    return _AggregatorFn.apply(x, mask, pos, *tail, heads, eps, drop_p, seeds, *params)
             if pos is not None:
                 x = x + pos[:, :N, :]
                 pos = None

@@ -559,6 +559,25 @@ int b200clip_xfblock(int backward, const void* const* ptrs, int B, int N, int D,
 int b200clip_xfblock_wgrad(const float* a, int64_t lda, const float* b, int64_t ldb, float* dw, float* db, int J, int I,
                            int R, const float* a2, const float* xhat, float* dgamma, float* dbeta, int D2, void* stream);
 
+/* The whole EnhancedVideoAggregator.forward with depth >= 1 blocks (models/video_aggregator.py:128-158) as ONE host call per
+ * direction: positional add, `depth` x xfblock, final LayerNorm + query pool (K9); backward = the reverse with every parameter
+ * gradient. Same kernels as the separate entry points; what this removes is host work between the launches.
+ *   aggregator_sizes: sizes[0] = floats the forward saves per block, [1] = floats of backward work space, [2] = parameter-
+ *                     gradient floats per block, packed in the order of ptrs[15 ..].
+ *   ptrs: HOST array of 15 + 12 depth device pointers —
+ *     [0] x [B,N,D] (strides x_sb, x_sn; forward)   [1] pos_encoding [pos_rows, D] or NULL   [2] mask [B,N] bytes or NULL
+ *     [3] acts [depth + 1, B, N, D] (acts[0] = x + pos, acts[i + 1] = output of block i; kept for the backward)
+ *     [4] saved [depth, sizes[0]]   [5] out [B, D]   [6] final_ln.weight [7] final_ln.bias [8] attn_query [D]
+ *     backward: [9] dout [B,D]  [10] dact [2, B, N, D] (dx = dact[0] on return)  [11] work [sizes[1]]
+ *               [12] d(final_ln.weight | final_ln.bias | attn_query) [3 D]  [13] d pos_encoding [pos_rows, D] (NULL iff [1] is)
+ *               [14] block gradients [depth, sizes[2]]
+ *     [15 + 12 i ..] the parameters of block i in the order of xfblock ptrs[3 .. 14].
+ *   eps_host: HOST array {eps1, eps2} per block, then the final LayerNorm's; seeds_host: HOST array of `depth` dropout seeds. */
+int b200clip_aggregator_sizes(int B, int N, int D, int heads, int F, int64_t* sizes);
+int b200clip_aggregator(int backward, const void* const* ptrs, int depth, int B, int N, int D, int heads, int F,
+                        const float* eps_host, float drop_p, const int64_t* seeds_host, int64_t mask_sb, int64_t x_sb,
+                        int64_t x_sn, int pos_rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K11  Gated-attention MIL pooling (models/multi_instance_linear_probing.py:493-507 `_attention_pooling`, and each of the
  *      two levels of :509-536 `_hierarchical_attention_pooling`), fp32:

@@ -109,3 +109,41 @@ def test_aggregator_with_fused_blocks_matches_pytorch_blocks(env):
     for k, v in res["0"][2].items():
         if v.norm() > 0:
             assert _rel(res["1"][2][k], v) <= 1e-4, k
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_whole_aggregator_node_equals_per_block_nodes(env, train):
+    """The single autograd node over positional add + blocks + tail launches the same kernels as the per-module path
+    (B200CLIP_AGG_FUSED=0): same output bit for bit, gradients up to the atomics of the tail; with dropout the same seeds
+    are drawn in the same order."""
+    from deepcoro_clip_b200 import EnhancedVideoAggregator
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(7)
+    agg = EnhancedVideoAggregator(512, dropout=0.2, aggregator_depth=3).to(dev).train(train)
+    xa = torch.randn(6, 5, 512, device=dev)
+    mask = torch.zeros(6, 5, dtype=torch.bool, device=dev)
+    mask[2, 3:] = True
+    ga = torch.randn(6, 512, device=dev)
+    res = {}
+    saved = os.environ.get("B200CLIP_AGG_FUSED")
+    try:
+        for mode in ("1", "0"):
+            os.environ["B200CLIP_AGG_FUSED"] = mode
+            agg.zero_grad(set_to_none=True)
+            xr = xa.clone().requires_grad_(True)
+            torch.manual_seed(11)
+            out = agg(xr, mask)
+            out.backward(ga)
+            res[mode] = (out.detach(), xr.grad, {k: v.grad.clone() for k, v in agg.named_parameters() if v.grad is not None})
+    finally:
+        if saved is None:
+            os.environ.pop("B200CLIP_AGG_FUSED", None)
+        else:
+            os.environ["B200CLIP_AGG_FUSED"] = saved
+    assert torch.equal(res["1"][0], res["0"][0])
+    assert _rel(res["1"][1], res["0"][1]) <= 1e-6
+    assert set(res["1"][2]) == set(res["0"][2])
+    for k, v in res["0"][2].items():
+        assert res["1"][2][k].shape == v.shape
+        if v.norm() > 0:
+            assert _rel(res["1"][2][k], v) <= 1e-6, k
