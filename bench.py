@@ -788,8 +788,29 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
         xa.grad = None
         agg(xa).backward(ga)
     ms = t_ms(agg_fb)
-    res["aggregator_fwd_bwd"] = {"ms": ms, "note": "EnhancedVideoAggregator (depth 2, train mode): 2 x (1 + 5) cluster-kernel launches "
-                                                   "+ the query-pool tail; latency-bound, [8, 4, 512] fp32"}
+    res["aggregator_fwd_bwd"] = {"ms": ms, "note": "EnhancedVideoAggregator (depth 2, train mode): one library call per direction "
+                                                   "(positional add, 2 x (1 + 5) block launches, query-pool tail); "
+                                                   "latency-bound, [8, 4, 512] fp32"}
+    # gated-attention MIL pooling of the probing head on patch tokens, two levels (not part of `whole`)
+    try:
+        from deepcoro_clip_b200 import GatedAttentionPooling
+        Lm, Hd = 1568, 128
+        mil = GatedAttentionPooling(D, Hd).to(dev)
+        xm = torch.randn(S, V, Lm, D, device=dev, requires_grad=True)
+        gm = torch.randn(S, D, device=dev)
+
+        def mil_fb():
+            xm.grad = None
+            mil(xm).backward(gm)
+        ms = t_ms(mil_fb)
+        fl = 3 * 2.0 * S * V * Lm * D * 2 * Hd
+        res["mil_gated_pool_fwd_bwd"] = {
+            "ms": ms, "algorithmic_flops": fl, "TFLOPps": fl / ms / 1e9, "frac_fp32_fma": fl / ms / 1e9 / (148 * 128 * 2 * 1.965e-3),
+            "note": f"[{S}, {V}, {Lm}, {D}] fp32, hidden {Hd}: three [R x 512] x [512 x 256] products on fp32 FMA tiles (fp32 parity "
+                    "with the reference rules out one-pass bf16 / tf32 tensor-core products); fraction of 148 SMs x 128 FMA x 1.965 GHz"}
+        del xm, mil
+    except Exception as e:
+        res["mil_gated_pool_fwd_bwd"] = {"error": f"{type(e).__name__}: {e}"}
     ms = t_ms(whole, steps)
     total_bytes = 2 * b_rope + 4 * bx
     out = {"metric": "study-mode token path fwd+bwd (config 3)", "value": S * ctx.world / (ms * 1e-3), "unit": "studies/s",
