@@ -105,6 +105,22 @@ def call(name: str, *args) -> None:
         raise B200ClipError(f"b200clip_{name} failed: {msg} (code {rc})")
 
 
+def try_call(name: str, *args) -> bool:
+    """Like ``call`` for entry points that answer B2_ENOSYS (-38) when a shape does not qualify for a specialised kernel:
+    returns False in that case (nothing was launched) so the caller can take the general path; raises on any other error."""
+    global LAUNCHES
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(lib(), "b200clip_" + name)
+    rc = fn(*[a.data_ptr() if isinstance(a, _Tensor) else a for a in args])
+    if rc == -38:
+        return False
+    LAUNCHES += 1
+    if rc != 0:
+        raise B200ClipError(f"b200clip_{name} failed: {lib().b200clip_strerror(rc).decode()} (code {rc})")
+    return True
+
+
 def stream_ptr(device=None) -> int:
     """Raw cudaStream_t of torch's current stream on ``device``."""
     idx = device.index if isinstance(device, torch.device) and device.index is not None else (

@@ -58,6 +58,8 @@ struct BwParams {
   int ldd;
   double* scal;                // [4] fp64 atomics: 0: sum G*f(S), 1: sum softplus(L), 2: sum G ; may be null
   const float* dyn;            // optional device block from dyn_prep: overrides scale2/shift2/inv_tau/bias/out_scale
+  int gstore;                  // logits_bwd3.cu only: every G tile is also stored (bf16, scaled by gnorm) through the kernel's
+                               // fourth tensor map, for the transposed product of gt_gemm.cu
   int stable;                  // CLIP / gated only, read from dyn[11] inside the kernel: rowscale / colscale hold log2-domain
                                // log-sum-exps (minus log2 c) and G = 2^(L2 - rowscale_i) + 2^(L2 - colscale_j), two
                                // exponentials that are each <= c, instead of P * (c / rowsum_i + c / colsum_j) with the

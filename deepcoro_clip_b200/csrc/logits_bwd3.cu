@@ -52,6 +52,14 @@ struct Bw3Cfg {
   static_assert(kSmem <= 232448, "shared memory budget");
 };
 
+__device__ __forceinline__ void bw3_tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bw3_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bw3_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bw3_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -160,7 +168,7 @@ struct Bw3Sched {
 template <int kMode, int kNJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BW_THREADS, 1)
 bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmYs,
-           const __grid_constant__ CUtensorMap tmYo, BwParams p) {
+           const __grid_constant__ CUtensorMap tmYo, const __grid_constant__ CUtensorMap tmG, BwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using C = Bw3Cfg<kNJ>;
@@ -413,6 +421,11 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const bool has_diag = !BwIsSiglip<kMode>::value && p.ydiag != 0.f && dlo > -BW_BM && dlo < kNJ;
         const uint32_t cs_addr = smem_u32(col_s) + (warp - 4) * 32 * 4;
         const uint32_t ga = grow_addr + buf * C::kGBuf;
+        if (kNJ == 256 && p.gstore) {
+          // this warp's TMA store of tile t - 2 (same G buffer) has finished reading shared memory
+          if (lane == 0) bw3_bulk_wait_read1();
+          __syncwarp();
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int cc = ctile + 32 * c;
@@ -456,6 +469,13 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
+        if (kNJ == 256 && p.gstore && lane == 0) {
+          // the warp's own [32 rows x 64 columns] box of the tile: rows 32 (q & 1) .. of chunk ctile / 64 (4 KB, contiguous,
+          // 1024-byte aligned: the swizzle pattern repeats every 8 rows) -> G[row0 .., j kNJ + ctile ..]; clipped at the edges
+          bw3_tma_store_2d(&tmG, smem_u32(gbuf) + buf * C::kGBuf + (ctile >> 6) * BW3_XCHUNK + (q & 1) * 32 * 128,
+                           j * kNJ + ctile, xt * BW_BM + BW3_XROWS * (int)rank + (q & 1) * 32);
+          bw3_bulk_commit();
+        }
         if (lane == 0) mbar_arrive_cluster(buf ? gready_remote1 : gready_remote0);
         if (p.scal) {
           dtacc += (double)tacc;
@@ -520,6 +540,7 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
   }
 
+  if (kNJ == 256 && p.gstore && warp >= 4 && lane == 0) bw3_bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -535,8 +556,8 @@ namespace b2host {
 using namespace b2;
 
 template <int kMode, int kNJ>
-static int launch_bw3(const CUtensorMap& tmX, const CUtensorMap& tmYs, const CUtensorMap& tmYo, const BwParams& p,
-                      int grid, cudaStream_t stream) {
+static int launch_bw3(const CUtensorMap& tmX, const CUtensorMap& tmYs, const CUtensorMap& tmYo, const CUtensorMap& tmG,
+                      const BwParams& p, int grid, cudaStream_t stream) {
   static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[current_device() & 63];   // cudaFuncSetAttribute is per device
   constexpr int smem = Bw3Cfg<kNJ>::kSmem;
@@ -545,7 +566,7 @@ static int launch_bw3(const CUtensorMap& tmX, const CUtensorMap& tmYs, const CUt
       return B2_ECUDA;
     attr_done = true;
   }
-  bw3_kernel<kMode, kNJ><<<grid, BW_THREADS, smem, stream>>>(tmX, tmYs, tmYo, p);
+  bw3_kernel<kMode, kNJ><<<grid, BW_THREADS, smem, stream>>>(tmX, tmYs, tmYo, tmG, p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 
@@ -555,12 +576,13 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
                       int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
                       const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
                       const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
-                      int nseg_hint, cudaStream_t stream) {
+                      int nseg_hint, cudaStream_t stream, void* gstore, int ldg) {
   if (hp || hi_off != 0 || Kp != Dp || Dp % 256 || Dp > 768 || sm_count() < 2) return B2_ENOSYS;
   // 256 Y rows per step whenever the X panel and the S buffers allow it (Kp <= 512); B200CLIP_BWD3_NJ=128 forces 128
   static const bool nj256_ok = [] { const char* e = getenv("B200CLIP_BWD3_NJ"); return !(e && e[0] == '1' && e[1] == '2'); }();
   const int NJ = (Kp <= 512 && nj256_ok) ? 256 : 128;
   if (mode != BW_CLIP && mode != BW_GATED && mode != BW_SIGLIP) return B2_ENOSYS;
+  if (gstore && (NJ != 256 || ldg % 8 || ldg < Ny)) return B2_ENOSYS;       // G tiles are stored by the 256-column variant only
   BwParams p;
   p.Nx = Nx; p.Ny = Ny; p.Kp = Kp; p.Dp = Dp; p.D = D; p.hi_off = 0; p.ydiag = ydiag; p.diag_off = diag_off;
   p.diag_corr = diag_corr;
@@ -577,20 +599,39 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
   p.gnorm = gnorm > 0.f ? gnorm : 1.f;
   p.hp = 0;
   p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f; p.stable = 0;
-  p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn;
-  CUtensorMap tmX, tmYs, tmYo;
+  p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn; p.gstore = gstore ? 1 : 0;
+  CUtensorMap tmX, tmYs, tmYo, tmG;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, Kp, ldx, BW3_XROWS))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmYs, Y, Ny, Kp, ldy, NJ / 2))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmYo, Y, Ny, Kp, ldy, 128))) return rc;
+  if (gstore) {
+    if ((rc = make_tmap_bf16_2d(&tmG, gstore, Nx, Ny, ldg, 32))) return rc;
+  } else {
+    tmG = tmX;      // never dereferenced
+  }
   const long long items = p.nseg > 0 ? (long long)p.x_tiles * p.nseg : (long long)p.x_tiles * p.y_tiles;
   const int grid = 2 * (int)(items < clusters ? items : clusters);
-#define LAUNCH3(M) (NJ == 256 ? launch_bw3<M, 256>(tmX, tmYs, tmYo, p, grid, stream) \
-                              : launch_bw3<M, 128>(tmX, tmYs, tmYo, p, grid, stream))
+#define LAUNCH3(M) (NJ == 256 ? launch_bw3<M, 256>(tmX, tmYs, tmYo, tmG, p, grid, stream) \
+                              : launch_bw3<M, 128>(tmX, tmYs, tmYo, tmG, p, grid, stream))
   if (mode == BW_CLIP) return LAUNCH3(BW_CLIP);
   if (mode == BW_GATED) return LAUNCH3(BW_GATED);
   return LAUNCH3(BW_SIGLIP);
 #undef LAUNCH3
+}
+
+// Both gradients of the softmax / gated contrastive step from ONE recompute of the logits: dX += G Y as above with every G tile
+// stored (bf16, [Nx, ldg]) and dY += G^T X by gt_gemm.cu. Square single-GPU problems whose G fits the caller's buffer; the
+// diagonal corrections of the Y side equal those of the X side (same G_ii). B2_ENOSYS when the shape does not qualify.
+int logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
+                    float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn, float ydiag,
+                    int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy, double* scal, void* G, int ldg,
+                    cudaStream_t stream) {
+  if (!G || !dY || !dyn || (mode != BW_CLIP && mode != BW_GATED) || Dp > 512) return B2_ENOSYS;
+  int rc = logits_bwd_pair64(mode, X, Y, Nx, Ny, Kp, Dp, D, 0, ldx, ldy, 0.f, 0.f, 0.f, 0.f, wneg_c, rowscale, colscale, 0.f,
+                             gnorm, 0, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal, 0, stream, G, ldg);
+  if (rc) return rc;
+  return gt_gemm(G, ldg, Nx, Ny, X, ldx, Dp, D, dyn, gnorm, dY, lddy, stream);
 }
 
 }  // namespace b2host

@@ -17,6 +17,7 @@ sums are all-reduced and the per-row sums all-gathered (three [N]-sized collecti
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -27,6 +28,13 @@ from . import dist_plan, ops, symm
 from ._lib import B200ClipError
 
 BW_CLIP, BW_GATED, BW_SIGLIP, BW_SIGLIP_ENT = 0, 1, 2, 3
+_GSTORE_MAX_BYTES = 4 << 30   # largest stored gradient-tile matrix (bf16 [N, N]: 2 GiB at N = 32,768) of the one-recompute backward
+
+
+def _al64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
 _LOCAL = "local"   # cfg['group'] marker: never gather, even inside an initialised process group
 
 
@@ -212,7 +220,30 @@ class _ClipLossFn(torch.autograd.Function):
             ctx.scal_used = True
         ydiag = (1.0 - eps) / N
         lt_work = None
-        if need_v or need_lt:
+        # One recompute of the logits for both gradients (single GPU, plain bf16 operands, D <= 512): the video-side pass stores
+        # its G tiles (bf16, 2 N^2 bytes) and the text-side gradient is the plain product G^T V̂ (csrc/gt_gemm.cu) instead of a
+        # second pass with a second recompute. B200CLIP_GSTORE=0 keeps the two passes (A/B measurements).
+        both = False
+        if (W == 1 and need_v and need_t and K == Kp and Kp in (256, 512) and 2 * B * _al64(N) <= _GSTORE_MAX_BYTES
+                and os.environ.get("B200CLIP_GSTORE", "1") != "0"):
+            dVh, dTh = ws[:nbd].view(B, D), ws[nbd:2 * nbd].view(B, D)
+            dcv = ws[2 * nbd:2 * nbd + 2 * B]
+            G = torch.empty((B, _al64(N)), dtype=torch.bfloat16, device=dev)
+            both = ops.logits_bwd_both(mode, vop, tall, B, N, K, D, dyn, rowscale_all, colscale_all, dVh, dTh, scal, G,
+                                       ydiag=ydiag, diag_off=0, diag_corr=dcv, gnorm=2.0 * N)
+            del G
+        if both:
+            dV = ops.l2norm_backward(dVh, video, vinv, other_x=text, other_inv=tinv, other_hi=top[:, K - Kp:], diag_corr=dcv,
+                                     usum=tsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3], dev_gmul=gmul)
+            # G_jj is the same number on both sides: the text rows take the same diagonal corrections
+            dT = ops.l2norm_backward(dTh, text, tinv, other_x=video, other_inv=vinv, other_hi=vop[:, K - Kp:], diag_corr=dcv,
+                                     usum=vsum, ucoef=-eps / (N * N), dev_omul=dyn[2:3], dev_gmul=gmul)
+            if dV.dtype != video.dtype:
+                dV = dV.to(video.dtype)
+            if dT.dtype != text.dtype:
+                dT = dT.to(text.dtype)
+            need_v = need_t = False        # done; d log_temp below
+        if need_v or (need_lt and not both):
             dVh = ws[:nbd].view(B, D)
             dcv = ws[2 * nbd:2 * nbd + 2 * B]
             ops.logits_bwd(mode, vop, tall, B, N, K, Kp, D, dyn, rowscale_all[lo:hi], colscale_all, dVh, scal,

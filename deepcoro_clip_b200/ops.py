@@ -7,7 +7,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import DTYPE_CODE, call, i64, stream_ptr
+from ._lib import DTYPE_CODE, call, i64, stream_ptr, try_call
 
 LOG2E = math.log2(math.e)
 GATED_BOUND = 0.7310585786300049  # max of s*sigmoid(s) on [-1, 1] (at s = 1)
@@ -114,6 +114,15 @@ def logits_bwd(mode, X, Y, Nx, Ny, K, Dp, D, dyn, rowscale, colscale, dX, scal, 
     call("logits_bwd", mode, X, Y, Nx, Ny, K, Dp, D, K - Dp, X.stride(0), Y.stride(0), 0.0, 0.0, 0.0, 0.0, float(wneg_c),
          rowscale, colscale, 0.0, float(gnorm), int(hp), dyn, float(ydiag), int(diag_off), diag_corr, dX, dX.stride(0), scal, nseg, stream_ptr(X.device))
 
+
+
+def logits_bwd_both(mode, X, Y, Nx, Ny, K, D, dyn, rowscale, colscale, dX, dY, scal, G, *, ydiag=0.0, diag_off=0, diag_corr=None,
+                    gnorm=1.0) -> bool:
+    """dX += G Y and dY += G^T X from one recompute of the logits (G kept in the caller's bf16 buffer ``G`` [Nx, >= Ny]).
+    False when the shape does not qualify (nothing launched)."""
+    return try_call("logits_bwd_both", mode, X, Y, Nx, Ny, K, K, D, X.stride(0), Y.stride(0), 0.0, rowscale, colscale,
+                    float(gnorm), dyn, float(ydiag), int(diag_off), diag_corr, dX, dX.stride(0), dY, dY.stride(0), scal, G,
+                    G.stride(0), stream_ptr(X.device))
 
 call = call  # re-export for the loss module
 i64 = i64

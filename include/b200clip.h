@@ -178,6 +178,18 @@ int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, 
                         const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal, int nseg_hint,
                         void* stream);
 
+/* K3b  Both gradients of the softmax (mode 0) / gated (mode 1) contrastive step from ONE recompute of the logits
+ *      (utils/loss/contrastive.py:150-164 backward: dV̂ = G T̂ / tau, dT̂ = G^T V̂ / tau). logits_bwd as above for dX with every
+ *      G tile also stored through TMA (bf16, scaled by gnorm, row-major G [Nx, ldg], ldg % 8 == 0, caller-owned: 2 Nx ldg
+ *      bytes), then dY[Ny, D] += dyn[2] / gnorm * G^T X as a tcgen05 product with both operands MN-major (csrc/gt_gemm.cu).
+ *      Executed work 8 instead of 10 Nx Ny D per step. Plain bf16 operands, Kp == Dp in {256, 512}, dyn required;
+ *      B2_ENOSYS otherwise (the caller then launches logits_bwd twice). dX and dY are ACCUMULATED (caller zeroes);
+ *      diag_corr of the Y side equals the one written here when the problem is square with diag_off = 0. */
+int b200clip_logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
+                             float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn,
+                             float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy,
+                             double* scal, void* G, int ldg, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Device-side scalar plumbing (no host sync on log_temp / bias).
  *   dyn_prep     : tau = exp(log_temp) [clamped at clamp_min if > 0: contrastive.py:153, 266]; bound = max of

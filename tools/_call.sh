@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_xfblock.py tests/test_gpu_tokens.py -x -q 2>&1 | tail -4
-timeout 300 python tools/gpu_check_xfblock.py 2>&1 | grep -v Warning | tail -4
-timeout 300 python tools/gpu_host_profile_agg.py 2>&1 | grep -v Warning > gpurun_out/agg_host.log; grep "host" gpurun_out/agg_host.log
+timeout 900 python -m pytest tests/test_gpu_clip_loss.py -x -q 2>&1 | tail -6
+timeout 600 python bench.py --steps 10 --warmup 3 --legs none 2>&1 | tail -1 | tee gpurun_out/bench_gstore.json | cut -c1-1200
+B200CLIP_GSTORE=0 timeout 600 python bench.py --steps 10 --warmup 3 --legs none 2>&1 | tail -1 | cut -c1-400
