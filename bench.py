@@ -407,6 +407,39 @@ def bwd_kernel_roofline(ctx: Ctx, B: int, N: int, D: int, log_temp, step_ms: flo
     else:
         kname = "bw2_kernel / bw_kernel<CLIP> (128-row kernels: S recomputed per 256-column slice of D)"
         executed = (1 + (Kp + 255) // 256) * achieved
+    # the step's backward as it runs on one GPU (loss.py): ONE recompute — bw3 storing its G tiles + the transposed product
+    # of gt_gemm.cu — timed as the pair and the product alone
+    pair = None
+    if bw3 and Kp <= 512 and B == N and ctx.world == 1 and os.environ.get("B200CLIP_GSTORE", "1") != "0":
+        try:
+            G = torch.empty(ops.gstore_elems(B, N), dtype=torch.bfloat16, device=dev)
+            dY = torch.zeros(N, D, device=dev)
+
+            def both():
+                ops.logits_bwd_both(0, x, y, B, N, Kp, D, dyn, rs, cs, dX, dY, scal, G, gnorm=2.0 * N)
+
+            def gemm():
+                ops.call("gt_gemm", G, G.numel(), B, N, x, x.stride(0), Kp, D, dyn, 2.0 * N, dY, dY.stride(0), ops.stream_ptr(dev))
+            tm = {}
+            for nm, fn in (("pair", both), ("gemm", gemm)):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                tm[nm] = e0.elapsed_time(e1) / reps
+            pair = {"kernels": "bw3_kernel<CLIP, 256> with TMA stores of its G tiles (bf16, N^2 elements in [64 x 64] blocks) + gt_gemm_kernel (dY = G^T X, "
+                               "cta_group::2 M=256, both operands MN-major)",
+                    "ms_pair": tm["pair"], "ms_gt_gemm": tm["gemm"], "ms_bw3_with_store": tm["pair"] - tm["gemm"],
+                    "pair_algorithmic_tflops": 2 * alg / (tm["pair"] * 1e-3) / 1e12,
+                    "pair_frac": 2 * alg / (tm["pair"] * 1e-3) / 1e12 / bf16_burst,
+                    "gt_gemm_tflops": alg / (tm["gemm"] * 1e-3) / 1e12, "gt_gemm_frac": alg / (tm["gemm"] * 1e-3) / 1e12 / bf16_burst,
+                    "note": "both gradients from one recompute: executed 6*B*N*D for 4*B*N*D algorithmic (two passes: 8)"}
+            del G, dY
+        except Exception as e:
+            pair = {"error": f"{type(e).__name__}: {e}"}
     traffic = None
     prof = ROOT / "profiles" / ncu_summary if ncu_summary else None
     if prof is not None and prof.exists() and ctx.world == 1:
@@ -422,8 +455,15 @@ def bwd_kernel_roofline(ctx: Ctx, B: int, N: int, D: int, log_temp, step_ms: flo
     roof["step_algorithmic_tflops"] = step_alg / (step_ms * 1e-3) / 1e12
     roof["step_frac_of_peak"] = roof["step_algorithmic_tflops"] / bf16_burst
     roof["step_peak"] = bf16_burst
-    roof["step_note"] = ("the step executes 10*N^2*D FLOP for 6*N^2*D algorithmic (S is formed in the forward and once per "
-                         "gradient side), so 0.6 of the burst peak is the ceiling of the step fraction")
+    if pair is not None:
+        roof["backward_one_recompute"] = pair
+    if pair is not None and "error" not in pair:
+        roof["step_note"] = ("one GPU: the step executes 8*N^2*D FLOP for 6*N^2*D algorithmic (S in the forward and once in the "
+                             "backward, whose G tiles feed both gradients), so 0.75 of the burst peak is the ceiling of the step "
+                             "fraction; `frac` above is the dominant kernel alone WITHOUT the G stores")
+    else:
+        roof["step_note"] = ("the step executes 10*N^2*D FLOP for 6*N^2*D algorithmic (S is formed in the forward and once per "
+                             "gradient side), so 0.6 of the burst peak is the ceiling of the step fraction")
     return roof
 
 

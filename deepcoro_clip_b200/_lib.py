@@ -19,7 +19,7 @@ _HEADER = _PKG.parent / "include" / "b200clip.h"
 _lib = None
 LAUNCHES = 0      # number of b200clip_* kernel-launching calls made by this process (bench.py reports it)
 _NO_LAUNCH = {"abi_version", "strerror", "sm_count", "attnpool_splits", "attnpool_bwd_splits", "retrieval_segments",
-              "rowlse_slots", "milpool_plan"}
+              "rowlse_slots", "milpool_plan", "gstore_elems", "aggregator_sizes"}
 
 DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 

@@ -137,11 +137,22 @@ int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, 
 int b200clip_logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
                              float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn,
                              float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy,
-                             double* scal, void* G, int ldg, void* stream) {
+                             double* scal, void* G, int64_t g_elems, void* stream) {
   if (!X || !Y || !dX || !dY || !G || !rowscale || !colscale || !dyn) return B2_EINVAL;
   if (Nx <= 0 || Ny <= 0 || Kp != Dp || Dp <= 0 || Dp % 64 || D > Dp || D <= 0) return B2_EINVAL;
   return logits_bwd_both(mode, X, Y, Nx, Ny, Kp, Dp, D, ldx, ldy, wneg_c, rowscale, colscale, gnorm, dyn, ydiag, diag_off,
-                         diag_corr, dX, ldd, dY, lddy, scal, G, ldg, S(stream));
+                         diag_corr, dX, ldd, dY, lddy, scal, G, g_elems, S(stream));
+}
+
+int b200clip_gstore_elems(int Nx, int Ny, int64_t* elems) {
+  if (!elems || Nx <= 0 || Ny <= 0) return B2_EINVAL;
+  *elems = gstore_elems(Nx, Ny);
+  return B2_OK;
+}
+
+int b200clip_gt_gemm(const void* G, int64_t g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
+                     float gnorm, float* dY, int ldd, void* stream) {
+  return gt_gemm(G, g_elems, Nx, Ny, X, ldx, Dp, D, dyn, gnorm, dY, ldd, S(stream));
 }
 
 int b200clip_dyn_prep(const float* log_temp, const float* bias, float clamp_min, float bound, float* dyn,

@@ -3,13 +3,19 @@
 // logits_bwd3.cu forms every G tile (recompute S, softmax both ways, round to bf16) for dX += G Y. The text-side gradient
 // dY = G^T X used to be a second launch of the same kernel with the operands swapped — a second S recompute, 4 B N D executed
 // FLOP for 2 B N D of work. When the whole G fits in HBM (2 B N bytes: 2 GB at 32k x 32k, single-GPU case) the first launch
-// stores its G tiles with TMA (bf16, row-major [Nx, ldg]) and this kernel does the plain product: executed work of the step
-// 8 instead of 10 B N D (SURVEY 8d counts 6).
+// stores its G tiles with TMA and this kernel does the plain product: executed work of the step 8 instead of 10 B N D
+// (SURVEY 8d counts 6).
+//
+// G layout (bf16): [64 x 64] blocks of 8 KB, block (ib, jb) = rows 64 ib .., columns 64 jb .. at element offset
+// (ib * nJB + jb) * 4096 with nJB = 4 * ceil(Ny / 256) and ib < 2 * ceil(Nx / 128); inside a block row r holds its 64 columns
+// as eight 16-byte units, unit u at position u ^ (r & 7) — the SWIZZLE_128B operand image logits_bwd3.cu already builds in
+// shared memory, so its store and this kernel's load are byte-for-byte copies of 4 / 16 KB (row-major G measured 0.33 ms
+// slower in the storing kernel: 32 row segments 2 Ny bytes apart per box). Blocks past the edges hold zeros.
 //
 //   cluster (2 CTAs) = one 256-row tile of dY (256 columns j of G); CTA rank r owns rows [128 r, 128 r + 128)
 //   tcgen05.mma.cta_group::2, M = 256, N = 256 per accumulator part (Dp / 256 parts: the whole output width in TMEM),
 //   K = 64 rows i of G per stage:
-//     A = G[i0 .. i0+63, j0 + 128 r .. +127] : MN-major (j contiguous), two [64 i x 64 j] SWIZZLE_128B boxes, LBO 8 KB
+//     A = G[i0 .. i0+63, j0 + 128 r .. +127] : MN-major (j contiguous), two consecutive [64 i x 64 j] blocks, LBO 8 KB
 //     B = X[i0 .. i0+63, 256 n + 128 r .. +127] : MN-major (d contiguous), two boxes per part — each CTA feeds half of N
 //   The flattened (tile, k-step) sequence is cut into one contiguous, equally long range per cluster (perfect balance:
 //   128 tiles on 74 clusters would otherwise be 1.73 waves); every piece drains with red.global.add into the zeroed dY.
@@ -31,7 +37,7 @@ struct GgParams {
   const float* dyn;      // dyn[2] = 1 / tau (device)
   float* dY;
   int ldd;
-  int tiles, ksteps;
+  int tiles, ksteps, njb;
 };
 
 struct GgSched {
@@ -109,8 +115,7 @@ gt_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           uint8_t* st = smem + slot * GG_STAGE;
           if (leader) mbar_expect_tx(&full_bar[slot], 2 * (2 + 2 * nparts) * GG_BOX);
           const int i0 = ks * GG_BK;
-          tma_load_2d_pair(st, &tmG, &full_bar[slot], j0, i0);
-          tma_load_2d_pair(st + GG_BOX, &tmG, &full_bar[slot], j0 + 64, i0);
+          tma_load_2d_pair(st, &tmG, &full_bar[slot], 0, (ks * p.njb + (j0 >> 6)) * 64);      // two blocks, 16 KB
           for (int n = 0; n < nparts; ++n) {
             const int d0 = 256 * n + 128 * (int)rank;
             tma_load_2d_pair(st + (2 + 2 * n) * GG_BOX, &tmX, &full_bar[slot], d0, i0);
@@ -209,12 +214,18 @@ gt_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
 namespace b2host {
 using namespace b2;
 
-// dY[Ny, D] (fp32, pitch ldd, pre-zeroed or holding a partial sum) += dyn[2] / gnorm * G^T X ; G [Nx, ldg] bf16 (ldg % 8 == 0),
-// X [Nx, ldx] bf16 operand panel of width Dp in {256, 512}. B2_ENOSYS for other widths.
-int gt_gemm(const void* G, int ldg, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn, float gnorm,
-            float* dY, int ldd, cudaStream_t stream) {
+long long gstore_elems(int Nx, int Ny) {
+  return 2ll * ((Nx + 127) / 128) * 4ll * ((Ny + 255) / 256) * 4096ll;
+}
+
+// dY[Ny, D] (fp32, pitch ldd, pre-zeroed or holding a partial sum) += dyn[2] / gnorm * G^T X ; G in the blocked layout above
+// (g_elems >= gstore_elems(Nx, Ny), 128-byte aligned), X [Nx, ldx] bf16 operand panel of width Dp in {256, 512}.
+// B2_ENOSYS for other widths.
+int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
+            float gnorm, float* dY, int ldd, cudaStream_t stream) {
   if (Dp % 256 || Dp > 512 || sm_count() < 2) return B2_ENOSYS;
-  if (!G || !X || !dyn || !dY || Nx < 1 || Ny < 1 || D < 1 || D > Dp || ldg % 8 || ldg < Ny) return B2_EINVAL;
+  if (!G || !X || !dyn || !dY || Nx < 1 || Ny < 1 || D < 1 || D > Dp) return B2_EINVAL;
+  if (g_elems < gstore_elems(Nx, Ny)) return B2_ENOMEM;
   static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[current_device() & 63];
   if (!attr_done) {
@@ -224,10 +235,11 @@ int gt_gemm(const void* G, int ldg, int Nx, int Ny, const void* X, int ldx, int 
   GgParams p;
   p.Nx = Nx; p.Ny = Ny; p.Dp = Dp; p.D = D; p.inv_gnorm = 1.f / (gnorm > 0.f ? gnorm : 1.f); p.dyn = dyn; p.dY = dY; p.ldd = ldd;
   p.tiles = (Ny + 255) / 256;
-  p.ksteps = (Nx + GG_BK - 1) / GG_BK;
+  p.ksteps = 2 * ((Nx + 127) / 128);      // every row block the storing kernel wrote (zeros past Nx)
+  p.njb = 4 * p.tiles;
   CUtensorMap tmG, tmX;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&tmG, G, Nx, Ny, ldg, 64))) return rc;
+  if ((rc = make_tmap_bf16_rows64(&tmG, G, (uint64_t)(gstore_elems(Nx, Ny) / 64), 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, Dp, ldx, 64))) return rc;
   const long long total = (long long)p.tiles * p.ksteps;
   const int clusters = sm_count() / 2;

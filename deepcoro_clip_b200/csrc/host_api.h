@@ -56,14 +56,15 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
                       int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
                       const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
                       const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
-                      int nseg_hint, cudaStream_t stream, void* gstore = nullptr, int ldg = 0);
+                      int nseg_hint, cudaStream_t stream, void* gstore = nullptr, long long g_elems = 0);
 int logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
                     float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn, float ydiag,
-                    int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy, double* scal, void* G, int ldg,
-                    cudaStream_t stream);
-// gt_gemm.cu: dY += dyn[2] / gnorm * G^T X from the stored bf16 gradient tiles
-int gt_gemm(const void* G, int ldg, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn, float gnorm,
-            float* dY, int ldd, cudaStream_t stream);
+                    int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy, double* scal, void* G,
+                    long long g_elems, cudaStream_t stream);
+// gt_gemm.cu: dY += dyn[2] / gnorm * G^T X from the stored bf16 gradient tiles (blocked layout, gstore_elems() elements)
+long long gstore_elems(int Nx, int Ny);
+int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
+            float gnorm, float* dY, int ldd, cudaStream_t stream);
 
 // attnpool_mma.cu: 16-bit inputs on mma.sync (heads <= 8, D % 128 == 0, D <= 1024, 16-byte aligned rows)
 bool attnpool_mma_ok(const void* x, int dtype, long long sb, long long sn, int D, int H);
@@ -256,6 +257,7 @@ int querypool(int backward, const float* x, long long sb, long long sn, const fl
 // tmap.cu
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                       uint32_t box_rows);
+int make_tmap_bf16_rows64(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows);
 int sm_count();
 int current_device();   // tmap.cu
 

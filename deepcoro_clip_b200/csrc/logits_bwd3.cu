@@ -52,9 +52,13 @@ struct Bw3Cfg {
   static_assert(kSmem <= 232448, "shared memory budget");
 };
 
+// TMA store with an evict-first L2 policy: the 2 N^2 bytes of G stream through L2 once and must not displace the Y operand
+// that every cluster keeps re-reading from it
 __device__ __forceinline__ void bw3_tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(x), "r"(y) : "memory");
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(x), "r"(y), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bw3_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bw3_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -469,14 +473,16 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(buf ? gready_remote1 : gready_remote0);
         if (kNJ == 256 && p.gstore && lane == 0) {
-          // the warp's own [32 rows x 64 columns] box of the tile: rows 32 (q & 1) .. of chunk ctile / 64 (4 KB, contiguous,
-          // 1024-byte aligned: the swizzle pattern repeats every 8 rows) -> G[row0 .., j kNJ + ctile ..]; clipped at the edges
-          bw3_tma_store_2d(&tmG, smem_u32(gbuf) + buf * C::kGBuf + (ctile >> 6) * BW3_XCHUNK + (q & 1) * 32 * 128,
-                           j * kNJ + ctile, xt * BW_BM + BW3_XROWS * (int)rank + (q & 1) * 32);
+          // the warp's own [32 rows x 64 columns] half of chunk ctile / 64: 4 KB, contiguous in shared memory, already in the
+          // SWIZZLE_128B operand layout -> copied byte for byte into block (row block 2 xt + rank, column block 4 j + chunk) of
+          // the blocked G buffer (8 KB per [64 x 64] block, gt_gemm.cu loads the blocks as its MN-major A operand): 4 KB
+          // sequential writes instead of 32 row segments 2 Ny bytes apart
+          bw3_tma_store_2d(&tmG, smem_u32(gbuf) + buf * C::kGBuf + (ctile >> 6) * BW3_XCHUNK + (q & 1) * 32 * 128, 0,
+                           ((2 * xt + (int)rank) * (4 * p.y_tiles) + 4 * j + (ctile >> 6)) * 64 + (q & 1) * 32);
           bw3_bulk_commit();
         }
-        if (lane == 0) mbar_arrive_cluster(buf ? gready_remote1 : gready_remote0);
         if (p.scal) {
           dtacc += (double)tacc;
           if (BwIsSiglip<kMode>::value) {
@@ -576,13 +582,14 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
                       int ldy, float scale2, float shift2, float inv_tau, float bias, float wneg_c,
                       const float* rowscale, const float* colscale, float out_scale, float gnorm, int hp,
                       const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal,
-                      int nseg_hint, cudaStream_t stream, void* gstore, int ldg) {
+                      int nseg_hint, cudaStream_t stream, void* gstore, long long g_elems) {
   if (hp || hi_off != 0 || Kp != Dp || Dp % 256 || Dp > 768 || sm_count() < 2) return B2_ENOSYS;
   // 256 Y rows per step whenever the X panel and the S buffers allow it (Kp <= 512); B200CLIP_BWD3_NJ=128 forces 128
   static const bool nj256_ok = [] { const char* e = getenv("B200CLIP_BWD3_NJ"); return !(e && e[0] == '1' && e[1] == '2'); }();
   const int NJ = (Kp <= 512 && nj256_ok) ? 256 : 128;
   if (mode != BW_CLIP && mode != BW_GATED && mode != BW_SIGLIP) return B2_ENOSYS;
-  if (gstore && (NJ != 256 || ldg % 8 || ldg < Ny)) return B2_ENOSYS;       // G tiles are stored by the 256-column variant only
+  if (gstore && NJ != 256) return B2_ENOSYS;       // G tiles are stored by the 256-column variant only
+  if (gstore && g_elems < gstore_elems(Nx, Ny)) return B2_ENOMEM;
   BwParams p;
   p.Nx = Nx; p.Ny = Ny; p.Kp = Kp; p.Dp = Dp; p.D = D; p.hi_off = 0; p.ydiag = ydiag; p.diag_off = diag_off;
   p.diag_corr = diag_corr;
@@ -606,7 +613,7 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
   if ((rc = make_tmap_bf16_2d(&tmYs, Y, Ny, Kp, ldy, NJ / 2))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmYo, Y, Ny, Kp, ldy, 128))) return rc;
   if (gstore) {
-    if ((rc = make_tmap_bf16_2d(&tmG, gstore, Nx, Ny, ldg, 32))) return rc;
+    if ((rc = make_tmap_bf16_rows64(&tmG, gstore, (uint64_t)(gstore_elems(Nx, Ny) / 64), 32))) return rc;
   } else {
     tmG = tmX;      // never dereferenced
   }
@@ -621,17 +628,17 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
 }
 
 // Both gradients of the softmax / gated contrastive step from ONE recompute of the logits: dX += G Y as above with every G tile
-// stored (bf16, [Nx, ldg]) and dY += G^T X by gt_gemm.cu. Square single-GPU problems whose G fits the caller's buffer; the
+// stored (bf16, blocked layout of gt_gemm.cu) and dY += G^T X by gt_gemm.cu. Square single-GPU problems whose G fits the caller's buffer; the
 // diagonal corrections of the Y side equal those of the X side (same G_ii). B2_ENOSYS when the shape does not qualify.
 int logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
                     float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn, float ydiag,
-                    int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy, double* scal, void* G, int ldg,
-                    cudaStream_t stream) {
+                    int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy, double* scal, void* G,
+                    long long g_elems, cudaStream_t stream) {
   if (!G || !dY || !dyn || (mode != BW_CLIP && mode != BW_GATED) || Dp > 512) return B2_ENOSYS;
   int rc = logits_bwd_pair64(mode, X, Y, Nx, Ny, Kp, Dp, D, 0, ldx, ldy, 0.f, 0.f, 0.f, 0.f, wneg_c, rowscale, colscale, 0.f,
-                             gnorm, 0, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal, 0, stream, G, ldg);
+                             gnorm, 0, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal, 0, stream, G, g_elems);
   if (rc) return rc;
-  return gt_gemm(G, ldg, Nx, Ny, X, ldx, Dp, D, dyn, gnorm, dY, lddy, stream);
+  return gt_gemm(G, g_elems, Nx, Ny, X, ldx, Dp, D, dyn, gnorm, dY, lddy, stream);
 }
 
 }  // namespace b2host

@@ -41,6 +41,22 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return r == CUDA_SUCCESS ? B2_OK : B2_EINVAL;
 }
 
+// Dense [rows, 64] bf16 matrix (row pitch 128 bytes), no swizzle: boxes of `box_rows` rows are copied byte for byte. Used
+// for buffers that already hold SWIZZLE_128B operand images (the stored gradient tiles of logits_bwd3.cu / gt_gemm.cu).
+int make_tmap_bf16_rows64(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return B2_ENOSYS;
+  if (!base || (reinterpret_cast<uintptr_t>(base) & 127) || box_rows == 0 || box_rows > 256 || rows == 0) return B2_EINVAL;
+  cuuint64_t gdim[2] = {64, rows};
+  cuuint64_t gstride[1] = {128};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B2_OK : B2_EINVAL;
+}
+
 int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);

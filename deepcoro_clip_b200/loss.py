@@ -31,10 +31,6 @@ BW_CLIP, BW_GATED, BW_SIGLIP, BW_SIGLIP_ENT = 0, 1, 2, 3
 _GSTORE_MAX_BYTES = 4 << 30   # largest stored gradient-tile matrix (bf16 [N, N]: 2 GiB at N = 32,768) of the one-recompute backward
 
 
-def _al64(n: int) -> int:
-    return (n + 63) // 64 * 64
-
-
 _LOCAL = "local"   # cfg['group'] marker: never gather, even inside an initialised process group
 
 
@@ -221,14 +217,14 @@ class _ClipLossFn(torch.autograd.Function):
         ydiag = (1.0 - eps) / N
         lt_work = None
         # One recompute of the logits for both gradients (single GPU, plain bf16 operands, D <= 512): the video-side pass stores
-        # its G tiles (bf16, 2 N^2 bytes) and the text-side gradient is the plain product G^T V̂ (csrc/gt_gemm.cu) instead of a
+        # its G tiles (bf16, 2 N^2 bytes, blocked layout) and the text-side gradient is the plain product G^T V̂ (csrc/gt_gemm.cu) instead of a
         # second pass with a second recompute. B200CLIP_GSTORE=0 keeps the two passes (A/B measurements).
         both = False
-        if (W == 1 and need_v and need_t and K == Kp and Kp in (256, 512) and 2 * B * _al64(N) <= _GSTORE_MAX_BYTES
+        if (W == 1 and need_v and need_t and K == Kp and Kp in (256, 512) and 2 * ops.gstore_elems(B, N) <= _GSTORE_MAX_BYTES
                 and os.environ.get("B200CLIP_GSTORE", "1") != "0"):
             dVh, dTh = ws[:nbd].view(B, D), ws[nbd:2 * nbd].view(B, D)
             dcv = ws[2 * nbd:2 * nbd + 2 * B]
-            G = torch.empty((B, _al64(N)), dtype=torch.bfloat16, device=dev)
+            G = torch.empty(ops.gstore_elems(B, N), dtype=torch.bfloat16, device=dev)
             both = ops.logits_bwd_both(mode, vop, tall, B, N, K, D, dyn, rowscale_all, colscale_all, dVh, dTh, scal, G,
                                        ydiag=ydiag, diag_off=0, diag_corr=dcv, gnorm=2.0 * N)
             del G

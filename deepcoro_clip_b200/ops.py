@@ -116,13 +116,19 @@ def logits_bwd(mode, X, Y, Nx, Ny, K, Dp, D, dyn, rowscale, colscale, dX, scal, 
 
 
 
+def gstore_elems(Nx: int, Ny: int) -> int:
+    """bf16 elements of the blocked gradient-tile buffer of ``logits_bwd_both`` (8 KB per [64 x 64] block, include/b200clip.h K3b)."""
+    return 2 * ((Nx + 127) // 128) * 4 * ((Ny + 255) // 256) * 4096
+
+
 def logits_bwd_both(mode, X, Y, Nx, Ny, K, D, dyn, rowscale, colscale, dX, dY, scal, G, *, ydiag=0.0, diag_off=0, diag_corr=None,
                     gnorm=1.0) -> bool:
-    """dX += G Y and dY += G^T X from one recompute of the logits (G kept in the caller's bf16 buffer ``G`` [Nx, >= Ny]).
-    False when the shape does not qualify (nothing launched)."""
+    """dX += G Y and dY += G^T X from one recompute of the logits (G tiles kept in the caller's flat bf16 buffer ``G`` of
+    ``gstore_elems(Nx, Ny)`` elements). False when the shape does not qualify (nothing launched)."""
     return try_call("logits_bwd_both", mode, X, Y, Nx, Ny, K, K, D, X.stride(0), Y.stride(0), 0.0, rowscale, colscale,
                     float(gnorm), dyn, float(ydiag), int(diag_off), diag_corr, dX, dX.stride(0), dY, dY.stride(0), scal, G,
-                    G.stride(0), stream_ptr(X.device))
+                    G.numel(), stream_ptr(X.device))
+
 
 call = call  # re-export for the loss module
 i64 = i64

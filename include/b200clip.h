@@ -180,15 +180,23 @@ int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, 
 
 /* K3b  Both gradients of the softmax (mode 0) / gated (mode 1) contrastive step from ONE recompute of the logits
  *      (utils/loss/contrastive.py:150-164 backward: dV̂ = G T̂ / tau, dT̂ = G^T V̂ / tau). logits_bwd as above for dX with every
- *      G tile also stored through TMA (bf16, scaled by gnorm, row-major G [Nx, ldg], ldg % 8 == 0, caller-owned: 2 Nx ldg
- *      bytes), then dY[Ny, D] += dyn[2] / gnorm * G^T X as a tcgen05 product with both operands MN-major (csrc/gt_gemm.cu).
- *      Executed work 8 instead of 10 Nx Ny D per step. Plain bf16 operands, Kp == Dp in {256, 512}, dyn required;
- *      B2_ENOSYS otherwise (the caller then launches logits_bwd twice). dX and dY are ACCUMULATED (caller zeroes);
- *      diag_corr of the Y side equals the one written here when the problem is square with diag_off = 0. */
+ *      G tile also stored through TMA (bf16, scaled by gnorm), then dY[Ny, D] += dyn[2] / gnorm * G^T X as a tcgen05 product
+ *      with both operands MN-major (csrc/gt_gemm.cu). Executed work 8 instead of 10 Nx Ny D per step.
+ *      G: caller-owned bf16 buffer of gstore_elems(Nx, Ny) elements, 128-byte aligned, in the BLOCKED layout the two kernels
+ *      share: [64 x 64] blocks of 8 KB, block (ib, jb) = rows 64 ib .., columns 64 jb .. at element offset
+ *      (ib * nJB + jb) * 4096, nJB = 4 ceil(Ny / 256), ib < 2 ceil(Nx / 128); inside a block row r holds its 64 columns as eight
+ *      16-byte units, unit u at position u ^ (r & 7) (the SWIZZLE_128B operand image); blocks past the edges hold zeros.
+ *      Plain bf16 operands, Kp == Dp in {256, 512}, dyn required; B2_ENOSYS otherwise (the caller then launches logits_bwd
+ *      twice), B2_ENOMEM if g_elems is too small. dX and dY are ACCUMULATED (caller zeroes); diag_corr of the Y side equals
+ *      the one written here when the problem is square with diag_off = 0.
+ *      gt_gemm alone: the product for any G in that layout and bf16 X [Nx, ldx] of padded width Dp in {256, 512}. */
+int b200clip_gstore_elems(int Nx, int Ny, int64_t* elems);
+int b200clip_gt_gemm(const void* G, int64_t g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
+                     float gnorm, float* dY, int ldd, void* stream);
 int b200clip_logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
                              float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn,
                              float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy,
-                             double* scal, void* G, int ldg, void* stream);
+                             double* scal, void* G, int64_t g_elems, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Device-side scalar plumbing (no host sync on log_temp / bias).
