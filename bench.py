@@ -410,7 +410,7 @@ def bwd_kernel_roofline(ctx: Ctx, B: int, N: int, D: int, log_temp, step_ms: flo
     # the step's backward as it runs on one GPU (loss.py): ONE recompute — bw3 storing its G tiles + the transposed product
     # of gt_gemm.cu — timed as the pair and the product alone
     pair = None
-    if bw3 and Kp <= 512 and B == N and ctx.world == 1 and os.environ.get("B200CLIP_GSTORE", "1") != "0":
+    if bw3 and B == N and ctx.world == 1 and os.environ.get("B200CLIP_GSTORE", "1") != "0":
         try:
             G = torch.empty(ops.gstore_elems(B, N), dtype=torch.bfloat16, device=dev)
             dY = torch.zeros(N, D, device=dev)
@@ -430,7 +430,7 @@ def bwd_kernel_roofline(ctx: Ctx, B: int, N: int, D: int, log_temp, step_ms: flo
                     fn()
                 e1.record(); torch.cuda.synchronize()
                 tm[nm] = e0.elapsed_time(e1) / reps
-            pair = {"kernels": "bw3_kernel<CLIP, 256> with TMA stores of its G tiles (bf16, N^2 elements in [64 x 64] blocks) + gt_gemm_kernel (dY = G^T X, "
+            pair = {"kernels": f"bw3_kernel<CLIP, {256 if Kp <= 512 else 128}> with TMA stores of its G tiles (bf16, N^2 elements in [64 x 64] blocks) + gt_gemm_kernel (dY = G^T X, "
                                "cta_group::2 M=256, both operands MN-major)",
                     "ms_pair": tm["pair"], "ms_gt_gemm": tm["gemm"], "ms_bw3_with_store": tm["pair"] - tm["gemm"],
                     "pair_algorithmic_tflops": 2 * alg / (tm["pair"] * 1e-3) / 1e12,

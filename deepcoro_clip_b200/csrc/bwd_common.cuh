@@ -58,6 +58,7 @@ struct BwParams {
   int ldd;
   double* scal;                // [4] fp64 atomics: 0: sum G*f(S), 1: sum softplus(L), 2: sum G ; may be null
   const float* dyn;            // optional device block from dyn_prep: overrides scale2/shift2/inv_tau/bias/out_scale
+  int gnjb;                    // column blocks per block row of the stored-G buffer (4 * ceil(Ny / 256))
   int gstore;                  // logits_bwd3.cu only: every G tile is also stored (bf16, scaled by gnorm) through the kernel's
                                // fourth tensor map, for the transposed product of gt_gemm.cu
   int stable;                  // CLIP / gated only, read from dyn[11] inside the kernel: rowscale / colscale hold log2-domain

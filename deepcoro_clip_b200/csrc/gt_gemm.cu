@@ -38,6 +38,7 @@ struct GgParams {
   float* dY;
   int ldd;
   int tiles, ksteps, njb;
+  int d_off;             // first output column of this launch (Dp = its width: 256 or 512)
 };
 
 struct GgSched {
@@ -117,7 +118,7 @@ gt_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           const int i0 = ks * GG_BK;
           tma_load_2d_pair(st, &tmG, &full_bar[slot], 0, (ks * p.njb + (j0 >> 6)) * 64);      // two blocks, 16 KB
           for (int n = 0; n < nparts; ++n) {
-            const int d0 = 256 * n + 128 * (int)rank;
+            const int d0 = p.d_off + 256 * n + 128 * (int)rank;
             tma_load_2d_pair(st + (2 + 2 * n) * GG_BOX, &tmX, &full_bar[slot], d0, i0);
             tma_load_2d_pair(st + (3 + 2 * n) * GG_BOX, &tmX, &full_bar[slot], d0 + 64, i0);
           }
@@ -173,7 +174,7 @@ gt_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       for (int n = 0; n < nparts; ++n) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int d0 = 256 * n + 128 * half + 32 * c;
+          const int d0 = p.d_off + 256 * n + 128 * half + 32 * c;
           if (d0 < p.D) {                        // warp-uniform
             uint32_t a[32];
             tmem_ld32(tmem_base + lane_off + n * 256 + half * 128 + c * 32, a);
@@ -219,11 +220,11 @@ long long gstore_elems(int Nx, int Ny) {
 }
 
 // dY[Ny, D] (fp32, pitch ldd, pre-zeroed or holding a partial sum) += dyn[2] / gnorm * G^T X ; G in the blocked layout above
-// (g_elems >= gstore_elems(Nx, Ny), 128-byte aligned), X [Nx, ldx] bf16 operand panel of width Dp in {256, 512}.
+// (g_elems >= gstore_elems(Nx, Ny), 128-byte aligned), X [Nx, ldx] bf16 operand panel of width Dp in {256, 512, 768}.
 // B2_ENOSYS for other widths.
 int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
             float gnorm, float* dY, int ldd, cudaStream_t stream) {
-  if (Dp % 256 || Dp > 512 || sm_count() < 2) return B2_ENOSYS;
+  if (Dp % 256 || Dp > 768 || sm_count() < 2) return B2_ENOSYS;
   if (!G || !X || !dyn || !dY || Nx < 1 || Ny < 1 || D < 1 || D > Dp) return B2_EINVAL;
   if (g_elems < gstore_elems(Nx, Ny)) return B2_ENOMEM;
   static bool attr_done_dev[64] = {};
@@ -233,7 +234,7 @@ int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int
     attr_done = true;
   }
   GgParams p;
-  p.Nx = Nx; p.Ny = Ny; p.Dp = Dp; p.D = D; p.inv_gnorm = 1.f / (gnorm > 0.f ? gnorm : 1.f); p.dyn = dyn; p.dY = dY; p.ldd = ldd;
+  p.Nx = Nx; p.Ny = Ny; p.D = D; p.inv_gnorm = 1.f / (gnorm > 0.f ? gnorm : 1.f); p.dyn = dyn; p.dY = dY; p.ldd = ldd;
   p.tiles = (Ny + 255) / 256;
   p.ksteps = 2 * ((Nx + 127) / 128);      // every row block the storing kernel wrote (zeros past Nx)
   p.njb = 4 * p.tiles;
@@ -244,7 +245,13 @@ int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int
   const long long total = (long long)p.tiles * p.ksteps;
   const int clusters = sm_count() / 2;
   const int grid = 2 * (int)(total < clusters ? total : clusters);
-  gt_gemm_kernel<<<grid, GG_THREADS, GG_SMEM, stream>>>(tmG, tmX, p);
+  // the accumulator of a CTA is [128 x 512] fp32 (all of TMEM): wider outputs take a second sweep over G for the rest
+  for (int off = 0; off < Dp; off += 512) {
+    p.d_off = off;
+    p.Dp = Dp - off < 512 ? Dp - off : 512;
+    if (off >= D) break;
+    gt_gemm_kernel<<<grid, GG_THREADS, GG_SMEM, stream>>>(tmG, tmX, p);
+  }
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -425,10 +425,14 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const bool has_diag = !BwIsSiglip<kMode>::value && p.ydiag != 0.f && dlo > -BW_BM && dlo < kNJ;
         const uint32_t cs_addr = smem_u32(col_s) + (warp - 4) * 32 * 4;
         const uint32_t ga = grow_addr + buf * C::kGBuf;
-        if (kNJ == 256 && p.gstore) {
-          // this warp's TMA store of tile t - 2 (same G buffer) has finished reading shared memory
-          if (lane == 0) bw3_bulk_wait_read1();
-          __syncwarp();
+        if (p.gstore) {
+          // the TMA store of tile t - 2 (same G buffer) has finished reading shared memory. kNJ = 256: a warp owns a whole
+          // [32 x 64] box; kNJ = 128: the two warps of a lane quarter share one (32 columns each), warp wg = 0 stores it
+          if (kNJ == 256 || wg == 0) {
+            if (lane == 0) bw3_bulk_wait_read1();
+            __syncwarp();
+          }
+          if (kNJ == 128) named_bar_sync(1 + q, 64);
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -473,14 +477,15 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
+        if (kNJ == 128 && p.gstore) named_bar_sync(1 + q, 64);      // both halves of the box are written and fenced
         if (lane == 0) mbar_arrive_cluster(buf ? gready_remote1 : gready_remote0);
-        if (kNJ == 256 && p.gstore && lane == 0) {
+        if (p.gstore && lane == 0 && (kNJ == 256 || wg == 0)) {
           // the warp's own [32 rows x 64 columns] half of chunk ctile / 64: 4 KB, contiguous in shared memory, already in the
           // SWIZZLE_128B operand layout -> copied byte for byte into block (row block 2 xt + rank, column block 4 j + chunk) of
           // the blocked G buffer (8 KB per [64 x 64] block, gt_gemm.cu loads the blocks as its MN-major A operand): 4 KB
           // sequential writes instead of 32 row segments 2 Ny bytes apart
           bw3_tma_store_2d(&tmG, smem_u32(gbuf) + buf * C::kGBuf + (ctile >> 6) * BW3_XCHUNK + (q & 1) * 32 * 128, 0,
-                           ((2 * xt + (int)rank) * (4 * p.y_tiles) + 4 * j + (ctile >> 6)) * 64 + (q & 1) * 32);
+                           ((2 * xt + (int)rank) * p.gnjb + (kNJ / 64) * j + (ctile >> 6)) * 64 + (q & 1) * 32);
           bw3_bulk_commit();
         }
         if (p.scal) {
@@ -546,7 +551,7 @@ bw3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
   }
 
-  if (kNJ == 256 && p.gstore && warp >= 4 && lane == 0) bw3_bulk_wait_all();
+  if (p.gstore && warp >= 4 && lane == 0) bw3_bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -588,7 +593,6 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
   static const bool nj256_ok = [] { const char* e = getenv("B200CLIP_BWD3_NJ"); return !(e && e[0] == '1' && e[1] == '2'); }();
   const int NJ = (Kp <= 512 && nj256_ok) ? 256 : 128;
   if (mode != BW_CLIP && mode != BW_GATED && mode != BW_SIGLIP) return B2_ENOSYS;
-  if (gstore && NJ != 256) return B2_ENOSYS;       // G tiles are stored by the 256-column variant only
   if (gstore && g_elems < gstore_elems(Nx, Ny)) return B2_ENOMEM;
   BwParams p;
   p.Nx = Nx; p.Ny = Ny; p.Kp = Kp; p.Dp = Dp; p.D = D; p.hi_off = 0; p.ydiag = ydiag; p.diag_off = diag_off;
@@ -606,7 +610,7 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
   p.gnorm = gnorm > 0.f ? gnorm : 1.f;
   p.hp = 0;
   p.lclamp = 30.f; p.yneg = 0.f; p.ent_coef = 0.f; p.stable = 0;
-  p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn; p.gstore = gstore ? 1 : 0;
+  p.dX = dX; p.ldd = ldd; p.scal = scal; p.dyn = dyn; p.gstore = gstore ? 1 : 0; p.gnjb = 4 * ((Ny + 255) / 256);
   CUtensorMap tmX, tmYs, tmYo, tmG;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, Kp, ldx, BW3_XROWS))) return rc;
@@ -634,7 +638,7 @@ int logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int 
                     float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn, float ydiag,
                     int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy, double* scal, void* G,
                     long long g_elems, cudaStream_t stream) {
-  if (!G || !dY || !dyn || (mode != BW_CLIP && mode != BW_GATED) || Dp > 512) return B2_ENOSYS;
+  if (!G || !dY || !dyn || (mode != BW_CLIP && mode != BW_GATED)) return B2_ENOSYS;
   int rc = logits_bwd_pair64(mode, X, Y, Nx, Ny, Kp, Dp, D, 0, ldx, ldy, 0.f, 0.f, 0.f, 0.f, wneg_c, rowscale, colscale, 0.f,
                              gnorm, 0, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal, 0, stream, G, g_elems);
   if (rc) return rc;

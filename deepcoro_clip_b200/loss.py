@@ -216,11 +216,11 @@ class _ClipLossFn(torch.autograd.Function):
             ctx.scal_used = True
         ydiag = (1.0 - eps) / N
         lt_work = None
-        # One recompute of the logits for both gradients (single GPU, plain bf16 operands, D <= 512): the video-side pass stores
+        # One recompute of the logits for both gradients (single GPU, plain bf16 operands, padded D in {256, 512, 768}): the video-side pass stores
         # its G tiles (bf16, 2 N^2 bytes, blocked layout) and the text-side gradient is the plain product G^T V̂ (csrc/gt_gemm.cu) instead of a
         # second pass with a second recompute. B200CLIP_GSTORE=0 keeps the two passes (A/B measurements).
         both = False
-        if (W == 1 and need_v and need_t and K == Kp and Kp in (256, 512) and 2 * ops.gstore_elems(B, N) <= _GSTORE_MAX_BYTES
+        if (W == 1 and need_v and need_t and K == Kp and Kp in (256, 512, 768) and 2 * ops.gstore_elems(B, N) <= _GSTORE_MAX_BYTES
                 and os.environ.get("B200CLIP_GSTORE", "1") != "0"):
             dVh, dTh = ws[:nbd].view(B, D), ws[nbd:2 * nbd].view(B, D)
             dcv = ws[2 * nbd:2 * nbd + 2 * B]

@@ -186,10 +186,11 @@ int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, 
  *      share: [64 x 64] blocks of 8 KB, block (ib, jb) = rows 64 ib .., columns 64 jb .. at element offset
  *      (ib * nJB + jb) * 4096, nJB = 4 ceil(Ny / 256), ib < 2 ceil(Nx / 128); inside a block row r holds its 64 columns as eight
  *      16-byte units, unit u at position u ^ (r & 7) (the SWIZZLE_128B operand image); blocks past the edges hold zeros.
- *      Plain bf16 operands, Kp == Dp in {256, 512}, dyn required; B2_ENOSYS otherwise (the caller then launches logits_bwd
+ *      Plain bf16 operands, Kp == Dp in {256, 512, 768}, dyn required; B2_ENOSYS otherwise (the caller then launches logits_bwd
  *      twice), B2_ENOMEM if g_elems is too small. dX and dY are ACCUMULATED (caller zeroes); diag_corr of the Y side equals
  *      the one written here when the problem is square with diag_off = 0.
- *      gt_gemm alone: the product for any G in that layout and bf16 X [Nx, ldx] of padded width Dp in {256, 512}. */
+ *      gt_gemm alone: the product for any G in that layout and bf16 X [Nx, ldx] of padded width Dp in {256, 512, 768} (the
+ *      accumulator of a CTA holds 512 columns: Dp = 768 sweeps G twice). */
 int b200clip_gstore_elems(int Nx, int Ny, int64_t* elems);
 int b200clip_gt_gemm(const void* G, int64_t g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
                      float gnorm, float* dY, int ldd, void* stream);

@@ -14,7 +14,7 @@ def _rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("Nx,Ny,D", [(1000, 777, 200), (4097, 4099, 512), (64, 300, 256), (3000, 520, 500)])
+@pytest.mark.parametrize("Nx,Ny,D", [(1000, 777, 200), (4097, 4099, 512), (64, 300, 256), (3000, 520, 500), (1000, 777, 700), (2050, 260, 768)])
 def test_gt_gemm_matches_float64_matmul(Nx, Ny, D):
     """dY += dyn[2] / gnorm * G^T X on ragged shapes (rows / columns that are no multiples of the 256 x 64 tiles, D below the
     padded width), accumulating into a non-zero dY."""
@@ -45,7 +45,8 @@ def test_gt_gemm_matches_float64_matmul(Nx, Ny, D):
 
 
 @pytest.mark.parametrize("N,D,kw", [(1500, 512, {}), (777, 256, {}), (2048, 512, {"label_smoothing": 0.1}),
-                                    (1029, 512, {"gated": True}), (640, 512, {"tau": 0.004})])
+                                    (1029, 512, {"gated": True}), (640, 512, {"tau": 0.004}), (1500, 768, {}), (900, 768, {"label_smoothing": 0.05}),
+                                    (385, 768, {"tau": 0.004})])
 def test_clip_gradients_one_recompute_vs_two_passes(N, D, kw):
     from deepcoro_clip_b200 import loss as L
     dev = torch.device("cuda", 0)
