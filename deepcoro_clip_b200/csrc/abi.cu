@@ -138,7 +138,8 @@ int b200clip_logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int
                              float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn,
                              float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy,
                              double* scal, void* G, int64_t g_elems, void* stream) {
-  if (!X || !Y || !dX || !dY || !G || !rowscale || !colscale || !dyn) return B2_EINVAL;
+  if (!X || !Y || !dX || !dY || !G || !dyn) return B2_EINVAL;
+  if (mode != 2 && (!rowscale || !colscale)) return B2_EINVAL;      // the sigmoid mode (2) has no row / column statistics
   if (Nx <= 0 || Ny <= 0 || Kp != Dp || Dp <= 0 || Dp % 64 || D > Dp || D <= 0) return B2_EINVAL;
   return logits_bwd_both(mode, X, Y, Nx, Ny, Kp, Dp, D, ldx, ldy, wneg_c, rowscale, colscale, gnorm, dyn, ydiag, diag_off,
                          diag_corr, dX, ldd, dY, lddy, scal, G, g_elems, S(stream));

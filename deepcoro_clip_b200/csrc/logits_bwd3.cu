@@ -631,14 +631,14 @@ int logits_bwd_pair64(int mode, const void* X, const void* Y, int Nx, int Ny, in
 #undef LAUNCH3
 }
 
-// Both gradients of the softmax / gated contrastive step from ONE recompute of the logits: dX += G Y as above with every G tile
+// Both gradients of the softmax / gated / sigmoid contrastive step from ONE recompute of the logits: dX += G Y as above with every G tile
 // stored (bf16, blocked layout of gt_gemm.cu) and dY += G^T X by gt_gemm.cu. Square single-GPU problems whose G fits the caller's buffer; the
 // diagonal corrections of the Y side equal those of the X side (same G_ii). B2_ENOSYS when the shape does not qualify.
 int logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int Kp, int Dp, int D, int ldx, int ldy,
                     float wneg_c, const float* rowscale, const float* colscale, float gnorm, const float* dyn, float ydiag,
                     int diag_off, float* diag_corr, float* dX, int ldd, float* dY, int lddy, double* scal, void* G,
                     long long g_elems, cudaStream_t stream) {
-  if (!G || !dY || !dyn || (mode != BW_CLIP && mode != BW_GATED)) return B2_ENOSYS;
+  if (!G || !dY || !dyn || (mode != BW_CLIP && mode != BW_GATED && mode != BW_SIGLIP)) return B2_ENOSYS;
   int rc = logits_bwd_pair64(mode, X, Y, Nx, Ny, Kp, Dp, D, 0, ldx, ldy, 0.f, 0.f, 0.f, 0.f, wneg_c, rowscale, colscale, 0.f,
                              gnorm, 0, dyn, ydiag, diag_off, diag_corr, dX, ldd, scal, 0, stream, G, g_elems);
   if (rc) return rc;

@@ -536,9 +536,19 @@ class _SigLIPFn(torch.autograd.Function):
                 dTh = rplan.buf[rslot][:T * D].view(T, D)
             else:
                 dTh = arena[32 + B * D:].view(T, D)
-            ops.logits_bwd(mode, vop, top, B, T, K, Kp, D, dyn, rowvec, None, dVh, acc[0:4], wneg_c=wn * c, gnorm=gn,
-                           hp=x3)
-            ops.logits_bwd(mode, top, vop, T, B, K, Kp, D, dyn, None, rowvec, dTh, None, wneg_c=wn * c, gnorm=gn, hp=x3)
+            # one recompute of the logits for both gradients (CLIPLoss above): the [B, T] slab of G is stored and the text-side
+            # gradient is G^T V̂ — valid for any world size here, the text gradient is summed over the ranks anyway
+            both = False
+            if (mode == BW_SIGLIP and not x3 and K == Kp and Kp in (256, 512, 768)
+                    and 2 * ops.gstore_elems(B, T) <= _GSTORE_MAX_BYTES and os.environ.get("B200CLIP_GSTORE", "1") != "0"):
+                G = torch.empty(ops.gstore_elems(B, T), dtype=torch.bfloat16, device=dev)
+                both = ops.logits_bwd_both(mode, vop, top, B, T, K, D, dyn, None, None, dVh, dTh, acc[0:4], G, gnorm=gn,
+                                           wneg_c=wn * c)
+                del G
+            if not both:
+                ops.logits_bwd(mode, vop, top, B, T, K, Kp, D, dyn, rowvec, None, dVh, acc[0:4], wneg_c=wn * c, gnorm=gn,
+                               hp=x3)
+                ops.logits_bwd(mode, top, vop, T, B, K, Kp, D, dyn, None, rowvec, dTh, None, wneg_c=wn * c, gnorm=gn, hp=x3)
         else:
             ops.call("siglip_dense_fwd", vop, top, B, T, K, vop.stride(0), top.stride(0), dyn, acc[1:2], st)
         flags = int(pw is not None) | (2 if cfg["pos_rule_mask"] else 0)

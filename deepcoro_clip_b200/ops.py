@@ -122,10 +122,10 @@ def gstore_elems(Nx: int, Ny: int) -> int:
 
 
 def logits_bwd_both(mode, X, Y, Nx, Ny, K, D, dyn, rowscale, colscale, dX, dY, scal, G, *, ydiag=0.0, diag_off=0, diag_corr=None,
-                    gnorm=1.0) -> bool:
+                    gnorm=1.0, wneg_c=0.0) -> bool:
     """dX += G Y and dY += G^T X from one recompute of the logits (G tiles kept in the caller's flat bf16 buffer ``G`` of
     ``gstore_elems(Nx, Ny)`` elements). False when the shape does not qualify (nothing launched)."""
-    return try_call("logits_bwd_both", mode, X, Y, Nx, Ny, K, K, D, X.stride(0), Y.stride(0), 0.0, rowscale, colscale,
+    return try_call("logits_bwd_both", mode, X, Y, Nx, Ny, K, K, D, X.stride(0), Y.stride(0), float(wneg_c), rowscale, colscale,
                     float(gnorm), dyn, float(ydiag), int(diag_off), diag_corr, dX, dX.stride(0), dY, dY.stride(0), scal, G,
                     G.numel(), stream_ptr(X.device))
 

@@ -178,7 +178,8 @@ int b200clip_logits_bwd(int mode, const void* X, const void* Y, int Nx, int Ny, 
                         const float* dyn, float ydiag, int diag_off, float* diag_corr, float* dX, int ldd, double* scal, int nseg_hint,
                         void* stream);
 
-/* K3b  Both gradients of the softmax (mode 0) / gated (mode 1) contrastive step from ONE recompute of the logits
+/* K3b  Both gradients of the softmax (mode 0) / gated (mode 1) / sigmoid (mode 2, rowscale = colscale = NULL) contrastive step
+ *      from ONE recompute of the logits
  *      (utils/loss/contrastive.py:150-164 backward: dV̂ = G T̂ / tau, dT̂ = G^T V̂ / tau). logits_bwd as above for dX with every
  *      G tile also stored through TMA (bf16, scaled by gnorm), then dY[Ny, D] += dyn[2] / gnorm * G^T X as a tcgen05 product
  *      with both operands MN-major (csrc/gt_gemm.cu). Executed work 8 instead of 10 Nx Ny D per step.

@@ -1,3 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_gt_gemm.py -x -q 2>&1 | tail -3
-timeout 600 python bench.py --steps 10 --warmup 3 --legs clip32k_d768 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_x.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_x.json')); e=d['roofline']['backward_one_recompute']; print(d['ms_per_step'], e['ms_pair'], e['ms_gt_gemm'], e['ms_bw3_with_store'], d['parity']['grad_rel_sampled_rows']); d=d['clip32k_d768']; e=d['roofline']['backward_one_recompute']; print(d['ms_per_step'], e['ms_pair'], e['ms_gt_gemm'], e['ms_bw3_with_store'], d['parity']['grad_rel_sampled_rows'])"
+timeout 900 python -m pytest tests/test_gpu_siglip.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -3
+timeout 600 python bench.py --steps 10 --warmup 3 --legs siglip_c2 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_x.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_x.json')); e=d['siglip_c2']; print(e.get('ms_per_step'), json.dumps(e.get('parity'))[:300])"
+B200CLIP_GSTORE=0 timeout 600 python bench.py --steps 10 --warmup 3 --legs siglip_c2 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_x.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_x.json')); e=d['siglip_c2']; print(e.get('ms_per_step'))"
