@@ -19,7 +19,7 @@ _HEADER = _PKG.parent / "include" / "b200clip.h"
 _lib = None
 LAUNCHES = 0      # number of b200clip_* kernel-launching calls made by this process (bench.py reports it)
 _NO_LAUNCH = {"abi_version", "strerror", "sm_count", "attnpool_splits", "attnpool_bwd_splits", "retrieval_segments",
-              "rowlse_slots", "milpool_plan", "gstore_elems", "aggregator_sizes"}
+              "rowlse_slots", "milpool_plan", "milpool_tc_plan", "gstore_elems", "aggregator_sizes"}
 
 DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
@@ -115,7 +115,8 @@ def try_call(name: str, *args) -> bool:
     rc = fn(*[a.data_ptr() if isinstance(a, _Tensor) else a for a in args])
     if rc == -38:
         return False
-    LAUNCHES += 1
+    if name not in _NO_LAUNCH:
+        LAUNCHES += 1
     if rc != 0:
         raise B200ClipError(f"b200clip_{name} failed: {lib().b200clip_strerror(rc).decode()} (code {rc})")
     return True

@@ -519,6 +519,30 @@ int b200clip_milpool_bwd(const float* x, int64_t x_sseq, int64_t x_stok, const f
                      dpre, wpart, fpart, dW, dsmall, S(stream));
 }
 
+int b200clip_milpool_tc_plan(int S, int L, int D, int Hd, int64_t* plan) {
+  if (!plan || S < 1 || !milpool_tc_ok((long long)S * L, L, D, Hd)) return B2_ENOSYS;
+  long long t[5];
+  milpool_tc_plan(S, L, D, Hd, t);
+  for (int i = 0; i < 5; ++i) plan[i] = t[i];
+  return B2_OK;
+}
+
+int b200clip_milpool_tc_fwd(const float* x, int64_t x_sseq, int64_t x_stok, const uint8_t* valid, int64_t valid_sseq,
+                            const float* V, const float* bV, const float* U, const float* bU, const float* w, const float* bw,
+                            int S, int L, int D, int Hd, float drop_p, int64_t seed, void* x3, void* w3, void* wt3, float* tg,
+                            float* spart, float* attn, float* opart, float* out, void* stream) {
+  return milpool_tc_fwd(x, x_sseq, x_stok, valid, valid_sseq, V, bV, U, bU, w, bw, S, L, D, Hd, drop_p,
+                        (unsigned long long)seed, x3, w3, wt3, tg, spart, attn, opart, out, S(stream));
+}
+
+int b200clip_milpool_tc_bwd(const float* x, int64_t x_sseq, int64_t x_stok, const float* w, int S, int L, int D, int Hd,
+                            float drop_p, int64_t seed, const void* x3, const void* wt3, const float* tg, const float* attn,
+                            const float* dout, float* ds, float* dx, void* dpre3, void* ghi, void* glo, float* ad,
+                            float* fpart, float* dW, float* dsmall, const float* one3, void* stream) {
+  return milpool_tc_bwd(x, x_sseq, x_stok, w, S, L, D, Hd, drop_p, (unsigned long long)seed, x3, wt3, tg, attn, dout, ds, dx,
+                        dpre3, ghi, glo, ad, fpart, dW, dsmall, one3, S(stream));
+}
+
 int b200clip_symm_barrier(void* const* flags_host, int world, int rank, int channel, void* stream) {
   return symm_barrier(flags_host, world, rank, channel, S(stream));
 }

@@ -238,6 +238,17 @@ int milpool_bwd(const float* x, long long sx_seq, long long sx_tok, const float*
                 const float* dout, float* ds, float* dx, float* dpre, float* wpart, float* fpart, float* dW, float* dsmall,
                 cudaStream_t s);
 
+bool milpool_tc_ok(long long R, int L, int D, int Hd);
+void milpool_tc_plan(int S, int L, int D, int Hd, long long* plan);
+int milpool_tc_fwd(const float* x, long long sx_seq, long long sx_tok, const uint8_t* mask, long long smask, const float* V,
+                   const float* bV, const float* U, const float* bU, const float* w, const float* bw, int S, int L, int D,
+                   int Hd, float drop_p, unsigned long long seed, void* x3, void* w3, void* wt3, float* tg, float* spart,
+                   float* attn, float* opart, float* out, cudaStream_t s);
+int milpool_tc_bwd(const float* x, long long sx_seq, long long sx_tok, const float* w, int S, int L, int D, int Hd,
+                   float drop_p, unsigned long long seed, const void* x3, const void* wt3, const float* tg, const float* attn,
+                   const float* dout, float* ds, float* dx, void* dpre3, void* ghi, void* glo, float* ad, float* fpart,
+                   float* dW, float* dsmall, const float* one3, cudaStream_t s);
+
 // scalars.cu: symmetric-memory plumbing of the multi-GPU CLIP path
 int symm_barrier(void* const* flags_host, int world, int rank, int channel, cudaStream_t s);
 int symm_allreduce_f32(void* const* bufs_host, long long n, int world, int rank, cudaStream_t s);

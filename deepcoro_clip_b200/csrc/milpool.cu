@@ -16,7 +16,7 @@
 //   mil_dx         : dx = drop(A) dout + dpre [V; U].
 //   mil_dw         : d[V; U] = dpre^T x, rows split over grid.z into partial products;
 //   mil_reduce     : fixed-order sums of the partials (deterministic).
-#include "common.cuh"
+#include "tile_engine.cuh"
 #include "host_api.h"
 
 namespace b2 {
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) mil_dpre_kernel(MilParams p) {
 // fixed-order sums of the partials: one thread per element of d[V; U] over the Z row ranges, one warp per bias / w element
 // over the row chunks (lane-strided, then a shuffle tree)
 __global__ void __launch_bounds__(256) mil_reduce_kernel(MilParams p) {
-  const long long n1 = 2ll * p.Hd * p.D, n2 = 3 * p.Hd + 1, nb1 = (n1 + 255) / 256;
+  const long long n1 = p.Z > 0 ? 2ll * p.Hd * p.D : 0, n2 = 3 * p.Hd + 1, nb1 = (n1 + 255) / 256;
   if (blockIdx.x < nb1) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i < n1) {
@@ -484,6 +484,217 @@ __global__ void __launch_bounds__(256) mil_reduce_kernel(MilParams p) {
       t = warp_sum(t);
       if ((threadIdx.x & 31) == 0) p.dsmall[j] = t;
     }
+  }
+}
+
+
+// =====================================================================================================================
+// Tensor-core variant (R >= 1024 rows, D in {256, 512, 768}): the three products on tcgen05 with split-precision operands.
+// A value v is carried as hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits); a product a b is formed as
+// lo_a hi_b + hi_a lo_b + hi_a hi_b by ONE bf16 product over a three times longer K: A operand rows [lo | hi | hi], B operand
+// rows [hi | lo | hi] (the bf16x3 scheme of the loss kernels, 2^-17 relative per product, fp32 accumulation in TMEM).
+//   gate logits : tile engine (tile_engine.cuh) over A = x3 [R, 3 D], B = w3 [2 Hd, 3 D] with the gate columns interleaved
+//                 (row 2u = V_u, 2u + 1 = U_u: a unit's pair sits in the same 32-column chunk of a thread); the epilogue
+//                 applies tanh * sigmoid * w, writes t / g and the partial logit of its 128-column half.
+//   dx          : same engine over A = dpre3 [R, 3 Hp], B = wt3 [D, 3 Hp] (Hp = 2 Hd rounded up to 64, zero padded); the
+//                 epilogue adds drop(A_l) dout and writes dx.
+//   d[V; U]     : gt_gemm.cu (dY += G^T X from [64 x 64] blocks of G, both operands MN-major) called three times:
+//                 (dpre_hi, x_hi), (dpre_hi, x_lo), (dpre_lo, x_hi) — x_hi / x_lo are panels of x3.
+// =====================================================================================================================
+__device__ __forceinline__ void mil_split(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t mil_pack(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// x3[r, 0:D] = lo(x_r), x3[r, D:2D] = x3[r, 2D:3D] = hi(x_r)
+__global__ void __launch_bounds__(256) mil_split_x_kernel(MilParams p, __nv_bfloat16* __restrict__ x3) {
+  const int dq = p.D >> 2;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= p.R * dq) return;
+  const long long r = i / dq;
+  const int d = (int)(i - r * dq) * 4;
+  const float4 v = mg_ld4(mil_xrow(p, r) + d);
+  __nv_bfloat16 h[4], l[4];
+  mil_split(v.x, h[0], l[0]); mil_split(v.y, h[1], l[1]); mil_split(v.z, h[2], l[2]); mil_split(v.w, h[3], l[3]);
+  const uint2 hv = make_uint2(mil_pack(h[0], h[1]), mil_pack(h[2], h[3])), lv = make_uint2(mil_pack(l[0], l[1]), mil_pack(l[2], l[3]));
+  __nv_bfloat16* row = x3 + r * (3ll * p.D) + d;
+  *reinterpret_cast<uint2*>(row) = lv;
+  *reinterpret_cast<uint2*>(row + p.D) = hv;
+  *reinterpret_cast<uint2*>(row + 2 * p.D) = hv;
+}
+
+// w3 [2 Hd, 3 D] rows interleaved (2u = V_u, 2u + 1 = U_u): [hi | lo | hi];  wt3 [D, 3 Hp]: wt3[n, c] the same split of
+// column n of row c, zero for c >= 2 Hd
+__global__ void __launch_bounds__(256) mil_prep_w_kernel(MilParams p, int Hp, __nv_bfloat16* __restrict__ w3,
+                                                         __nv_bfloat16* __restrict__ wt3) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (long long)Hp * p.D) return;
+  const int c = (int)(i / p.D), n = (int)(i - (long long)c * p.D);
+  __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+  if (c < 2 * p.Hd) {
+    mil_split(((c & 1) ? p.U : p.V)[(long long)(c >> 1) * p.D + n], hi, lo);
+    __nv_bfloat16* wr = w3 + (long long)c * (3ll * p.D) + n;
+    wr[0] = hi;
+    wr[p.D] = lo;
+    wr[2 * p.D] = hi;
+  }
+  __nv_bfloat16* tr = wt3 + (long long)n * (3ll * Hp) + c;
+  tr[0] = hi;
+  tr[Hp] = lo;
+  tr[2 * Hp] = hi;
+}
+
+struct MilGateEpiParams {
+  const float *bV, *bU, *w;
+  float *tg, *spart;
+  int Hd;
+  long long R;
+};
+struct MilGateEpi {
+  using Params = MilGateEpiParams;
+  struct State { float part; };
+  __device__ static __forceinline__ void init(State& st, const Params&) { st.part = 0.f; }
+  __device__ static __forceinline__ void begin_outer(State&, const Params&, int, const TeCtx&) {}
+  __device__ static __forceinline__ void chunk(State& st, const Params& p, const TeCtx& ctx, int c, const uint32_t (&acc)[32]) {
+    const int u0 = (ctx.col0 + c * 32) >> 1;        // 16 units per chunk: columns 2u (V) and 2u + 1 (U)
+    if (!ctx.row_ok || u0 >= p.Hd) return;
+    float* trow = p.tg + (long long)ctx.row * (2ll * p.Hd) + u0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (u0 + 4 * k >= p.Hd) break;                // Hd % 4 == 0: whole quads
+      float t[4], g[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int u = u0 + 4 * k + e;
+        t[e] = tanhf(__uint_as_float(acc[2 * (4 * k + e)]) + __ldg(p.bV + u));
+        g[e] = 1.f / (1.f + expf(-(__uint_as_float(acc[2 * (4 * k + e) + 1]) + __ldg(p.bU + u))));
+        st.part = fmaf(__ldg(p.w + u), t[e] * g[e], st.part);
+      }
+      *reinterpret_cast<float4*>(trow + 4 * k) = make_float4(t[0], t[1], t[2], t[3]);
+      *reinterpret_cast<float4*>(trow + p.Hd + 4 * k) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State& st, const Params& p, const TeCtx& ctx) {
+    if (ctx.row_ok) p.spart[(long long)(2 * ctx.n_block + ctx.wg) * p.R + ctx.row] = st.part;
+    st.part = 0.f;
+  }
+  __device__ static __forceinline__ void end_outer(State&, const Params&, int, const TeCtx&) {}
+};
+
+struct MilDxEpiParams {
+  const float *ad, *dout;      // drop(A_l) per row, upstream gradient [S, D]
+  float* dx;                   // [R, D]
+  int D, L;
+};
+struct MilDxEpi {
+  using Params = MilDxEpiParams;
+  struct State {};
+  __device__ static __forceinline__ void init(State&, const Params&) {}
+  __device__ static __forceinline__ void begin_outer(State&, const Params&, int, const TeCtx&) {}
+  __device__ static __forceinline__ void chunk(State&, const Params& p, const TeCtx& ctx, int c, const uint32_t (&acc)[32]) {
+    const int n0 = ctx.col0 + c * 32;
+    if (!ctx.row_ok || n0 >= p.D) return;           // D % 32 == 0
+    const float a = __ldg(p.ad + ctx.row);
+    const float* dr = p.dout + (long long)(ctx.row / p.L) * p.D + n0;
+    float* xr = p.dx + (long long)ctx.row * p.D + n0;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      const float4 g = mg_ld4(dr + e);
+      *reinterpret_cast<float4*>(xr + e) = make_float4(fmaf(a, g.x, __uint_as_float(acc[e])), fmaf(a, g.y, __uint_as_float(acc[e + 1])),
+                                                      fmaf(a, g.z, __uint_as_float(acc[e + 2])), fmaf(a, g.w, __uint_as_float(acc[e + 3])));
+    }
+  }
+  __device__ static __forceinline__ void end_tile(State&, const Params&, const TeCtx&) {}
+  __device__ static __forceinline__ void end_outer(State&, const Params&, int, const TeCtx&) {}
+};
+
+// dpre in the three forms its consumers read, from t / g / ds (64 rows per CTA, a thread = 4 units = 8 interleaved columns):
+//   dpre3 [R, 3 Hp] = [lo | hi | hi] (A operand of the dx product, zero in the padded columns),
+//   ghi / glo: [64 x 64] blocks of gt_gemm.cu (8 KB each, 16-byte unit q of row r at position q ^ (r & 7)), zero rows past R,
+//   ad[r] = drop(A_r); and the partial sums of the bias / w gradients as mil_dpre_kernel.
+__global__ void __launch_bounds__(256) mil_dpre_tc_kernel(MilParams p, int Hp, int njb, __nv_bfloat16* __restrict__ dpre3,
+                                                          __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
+                                                          float* __restrict__ ad) {
+  __shared__ float sd[MG_FCH];
+  __shared__ float4 red[3][256];
+  __shared__ float sred[8];
+  const int tid = threadIdx.x, Hd = p.Hd;
+  const long long rbeg = (long long)blockIdx.x * MG_FCH;
+  const int nr = (int)max(0ll, min((long long)MG_FCH, p.R - rbeg));
+  float mine = 0.f;
+  if (tid < MG_FCH) {
+    sd[tid] = tid < nr ? p.ds[rbeg + tid] : 0.f;
+    mine = sd[tid];
+    if (tid < nr) ad[rbeg + tid] = p.attn[rbeg + tid] * mil_keepscale(p, rbeg + tid);
+  }
+  const float tot = mil_block_reduce(mine, false, sred);
+  float* dst = p.fpart + (long long)blockIdx.x * (3 * Hd + 4);
+  if (tid == 0) dst[3 * Hd] = tot;
+  const int nq = Hp >> 3;                              // 8-column units per row (4 hidden units each)
+  for (int q0 = 0; q0 < nq; q0 += 256) {
+    const int nqc = min(256, nq - q0), ng = 256 / nqc, g = tid / nqc, qi = tid - g * nqc, u = (q0 + qi) * 4, c = 2 * u;
+    float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), su = sv, sw = sv;
+    if (g < ng) {
+      const bool uok = u < Hd;
+      const float4 ww = uok ? mg_ld4(p.w + u) : sv;
+      for (int i = g; i < MG_FCH; i += ng) {
+        const long long r = rbeg + i;
+        float pvv[4] = {0.f, 0.f, 0.f, 0.f}, puv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i < nr && uok) {
+          const long long off = r * (2ll * Hd) + u;
+          const float4 t = mg_ld4(p.tg + off), gg = mg_ld4(p.tg + off + Hd);
+          const float d = sd[i];
+#define MIL_ONE(k, cmp)                              \
+  {                                                  \
+    const float tgp = t.cmp * gg.cmp, b = d * ww.cmp; \
+    pvv[k] = b * gg.cmp * (1.f - t.cmp * t.cmp);     \
+    puv[k] = b * tgp * (1.f - gg.cmp);               \
+    sv.cmp += pvv[k];                                \
+    su.cmp += puv[k];                                \
+    sw.cmp = fmaf(d, tgp, sw.cmp);                   \
+  }
+          MIL_ONE(0, x) MIL_ONE(1, y) MIL_ONE(2, z) MIL_ONE(3, w)
+#undef MIL_ONE
+        }
+        __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mil_split(pvv[k], h[2 * k], l[2 * k]);
+          mil_split(puv[k], h[2 * k + 1], l[2 * k + 1]);
+        }
+        const uint4 hv = make_uint4(mil_pack(h[0], h[1]), mil_pack(h[2], h[3]), mil_pack(h[4], h[5]), mil_pack(h[6], h[7]));
+        const uint4 lv = make_uint4(mil_pack(l[0], l[1]), mil_pack(l[2], l[3]), mil_pack(l[4], l[5]), mil_pack(l[6], l[7]));
+        if (i < nr) {
+          __nv_bfloat16* row = dpre3 + r * (3ll * Hp) + c;
+          *reinterpret_cast<uint4*>(row) = lv;
+          *reinterpret_cast<uint4*>(row + Hp) = hv;
+          *reinterpret_cast<uint4*>(row + 2 * Hp) = hv;
+        }
+        // block (r / 64 = blockIdx.x, c / 64), row i, 16-byte unit (c % 64) / 8 swizzled with the row
+        const long long boff = ((long long)blockIdx.x * njb + (c >> 6)) * 4096 + i * 64 + ((((c & 63) >> 3) ^ (i & 7)) << 3);
+        *reinterpret_cast<uint4*>(ghi + boff) = hv;
+        *reinterpret_cast<uint4*>(glo + boff) = lv;
+      }
+    }
+    red[0][tid] = sv;
+    red[1][tid] = su;
+    red[2][tid] = sw;
+    __syncthreads();
+    if (tid < nqc && (q0 + tid) * 4 < Hd) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float4 t = red[k][tid];
+        for (int gg = 1; gg < ng; ++gg) {
+          const float4 o = red[k][gg * nqc + tid];
+          t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        }
+        *reinterpret_cast<float4*>(dst + k * Hd + (q0 + tid) * 4) = t;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -557,6 +768,112 @@ int milpool_bwd(const float* x, long long sx_seq, long long sx_tok, const float*
   mil_dw_kernel<<<dim3((2 * Hd + 127) / 128, (D + 127) / 128, p.Z), MG_THREADS, 0, s>>>(p);
   const long long n1 = 2ll * Hd * D, n2 = 3 * Hd + 1;
   mil_reduce_kernel<<<(unsigned)((n1 + 255) / 256 + (n2 + 7) / 8), 256, 0, s>>>(p);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+
+// ---- tensor-core variant ---------------------------------------------------------------------------------------------
+bool milpool_tc_ok(long long R, int L, int D, int Hd) {
+  return milpool_ok(L, D, Hd) && (D == 256 || D == 512 || D == 768) && R >= 1024 && R < (1ll << 31) - 256 && Hd <= 4096 &&
+         sm_count() >= 2;
+}
+
+// plan[0] = P, [1] = row chunks (64 rows each, rounded up to whole 128-row groups), [2] = partial-logit slots,
+// [3] = Hp (gate columns padded to 64), [4] = bf16 elements of each blocked dpre buffer (gt_gemm.cu layout)
+void milpool_tc_plan(int S, int L, int D, int Hd, long long* plan) {
+  int base[4];
+  milpool_plan(S, L, D, Hd, base);
+  const long long R = (long long)S * L;
+  plan[0] = base[0];
+  plan[1] = 2 * ((R + 127) / 128);
+  plan[2] = 2 * ((2 * Hd + TE_BN - 1) / TE_BN);
+  plan[3] = (2 * Hd + 63) / 64 * 64;
+  plan[4] = gstore_elems((int)R, 2 * Hd);
+}
+
+template <class Epi>
+static int mil_launch_te(const void* A, const void* B, int Ma, int Nb, int Kp, const typename Epi::Params& ep, cudaStream_t s) {
+  TeShape g{};
+  g.Ma = Ma; g.Nb = Nb; g.Kp = Kp;
+  g.m_tiles = (Ma + TE_BM - 1) / TE_BM;
+  g.n_blocks = (Nb + TE_BN - 1) / TE_BN;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tmA, A, Ma, Kp, Kp, TE_BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmB, B, Nb, Kp, Kp, TE_BN))) return rc;
+  auto kern = te_kernel<Epi, true>;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device() & 63];
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_BYTES) != cudaSuccess) return B2_ECUDA;
+    attr_done = true;
+  }
+  const long long total = (long long)g.m_tiles * g.n_blocks;
+  int grid = sm_count();
+  if (total < grid) grid = (int)total;
+  kern<<<grid, TE_THREADS, TE_SMEM_BYTES, s>>>(tmA, tmB, g, ep);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int milpool_tc_fwd(const float* x, long long sx_seq, long long sx_tok, const uint8_t* mask, long long smask, const float* V,
+                   const float* bV, const float* U, const float* bU, const float* w, const float* bw, int S, int L, int D,
+                   int Hd, float drop_p, unsigned long long seed, void* x3, void* w3, void* wt3, float* tg, float* spart,
+                   float* attn, float* opart, float* out, cudaStream_t s) {
+  MilParams p;
+  if (int rc = mil_fill(p, x, sx_seq, sx_tok, S, L, D, Hd, V, U, w, drop_p, seed)) return rc;
+  if (!milpool_tc_ok(p.R, L, D, Hd)) return B2_ENOSYS;
+  long long plan[5];
+  milpool_tc_plan(S, L, D, Hd, plan);
+  if (!bV || !bU || !bw || !x3 || !w3 || !wt3 || !tg || !spart || !attn || !out || (p.P > 1 && !opart)) return B2_EINVAL;
+  p.bV = bV; p.bU = bU; p.bw = bw; p.mask = mask; p.smask = smask;
+  p.tg = tg; p.spart = spart; p.attn = attn; p.opart = opart; p.out = out;
+  p.nut = (int)plan[2];
+  const int Hp = (int)plan[3];
+  mil_split_x_kernel<<<(unsigned)((p.R * (D / 4) + 255) / 256), 256, 0, s>>>(p, static_cast<__nv_bfloat16*>(x3));
+  mil_prep_w_kernel<<<(unsigned)(((long long)Hp * D + 255) / 256), 256, 0, s>>>(p, Hp, static_cast<__nv_bfloat16*>(w3),
+                                                                                static_cast<__nv_bfloat16*>(wt3));
+  MilGateEpiParams ep{bV, bU, w, tg, spart, Hd, p.R};
+  if (int rc = mil_launch_te<MilGateEpi>(x3, w3, (int)p.R, 2 * Hd, 3 * D, ep, s)) return rc;
+  const size_t smem = (size_t)L * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(mil_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mil_pool_fwd_kernel<<<dim3(p.P, S), 256, smem, s>>>(p);
+  if (p.P > 1) mil_pool_combine_kernel<<<(unsigned)(((long long)S * D + 255) / 256), 256, 0, s>>>(p);
+  return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+// one3: device floats with one3[2] == 1 (the scale slot gt_gemm reads). dW [2 Hd, D] comes back with INTERLEAVED rows
+// (2u = dV_u, 2u + 1 = dU_u); dsmall as in milpool_bwd.
+int milpool_tc_bwd(const float* x, long long sx_seq, long long sx_tok, const float* w, int S, int L, int D, int Hd,
+                   float drop_p, unsigned long long seed, const void* x3, const void* wt3, const float* tg, const float* attn,
+                   const float* dout, float* ds, float* dx, void* dpre3, void* ghi, void* glo, float* ad, float* fpart,
+                   float* dW, float* dsmall, const float* one3, cudaStream_t s) {
+  MilParams p;
+  if (int rc = mil_fill(p, x, sx_seq, sx_tok, S, L, D, Hd, w, w, w, drop_p, seed)) return rc;      // V / U are not read here
+  if (!milpool_tc_ok(p.R, L, D, Hd)) return B2_ENOSYS;
+  if (!x3 || !wt3 || !tg || !attn || !dout || !ds || !dx || !dpre3 || !ghi || !glo || !ad || !fpart || !dW || !dsmall || !one3)
+    return B2_EINVAL;
+  long long plan[5];
+  milpool_tc_plan(S, L, D, Hd, plan);
+  const int Hp = (int)plan[3], njb = 4 * ((2 * Hd + 255) / 256);
+  p.tg = const_cast<float*>(tg); p.attn = const_cast<float*>(attn); p.dout = dout;
+  p.ds = ds; p.dx = dx; p.fpart = fpart; p.dW = dW; p.dsmall = dsmall;
+  p.chunks = (int)plan[1];
+  p.Z = 0;                                           // mil_reduce: the bias / w sums only
+  mil_dA_kernel<<<(unsigned)((p.R + 7) / 8), 256, 0, s>>>(p);
+  mil_ds_kernel<<<S, 256, 0, s>>>(p);
+  mil_dpre_tc_kernel<<<p.chunks, 256, 0, s>>>(p, Hp, njb, static_cast<__nv_bfloat16*>(dpre3), static_cast<__nv_bfloat16*>(ghi),
+                                               static_cast<__nv_bfloat16*>(glo), ad);
+  MilDxEpiParams ep{ad, dout, dx, D, L};
+  if (int rc = mil_launch_te<MilDxEpi>(dpre3, wt3, (int)p.R, D, 3 * Hp, ep, s)) return rc;
+  if (cudaMemsetAsync(dW, 0, (size_t)2 * Hd * D * sizeof(float), s) != cudaSuccess) return B2_ECUDA;
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x3);
+  const long long ge = plan[4];
+  int rc = gt_gemm(ghi, ge, (int)p.R, 2 * Hd, xb + D, 3 * D, D, D, one3, 1.f, dW, D, s);           // hi x hi
+  if (!rc) rc = gt_gemm(ghi, ge, (int)p.R, 2 * Hd, xb, 3 * D, D, D, one3, 1.f, dW, D, s);          // hi x lo
+  if (!rc) rc = gt_gemm(glo, ge, (int)p.R, 2 * Hd, xb + D, 3 * D, D, D, one3, 1.f, dW, D, s);      // lo x hi
+  if (rc) return rc;
+  const long long n2 = 3 * Hd + 1;
+  mil_reduce_kernel<<<(unsigned)((n2 + 7) / 8), 256, 0, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
 }
 

@@ -2,23 +2,43 @@
 models/multi_instance_linear_probing.py::MultiInstanceLinearProbing._attention_pooling (reference :493-507) and
 ._hierarchical_attention_pooling (:509-536), SURVEY §8f #4. Same parameters (attention_V / attention_U / attention_w,
 attn_dropout) and argument meaning; the gate products, the masked softmax and the weighted sum run in csrc/milpool.cu
-(2-3 launches forward, 6 backward per level). ``install()`` rebinds the two methods on the reference class."""
+(fp32 FMA tiles, or tcgen05 products on split-precision operands for >= 1024 rows and D in {256, 512, 768}). ``install()`` rebinds the two methods on the reference class."""
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import call, i64, lib, stream_ptr
+from ._lib import call, i64, lib, stream_ptr, try_call
 
 
 def _plan(S: int, L: int, D: int, Hd: int):
     buf = (ctypes.c_int * 4)()
     call("milpool_plan", S, L, D, Hd, buf)
     return tuple(buf)
+
+
+def _tc_plan(S: int, L: int, D: int, Hd: int):
+    """(P, chunks, slots, Hp, g_elems) of the tensor-core variant, or None when the shape does not qualify
+    (R = S L >= 1024 rows, D in {256, 512, 768}; B200CLIP_MIL_TC=0 keeps the fp32 FMA tiles)."""
+    if os.environ.get("B200CLIP_MIL_TC", "1") == "0":
+        return None
+    buf = (ctypes.c_int64 * 5)()
+    return tuple(buf) if try_call("milpool_tc_plan", S, L, D, Hd, buf) else None
+
+
+_ONE3: dict = {}
+
+
+def _one3(dev):
+    t = _ONE3.get(dev)
+    if t is None:
+        t = _ONE3[dev] = torch.ones(4, dtype=torch.float32, device=dev)
+    return t
 
 
 class _GatedPool(torch.autograd.Function):
@@ -29,28 +49,60 @@ class _GatedPool(torch.autograd.Function):
         S, L, D = x.shape
         Hd = V.shape[0]
         dev = x.device
-        P, Z, chunks, nut = _plan(S, L, D, Hd)
         R = S * L
         Vc, Uc, wc = V.detach().contiguous(), U.detach().contiguous(), w.detach().reshape(Hd).contiguous()
+        bVc, bUc, bwc = bV.detach().contiguous(), bU.detach().contiguous(), bw.detach().reshape(1).contiguous()
+        tcp = _tc_plan(S, L, D, Hd)
         tg = torch.empty((R, 2 * Hd), dtype=torch.float32, device=dev)
-        spart = torch.empty((nut, R), dtype=torch.float32, device=dev)
         attn = torch.empty(R, dtype=torch.float32, device=dev)
-        opart = torch.empty((S, P, D), dtype=torch.float32, device=dev) if P > 1 else None
         out = torch.empty((S, D), dtype=torch.float32, device=dev)
-        call("milpool_fwd", x, i64(x.stride(0)), i64(x.stride(1)), valid, i64(valid.stride(0) if valid is not None else 0),
-             Vc, bV.detach().contiguous(), Uc, bU.detach().contiguous(), wc, bw.detach().reshape(1).contiguous(), S, L, D, Hd,
+        vs = i64(valid.stride(0) if valid is not None else 0)
+        if tcp is not None:
+            P, chunks, slots, Hp, g_elems = tcp
+            x3 = torch.empty((R, 3 * D), dtype=torch.bfloat16, device=dev)
+            w3 = torch.empty((2 * Hd, 3 * D), dtype=torch.bfloat16, device=dev)
+            wt3 = torch.empty((D, 3 * Hp), dtype=torch.bfloat16, device=dev)
+            spart = torch.empty((slots, R), dtype=torch.float32, device=dev)
+            opart = torch.empty((S, P, D), dtype=torch.float32, device=dev) if P > 1 else None
+            call("milpool_tc_fwd", x, i64(x.stride(0)), i64(x.stride(1)), valid, vs, Vc, bVc, Uc, bUc, wc, bwc, S, L, D, Hd,
+                 float(drop_p), i64(seed), x3, w3, wt3, tg, spart, attn, opart, out, stream_ptr(dev))
+            ctx.save_for_backward(x, wc, tg, attn, x3, wt3)
+            ctx.cfg = (float(drop_p), int(seed), tcp, tuple(w.shape), tuple(bw.shape), Hd)
+            return out
+        P, Z, chunks, nut = _plan(S, L, D, Hd)
+        spart = torch.empty((nut, R), dtype=torch.float32, device=dev)
+        opart = torch.empty((S, P, D), dtype=torch.float32, device=dev) if P > 1 else None
+        call("milpool_fwd", x, i64(x.stride(0)), i64(x.stride(1)), valid, vs, Vc, bVc, Uc, bUc, wc, bwc, S, L, D, Hd,
              float(drop_p), i64(seed), tg, spart, attn, opart, out, stream_ptr(dev))
         ctx.save_for_backward(x, Vc, Uc, wc, tg, attn)
-        ctx.cfg = (float(drop_p), int(seed), Z, chunks, tuple(w.shape), tuple(bw.shape))
+        ctx.cfg = (float(drop_p), int(seed), None, Z, chunks, tuple(w.shape), tuple(bw.shape))
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        dev = dout.device
+        dout = dout.float().contiguous()
+        if ctx.cfg[2] is not None:
+            x, wc, tg, attn, x3, wt3 = ctx.saved_tensors
+            drop_p, seed, (P, chunks, slots, Hp, g_elems), w_shape, bw_shape, Hd = ctx.cfg
+            S, L, D = x.shape
+            R = S * L
+            ds = torch.empty(R, dtype=torch.float32, device=dev)
+            ad = torch.empty(R, dtype=torch.float32, device=dev)
+            dx = torch.empty((S, L, D), dtype=torch.float32, device=dev)
+            dpre3 = torch.empty((R, 3 * Hp), dtype=torch.bfloat16, device=dev)
+            g2 = torch.empty((2, g_elems), dtype=torch.bfloat16, device=dev)
+            fpart = torch.empty((chunks, 3 * Hd + 4), dtype=torch.float32, device=dev)
+            dW = torch.empty((Hd, 2, D), dtype=torch.float32, device=dev)             # rows interleaved: [u, (V, U), :]
+            dsm = torch.empty(3 * Hd + 1, dtype=torch.float32, device=dev)
+            call("milpool_tc_bwd", x, i64(x.stride(0)), i64(x.stride(1)), wc, S, L, D, Hd, drop_p, i64(seed), x3, wt3, tg, attn,
+                 dout, ds, dx, dpre3, g2[0], g2[1], ad, fpart, dW, dsm, _one3(dev), stream_ptr(dev))
+            return (dx, None, dW[:, 0], dsm[:Hd], dW[:, 1], dsm[Hd:2 * Hd], dsm[2 * Hd:3 * Hd].view(w_shape),
+                    dsm[3 * Hd:].view(bw_shape), None, None)
         x, Vc, Uc, wc, tg, attn = ctx.saved_tensors
-        drop_p, seed, Z, chunks, w_shape, bw_shape = ctx.cfg
+        drop_p, seed, _, Z, chunks, w_shape, bw_shape = ctx.cfg
         S, L, D = x.shape
         Hd = Vc.shape[0]
-        dev = x.device
         R = S * L
         ds = torch.empty(R, dtype=torch.float32, device=dev)
         dx = torch.empty((S, L, D), dtype=torch.float32, device=dev)
@@ -60,7 +112,7 @@ class _GatedPool(torch.autograd.Function):
         dW = torch.empty((2 * Hd, D), dtype=torch.float32, device=dev)
         dsm = torch.empty(3 * Hd + 1, dtype=torch.float32, device=dev)
         call("milpool_bwd", x, i64(x.stride(0)), i64(x.stride(1)), Vc, Uc, wc, S, L, D, Hd, drop_p, i64(seed), tg, attn,
-             dout.float().contiguous(), ds, dx, dpre, wpart, fpart, dW, dsm, stream_ptr(dev))
+             dout, ds, dx, dpre, wpart, fpart, dW, dsm, stream_ptr(dev))
         return (dx, None, dW[:Hd], dsm[:Hd], dW[Hd:], dsm[Hd:2 * Hd], dsm[2 * Hd:3 * Hd].view(w_shape),
                 dsm[3 * Hd:].view(bw_shape), None, None)
 

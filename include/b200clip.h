@@ -626,6 +626,25 @@ int b200clip_milpool_bwd(const float* x, int64_t x_sseq, int64_t x_stok, const f
                          const float* dout, float* ds, float* dx, float* dpre, float* wpart, float* fpart, float* dW,
                          float* dsmall, void* stream);
 
+/* K11b The same pooling with its three products on tcgen05 (R = S L >= 1024 rows, D in {256, 512, 768}; B2_ENOSYS otherwise:
+ *      use K11). Split-precision operands: v = hi + lo in bf16, a b = lo_a hi_b + hi_a lo_b + hi_a hi_b as ONE bf16 product over
+ *      a three times longer K (A rows [lo | hi | hi], B rows [hi | lo | hi]), fp32 accumulation — 2^-17 relative per product.
+ *   milpool_tc_plan: plan[5] = {P, chunks, slots, Hp, g_elems}. Work buffers (R = S L, bf16 unless noted):
+ *     forward : x3 [R, 3 D], w3 [2 Hd, 3 D], wt3 [D, 3 Hp] (kept for the backward), tg [R, 2 Hd] fp32, spart [slots, R] fp32,
+ *               attn [R] fp32, opart [S, P, D] fp32 (P > 1), out [S, D] fp32.
+ *     backward: ds [R] fp32, dx [R, D] fp32 (written), dpre3 [R, 3 Hp], ghi / glo [g_elems] (128-byte aligned, K3b layout),
+ *               ad [R] fp32, fpart [chunks, 3 Hd + 4] fp32, dW [2 Hd, D] fp32 with INTERLEAVED rows (2u = dV_u, 2u + 1 = dU_u),
+ *               dsmall [3 Hd + 1] fp32 as in K11; one3: three device floats with one3[2] = 1. */
+int b200clip_milpool_tc_plan(int S, int L, int D, int Hd, int64_t* plan);
+int b200clip_milpool_tc_fwd(const float* x, int64_t x_sseq, int64_t x_stok, const uint8_t* valid, int64_t valid_sseq,
+                            const float* V, const float* bV, const float* U, const float* bU, const float* w, const float* bw,
+                            int S, int L, int D, int Hd, float drop_p, int64_t seed, void* x3, void* w3, void* wt3, float* tg,
+                            float* spart, float* attn, float* opart, float* out, void* stream);
+int b200clip_milpool_tc_bwd(const float* x, int64_t x_sseq, int64_t x_stok, const float* w, int S, int L, int D, int Hd,
+                            float drop_p, int64_t seed, const void* x3, const void* wt3, const float* tg, const float* attn,
+                            const float* dout, float* ds, float* dx, void* dpre3, void* ghi, void* glo, float* ad,
+                            float* fpart, float* dW, float* dsmall, const float* one3, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K9  Multi-view query pool: tail of EnhancedVideoAggregator.forward (models/video_aggregator.py:119-123, 128-158).
  *   x [B, N, D] fp32 (strides sb, sn), pos [>=N, D] or NULL, final LayerNorm (ln_w, ln_b, eps), attn_query [D],

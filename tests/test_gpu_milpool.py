@@ -1,6 +1,9 @@
 """Gated-attention MIL pooling (csrc/milpool.cu through deepcoro_clip_b200.mil_pooling) against the goldens generated from
 the reference's MultiInstanceLinearProbing._pool_instances (models/multi_instance_linear_probing.py:493-536) and against
-the float64 oracle at larger shapes. Tolerances: 2e-5 relative (forward), 5e-5 (gradients) — fp32 FMA products."""
+the float64 oracle at larger shapes. Tolerances: 2e-5 relative (forward), 5e-5 (gradients) for the fp32 FMA tiles (every
+golden, < 1024 rows); 1e-4 / 2e-4 for the tensor-core variant (>= 1024 rows, D in {256, 512, 768}), whose products carry
+16 mantissa bits per operand (hi + lo bf16, lo*lo dropped: ~4e-6 relative per pre-activation, amplified by |w| sqrt(hidden)
+on the way to the softmax — 2.4e-5 expected at hidden = 512 with unit-variance w; B200CLIP_MIL_TC=0 keeps fp32 products)."""
 from pathlib import Path
 
 import numpy as np
@@ -51,10 +54,12 @@ def test_golden(name):
 
 
 @pytest.mark.parametrize("shape,hd,masked", [((7, 300, 128), 64, True), ((300, 9, 512), 128, True), ((2, 3, 700, 256), 72, True),
-                                             ((3, 1, 48), 8, False)])
+                                             ((3, 1, 48), 8, False), ((5, 333, 768), 40, True), ((9, 130, 512), 512, False),
+                                             ((1, 1100, 256), 8, True)])
 def test_against_oracle(shape, hd, masked):
     """Ragged tiles (rows, hidden units and columns that are no multiples of the tile sizes), the split pooling pass
-    (L >= 256), many sequences, a single instance."""
+    (L >= 256), many sequences, a single instance; >= 1024 rows with D in {256, 512, 768} run the tensor-core variant
+    (split-precision operands), the others the fp32 FMA tiles."""
     from oracle import token_oracle as to
     rng = np.random.default_rng(5)
     D = shape[-1]
@@ -74,7 +79,9 @@ def test_against_oracle(shape, hd, masked):
         out, c = to.mil_gated_pool_forward(x, mask, V, bV, U, bU, w, bw, want_cache=True)
         want = to.mil_gated_pool_backward(go, c)
     want["out"] = out
-    _check(_module(V, bV, U, bU, w, bw), x, mask, go, want)
+    rows = int(np.prod(shape[:-1]))
+    tc = rows >= 1024 and D in (256, 512, 768)
+    _check(_module(V, bV, U, bU, w, bw), x, mask, go, want, *((1e-4, 2e-4) if tc else (2e-5, 5e-5)))
 
 
 def test_strided_rows_and_empty_sequence():
@@ -128,3 +135,33 @@ def test_requires_cuda_and_shapes():
         mod(torch.randn(2, 3, 64, device="cuda"), torch.ones(2, 4, dtype=torch.bool, device="cuda"))
     with pytest.raises(ValueError):
         GatedAttentionPooling(60, 16).cuda()(torch.randn(2, 3, 60, device="cuda"))
+
+
+def test_tensor_core_variant_matches_fma_tiles():
+    """Same module, same inputs through both variants (B200CLIP_MIL_TC=0 forces the fp32 FMA tiles)."""
+    import os
+    from deepcoro_clip_b200 import GatedAttentionPooling
+    torch.manual_seed(4)
+    mod = GatedAttentionPooling(512, 128, dropout=0.25).cuda().train()
+    x = torch.randn(6, 400, 512, device="cuda")
+    mask = torch.rand(6, 400, device="cuda") > 0.2
+    mask[:, 0] = True
+    go = torch.randn(6, 512, device="cuda")
+    res = {}
+    saved = os.environ.get("B200CLIP_MIL_TC")
+    try:
+        for mode in ("1", "0"):
+            os.environ["B200CLIP_MIL_TC"] = mode
+            mod.zero_grad(set_to_none=True)
+            xr = x.clone().requires_grad_(True)
+            torch.manual_seed(8)                      # same dropout seed
+            out = mod(xr, mask)
+            out.backward(go)
+            res[mode] = [out.detach(), xr.grad] + [p.grad.clone() for p in mod.parameters()]
+    finally:
+        if saved is None:
+            os.environ.pop("B200CLIP_MIL_TC", None)
+        else:
+            os.environ["B200CLIP_MIL_TC"] = saved
+    for a, b in list(zip(res["1"], res["0"]))[:-1]:       # the last one is d b_w = 0 up to rounding
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= 5e-5
