@@ -846,8 +846,10 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
         fl = 3 * 2.0 * S * V * Lm * D * 2 * Hd
         res["mil_gated_pool_fwd_bwd"] = {
             "ms": ms, "algorithmic_flops": fl, "TFLOPps": fl / ms / 1e9, "frac_fp32_fma": fl / ms / 1e9 / (148 * 128 * 2 * 1.965e-3),
-            "note": f"[{S}, {V}, {Lm}, {D}] fp32, hidden {Hd}: three [R x 512] x [512 x 256] products on fp32 FMA tiles (fp32 parity "
-                    "with the reference rules out one-pass bf16 / tf32 tensor-core products); fraction of 148 SMs x 128 FMA x 1.965 GHz"}
+            "note": f"[{S}, {V}, {Lm}, {D}] fp32, hidden {Hd}, two levels: three [R x 512] x [512 x 256] products on tcgen05 with "
+                    "split-precision operands (bf16 hi + lo, 3x the bf16 FLOP) + the streaming passes around them (operand split, "
+                    "gate epilogue, pooling, dpre); frac_fp32_fma = algorithmic rate over the CUDA-core FMA peak 148 x 128 x "
+                    "1.965 GHz, the ceiling of an fp32 implementation"}
         del xm, mil
     except Exception as e:
         res["mil_gated_pool_fwd_bwd"] = {"error": f"{type(e).__name__}: {e}"}

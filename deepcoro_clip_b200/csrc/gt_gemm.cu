@@ -39,16 +39,19 @@ struct GgParams {
   int ldd;
   int tiles, ksteps, njb;
   int d_off;             // first output column of this launch (Dp = its width: 256 or 512)
+  // up to three (G, X) source pairs summed into the same accumulator (split-precision products: hi*hi + hi*lo + lo*hi):
+  // source s reads the G block rows g_blk_off[s] + k and the X columns x_col_off[s] + d
+  int nsrc, g_blk_off[3], x_col_off[3];
 };
 
 struct GgSched {
   long long r, r1;
   int ksteps;
   __device__ __forceinline__ void init(const GgParams& p, int cid, int ncl) {
-    const long long total = (long long)p.tiles * p.ksteps;
+    ksteps = p.ksteps * p.nsrc;
+    const long long total = (long long)p.tiles * ksteps;
     r = total * cid / ncl;
     r1 = total * (cid + 1) / ncl;
-    ksteps = p.ksteps;
   }
   __device__ __forceinline__ bool next(int& tile, int& k0, int& k1) {
     if (r >= r1) return false;
@@ -115,10 +118,10 @@ gt_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           mbar_wait(&empty_bar[slot], phase ^ 1);
           uint8_t* st = smem + slot * GG_STAGE;
           if (leader) mbar_expect_tx(&full_bar[slot], 2 * (2 + 2 * nparts) * GG_BOX);
-          const int i0 = ks * GG_BK;
-          tma_load_2d_pair(st, &tmG, &full_bar[slot], 0, (ks * p.njb + (j0 >> 6)) * 64);      // two blocks, 16 KB
+          const int src = ks / p.ksteps, kk = ks - src * p.ksteps, i0 = kk * GG_BK;
+          tma_load_2d_pair(st, &tmG, &full_bar[slot], 0, ((p.g_blk_off[src] + kk) * p.njb + (j0 >> 6)) * 64);   // two blocks, 16 KB
           for (int n = 0; n < nparts; ++n) {
-            const int d0 = p.d_off + 256 * n + 128 * (int)rank;
+            const int d0 = p.x_col_off[src] + p.d_off + 256 * n + 128 * (int)rank;
             tma_load_2d_pair(st + (2 + 2 * n) * GG_BOX, &tmX, &full_bar[slot], d0, i0);
             tma_load_2d_pair(st + (3 + 2 * n) * GG_BOX, &tmX, &full_bar[slot], d0 + 64, i0);
           }
@@ -219,30 +222,40 @@ long long gstore_elems(int Nx, int Ny) {
   return 2ll * ((Nx + 127) / 128) * 4ll * ((Ny + 255) / 256) * 4096ll;
 }
 
-// dY[Ny, D] (fp32, pitch ldd, pre-zeroed or holding a partial sum) += dyn[2] / gnorm * G^T X ; G in the blocked layout above
-// (g_elems >= gstore_elems(Nx, Ny), 128-byte aligned), X [Nx, ldx] bf16 operand panel of width Dp in {256, 512, 768}.
-// B2_ENOSYS for other widths.
-int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
-            float gnorm, float* dY, int ldd, cudaStream_t stream) {
+// dY[Ny, D] (fp32, pitch ldd, pre-zeroed or holding a partial sum) += dyn[2] / gnorm * sum_s G_s^T X_s ; the G_s are block-row
+// ranges of ONE blocked buffer (g_elems_total elements, 128-byte aligned; source s starts at block row g_blk_off[s], each
+// holding 2 ceil(Nx / 128) block rows), the X_s column ranges [x_col_off[s], x_col_off[s] + Dp) of ONE bf16 matrix
+// [Nx, x_cols] with pitch ldx; Dp in {256, 512, 768}. B2_ENOSYS for other widths.
+int gt_gemm_multi(const void* G, long long g_elems_total, int nsrc, const int* g_blk_off, int Nx, int Ny, const void* X,
+                  int ldx, int x_cols, const int* x_col_off, int Dp, int D, const float* dyn, float gnorm, float* dY, int ldd,
+                  cudaStream_t stream) {
   if (Dp % 256 || Dp > 768 || sm_count() < 2) return B2_ENOSYS;
-  if (!G || !X || !dyn || !dY || Nx < 1 || Ny < 1 || D < 1 || D > Dp) return B2_EINVAL;
-  if (g_elems < gstore_elems(Nx, Ny)) return B2_ENOMEM;
+  if (!G || !X || !dyn || !dY || Nx < 1 || Ny < 1 || D < 1 || D > Dp || nsrc < 1 || nsrc > 3) return B2_EINVAL;
+  const long long per = gstore_elems(Nx, Ny);
+  GgParams p;
+  p.Nx = Nx; p.Ny = Ny; p.D = D; p.inv_gnorm = 1.f / (gnorm > 0.f ? gnorm : 1.f); p.dyn = dyn; p.dY = dY; p.ldd = ldd;
+  p.tiles = (Ny + 255) / 256;
+  p.ksteps = 2 * ((Nx + 127) / 128);      // every row block the storing kernel wrote (zeros past Nx)
+  p.njb = 4 * p.tiles;
+  p.nsrc = nsrc;
+  for (int s = 0; s < 3; ++s) {
+    p.g_blk_off[s] = s < nsrc ? g_blk_off[s] : 0;
+    p.x_col_off[s] = s < nsrc ? x_col_off[s] : 0;
+    if (s < nsrc && ((long long)(p.g_blk_off[s] + p.ksteps) * p.njb * 4096 > g_elems_total || p.x_col_off[s] + Dp > x_cols))
+      return B2_ENOMEM;
+  }
+  if (g_elems_total < per) return B2_ENOMEM;
   static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[current_device() & 63];
   if (!attr_done) {
     if (cudaFuncSetAttribute(gt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GG_SMEM) != cudaSuccess) return B2_ECUDA;
     attr_done = true;
   }
-  GgParams p;
-  p.Nx = Nx; p.Ny = Ny; p.D = D; p.inv_gnorm = 1.f / (gnorm > 0.f ? gnorm : 1.f); p.dyn = dyn; p.dY = dY; p.ldd = ldd;
-  p.tiles = (Ny + 255) / 256;
-  p.ksteps = 2 * ((Nx + 127) / 128);      // every row block the storing kernel wrote (zeros past Nx)
-  p.njb = 4 * p.tiles;
   CUtensorMap tmG, tmX;
   int rc;
-  if ((rc = make_tmap_bf16_rows64(&tmG, G, (uint64_t)(gstore_elems(Nx, Ny) / 64), 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, Dp, ldx, 64))) return rc;
-  const long long total = (long long)p.tiles * p.ksteps;
+  if ((rc = make_tmap_bf16_rows64(&tmG, G, (uint64_t)(g_elems_total / 64), 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmX, X, Nx, x_cols, ldx, 64))) return rc;
+  const long long total = (long long)p.tiles * p.ksteps * nsrc;
   const int clusters = sm_count() / 2;
   const int grid = 2 * (int)(total < clusters ? total : clusters);
   // the accumulator of a CTA is [128 x 512] fp32 (all of TMEM): wider outputs take a second sweep over G for the rest
@@ -253,6 +266,12 @@ int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int
     gt_gemm_kernel<<<grid, GG_THREADS, GG_SMEM, stream>>>(tmG, tmX, p);
   }
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
+}
+
+int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
+            float gnorm, float* dY, int ldd, cudaStream_t stream) {
+  const int zero = 0;
+  return gt_gemm_multi(G, g_elems, 1, &zero, Nx, Ny, X, ldx, Dp, &zero, Dp, D, dyn, gnorm, dY, ldd, stream);
 }
 
 }  // namespace b2host

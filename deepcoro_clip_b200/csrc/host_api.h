@@ -65,6 +65,9 @@ int logits_bwd_both(int mode, const void* X, const void* Y, int Nx, int Ny, int 
 long long gstore_elems(int Nx, int Ny);
 int gt_gemm(const void* G, long long g_elems, int Nx, int Ny, const void* X, int ldx, int Dp, int D, const float* dyn,
             float gnorm, float* dY, int ldd, cudaStream_t stream);
+int gt_gemm_multi(const void* G, long long g_elems_total, int nsrc, const int* g_blk_off, int Nx, int Ny, const void* X,
+                  int ldx, int x_cols, const int* x_col_off, int Dp, int D, const float* dyn, float gnorm, float* dY, int ldd,
+                  cudaStream_t stream);
 
 // attnpool_mma.cu: 16-bit inputs on mma.sync (heads <= 8, D % 128 == 0, D <= 1024, 16-byte aligned rows)
 bool attnpool_mma_ok(const void* x, int dtype, long long sb, long long sn, int D, int H);

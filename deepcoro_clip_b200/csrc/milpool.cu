@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(256) mil_reduce_kernel(MilParams p) {
 
 
 // =====================================================================================================================
-// Tensor-core variant (R >= 1024 rows, D in {256, 512, 768}): the three products on tcgen05 with split-precision operands.
+// Tensor-core variant (D in {256, 512, 768}): the three products on tcgen05 with split-precision operands.
 // A value v is carried as hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits); a product a b is formed as
 // lo_a hi_b + hi_a lo_b + hi_a hi_b by ONE bf16 product over a three times longer K: A operand rows [lo | hi | hi], B operand
 // rows [hi | lo | hi] (the bf16x3 scheme of the loss kernels, 2^-17 relative per product, fp32 accumulation in TMEM).
@@ -774,7 +774,7 @@ int milpool_bwd(const float* x, long long sx_seq, long long sx_tok, const float*
 
 // ---- tensor-core variant ---------------------------------------------------------------------------------------------
 bool milpool_tc_ok(long long R, int L, int D, int Hd) {
-  return milpool_ok(L, D, Hd) && (D == 256 || D == 512 || D == 768) && R >= 1024 && R < (1ll << 31) - 256 && Hd <= 4096 &&
+  return milpool_ok(L, D, Hd) && (D == 256 || D == 512 || D == 768) && R >= 1 && R < (1ll << 31) - 256 && Hd <= 4096 &&
          sm_count() >= 2;
 }
 
@@ -866,12 +866,12 @@ int milpool_tc_bwd(const float* x, long long sx_seq, long long sx_tok, const flo
   MilDxEpiParams ep{ad, dout, dx, D, L};
   if (int rc = mil_launch_te<MilDxEpi>(dpre3, wt3, (int)p.R, D, 3 * Hp, ep, s)) return rc;
   if (cudaMemsetAsync(dW, 0, (size_t)2 * Hd * D * sizeof(float), s) != cudaSuccess) return B2_ECUDA;
-  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x3);
+  // hi*hi + hi*lo + lo*hi in ONE pass (one accumulator, one drain): glo follows ghi in memory, x_hi / x_lo are panels of x3
   const long long ge = plan[4];
-  int rc = gt_gemm(ghi, ge, (int)p.R, 2 * Hd, xb + D, 3 * D, D, D, one3, 1.f, dW, D, s);           // hi x hi
-  if (!rc) rc = gt_gemm(ghi, ge, (int)p.R, 2 * Hd, xb, 3 * D, D, D, one3, 1.f, dW, D, s);          // hi x lo
-  if (!rc) rc = gt_gemm(glo, ge, (int)p.R, 2 * Hd, xb + D, 3 * D, D, D, one3, 1.f, dW, D, s);      // lo x hi
-  if (rc) return rc;
+  if (static_cast<__nv_bfloat16*>(glo) != static_cast<__nv_bfloat16*>(ghi) + ge) return B2_EINVAL;
+  const int nib = (int)plan[1];
+  const int gsrc[3] = {0, 0, nib}, xsrc[3] = {D, 0, D};
+  if (int rc = gt_gemm_multi(ghi, 2 * ge, 3, gsrc, (int)p.R, 2 * Hd, x3, 3 * D, 3 * D, xsrc, D, D, one3, 1.f, dW, D, s)) return rc;
   const long long n2 = 3 * Hd + 1;
   mil_reduce_kernel<<<(unsigned)((n2 + 7) / 8), 256, 0, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? B2_OK : B2_ECUDA;
