@@ -1,4 +1,8 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_milpool.py -q 2>&1 | tail -5
-timeout 600 python tools/gpu_check_milpool.py 2>&1 | grep -v Warning | tee gpurun_out/r02_milpool_check.log | tail -10
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"(te_kernel|gt_gemm_kernel|mil_split_x|mil_dpre_tc)" -c 7 -f -o gpurun_out/r02_milpool_tc python tools/gpu_milpool_step.py 128 1 > gpurun_out/ncu_mil.log 2>&1; tail -2 gpurun_out/ncu_mil.log
+set -u
+OUT=gpurun_out; TAG=r02c; mkdir -p $OUT
+timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > $OUT/${TAG}_pytest_gpu.log 2>&1
+echo "pytest rc=$? : $(tail -1 $OUT/${TAG}_pytest_gpu.log)"
+timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
+echo "smoke rc=$? : $(tail -1 $OUT/${TAG}_smoke.log)"
+timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+echo "bench rc=$? : $(cut -c1-200 $OUT/${TAG}_bench.json)"
