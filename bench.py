@@ -761,8 +761,17 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
     ms = t_ms(pool_f)
     res["attnpool_fwd"] = {"ms": ms, "algorithmic_bytes": bx, "GBps": bx / ms / 1e6, "frac_hbm": bx / ms / 1e6 / hbm}
 
+    # parameter gradients are reset like optimizer.zero_grad(set_to_none=True) does every step (otherwise autograd adds into
+    # the old .grad: one extra kernel per parameter that no training step pays)
+    pool_params, agg_params = list(pool.parameters()), list(agg.parameters())
+
+    def reset(params):
+        for prm in params:
+            prm.grad = None
+
     def pool_fb():
         x.grad = None
+        reset(pool_params)
         pool(x).backward(gy)
     ms = t_ms(pool_fb)
     res["attnpool_fwd_bwd"] = {"ms": ms, "algorithmic_bytes": 4 * bx, "GBps": 4 * bx / ms / 1e6,
@@ -820,12 +829,14 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
 
     def whole():
         q.grad = None; k.grad = None; x.grad = None; xa.grad = None
+        reset(pool_params); reset(agg_params)
         qo, ko = rope(q, k, 16, 14, 14)
         torch.autograd.backward((qo, ko), (gq, gk))
         pool(x).backward(gy)
         agg(xa).backward(ga)
     def agg_fb():
         xa.grad = None
+        reset(agg_params)
         agg(xa).backward(ga)
     ms = t_ms(agg_fb)
     res["aggregator_fwd_bwd"] = {"ms": ms, "note": "EnhancedVideoAggregator (depth 2, train mode): one library call per direction "
@@ -839,8 +850,11 @@ def tokens_leg(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
         xm = torch.randn(S, V, Lm, D, device=dev, requires_grad=True)
         gm = torch.randn(S, D, device=dev)
 
+        mil_params = list(mil.parameters())
+
         def mil_fb():
             xm.grad = None
+            reset(mil_params)
             mil(xm).backward(gm)
         ms = t_ms(mil_fb)
         fl = 3 * 2.0 * S * V * Lm * D * 2 * Hd
