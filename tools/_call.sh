@@ -1,8 +1,3 @@
-set -u
-OUT=gpurun_out; TAG=r02c; mkdir -p $OUT
-timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > $OUT/${TAG}_pytest_gpu.log 2>&1
-echo "pytest rc=$? : $(tail -1 $OUT/${TAG}_pytest_gpu.log)"
-timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
-echo "smoke rc=$? : $(tail -1 $OUT/${TAG}_smoke.log)"
-timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
-echo "bench rc=$? : $(cut -c1-200 $OUT/${TAG}_bench.json)"
+mkdir -p gpurun_out
+timeout 420 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_gt_gemm.py tests/test_gpu_milpool.py -x -q -p no:cacheprovider > gpurun_out/r02c_memcheck.log 2>&1
+echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|Error" gpurun_out/r02c_memcheck.log | head -10
