@@ -2,7 +2,7 @@
 models/multi_instance_linear_probing.py::MultiInstanceLinearProbing._attention_pooling (reference :493-507) and
 ._hierarchical_attention_pooling (:509-536), SURVEY §8f #4. Same parameters (attention_V / attention_U / attention_w,
 attn_dropout) and argument meaning; the gate products, the masked softmax and the weighted sum run in csrc/milpool.cu
-(fp32 FMA tiles, or tcgen05 products on split-precision operands for D in {256, 512, 768}). ``install()`` rebinds the two methods on the reference class."""
+(fp32 FMA tiles, or tcgen05 products on split-precision operands for >= 1024 rows and D in {256, 512, 768}). ``install()`` rebinds the two methods on the reference class."""
 from __future__ import annotations
 
 import ctypes
@@ -24,7 +24,7 @@ def _plan(S: int, L: int, D: int, Hd: int):
 
 def _tc_plan(S: int, L: int, D: int, Hd: int):
     """(P, chunks, slots, Hp, g_elems) of the tensor-core variant, or None when the shape does not qualify
-    (D in {256, 512, 768}; B200CLIP_MIL_TC=0 keeps the fp32 FMA tiles)."""
+    (R = S L >= 1024 rows, D in {256, 512, 768}; B200CLIP_MIL_TC=0 keeps the fp32 FMA tiles)."""
     if os.environ.get("B200CLIP_MIL_TC", "1") == "0":
         return None
     buf = (ctypes.c_int64 * 5)()

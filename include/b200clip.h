@@ -626,7 +626,7 @@ int b200clip_milpool_bwd(const float* x, int64_t x_sseq, int64_t x_stok, const f
                          const float* dout, float* ds, float* dx, float* dpre, float* wpart, float* fpart, float* dW,
                          float* dsmall, void* stream);
 
-/* K11b The same pooling with its three products on tcgen05 (D in {256, 512, 768}; B2_ENOSYS otherwise:
+/* K11b The same pooling with its three products on tcgen05 (R = S L >= 1024 rows, D in {256, 512, 768}; B2_ENOSYS otherwise:
  *      use K11). Split-precision operands: v = hi + lo in bf16, a b = lo_a hi_b + hi_a lo_b + hi_a hi_b as ONE bf16 product over
  *      a three times longer K (A rows [lo | hi | hi], B rows [hi | lo | hi]), fp32 accumulation — 2^-17 relative per product.
  *   milpool_tc_plan: plan[5] = {P, chunks, slots, Hp, g_elems}. Work buffers (R = S L, bf16 unless noted):

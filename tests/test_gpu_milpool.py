@@ -1,7 +1,7 @@
 """Gated-attention MIL pooling (csrc/milpool.cu through deepcoro_clip_b200.mil_pooling) against the goldens generated from
 the reference's MultiInstanceLinearProbing._pool_instances (models/multi_instance_linear_probing.py:493-536) and against
 the float64 oracle at larger shapes. Tolerances: 2e-5 relative (forward), 5e-5 (gradients) for the fp32 FMA tiles (every
-golden; D not in {256, 512, 768}); 1e-4 / 2e-4 for the tensor-core variant (D in {256, 512, 768}), whose products carry
+golden; < 1024 rows or D not in {256, 512, 768}); 1e-4 / 2e-4 for the tensor-core variant (>= 1024 rows, D in {256, 512, 768}), whose products carry
 16 mantissa bits per operand (hi + lo bf16, lo*lo dropped: ~4e-6 relative per pre-activation, amplified by |w| sqrt(hidden)
 on the way to the softmax — 2.4e-5 expected at hidden = 512 with unit-variance w; B200CLIP_MIL_TC=0 keeps fp32 products)."""
 from pathlib import Path
@@ -58,7 +58,7 @@ def test_golden(name):
                                              ((1, 1100, 256), 8, True)])
 def test_against_oracle(shape, hd, masked):
     """Ragged tiles (rows, hidden units and columns that are no multiples of the tile sizes), the split pooling pass
-    (L >= 256), many sequences, a single instance; D in {256, 512, 768} runs the tensor-core variant
+    (L >= 256), many sequences, a single instance; >= 1024 rows with D in {256, 512, 768} run the tensor-core variant
     (split-precision operands), the others the fp32 FMA tiles."""
     from oracle import token_oracle as to
     rng = np.random.default_rng(5)
@@ -80,7 +80,7 @@ def test_against_oracle(shape, hd, masked):
         want = to.mil_gated_pool_backward(go, c)
     want["out"] = out
     rows = int(np.prod(shape[:-1]))
-    tc = D in (256, 512, 768)
+    tc = rows >= 1024 and D in (256, 512, 768)
     _check(_module(V, bV, U, bU, w, bw), x, mask, go, want, *((1e-4, 2e-4) if tc else (2e-5, 5e-5)))
 
 

@@ -57,7 +57,7 @@ for shape, hd in (((6, 300, 256), 64), ((2, 3, 500, 128), 40), ((16, 5, 512), 12
     want = [od, xd.grad] + [p.grad for p in md.parameters()]
     errs = [rel(a, b) for a, b in zip(got[:-1], want[:-1])]      # the last one is d/d(bw) = 0 (softmax shift invariance)
     errs.append(abs(got[-1].item()) / max(1.0, want[-2].abs().max().item()))
-    good = max(errs) <= (1e-4 if shape[-1] in (256, 512, 768) else 2e-5)   # tensor-core variant: 16-bit-mantissa operands
+    good = max(errs) <= (1e-4 if (x.numel() // shape[-1] >= 1024 and shape[-1] in (256, 512, 768)) else 2e-5)   # tensor-core variant: 16-bit-mantissa operands
     ok &= good
     print(f"{shape} hidden {hd}: out {errs[0]:.1e} dx {errs[1]:.1e} worst param {max(errs[2:]):.1e}" + ("  ok" if good else "  MISMATCH " + str(errs)), flush=True)
 
