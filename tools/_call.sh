@@ -1,6 +1,6 @@
-set -u
-OUT=gpurun_out; TAG=r02c; mkdir -p $OUT
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531 tools/gpu_check_dist.py > $OUT/${TAG}_dist4.log 2>&1
-echo "dist check rc=$? : $(tail -1 $OUT/${TAG}_dist4.log | cut -c1-200)"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_n4.json 2> $OUT/${TAG}_bench_n4.err
-echo "bench4 rc=$? : $(cut -c1-250 $OUT/${TAG}_bench_n4.json)"
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_retrieval.py tests/test_gpu_z_topk_two_sweeps.py tests/test_gpu_kernels.py -q -p no:cacheprovider 2>&1 | tail -3
+timeout 600 python bench.py --steps 5 --warmup 3 --legs retrieval,topk10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_x.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_x.json'))
+for k in ('retrieval','topk10'):
+    e=d[k]; print(k, e.get('value'), {kk:vv for kk,vv in e.items() if 'ms' in kk or 'exact' in kk or 'parity' in kk})"
