@@ -99,13 +99,21 @@ struct RetrEpi {
     }
     if (kMaxK > 0) {
       // ---- top-k ----
+      // interior chunks (all 32 columns real — warp-uniform) skip the per-element bound test: the epilogue, not the tensor
+      // pipe, bounds this sweep, so every instruction of the branch-free part counts
       float cmax = -INFINITY;
+      if (nvalid >= 32) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, (e < nvalid) ? __uint_as_float(acc[e]) : -INFINITY);
+        for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, __uint_as_float(acc[e]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, (e < nvalid) ? __uint_as_float(acc[e]) : -INFINITY);
+      }
       if (cmax > st.thr && ctx.row_ok) {
         uint32_t m = 0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) m |= ((e < nvalid) && (__uint_as_float(acc[e]) > st.thr)) ? (1u << e) : 0u;
+        for (int e = 0; e < 32; ++e) m |= (__uint_as_float(acc[e]) > st.thr) ? (1u << e) : 0u;
+        if (nvalid < 32) m = nvalid <= 0 ? 0u : (m & ((1u << nvalid) - 1u));
         while (m) {
           const int e = __ffs(m) - 1;
           m &= m - 1;
