@@ -1,5 +1,9 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_retrieval.py -q -p no:cacheprovider 2>&1 | tail -2
-timeout 600 python bench.py --steps 5 --warmup 3 --legs topk10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_x.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_x.json'))
-e=d['topk10']; print('topk10', e.get('value'), {kk:vv for kk,vv in e.items() if 'ms' in kk or 'parity' in kk})"
+set -u
+OUT=gpurun_out; TAG=r02d; mkdir -p $OUT
+timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > $OUT/${TAG}_pytest_gpu.log 2>&1
+echo "pytest rc=$? : $(tail -1 $OUT/${TAG}_pytest_gpu.log)"
+timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
+echo "smoke rc=$? : $(tail -1 $OUT/${TAG}_smoke.log)"
+timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+echo "bench rc=$? : $(cut -c1-200 $OUT/${TAG}_bench.json)"
+timeout 200 python tools/gpu_bench_topk.py > $OUT/${TAG}_topk.log 2>&1; tail -3 $OUT/${TAG}_topk.log | cut -c1-400
