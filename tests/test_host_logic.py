@@ -392,3 +392,32 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"] == "clip32k"
+
+
+def test_plan_entry_points_agree_with_the_host_formulas():
+    """Host-only entry points of the C ABI (no launch, no device needed): buffer sizes the Python side computes on its own must
+    equal what the library expects (include/b200clip.h K3b, K11, K11b, the aggregator step)."""
+    import ctypes
+    from deepcoro_clip_b200 import _lib, ops
+    lib = _lib.lib()
+    out = ctypes.c_int64(0)
+    for nx, ny in ((1, 1), (128, 256), (129, 257), (1500, 1500), (32768, 32768), (1024, 8192)):
+        assert lib.b200clip_gstore_elems(nx, ny, ctypes.byref(out)) == 0
+        assert out.value == ops.gstore_elems(nx, ny)
+        assert out.value % 4096 == 0 and out.value >= nx * ny
+    assert lib.b200clip_gstore_elems(0, 5, ctypes.byref(out)) != 0
+    sizes = (ctypes.c_int64 * 3)()
+    B, N, D, H, F = 8, 4, 512, 4, 2048
+    assert lib.b200clip_aggregator_sizes(B, N, D, H, F, sizes) == 0
+    al = lambda n: (n + 63) // 64 * 64
+    R = B * N
+    assert sizes[0] == 6 * al(R * D) + 2 * al(R) + al(3 * R * D) + al(B * H * N * N) + 2 * al(R * F)
+    assert sizes[1] == 4 * al(R * D) + al(R * F) + al(3 * R * D)
+    assert sizes[2] == 4 * D * D + 2 * F * D + 9 * D + F
+    assert lib.b200clip_aggregator_sizes(B, 17, D, H, F, sizes) != 0          # more than 16 views: not a fused shape
+    plan = (ctypes.c_int * 4)()
+    assert lib.b200clip_milpool_plan(32, 1568, 512, 128, plan) == 0
+    P, Z, chunks, nut = tuple(plan)
+    assert 1 <= P <= 16 and Z >= 1 and chunks == (32 * 1568 + 63) // 64 and nut == 2
+    assert lib.b200clip_milpool_plan(4, 8, 60, 128, plan) != 0                # D % 16 != 0
+    assert lib.b200clip_milpool_ok(8, 512, 128) == 1 and lib.b200clip_milpool_ok(8, 512, 12) == 0
